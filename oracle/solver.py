@@ -1,0 +1,109 @@
+"""Oracle: SR / MinSR linear solve (test infrastructure).
+
+Restates
+  quantax/optimizer/sr.py:74-88    (Obar = (O - mean O) * sqrt(rw/Ns); _Omean),
+  quantax/optimizer/sr.py:180-195  (Ebar, energy, VarE),
+  quantax/optimizer/solver.py:12-21,94-101 (soft pseudo-inverse of eigenvalues),
+  quantax/optimizer/solver.py:128-149 (minnorm_pinv_eig, MinSR),
+  quantax/optimizer/solver.py:152-164 (lstsq_pinv_eig, SR),
+  quantax/optimizer/solver.py:167-201 (auto_pinv_eig),
+  quantax/optimizer/solver.py:262-294 (minsr_pinv_eig),
+  quantax/state/variational.py:558-579 (update: theta <- theta - step, skip if non-finite).
+``eigh`` is LAPACK syevd here and cuSOLVER/XLA in the reference (third party, unpinned):
+eigenvectors are only defined up to sign / rotation inside degenerate subspaces, so parity
+is asserted on T, on the spectrum and on the final step x, never on U itself.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def get_rtol(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float64:
+        return 1e-12
+    if dtype == np.float32:
+        return 1e-6
+    raise ValueError(dtype)
+
+
+def obar(Omat, rw):
+    ns = Omat.shape[0]
+    omean = np.mean(Omat * rw[:, None], axis=0)
+    factor = np.sqrt(rw / ns)[:, None]
+    return (Omat - np.mean(Omat, axis=0, keepdims=True)) * factor, omean
+
+
+def ebar(Eloc, rw):
+    ns = Eloc.shape[0]
+    emean = np.mean(Eloc * rw)
+    var = np.mean(np.abs(Eloc - emean) ** 2 * rw)
+    eb = (Eloc - np.mean(Eloc)) * np.sqrt(rw / ns)
+    return eb, float(np.real(emean)), float(np.real(var))
+
+
+def eigs_inv(vals, rtol=None, atol=0.0):
+    a = np.abs(vals)
+    if rtol is None:
+        rtol = get_rtol(a.dtype)
+    with np.errstate(divide="ignore", over="ignore", invalid="ignore"):
+        inv_factor = 1 + ((rtol * np.max(a) + atol) / a) ** 6
+        inv = 1 / (vals * inv_factor)
+    return np.where(a > 0.0, inv, 0.0)
+
+
+def _sum_without_noise(inputs, tol_snr):
+    x = np.sum(inputs, axis=0)
+    if tol_snr > 1e-6:
+        mean = x / inputs.shape[0]
+        var = np.sqrt(np.mean(np.abs(inputs - mean[None, :]) ** 2, axis=0) / inputs.shape[0])
+        snr = np.abs(mean) / var
+        x = x / (1 + (tol_snr / snr) ** 6)
+    return x
+
+
+def minnorm_pinv_eig(A, b, rtol=None, atol=0.0, tol_snr=0.0, return_parts=False):
+    T = A @ A.conj().T
+    vals, U = np.linalg.eigh(T)
+    inv = eigs_inv(vals, rtol, atol)
+    rho = _sum_without_noise(U.conj() * b[:, None], tol_snr)
+    x = A.conj().T @ (U @ (inv * rho))
+    if return_parts:
+        return x, T, vals
+    return x
+
+
+def lstsq_pinv_eig(A, b, rtol=None, atol=0.0, tol_snr=0.0):
+    S = A.conj().T @ A
+    vals, V = np.linalg.eigh(S)
+    inv = eigs_inv(vals, rtol, atol)
+    rho_sk = (A.conj() @ V.conj()) * b[:, None]
+    rho = _sum_without_noise(rho_sk, tol_snr)
+    return V @ (inv * rho)
+
+
+def auto_pinv_eig(A, b, rtol=None, atol=0.0, tol_snr=0.0):
+    if A.shape[0] < A.shape[1]:
+        return minnorm_pinv_eig(A, b, rtol, atol, tol_snr)
+    return lstsq_pinv_eig(A, b, rtol, atol, tol_snr)
+
+
+def minsr_pinv_eig(T, b, rtol=None, atol=0.0, tol_snr=0.0):
+    vals, U = np.linalg.eigh(T)
+    inv = eigs_inv(vals, rtol, atol)
+    rho = _sum_without_noise(U.conj() * b[:, None], tol_snr)
+    return U @ (inv * rho)
+
+
+def sr_step(Omat, Eloc, rw, rtol=None, atol=0.0):
+    """optimizer/sr.py:115-123 for VS_TYPE.real_or_holomorphic, imag_time=True."""
+    eb, energy, var = ebar(Eloc, rw)
+    ob, _ = obar(Omat, rw)
+    return auto_pinv_eig(ob, eb, rtol, atol), energy, var
+
+
+def update_params(params, step):
+    """variational.py:570-579."""
+    if not np.all(np.isfinite(step)):
+        return params
+    return params + (-step.real).astype(params.dtype)
