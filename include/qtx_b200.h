@@ -1,0 +1,231 @@
+/*
+ * qtx_b200.h -- C ABI of libqtx_b200.so: the B200 (sm_100a) kernels behind the quantax
+ * VMC hot path (Metropolis sweep -> Operator.Oloc -> Variational.jacobian -> SR/MinSR solve).
+ *
+ * The reference (ChenAo-Phys/quantax v0.2.1) is pure JAX and has no FFI boundary on this
+ * path; each entry point below replaces the body of one reference Python function (cited as
+ * file:line under /root/reference) and is what an XLA-FFI / ctypes binding binds
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function only enqueues work on `stream` (a cudaStream_t); no implicit
+ *     synchronisation and no allocation: scratch memory is passed in by the caller after a
+ *     *_workspace_size query.  Exceptions are documented per function (eigh handle setup).
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`; arrays are dense
+ *     row-major.
+ *   - return value: 0 on success, negative qtx_status otherwise; qtx_last_error() returns a
+ *     thread-local message.
+ *   - dtype arguments take QTX_F32 / QTX_F64.  `model_dtype` is the parameter / internal
+ *     arithmetic type of the network (reference default float32), amplitudes psi travel as
+ *     float64 (mult, expo) pairs with psi = mult * exp(expo): LogArray(sign, logabs) for
+ *     RBM_Dense, ScaleArray(significand, exponent) for ResConv
+ *     (quantax/utils/big_array.py:154,407; cast at quantax/state/variational.py:266).
+ *   - spins are int8 +-1, [ns, N] (quantax/sampler/samples.py:49).
+ */
+#ifndef QTX_B200_H
+#define QTX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* qtx_stream_t; /* cudaStream_t */
+
+enum qtx_status {
+  QTX_OK = 0,
+  QTX_ERR_INVALID = -1,     /* bad argument */
+  QTX_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+  QTX_ERR_UNSUPPORTED = -3, /* size or mode outside the implemented range */
+  QTX_ERR_SOLVER = -4       /* cuSOLVER failure or non-convergence */
+};
+
+enum qtx_dtype { QTX_F32 = 0, QTX_F64 = 1 };
+
+/* proposal kinds of the Metropolis sweep */
+enum qtx_proposal {
+  QTX_LOCAL_FLIP = 0,   /* quantax/sampler/common_samplers.py:14-33  */
+  QTX_SPIN_EXCHANGE = 1 /* quantax/sampler/common_samplers.py:58-162 (a.k.a. NeighborExchange) */
+};
+
+const char* qtx_last_error(void);
+int qtx_abi_version(void);
+/* number of kernels launched by this library on the calling thread since the last reset */
+int64_t qtx_launch_count(void);
+void qtx_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Hamiltonian term table (host -> device), replaces Operator.jax_op_list
+ * (quantax/operator/operator.py:219-236).  A term is a coefficient and up to 4 (site, op)
+ * pairs applied right-to-left (operator.py:107); op codes: 0 none, 1 'z', 2 'x', 3 '+', 4 '-',
+ * 5 'I'.  Terms are stored in op-list order; `nflips[t]` is the number of x/+/- factors.
+ * ------------------------------------------------------------------------------------------ */
+#define QTX_MAX_TERM_SITES 4
+enum qtx_opcode { QTX_OP_NONE = 0, QTX_OP_Z = 1, QTX_OP_X = 2, QTX_OP_P = 3, QTX_OP_M = 4, QTX_OP_I = 5 };
+
+/* ------------------------------------------------------------------------------------------
+ * RBM_Dense: psi(s) = prod_i cosh(theta_i), theta = W s + b
+ *   W [M, N] row-major (eqx Linear.weight), b [M]; flat parameter order [W.ravel(), b]
+ *   (quantax/model/shallow_nets.py:35-126).
+ * ------------------------------------------------------------------------------------------ */
+
+/* theta = W s + b and logabs = sum_i log|cosh theta_i| (sign is always +1 for real parameters).
+ * Replaces SingleDense.init_internal (shallow_nets.py:81-85) and the direct forward
+ * Variational.__call__ (quantax/state/variational.py:325-347) for RBM_Dense.
+ * theta_out [ns, M] in model dtype (nullable); logabs_out float64 [ns] (nullable). */
+int qtx_rbm_forward(int model_dtype, const void* W, const void* b, int N, int M,
+                    const int8_t* spins, int64_t ns, void* theta_out, double* logabs_out,
+                    qtx_stream_t stream);
+
+/* Scratch bytes needed by qtx_rbm_sweep / qtx_rbm_oloc (transposed copy of W). */
+size_t qtx_rbm_workspace_size(int model_dtype, int N, int M);
+
+/* Whole Metropolis sweep (all `nsweeps` steps, all chains) in ONE launch.
+ * Replaces Metropolis._partial_sweep / _single_sweep / _update
+ * (quantax/sampler/metropolis.py:246-322) with RefModel local updates
+ * (shallow_nets.py:87-108) for LocalFlip / SpinExchange proposals.
+ *
+ *   spins       [ns, N] in/out: chain state
+ *   nbr_table   [N, max_nb] int32, -1 padded (common_samplers.py:36-55); exchange only
+ *   hop         +1 / -1 : the hopping particle (common_samplers.py:138-142); exchange only
+ *   reweight    exponent n of the sampled |psi|^n (metropolis.py:300)
+ *   Randoms: if inj_u != NULL the proposals are INJECTED (parity mode): inj_pos [nsweeps, ns]
+ *   is the flipped site (LocalFlip) or the chosen particle site (exchange), inj_slot
+ *   [nsweeps, ns] the neighbour-table column (exchange), inj_u [nsweeps, ns] the uniforms of
+ *   metropolis.py:303.  Otherwise Philox4x32-10 with key=seed, counter=(chain0+chain,
+ *   step0+t) is used in-kernel.
+ *   Outputs: logabs_out [ns] = direct-forward amplitude of the final chains
+ *   (metropolis.py:201-213), logabs_chain_out [ns] (nullable) = the locally updated value
+ *   (for the drift check), naccept_out int32 [ns] (nullable), accept_log uint8
+ *   [nsweeps, ns] (nullable). */
+int qtx_rbm_sweep(int model_dtype, const void* W, const void* b, int N, int M,
+                  int8_t* spins, int64_t ns, int nsweeps, int kind,
+                  const int32_t* nbr_table, int max_nb, int hop, double reweight,
+                  const int32_t* inj_pos, const int32_t* inj_slot, const double* inj_u,
+                  uint64_t seed, uint64_t step0, uint64_t chain0,
+                  double* logabs_out, double* logabs_chain_out, int32_t* naccept_out,
+                  uint8_t* accept_log, void* workspace, size_t workspace_bytes,
+                  qtx_stream_t stream);
+
+/* Local energies for a spin Hamiltonian, fused: enumerate connected configurations, evaluate
+ * psi(s')/psi(s) by local updates from theta(s), reduce.  Replaces Operator.Oloc
+ * (quantax/operator/operator.py:510-562) incl. _apply_diag/_apply_off_diag/_get_conn/
+ * _get_Olocx (operator.py:81-184) and Variational.ref_forward (variational.py:301-323).
+ * Term table (device): coef float64 [nterms], sites uint16 [nterms, 4], ops uint8 [nterms, 4].
+ * eloc_out float64 [ns]; nconn_out int32 [ns] (nullable) = number of valid connections. */
+int qtx_rbm_oloc(int model_dtype, const void* W, const void* b, int N, int M,
+                 const int8_t* spins, int64_t ns,
+                 const double* term_coef, const uint16_t* term_sites, const uint8_t* term_ops,
+                 int nterms, double* eloc_out, int32_t* nconn_out,
+                 void* workspace, size_t workspace_bytes, qtx_stream_t stream);
+
+/* psi of connected configurations given their parent sample (Variational.ref_forward,
+ * variational.py:387-422 / 301-311): theta [ns, M] model dtype, s_old [ns, N],
+ * s_new [nconn, N], segment int32 [nconn] (-1 = padding -> output 0), nflips as in the
+ * reference (indices found by comparing s_new with s_old[segment], missing ones padded with
+ * site 0, shallow_nets.py:101).  logabs_out float64 [nconn]. */
+int qtx_rbm_ref_forward(int model_dtype, const void* W, int N, int M, const void* theta,
+                        const int8_t* s_old, int64_t ns, const int8_t* s_new,
+                        const int32_t* segment, int64_t nconn, int nflips,
+                        double* logabs_out, qtx_stream_t stream);
+
+/* Per-sample log-derivatives O[s, k] = d log psi(s) / d theta_k (Variational.jacobian,
+ * variational.py:424-511): O[s, i*N+j] = tanh(theta_i) s_j, O[s, M*N+i] = tanh(theta_i),
+ * computed in model dtype and cast to out_dtype (variational.py:491).
+ * If col_mean (float64 [M*N+M]) is given the row is centred, and if row_scale (float64 [ns])
+ * is given it is scaled: out = (O - mean) * scale, i.e. Obar of quantax/optimizer/sr.py:74-88
+ * written in a single pass.  out [ns, ld] with ld >= M*N+M elements per row. */
+int qtx_rbm_jacobian(int model_dtype, const void* W, const void* b, int N, int M,
+                     const int8_t* spins, int64_t ns, int out_dtype, void* out, int64_t ld,
+                     const double* col_mean, const double* row_scale, qtx_stream_t stream);
+
+/* Column mean of the RBM Jacobian without materialising it (mean over samples of
+ * tanh(theta_i) s_j, optionally weighted by w[s]): the `jnp.mean(Omat, axis=0)` of
+ * sr.py:77,86.  mean_out float64 [M*N+M]; scratch via qtx_rbm_colmean_workspace_size. */
+size_t qtx_rbm_colmean_workspace_size(int model_dtype, int N, int M, int64_t ns);
+int qtx_rbm_jacobian_colmean(int model_dtype, const void* W, const void* b, int N, int M,
+                             const int8_t* spins, int64_t ns, const double* weight,
+                             double* mean_out, void* workspace, size_t workspace_bytes,
+                             qtx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Connected-configuration enumeration for generic models (bit-exact mirror of
+ * _apply_off_diag + _get_conn, operator.py:96-165).  Terms with `nflips_sel` flips only.
+ *   count:  nonnan_out / valid_out int32 [ns]  (valid = not NaN and |H| > 1e-8)
+ *   fill:   offsets int64 [ns] = exclusive scan of valid counts (per device range);
+ *           writes segment int32, conn_idx int32, H float64 [conn_size] and (nullable)
+ *           s_conn int8 [conn_size, N]; entries past the total are padding
+ *           (segment -1, conn_idx -1, H 0, s_conn = last raw candidate of the last sample).
+ * ------------------------------------------------------------------------------------------ */
+int qtx_conn_count(const int8_t* spins, int64_t ns, int N, const double* term_coef,
+                   const uint16_t* term_sites, const uint8_t* term_ops, int nterms,
+                   int nflips_sel, int32_t* nonnan_out, int32_t* valid_out, qtx_stream_t stream);
+int qtx_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, int64_t* total_out,
+                           qtx_stream_t stream);
+int qtx_conn_fill(const int8_t* spins, int64_t ns, int N, const double* term_coef,
+                  const uint16_t* term_sites, const uint8_t* term_ops, int nterms,
+                  int nflips_sel, const int64_t* offsets, const int64_t* total, int64_t conn_size,
+                  int32_t* segment_out,
+                  int32_t* conn_idx_out, double* H_out, int8_t* s_conn_out, qtx_stream_t stream);
+/* diagonal part sum_t J_t prod_k (s_k / 2) over all-diagonal terms (operator.py:81-93) */
+int qtx_apply_diag(const int8_t* spins, int64_t ns, int N, const double* term_coef,
+                   const uint16_t* term_sites, const uint8_t* term_ops, int nterms,
+                   double* diag_out, qtx_stream_t stream);
+/* Eloc[seg] += H * (mult'/mult[seg]) * exp(expo' - expo[seg])  (_get_Olocx, operator.py:168-184) */
+int qtx_oloc_reduce(const int32_t* segment, const double* H, const double* mult_conn,
+                    const double* expo_conn, int64_t nconn, const double* mult, const double* expo,
+                    int64_t ns, double* eloc_inout, qtx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SR / MinSR dense algebra (quantax/optimizer/sr.py:74-123, solver.py:94-201)
+ * ------------------------------------------------------------------------------------------ */
+/* mean_out[k] = (1/ns) sum_s w[s] A[s,k]  (w nullable = 1);  A [ns, ld] of dtype */
+int qtx_colmean(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, const double* weight,
+                double* mean_out, qtx_stream_t stream);
+/* A[s,k] = (A[s,k] - mean[k]) * scale[s] in place (_Omat_to_Obar, sr.py:74-77) */
+int qtx_center_scale(int dtype, void* A, int64_t ns, int64_t np, int64_t ld, const double* mean,
+                     const double* scale, qtx_stream_t stream);
+/* Ebar, energy, VarE from local energies (SR.get_Ebar, sr.py:180-195); stats_out float64 [2]
+ * = {energy, VarE} on device. */
+int qtx_ebar(const double* eloc, const double* rw, int64_t ns, double* ebar_out, double* stats_out,
+             qtx_stream_t stream);
+
+/* T = A A^T  (solver.py:139), A [ns, ld] (np used columns), T_out float64/float32 [ns, ns]
+ * (both triangles written).  The contraction runs on tcgen05 tensor cores fed by TMA:
+ *   QTX_F64 input: error-free int8 slicing (Ozaki scheme) with `nslices` 7-bit slices
+ *   (0 = default for the dtype), exact int32 accumulation, float64 recombination;
+ *   QTX_F32 input: same with fewer slices.
+ * `T_accum != 0` adds into T_out (used to sum column shards). */
+size_t qtx_gram_workspace_size(int dtype, int64_t ns, int64_t np, int nslices);
+int qtx_gram(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int nslices,
+             double* T_out, int T_accum, void* workspace, size_t workspace_bytes,
+             qtx_stream_t stream);
+
+/* (lambda, U) = eigh(T); y = U (lambda^+ o (U^T b)) with the soft pseudo-inverse
+ * lambda^+ = 1 / (lambda (1 + ((rtol max|lambda| + atol)/|lambda|)^6)), 0 where lambda == 0
+ * (solver.py:94-101,142-146; minsr_pinv_eig solver.py:262-294).  rtol < 0 selects the dtype
+ * default (1e-12).  T [n, n] float64 is overwritten by U (column-major eigenvectors =
+ * row-major U^T); evals_out float64 [n] (nullable); y_out float64 [n].
+ * info_out int32 [1] device (0 = converged).  eigh is cuSOLVER syevd (library call). */
+size_t qtx_pinv_eig_workspace_size(int64_t n);
+int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double rtol, double atol,
+                       double* evals_out, double* y_out, int32_t* info_out, void* workspace,
+                       size_t workspace_bytes, qtx_stream_t stream);
+
+/* x[k] = sum_s A[s,k] y[s]  (the final A^dagger y of solver.py:146); x_out float64 [np] */
+int qtx_matvec_t(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, const double* y,
+                 double* x_out, int accumulate, qtx_stream_t stream);
+/* v[s] = sum_k A[s,k] x[k]; v_out float64 [ns] */
+int qtx_matvec(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, const double* x,
+               double* v_out, qtx_stream_t stream);
+/* params <- params - step (Variational.update, variational.py:558-579); the update is skipped
+ * when any step entry is non-finite; flag_out int32 [1] = 1 if applied. */
+int qtx_apply_update(int model_dtype, void* params, const double* step, double lr, int64_t np,
+                     int32_t* flag_out, qtx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QTX_B200_H */

@@ -1,0 +1,106 @@
+"""ctypes binding of libqtx_b200.so (the C ABI declared in include/qtx_b200.h).
+
+There is no CPU fallback: if the shared library is missing every compute entry point of the
+package raises.  PyTorch is used only as the owner of device memory and of the CUDA stream;
+tensors cross the boundary as raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libqtx_b200.so")
+
+QTX_F32, QTX_F64 = 0, 1
+QTX_LOCAL_FLIP, QTX_SPIN_EXCHANGE = 0, 1
+
+_vp, _i32, _i64, _u64, _f64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/qtx_b200.h
+SIGNATURES = {
+    "qtx_last_error": (C.c_char_p, []),
+    "qtx_abi_version": (_i32, []),
+    "qtx_launch_count": (_i64, []),
+    "qtx_launch_count_reset": (None, []),
+    "qtx_rbm_forward": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "qtx_rbm_workspace_size": (_sz, [_i32, _i32, _i32]),
+    "qtx_rbm_sweep": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _f64,
+                             _vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_rbm_oloc": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_rbm_ref_forward": (_i32, [_i32, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "qtx_rbm_jacobian": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "qtx_rbm_colmean_workspace_size": (_sz, [_i32, _i32, _i32, _i64]),
+    "qtx_rbm_jacobian_colmean": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_conn_count": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "qtx_exclusive_scan_i32": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "qtx_conn_fill": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "qtx_apply_diag": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "qtx_oloc_reduce": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "qtx_colmean": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "qtx_center_scale": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "qtx_ebar": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "qtx_gram_workspace_size": (_sz, [_i32, _i64, _i64, _i32]),
+    "qtx_gram": (_i32, [_i32, _vp, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "qtx_pinv_eig_workspace_size": (_sz, [_i64]),
+    "qtx_pinv_eig_solve": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_matvec_t": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
+    "qtx_matvec": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "qtx_apply_update": (_i32, [_i32, _vp, _vp, _f64, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+class QtxError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C quantax_b200/csrc`).  quantax_b200 has no CPU fallback."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise QtxError with the library message on failure."""
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise QtxError(f"{name} failed ({rc}): {L.qtx_last_error().decode()}")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise QtxError("quantax_b200 kernels need CUDA tensors; there is no CPU path")
+    if not t.is_contiguous():
+        raise QtxError("non-contiguous tensor passed to the C ABI")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return QTX_F32
+    if dt == torch.float64:
+        return QTX_F64
+    raise QtxError(f"unsupported dtype {dt}")

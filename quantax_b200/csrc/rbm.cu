@@ -1,0 +1,841 @@
+// RBM_Dense kernels: direct forward, persistent Metropolis sweep, fused local energies,
+// ref_forward, Jacobian (optionally centred/scaled) and its column mean.
+//
+// Design (B200): one warp owns one Markov chain / sample.  The M hidden pre-activations
+// theta live in registers (hidden unit i = r*32 + lane), the transposed weight matrix W^T
+// [N, M] is staged once per CTA in shared memory when it fits (160 KB for the 10x10, alpha=4
+// benchmark), so a proposal costs nflips conflict-free shared-memory rows, M/32 log-cosh
+// evaluations per lane and one shuffle reduction -- no HBM traffic inside the sweep.
+#include "common.cuh"
+
+namespace qtx {
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void transpose_w_kernel(const T* __restrict__ W, T* __restrict__ Wt, int N, int M) {
+  __shared__ T tile[32][33];
+  int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int i = i0 + r, j = j0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < M && j < N) ? W[(size_t)i * N + j] : T(0);
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int j = j0 + r, i = i0 + threadIdx.x;
+    if (i < M && j < N) Wt[(size_t)j * M + i] = tile[threadIdx.x][r];
+  }
+}
+
+template <typename T>
+static int transpose_w(const void* W, void* Wt, int N, int M, cudaStream_t st) {
+  dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
+  transpose_w_kernel<T><<<grid, block, 0, st>>>((const T*)W, (T*)Wt, N, M);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+// theta = W s + b (sum over sites first, bias last, as eqx.nn.Linear does), warp per sample
+template <typename T>
+__global__ void rbm_forward_kernel(const T* __restrict__ W, const T* __restrict__ b, int N, int M,
+                                   const int8_t* __restrict__ spins, int64_t ns, T* __restrict__ theta_out,
+                                   double* __restrict__ logabs_out) {
+  int lane = threadIdx.x & 31;
+  int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= ns) return;
+  const int8_t* sp = spins + s * N;
+  T la = 0;
+  for (int i = 0; i < M; ++i) {
+    T acc = 0;
+    for (int j = lane; j < N; j += 32) acc += W[(size_t)i * N + j] * (T)sp[j];
+    acc = warp_sum(acc) + b[i];
+    if (theta_out && lane == 0) theta_out[s * M + i] = acc;
+    la += lncosh(acc);
+  }
+  if (logabs_out && lane == 0) logabs_out[s] = (double)la;
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent sweep
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct SweepParams {
+  const T* Wt;  // [N, M]
+  const T* b;   // [M]
+  int N, M;
+  int8_t* spins;
+  int64_t ns;
+  int nsweeps, kind;
+  const int32_t* nbr;
+  int max_nb, hop;
+  double reweight;
+  const int32_t* inj_pos;
+  const int32_t* inj_slot;
+  const double* inj_u;
+  uint32_t seed_lo, seed_hi;
+  uint64_t step0, chain0;
+  double* logabs_out;
+  double* logabs_chain_out;
+  int32_t* naccept_out;
+  uint8_t* accept_log;
+};
+
+template <typename T>
+__device__ __forceinline__ void stage_w(T* dst, const T* __restrict__ src, size_t n) {
+  // 16-byte vector copy global -> shared (both 16B aligned by construction)
+  const size_t nvec = (n * sizeof(T)) / 16;
+  const int4* s4 = reinterpret_cast<const int4*>(src);
+  int4* d4 = reinterpret_cast<int4*>(dst);
+  for (size_t k = threadIdx.x; k < nvec; k += blockDim.x) d4[k] = __ldg(s4 + k);
+  for (size_t k = nvec * (16 / sizeof(T)) + threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+}
+
+__device__ __forceinline__ int spin_from_words(uint32_t myword, int j) {
+  uint32_t w = __shfl_sync(FULL, myword, j >> 5);
+  return ((w >> (j & 31)) & 1u) ? 1 : -1;
+}
+
+template <typename T, int RMAX, bool WSMEM>
+__global__ void __launch_bounds__(RMAX <= 8 ? 1024 : (sizeof(T) == 4 && RMAX <= 16 ? 896 : 512), 1)
+    rbm_sweep_kernel(SweepParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.N, M = p.M;
+  const T* Wt = p.Wt;
+  if (WSMEM) {
+    T* Ws = reinterpret_cast<T*>(smem_raw);
+    stage_w(Ws, p.Wt, (size_t)N * M);
+    __syncthreads();
+    Wt = Ws;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int64_t nwarps = (int64_t)gridDim.x * wpb;
+  const int NW = (N + 31) >> 5;
+  const bool rw2 = (p.reweight == 2.0);
+
+  for (int64_t chain = (int64_t)blockIdx.x * wpb + warp; chain < p.ns; chain += nwarps) {
+    int8_t* sp = p.spins + chain * N;
+    // spins -> bit words (bit = 1 for spin up); lane w keeps word w
+    uint32_t myword = 0;
+    for (int w = 0; w < NW; ++w) {
+      int j = w * 32 + lane;
+      uint32_t bal = __ballot_sync(FULL, j < N && sp[j] > 0);
+      if (lane == w) myword = bal;
+    }
+    // theta = W s + b
+    T th[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) th[r] = 0;
+    for (int j = 0; j < N; ++j) {
+      T sj = (T)spin_from_words(myword, j);
+      const T* col = Wt + (size_t)j * M;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        int i = r * 32 + lane;
+        if (i < M) th[r] += col[i] * sj;
+      }
+    }
+    T lsum = 0;
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      int i = r * 32 + lane;
+      if (i < M) {
+        th[r] += p.b[i];
+        lsum += lncosh(th[r]);
+      }
+    }
+    double la = (double)warp_sum(lsum);
+    int nacc = 0;
+
+    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;  // Philox outputs of step (t & ~31) + lane
+    for (int t = 0; t < p.nsweeps; ++t) {
+      int pos, slot = 0;
+      double u;
+      if (p.inj_u) {
+        size_t o = (size_t)t * p.ns + chain;
+        pos = p.inj_pos[o];
+        if (p.kind == QTX_SPIN_EXCHANGE) slot = p.inj_slot[o];
+        u = p.inj_u[o];
+      } else {
+        if ((t & 31) == 0) {
+          uint64_t step = p.step0 + (uint64_t)(t + lane);
+          q0 = (uint32_t)(p.chain0 + chain);
+          q1 = (uint32_t)step;
+          q2 = (uint32_t)(step >> 32);
+          q3 = 0;
+          philox4x32_10(q0, q1, q2, q3, p.seed_lo, p.seed_hi);
+        }
+        int src = t & 31;
+        uint32_t r0 = __shfl_sync(FULL, q0, src), r1 = __shfl_sync(FULL, q1, src);
+        uint32_t r2 = __shfl_sync(FULL, q2, src), r3 = __shfl_sync(FULL, q3, src);
+        u = (double)((((uint64_t)r2 << 32) | r3) >> 11) * 0x1.0p-53;
+        if (p.kind == QTX_LOCAL_FLIP) {
+          pos = (int)__umulhi(r0, (uint32_t)N);
+        } else {
+          // k-th site holding the hopping particle
+          uint32_t w = (lane < NW) ? myword : 0u;
+          if (p.hop < 0) {
+            w = ~w;
+            int rem = N - lane * 32;
+            if (lane >= NW) w = 0;
+            else if (rem < 32) w &= (1u << rem) - 1u;
+          }
+          int cnt = __popc(w), incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+          }
+          int nhop = __shfl_sync(FULL, incl, 31);
+          int k = (int)__umulhi(r0, (uint32_t)nhop);
+          uint32_t bal = __ballot_sync(FULL, incl > k);
+          int L = __ffs(bal) - 1;
+          int excl = __shfl_sync(FULL, incl - cnt, L);
+          uint32_t wl = __shfl_sync(FULL, w, L);
+          pos = L * 32 + (int)__fns(wl, 0, k - excl + 1);
+          slot = (int)__umulhi(r1, (uint32_t)p.max_nb);
+        }
+      }
+      int j0 = pos, j1 = -1;
+      bool moved = true;
+      if (p.kind == QTX_SPIN_EXCHANGE) {
+        int nb = p.nbr[pos * p.max_nb + slot];
+        if (nb < 0) nb = pos;
+        j1 = nb;
+        moved = spin_from_words(myword, j0) != spin_from_words(myword, j1);
+      }
+      bool acc = false;
+      if (moved) {
+        // new spin values at the flipped sites: s'_j = -s_j
+        T s0 = (T)(-spin_from_words(myword, j0));
+        const T* c0 = Wt + (size_t)j0 * M;
+        T s1 = 0;
+        const T* c1 = c0;
+        if (j1 >= 0) {
+          s1 = (T)(-spin_from_words(myword, j1));
+          c1 = Wt + (size_t)j1 * M;
+        }
+        T ls = 0;
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+          int i = r * 32 + lane;
+          if (i < M) {
+            T d = c0[i] * s0 + c1[i] * s1;
+            ls += lncosh(th[r] + T(2) * d);
+          }
+        }
+        double la_new = (double)warp_sum(ls);
+        double rate = exp(la_new - la);
+        rate = rw2 ? rate * rate : pow(rate, p.reweight);
+        acc = rate > 1.0 - u;  // |psi| == 0 cannot happen: log|cosh| >= 0
+        if (acc) {
+#pragma unroll
+          for (int r = 0; r < RMAX; ++r) {
+            int i = r * 32 + lane;
+            if (i < M) {
+              T d = c0[i] * s0 + c1[i] * s1;
+              th[r] = th[r] + T(2) * d;
+            }
+          }
+          la = la_new;
+          if (lane == (j0 >> 5)) myword ^= 1u << (j0 & 31);
+          if (j1 >= 0 && lane == (j1 >> 5)) myword ^= 1u << (j1 & 31);
+          ++nacc;
+        }
+      }
+      if (p.accept_log && lane == 0) p.accept_log[(size_t)t * p.ns + chain] = acc ? 1 : 0;
+    }
+
+    // write back the chain, its locally-updated amplitude and the direct-forward amplitude
+    for (int w = 0; w < NW; ++w) {
+      uint32_t word = __shfl_sync(FULL, myword, w);
+      int j = w * 32 + lane;
+      if (j < N) sp[j] = ((word >> lane) & 1u) ? 1 : -1;
+    }
+    if (lane == 0) {
+      if (p.logabs_chain_out) p.logabs_chain_out[chain] = la;
+      if (p.naccept_out) p.naccept_out[chain] = nacc;
+    }
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) th[r] = 0;
+    for (int j = 0; j < N; ++j) {
+      T sj = (T)spin_from_words(myword, j);
+      const T* col = Wt + (size_t)j * M;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        int i = r * 32 + lane;
+        if (i < M) th[r] += col[i] * sj;
+      }
+    }
+    lsum = 0;
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      int i = r * 32 + lane;
+      if (i < M) lsum += lncosh(th[r] + p.b[i]);
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0 && p.logabs_out) p.logabs_out[chain] = (double)lsum;
+  }
+}
+
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;
+
+template <typename T, int RMAX>
+static int launch_sweep(const SweepParams<T>& p, cudaStream_t st) {
+  const size_t wbytes = (size_t)p.N * p.M * sizeof(T);
+  const bool wsmem = wbytes <= kSmemBudget;
+  const int maxthreads = RMAX <= 8 ? 1024 : (sizeof(T) == 4 && RMAX <= 16 ? 896 : 512);
+  const int sms = num_sms();
+  int wpb = (int)((p.ns + sms - 1) / sms);
+  if (wpb > maxthreads / 32) wpb = maxthreads / 32;
+  if (wpb < 1) wpb = 1;
+  int64_t nblk = (p.ns + wpb - 1) / wpb;
+  int per_sm = wsmem ? 1 : (2048 / (wpb * 32) > 0 ? 2048 / (wpb * 32) : 1);
+  if (nblk > (int64_t)sms * per_sm) nblk = (int64_t)sms * per_sm;
+  if (wsmem) {
+    auto k = rbm_sweep_kernel<T, RMAX, true>;
+    QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
+    k<<<(unsigned)nblk, wpb * 32, wbytes, st>>>(p);
+  } else {
+    rbm_sweep_kernel<T, RMAX, false><<<(unsigned)nblk, wpb * 32, 0, st>>>(p);
+  }
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+template <typename T>
+static int sweep_dispatch(const SweepParams<T>& p, cudaStream_t st) {
+  const int M = p.M;
+  if (M <= 64) return launch_sweep<T, 2>(p, st);
+  if (M <= 128) return launch_sweep<T, 4>(p, st);
+  if (M <= 256) return launch_sweep<T, 8>(p, st);
+  if (M <= 512) return launch_sweep<T, 16>(p, st);
+  if (M <= 1024) return launch_sweep<T, 32>(p, st);
+  set_error("qtx_rbm_sweep: M=%d > 1024 hidden units is not supported", M);
+  return QTX_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused local energy
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct OlocParams {
+  const T* Wt;
+  const T* b;
+  int N, M;
+  const int8_t* spins;
+  int64_t ns;
+  const double* coef;
+  const uint16_t* sites;  // [nterms, 4]
+  const uint8_t* ops;     // [nterms, 4]
+  int nterms;
+  double* eloc;
+  int32_t* nconn;
+  int terms_in_smem;
+};
+
+template <typename T, int RMAX, bool WSMEM>
+__global__ void __launch_bounds__(RMAX <= 8 ? 1024 : (sizeof(T) == 4 && RMAX <= 16 ? 896 : 512), 1)
+    rbm_oloc_kernel(OlocParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.N, M = p.M;
+  unsigned char* sm = smem_raw;
+  const T* Wt = p.Wt;
+  if (WSMEM) {
+    T* Ws = reinterpret_cast<T*>(sm);
+    stage_w(Ws, p.Wt, (size_t)N * M);
+    Wt = Ws;
+    sm += (((size_t)N * M * sizeof(T)) + 15) / 16 * 16;
+  }
+  const double* coef = p.coef;
+  const uint2* sites = reinterpret_cast<const uint2*>(p.sites);
+  const uint32_t* ops = reinterpret_cast<const uint32_t*>(p.ops);
+  if (p.terms_in_smem) {
+    double* c_s = reinterpret_cast<double*>(sm);
+    uint2* s_s = reinterpret_cast<uint2*>(c_s + p.nterms);
+    uint32_t* o_s = reinterpret_cast<uint32_t*>(s_s + p.nterms);
+    for (int t = threadIdx.x; t < p.nterms; t += blockDim.x) {
+      c_s[t] = p.coef[t];
+      s_s[t] = sites[t];
+      o_s[t] = ops[t];
+    }
+    coef = c_s; sites = s_s; ops = o_s;
+    sm += (size_t)p.nterms * 20;
+    sm = (unsigned char*)(((uintptr_t)sm + 15) / 16 * 16);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  int8_t* myspins = reinterpret_cast<int8_t*>(sm) + (size_t)warp * ((N + 15) / 16 * 16);
+  __syncthreads();
+  const int64_t nwarps = (int64_t)gridDim.x * wpb;
+
+  for (int64_t s = (int64_t)blockIdx.x * wpb + warp; s < p.ns; s += nwarps) {
+    const int8_t* sp = p.spins + s * N;
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) myspins[j] = sp[j];
+    __syncwarp();
+    T th[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) th[r] = 0;
+    for (int j = 0; j < N; ++j) {
+      T sj = (T)myspins[j];
+      const T* col = Wt + (size_t)j * M;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        int i = r * 32 + lane;
+        if (i < M) th[r] += col[i] * sj;
+      }
+    }
+    T lsum = 0;
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      int i = r * 32 + lane;
+      if (i < M) {
+        th[r] += p.b[i];
+        lsum += lncosh(th[r]);
+      }
+    }
+    const double la = (double)warp_sum(lsum);
+    double e = 0.0;
+    int nconn = 0;
+    for (int t = 0; t < p.nterms; ++t) {
+      double c = coef[t];
+      uint2 st = sites[t];
+      uint32_t op4 = ops[t];
+      int site[4] = {(int)(st.x & 0xffff), (int)(st.x >> 16), (int)(st.y & 0xffff), (int)(st.y >> 16)};
+      bool valid = true;
+      int nfl = 0;
+      const T* cp[4];
+      T sg[4];
+#pragma unroll
+      for (int k = 3; k >= 0; --k) {  // right-most operator acts first (operator.py:107)
+        int op = (op4 >> (8 * k)) & 0xff;
+        cp[k] = nullptr;
+        sg[k] = 0;
+        if (op == QTX_OP_NONE || op == QTX_OP_I) continue;
+        int sk = myspins[site[k]];
+        if (op == QTX_OP_Z) {
+          c = c * sk / 2;
+        } else {
+          if (op == QTX_OP_X) c = c / 2;
+          else if (op == QTX_OP_P) valid = valid && (sk < 0);
+          else valid = valid && (sk > 0);
+          cp[k] = Wt + (size_t)site[k] * M;
+          sg[k] = (T)(-sk);  // new spin value at the flipped site
+          ++nfl;
+        }
+      }
+      if (nfl == 0) {
+        e += c;
+        continue;
+      }
+      if (!valid || fabs(c) <= 1e-8) continue;  // NaN or isclose(H, 0) (operator.py:154)
+      ++nconn;
+      T ls = 0;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        int i = r * 32 + lane;
+        if (i < M) {
+          T d = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (cp[k]) d += cp[k][i] * sg[k];
+          ls += lncosh(th[r] + T(2) * d);
+        }
+      }
+      double la_new = (double)warp_sum(ls);
+      e += c * exp(la_new - la);
+    }
+    if (lane == 0) {
+      p.eloc[s] = e;
+      if (p.nconn) p.nconn[s] = nconn;
+    }
+  }
+}
+
+template <typename T, int RMAX>
+static int launch_oloc(OlocParams<T> p, cudaStream_t st) {
+  const size_t wbytes = (((size_t)p.N * p.M * sizeof(T)) + 15) / 16 * 16;
+  const size_t tbytes = ((size_t)p.nterms * 20 + 15) / 16 * 16;
+  const int maxthreads = RMAX <= 8 ? 1024 : (sizeof(T) == 4 && RMAX <= 16 ? 896 : 512);
+  const int sms = num_sms();
+  int wpb = (int)((p.ns + sms - 1) / sms);
+  if (wpb > maxthreads / 32) wpb = maxthreads / 32;
+  if (wpb < 1) wpb = 1;
+  const size_t sbytes = (size_t)wpb * ((p.N + 15) / 16 * 16);
+  const bool wsmem = wbytes + sbytes + 64 <= kSmemBudget;
+  size_t smem = (wsmem ? wbytes : 0) + sbytes + 64;
+  p.terms_in_smem = (smem + tbytes <= kSmemBudget) ? 1 : 0;
+  if (p.terms_in_smem) smem += tbytes;
+  int64_t nblk = (p.ns + wpb - 1) / wpb;
+  int per_sm = wsmem ? 1 : (2048 / (wpb * 32) > 0 ? 2048 / (wpb * 32) : 1);
+  if (nblk > (int64_t)sms * per_sm) nblk = (int64_t)sms * per_sm;
+  if (wsmem) {
+    auto k = rbm_oloc_kernel<T, RMAX, true>;
+    QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nblk, wpb * 32, smem, st>>>(p);
+  } else {
+    auto k = rbm_oloc_kernel<T, RMAX, false>;
+    QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nblk, wpb * 32, smem, st>>>(p);
+  }
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+template <typename T>
+static int oloc_dispatch(const OlocParams<T>& p, cudaStream_t st) {
+  const int M = p.M;
+  if (M <= 64) return launch_oloc<T, 2>(p, st);
+  if (M <= 128) return launch_oloc<T, 4>(p, st);
+  if (M <= 256) return launch_oloc<T, 8>(p, st);
+  if (M <= 512) return launch_oloc<T, 16>(p, st);
+  if (M <= 1024) return launch_oloc<T, 32>(p, st);
+  set_error("qtx_rbm_oloc: M=%d > 1024 hidden units is not supported", M);
+  return QTX_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ref_forward: psi of connected configurations from the parent's theta
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rbm_ref_forward_kernel(const T* __restrict__ W, int N, int M, const T* __restrict__ theta,
+                                       const int8_t* __restrict__ s_old, const int8_t* __restrict__ s_new,
+                                       const int32_t* __restrict__ segment, int64_t nconn, int nflips,
+                                       double* __restrict__ logabs_out) {
+  const int lane = threadIdx.x & 31;
+  int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= nconn) return;
+  int seg = segment[c];
+  if (seg < 0) {
+    // padding entry: the reference gathers row -1 (jnp negative index); its value is multiplied by
+    // H = 0 downstream.  We emit logabs = 0.
+    if (lane == 0) logabs_out[c] = 0.0;
+    return;
+  }
+  const int8_t* so = s_old + (size_t)seg * N;
+  const int8_t* sn = s_new + c * N;
+  // first `nflips` differing sites in ascending order, missing ones padded with site 0
+  int idx[QTX_MAX_TERM_SITES] = {0, 0, 0, 0};
+  int found = 0;
+  for (int j0 = 0; j0 < N && found < nflips; j0 += 32) {
+    int j = j0 + lane;
+    uint32_t bal = __ballot_sync(FULL, j < N && so[j] != sn[j]);
+    while (bal && found < nflips) {
+      int bpos = __ffs(bal) - 1;
+      idx[found++] = j0 + bpos;
+      bal &= bal - 1;
+    }
+  }
+  const T* th = theta + (size_t)seg * M;
+  T ls = 0;
+  for (int i = lane; i < M; i += 32) {
+    T d = 0;
+    for (int k = 0; k < nflips; ++k) d += W[(size_t)i * N + idx[k]] * (T)sn[idx[k]];
+    ls += lncosh(th[i] + T(2) * d);
+  }
+  ls = warp_sum(ls);
+  if (lane == 0) logabs_out[c] = (double)ls;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobian: O[s, i*N+j] = tanh(theta_i) s_j ; O[s, M*N+i] = tanh(theta_i)
+// one CTA per (sample, column tile); fully coalesced 16-byte stores
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename OutT>
+__global__ void __launch_bounds__(256) rbm_jacobian_kernel(const T* __restrict__ W, const T* __restrict__ b, int N,
+                                                           int M, const int8_t* __restrict__ spins, int64_t ns,
+                                                           OutT* __restrict__ out, int64_t ld,
+                                                           const double* __restrict__ col_mean,
+                                                           const double* __restrict__ row_scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* t_s = reinterpret_cast<T*>(smem_raw);          // [M] tanh(theta)
+  T* s_s = t_s + ((M + 3) / 4 * 4);                  // [N] spins as T
+  const int64_t s = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int8_t* sp = spins + s * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) s_s[j] = (T)sp[j];
+  __syncthreads();
+  for (int i = warp; i < M; i += nw) {
+    T acc = 0;
+    for (int j = lane; j < N; j += 32) acc += W[(size_t)i * N + j] * s_s[j];
+    acc = warp_sum(acc) + b[i];
+    if (lane == 0) t_s[i] = tanh(acc);
+  }
+  __syncthreads();
+  const double scale = row_scale ? row_scale[s] : 1.0;
+  const int64_t MN = (int64_t)M * N, NP = MN + M;
+  OutT* row = out + s * ld;
+  constexpr int V = 16 / sizeof(OutT);  // elements per 16-byte store
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  if (vec_ok) {
+    const int64_t stride = (int64_t)blockDim.x * V;
+    const int di = (int)(stride / N), dj = (int)(stride % N);
+    int64_t k = (int64_t)threadIdx.x * V;
+    int i = (int)(k / N), j = (int)(k % N);
+    for (; k < NP; k += stride) {
+      OutT v[V];
+      int ii = i, jj = j;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        int64_t kk = k + e;
+        double val = 0.0;
+        if (kk < MN) val = (double)(t_s[ii] * s_s[jj]);
+        else if (kk < NP) val = (double)t_s[kk - MN];
+        if (col_mean && kk < NP) val -= col_mean[kk];
+        v[e] = (OutT)(val * scale);
+        if (++jj == N) { jj = 0; ++ii; }
+      }
+      if (k + V <= NP) {
+        *reinterpret_cast<int4*>(row + k) = *reinterpret_cast<int4*>(v);
+      } else {
+        for (int e = 0; e < V && k + e < NP; ++e) row[k + e] = v[e];
+      }
+      i += di; j += dj;
+      if (j >= N) { j -= N; ++i; }
+    }
+  } else {
+    for (int64_t k = threadIdx.x; k < NP; k += blockDim.x) {
+      double val = (k < MN) ? (double)(t_s[k / N] * s_s[k % N]) : (double)t_s[k - MN];
+      if (col_mean) val -= col_mean[k];
+      row[k] = (OutT)(val * scale);
+    }
+  }
+}
+
+// tanh(theta) table [ns, M] (model dtype) for the column-mean kernel
+template <typename T>
+__global__ void rbm_tanh_kernel(const T* __restrict__ W, const T* __restrict__ b, int N, int M,
+                                const int8_t* __restrict__ spins, int64_t ns, T* __restrict__ t_out) {
+  int lane = threadIdx.x & 31;
+  int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= ns) return;
+  const int8_t* sp = spins + s * N;
+  for (int i = 0; i < M; ++i) {
+    T acc = 0;
+    for (int j = lane; j < N; j += 32) acc += W[(size_t)i * N + j] * (T)sp[j];
+    acc = warp_sum(acc) + b[i];
+    if (lane == 0) t_out[s * M + i] = tanh(acc);
+  }
+}
+
+// mean[i*N+j] = (1/ns) sum_s w_s t[s,i] spins[s,j];  mean[M*N+i] = (1/ns) sum_s w_s t[s,i]
+// grid (ceil(NP/128), SPLIT): each CTA reduces a slice of samples, combined with atomicAdd(double)
+template <typename T>
+__global__ void rbm_colmean_kernel(const T* __restrict__ t, const int8_t* __restrict__ spins, int N, int M,
+                                   int64_t ns, const double* __restrict__ weight, double* __restrict__ mean_out) {
+  const int64_t MN = (int64_t)M * N, NP = MN + M;
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= NP) return;
+  int i, j;
+  if (k < MN) { i = (int)(k / N); j = (int)(k % N); } else { i = (int)(k - MN); j = -1; }
+  int64_t chunk = (ns + gridDim.y - 1) / gridDim.y;
+  int64_t s0 = blockIdx.y * chunk, s1 = s0 + chunk < ns ? s0 + chunk : ns;
+  double acc = 0.0;
+  for (int64_t s = s0; s < s1; ++s) {
+    double v = (double)t[s * M + i];
+    if (j >= 0) v = (double)(t[s * M + i] * (T)spins[s * N + j]);
+    if (weight) v *= weight[s];
+    acc += v;
+  }
+  atomicAdd(mean_out + k, acc / (double)ns);
+}
+
+}  // namespace qtx
+
+// ===============================================================================================
+// C ABI
+// ===============================================================================================
+using namespace qtx;
+
+extern "C" size_t qtx_rbm_workspace_size(int model_dtype, int N, int M) {
+  size_t es = model_dtype == QTX_F64 ? 8 : 4;
+  return ((size_t)N * M * es + 255) / 256 * 256;
+}
+
+extern "C" int qtx_rbm_forward(int model_dtype, const void* W, const void* b, int N, int M, const int8_t* spins,
+                               int64_t ns, void* theta_out, double* logabs_out, qtx_stream_t stream) {
+  QTX_REQUIRE(W && b && spins && N > 0 && M > 0 && ns >= 0, QTX_ERR_INVALID, "qtx_rbm_forward: bad argument");
+  if (ns == 0) return QTX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned grid = (unsigned)((ns + 7) / 8);
+  if (model_dtype == QTX_F32)
+    rbm_forward_kernel<float><<<grid, 256, 0, st>>>((const float*)W, (const float*)b, N, M, spins, ns,
+                                                    (float*)theta_out, logabs_out);
+  else if (model_dtype == QTX_F64)
+    rbm_forward_kernel<double><<<grid, 256, 0, st>>>((const double*)W, (const double*)b, N, M, spins, ns,
+                                                     (double*)theta_out, logabs_out);
+  else QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_rbm_forward: bad dtype %d", model_dtype);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+template <typename T>
+static int rbm_sweep_impl(const void* W, const void* b, int N, int M, int8_t* spins, int64_t ns, int nsweeps, int kind,
+                          const int32_t* nbr, int max_nb, int hop, double reweight, const int32_t* inj_pos,
+                          const int32_t* inj_slot, const double* inj_u, uint64_t seed, uint64_t step0, uint64_t chain0,
+                          double* logabs_out, double* logabs_chain_out, int32_t* naccept_out, uint8_t* accept_log,
+                          void* ws, cudaStream_t st) {
+  int rc = transpose_w<T>(W, ws, N, M, st);
+  if (rc) return rc;
+  SweepParams<T> p;
+  p.Wt = (const T*)ws; p.b = (const T*)b; p.N = N; p.M = M; p.spins = spins; p.ns = ns;
+  p.nsweeps = nsweeps; p.kind = kind; p.nbr = nbr; p.max_nb = max_nb; p.hop = hop; p.reweight = reweight;
+  p.inj_pos = inj_pos; p.inj_slot = inj_slot; p.inj_u = inj_u;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.step0 = step0; p.chain0 = chain0;
+  p.logabs_out = logabs_out; p.logabs_chain_out = logabs_chain_out; p.naccept_out = naccept_out;
+  p.accept_log = accept_log;
+  return sweep_dispatch<T>(p, st);
+}
+
+extern "C" int qtx_rbm_sweep(int model_dtype, const void* W, const void* b, int N, int M, int8_t* spins, int64_t ns,
+                             int nsweeps, int kind, const int32_t* nbr_table, int max_nb, int hop, double reweight,
+                             const int32_t* inj_pos, const int32_t* inj_slot, const double* inj_u, uint64_t seed,
+                             uint64_t step0, uint64_t chain0, double* logabs_out, double* logabs_chain_out,
+                             int32_t* naccept_out, uint8_t* accept_log, void* workspace, size_t workspace_bytes,
+                             qtx_stream_t stream) {
+  QTX_REQUIRE(W && b && spins && N > 0 && M > 0 && ns >= 0 && nsweeps >= 0, QTX_ERR_INVALID,
+              "qtx_rbm_sweep: bad argument");
+  QTX_REQUIRE(N <= 1024, QTX_ERR_UNSUPPORTED, "qtx_rbm_sweep: N=%d > 1024 sites is not supported", N);
+  QTX_REQUIRE(kind == QTX_LOCAL_FLIP || kind == QTX_SPIN_EXCHANGE, QTX_ERR_INVALID, "qtx_rbm_sweep: bad kind %d", kind);
+  if (kind == QTX_SPIN_EXCHANGE)
+    QTX_REQUIRE(nbr_table && max_nb > 0 && (hop == 1 || hop == -1), QTX_ERR_INVALID,
+                "qtx_rbm_sweep: exchange needs a neighbour table and hop = +-1");
+  if (inj_u) QTX_REQUIRE(inj_pos && (kind == QTX_LOCAL_FLIP || inj_slot), QTX_ERR_INVALID,
+                         "qtx_rbm_sweep: injected randoms need inj_pos (and inj_slot for exchange)");
+  QTX_REQUIRE(workspace && workspace_bytes >= qtx_rbm_workspace_size(model_dtype, N, M), QTX_ERR_INVALID,
+              "qtx_rbm_sweep: workspace too small");
+  if (ns == 0) return QTX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model_dtype == QTX_F32)
+    return rbm_sweep_impl<float>(W, b, N, M, spins, ns, nsweeps, kind, nbr_table, max_nb, hop, reweight, inj_pos,
+                                 inj_slot, inj_u, seed, step0, chain0, logabs_out, logabs_chain_out, naccept_out,
+                                 accept_log, workspace, st);
+  if (model_dtype == QTX_F64)
+    return rbm_sweep_impl<double>(W, b, N, M, spins, ns, nsweeps, kind, nbr_table, max_nb, hop, reweight, inj_pos,
+                                  inj_slot, inj_u, seed, step0, chain0, logabs_out, logabs_chain_out, naccept_out,
+                                  accept_log, workspace, st);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_rbm_sweep: bad dtype %d", model_dtype);
+}
+
+template <typename T>
+static int rbm_oloc_impl(const void* W, const void* b, int N, int M, const int8_t* spins, int64_t ns,
+                         const double* coef, const uint16_t* sites, const uint8_t* ops, int nterms, double* eloc,
+                         int32_t* nconn, void* ws, cudaStream_t st) {
+  int rc = transpose_w<T>(W, ws, N, M, st);
+  if (rc) return rc;
+  OlocParams<T> p;
+  p.Wt = (const T*)ws; p.b = (const T*)b; p.N = N; p.M = M; p.spins = spins; p.ns = ns;
+  p.coef = coef; p.sites = sites; p.ops = ops; p.nterms = nterms; p.eloc = eloc; p.nconn = nconn;
+  p.terms_in_smem = 0;
+  return oloc_dispatch<T>(p, st);
+}
+
+extern "C" int qtx_rbm_oloc(int model_dtype, const void* W, const void* b, int N, int M, const int8_t* spins,
+                            int64_t ns, const double* term_coef, const uint16_t* term_sites, const uint8_t* term_ops,
+                            int nterms, double* eloc_out, int32_t* nconn_out, void* workspace, size_t workspace_bytes,
+                            qtx_stream_t stream) {
+  QTX_REQUIRE(W && b && spins && eloc_out && N > 0 && M > 0 && ns >= 0 && nterms >= 0, QTX_ERR_INVALID,
+              "qtx_rbm_oloc: bad argument");
+  QTX_REQUIRE(nterms == 0 || (term_coef && term_sites && term_ops), QTX_ERR_INVALID, "qtx_rbm_oloc: null term table");
+  QTX_REQUIRE(workspace && workspace_bytes >= qtx_rbm_workspace_size(model_dtype, N, M), QTX_ERR_INVALID,
+              "qtx_rbm_oloc: workspace too small");
+  if (ns == 0) return QTX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model_dtype == QTX_F32)
+    return rbm_oloc_impl<float>(W, b, N, M, spins, ns, term_coef, term_sites, term_ops, nterms, eloc_out, nconn_out,
+                                workspace, st);
+  if (model_dtype == QTX_F64)
+    return rbm_oloc_impl<double>(W, b, N, M, spins, ns, term_coef, term_sites, term_ops, nterms, eloc_out, nconn_out,
+                                 workspace, st);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_rbm_oloc: bad dtype %d", model_dtype);
+}
+
+extern "C" int qtx_rbm_ref_forward(int model_dtype, const void* W, int N, int M, const void* theta,
+                                   const int8_t* s_old, int64_t ns, const int8_t* s_new, const int32_t* segment,
+                                   int64_t nconn, int nflips, double* logabs_out, qtx_stream_t stream) {
+  QTX_REQUIRE(W && theta && s_old && s_new && segment && logabs_out && N > 0 && M > 0, QTX_ERR_INVALID,
+              "qtx_rbm_ref_forward: bad argument");
+  QTX_REQUIRE(nflips >= 1 && nflips <= QTX_MAX_TERM_SITES, QTX_ERR_UNSUPPORTED,
+              "qtx_rbm_ref_forward: nflips=%d outside 1..%d", nflips, QTX_MAX_TERM_SITES);
+  (void)ns;
+  if (nconn == 0) return QTX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned grid = (unsigned)((nconn + 7) / 8);
+  if (model_dtype == QTX_F32)
+    rbm_ref_forward_kernel<float><<<grid, 256, 0, st>>>((const float*)W, N, M, (const float*)theta, s_old, s_new,
+                                                        segment, nconn, nflips, logabs_out);
+  else if (model_dtype == QTX_F64)
+    rbm_ref_forward_kernel<double><<<grid, 256, 0, st>>>((const double*)W, N, M, (const double*)theta, s_old, s_new,
+                                                         segment, nconn, nflips, logabs_out);
+  else QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_rbm_ref_forward: bad dtype %d", model_dtype);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+template <typename T, typename OutT>
+static int jac_launch(const void* W, const void* b, int N, int M, const int8_t* spins, int64_t ns, void* out,
+                      int64_t ld, const double* mean, const double* scale, cudaStream_t st) {
+  size_t smem = ((size_t)(M + 3) / 4 * 4 + N) * sizeof(T) + 16;
+  QTX_REQUIRE(smem <= kSmemBudget, QTX_ERR_UNSUPPORTED, "qtx_rbm_jacobian: M+N too large for shared memory");
+  auto k = rbm_jacobian_kernel<T, OutT>;
+  if (smem > 48 * 1024) QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)ns, 256, smem, st>>>((const T*)W, (const T*)b, N, M, spins, ns, (OutT*)out, ld, mean, scale);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_rbm_jacobian(int model_dtype, const void* W, const void* b, int N, int M, const int8_t* spins,
+                                int64_t ns, int out_dtype, void* out, int64_t ld, const double* col_mean,
+                                const double* row_scale, qtx_stream_t stream) {
+  QTX_REQUIRE(W && b && spins && out && N > 0 && M > 0 && ns >= 0, QTX_ERR_INVALID, "qtx_rbm_jacobian: bad argument");
+  QTX_REQUIRE(ld >= (int64_t)M * N + M, QTX_ERR_INVALID, "qtx_rbm_jacobian: ld smaller than the parameter count");
+  QTX_REQUIRE(ns < (1ll << 31), QTX_ERR_UNSUPPORTED, "qtx_rbm_jacobian: ns too large");
+  if (ns == 0) return QTX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model_dtype == QTX_F32 && out_dtype == QTX_F64)
+    return jac_launch<float, double>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, st);
+  if (model_dtype == QTX_F32 && out_dtype == QTX_F32)
+    return jac_launch<float, float>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, st);
+  if (model_dtype == QTX_F64 && out_dtype == QTX_F64)
+    return jac_launch<double, double>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, st);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_rbm_jacobian: unsupported dtype pair (%d -> %d)", model_dtype, out_dtype);
+}
+
+extern "C" size_t qtx_rbm_colmean_workspace_size(int model_dtype, int N, int M, int64_t ns) {
+  (void)N;
+  size_t es = model_dtype == QTX_F64 ? 8 : 4;
+  return ((size_t)ns * M * es + 255) / 256 * 256;
+}
+
+template <typename T>
+static int colmean_impl(const void* W, const void* b, int N, int M, const int8_t* spins, int64_t ns,
+                        const double* weight, double* mean_out, void* ws, cudaStream_t st) {
+  T* t = (T*)ws;
+  rbm_tanh_kernel<T><<<(unsigned)((ns + 7) / 8), 256, 0, st>>>((const T*)W, (const T*)b, N, M, spins, ns, t);
+  QTX_LAUNCH_CHECK();
+  const int64_t NP = (int64_t)M * N + M;
+  QTX_CUDA(cudaMemsetAsync(mean_out, 0, NP * sizeof(double), st));
+  unsigned gx = (unsigned)((NP + 127) / 128);
+  int split = (int)((4 * (int64_t)num_sms() + gx - 1) / gx);
+  if (split < 1) split = 1;
+  if (split > 64) split = 64;
+  if (split > ns) split = (int)ns;
+  rbm_colmean_kernel<T><<<dim3(gx, split), 128, 0, st>>>(t, spins, N, M, ns, weight, mean_out);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_rbm_jacobian_colmean(int model_dtype, const void* W, const void* b, int N, int M,
+                                        const int8_t* spins, int64_t ns, const double* weight, double* mean_out,
+                                        void* workspace, size_t workspace_bytes, qtx_stream_t stream) {
+  QTX_REQUIRE(W && b && spins && mean_out && N > 0 && M > 0 && ns > 0, QTX_ERR_INVALID,
+              "qtx_rbm_jacobian_colmean: bad argument");
+  QTX_REQUIRE(workspace && workspace_bytes >= qtx_rbm_colmean_workspace_size(model_dtype, N, M, ns), QTX_ERR_INVALID,
+              "qtx_rbm_jacobian_colmean: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model_dtype == QTX_F32) return colmean_impl<float>(W, b, N, M, spins, ns, weight, mean_out, workspace, st);
+  if (model_dtype == QTX_F64) return colmean_impl<double>(W, b, N, M, spins, ns, weight, mean_out, workspace, st);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_rbm_jacobian_colmean: bad dtype %d", model_dtype);
+}

@@ -1,0 +1,148 @@
+// eigh + soft pseudo-inverse of the SR / MinSR solve (quantax/optimizer/solver.py:94-101,142-146).
+// The eigendecomposition is cuSOLVER syevd (a library call, reported separately in the bench);
+// the pseudo-inverse epilogue is three small kernels on the eigenvector matrix.
+#include <cusolverDn.h>
+
+#include "common.cuh"
+
+namespace qtx {
+
+static thread_local cusolverDnHandle_t g_solver = nullptr;
+
+static int solver_handle(cusolverDnHandle_t* h) {
+  if (!g_solver) {
+    cusolverStatus_t s = cusolverDnCreate(&g_solver);
+    if (s != CUSOLVER_STATUS_SUCCESS) {
+      set_error("cusolverDnCreate failed with status %d", (int)s);
+      g_solver = nullptr;
+      return QTX_ERR_SOLVER;
+    }
+  }
+  *h = g_solver;
+  return QTX_OK;
+}
+
+// rho[k] = sum_i Ut[k, i] b[i]   (Ut row-major = eigenvectors as rows), CTA per k
+__global__ void __launch_bounds__(256) rows_dot_kernel(const double* __restrict__ Ut, int64_t n,
+                                                       const double* __restrict__ b, double* __restrict__ rho) {
+  __shared__ double red[8];
+  const int64_t k = blockIdx.x;
+  const double* row = Ut + k * n;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += row[i] * b[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    rho[k] = t;
+  }
+}
+
+// coef[k] = lambda_k^+ * rho[k];  lambda^+ = 1/(lambda (1 + (tol/|lambda|)^6)), 0 where lambda == 0
+__global__ void __launch_bounds__(1024) pinv_coef_kernel(const double* __restrict__ evals, int64_t n, double rtol,
+                                                         double atol, double* __restrict__ rho) {
+  __shared__ double red[32];
+  __shared__ double bc;
+  double mx = 0.0;
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) mx = fmax(mx, fabs(evals[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    if (threadIdx.x == 0) bc = mx;
+  }
+  __syncthreads();
+  const double tol = rtol * bc + atol;
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+    double v = evals[k], a = fabs(v);
+    double q = tol / a;
+    double q2 = q * q;
+    double f = 1.0 + q2 * q2 * q2;
+    double inv = 1.0 / (v * f);
+    rho[k] = (a > 0.0) ? inv * rho[k] : 0.0;
+  }
+}
+
+// y[i] = sum_k Ut[k, i] coef[k]: thread per column i, rows split over grid.y
+__global__ void __launch_bounds__(256) cols_comb_kernel(const double* __restrict__ Ut, int64_t n,
+                                                        const double* __restrict__ coef, double* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t chunk = (n + gridDim.y - 1) / gridDim.y;
+  int64_t k0 = blockIdx.y * chunk, k1 = k0 + chunk < n ? k0 + chunk : n;
+  double acc = 0.0;
+  for (int64_t k = k0; k < k1; ++k) acc += Ut[k * n + i] * coef[k];
+  atomicAdd(y + i, acc);
+}
+
+}  // namespace qtx
+
+using namespace qtx;
+
+static int syevd_lwork(int64_t n, int* lwork) {
+  cusolverDnHandle_t h;
+  int rc = solver_handle(&h);
+  if (rc) return rc;
+  cusolverStatus_t s =
+      cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, nullptr, (int)n,
+                                  nullptr, lwork);
+  if (s != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cusolverDnDsyevd_bufferSize failed with status %d", (int)s);
+    return QTX_ERR_SOLVER;
+  }
+  return QTX_OK;
+}
+
+extern "C" size_t qtx_pinv_eig_workspace_size(int64_t n) {
+  int lwork = 0;
+  if (n <= 0 || n > 46340 || syevd_lwork(n, &lwork)) return 0;
+  // [lwork doubles | evals n | rho n]
+  return ((size_t)lwork + 2 * (size_t)n) * sizeof(double) + 256;
+}
+
+extern "C" int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double rtol, double atol, double* evals_out,
+                                  double* y_out, int32_t* info_out, void* workspace, size_t workspace_bytes,
+                                  qtx_stream_t stream) {
+  QTX_REQUIRE(T && b && y_out && info_out && workspace && n > 0 && n <= 46340, QTX_ERR_INVALID,
+              "qtx_pinv_eig_solve: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cusolverDnHandle_t h;
+  int rc = solver_handle(&h);
+  if (rc) return rc;
+  int lwork = 0;
+  rc = syevd_lwork(n, &lwork);
+  if (rc) return rc;
+  QTX_REQUIRE(workspace_bytes >= ((size_t)lwork + 2 * (size_t)n) * sizeof(double), QTX_ERR_INVALID,
+              "qtx_pinv_eig_solve: workspace too small");
+  double* work = (double*)workspace;
+  double* evals = work + lwork;
+  double* rho = evals + n;
+  if (rtol < 0) rtol = 1e-12;  // solver.py:12-21 for float64
+  cusolverStatus_t s = cusolverDnSetStream(h, st);
+  QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnSetStream failed (%d)", (int)s);
+  // row-major symmetric == column-major symmetric; on exit T holds column-major eigenvectors,
+  // i.e. row k of the buffer is eigenvector k.
+  s = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, T, (int)n, evals, work, lwork,
+                       info_out);
+  QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnDsyevd failed (%d)", (int)s);
+  count_launch();
+  rows_dot_kernel<<<(unsigned)n, 256, 0, st>>>(T, n, b, rho);
+  QTX_LAUNCH_CHECK();
+  pinv_coef_kernel<<<1, 1024, 0, st>>>(evals, n, rtol, atol, rho);
+  QTX_LAUNCH_CHECK();
+  QTX_CUDA(cudaMemsetAsync(y_out, 0, n * sizeof(double), st));
+  unsigned gx = (unsigned)((n + 255) / 256);
+  int64_t split = (4ll * num_sms() + gx - 1) / gx;
+  if (split > n) split = n;
+  if (split < 1) split = 1;
+  cols_comb_kernel<<<dim3(gx, (unsigned)split), 256, 0, st>>>(T, n, rho, y_out);
+  QTX_LAUNCH_CHECK();
+  if (evals_out) QTX_CUDA(cudaMemcpyAsync(evals_out, evals, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return QTX_OK;
+}

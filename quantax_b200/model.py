@@ -1,0 +1,158 @@
+"""Variational ansaetze of the hot path: RBM_Dense and ResConv parameter containers.
+
+Mirrors quantax/model/shallow_nets.py:111-126 (RBM_Dense) and quantax/model/conv_nets.py:95-183
+(ResConv).  A model owns ONE flat parameter vector on the device, laid out in the reference's
+``ravel_pytree`` order (quantax/state/variational.py:236-243), so the Jacobian columns, the SR
+step and ``Variational.update`` address parameters exactly as the reference does:
+  RBM_Dense : [W.ravel() (M x N row-major), b (M)]
+  ResConv   : per block conv1.weight [C,Cin,kh,kw], conv1.bias [C], conv2.weight, conv2.bias
+              (the last conv has no bias, conv_nets.py:66,75).
+All arithmetic happens in the CUDA kernels; these classes only hold parameters and metadata.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .global_defs import device, get_lattice, get_sites, get_subkeys
+
+_TRUNC_STD = 0.87962566103423978  # std of a unit normal truncated to [-2, 2] (jax.nn.initializers)
+
+
+def _truncated_normal(rng, shape):
+    out = rng.standard_normal(shape)
+    bad = np.abs(out) > 2
+    while bad.any():
+        out[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(out) > 2
+    return out / _TRUNC_STD
+
+
+def _get_scale(features: int, nsites: int) -> float:
+    """Scalar in [0, 0.99] such that std(sum_i log|cosh(scale*x_i)|) over 1000 Gaussian inputs is
+    closest to 0.1*sqrt(N) (quantax/model/shallow_nets.py:17-32; the jax key(0) stream is not
+    reproduced, a fixed NumPy stream is used instead)."""
+    x = np.random.default_rng(0).standard_normal((1000, features))
+    target = 0.1 * np.sqrt(nsites)
+    best, arg = np.inf, 0.0
+    for scale in np.arange(0, 1, 0.01):
+        out = np.sum(np.log(np.abs(np.cosh(x * scale))), axis=1)
+        err = (np.std(out) - target) ** 2
+        if err < best:
+            best, arg = err, scale
+    return float(arg)
+
+
+class RBM_Dense:
+    r"""psi(s) = prod_i cosh(W s + b)  (quantax/model/shallow_nets.py:111-126)."""
+
+    is_ref_model = True  # quantax.nn.RefModel: supports init_internal / ref_forward
+    kind = "rbm"
+
+    def __init__(self, features: int, use_bias: bool = True, dtype=torch.float32, params: Optional[torch.Tensor] = None):
+        if dtype not in (torch.float32, torch.float64):
+            raise NotImplementedError("complex RBM parameters are outside the B200 hot path")
+        if not use_bias:
+            raise NotImplementedError("RBM_Dense(use_bias=False) is not implemented")
+        sites = get_sites()
+        self.N = sites.Nmodes
+        self.M = int(features)
+        self.dtype = dtype
+        self.holomorphic = False
+        if params is None:
+            rng = np.random.default_rng(get_subkeys() & 0xFFFFFFFF)
+            w = _truncated_normal(rng, (self.M, self.N)) / np.sqrt(self.N)  # LeCun normal, fan_in = N
+            w *= _get_scale(self.M, sites.Nsites)
+            flat = np.concatenate([w.ravel(), np.zeros(self.M)])
+            params = torch.from_numpy(flat).to(device=device(), dtype=dtype)
+        self.params = params.to(device=device(), dtype=dtype).contiguous()
+        assert self.params.numel() == self.M * self.N + self.M
+
+    @property
+    def nparams(self) -> int:
+        return self.M * self.N + self.M
+
+    @property
+    def W(self) -> torch.Tensor:
+        return self.params[: self.M * self.N].view(self.M, self.N)
+
+    @property
+    def b(self) -> torch.Tensor:
+        return self.params[self.M * self.N:]
+
+
+class ResConv:
+    """Deep convolutional residual network (quantax/model/conv_nets.py:95-183)."""
+
+    is_ref_model = False
+    kind = "resconv"
+
+    def __init__(self, nblocks: int, channels: int, kernel_size: int, final_activation=None, trans_symm=None,
+                 dtype=torch.float32, out_dtype=None, params: Optional[torch.Tensor] = None):
+        from . import nn
+
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("`ResSum` doesn't support complex dtypes.")
+        if out_dtype is not None and out_dtype != dtype:
+            raise NotImplementedError("complex / mixed out_dtype is outside the B200 hot path of this round")
+        if trans_symm is not None:
+            raise NotImplementedError("only the default translation symmetry (sector 0) is implemented")
+        lattice = get_lattice()
+        if not all(bc != 0 for bc in lattice.boundary):
+            raise NotImplementedError("open boundaries are outside the B200 hot path")
+        if lattice.ndim > 2:
+            raise NotImplementedError("3D lattices are not implemented")
+        if isinstance(kernel_size, (tuple, list)):
+            raise NotImplementedError("anisotropic kernels are not implemented")
+        if kernel_size % 2 != 1:
+            raise NotImplementedError("even kernel sizes are not implemented")
+        self.nblocks, self.channels, self.kernel_size = int(nblocks), int(channels), int(kernel_size)
+        if final_activation is None:
+            final_activation = nn.exp_by_scale
+        if final_activation is nn.exp_by_scale:
+            self.final = 0
+        elif final_activation is nn.sinhp1_by_scale:
+            self.final = 1
+        else:
+            raise NotImplementedError("final_activation must be exp_by_scale or sinhp1_by_scale")
+        self.final_activation = final_activation
+        self.dtype = dtype
+        self.holomorphic = False
+        ext = lattice.shape[1:]
+        self.Lx, self.Ly = (1, ext[0]) if len(ext) == 1 else (ext[0], ext[1])
+        self.kh = 1 if self.Lx == 1 and len(ext) == 1 else self.kernel_size
+        self.kw = self.kernel_size
+        self.N = lattice.Nsites
+        # parameter layout
+        self.layout = []  # (name, offset, shape)
+        off = 0
+        for i in range(self.nblocks):
+            for name, cin, last in (("conv1", 1 if i == 0 else self.channels, False),
+                                    ("conv2", self.channels, i == self.nblocks - 1)):
+                shape = (self.channels, cin, self.kh, self.kw)
+                self.layout.append((f"block{i}.{name}.weight", off, shape))
+                off += int(np.prod(shape))
+                if not last:
+                    self.layout.append((f"block{i}.{name}.bias", off, (self.channels,)))
+                    off += self.channels
+        self._nparams = off
+        if params is None:
+            rng = np.random.default_rng(get_subkeys() & 0xFFFFFFFF)
+            flat = np.zeros(off)
+            for name, o, shape in self.layout:
+                if name.endswith("weight"):
+                    fan_in = shape[1] * shape[2] * shape[3]  # He normal (conv_nets.py:71)
+                    flat[o:o + int(np.prod(shape))] = (_truncated_normal(rng, shape) * np.sqrt(2.0 / fan_in)).ravel()
+            params = torch.from_numpy(flat)
+        self.params = params.to(device=device(), dtype=dtype).contiguous()
+        assert self.params.numel() == off
+
+    @property
+    def nparams(self) -> int:
+        return self._nparams
+
+    def named_parameters(self):
+        for name, o, shape in self.layout:
+            yield name, self.params[o:o + int(np.prod(shape))].view(shape)

@@ -1,0 +1,313 @@
+"""Stochastic reconfiguration (SR / MinSR) and its linear solvers.
+
+Mirrors quantax/optimizer/sr.py:17-195 (``QNGD``, ``SR``) and quantax/optimizer/solver.py:94-294
+(``auto_pinv_eig``, ``minnorm_pinv_eig``, ``lstsq_pinv_eig``, ``minsr_pinv_eig``).  ``MinSR`` is
+the pre-0.2 name of ``SR`` with the min-norm solver forced.
+
+Data-parallel layout (one process per GPU): each rank owns ``Ns / P`` rows of the Jacobian.
+Cross-rank traffic is exactly the reference's implicit GSPMD traffic made explicit:
+  * all-gather of the local energies (Ns float64),
+  * all-reduce of the Jacobian column means ([Np]),
+  * row-sharded -> column-sharded exchange of Obar (all-to-all, solver.py:134-137),
+  * all-reduce of the partial Gram matrices (solver.py:139),
+  * all-gather of the column shards of the step (solver.py:146).
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib
+from .global_defs import device, get_default_dtype, world
+from .state import VS_TYPE, Variational
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+class _Workspaces:
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key: str, nbytes: int) -> torch.Tensor:
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device())
+            self._bufs[key] = buf
+        return buf
+
+
+_WS = _Workspaces()
+
+# Gram algorithm: 0 = tcgen05 int8-sliced tensor-core kernel with the dtype's default slice count,
+# k > 0 = k slices, -1 = FP64 FMA cross-check kernel.  QTX_GRAM_NSLICES overrides (dev knob).
+DEFAULT_NSLICES = int(os.environ.get("QTX_GRAM_NSLICES", "-1"))
+
+
+# ---- dense building blocks -----------------------------------------------------------------------
+def gram(A: torch.Tensor, out: Optional[torch.Tensor] = None, nslices: Optional[int] = None, accumulate: bool = False):
+    """T = A A^T (float64 [ns, ns]) on the tensor cores (qtx_gram)."""
+    if nslices is None:
+        nslices = DEFAULT_NSLICES
+    ns, npar = A.shape
+    if out is None:
+        out = torch.empty((ns, ns), dtype=torch.float64, device=A.device)
+    dt = _lib.dtype_code(A.dtype)
+    wsz = _lib.lib().qtx_gram_workspace_size(dt, ns, npar, nslices)
+    ws = _WS.get("gram", wsz)
+    _lib.call("qtx_gram", dt, _lib.ptr(A), ns, npar, A.stride(0), int(nslices), _lib.ptr(out), int(accumulate),
+              _lib.ptr(ws), wsz, _lib.stream())
+    return out
+
+
+def pinv_eig_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol: float, want_evals: bool = False):
+    """y = U (lambda^+ o U^T b) from eigh(T); T is overwritten by the eigenvectors (qtx_pinv_eig_solve)."""
+    n = T.shape[0]
+    y = torch.empty(n, dtype=torch.float64, device=T.device)
+    evals = torch.empty(n, dtype=torch.float64, device=T.device) if want_evals else None
+    info = torch.empty(1, dtype=torch.int32, device=T.device)
+    wsz = _lib.lib().qtx_pinv_eig_workspace_size(n)
+    if wsz == 0:
+        raise _lib.QtxError(f"qtx_pinv_eig_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
+    ws = _WS.get("eig", wsz)
+    _lib.call("qtx_pinv_eig_solve", _lib.ptr(T), n, _lib.ptr(b.contiguous()), -1.0 if rtol is None else float(rtol),
+              float(atol), _lib.ptr(evals), _lib.ptr(y), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+    return (y, evals, info) if want_evals else (y, info)
+
+
+def matvec_t(A: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """x = A^T y (float64 [np])."""
+    ns, npar = A.shape
+    x = torch.empty(npar, dtype=torch.float64, device=A.device)
+    _lib.call("qtx_matvec_t", _lib.dtype_code(A.dtype), _lib.ptr(A), ns, npar, A.stride(0), _lib.ptr(y.contiguous()),
+              _lib.ptr(x), 0, _lib.stream())
+    return x
+
+
+def matvec(A: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    ns, npar = A.shape
+    v = torch.empty(ns, dtype=torch.float64, device=A.device)
+    _lib.call("qtx_matvec", _lib.dtype_code(A.dtype), _lib.ptr(A), ns, npar, A.stride(0), _lib.ptr(x.contiguous()),
+              _lib.ptr(v), _lib.stream())
+    return v
+
+
+# ---- solvers (callables (A, b) -> x; A is the rank-local row block of Obar) -----------------------
+def _check_snr(tol_snr: float):
+    if tol_snr > 1e-6:
+        raise NotImplementedError("SNR regularisation (tol_snr > 0) is not implemented")
+
+
+def minnorm_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0, nslices: Optional[int] = None):
+    """x = A^+ b through T = A A^+ (MinSR, solver.py:128-149)."""
+    _check_snr(tol_snr)
+
+    def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        rank, P = world()
+        if P == 1:
+            T = gram(A, nslices=nslices)
+            y, info = pinv_eig_solve(T, b, rtol, atol)
+            solve.last_info = info
+            return matvec_t(A, y)
+        dist = _dist()
+        nl, npar = A.shape
+        npc = (npar + P - 1) // P  # array_extend(Adag, ndevices): pad the parameter axis (solver.py:136)
+        send = torch.zeros((P, nl, npc), dtype=A.dtype, device=A.device)
+        if npc * P == npar:
+            send.copy_(A.view(nl, P, npc).permute(1, 0, 2))
+        else:
+            flat = torch.zeros((nl, P * npc), dtype=A.dtype, device=A.device)
+            flat[:, :npar] = A
+            send.copy_(flat.view(nl, P, npc).permute(1, 0, 2))
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)  # row-sharded -> column-sharded
+        Ac = recv.view(P * nl, npc)
+        T = gram(Ac, nslices=nslices)
+        dist.all_reduce(T)
+        bfull = torch.empty(P * nl, dtype=torch.float64, device=A.device)
+        dist.all_gather_into_tensor(bfull, b.contiguous())
+        y, info = pinv_eig_solve(T, bfull, rtol, atol)
+        solve.last_info = info
+        xc = matvec_t(Ac, y)
+        x = torch.empty(P * npc, dtype=torch.float64, device=A.device)
+        dist.all_gather_into_tensor(x, xc)
+        return x[:npar].contiguous()
+
+    solve.last_info = None
+    return solve
+
+
+def lstsq_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0, nslices: Optional[int] = None):
+    """x = (A^+ A)^-1 A^+ b through S = A^+ A (SR, solver.py:152-164)."""
+    _check_snr(tol_snr)
+
+    def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        rank, P = world()
+        At = A.t().contiguous()  # [np, nl]: S = At At^T sums over the local samples
+        S = gram(At, nslices=nslices)
+        F = matvec_t(A, b)
+        if P > 1:
+            _dist().all_reduce(S)
+            _dist().all_reduce(F)
+        x, info = pinv_eig_solve(S, F, rtol, atol)
+        solve.last_info = info
+        return x
+
+    solve.last_info = None
+    return solve
+
+
+def auto_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0, nslices: Optional[int] = None):
+    """SR when Ns >= Np, MinSR otherwise (solver.py:167-201); Ns is the GLOBAL sample count."""
+    mn = minnorm_pinv_eig(rtol, atol, tol_snr, nslices)
+    ls = lstsq_pinv_eig(rtol, atol, tol_snr, nslices)
+
+    def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        _, P = world()
+        return mn(A, b) if A.shape[0] * P < A.shape[1] else ls(A, b)
+
+    return solve
+
+
+def minsr_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0):
+    """Solver of T x = b for a given Hermitian T (solver.py:262-294)."""
+    _check_snr(tol_snr)
+
+    def solve(T: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        y, _ = pinv_eig_solve(T.clone(), b, rtol, atol)
+        return y
+
+    return solve
+
+
+# ---- optimizers ---------------------------------------------------------------------------------
+class QNGD:
+    """Quantum natural gradient descent base class (sr.py:17-128)."""
+
+    def __init__(self, state: Variational, imag_time: bool = True, solver: Optional[Callable] = None):
+        if not imag_time:
+            raise NotImplementedError("real-time evolution needs a complex default dtype (outside the hot path)")
+        self._state = state
+        self._imag_time = imag_time
+        self._solver = auto_pinv_eig() if solver is None else solver
+        self._Omean = None
+        self.timers = None  # optional dict name -> [(start_event, end_event)]
+
+    state = property(lambda self: self._state)
+    holomorphic = property(lambda self: False)
+    vs_type = property(lambda self: self._state.vs_type)
+    imag_time = property(lambda self: self._imag_time)
+
+    def _tic(self, name):
+        if self.timers is None:
+            return None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        self.timers.setdefault(name, []).append(ev)
+        return ev
+
+    @staticmethod
+    def _toc(ev):
+        if ev is not None:
+            ev[1].record()
+
+    def get_Ebar(self, samples) -> torch.Tensor:
+        raise NotImplementedError
+
+    def get_Obar(self, samples) -> torch.Tensor:
+        r"""Obar = (O - <O>) sqrt(rw / Ns) for the rank-local samples (sr.py:79-88)."""
+        rank, P = world()
+        state = self._state
+        ns_glob = samples.nsamples * P
+        rw = samples.reweight_factor
+        scale = torch.sqrt(rw / ns_glob)
+        ev = self._tic("jacobian")
+        mean = state.jacobian_colmean(samples.spins)
+        if mean is not None:
+            # one-pass path: column means first (without materialising O), then write Obar directly
+            if P > 1:
+                _dist().all_reduce(mean)
+                mean /= P
+            self._Omean = mean  # == mean(O * rw) for reweight 2 (rw = 1)
+            Obar = state.jacobian(samples.spins, col_mean=mean, row_scale=scale)
+        else:
+            Omat = state.jacobian(samples.spins)
+            mean = torch.empty(Omat.shape[1], dtype=torch.float64, device=Omat.device)
+            dt = _lib.dtype_code(Omat.dtype)
+            _lib.call("qtx_colmean", dt, _lib.ptr(Omat), Omat.shape[0], Omat.shape[1], Omat.stride(0), None,
+                      _lib.ptr(mean), _lib.stream())
+            if P > 1:
+                _dist().all_reduce(mean)
+                mean /= P
+            self._Omean = mean
+            _lib.call("qtx_center_scale", dt, _lib.ptr(Omat), Omat.shape[0], Omat.shape[1], Omat.stride(0),
+                      _lib.ptr(mean), _lib.ptr(scale), _lib.stream())
+            Obar = Omat
+        self._toc(ev)
+        return Obar
+
+    def solve(self, Obar: torch.Tensor, Ebar: torch.Tensor) -> torch.Tensor:
+        """Solve Obar x = Ebar (sr.py:90-113, real parameters / real output)."""
+        ev = self._tic("solve")
+        step = self._solver(Obar, Ebar)
+        self._toc(ev)
+        return step.to(get_default_dtype())
+
+    def get_step(self, samples) -> torch.Tensor:
+        Ebar = self.get_Ebar(samples)
+        Obar = self.get_Obar(samples)
+        return self.solve(Obar, Ebar)
+
+
+class SR(QNGD):
+    """Stochastic reconfiguration; picks SR or MinSR by shape (sr.py:131-195)."""
+
+    def __init__(self, state: Variational, hamiltonian, imag_time: bool = True, solver: Optional[Callable] = None):
+        super().__init__(state, imag_time, solver)
+        self._hamiltonian = hamiltonian
+        self._stats = None
+
+    hamiltonian = property(lambda self: self._hamiltonian)
+
+    @property
+    def energy(self) -> Optional[float]:
+        return None if self._stats is None else float(self._stats[0].item())
+
+    @property
+    def VarE(self) -> Optional[float]:
+        return None if self._stats is None else float(self._stats[1].item())
+
+    def get_Ebar(self, samples) -> torch.Tensor:
+        r"""Ebar = (Eloc - <Eloc>) sqrt(rw / Ns); also stores energy and VarE (sr.py:180-195)."""
+        rank, P = world()
+        ev = self._tic("oloc")
+        Eloc = self._hamiltonian.Oloc(self._state, samples).to(torch.float64)
+        self._toc(ev)
+        rw = samples.reweight_factor
+        nl = Eloc.shape[0]
+        if P > 1:
+            full = torch.empty(nl * P, dtype=torch.float64, device=Eloc.device)
+            _dist().all_gather_into_tensor(full, Eloc.contiguous())
+            rwf = torch.empty(nl * P, dtype=torch.float64, device=Eloc.device)
+            _dist().all_gather_into_tensor(rwf, rw.contiguous())
+            Eloc, rw = full, rwf
+        ebar = torch.empty_like(Eloc)
+        stats = torch.empty(2, dtype=torch.float64, device=Eloc.device)
+        _lib.call("qtx_ebar", _lib.ptr(Eloc), _lib.ptr(rw.contiguous()), Eloc.shape[0], _lib.ptr(ebar),
+                  _lib.ptr(stats), _lib.stream())
+        self._stats = stats
+        self._Eloc = Eloc
+        return ebar[rank * nl:(rank + 1) * nl].contiguous() if P > 1 else ebar
+
+
+class MinSR(SR):
+    """SR with the min-norm (Ns x Ns) solver forced -- the name used by BASELINE.json and by
+    older quantax releases (docs/.doctrees/optimizer/quantax.optimizer.MinSR)."""
+
+    def __init__(self, state: Variational, hamiltonian, imag_time: bool = True, solver: Optional[Callable] = None):
+        super().__init__(state, hamiltonian, imag_time, minnorm_pinv_eig() if solver is None else solver)

@@ -1,0 +1,257 @@
+"""Variational state: psi(s), cached internals, local updates, per-sample log-derivatives.
+
+Mirrors quantax/state/variational.py:97-587 (``Variational``) and the ``State`` protocol of
+quantax/state/state.py:19-161 for the models of the hot path.  Every method routes to the C ABI
+(include/qtx_b200.h); there is no PyTorch implementation of the arithmetic.
+"""
+from __future__ import annotations
+
+from enum import Enum
+from typing import Optional, Tuple
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _lib
+from .global_defs import device, get_default_dtype, get_sites
+from .utils import LogArray, ScaleArray
+
+
+class VS_TYPE(Enum):
+    """quantax/state/variational.py:40-94."""
+
+    real_or_holomorphic = 0
+    non_holomorphic = 1
+    real_to_complex = 2
+
+
+class State:
+    """Abstract state (quantax/state/state.py:19-100): default no-op internals."""
+
+    def __init__(self, symm=None):
+        if symm is not None:
+            raise NotImplementedError("state-level symmetry projection is not implemented in this round")
+        sites = get_sites()
+        self._Nsites, self._Nmodes = sites.Nsites, sites.Nmodes
+
+    Nsites = property(lambda self: self._Nsites)
+    Nmodes = property(lambda self: self._Nmodes)
+    use_ref = property(lambda self: False)
+
+    def init_internal(self, s):
+        return None
+
+
+class Variational(State):
+    def __init__(self, model, param_file=None, symm=None, max_parallel=None, use_ref: bool = True):
+        super().__init__(symm)
+        self._model = model
+        if param_file is not None:
+            self.load(param_file)
+        if max_parallel is None or isinstance(max_parallel, int):
+            self._forward_chunk = self._backward_chunk = self._ref_chunk = max_parallel
+        elif len(max_parallel) == 2:
+            self._forward_chunk, self._backward_chunk = max_parallel
+            self._ref_chunk = self._forward_chunk
+        else:
+            self._forward_chunk, self._backward_chunk, self._ref_chunk = max_parallel
+        self._use_ref = bool(use_ref) and getattr(model, "is_ref_model", False)
+        self._vs_type = VS_TYPE.real_or_holomorphic
+        self._ws = {}
+
+    # ---- properties (variational.py:180-226) ------------------------------------------------
+    use_ref = property(lambda self: self._use_ref)
+    model = property(lambda self: self._model)
+    holomorphic = property(lambda self: False)
+    forward_chunk = property(lambda self: self._forward_chunk)
+    backward_chunk = property(lambda self: self._backward_chunk)
+    ref_chunk = property(lambda self: self._ref_chunk)
+    nparams = property(lambda self: self._model.nparams)
+    dtype = property(lambda self: self._model.dtype)
+    vs_type = property(lambda self: self._vs_type)
+
+    def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device())
+            self._ws[key] = buf
+        return buf
+
+    def _mdt(self) -> int:
+        return _lib.dtype_code(self._model.dtype)
+
+    @staticmethod
+    def _spins(s) -> torch.Tensor:
+        from .operator import _as_spins
+
+        return _as_spins(s)
+
+    # ---- forward (variational.py:325-347) -----------------------------------------------------
+    def __call__(self, s):
+        s = self._spins(s).reshape(-1, self.Nmodes)
+        m = self._model
+        ns = s.shape[0]
+        if m.kind == "rbm":
+            logabs = torch.empty(ns, dtype=torch.float64, device=s.device)
+            _lib.call("qtx_rbm_forward", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
+                      None, _lib.ptr(logabs), _lib.stream())
+            return LogArray(torch.ones_like(logabs), logabs)
+        from .resconv import resconv_forward
+
+        return resconv_forward(self, s)
+
+    def init_internal(self, s):
+        """theta = W s + b for RefModels, None otherwise (variational.py:349-356)."""
+        if not self._use_ref:
+            return None
+        s = self._spins(s)
+        m = self._model
+        theta = torch.empty((s.shape[0], m.M), dtype=m.dtype, device=s.device)
+        _lib.call("qtx_rbm_forward", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), s.shape[0],
+                  _lib.ptr(theta), None, _lib.stream())
+        return theta
+
+    def ref_forward(self, s, s_old, nflips: int, idx_segment, internal):
+        """psi of configurations `s` that differ from s_old[idx_segment] by `nflips` flips
+        (variational.py:387-422)."""
+        s = self._spins(s)
+        if not self._use_ref:
+            return self(s)
+        m = self._model
+        s_old = self._spins(s_old)
+        if internal is None:
+            internal = self.init_internal(s_old)
+        seg = idx_segment.to(device=s.device, dtype=torch.int32).contiguous()
+        logabs = torch.empty(s.shape[0], dtype=torch.float64, device=s.device)
+        _lib.call("qtx_rbm_ref_forward", self._mdt(), _lib.ptr(m.W), m.N, m.M, _lib.ptr(internal.contiguous()),
+                  _lib.ptr(s_old), s_old.shape[0], _lib.ptr(s), _lib.ptr(seg), s.shape[0], int(nflips),
+                  _lib.ptr(logabs), _lib.stream())
+        return LogArray(torch.ones_like(logabs), logabs)
+
+    def ref_forward_with_updates(self, s, s_old, nflips: int, internal):
+        """One proposal for every chain (variational.py:358-385).  The persistent sweep kernel
+        (``fused_sweep``) replaces the per-step use of this method; it is kept for API parity."""
+        s = self._spins(s)
+        if not self._use_ref:
+            return self(s), None
+        seg = torch.arange(s.shape[0], dtype=torch.int32, device=s.device)
+        psi = self.ref_forward(s, s_old, nflips, seg, internal)
+        return psi, self.init_internal(s)
+
+    # ---- fused hot-path entry points ------------------------------------------------------------
+    def fused_sweep(self, spins: torch.Tensor, nsweeps: int, kind: int, nbr, max_nb: int, hop: int, reweight: float,
+                    seed: int, step0: int, chain0: int, injected=None, record: bool = False):
+        """Whole Metropolis sweep in one launch (RBM) -- see qtx_rbm_sweep."""
+        m = self._model
+        if m.kind != "rbm":
+            from .resconv import resconv_sweep
+
+            return resconv_sweep(self, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed, step0, chain0,
+                                 injected, record)
+        ns = spins.shape[0]
+        dev = spins.device
+        logabs = torch.empty(ns, dtype=torch.float64, device=dev)
+        logabs_chain = torch.empty(ns, dtype=torch.float64, device=dev)
+        nacc = torch.empty(ns, dtype=torch.int32, device=dev)
+        log = torch.empty((nsweeps, ns), dtype=torch.uint8, device=dev) if record else None
+        wsz = _lib.lib().qtx_rbm_workspace_size(self._mdt(), m.N, m.M)
+        ws = self._workspace("rbm", wsz)
+        pos = slot = u = None
+        if injected is not None:
+            pos, slot, u = injected
+            pos = pos.to(device=dev, dtype=torch.int32).contiguous()
+            slot = None if slot is None else slot.to(device=dev, dtype=torch.int32).contiguous()
+            u = u.to(device=dev, dtype=torch.float64).contiguous()
+        _lib.call("qtx_rbm_sweep", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(spins), ns,
+                  int(nsweeps), int(kind), _lib.ptr(nbr), int(max_nb), int(hop), float(reweight), _lib.ptr(pos),
+                  _lib.ptr(slot), _lib.ptr(u), int(seed) & 0xFFFFFFFFFFFFFFFF, int(step0), int(chain0),
+                  _lib.ptr(logabs), _lib.ptr(logabs_chain), _lib.ptr(nacc), _lib.ptr(log), _lib.ptr(ws), wsz,
+                  _lib.stream())
+        one = torch.ones_like(logabs)
+        return LogArray(one, logabs), LogArray(one, logabs_chain), nacc, log
+
+    @property
+    def fused_oloc(self):
+        """Fused local-energy kernel when the model supports local updates, else None."""
+        if self._model.kind == "rbm" and self._use_ref:
+            return self._rbm_oloc
+        return None
+
+    def _rbm_oloc(self, operator, s: torch.Tensor) -> torch.Tensor:
+        m = self._model
+        t = operator.term_table
+        ns = s.shape[0]
+        eloc = torch.empty(ns, dtype=torch.float64, device=s.device)
+        nconn = torch.empty(ns, dtype=torch.int32, device=s.device)
+        wsz = _lib.lib().qtx_rbm_workspace_size(self._mdt(), m.N, m.M)
+        ws = self._workspace("rbm", wsz)
+        _lib.call("qtx_rbm_oloc", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
+                  _lib.ptr(t.coef), _lib.ptr(t.sites), _lib.ptr(t.ops), t.nterms, _lib.ptr(eloc), _lib.ptr(nconn),
+                  _lib.ptr(ws), wsz, _lib.stream())
+        operator._connectivity = nconn
+        return eloc
+
+    # ---- jacobian (variational.py:424-511) ----------------------------------------------------
+    def jacobian(self, fock_states, out: Optional[torch.Tensor] = None, col_mean=None, row_scale=None):
+        r"""O[s, k] = (1/psi) d psi / d theta_k, [ns, nparams] in the default dtype; column order =
+        ``get_params_flatten``.  With ``col_mean`` / ``row_scale`` the centred and scaled matrix
+        Obar of sr.py:74-88 is written directly."""
+        s = self._spins(fock_states)
+        m = self._model
+        ns = s.shape[0]
+        odt = get_default_dtype()
+        if out is None:
+            out = torch.empty((ns, m.nparams), dtype=odt, device=s.device)
+        if m.kind == "rbm":
+            _lib.call("qtx_rbm_jacobian", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
+                      _lib.dtype_code(out.dtype), _lib.ptr(out), out.stride(0), _lib.ptr(col_mean),
+                      _lib.ptr(row_scale), _lib.stream())
+            return out
+        from .resconv import resconv_jacobian
+
+        resconv_jacobian(self, s, out)
+        if col_mean is not None or row_scale is not None:
+            _lib.call("qtx_center_scale", _lib.dtype_code(out.dtype), _lib.ptr(out), ns, m.nparams, out.stride(0),
+                      _lib.ptr(col_mean), _lib.ptr(row_scale), _lib.stream())
+        return out
+
+    def jacobian_colmean(self, fock_states, weight=None) -> Optional[torch.Tensor]:
+        """Column mean of the Jacobian without materialising it (RBM), else None."""
+        m = self._model
+        if m.kind != "rbm":
+            return None
+        s = self._spins(fock_states)
+        ns = s.shape[0]
+        mean = torch.empty(m.nparams, dtype=torch.float64, device=s.device)
+        wsz = _lib.lib().qtx_rbm_colmean_workspace_size(self._mdt(), m.N, m.M, ns)
+        ws = self._workspace("colmean", wsz)
+        _lib.call("qtx_rbm_jacobian_colmean", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
+                  _lib.ptr(weight), _lib.ptr(mean), _lib.ptr(ws), wsz, _lib.stream())
+        return mean
+
+    # ---- parameters (variational.py:545-587) ----------------------------------------------------
+    def get_params_flatten(self) -> torch.Tensor:
+        return self._model.params
+
+    def update(self, step: torch.Tensor, lr: float = 1.0) -> None:
+        r"""theta' = theta - step (skipped, with a warning, when the step is not finite)."""
+        step = step.to(device=device(), dtype=torch.float64).contiguous()
+        flag = torch.empty(1, dtype=torch.int32, device=step.device)
+        _lib.call("qtx_apply_update", self._mdt(), _lib.ptr(self._model.params), _lib.ptr(step), float(lr),
+                  step.numel(), _lib.ptr(flag), _lib.stream())
+        self._last_update_flag = flag  # checked lazily: no host sync on the hot path
+
+    def check_last_update(self) -> bool:
+        flag = getattr(self, "_last_update_flag", None)
+        ok = True if flag is None else bool(flag.item())
+        if not ok:
+            warn("Got invalid update step. The update is interrupted.")
+        return ok
+
+    def save(self, file) -> None:
+        np.save(file, self._model.params.detach().cpu().numpy())
+
+    def load(self, file) -> None:
+        p = torch.from_numpy(np.load(file))
+        self._model.params.copy_(p.to(self._model.params))

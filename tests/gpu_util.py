@@ -1,0 +1,32 @@
+"""Helpers shared by the GPU parity tests (product on cuda:0 vs the CPU oracle)."""
+import numpy as np
+import torch
+
+from oracle import models as omodels, operator as oop, sampler as osmp, sites as osites
+
+
+def make_rbm(qtx, N, M, dtype, seed=0, scale=0.6):
+    """Same random weights in the product model and in the oracle model."""
+    net = omodels.RBM.random(N, M, np.float32 if dtype == torch.float32 else np.float64, seed=seed, scale=scale)
+    flat = torch.from_numpy(net.params().copy())
+    model = qtx.model.RBM_Dense(M, dtype=dtype, params=flat)
+    return model, net
+
+
+def lattice_pair(qtx, kind, L, nparticles=None):
+    qtx.sites.Sites._SITES = None
+    if kind == "chain":
+        return qtx.sites.Chain(L, Nparticles=nparticles), osites.Chain(L, Nparticles=nparticles)
+    if kind == "square":
+        return qtx.sites.Square(L, Nparticles=nparticles), osites.Square(L, Nparticles=nparticles)
+    if kind == "triangular":
+        return qtx.sites.Triangular(L, Nparticles=nparticles), osites.Triangular(L, Nparticles=nparticles)
+    raise ValueError(kind)
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+def chains_equal(a, b):
+    return (np.asarray(a) == np.asarray(b)).all(axis=1)

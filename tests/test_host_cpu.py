@@ -1,0 +1,148 @@
+"""CPU tests of the product's host layer: lattice tables, operator lists, term-table compilation,
+and that the C-ABI library loads and exports every symbol declared in include/qtx_b200.h."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import operator as oop, sites as osites
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_tables.npz"))
+
+
+def _mk(name):
+    from quantax_b200 import sites
+
+    return {
+        "chain8": lambda: sites.Chain(8),
+        "square4": lambda: sites.Square(4, Nparticles=(8, 8)),
+        "square10": lambda: sites.Square(10, Nparticles=(50, 50)),
+        "square16": lambda: sites.Square(16, Nparticles=(128, 128)),
+        "triangular12": lambda: sites.Triangular(12, Nparticles=(72, 72)),
+    }[name]()
+
+
+@pytest.mark.parametrize("name", ["chain8", "square4", "square10", "square16", "triangular12"])
+def test_product_bond_tables_match_reference(name):
+    lat = _mk(name)
+    assert np.allclose(lat.coord, GOLD[f"{name}/coord"])
+    for n in (1, 2):
+        assert np.array_equal(lat.get_neighbor(n), GOLD[f"{name}/nb{n}"])
+    assert [np.array_equal(a, b) for a, b in zip(lat.get_neighbor([1, 2]), [GOLD[f"{name}/nb1"], GOLD[f"{name}/nb2"]])]
+
+
+@pytest.mark.parametrize("name", ["square4", "square10"])
+def test_product_op_lists_match_reference(name):
+    from quantax_b200 import operator
+
+    _mk(name)
+    ops = {"heis": operator.Heisenberg(), "heis_msr": operator.Heisenberg(msr=True),
+           "j1j2_msr": operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)}
+    for oname, op in ops.items():
+        assert [o for o, _ in op.op_list] == list(GOLD[f"{name}/{oname}/names"])
+        J = np.array([t[0] for _, ts in op.op_list for t in ts], dtype=np.float64)
+        assert np.array_equal(J, GOLD[f"{name}/{oname}/J"])
+        idx = [list(t[1:]) for _, ts in op.op_list for t in ts]
+        for a, b in zip(idx, GOLD[f"{name}/{oname}/idx"]):
+            assert a == [v for v in b if v >= 0]
+
+
+def test_product_ising_op_list_matches_reference():
+    from quantax_b200 import operator
+
+    _mk("chain8")
+    op = operator.Ising(h=1.0)
+    assert [o for o, _ in op.op_list] == list(GOLD["chain8/ising_h1/names"])
+    J = np.array([t[0] for _, ts in op.op_list for t in ts])
+    assert np.array_equal(J, GOLD["chain8/ising_h1/J"])
+
+
+def test_operator_algebra():
+    from quantax_b200 import operator as O
+
+    _mk("square4")
+    a = O.sigma_p(0) @ O.sigma_m(1)
+    assert a.op_list == [["+-", [[1.0, 0, 1]]]]
+    assert a.H.op_list == [["+-", [[1.0, 1, 0]]]]  # (S+_0 S-_1)^dagger = S+_1 S-_0 (operator.py:361-375)
+    b = 2 * a + O.sigma_z(2) @ O.sigma_z(3) - a
+    names = [o for o, _ in b.op_list]
+    assert names == ["+-", "zz"]
+    assert [t[0] for t in b.op_list[0][1]] == [2.0, -1.0]
+    with pytest.raises(ValueError):
+        a + 1.0
+    assert (a + 0) is a
+    assert (a / 2).op_list[0][1][0][0] == 0.5
+    assert O.sigma_x(1, 2).op_list == [["x", [[2.0, 6]]]]  # coordinate indexing (site_operator.py:19-32)
+
+
+def test_compile_terms_matches_oracle_semantics():
+    from quantax_b200 import operator as O
+
+    _mk("square4")
+    H = O.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
+    coef, sites, ops, nfl = O.compile_terms(H.op_list)
+    assert coef.shape == (192,) and sites.shape == (192, 4) and ops.shape == (192, 4)
+    assert list(nfl[:128]) == [2] * 128 and list(nfl[128:]) == [0] * 64
+    assert np.array_equal(ops[0], [3, 4, 0, 0]) and np.array_equal(ops[64], [4, 3, 0, 0])
+    assert np.array_equal(ops[128], [1, 1, 0, 0])
+    with pytest.raises(NotImplementedError):
+        O.compile_terms([["y", [[1.0, 0]]]])
+    with pytest.raises(NotImplementedError):
+        O.compile_terms([["+-", [[1.0, 0, 0]]]])
+
+
+def test_site_neighbor_table_matches_oracle():
+    from quantax_b200.sampler import _site_neighbors
+
+    _mk("square10")
+    assert np.array_equal(_site_neighbors(1), osites.site_neighbor_table(osites.Square(10), 1))
+    assert np.array_equal(_site_neighbors([1, 2]), osites.site_neighbor_table(osites.Square(10), [1, 2]))
+
+
+def test_error_behaviour_of_constructors():
+    """Same exceptions as the reference: sampler.py:29-33, common_samplers.py:132-136, sites.py:71-81."""
+    from quantax_b200 import sites
+
+    with pytest.raises(ValueError):
+        sites.Square(4, Nparticles=(8, 7))
+    sites.Sites._SITES = None
+    with pytest.raises(ValueError):
+        sites.Square(4, Nparticles=8)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library must load without a GPU and export exactly the header's entry points."""
+    from quantax_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "qtx_b200.h")).read()
+    declared = set(re.findall(r"\b(qtx_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert os.path.exists(_lib.LIB_PATH), "libqtx_b200.so is not built (run __graft_entry__.build())"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert handle.qtx_abi_version() == 1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "quantax_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_no_cuda_means_loud_failure():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from quantax_b200 import _lib
+
+    with pytest.raises(_lib.QtxError):
+        _lib.ptr(torch.zeros(4))

@@ -1,0 +1,181 @@
+"""Pins the CPU oracle against the reference's own tables (tests/golden/ref_tables.npz, produced by
+tests/golden/make_golden.py from /root/reference) and against the known answers printed in the
+reference tutorials."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import models, operator as oop, sampler as osmp, sites as osites, solver as osolver
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_tables.npz"))
+
+LATTICES = {
+    "chain8": lambda: osites.Chain(8),
+    "square4": lambda: osites.Square(4, Nparticles=(8, 8)),
+    "square6": lambda: osites.Square(6),
+    "square10": lambda: osites.Square(10),
+    "square16": lambda: osites.Square(16),
+    "triangular6": lambda: osites.Triangular(6),
+    "triangular12": lambda: osites.Triangular(12),
+}
+
+
+@pytest.mark.parametrize("name", list(LATTICES))
+def test_bond_tables_match_reference(name):
+    lat = LATTICES[name]()
+    assert np.allclose(lat.coord, GOLD[f"{name}/coord"])
+    for n in (1, 2):
+        assert np.array_equal(lat.get_neighbor(n), GOLD[f"{name}/nb{n}"])
+
+
+def _flat(op_list):
+    J = np.array([t[0] for _, ts in op_list for t in ts], dtype=np.float64)
+    idx = [list(t[1:]) for _, ts in op_list for t in ts]
+    return [o for o, _ in op_list], J, idx
+
+
+@pytest.mark.parametrize("name", list(LATTICES))
+def test_op_lists_match_reference(name):
+    lat = LATTICES[name]()
+    if name == "chain8":
+        ops = {"ising_h1": oop.ising_op_list(lat, h=1.0), "ising_h0.5_J2": oop.ising_op_list(lat, h=0.5, J=2.0)}
+    else:
+        ops = {"heis": oop.heisenberg_op_list(lat), "heis_msr": oop.heisenberg_op_list(lat, msr=True),
+               "j1j2_msr": oop.heisenberg_op_list(lat, J=[1, 0.5], n_neighbor=[1, 2], msr=True)}
+    for oname, ol in ops.items():
+        names, J, idx = _flat(ol)
+        assert names == list(GOLD[f"{name}/{oname}/names"])
+        assert np.array_equal(J, GOLD[f"{name}/{oname}/J"])
+        for a, b in zip(idx, GOLD[f"{name}/{oname}/idx"]):
+            assert a == [v for v in b if v >= 0]
+
+
+def test_ed_energies_of_reference_tutorials():
+    lat = osites.Square(4, Nparticles=(8, 8))
+    e = oop.ed_lowest(oop.to_array_op_list(oop.heisenberg_op_list(lat, msr=True)), 16, nup=8, k=2)
+    assert abs(e[0] - (-44.913932833715506)) < 1e-9  # tutorials/exact_diag.ipynb:191
+    assert abs(e[1] - (-42.599539490653896)) < 1e-9
+    e = oop.ed_lowest(oop.to_array_op_list(oop.heisenberg_op_list(lat, J=[1, 0.5], n_neighbor=[1, 2], msr=True)),
+                      16, nup=8, k=1)
+    assert abs(e[0] - (-33.831693405579394)) < 1e-9  # tutorials/J1J2.ipynb:374
+
+
+def test_local_update_equals_direct_forward():
+    """tutorials/local_updates.ipynb:189,233."""
+    rng = np.random.default_rng(0)
+    net = models.RBM.random(64, 256, np.float64, seed=1)
+    s_old = osmp.rand_states(128, 64, seed=2)
+    theta = net.init_internal(s_old)
+    s_new = s_old.copy()
+    s_new[:, 0] *= -1
+    (sg, la), _ = net.ref_forward(s_new, s_old, 1, theta)
+    sg2, la2 = net.forward(s_new)
+    assert np.allclose(la, la2, rtol=1e-12, atol=1e-12) and np.array_equal(sg, sg2)
+
+
+def test_oloc_local_updates_equals_direct():
+    """tutorials/local_updates.ipynb:354: Oloc through local updates == through full forwards."""
+    lat = osites.Chain(16)
+    H = oop.to_array_op_list(oop.ising_op_list(lat, h=1.0))
+    net = models.RBM.random(16, 32, np.float64, seed=3)
+    s = osmp.rand_states(32, 16, seed=4)
+    direct = oop.oloc(H, net.forward, s)
+    theta = net.init_internal(s)
+    diag = oop.apply_diag(s, H)
+    # local-update path: every flip i, ratio from theta
+    out = diag.copy()
+    la = net.forward(s)[1]
+    for i in range(16):
+        s2 = s.copy()
+        s2[:, i] *= -1
+        (_, la2), _ = net.ref_forward(s2, s, 1, theta)
+        out += -1.0 * np.exp(la2 - la)
+    assert np.allclose(out, direct, rtol=1e-12)
+
+
+def test_variational_energy_is_above_ground_state_and_unbiased():
+    """<Eloc> over exact sampling of |psi|^2 equals <psi|H|psi>/<psi|psi> (4-site chain)."""
+    lat = osites.Chain(4)
+    H = oop.to_array_op_list(oop.ising_op_list(lat, h=0.7))
+    net = models.RBM.random(4, 6, np.float64, seed=5)
+    import itertools
+
+    s = np.array(list(itertools.product([1, -1], repeat=4)), dtype=np.int8)
+    psi = models.dense_value(net.forward(s))
+    E = oop.oloc(H, net.forward, s)
+    evar = np.sum(psi ** 2 * E) / np.sum(psi ** 2)
+    e0 = oop.ed_lowest(H, 4, k=1)[0]
+    assert evar >= e0 - 1e-12
+
+
+def test_resconv_jacobian_finite_differences():
+    rng = np.random.default_rng(1)
+    for final in ("exp", "sinhp1"):
+        net = models.ResConv.random((4, 4), 2, 3, 3, dtype=np.float64, seed=3, final=final, bias_std=0.1)
+        s = rng.choice([-1, 1], size=(2, 16)).astype(np.int8)
+        J = net.jacobian(s)
+        p0 = net.params()
+
+        def setp(p):
+            o = 0
+            for blk in net.blocks:
+                for k in ("w1", "b1", "w2", "b2"):
+                    if blk[k] is not None:
+                        n = blk[k].size
+                        blk[k] = p[o:o + n].reshape(blk[k].shape).copy()
+                        o += n
+
+        def logpsi():
+            m, e = net.forward(s)
+            return np.log(np.abs(m)) + e
+
+        eps = 1e-6
+        for k in rng.choice(p0.size, 40, replace=False):
+            p = p0.copy(); p[k] += eps; setp(p); lp = logpsi()
+            p[k] -= 2 * eps; setp(p); lm = logpsi()
+            assert np.allclose((lp - lm) / (2 * eps), J[:, k], atol=1e-7)
+        setp(p0)
+
+
+def test_philox_known_answer():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    r = osmp.philox4x32(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in r] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    r = osmp.philox4x32(0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(v) for v in r] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    r = osmp.philox4x32(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0)
+    assert [int(v) for v in r] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_solver_minnorm_and_lstsq_agree_with_lstsq():
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((20, 50)); b = rng.standard_normal(20)
+    x = osolver.minnorm_pinv_eig(A, b)
+    assert np.allclose(x, np.linalg.lstsq(A, b, rcond=None)[0], atol=1e-9)
+    A = rng.standard_normal((50, 20)); b = rng.standard_normal(50)
+    x = osolver.lstsq_pinv_eig(A, b)
+    assert np.allclose(x, np.linalg.lstsq(A, b, rcond=None)[0], atol=1e-9)
+
+
+def test_oracle_vmc_converges_to_ed_quick_start():
+    """README quick start (config A): Ising chain L=8, h=1, RBM_Dense(16), LocalFlip, SR."""
+    lat = osites.Chain(8)
+    H = oop.to_array_op_list(oop.ising_op_list(lat, h=1.0))
+    net = models.RBM.random(8, 16, np.float32, seed=1, scale=0.3)
+    cm = osmp.RBMChainModel(net)
+    ns = 256
+    spins = osmp.sweep(cm, osmp.rand_states(ns, 8, seed=2), 160, "localflip", seed=7, step0=0)["spins"]
+    step0, hist = 160, []
+    for it in range(60):
+        out = osmp.sweep(cm, spins, 16, "localflip", seed=7, step0=step0)
+        step0 += 16
+        spins = out["spins"]
+        E = oop.oloc(H, net.forward, spins, out["psi"])
+        x, e, v = osolver.sr_step(net.jacobian(spins), E, np.ones(ns))
+        p = osolver.update_params(net.params(), x * 0.03)
+        net.W = p[: net.W.size].reshape(net.W.shape).copy()
+        net.b = p[net.W.size:].copy()
+        hist.append(e)
+    e0 = oop.ed_lowest(H, 8, k=1)[0]
+    assert abs(np.mean(hist[-10:]) - e0) < 0.05 * abs(e0) and np.mean(hist[-10:]) > e0 - 0.05
