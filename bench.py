@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the VMC hot path (BASELINE.json): VMC samples/s for sweep + Oloc, and MinSR step ms.
+
+Workload (N=1): BASELINE.json configs[1] -- 10x10 Heisenberg (Marshall sign), RBM_Dense alpha=4
+(M=400, Np=40400, float32 parameters, float64 Jacobian / Gram / eigh as the reference's default
+dtype), SpinExchange (= NeighborExchange), Ns=4096, MinSR.  A "step" is one VMC step:
+sweep (2N = 200 proposals per chain) -> Oloc -> Jacobian (centred, scaled) -> Gram -> eigh +
+pseudo-inverse -> A^T y -> parameter update, on synthetic random-init weights and thermalised
+random chains.
+
+  value     = chains processed by (sweep + Oloc) per second, inputs resident in HBM, max over ranks
+  e2e       = the same through the public API with HOST buffers: every step copies the chains and
+              the parameters host->device from pinned memory, runs sweep + Oloc, and copies the
+              new chains and the local energies device->host.
+  N > 1     = weak scaling of the partitioned part: every GPU owns 4096 chains (no data-path
+              collective in sweep + Oloc); the MinSR part of the step is the named config's
+              Ns=4096 system with its rows sharded over the N GPUs (4096/N rows each), which
+              exercises the all-to-all / all-reduce / all-gather of the distributed solve.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, NumPy on the
+host cores; the reference itself needs jax, which is not installable here) on a bounded sample
+of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L, ALPHA, NS = 10, 4, 4096
+METRIC = "vmc_samples_per_sec_sweep_oloc"
+WORKLOAD = "heisenberg10x10_msr_rbm_dense_alpha4_spinexchange_ns4096_minsr"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference algorithm)
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(ns_sweep=512, ns_minsr=1024, steps=1, warmup=0):
+    import numpy as np
+
+    from oracle import models as om, operator as oop, sampler as osmp, sites as osites, solver as osolver
+
+    try:
+        import torch
+
+        torch.set_num_threads(os.cpu_count() or 1)
+    except Exception:
+        pass
+    N, M = L * L, ALPHA * L * L
+    lat = osites.Square(L, Nparticles=(N // 2, N // 2))
+    H = oop.to_array_op_list(oop.heisenberg_op_list(lat, msr=True))
+    net = om.RBM.random(N, M, np.float32, seed=1, scale=0.3)
+    table = osites.site_neighbor_table(lat)
+    cm = osmp.RBMChainModel(net)
+    spins = osmp.rand_states(ns_sweep, N, N // 2, seed=2)
+    t_sw, t_ms = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = osmp.sweep(cm, spins, 2 * N, "exchange", neighbors=table, seed=7, step0=it * 2 * N)
+        spins = out["spins"]
+        E = oop.oloc(H, net.forward, spins, out["psi"])
+        t1 = time.perf_counter()
+        sm = osmp.rand_states(ns_minsr, N, N // 2, seed=3)
+        Em = oop.oloc(H, net.forward, sm)
+        t2 = time.perf_counter()
+        x, e, v = osolver.sr_step(net.jacobian(sm), Em, np.ones(ns_minsr))
+        t3 = time.perf_counter()
+        if it >= warmup:
+            t_sw.append(t1 - t0)
+            t_ms.append(t3 - t2)
+    sw = float(np.mean(t_sw))
+    return {
+        "value": ns_sweep / sw,
+        "unit": "samples/s",
+        "cores": os.cpu_count(),
+        "kind": "port",
+        "sample": f"NumPy oracle (restated reference, not quantax/jax itself): sweep+Oloc on {ns_sweep} of {NS} chains "
+                  f"(full 200-step sweep), MinSR (Jacobian+Gram+eigh+A^T y) on {ns_minsr} of {NS} rows x 40400 params",
+        "sweep_oloc_s": sw,
+        "minsr_step_ms_at_sample": float(np.mean(t_ms)) * 1e3,
+        "minsr_rows": ns_minsr,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    cb = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["sweep_oloc_s"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 model / f64 psi, Jacobian, solve",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU oracle port on a bounded sample"},
+        "minsr_step_ms": cb["minsr_step_ms_at_sample"], "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import quantax_b200 as qtx
+    from quantax_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    import warnings
+
+    warnings.simplefilter("ignore")
+
+    N, M = L * L, ALPHA * L * L
+    qtx.set_random_seed(42)
+    qtx.sites.Square(L, Nparticles=(N // 2, N // 2))
+    H = qtx.operator.Heisenberg(msr=True)
+    model = qtx.model.RBM_Dense(features=M)
+    state = qtx.state.Variational(model)
+    # weak scaling of the partitioned part: NS chains on every GPU
+    sampler = qtx.sampler.SpinExchange(state, nsamples=NS * world)
+    optimizer = qtx.optimizer.SR(state, H)
+    rows = NS // world  # MinSR rows of this rank (global NS rows as in the named config)
+    Np = model.nparams
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def vmc_step(timed):
+        flush.fill_(1)
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        samples = sampler.sweep()
+        Eloc_all = H.Oloc(state, samples)
+        e[1].record()
+        sub = qtx.sampler.Samples(samples.spins[:rows], samples.psi[:rows], None, samples.reweight_factor[:rows])
+        e[2].record()
+        Ebar = optimizer.get_Ebar(sub, Eloc=Eloc_all[:rows].contiguous())
+        Obar = optimizer.get_Obar(sub)
+        step = optimizer.solve(Obar, Ebar)
+        state.update(step * 1e-3)
+        e[3].record()
+        if timed is not None:
+            timed.append(e)
+        return samples
+
+    for _ in range(args.warmup):
+        vmc_step(None)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    optimizer.timers = {}
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    _lib.lib().qtx_launch_count_reset()
+    timed = []
+    torch.cuda.synchronize()
+    t_all0 = ev(); t_all1 = ev()
+    t_all0.record()
+    for _ in range(args.steps):
+        vmc_step(timed)
+    t_all1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = int(_lib.lib().qtx_launch_count())
+    clk = clocks.stop()
+    sweep_oloc_ms = sum(e[0].elapsed_time(e[1]) for e in timed)
+    minsr_ms = sum(e[2].elapsed_time(e[3]) for e in timed)
+    total_ms = t_all0.elapsed_time(t_all1)
+    phase = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in optimizer.timers.items()}
+    optimizer.timers = None
+
+    # kernel-level timing of the dominant own kernel (Gram) and of eigh, on the launching stream
+    from quantax_b200.optimizer import gram, pinv_eig_solve, matvec_t, DEFAULT_NSLICES
+
+    A = torch.randn((NS if world == 1 else NS, Np // world if world > 1 else Np), dtype=torch.float64, device=dev) / 64
+    for _ in range(2):
+        T = gram(A)
+    g0, g1 = ev(), ev()
+    reps = 3
+    flush.fill_(2)
+    g0.record()
+    for _ in range(reps):
+        T = gram(A)
+    g1.record()
+    torch.cuda.synchronize()
+    gram_ms = g0.elapsed_time(g1) / reps
+    b = torch.randn(NS, dtype=torch.float64, device=dev)
+    h0, h1 = ev(), ev()
+    h0.record()
+    y, info = pinv_eig_solve(T.clone(), b, None, 0.0)
+    h1.record()
+    torch.cuda.synchronize()
+    eigh_ms = h0.elapsed_time(h1)
+    del A, T
+
+    # e2e: host buffers, copies inside the timed region
+    spins_host = torch.empty((NS, N), dtype=torch.int8).pin_memory()
+    params_host = torch.empty(Np, dtype=torch.float32).pin_memory()
+    eloc_host = torch.empty(NS, dtype=torch.float64).pin_memory()
+    spins_host.copy_(sampler._spins)
+    params_host.copy_(model.params)
+    torch.cuda.synchronize()
+    e2e_steps = max(3, args.steps)
+    for it in range(2 + e2e_steps):
+        if it == 2:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+        sampler._spins.copy_(spins_host, non_blocking=True)
+        model.params.copy_(params_host, non_blocking=True)
+        samples = sampler.sweep()
+        El = H.Oloc(state, samples)
+        spins_host.copy_(samples.spins, non_blocking=True)
+        eloc_host.copy_(El, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = NS * N + Np * 4
+    d2h = NS * N + NS * 8
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sweep_oloc_ms, minsr_ms, total_ms, e2e_s, gram_ms, eigh_ms = (allmax(v) for v in (sweep_oloc_ms, minsr_ms, total_ms,
+                                                                                      e2e_s, gram_ms, eigh_ms))
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops", 1590.0)
+        ns_g, np_g = NS, (Np // world if world > 1 else Np)
+        gram_flops = float(ns_g) * (ns_g + 1) * np_g  # SYRK count: Ns(Ns+1)/2 dot products of length Np
+        ach = gram_flops / (gram_ms * 1e-3) / 1e12
+        value = NS * world * args.steps / (sweep_oloc_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 model / f64 psi, Jacobian, Gram, eigh", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chains_per_gpu": NS, "sweep_steps": 2 * N, "minsr_rows_global": NS,
+                       "nparams": Np, "l2": "256 MiB buffer written before every step (L2 flush)",
+                       "gram_nslices": DEFAULT_NSLICES},
+            "sweep_oloc_ms": sweep_oloc_ms / args.steps, "minsr_step_ms": minsr_ms / args.steps,
+            "minsr_phases_ms": {**phase, "gram_kernel_alone": gram_ms, "eigh_pinv_alone": eigh_ms},
+            "e2e": {"value": NS * world * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clk,
+            "roofline": {"kernel": "qtx_gram (T = Obar Obar^T)", "bound": "tensor", "achieved": ach, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                         "note": "achieved = float64-equivalent SYRK flops Ns(Ns+1)Np / CUDA-event time; peak = measured "
+                                 "cuBLAS bf16 (MEASURED_PEAKS.json, burst)" if peaks else "fallback peak"},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,11 +63,10 @@ class RBM:
     def ref_forward(self, s_new, s_old, nflips, theta):
         """shallow_nets.py:87-108.  ``argwhere(size=nflips)`` pads missing indices with 0."""
         ns = s_new.shape[0]
-        idx = np.zeros((ns, nflips), dtype=np.int64)
-        for c in range(ns):
-            nz = np.flatnonzero(s_new[c] != s_old[c])[:nflips]
-            idx[c, : nz.size] = nz
+        diff = s_new != s_old
+        idx = np.argsort(~diff, axis=1, kind="stable")[:, :nflips]  # first differing sites, ascending
         ar = np.arange(ns)[:, None]
+        idx = np.where(diff[ar, idx], idx, 0)  # fill_value 0 of jnp.argwhere(size=nflips)
         sv = s_new[ar, idx].astype(self.dtype)  # [ns, nflips]
         Wc = self.W.T[idx]  # [ns, nflips, M]
         theta_new = theta + 2 * np.einsum("cfm,cf->cm", Wc, sv).astype(self.dtype)

@@ -94,6 +94,17 @@ def ptr(t):
     return t.data_ptr()
 
 
+def ptr2d(t):
+    """Row-major matrix whose rows may be padded (leading dimension = t.stride(0))."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise QtxError("quantax_b200 kernels need CUDA tensors; there is no CPU path")
+    if t.ndim != 2 or t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        raise QtxError("expected a row-major matrix with unit column stride")
+    return t.data_ptr()
+
+
 def stream():
     return torch.cuda.current_stream().cuda_stream
 

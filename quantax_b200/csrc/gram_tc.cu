@@ -1,8 +1,460 @@
+// T = A A^T on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM,
+// operands staged by TMA) with float64-grade accuracy.
+//
+// tcgen05 has no FP64 MMA kind, and the reference computes the MinSR Gram matrix in float64
+// (quantax/optimizer/solver.py:139 on the float64 Jacobian of variational.py:491).  We therefore
+// use an error-free transformation (Ozaki scheme):
+//   1. every row r of A is scaled by a power of two 2^-e_r so that |v| < 1, and cut into `s`
+//      signed digits  v = q_1 2^-6 + q_2 2^-13 + ... + q_s 2^-(7s-1) + O(2^-7s), |q_a| <= 64 (int8);
+//   2. the int8 digit matrices are multiplied pairwise on the tensor cores with EXACT int32
+//      accumulation:  S_ab[i,j] = sum_k q_a[i,k] q_b[j,k].  Pairs with the same level d = a + b
+//      share the weight 2^(-7d+2) and therefore one TMEM accumulator; pairs with d > s + 1 are
+//      below the truncation error and skipped (s (s+1) / 2 products instead of s^2);
+//   3. the epilogue recombines the levels in float64:
+//      T[i,j] = 2^(e_i+e_j) sum_d 2^(-7d+2) S_d[i,j]  -- every term is exact, the sum is rounded.
+// Only tiles on or below the diagonal are computed; the epilogue mirrors them.
+//
+// Kernel structure (one CTA per SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA
+// issuer (single thread) + TMEM allocator, warps 2-5 = epilogue (TMEM -> registers -> float64 ->
+// global).  A tile is 128 x 128 outputs; TMEM holds up to four level accumulators of 128 columns
+// (all 512 columns), so `s` digits need ceil(s / 4) passes over K.  One pipeline stage holds one
+// 32-element K block of all needed digit slices of both row panels (2 * s * 4 KB).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace qtx {
-size_t gram_tc_workspace(int, int64_t, int64_t, int) { return 256; }
-int gram_tc(int, const void*, int64_t, int64_t, int64_t, int, double*, int, void*, size_t, cudaStream_t) {
-  set_error("qtx_gram: tensor-core path not built yet");
-  return QTX_ERR_UNSUPPORTED;
+
+constexpr int kTile = 128;       // output tile edge (UMMA M = N = 128)
+constexpr int kBK = 32;          // K elements (= bytes) per pipeline stage and per UMMA instruction
+constexpr int kSliceBytes = kTile * kBK;  // 4096
+constexpr int kMaxSlices = 8;
+constexpr int kLevelsPerPass = 4;
+constexpr int kThreads = 192;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a lost arrival traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, int8 x int8 -> int32, issued by ONE thread
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 32-byte swizzled operand tile [128 rows][32 B]: 8-row groups are 256 B apart
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;               // leading byte offset (unused for swizzled K-major), 16 B units
+  d |= (uint64_t)(256 >> 4) << 32;      // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;               // descriptor version (Blackwell)
+  d |= (uint64_t)6 << 61;               // SWIZZLE_32B
+  return d;
+}
+
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, M = N = 128
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) |
+                              ((uint32_t)(kTile >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------
+// slicing kernel: one CTA per (padded) row
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gram_split_kernel(const T* __restrict__ A, int64_t ns, int64_t np, int64_t ld,
+                                                         int64_t k0, int64_t kc, int64_t kc_pad, int64_t ns_pad,
+                                                         int nslices, int8_t* __restrict__ Q,
+                                                         double* __restrict__ rowscale, int first_chunk) {
+  __shared__ double red[8];
+  __shared__ double s_inv;
+  const int64_t r = blockIdx.x;
+  const int tid = threadIdx.x;
+  double inv = 0.0;
+  if (r < ns) {
+    // row scale from the FULL row (all K chunks share it)
+    double mx = 0.0;
+    const T* row = A + r * ld;
+    for (int64_t k = tid; k < np; k += blockDim.x) mx = fmax(mx, fabs((double)row[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+      double sc = 1.0;
+      if (!isfinite(mx)) {
+        sc = nan("");
+        s_inv = 0.0;
+      } else if (mx > 0.0) {
+        int e;
+        frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)  ->  |x| 2^-e < 1
+        sc = scalbn(1.0, e);
+        s_inv = scalbn(1.0, -e);
+      } else {
+        s_inv = 0.0;
+      }
+      if (first_chunk) rowscale[r] = sc;
+    }
+    __syncthreads();
+    inv = s_inv;
+  } else if (tid == 0 && first_chunk) {
+    rowscale[r] = 0.0;
+  }
+  // 4 consecutive k per thread -> one coalesced 4-byte store per slice (a warp writes 128 B)
+  const T* row = A + (r < ns ? r : 0) * ld;
+  for (int64_t kb = (int64_t)tid * 4; kb < kc_pad; kb += (int64_t)blockDim.x * 4) {
+    uint32_t w[kMaxSlices];
+#pragma unroll
+    for (int a = 0; a < kMaxSlices; ++a) w[a] = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int64_t k = k0 + kb + e;
+      double v = (r < ns && kb + e < kc && k < np) ? (double)row[k] * inv : 0.0;
+      double res = v * 64.0;
+#pragma unroll
+      for (int a = 0; a < kMaxSlices; ++a) {
+        if (a < nslices) {
+          double qa = rint(res);
+          w[a] |= ((uint32_t)(int)qa & 0xffu) << (8 * e);
+          res = (res - qa) * 128.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < kMaxSlices; ++a)
+      if (a < nslices) *reinterpret_cast<uint32_t*>(Q + ((int64_t)a * ns_pad + r) * kc_pad + kb) = w[a];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+struct GramTcParams {
+  int nb;         // row blocks of 128
+  int nkb;        // K blocks of 32
+  int nslices;
+  int stages;
+  int64_t ns;     // true rows
+  const double* rowscale;
+  double* T;
+  int accum;
+};
+
+__device__ __forceinline__ void tile_from_index(int t, int& I, int& J) {
+  int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while ((i + 1) * (i + 2) / 2 <= t) ++i;
+  while (i * (i + 1) / 2 > t) --i;
+  I = i;
+  J = t - i * (i + 1) / 2;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, GramTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int s = p.nslices;
+  const uint32_t stage_bytes = 2u * s * kSliceBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(full_bar + i, 1);
+      mbar_init(empty_bar + i, 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);  // one arrival per epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int ntiles = p.nb * (p.nb + 1) / 2;
+  const int npasses = (s + kLevelsPerPass - 1) / kLevelsPerPass;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int I, J;
+        tile_from_index(t, I, J);
+        for (int pass = 0; pass < npasses; ++pass) {
+          const int d_hi = min(2 + (pass + 1) * kLevelsPerPass - 1, s + 1);
+          const int nsl = min(s, d_hi - 1);  // digit slices 1..nsl are needed by this pass
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            mbar_expect_tx(full_bar + stage, 2u * nsl * kSliceBytes);
+            unsigned char* base = smem + (size_t)stage * stage_bytes;
+            for (int a = 0; a < nsl; ++a) {
+              tma_load_3d(base + (size_t)a * kSliceBytes, &tmap, full_bar + stage, kb * kBK, I * kTile, a);
+              tma_load_3d(base + (size_t)(s + a) * kSliceBytes, &tmap, full_bar + stage, kb * kBK, J * kTile, a);
+            }
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int pass = 0; pass < npasses; ++pass) {
+          const int d_lo = 2 + pass * kLevelsPerPass;
+          const int d_hi = min(d_lo + kLevelsPerPass - 1, s + 1);
+          mbar_wait(tmem_empty, tphase ^ 1);  // epilogue has drained the accumulators
+          tc_fence_after();
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(full_bar + stage, phase);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
+            for (int d = d_lo; d <= d_hi; ++d) {
+              const uint32_t acc = tmem_base + (uint32_t)(d - d_lo) * kTile;
+              const int a_lo = max(1, d - s), a_hi = min(s, d - 1);
+              for (int a = a_lo; a <= a_hi; ++a) {
+                const int b = d - a;
+                uint64_t da = make_desc_sw32(base + (uint32_t)(a - 1) * kSliceBytes);
+                uint64_t db = make_desc_sw32(base + (uint32_t)(s + b - 1) * kSliceBytes);
+                umma_i8(acc, da, db, kIdescI8, (kb > 0 || a > a_lo) ? 1u : 0u);
+              }
+            }
+            umma_commit(empty_bar + stage);  // frees the smem stage once these MMAs have read it
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(tmem_full);  // accumulators complete
+          tphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 =====
+    const int lg = warp & 3;
+    uint32_t tphase = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int I, J;
+      tile_from_index(t, I, J);
+      const int64_t row = (int64_t)I * kTile + lg * 32 + lane;
+      const double rs_i = (row < p.ns) ? p.rowscale[row] : 0.0;
+      for (int pass = 0; pass < npasses; ++pass) {
+        const int d_lo = 2 + pass * kLevelsPerPass;
+        const int d_hi = min(d_lo + kLevelsPerPass - 1, s + 1);
+        mbar_wait(tmem_full, tphase);
+        tc_fence_after();
+        const bool add = (pass > 0) || (p.accum != 0);
+        for (int c0 = 0; c0 < kTile; c0 += 16) {
+          double sum[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sum[e] = 0.0;
+          for (int d = d_hi; d >= d_lo; --d) {  // smallest weights first
+            int32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d - d_lo) * kTile + c0, v);
+            tmem_ld_wait();
+            const double w = scalbn(1.0, -7 * d + 2);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sum[e] += w * (double)v[e];
+          }
+          if (row < p.ns) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int64_t col = (int64_t)J * kTile + c0 + e;
+              if (col < p.ns && (I != J || col <= row)) {
+                const double val = sum[e] * (rs_i * p.rowscale[col]);
+                double* p1 = p.T + row * p.ns + col;
+                *p1 = add ? *p1 + val : val;
+                if (col != row) {
+                  double* p2 = p.T + col * p.ns + row;
+                  *p2 = add ? *p2 + val : val;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
+        tphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static int default_slices(int dtype) { return dtype == QTX_F64 ? 8 : 4; }
+
+static void gram_tc_sizes(int dtype, int64_t ns, int64_t np, int nslices, int& s, int64_t& ns_pad, int64_t& kc,
+                          int64_t& kc_pad) {
+  s = nslices > 0 ? nslices : default_slices(dtype);
+  ns_pad = (ns + kTile - 1) / kTile * kTile;
+  // exact int32 accumulation: up to s pairs per level, |q| <= 64  ->  K * s * 4096 < 2^31
+  int64_t kmax = ((int64_t)1 << 31) / (4096 * (int64_t)s) - 1;
+  kmax = kmax / 64 * 64;
+  kc = np < kmax ? np : kmax;
+  kc_pad = (kc + 63) / 64 * 64;
+}
+
+size_t gram_tc_workspace(int dtype, int64_t ns, int64_t np, int nslices) {
+  int s;
+  int64_t ns_pad, kc, kc_pad;
+  gram_tc_sizes(dtype, ns, np, nslices, s, ns_pad, kc, kc_pad);
+  return (size_t)s * ns_pad * kc_pad + (size_t)ns_pad * sizeof(double) + 1024;
+}
+
+int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int nslices, double* Tout, int accum,
+            void* ws, size_t ws_bytes, cudaStream_t st) {
+  int s;
+  int64_t ns_pad, kc, kc_pad;
+  gram_tc_sizes(dtype, ns, np, nslices, s, ns_pad, kc, kc_pad);
+  QTX_REQUIRE(s >= 1 && s <= kMaxSlices, QTX_ERR_INVALID, "qtx_gram: nslices must be in 1..%d", kMaxSlices);
+  QTX_REQUIRE(ws && ws_bytes >= gram_tc_workspace(dtype, ns, np, nslices), QTX_ERR_INVALID,
+              "qtx_gram: workspace too small");
+  QTX_REQUIRE(ns_pad / kTile < 30000, QTX_ERR_UNSUPPORTED, "qtx_gram: ns too large");
+  EncodeTiledFn encode = get_encode_fn();
+  QTX_REQUIRE(encode != nullptr, QTX_ERR_CUDA, "qtx_gram: cuTensorMapEncodeTiled is unavailable");
+  double* rowscale = reinterpret_cast<double*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  int8_t* Q = reinterpret_cast<int8_t*>(((uintptr_t)(rowscale + ns_pad) + 255) & ~(uintptr_t)255);
+
+  CUtensorMap tmap;
+  cuuint64_t gdim[3] = {(cuuint64_t)kc_pad, (cuuint64_t)ns_pad, (cuuint64_t)s};
+  cuuint64_t gstride[2] = {(cuuint64_t)kc_pad, (cuuint64_t)kc_pad * (cuuint64_t)ns_pad};
+  cuuint32_t box[3] = {kBK, kTile, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, Q, gdim, gstride, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QTX_REQUIRE(cr == CUDA_SUCCESS, QTX_ERR_CUDA, "qtx_gram: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+  const uint32_t stage_bytes = 2u * s * kSliceBytes;
+  int stages = (int)((220 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  QTX_REQUIRE(stages >= 2, QTX_ERR_UNSUPPORTED, "qtx_gram: pipeline does not fit in shared memory");
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 2) * 8 + 16;
+  QTX_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+  GramTcParams p;
+  p.nb = (int)(ns_pad / kTile);
+  p.nslices = s;
+  p.stages = stages;
+  p.ns = ns;
+  p.rowscale = rowscale;
+  p.T = Tout;
+  const int ntiles = p.nb * (p.nb + 1) / 2;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  int chunk = 0;
+  for (int64_t k0 = 0; k0 < np; k0 += kc, ++chunk) {
+    const int64_t kcur = (np - k0) < kc ? (np - k0) : kc;
+    const int64_t kcur_pad = (kcur + 63) / 64 * 64;
+    QTX_REQUIRE(kcur_pad == kc_pad || chunk > 0, QTX_ERR_INVALID, "qtx_gram: internal chunk error");
+    if (dtype == QTX_F64)
+      gram_split_kernel<double><<<(unsigned)ns_pad, 256, 0, st>>>((const double*)A, ns, np, ld, k0, kcur, kc_pad,
+                                                                  ns_pad, s, Q, rowscale, chunk == 0);
+    else
+      gram_split_kernel<float><<<(unsigned)ns_pad, 256, 0, st>>>((const float*)A, ns, np, ld, k0, kcur, kc_pad, ns_pad,
+                                                                 s, Q, rowscale, chunk == 0);
+    QTX_LAUNCH_CHECK();
+    p.nkb = (int)(kc_pad / kBK);
+    p.accum = (accum != 0 || chunk > 0) ? 1 : 0;
+    gram_tc_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+    QTX_LAUNCH_CHECK();
+  }
+  return QTX_OK;
+}
+
 }  // namespace qtx

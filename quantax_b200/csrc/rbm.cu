@@ -656,8 +656,8 @@ extern "C" size_t qtx_rbm_workspace_size(int model_dtype, int N, int M) {
 
 extern "C" int qtx_rbm_forward(int model_dtype, const void* W, const void* b, int N, int M, const int8_t* spins,
                                int64_t ns, void* theta_out, double* logabs_out, qtx_stream_t stream) {
-  QTX_REQUIRE(W && b && spins && N > 0 && M > 0 && ns >= 0, QTX_ERR_INVALID, "qtx_rbm_forward: bad argument");
   if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(W && b && spins && N > 0 && M > 0 && ns >= 0, QTX_ERR_INVALID, "qtx_rbm_forward: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned grid = (unsigned)((ns + 7) / 8);
   if (model_dtype == QTX_F32)
@@ -736,6 +736,7 @@ extern "C" int qtx_rbm_oloc(int model_dtype, const void* W, const void* b, int N
                             int64_t ns, const double* term_coef, const uint16_t* term_sites, const uint8_t* term_ops,
                             int nterms, double* eloc_out, int32_t* nconn_out, void* workspace, size_t workspace_bytes,
                             qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
   QTX_REQUIRE(W && b && spins && eloc_out && N > 0 && M > 0 && ns >= 0 && nterms >= 0, QTX_ERR_INVALID,
               "qtx_rbm_oloc: bad argument");
   QTX_REQUIRE(nterms == 0 || (term_coef && term_sites && term_ops), QTX_ERR_INVALID, "qtx_rbm_oloc: null term table");

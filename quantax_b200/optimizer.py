@@ -46,7 +46,7 @@ _WS = _Workspaces()
 
 # Gram algorithm: 0 = tcgen05 int8-sliced tensor-core kernel with the dtype's default slice count,
 # k > 0 = k slices, -1 = FP64 FMA cross-check kernel.  QTX_GRAM_NSLICES overrides (dev knob).
-DEFAULT_NSLICES = int(os.environ.get("QTX_GRAM_NSLICES", "-1"))
+DEFAULT_NSLICES = int(os.environ.get("QTX_GRAM_NSLICES", "0"))
 
 
 # ---- dense building blocks -----------------------------------------------------------------------
@@ -60,7 +60,7 @@ def gram(A: torch.Tensor, out: Optional[torch.Tensor] = None, nslices: Optional[
     dt = _lib.dtype_code(A.dtype)
     wsz = _lib.lib().qtx_gram_workspace_size(dt, ns, npar, nslices)
     ws = _WS.get("gram", wsz)
-    _lib.call("qtx_gram", dt, _lib.ptr(A), ns, npar, A.stride(0), int(nslices), _lib.ptr(out), int(accumulate),
+    _lib.call("qtx_gram", dt, _lib.ptr2d(A), ns, npar, A.stride(0), int(nslices), _lib.ptr(out), int(accumulate),
               _lib.ptr(ws), wsz, _lib.stream())
     return out
 
@@ -84,7 +84,7 @@ def matvec_t(A: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """x = A^T y (float64 [np])."""
     ns, npar = A.shape
     x = torch.empty(npar, dtype=torch.float64, device=A.device)
-    _lib.call("qtx_matvec_t", _lib.dtype_code(A.dtype), _lib.ptr(A), ns, npar, A.stride(0), _lib.ptr(y.contiguous()),
+    _lib.call("qtx_matvec_t", _lib.dtype_code(A.dtype), _lib.ptr2d(A), ns, npar, A.stride(0), _lib.ptr(y.contiguous()),
               _lib.ptr(x), 0, _lib.stream())
     return x
 
@@ -92,7 +92,7 @@ def matvec_t(A: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
 def matvec(A: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     ns, npar = A.shape
     v = torch.empty(ns, dtype=torch.float64, device=A.device)
-    _lib.call("qtx_matvec", _lib.dtype_code(A.dtype), _lib.ptr(A), ns, npar, A.stride(0), _lib.ptr(x.contiguous()),
+    _lib.call("qtx_matvec", _lib.dtype_code(A.dtype), _lib.ptr2d(A), ns, npar, A.stride(0), _lib.ptr(x.contiguous()),
               _lib.ptr(v), _lib.stream())
     return v
 
@@ -258,8 +258,8 @@ class QNGD:
         self._toc(ev)
         return step.to(get_default_dtype())
 
-    def get_step(self, samples) -> torch.Tensor:
-        Ebar = self.get_Ebar(samples)
+    def get_step(self, samples, **kw) -> torch.Tensor:
+        Ebar = self.get_Ebar(samples, **kw)
         Obar = self.get_Obar(samples)
         return self.solve(Obar, Ebar)
 
@@ -282,12 +282,14 @@ class SR(QNGD):
     def VarE(self) -> Optional[float]:
         return None if self._stats is None else float(self._stats[1].item())
 
-    def get_Ebar(self, samples) -> torch.Tensor:
-        r"""Ebar = (Eloc - <Eloc>) sqrt(rw / Ns); also stores energy and VarE (sr.py:180-195)."""
+    def get_Ebar(self, samples, Eloc: Optional[torch.Tensor] = None) -> torch.Tensor:
+        r"""Ebar = (Eloc - <Eloc>) sqrt(rw / Ns); also stores energy and VarE (sr.py:180-195).
+        ``Eloc`` may be passed when the local energies of these samples are already known."""
         rank, P = world()
-        ev = self._tic("oloc")
-        Eloc = self._hamiltonian.Oloc(self._state, samples).to(torch.float64)
-        self._toc(ev)
+        if Eloc is None:
+            ev = self._tic("oloc")
+            Eloc = self._hamiltonian.Oloc(self._state, samples).to(torch.float64)
+            self._toc(ev)
         rw = samples.reweight_factor
         nl = Eloc.shape[0]
         if P > 1:

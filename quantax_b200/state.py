@@ -205,14 +205,14 @@ class Variational(State):
             out = torch.empty((ns, m.nparams), dtype=odt, device=s.device)
         if m.kind == "rbm":
             _lib.call("qtx_rbm_jacobian", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
-                      _lib.dtype_code(out.dtype), _lib.ptr(out), out.stride(0), _lib.ptr(col_mean),
+                      _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), _lib.ptr(col_mean),
                       _lib.ptr(row_scale), _lib.stream())
             return out
         from .resconv import resconv_jacobian
 
         resconv_jacobian(self, s, out)
         if col_mean is not None or row_scale is not None:
-            _lib.call("qtx_center_scale", _lib.dtype_code(out.dtype), _lib.ptr(out), ns, m.nparams, out.stride(0),
+            _lib.call("qtx_center_scale", _lib.dtype_code(out.dtype), _lib.ptr2d(out), ns, m.nparams, out.stride(0),
                       _lib.ptr(col_mean), _lib.ptr(row_scale), _lib.stream())
         return out
 

@@ -67,7 +67,7 @@ def test_ebar_energy_variance(qtx):
         assert np.allclose(to_np(st), [e_o, v_o], rtol=1e-12)
 
 
-@pytest.mark.parametrize("nslices", [-1])
+@pytest.mark.parametrize("nslices", [-1, 0])
 def test_gram_fma(qtx, nslices):
     from quantax_b200.optimizer import gram
 
