@@ -151,6 +151,53 @@ int qtx_rbm_jacobian_colmean(int model_dtype, const void* W, const void* b, int 
                              qtx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * ResConv (quantax/model/conv_nets.py:26-183): pre-activation residual CNN with circular padding,
+ * tanh-GELU, final exp / sinh+1 "by scale" activation, channel mean and translation sum.
+ *   params: flat vector in the reference's ravel_pytree order (per block conv1.weight
+ *   [C,Cin,kh,kw], conv1.bias [C], conv2.weight [C,C,kh,kw], conv2.bias [C]; the last conv has no
+ *   bias).  Chains (1-D lattices) use lx = 1, kh = 1.  final_act: 0 = exp_by_scale,
+ *   1 = sinhp1_by_scale (quantax/nn/activation.py:7-32).
+ *   psi = significand * exp(exponent) (ScaleArray), float64 [ns] each
+ *   (quantax/state/variational.py:262-266 with the Identity symmetry).
+ * ------------------------------------------------------------------------------------------ */
+int64_t qtx_resconv_nparams(int nblocks, int channels, int lx, int ly, int kh, int kw);
+size_t qtx_resconv_workspace_size(int model_dtype, int64_t ns, int nblocks, int channels, int lx,
+                                  int ly, int kh, int kw, int need_grad);
+/* Batched direct forward: Variational.__call__ / _fulljit_forward (variational.py:268-274,325-347). */
+int qtx_resconv_forward(int model_dtype, const void* params, int nblocks, int channels, int lx,
+                        int ly, int kh, int kw, int final_act, const int8_t* spins, int64_t ns,
+                        double* significand_out, double* exponent_out, void* workspace,
+                        size_t workspace_bytes, qtx_stream_t stream);
+/* Per-sample log-derivatives (Variational.jacobian, variational.py:424-511): softmax-weighted
+ * backprop through the net, exponent is stop-gradient; out [ns, ld] of out_dtype, columns in
+ * parameter order.  significand_out / exponent_out are nullable. */
+int qtx_resconv_jacobian(int model_dtype, const void* params, int nblocks, int channels, int lx,
+                         int ly, int kh, int kw, int final_act, const int8_t* spins, int64_t ns,
+                         int out_dtype, void* out, int64_t ld, double* significand_out,
+                         double* exponent_out, void* workspace, size_t workspace_bytes,
+                         qtx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model-agnostic Metropolis step for states without local updates (full forward per proposal,
+ * variational.py:383-384): propose -> (caller evaluates psi(new_spins)) -> accept.
+ * The Philox stream is the one of qtx_rbm_sweep: counter (chain0+chain, step), key seed.
+ *   propose: new_spins [ns, N], moved uint8 [ns] (any(s' != s), metropolis.py:314); inj_pos /
+ *            inj_slot int32 [ns] for THIS step (nullable).
+ *   accept : metropolis.py:299-322 on (mult, expo) pairs; spins / mult / expo updated in place;
+ *            inj_u float64 [ns] for this step (nullable); naccept int32 [ns] incremented
+ *            (nullable); accept_log uint8 [ns] (nullable).
+ * ------------------------------------------------------------------------------------------ */
+int qtx_metropolis_propose(int kind, const int8_t* spins, int64_t ns, int N,
+                           const int32_t* nbr_table, int max_nb, int hop, const int32_t* inj_pos,
+                           const int32_t* inj_slot, uint64_t seed, uint64_t step, uint64_t chain0,
+                           int8_t* new_spins, uint8_t* moved, qtx_stream_t stream);
+int qtx_metropolis_accept(int8_t* spins, const int8_t* new_spins, const uint8_t* moved, int64_t ns,
+                          int N, double* mult, double* expo, const double* mult_new,
+                          const double* expo_new, double reweight, const double* inj_u,
+                          uint64_t seed, uint64_t step, uint64_t chain0, int32_t* naccept,
+                          uint8_t* accept_log, qtx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Connected-configuration enumeration for generic models (bit-exact mirror of
  * _apply_off_diag + _get_conn, operator.py:96-165).  Terms with `nflips_sel` flips only.
  *   count:  nonnan_out / valid_out int32 [ns]  (valid = not NaN and |H| > 1e-8)

@@ -34,6 +34,16 @@ SIGNATURES = {
     "qtx_rbm_jacobian": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "qtx_rbm_colmean_workspace_size": (_sz, [_i32, _i32, _i32, _i64]),
     "qtx_rbm_jacobian_colmean": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_resconv_nparams": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "qtx_resconv_workspace_size": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "qtx_resconv_forward": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz,
+                                   _vp]),
+    "qtx_resconv_jacobian": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _i64,
+                                    _vp, _vp, _vp, _sz, _vp]),
+    "qtx_metropolis_propose": (_i32, [_i32, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _u64, _u64, _u64, _vp, _vp,
+                                      _vp]),
+    "qtx_metropolis_accept": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f64, _vp, _u64, _u64, _u64, _vp,
+                                     _vp, _vp]),
     "qtx_conn_count": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "qtx_exclusive_scan_i32": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "qtx_conn_fill": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -1,1 +1,716 @@
+// ResConv (quantax/model/conv_nets.py:26-183): batched forward, per-sample log-derivative
+// Jacobian, and the model-agnostic Metropolis propose / accept kernels used when a state has no
+// local-update path (quantax/state/variational.py:383-384: full forward per proposal).
+//
+// Layout: activations [ns, C, Lx*Ly] in model dtype, weights in the reference's flat parameter
+// order (conv1.weight [C,Cin,kh,kw], conv1.bias [C], conv2.weight, conv2.bias per block; the last
+// conv has no bias).  A convolution layer is an implicit GEMM over (sample, position) x out-channel
+// with K = Cin*kh*kw: the CTA stages a channel chunk of whole (circularly padded) images in shared
+// memory, so the kh*kw taps re-read shared memory instead of L2, and each thread keeps a
+// 4 x 8 (position x out-channel) register tile.  Arithmetic stays in the model dtype (float32 by
+// default: the 1e-5 parity bar rules out single-pass TF32), so these kernels are bound by the FP32
+// FMA pipe, not by HBM.
 #include "common.cuh"
+
+namespace qtx {
+
+constexpr int kConvThreads = 256;
+constexpr int kOT = 32;   // out-channel tile per CTA
+constexpr int kTN = 8;    // out channels per thread
+constexpr int kTM = 4;    // positions per thread
+constexpr int kCK = 8;    // in-channel chunk
+constexpr int kPT = 256;  // positions per CTA (64 position groups x kTM)
+
+template <typename T>
+__device__ __forceinline__ T gelu_f(T x) {
+  const T u = T(0.7978845608028654) * (x + T(0.044715) * x * x * x);
+  return T(0.5) * x * (T(1) + tanh(u));
+}
+template <typename T>
+__device__ __forceinline__ T gelu_grad_f(T x) {
+  const T u = T(0.7978845608028654) * (x + T(0.044715) * x * x * x);
+  const T t = tanh(u);
+  const T du = T(0.7978845608028654) * (T(1) + T(3 * 0.044715) * x * x);
+  return T(0.5) * (T(1) + t) + T(0.5) * x * (T(1) - t * t) * du;
+}
+
+template <typename T>
+struct ConvParams {
+  const T* in;      // [ns, cin, N]
+  const T* w;       // [cout, cin, kh, kw]  (or pre-transposed for the backward-data pass)
+  const T* bias;    // [cout] or null
+  const T* res;     // residual added after the multiply, [ns, res_ch, N], res_ch in {0, 1, cout}
+  const T* mul;     // if non-null: out = (conv + bias) * mul_scale * gelu'(mul_alpha * mul[s,o,r]) + res
+  T* out;           // [ns, cout, N]
+  int64_t ns;
+  int cin, cout, lx, ly, kh, kw, res_ch;
+  int in_act;       // 0: f(x) = alpha*x ; 1: f(x) = gelu(alpha*x)
+  T alpha, mul_alpha, mul_scale;
+  int s_tile;       // samples per CTA
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kConvThreads) conv_circ_kernel(ConvParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.lx * p.ly, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+  const int Hp = p.lx + p.kh - 1, Wp = p.ly + p.kw - 1, HW = Hp * Wp;
+  const int taps = p.kh * p.kw;
+  T* act_s = reinterpret_cast<T*>(smem_raw);                 // [kCK][s_tile][HW]
+  T* w_s = act_s + (size_t)kCK * p.s_tile * HW;              // [kCK][taps][kOT]
+  const int tid = threadIdx.x;
+  const int og = tid >> 6, pg = tid & 63;                    // 4 channel groups x 64 position groups
+  const int64_t s0 = (int64_t)blockIdx.x * p.s_tile;
+  const int o0 = blockIdx.y * kOT;
+  const int pos0 = blockIdx.z * kPT;                         // position tile inside the sample group
+  const int P = p.s_tile * N;
+
+  int base[kTM];
+  bool pvalid[kTM];
+#pragma unroll
+  for (int t = 0; t < kTM; ++t) {
+    int pos = pos0 + pg + 64 * t;
+    pvalid[t] = pos < P && (s0 + pos / N) < p.ns;
+    int sl = pvalid[t] ? pos / N : 0, r = pvalid[t] ? pos % N : 0;
+    base[t] = sl * HW + (r / p.ly) * Wp + (r % p.ly);
+  }
+  T acc[kTM][kTN];
+#pragma unroll
+  for (int t = 0; t < kTM; ++t)
+#pragma unroll
+    for (int n = 0; n < kTN; ++n) acc[t][n] = 0;
+
+  for (int c0 = 0; c0 < p.cin; c0 += kCK) {
+    __syncthreads();
+    // stage activations (with the input transform and the circular halo)
+    const int nact = kCK * p.s_tile * HW;
+    for (int e = tid; e < nact; e += kConvThreads) {
+      int ck = e / (p.s_tile * HW), rem = e % (p.s_tile * HW);
+      int sl = rem / HW, q = rem % HW;
+      int hp = q / Wp, wp = q % Wp;
+      int h = hp - ph, w = wp - pw;
+      h += (h < 0) ? p.lx : 0; h -= (h >= p.lx) ? p.lx : 0;
+      w += (w < 0) ? p.ly : 0; w -= (w >= p.ly) ? p.ly : 0;
+      T v = 0;
+      int c = c0 + ck;
+      if (c < p.cin && s0 + sl < p.ns) {
+        v = p.alpha * p.in[((s0 + sl) * p.cin + c) * N + h * p.ly + w];
+        if (p.in_act == 1) v = gelu_f(v);
+      }
+      act_s[e] = v;
+    }
+    // stage weights as [ck][tap][o]
+    const int nw = kCK * taps * kOT;
+    for (int e = tid; e < nw; e += kConvThreads) {
+      int o = e % kOT, tap = (e / kOT) % taps, ck = e / (kOT * taps);
+      int c = c0 + ck;
+      T v = 0;
+      if (c < p.cin && o0 + o < p.cout) v = p.w[((size_t)(o0 + o) * p.cin + c) * taps + tap];
+      w_s[e] = v;
+    }
+    __syncthreads();
+    for (int ck = 0; ck < kCK; ++ck) {
+      const T* a_c = act_s + (size_t)ck * p.s_tile * HW;
+      const T* w_c = w_s + (size_t)ck * taps * kOT + og * kTN;
+      for (int dy = 0; dy < p.kh; ++dy)
+        for (int dx = 0; dx < p.kw; ++dx) {
+          const int off = dy * Wp + dx;
+          T a[kTM], wv[kTN];
+#pragma unroll
+          for (int t = 0; t < kTM; ++t) a[t] = a_c[base[t] + off];
+          const T* wr = w_c + (dy * p.kw + dx) * kOT;
+#pragma unroll
+          for (int n = 0; n < kTN; ++n) wv[n] = wr[n];
+#pragma unroll
+          for (int t = 0; t < kTM; ++t)
+#pragma unroll
+            for (int n = 0; n < kTN; ++n) acc[t][n] += a[t] * wv[n];
+        }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kTM; ++t) {
+    if (!pvalid[t]) continue;
+    int pos = pos0 + pg + 64 * t;
+    int64_t s = s0 + pos / N;
+    int r = pos % N;
+#pragma unroll
+    for (int n = 0; n < kTN; ++n) {
+      int o = o0 + og * kTN + n;
+      if (o >= p.cout) continue;
+      T v = acc[t][n];
+      if (p.bias) v += p.bias[o];
+      const int64_t oi = (s * p.cout + o) * N + r;
+      if (p.mul) v = v * (p.mul_scale * gelu_grad_f(p.mul_alpha * p.mul[oi]));
+      if (p.res_ch == p.cout) v += p.res[oi];
+      else if (p.res_ch == 1) v += p.res[s * N + r];
+      p.out[oi] = v;
+    }
+  }
+}
+
+template <typename T>
+static int launch_conv(ConvParams<T> p, cudaStream_t st) {
+  const int N = p.lx * p.ly;
+  p.s_tile = kPT / N > 0 ? kPT / N : 1;
+  const int Hp = p.lx + p.kh - 1, Wp = p.ly + p.kw - 1;
+  size_t smem = ((size_t)kCK * p.s_tile * Hp * Wp + (size_t)kCK * p.kh * p.kw * kOT) * sizeof(T);
+  QTX_REQUIRE(smem <= 200 * 1024, QTX_ERR_UNSUPPORTED, "resconv: lattice too large for the conv tile (%zu B smem)", smem);
+  auto k = conv_circ_kernel<T>;
+  if (smem > 48 * 1024) QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int P = p.s_tile * N;
+  dim3 grid((unsigned)((p.ns + p.s_tile - 1) / p.s_tile), (unsigned)((p.cout + kOT - 1) / kOT),
+            (unsigned)((P + kPT - 1) / kPT));
+  k<<<grid, kConvThreads, smem, st>>>(p);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void spins_to_act_kernel(const int8_t* __restrict__ s, int64_t n, T* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (T)s[i];
+}
+
+// wT[c][o][kh-1-dy][kw-1-dx] = w[o][c][dy][dx]   (backward-data pass = conv with these weights)
+template <typename T>
+__global__ void weight_transpose_flip_kernel(const T* __restrict__ w, int cout, int cin, int kh, int kw,
+                                             T* __restrict__ wT) {
+  const int taps = kh * kw, n = cout * cin * taps;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    int tap = e % taps, c = (e / taps) % cin, o = e / (taps * cin);
+    int dy = tap / kw, dx = tap % kw;
+    wT[((size_t)c * cout + o) * taps + (kh - 1 - dy) * kw + (kw - 1 - dx)] = w[e];
+  }
+}
+
+// final layer (conv_nets.py:167-173, nn/activation.py:7-14,26-32, nn/conv.py:61-68): one CTA per sample.
+//   z = x / sqrt(nblocks+1); m = max|z|; sig = exp(z-m) | sinh-plus-one form; a_r = mean_c sig;
+//   significand = sum_r a_r * c1, exponent = m + log(1/N)           (all in model dtype)
+// If dz != null also writes the backward seed dz = dsig / sum(sig) / sqrt(nblocks+1).
+template <typename T>
+__global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict__ x, int64_t ns, int C, int N,
+                                                            T inv_norm, int final_act, double* __restrict__ sig_out,
+                                                            double* __restrict__ exp_out, T* __restrict__ dz) {
+  __shared__ T red[32];
+  __shared__ T bc;
+  const int64_t s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* xs = x + s * C * N;
+  const int CN = C * N;
+  T m = 0;
+  for (int e = tid; e < CN; e += blockDim.x) m = fmax(m, fabs(xs[e] * inv_norm));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    T mm = red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
+    bc = mm;
+  }
+  __syncthreads();
+  m = bc;
+  const T em = exp(-m);
+  // thread owns positions r = tid, tid+blockDim, ...: channel mean first, then the sum over positions
+  T part = 0, tot = 0;
+  for (int r = tid; r < N; r += blockDim.x) {
+    T a = 0;
+    for (int c = 0; c < C; ++c) {
+      T z = xs[c * N + r] * inv_norm;
+      T sg = exp(z - m);
+      if (final_act == 1) sg = (sg - exp(-z - m)) / T(2) + em;
+      a += sg;
+    }
+    tot += a;
+    part += a / (T)C;
+  }
+  __syncthreads();
+  T p1 = warp_sum(part), p2 = warp_sum(tot);
+  if (lane == 0) { red[warp] = p1; red[warp + 16] = p2; }
+  __syncthreads();
+  if (tid == 0) {
+    T a = 0, b = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += red[w]; b += red[w + 16]; }
+    const T ch = T(1) / (T)N;          // character of sector 0 (symmetry.py:391)
+    const T ech = log(ch);             // ScaleArray.from_value(character).normalize() (big_array.py:442-451)
+    const T c1 = ch * exp(T(0) - ech);
+    if (sig_out) sig_out[s] = (double)(a * c1);
+    if (exp_out) exp_out[s] = (double)(m + ech);
+    bc = b;
+  }
+  if (dz) {
+    __syncthreads();
+    const T total = bc;
+    T* d = dz + s * C * N;
+    for (int e = tid; e < CN; e += blockDim.x) {
+      T z = xs[e] * inv_norm;
+      T ds = exp(z - m);
+      if (final_act == 1) ds = (ds + exp(-z - m)) / T(2);
+      d[e] = ds / total * inv_norm;
+    }
+  }
+}
+
+// per-sample weight gradient written straight into the Jacobian row:
+//   O[s, col0 + (o*cin + c)*taps + tap] = sum_r delta[s,o,r] * f(alpha * a[s,c,r+tap])
+// CTA per (sample, out-channel tile of 32); thread tile 4 (o) x 3 (q = flattened (c, tap)).
+template <typename T, typename OutT>
+__global__ void __launch_bounds__(192) conv_wgrad_kernel(const T* __restrict__ delta, const T* __restrict__ a, int cin,
+                                                         int cout, int lx, int ly, int kh, int kw, T alpha, int in_act,
+                                                         OutT* __restrict__ out, int64_t ld, int64_t col0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = lx * ly, ph = (kh - 1) / 2, pw = (kw - 1) / 2;
+  const int Hp = lx + kh - 1, Wp = ly + kw - 1, HW = Hp * Wp, taps = kh * kw;
+  T* d_s = reinterpret_cast<T*>(smem_raw);   // [32][N]
+  T* a_s = d_s + 32 * N;                     // [kCK][HW]
+  const int64_t s = blockIdx.x;
+  const int o0 = blockIdx.y * 32;
+  const int tid = threadIdx.x, og = tid / 24, qg = tid % 24;
+  for (int e = tid; e < 32 * N; e += blockDim.x) {
+    int o = e / N, r = e % N;
+    d_s[e] = (o0 + o < cout) ? delta[(s * cout + o0 + o) * N + r] : T(0);
+  }
+  const int QC = kCK * taps;  // q's per chunk
+  for (int c0 = 0; c0 < cin; c0 += kCK) {
+    __syncthreads();
+    for (int e = tid; e < kCK * HW; e += blockDim.x) {
+      int ck = e / HW, q = e % HW, hp = q / Wp, wp = q % Wp;
+      int h = hp - ph, w = wp - pw;
+      h += (h < 0) ? lx : 0; h -= (h >= lx) ? lx : 0;
+      w += (w < 0) ? ly : 0; w -= (w >= ly) ? ly : 0;
+      T v = 0;
+      if (c0 + ck < cin) {
+        v = alpha * a[(s * cin + c0 + ck) * N + h * ly + w];
+        if (in_act == 1) v = gelu_f(v);
+      }
+      a_s[e] = v;
+    }
+    __syncthreads();
+    for (int qb = qg * 3; qb < QC; qb += 72) {
+      int offs[3];
+      bool qv[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        int q = qb + j;
+        qv[j] = q < QC && (c0 + q / taps) < cin;
+        int ck = qv[j] ? q / taps : 0, tap = qv[j] ? q % taps : 0;
+        offs[j] = ck * HW + (tap / kw) * Wp + (tap % kw);
+      }
+      T acc[4][3];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j] = 0;
+      for (int h = 0; h < lx; ++h)
+        for (int w = 0; w < ly; ++w) {
+          const int r = h * ly + w, pos = h * Wp + w;
+          T dv[4], av[3];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dv[i] = d_s[(og * 4 + i) * N + r];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) av[j] = a_s[offs[j] + pos];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[i][j] += dv[i] * av[j];
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int o = o0 + og * 4 + i;
+        if (o >= cout) continue;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (!qv[j]) continue;
+          int q = qb + j;
+          int c = c0 + q / taps, tap = q % taps;
+          out[s * ld + col0 + ((int64_t)o * cin + c) * taps + tap] = (OutT)acc[i][j];
+        }
+      }
+    }
+  }
+}
+
+// bias gradient: O[s, col0 + o] = sum_r delta[s,o,r]; warp per (sample, o)
+template <typename T, typename OutT>
+__global__ void conv_bgrad_kernel(const T* __restrict__ delta, int64_t ns, int cout, int N, OutT* __restrict__ out,
+                                  int64_t ld, int64_t col0) {
+  const int lane = threadIdx.x & 31;
+  int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= ns * cout) return;
+  int64_t s = wid / cout;
+  int o = (int)(wid % cout);
+  const T* d = delta + (s * cout + o) * N;
+  T acc = 0;
+  for (int r = lane; r < N; r += 32) acc += d[r];
+  acc = warp_sum(acc);
+  if (lane == 0) out[s * ld + col0 + o] = (OutT)acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic Metropolis propose / accept (models without local updates)
+// ---------------------------------------------------------------------------------------------
+struct ProposeParams {
+  const int8_t* spins;  // [ns, N] current chains
+  int8_t* new_spins;    // [ns, N]
+  uint8_t* moved;       // [ns]
+  int64_t ns;
+  int N, kind, max_nb, hop;
+  const int32_t* nbr;
+  const int32_t* inj_pos;   // [ns] for this step (nullable -> Philox)
+  const int32_t* inj_slot;
+  uint32_t seed_lo, seed_hi;
+  uint64_t step, chain0;
+};
+
+__global__ void __launch_bounds__(256) propose_kernel(ProposeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chain >= p.ns) return;
+  const int8_t* sp = p.spins + chain * p.N;
+  int8_t* np_ = p.new_spins + chain * p.N;
+  int pos, slot = 0;
+  if (p.inj_pos) {
+    pos = p.inj_pos[chain];
+    if (p.kind == QTX_SPIN_EXCHANGE) slot = p.inj_slot[chain];
+  } else {
+    uint32_t r0 = (uint32_t)(p.chain0 + chain), r1 = (uint32_t)p.step, r2 = (uint32_t)(p.step >> 32), r3 = 0;
+    philox4x32_10(r0, r1, r2, r3, p.seed_lo, p.seed_hi);
+    if (p.kind == QTX_LOCAL_FLIP) {
+      pos = (int)__umulhi(r0, (uint32_t)p.N);
+    } else {
+      // k-th site holding the hopping particle (same stream mapping as rbm_sweep_kernel)
+      int nhop = 0;
+      for (int j0 = 0; j0 < p.N; j0 += 32) {
+        int j = j0 + lane;
+        nhop += __popc(__ballot_sync(FULL, j < p.N && sp[j] == p.hop));
+      }
+      int k = (int)__umulhi(r0, (uint32_t)nhop);
+      pos = 0;
+      int seen = 0;
+      for (int j0 = 0; j0 < p.N; j0 += 32) {
+        int j = j0 + lane;
+        uint32_t bal = __ballot_sync(FULL, j < p.N && sp[j] == p.hop);
+        int c = __popc(bal);
+        if (k < seen + c) {
+          pos = j0 + (int)__fns(bal, 0, k - seen + 1);
+          break;
+        }
+        seen += c;
+      }
+      slot = (int)__umulhi(r1, (uint32_t)p.max_nb);
+    }
+  }
+  int j1 = -1;
+  if (p.kind == QTX_SPIN_EXCHANGE) {
+    j1 = p.nbr[pos * p.max_nb + slot];
+    if (j1 < 0) j1 = pos;
+  }
+  const int8_t s0 = sp[pos], s1 = j1 >= 0 ? sp[j1] : 0;
+  for (int j = lane; j < p.N; j += 32) {
+    int8_t v = sp[j];
+    if (p.kind == QTX_LOCAL_FLIP) {
+      if (j == pos) v = -v;
+    } else {
+      if (j == pos) v = s1;
+      if (j == j1) v = s0;
+      if (j == pos && j1 == pos) v = s0;
+    }
+    np_[j] = v;
+  }
+  if (lane == 0) p.moved[chain] = (p.kind == QTX_LOCAL_FLIP) ? 1 : (s0 != s1);
+}
+
+struct AcceptParams {
+  int8_t* spins;            // [ns, N] updated in place
+  const int8_t* new_spins;
+  const uint8_t* moved;
+  double* mult; double* expo;            // current psi, updated in place
+  const double* mult_new; const double* expo_new;
+  int64_t ns; int N;
+  double reweight;
+  const double* inj_u;      // [ns] for this step (nullable -> Philox)
+  uint32_t seed_lo, seed_hi;
+  uint64_t step, chain0;
+  int32_t* naccept;         // [ns] incremented (nullable)
+  uint8_t* accept_log;      // [ns] for this step (nullable)
+};
+
+// metropolis.py:299-322: ratio = |psi'/psi|^n formed in the container then densified
+__global__ void __launch_bounds__(256) accept_kernel(AcceptParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chain >= p.ns) return;
+  double u;
+  if (p.inj_u) {
+    u = p.inj_u[chain];
+  } else {
+    uint32_t r0 = (uint32_t)(p.chain0 + chain), r1 = (uint32_t)p.step, r2 = (uint32_t)(p.step >> 32), r3 = 0;
+    philox4x32_10(r0, r1, r2, r3, p.seed_lo, p.seed_hi);
+    u = (double)((((uint64_t)r2 << 32) | r3) >> 11) * 0x1.0p-53;
+  }
+  const double m0 = p.mult[chain], e0 = p.expo[chain], m1 = p.mult_new[chain], e1 = p.expo_new[chain];
+  double rate = fabs((m1 / m0) * exp(e1 - e0));
+  rate = (p.reweight == 2.0) ? rate * rate : pow(rate, p.reweight);
+  const bool zero_old = fabs(m0 * exp(e0)) == 0.0;
+  const bool acc = ((rate > 1.0 - u) || zero_old) && p.moved[chain];
+  if (acc) {
+    int8_t* sp = p.spins + chain * p.N;
+    const int8_t* np_ = p.new_spins + chain * p.N;
+    for (int j = lane; j < p.N; j += 32) sp[j] = np_[j];
+    if (lane == 0) {
+      p.mult[chain] = m1;
+      p.expo[chain] = e1;
+      if (p.naccept) p.naccept[chain] += 1;
+    }
+  }
+  if (lane == 0 && p.accept_log) p.accept_log[chain] = acc ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole-network drivers
+// ---------------------------------------------------------------------------------------------
+struct NetShape {
+  int nblocks, C, lx, ly, kh, kw, final_act;
+  int N() const { return lx * ly; }
+  int64_t w1_size(int i) const { return (int64_t)C * (i == 0 ? 1 : C) * kh * kw; }
+  int64_t w2_size() const { return (int64_t)C * C * kh * kw; }
+  int64_t nparams() const {
+    int64_t n = 0;
+    for (int i = 0; i < nblocks; ++i) n += w1_size(i) + C + w2_size() + (i == nblocks - 1 ? 0 : C);
+    return n;
+  }
+};
+
+template <typename T>
+static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins, int64_t ns, double* sig_out,
+                       double* exp_out, void* out, int out_dtype, int64_t ld, void* ws, cudaStream_t st) {
+  const int N = sh.N(), C = sh.C, nb = sh.nblocks;
+  const bool grad = out != nullptr;
+  const int64_t act = ns * C * N;
+  T* base = reinterpret_cast<T*>(ws);
+  T* x0 = base;                       // [ns, 1, N]
+  T* X = x0 + ns * N;                 // grad: (nb+1) buffers X_1..X_nb (+ scratch); else 1 buffer
+  T* Hs = X + (grad ? (int64_t)nb * act : act);   // grad: nb buffers; else 1
+  T* scratch = Hs + (grad ? (int64_t)nb * act : act);  // grad only: 2 gradient buffers + transposed weights
+  {
+    int64_t n = ns * N;
+    unsigned g = (unsigned)((n + 255) / 256);
+    if (g > 8u * num_sms()) g = 8u * num_sms();
+    spins_to_act_kernel<T><<<g, 256, 0, st>>>(spins, n, x0);
+    QTX_LAUNCH_CHECK();
+  }
+  // parameter offsets
+  const T* pw1[64]; const T* pb1[64]; const T* pw2[64]; const T* pb2[64];
+  int64_t col_w1[64], col_b1[64], col_w2[64], col_b2[64];
+  QTX_REQUIRE(nb <= 64, QTX_ERR_UNSUPPORTED, "resconv: more than 64 blocks");
+  {
+    int64_t off = 0;
+    for (int i = 0; i < nb; ++i) {
+      pw1[i] = params + off; col_w1[i] = off; off += sh.w1_size(i);
+      pb1[i] = params + off; col_b1[i] = off; off += C;
+      pw2[i] = params + off; col_w2[i] = off; off += sh.w2_size();
+      if (i == nb - 1) { pb2[i] = nullptr; col_b2[i] = -1; }
+      else { pb2[i] = params + off; col_b2[i] = off; off += C; }
+    }
+  }
+  // ---- forward (conv_nets.py:78-92) ----
+  for (int i = 0; i < nb; ++i) {
+    const T* xin = (i == 0) ? x0 : (grad ? X + (int64_t)(i - 1) * act : X);
+    T* h = grad ? Hs + (int64_t)i * act : Hs;
+    T* xout = grad ? X + (int64_t)i * act : X;
+    ConvParams<T> p{};
+    p.ns = ns; p.lx = sh.lx; p.ly = sh.ly; p.kh = sh.kh; p.kw = sh.kw;
+    p.in = xin; p.cin = (i == 0) ? 1 : C; p.cout = C; p.w = pw1[i]; p.bias = pb1[i];
+    p.alpha = (i == 0) ? (T)(1.0 / sqrt(2.0)) : (T)(1.0 / sqrt((double)(i + 1)));
+    p.in_act = (i == 0) ? 0 : 1;
+    p.res = nullptr; p.res_ch = 0; p.mul = nullptr; p.out = h;
+    int rc = launch_conv<T>(p, st);
+    if (rc) return rc;
+    ConvParams<T> q{};
+    q.ns = ns; q.lx = sh.lx; q.ly = sh.ly; q.kh = sh.kh; q.kw = sh.kw;
+    q.in = h; q.cin = C; q.cout = C; q.w = pw2[i]; q.bias = pb2[i]; q.alpha = 1; q.in_act = 1;
+    q.res = xin; q.res_ch = (i == 0) ? 1 : C; q.mul = nullptr; q.out = xout;
+    rc = launch_conv<T>(q, st);
+    if (rc) return rc;
+  }
+  const T* xlast = grad ? X + (int64_t)(nb - 1) * act : X;
+  T* dA = grad ? scratch : nullptr;           // gradient w.r.t. the current block output
+  T* dB = grad ? scratch + act : nullptr;
+  T* wT = grad ? scratch + 2 * act : nullptr;
+  resconv_final_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
+                                                        sh.final_act, sig_out, exp_out, dA);
+  QTX_LAUNCH_CHECK();
+  if (!grad) return QTX_OK;
+
+  // ---- backward: per-sample parameter gradients straight into the Jacobian rows ----
+  const int taps = sh.kh * sh.kw;
+  auto wgrad = [&](const T* delta, const T* a, int cin, T alpha, int in_act, int64_t col0) -> int {
+    size_t smem = ((size_t)32 * N + (size_t)kCK * (sh.lx + sh.kh - 1) * (sh.ly + sh.kw - 1)) * sizeof(T);
+    dim3 grid((unsigned)ns, (unsigned)((C + 31) / 32));
+    if (out_dtype == QTX_F64) {
+      auto k = conv_wgrad_kernel<T, double>;
+      if (smem > 48 * 1024) QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, 192, smem, st>>>(delta, a, cin, C, sh.lx, sh.ly, sh.kh, sh.kw, alpha, in_act, (double*)out, ld, col0);
+    } else {
+      auto k = conv_wgrad_kernel<T, float>;
+      if (smem > 48 * 1024) QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, 192, smem, st>>>(delta, a, cin, C, sh.lx, sh.ly, sh.kh, sh.kw, alpha, in_act, (float*)out, ld, col0);
+    }
+    QTX_LAUNCH_CHECK();
+    return QTX_OK;
+  };
+  auto bgrad = [&](const T* delta, int64_t col0) -> int {
+    unsigned g = (unsigned)((ns * C + 7) / 8);
+    if (out_dtype == QTX_F64) conv_bgrad_kernel<T, double><<<g, 256, 0, st>>>(delta, ns, C, N, (double*)out, ld, col0);
+    else conv_bgrad_kernel<T, float><<<g, 256, 0, st>>>(delta, ns, C, N, (float*)out, ld, col0);
+    QTX_LAUNCH_CHECK();
+    return QTX_OK;
+  };
+  T* dX = dA;  // gradient w.r.t. X_{i+1}
+  T* tmp = dB;
+  for (int i = nb - 1; i >= 0; --i) {
+    const T* xin = (i == 0) ? x0 : X + (int64_t)(i - 1) * act;
+    const T* h = Hs + (int64_t)i * act;
+    int rc;
+    // conv2: y = conv2(gelu(h)) + b2
+    if ((rc = wgrad(dX, h, C, (T)1, 1, col_w2[i]))) return rc;
+    if (col_b2[i] >= 0 && (rc = bgrad(dX, col_b2[i]))) return rc;
+    // dh = conv2^T(dX) * gelu'(h)
+    weight_transpose_flip_kernel<T><<<64, 256, 0, st>>>(pw2[i], C, C, sh.kh, sh.kw, wT);
+    QTX_LAUNCH_CHECK();
+    ConvParams<T> p{};
+    p.ns = ns; p.lx = sh.lx; p.ly = sh.ly; p.kh = sh.kh; p.kw = sh.kw;
+    p.in = dX; p.cin = C; p.cout = C; p.w = wT; p.bias = nullptr; p.alpha = 1; p.in_act = 0;
+    p.res = nullptr; p.res_ch = 0; p.mul = h; p.mul_alpha = 1; p.mul_scale = 1; p.out = tmp;
+    if ((rc = launch_conv<T>(p, st))) return rc;
+    // conv1: h = conv1(a1) + b1
+    const T alpha1 = (i == 0) ? (T)(1.0 / sqrt(2.0)) : (T)(1.0 / sqrt((double)(i + 1)));
+    if ((rc = wgrad(tmp, xin, (i == 0) ? 1 : C, alpha1, (i == 0) ? 0 : 1, col_w1[i]))) return rc;
+    if ((rc = bgrad(tmp, col_b1[i]))) return rc;
+    if (i > 0) {
+      // dX_in = conv1^T(dh) * gelu'(x/sqrt(i+1)) / sqrt(i+1) + dX   (residual)
+      weight_transpose_flip_kernel<T><<<64, 256, 0, st>>>(pw1[i], C, C, sh.kh, sh.kw, wT);
+      QTX_LAUNCH_CHECK();
+      ConvParams<T> q{};
+      q.ns = ns; q.lx = sh.lx; q.ly = sh.ly; q.kh = sh.kh; q.kw = sh.kw;
+      q.in = tmp; q.cin = C; q.cout = C; q.w = wT; q.bias = nullptr; q.alpha = 1; q.in_act = 0;
+      q.res = dX; q.res_ch = C; q.mul = xin; q.mul_alpha = alpha1; q.mul_scale = alpha1;
+      // in-place on dX is safe: each thread reads res at exactly the index it writes
+      q.out = dX;
+      if ((rc = launch_conv<T>(q, st))) return rc;
+    }
+  }
+  (void)taps;
+  return QTX_OK;
+}
+
+static size_t resconv_ws(int dtype, int64_t ns, const NetShape& sh, bool grad) {
+  size_t es = dtype == QTX_F64 ? 8 : 4;
+  int64_t act = ns * sh.C * sh.N();
+  int64_t elems = ns * sh.N();
+  if (grad) elems += (int64_t)(2 * sh.nblocks + 2) * act + (int64_t)sh.C * sh.C * sh.kh * sh.kw;
+  else elems += 2 * act;
+  return (size_t)elems * es + 256;
+}
+
+}  // namespace qtx
+
+using namespace qtx;
+
+static bool shape_ok(int nblocks, int C, int lx, int ly, int kh, int kw, int final_act) {
+  return nblocks >= 1 && C >= 1 && lx >= 1 && ly >= 1 && kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1) && kh <= lx + 1 &&
+         (final_act == 0 || final_act == 1);
+}
+
+extern "C" int64_t qtx_resconv_nparams(int nblocks, int channels, int lx, int ly, int kh, int kw) {
+  NetShape sh{nblocks, channels, lx, ly, kh, kw, 0};
+  return sh.nparams();
+}
+
+extern "C" size_t qtx_resconv_workspace_size(int model_dtype, int64_t ns, int nblocks, int channels, int lx, int ly,
+                                             int kh, int kw, int need_grad) {
+  NetShape sh{nblocks, channels, lx, ly, kh, kw, 0};
+  return resconv_ws(model_dtype, ns, sh, need_grad != 0);
+}
+
+extern "C" int qtx_resconv_forward(int model_dtype, const void* params, int nblocks, int channels, int lx, int ly,
+                                   int kh, int kw, int final_act, const int8_t* spins, int64_t ns,
+                                   double* significand_out, double* exponent_out, void* workspace,
+                                   size_t workspace_bytes, qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(params && spins && significand_out && exponent_out && workspace, QTX_ERR_INVALID,
+              "qtx_resconv_forward: bad argument");
+  QTX_REQUIRE(shape_ok(nblocks, channels, lx, ly, kh, kw, final_act), QTX_ERR_INVALID,
+              "qtx_resconv_forward: bad network shape");
+  NetShape sh{nblocks, channels, lx, ly, kh, kw, final_act};
+  QTX_REQUIRE(workspace_bytes >= resconv_ws(model_dtype, ns, sh, false), QTX_ERR_INVALID,
+              "qtx_resconv_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model_dtype == QTX_F32)
+    return resconv_run<float>(sh, (const float*)params, spins, ns, significand_out, exponent_out, nullptr, 0, 0,
+                              workspace, st);
+  if (model_dtype == QTX_F64)
+    return resconv_run<double>(sh, (const double*)params, spins, ns, significand_out, exponent_out, nullptr, 0, 0,
+                               workspace, st);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_resconv_forward: bad dtype %d", model_dtype);
+}
+
+extern "C" int qtx_resconv_jacobian(int model_dtype, const void* params, int nblocks, int channels, int lx, int ly,
+                                    int kh, int kw, int final_act, const int8_t* spins, int64_t ns, int out_dtype,
+                                    void* out, int64_t ld, double* significand_out, double* exponent_out,
+                                    void* workspace, size_t workspace_bytes, qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(params && spins && out && workspace, QTX_ERR_INVALID, "qtx_resconv_jacobian: bad argument");
+  QTX_REQUIRE(shape_ok(nblocks, channels, lx, ly, kh, kw, final_act), QTX_ERR_INVALID,
+              "qtx_resconv_jacobian: bad network shape");
+  NetShape sh{nblocks, channels, lx, ly, kh, kw, final_act};
+  QTX_REQUIRE(ld >= sh.nparams(), QTX_ERR_INVALID, "qtx_resconv_jacobian: ld smaller than the parameter count");
+  QTX_REQUIRE(out_dtype == QTX_F32 || out_dtype == QTX_F64, QTX_ERR_INVALID, "qtx_resconv_jacobian: bad out dtype");
+  QTX_REQUIRE(workspace_bytes >= resconv_ws(model_dtype, ns, sh, true), QTX_ERR_INVALID,
+              "qtx_resconv_jacobian: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model_dtype == QTX_F32)
+    return resconv_run<float>(sh, (const float*)params, spins, ns, significand_out, exponent_out, out, out_dtype, ld,
+                              workspace, st);
+  if (model_dtype == QTX_F64)
+    return resconv_run<double>(sh, (const double*)params, spins, ns, significand_out, exponent_out, out, out_dtype,
+                               ld, workspace, st);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_resconv_jacobian: bad dtype %d", model_dtype);
+}
+
+extern "C" int qtx_metropolis_propose(int kind, const int8_t* spins, int64_t ns, int N, const int32_t* nbr_table,
+                                      int max_nb, int hop, const int32_t* inj_pos, const int32_t* inj_slot,
+                                      uint64_t seed, uint64_t step, uint64_t chain0, int8_t* new_spins,
+                                      uint8_t* moved, qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(spins && new_spins && moved && N > 0, QTX_ERR_INVALID, "qtx_metropolis_propose: bad argument");
+  QTX_REQUIRE(kind == QTX_LOCAL_FLIP || (kind == QTX_SPIN_EXCHANGE && nbr_table && max_nb > 0), QTX_ERR_INVALID,
+              "qtx_metropolis_propose: bad kind / neighbour table");
+  ProposeParams p;
+  p.spins = spins; p.new_spins = new_spins; p.moved = moved; p.ns = ns; p.N = N; p.kind = kind; p.max_nb = max_nb;
+  p.hop = hop; p.nbr = nbr_table; p.inj_pos = inj_pos; p.inj_slot = inj_slot;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.step = step; p.chain0 = chain0;
+  propose_kernel<<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_metropolis_accept(int8_t* spins, const int8_t* new_spins, const uint8_t* moved, int64_t ns, int N,
+                                     double* mult, double* expo, const double* mult_new, const double* expo_new,
+                                     double reweight, const double* inj_u, uint64_t seed, uint64_t step,
+                                     uint64_t chain0, int32_t* naccept, uint8_t* accept_log, qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(spins && new_spins && moved && mult && expo && mult_new && expo_new && N > 0, QTX_ERR_INVALID,
+              "qtx_metropolis_accept: bad argument");
+  AcceptParams p;
+  p.spins = spins; p.new_spins = new_spins; p.moved = moved; p.mult = mult; p.expo = expo; p.mult_new = mult_new;
+  p.expo_new = expo_new; p.ns = ns; p.N = N; p.reweight = reweight; p.inj_u = inj_u;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.step = step; p.chain0 = chain0;
+  p.naccept = naccept; p.accept_log = accept_log;
+  accept_kernel<<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}

@@ -1,0 +1,98 @@
+"""ResConv entry points of ``Variational``: batched forward, generic Metropolis sweep (full forward
+per proposal, quantax/state/variational.py:383-384) and the per-sample Jacobian.  All arithmetic
+is in libqtx_b200 (csrc/resconv.cu); this module only chunks batches so the activation workspace
+stays bounded (the role of ``max_parallel`` / ``forward_chunk`` in the reference,
+quantax/state/variational.py:166-174, quantax/utils/function.py:88-146)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .utils import ScaleArray
+
+# default per-launch sample caps when the state has no max_parallel (bytes of activation workspace)
+_FWD_BUDGET = 4 << 30
+_BWD_BUDGET = 12 << 30
+
+
+def _shape_args(m):
+    return (m.nblocks, m.channels, m.Lx, m.Ly, m.kh, m.kw)
+
+
+def _chunk(state, ns, grad):
+    m = state.model
+    mdt = _lib.dtype_code(m.dtype)
+    per = _lib.lib().qtx_resconv_workspace_size(mdt, 1, *_shape_args(m), int(grad))
+    cap = max(1, (_BWD_BUDGET if grad else _FWD_BUDGET) // max(per, 1))
+    user = state.backward_chunk if grad else state.forward_chunk
+    if user is not None:
+        cap = min(cap, int(user))
+    return max(1, min(ns, cap))
+
+
+def resconv_forward(state, s: torch.Tensor) -> ScaleArray:
+    m = state.model
+    mdt = _lib.dtype_code(m.dtype)
+    ns = s.shape[0]
+    sig = torch.empty(ns, dtype=torch.float64, device=s.device)
+    ex = torch.empty(ns, dtype=torch.float64, device=s.device)
+    if ns == 0:
+        return ScaleArray(sig, ex)
+    chunk = _chunk(state, ns, False)
+    wsz = _lib.lib().qtx_resconv_workspace_size(mdt, chunk, *_shape_args(m), 0)
+    ws = state._workspace("resconv_fwd", wsz)
+    for lo in range(0, ns, chunk):
+        hi = min(ns, lo + chunk)
+        _lib.call("qtx_resconv_forward", mdt, _lib.ptr(m.params), *_shape_args(m), m.final, _lib.ptr(s[lo:hi]),
+                  hi - lo, _lib.ptr(sig[lo:hi]), _lib.ptr(ex[lo:hi]), _lib.ptr(ws), wsz, _lib.stream())
+    return ScaleArray(sig, ex)
+
+
+def resconv_jacobian(state, s: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    m = state.model
+    mdt = _lib.dtype_code(m.dtype)
+    ns = s.shape[0]
+    if ns == 0:
+        return out
+    chunk = _chunk(state, ns, True)
+    wsz = _lib.lib().qtx_resconv_workspace_size(mdt, chunk, *_shape_args(m), 1)
+    ws = state._workspace("resconv_bwd", wsz)
+    for lo in range(0, ns, chunk):
+        hi = min(ns, lo + chunk)
+        _lib.call("qtx_resconv_jacobian", mdt, _lib.ptr(m.params), *_shape_args(m), m.final, _lib.ptr(s[lo:hi]),
+                  hi - lo, _lib.dtype_code(out.dtype), _lib.ptr2d(out[lo:hi]), out.stride(0), None, None,
+                  _lib.ptr(ws), wsz, _lib.stream())
+    return out
+
+
+def resconv_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed, step0, chain0, injected, record):
+    """``_partial_sweep`` for a state without local updates (metropolis.py:246-275): every step is
+    propose -> full forward of the proposed chains -> accept, all enqueued on the stream with no
+    host synchronisation; psi of the current chains is carried along (Samples.psi)."""
+    ns, N = spins.shape
+    dev = spins.device
+    psi = resconv_forward(state, spins)
+    mult, expo = psi.significand, psi.exponent
+    new_spins = torch.empty_like(spins)
+    moved = torch.empty(ns, dtype=torch.uint8, device=dev)
+    nacc = torch.zeros(ns, dtype=torch.int32, device=dev)
+    log = torch.empty((nsweeps, ns), dtype=torch.uint8, device=dev) if record else None
+    pos = slot = u = None
+    if injected is not None:
+        pos, slot, u = injected
+        pos = pos.to(device=dev, dtype=torch.int32).contiguous()
+        slot = None if slot is None else slot.to(device=dev, dtype=torch.int32).contiguous()
+        u = u.to(device=dev, dtype=torch.float64).contiguous()
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    st = _lib.stream()
+    for t in range(nsweeps):
+        _lib.call("qtx_metropolis_propose", int(kind), _lib.ptr(spins), ns, N, _lib.ptr(nbr), int(max_nb), int(hop),
+                  None if pos is None else _lib.ptr(pos[t]), None if slot is None else _lib.ptr(slot[t]), seed,
+                  int(step0) + t, int(chain0), _lib.ptr(new_spins), _lib.ptr(moved), st)
+        psi_new = resconv_forward(state, new_spins)
+        _lib.call("qtx_metropolis_accept", _lib.ptr(spins), _lib.ptr(new_spins), _lib.ptr(moved), ns, N,
+                  _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(psi_new.significand), _lib.ptr(psi_new.exponent),
+                  float(reweight), None if u is None else _lib.ptr(u[t]), seed, int(step0) + t, int(chain0),
+                  _lib.ptr(nacc), None if log is None else _lib.ptr(log[t]), st)
+    out = ScaleArray(mult, expo)
+    return out, out, nacc, log
