@@ -97,6 +97,50 @@ def matvec(A: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return v
 
 
+class _CudaOps:
+    """The dense kernels used by the distributed solve (tests substitute CPU stand-ins to exercise
+    the exchange logic over gloo)."""
+
+    def __init__(self, nslices):
+        self.nslices = nslices
+
+    def gram(self, A):
+        return gram(A, nslices=self.nslices)
+
+    pinv_eig_solve = staticmethod(pinv_eig_solve)
+    matvec_t = staticmethod(matvec_t)
+
+
+def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops):
+    """MinSR solve with the rows of A sharded over the ranks (solver.py:131-147 under GSPMD):
+    row-sharded -> column-sharded all-to-all (the parameter axis is zero-padded to a multiple of
+    the world size like ``array_extend(Adag, ndevices)``, solver.py:136), local Gram of the column
+    shard, all-reduce of the partial Ns x Ns Grams, replicated eigh + pseudo-inverse, column shard
+    of x = A^T y, all-gather.  Returns (x [Np], info)."""
+    dist = _dist()
+    P = dist.get_world_size()
+    nl, npar = A.shape
+    npc = (npar + P - 1) // P
+    if npc * P == npar:
+        send = A.view(nl, P, npc).permute(1, 0, 2).contiguous()
+    else:
+        flat = torch.zeros((nl, P * npc), dtype=A.dtype, device=A.device)
+        flat[:, :npar] = A
+        send = flat.view(nl, P, npc).permute(1, 0, 2).contiguous()
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    Ac = recv.view(P * nl, npc)  # all Ns rows (rank-major = global sample order), this rank's columns
+    T = ops.gram(Ac)
+    dist.all_reduce(T)
+    bfull = torch.empty(P * nl, dtype=b.dtype, device=b.device)
+    dist.all_gather_into_tensor(bfull, b.contiguous())
+    y, info = ops.pinv_eig_solve(T, bfull, rtol, atol)
+    xc = ops.matvec_t(Ac, y)
+    x = torch.empty(P * npc, dtype=xc.dtype, device=xc.device)
+    dist.all_gather_into_tensor(x, xc.contiguous())
+    return x[:npar].contiguous(), info
+
+
 # ---- solvers (callables (A, b) -> x; A is the rank-local row block of Obar) -----------------------
 def _check_snr(tol_snr: float):
     if tol_snr > 1e-6:
@@ -114,29 +158,9 @@ def minnorm_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: f
             y, info = pinv_eig_solve(T, b, rtol, atol)
             solve.last_info = info
             return matvec_t(A, y)
-        dist = _dist()
-        nl, npar = A.shape
-        npc = (npar + P - 1) // P  # array_extend(Adag, ndevices): pad the parameter axis (solver.py:136)
-        send = torch.zeros((P, nl, npc), dtype=A.dtype, device=A.device)
-        if npc * P == npar:
-            send.copy_(A.view(nl, P, npc).permute(1, 0, 2))
-        else:
-            flat = torch.zeros((nl, P * npc), dtype=A.dtype, device=A.device)
-            flat[:, :npar] = A
-            send.copy_(flat.view(nl, P, npc).permute(1, 0, 2))
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send)  # row-sharded -> column-sharded
-        Ac = recv.view(P * nl, npc)
-        T = gram(Ac, nslices=nslices)
-        dist.all_reduce(T)
-        bfull = torch.empty(P * nl, dtype=torch.float64, device=A.device)
-        dist.all_gather_into_tensor(bfull, b.contiguous())
-        y, info = pinv_eig_solve(T, bfull, rtol, atol)
+        x, info = distributed_minnorm(A, b, rtol, atol, _CudaOps(nslices))
         solve.last_info = info
-        xc = matvec_t(Ac, y)
-        x = torch.empty(P * npc, dtype=torch.float64, device=A.device)
-        dist.all_gather_into_tensor(x, xc)
-        return x[:npar].contiguous()
+        return x
 
     solve.last_info = None
     return solve
