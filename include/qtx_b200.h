@@ -198,6 +198,25 @@ int qtx_metropolis_accept(int8_t* spins, const int8_t* new_spins, const uint8_t*
                           uint8_t* accept_log, qtx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * State-level symmetry projection psi(s) = sum_g w_g psi(T_g s), w_g = chi_g chi_0 / |G|
+ * (quantax/state/variational.py:262-266, quantax/symmetry/symmetry.py:325-392).
+ *   images : out int8 [ns, nsymm, N], s_g = s[perm_g]; with z2 != 0 the second half is -s[perm_g]
+ *            (nsymm = 2 nperm).  perm int32 [nperm, N].
+ *   combine: signed log-sum-exp over the images in container arithmetic; (mult, expo) [ns, nsymm]
+ *            -> [ns].  kind 0 = LogArray result (sign, logabs), kind 1 = ScaleArray result
+ *            (significand, exponent).  coef_out (nullable) float64 [ns, nsymm] = w_g psi_g / psi,
+ *            the image weights of the projected log-derivative (variational.py:438-491).
+ *   weighted_rowsum: out[s, :] = sum_g coef[s, g] J[s nsymm + g, :]  (projected Jacobian rows).
+ * ------------------------------------------------------------------------------------------ */
+int qtx_symm_images(const int8_t* spins, int64_t ns, int N, const int32_t* perm, int nperm, int z2,
+                    int8_t* out, qtx_stream_t stream);
+int qtx_symm_combine(const double* mult, const double* expo, int64_t ns, int nsymm,
+                     const double* weights, int kind, double* mult_out, double* expo_out,
+                     double* coef_out, qtx_stream_t stream);
+int qtx_weighted_rowsum(int dtype, const void* J, int64_t ldj, const double* coef, int64_t ns,
+                        int nsymm, int64_t np, void* out, int64_t ldo, qtx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Connected-configuration enumeration for generic models (bit-exact mirror of
  * _apply_off_diag + _get_conn, operator.py:96-165).  Terms with `nflips_sel` flips only.
  *   count:  nonnan_out / valid_out int32 [ns]  (valid = not NaN and |H| > 1e-8)

@@ -6,7 +6,7 @@ ChenAo-Phys/quantax (README.md:42-76): same sub-module names and class signature
 arrays are CUDA ``torch.Tensor`` objects, all arithmetic runs in hand-written sm_100a kernels
 behind the C ABI of ``include/qtx_b200.h``.  There is no CPU fallback.
 """
-from . import global_defs, sites, utils, nn, operator, model, state, sampler, optimizer  # noqa: F401
+from . import global_defs, sites, symmetry, utils, nn, operator, model, state, sampler, optimizer  # noqa: F401
 from .global_defs import (  # noqa: F401
     PARTICLE_TYPE,
     get_default_dtype,

@@ -44,6 +44,9 @@ SIGNATURES = {
                                       _vp]),
     "qtx_metropolis_accept": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f64, _vp, _u64, _u64, _u64, _vp,
                                      _vp, _vp]),
+    "qtx_symm_images": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "qtx_symm_combine": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "qtx_weighted_rowsum": (_i32, [_i32, _vp, _i64, _vp, _i64, _i32, _i64, _vp, _i64, _vp]),
     "qtx_conn_count": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "qtx_exclusive_scan_i32": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "qtx_conn_fill": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -20,6 +20,7 @@
 // (all 512 columns), so `s` digits need ceil(s / 4) passes over K.  One pipeline stage holds one
 // 32-element K block of all needed digit slices of both row panels (2 * s * 4 KB).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -192,7 +193,11 @@ __global__ void __launch_bounds__(256) gram_split_kernel(const T* __restrict__ A
     }
 #pragma unroll
     for (int a = 0; a < kMaxSlices; ++a)
-      if (a < nslices) *reinterpret_cast<uint32_t*>(Q + ((int64_t)a * ns_pad + r) * kc_pad + kb) = w[a];
+      if (a < nslices) {
+        // K-blocked layout [slice][kblock][row][32 B]: one TMA box (128 rows x 32 B) is a contiguous 4 KB run
+        const int64_t nkb = kc_pad / kBK;
+        *reinterpret_cast<uint32_t*>(Q + (((int64_t)a * nkb + kb / kBK) * ns_pad + r) * kBK + (kb % kBK)) = w[a];
+      }
   }
 }
 
@@ -218,11 +223,32 @@ __device__ __forceinline__ void tile_from_index(int t, int& I, int& J) {
   J = t - i * (i + 1) / 2;
 }
 
+// One K block of one pass: all digit pairs (a, b) with level d = a + b in the pass, fully unrolled at
+// compile time so that the single issuing thread spends ~3 instructions per MMA (the descriptors of a
+// stage differ from the stage-0 descriptors only by a constant added to the low word).
+template <int S, int PASS>
+__device__ __forceinline__ void issue_kblock(uint32_t tmem_base, uint32_t desc_lo, uint32_t desc_hi, uint32_t acc_first) {
+  constexpr int d_lo = 2 + PASS * kLevelsPerPass;
+  constexpr int d_hi = (d_lo + kLevelsPerPass - 1 < S + 1) ? d_lo + kLevelsPerPass - 1 : S + 1;
+#pragma unroll
+  for (int d = d_lo; d <= d_hi; ++d) {
+    const int a_lo = (d - S > 1) ? d - S : 1, a_hi = (d - 1 < S) ? d - 1 : S;
+#pragma unroll
+    for (int a = a_lo; a <= a_hi; ++a) {
+      const int b = d - a;
+      const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo + (uint32_t)(a - 1) * (kSliceBytes >> 4));
+      const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo + (uint32_t)(S + b - 1) * (kSliceBytes >> 4));
+      umma_i8(tmem_base + (uint32_t)(d - d_lo) * kTile, da, db, kIdescI8, a == a_lo ? acc_first : 1u);
+    }
+  }
+}
+
+template <int S>
 __global__ void __launch_bounds__(kThreads, 1) gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, GramTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int s = p.nslices;
-  const uint32_t stage_bytes = 2u * s * kSliceBytes;
+  constexpr uint32_t stage_bytes = 2u * S * kSliceBytes;
+  constexpr int npasses = (S + kLevelsPerPass - 1) / kLevelsPerPass;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
@@ -244,9 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-
   const int ntiles = p.nb * (p.nb + 1) / 2;
-  const int npasses = (s + kLevelsPerPass - 1) / kLevelsPerPass;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -255,16 +279,20 @@ __global__ void __launch_bounds__(kThreads, 1) gram_tc_kernel(const __grid_const
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int I, J;
         tile_from_index(t, I, J);
+#pragma unroll
         for (int pass = 0; pass < npasses; ++pass) {
-          const int d_hi = min(2 + (pass + 1) * kLevelsPerPass - 1, s + 1);
-          const int nsl = min(s, d_hi - 1);  // digit slices 1..nsl are needed by this pass
+          const int d_hi = min(2 + (pass + 1) * kLevelsPerPass - 1, S + 1);
+          const int nsl = min(S, d_hi - 1);
           for (int kb = 0; kb < p.nkb; ++kb) {
             mbar_wait(empty_bar + stage, phase ^ 1);
-            mbar_expect_tx(full_bar + stage, 2u * nsl * kSliceBytes);
             unsigned char* base = smem + (size_t)stage * stage_bytes;
-            for (int a = 0; a < nsl; ++a) {
-              tma_load_3d(base + (size_t)a * kSliceBytes, &tmap, full_bar + stage, kb * kBK, I * kTile, a);
-              tma_load_3d(base + (size_t)(s + a) * kSliceBytes, &tmap, full_bar + stage, kb * kBK, J * kTile, a);
+            mbar_expect_tx(full_bar + stage, 2u * nsl * kSliceBytes);
+#pragma unroll
+            for (int a = 0; a < S; ++a) {
+              if (a < nsl) {
+                tma_load_3d(base + (size_t)a * kSliceBytes, &tmap, full_bar + stage, 0, I * kTile, a * p.nkb + kb);
+                tma_load_3d(base + (size_t)(S + a) * kSliceBytes, &tmap, full_bar + stage, 0, J * kTile, a * p.nkb + kb);
+              }
             }
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
@@ -275,26 +303,20 @@ __global__ void __launch_bounds__(kThreads, 1) gram_tc_kernel(const __grid_const
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, tphase = 0;
+      const uint64_t desc0 = make_desc_sw32(smem_u32(smem));
+      const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+#pragma unroll
         for (int pass = 0; pass < npasses; ++pass) {
-          const int d_lo = 2 + pass * kLevelsPerPass;
-          const int d_hi = min(d_lo + kLevelsPerPass - 1, s + 1);
           mbar_wait(tmem_empty, tphase ^ 1);  // epilogue has drained the accumulators
           tc_fence_after();
           for (int kb = 0; kb < p.nkb; ++kb) {
             mbar_wait(full_bar + stage, phase);
             tc_fence_after();
-            const uint32_t base = smem_u32(smem + (size_t)stage * stage_bytes);
-            for (int d = d_lo; d <= d_hi; ++d) {
-              const uint32_t acc = tmem_base + (uint32_t)(d - d_lo) * kTile;
-              const int a_lo = max(1, d - s), a_hi = min(s, d - 1);
-              for (int a = a_lo; a <= a_hi; ++a) {
-                const int b = d - a;
-                uint64_t da = make_desc_sw32(base + (uint32_t)(a - 1) * kSliceBytes);
-                uint64_t db = make_desc_sw32(base + (uint32_t)(s + b - 1) * kSliceBytes);
-                umma_i8(acc, da, db, kIdescI8, (kb > 0 || a > a_lo) ? 1u : 0u);
-              }
-            }
+            const uint32_t desc_lo = desc_lo0 + stage * (stage_bytes >> 4);
+            const uint32_t acc_first = kb > 0 ? 1u : 0u;
+            if (pass == 0) issue_kblock<S, 0>(tmem_base, desc_lo, desc_hi, acc_first);
+            else issue_kblock<S, (npasses > 1 ? 1 : 0)>(tmem_base, desc_lo, desc_hi, acc_first);
             umma_commit(empty_bar + stage);  // frees the smem stage once these MMAs have read it
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
@@ -314,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_tc_kernel(const __grid_const
       const double rs_i = (row < p.ns) ? p.rowscale[row] : 0.0;
       for (int pass = 0; pass < npasses; ++pass) {
         const int d_lo = 2 + pass * kLevelsPerPass;
-        const int d_hi = min(d_lo + kLevelsPerPass - 1, s + 1);
+        const int d_hi = min(d_lo + kLevelsPerPass - 1, S + 1);
         mbar_wait(tmem_full, tphase);
         tc_fence_after();
         const bool add = (pass > 0) || (p.accum != 0);
@@ -356,6 +378,14 @@ __global__ void __launch_bounds__(kThreads, 1) gram_tc_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int S>
+static int launch_gram_tc(const CUtensorMap& tmap, const GramTcParams& p, int grid, size_t smem, cudaStream_t st) {
+  QTX_CUDA(cudaFuncSetAttribute(gram_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_tc_kernel<S><<<grid, kThreads, smem, st>>>(tmap, p);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,8 +442,9 @@ int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int ns
   int8_t* Q = reinterpret_cast<int8_t*>(((uintptr_t)(rowscale + ns_pad) + 255) & ~(uintptr_t)255);
 
   CUtensorMap tmap;
-  cuuint64_t gdim[3] = {(cuuint64_t)kc_pad, (cuuint64_t)ns_pad, (cuuint64_t)s};
-  cuuint64_t gstride[2] = {(cuuint64_t)kc_pad, (cuuint64_t)kc_pad * (cuuint64_t)ns_pad};
+  // dims: (byte in K block, row, slice * nkb + kblock)
+  cuuint64_t gdim[3] = {(cuuint64_t)kBK, (cuuint64_t)ns_pad, (cuuint64_t)s * (cuuint64_t)(kc_pad / kBK)};
+  cuuint64_t gstride[2] = {(cuuint64_t)kBK, (cuuint64_t)kBK * (cuuint64_t)ns_pad};
   cuuint32_t box[3] = {kBK, kTile, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, Q, gdim, gstride, box, estr,
@@ -424,9 +455,12 @@ int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int ns
   const uint32_t stage_bytes = 2u * s * kSliceBytes;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
+  if (const char* e = getenv("QTX_GRAM_STAGES")) {
+    int v = atoi(e);
+    if (v >= 2 && v <= stages) stages = v;
+  }
   QTX_REQUIRE(stages >= 2, QTX_ERR_UNSUPPORTED, "qtx_gram: pipeline does not fit in shared memory");
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 2) * 8 + 16;
-  QTX_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   GramTcParams p;
   p.nb = (int)(ns_pad / kTile);
@@ -451,8 +485,18 @@ int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int ns
     QTX_LAUNCH_CHECK();
     p.nkb = (int)(kc_pad / kBK);
     p.accum = (accum != 0 || chunk > 0) ? 1 : 0;
-    gram_tc_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
-    QTX_LAUNCH_CHECK();
+    int rc = QTX_OK;
+    switch (s) {
+      case 1: rc = launch_gram_tc<1>(tmap, p, grid, smem, st); break;
+      case 2: rc = launch_gram_tc<2>(tmap, p, grid, smem, st); break;
+      case 3: rc = launch_gram_tc<3>(tmap, p, grid, smem, st); break;
+      case 4: rc = launch_gram_tc<4>(tmap, p, grid, smem, st); break;
+      case 5: rc = launch_gram_tc<5>(tmap, p, grid, smem, st); break;
+      case 6: rc = launch_gram_tc<6>(tmap, p, grid, smem, st); break;
+      case 7: rc = launch_gram_tc<7>(tmap, p, grid, smem, st); break;
+      default: rc = launch_gram_tc<8>(tmap, p, grid, smem, st); break;
+    }
+    if (rc) return rc;
   }
   return QTX_OK;
 }

@@ -543,6 +543,10 @@ __global__ void rbm_ref_forward_kernel(const T* __restrict__ W, int N, int M, co
 // Jacobian: O[s, i*N+j] = tanh(theta_i) s_j ; O[s, M*N+i] = tanh(theta_i)
 // one CTA per (sample, column tile); fully coalesced 16-byte stores
 // ---------------------------------------------------------------------------------------------
+template <typename OutT> struct OutVec2;
+template <> struct OutVec2<double> { using type = double2; };
+template <> struct OutVec2<float> { using type = float2; };
+
 template <typename T, typename OutT>
 __global__ void __launch_bounds__(256) rbm_jacobian_kernel(const T* __restrict__ W, const T* __restrict__ b, int N,
                                                            int M, const int8_t* __restrict__ spins, int64_t ns,
@@ -567,33 +571,36 @@ __global__ void __launch_bounds__(256) rbm_jacobian_kernel(const T* __restrict__
   const double scale = row_scale ? row_scale[s] : 1.0;
   const int64_t MN = (int64_t)M * N, NP = MN + M;
   OutT* row = out + s * ld;
-  constexpr int V = 16 / sizeof(OutT);  // elements per 16-byte store
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-  if (vec_ok) {
-    const int64_t stride = (int64_t)blockDim.x * V;
-    const int di = (int)(stride / N), dj = (int)(stride % N);
-    int64_t k = (int64_t)threadIdx.x * V;
-    int i = (int)(k / N), j = (int)(k % N);
-    for (; k < NP; k += stride) {
-      OutT v[V];
-      int ii = i, jj = j;
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        int64_t kk = k + e;
-        double val = 0.0;
-        if (kk < MN) val = (double)(t_s[ii] * s_s[jj]);
-        else if (kk < NP) val = (double)t_s[kk - MN];
-        if (col_mean && kk < NP) val -= col_mean[kk];
-        v[e] = (OutT)(val * scale);
-        if (++jj == N) { jj = 0; ++ii; }
+  using V2 = typename OutVec2<OutT>::type;
+  const int P2 = N >> 1;  // column pairs per hidden unit
+  const bool fast = ((N & 1) == 0) && P2 <= (int)blockDim.x && ((reinterpret_cast<uintptr_t>(row) & (sizeof(V2) - 1)) == 0) &&
+                    (!col_mean || (reinterpret_cast<uintptr_t>(col_mean) & 15) == 0);
+  if (fast) {
+    // thread <-> fixed column pair (2 jp, 2 jp + 1); G hidden units are written per block iteration as one
+    // contiguous run of G * N elements: fully coalesced 16-byte stores, ~10 instructions per pair.
+    const int G = blockDim.x / P2;
+    const int g = threadIdx.x / P2, jp = threadIdx.x - g * P2;
+    if (g < G) {
+      const T s0 = s_s[2 * jp], s1 = s_s[2 * jp + 1];
+      for (int i = g; i < M; i += G) {
+        const T t = t_s[i];
+        double v0 = (double)(t * s0), v1 = (double)(t * s1);
+        const int64_t k = (int64_t)i * N + 2 * jp;
+        if (col_mean) {
+          const double2 m = *reinterpret_cast<const double2*>(col_mean + k);
+          v0 -= m.x;
+          v1 -= m.y;
+        }
+        V2 o;
+        o.x = (OutT)(v0 * scale);
+        o.y = (OutT)(v1 * scale);
+        *reinterpret_cast<V2*>(row + k) = o;
       }
-      if (k + V <= NP) {
-        *reinterpret_cast<int4*>(row + k) = *reinterpret_cast<int4*>(v);
-      } else {
-        for (int e = 0; e < V && k + e < NP; ++e) row[k + e] = v[e];
-      }
-      i += di; j += dj;
-      if (j >= N) { j -= N; ++i; }
+    }
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      double v = (double)t_s[i];
+      if (col_mean) v -= col_mean[MN + i];
+      row[MN + i] = (OutT)(v * scale);
     }
   } else {
     for (int64_t k = threadIdx.x; k < NP; k += blockDim.x) {
@@ -604,42 +611,77 @@ __global__ void __launch_bounds__(256) rbm_jacobian_kernel(const T* __restrict__
   }
 }
 
-// tanh(theta) table [ns, M] (model dtype) for the column-mean kernel
-template <typename T>
-__global__ void rbm_tanh_kernel(const T* __restrict__ W, const T* __restrict__ b, int N, int M,
-                                const int8_t* __restrict__ spins, int64_t ns, T* __restrict__ t_out) {
-  int lane = threadIdx.x & 31;
-  int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// tanh(theta) table [ns, M] (model dtype) for the column-mean kernel: warp per sample, W^T [N, M] read
+// through L1/L2 with coalesced rows (hidden unit i = r*32 + lane), theta in registers.
+template <typename T, int RMAX>
+__global__ void __launch_bounds__(256) rbm_tanh_kernel(const T* __restrict__ Wt, const T* __restrict__ b, int N, int M,
+                                                       const int8_t* __restrict__ spins, int64_t ns,
+                                                       T* __restrict__ t_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= ns) return;
   const int8_t* sp = spins + s * N;
-  for (int i = 0; i < M; ++i) {
-    T acc = 0;
-    for (int j = lane; j < N; j += 32) acc += W[(size_t)i * N + j] * (T)sp[j];
-    acc = warp_sum(acc) + b[i];
-    if (lane == 0) t_out[s * M + i] = tanh(acc);
+  T th[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) th[r] = 0;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    const int jj = j0 + lane;
+    const int mine = jj < N ? sp[jj] : 0;
+    const int jn = min(32, N - j0);
+    for (int q = 0; q < jn; ++q) {
+      const T sj = (T)__shfl_sync(FULL, mine, q);
+      const T* col = Wt + (size_t)(j0 + q) * M;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        const int i = r * 32 + lane;
+        if (i < M) th[r] += col[i] * sj;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) {
+    const int i = r * 32 + lane;
+    if (i < M) t_out[s * M + i] = tanh(th[r] + b[i]);
   }
 }
 
 // mean[i*N+j] = (1/ns) sum_s w_s t[s,i] spins[s,j];  mean[M*N+i] = (1/ns) sum_s w_s t[s,i]
-// grid (ceil(NP/128), SPLIT): each CTA reduces a slice of samples, combined with atomicAdd(double)
+// CTA = 16 hidden units x all (N+1) columns x one chunk of 256 samples staged in shared memory;
+// float64 accumulation of the exact products, chunks combined with atomicAdd(double).
+constexpr int kCmI = 16;
 template <typename T>
-__global__ void rbm_colmean_kernel(const T* __restrict__ t, const int8_t* __restrict__ spins, int N, int M,
-                                   int64_t ns, const double* __restrict__ weight, double* __restrict__ mean_out) {
-  const int64_t MN = (int64_t)M * N, NP = MN + M;
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= NP) return;
-  int i, j;
-  if (k < MN) { i = (int)(k / N); j = (int)(k % N); } else { i = (int)(k - MN); j = -1; }
-  int64_t chunk = (ns + gridDim.y - 1) / gridDim.y;
-  int64_t s0 = blockIdx.y * chunk, s1 = s0 + chunk < ns ? s0 + chunk : ns;
-  double acc = 0.0;
-  for (int64_t s = s0; s < s1; ++s) {
-    double v = (double)t[s * M + i];
-    if (j >= 0) v = (double)(t[s * M + i] * (T)spins[s * N + j]);
-    if (weight) v *= weight[s];
-    acc += v;
+__global__ void __launch_bounds__(256) rbm_colmean_kernel(const T* __restrict__ t, const int8_t* __restrict__ spins,
+                                                          int N, int M, int64_t ns, const double* __restrict__ weight,
+                                                          double* __restrict__ mean_out, int kCmS) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* t_s = reinterpret_cast<T*>(smem_raw);                        // [kCmS][kCmI]
+  T* s_s = t_s + kCmS * kCmI;                                     // [kCmS][N+1] (last column = 1)
+  double* w_s = reinterpret_cast<double*>(s_s + (size_t)kCmS * (N + 1) + ((kCmS * (N + 1)) & 1));
+  const int i0 = blockIdx.x * kCmI;
+  const int64_t s0 = (int64_t)blockIdx.y * kCmS;
+  const int nsl = (int)min((int64_t)kCmS, ns - s0);
+  const int NC = N + 1;
+  for (int e = threadIdx.x; e < kCmS * kCmI; e += blockDim.x) {
+    int sl = e / kCmI, il = e % kCmI;
+    t_s[e] = (sl < nsl && i0 + il < M) ? t[(s0 + sl) * M + i0 + il] : T(0);
   }
-  atomicAdd(mean_out + k, acc / (double)ns);
+  for (int e = threadIdx.x; e < kCmS * NC; e += blockDim.x) {
+    int sl = e / NC, j = e % NC;
+    s_s[e] = (sl < nsl) ? (j < N ? (T)spins[(s0 + sl) * N + j] : T(1)) : T(0);
+  }
+  for (int e = threadIdx.x; e < kCmS; e += blockDim.x) w_s[e] = (e < nsl) ? (weight ? weight[s0 + e] : 1.0) : 0.0;
+  __syncthreads();
+  const int nout = kCmI * NC;
+  const double inv = 1.0 / (double)ns;
+  for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+    const int il = o / NC, j = o % NC;
+    if (i0 + il >= M) continue;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int sl = 0; sl < kCmS; ++sl) acc += w_s[sl] * (double)(t_s[sl * kCmI + il] * s_s[sl * NC + j]);
+    const int64_t k = (j < N) ? (int64_t)(i0 + il) * N + j : (int64_t)M * N + i0 + il;
+    atomicAdd(mean_out + k, acc * inv);
+  }
 }
 
 }  // namespace qtx
@@ -805,25 +847,42 @@ extern "C" int qtx_rbm_jacobian(int model_dtype, const void* W, const void* b, i
 }
 
 extern "C" size_t qtx_rbm_colmean_workspace_size(int model_dtype, int N, int M, int64_t ns) {
-  (void)N;
   size_t es = model_dtype == QTX_F64 ? 8 : 4;
-  return ((size_t)ns * M * es + 255) / 256 * 256;
+  return ((size_t)ns * M * es + 255) / 256 * 256 + ((size_t)N * M * es + 255) / 256 * 256;
+}
+
+template <typename T, int RMAX>
+static int tanh_launch(const T* Wt, const T* b, int N, int M, const int8_t* spins, int64_t ns, T* t, cudaStream_t st) {
+  rbm_tanh_kernel<T, RMAX><<<(unsigned)((ns + 7) / 8), 256, 0, st>>>(Wt, b, N, M, spins, ns, t);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
 }
 
 template <typename T>
 static int colmean_impl(const void* W, const void* b, int N, int M, const int8_t* spins, int64_t ns,
                         const double* weight, double* mean_out, void* ws, cudaStream_t st) {
   T* t = (T*)ws;
-  rbm_tanh_kernel<T><<<(unsigned)((ns + 7) / 8), 256, 0, st>>>((const T*)W, (const T*)b, N, M, spins, ns, t);
-  QTX_LAUNCH_CHECK();
+  T* Wt = (T*)((char*)ws + ((size_t)ns * M * sizeof(T) + 255) / 256 * 256);
+  int rc = transpose_w<T>(W, Wt, N, M, st);
+  if (rc) return rc;
+  if (M <= 64) rc = tanh_launch<T, 2>(Wt, (const T*)b, N, M, spins, ns, t, st);
+  else if (M <= 128) rc = tanh_launch<T, 4>(Wt, (const T*)b, N, M, spins, ns, t, st);
+  else if (M <= 256) rc = tanh_launch<T, 8>(Wt, (const T*)b, N, M, spins, ns, t, st);
+  else if (M <= 512) rc = tanh_launch<T, 16>(Wt, (const T*)b, N, M, spins, ns, t, st);
+  else if (M <= 1024) rc = tanh_launch<T, 32>(Wt, (const T*)b, N, M, spins, ns, t, st);
+  else QTX_REQUIRE(false, QTX_ERR_UNSUPPORTED, "qtx_rbm_jacobian_colmean: M=%d > 1024 is not supported", M);
+  if (rc) return rc;
   const int64_t NP = (int64_t)M * N + M;
   QTX_CUDA(cudaMemsetAsync(mean_out, 0, NP * sizeof(double), st));
-  unsigned gx = (unsigned)((NP + 127) / 128);
-  int split = (int)((4 * (int64_t)num_sms() + gx - 1) / gx);
-  if (split < 1) split = 1;
-  if (split > 64) split = 64;
-  if (split > ns) split = (int)ns;
-  rbm_colmean_kernel<T><<<dim3(gx, split), 128, 0, st>>>(t, spins, N, M, ns, weight, mean_out);
+  int kCmS = 256;  // samples staged per CTA; shrink (even values) until the tile fits in shared memory
+  auto smem_of = [&](int sc) { return ((size_t)sc * kCmI + (size_t)sc * (N + 1) + 1) * sizeof(T) + sc * sizeof(double) + 16; };
+  while (kCmS > 16 && smem_of(kCmS) > 100 * 1024) kCmS -= 16;
+  const size_t smem = smem_of(kCmS);
+  QTX_REQUIRE(smem <= kSmemBudget, QTX_ERR_UNSUPPORTED, "qtx_rbm_jacobian_colmean: N too large for shared memory");
+  auto k = rbm_colmean_kernel<T>;
+  if (smem > 48 * 1024) QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((M + kCmI - 1) / kCmI), (unsigned)((ns + kCmS - 1) / kCmS));
+  k<<<grid, 256, smem, st>>>(t, spins, N, M, ns, weight, mean_out, kCmS);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }

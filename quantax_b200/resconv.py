@@ -65,14 +65,14 @@ def resconv_jacobian(state, s: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def resconv_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed, step0, chain0, injected, record):
+def generic_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed, step0, chain0, injected, record):
     """``_partial_sweep`` for a state without local updates (metropolis.py:246-275): every step is
     propose -> full forward of the proposed chains -> accept, all enqueued on the stream with no
     host synchronisation; psi of the current chains is carried along (Samples.psi)."""
     ns, N = spins.shape
     dev = spins.device
-    psi = resconv_forward(state, spins)
-    mult, expo = psi.significand, psi.exponent
+    psi = state(spins)  # bare model or symmetry-projected, LogArray or ScaleArray
+    mult, expo = psi.mult.contiguous(), psi.expo.contiguous()
     new_spins = torch.empty_like(spins)
     moved = torch.empty(ns, dtype=torch.uint8, device=dev)
     nacc = torch.zeros(ns, dtype=torch.int32, device=dev)
@@ -89,10 +89,10 @@ def resconv_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed,
         _lib.call("qtx_metropolis_propose", int(kind), _lib.ptr(spins), ns, N, _lib.ptr(nbr), int(max_nb), int(hop),
                   None if pos is None else _lib.ptr(pos[t]), None if slot is None else _lib.ptr(slot[t]), seed,
                   int(step0) + t, int(chain0), _lib.ptr(new_spins), _lib.ptr(moved), st)
-        psi_new = resconv_forward(state, new_spins)
+        psi_new = state(new_spins)
         _lib.call("qtx_metropolis_accept", _lib.ptr(spins), _lib.ptr(new_spins), _lib.ptr(moved), ns, N,
-                  _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(psi_new.significand), _lib.ptr(psi_new.exponent),
+                  _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(psi_new.mult.contiguous()), _lib.ptr(psi_new.expo.contiguous()),
                   float(reweight), None if u is None else _lib.ptr(u[t]), seed, int(step0) + t, int(chain0),
                   _lib.ptr(nacc), None if log is None else _lib.ptr(log[t]), st)
-    out = ScaleArray(mult, expo)
+    out = type(psi)(mult, expo)
     return out, out, nacc, log

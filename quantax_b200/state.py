@@ -30,10 +30,13 @@ class State:
     """Abstract state (quantax/state/state.py:19-100): default no-op internals."""
 
     def __init__(self, symm=None):
-        if symm is not None:
-            raise NotImplementedError("state-level symmetry projection is not implemented in this round")
+        from .symmetry import Identity
+
         sites = get_sites()
         self._Nsites, self._Nmodes = sites.Nsites, sites.Nmodes
+        self._symm = Identity() if symm is None else symm
+
+    symm = property(lambda self: self._symm)
 
     Nsites = property(lambda self: self._Nsites)
     Nmodes = property(lambda self: self._Nmodes)
@@ -56,7 +59,9 @@ class Variational(State):
             self._ref_chunk = self._forward_chunk
         else:
             self._forward_chunk, self._backward_chunk, self._ref_chunk = max_parallel
-        self._use_ref = bool(use_ref) and getattr(model, "is_ref_model", False)
+        # local updates are implemented for the un-projected RefModel; a projected state evaluates
+        # full forwards of all symmetry images (the reference's use_ref=False code path)
+        self._use_ref = bool(use_ref) and getattr(model, "is_ref_model", False) and self._symm.is_identity
         self._vs_type = VS_TYPE.real_or_holomorphic
         self._ws = {}
 
@@ -88,8 +93,8 @@ class Variational(State):
         return _as_spins(s)
 
     # ---- forward (variational.py:325-347) -----------------------------------------------------
-    def __call__(self, s):
-        s = self._spins(s).reshape(-1, self.Nmodes)
+    def _forward_model(self, s: torch.Tensor):
+        """psi of the bare model (no projection) for a batch [ns, N]."""
         m = self._model
         ns = s.shape[0]
         if m.kind == "rbm":
@@ -100,6 +105,42 @@ class Variational(State):
         from .resconv import resconv_forward
 
         return resconv_forward(self, s)
+
+    def _images(self, s: torch.Tensor) -> torch.Tensor:
+        """All symmetry images [ns * nsymm, N] (symmetry.py:325-341)."""
+        perm, _ = self._symm.device_tables()
+        nsymm = self._symm.nsymm
+        out = torch.empty((s.shape[0] * nsymm, s.shape[1]), dtype=torch.int8, device=s.device)
+        _lib.call("qtx_symm_images", _lib.ptr(s), s.shape[0], s.shape[1], _lib.ptr(perm), perm.shape[0],
+                  int(self._symm.Z2_inversion != 0), _lib.ptr(out), _lib.stream())
+        return out
+
+    def _combine(self, psi_img, ns: int, want_coef: bool = False):
+        """psi = sum_g w_g psi_g (symmetry.py:386-392) in container arithmetic."""
+        _, w = self._symm.device_tables()
+        nsymm = self._symm.nsymm
+        kind = 0 if isinstance(psi_img, LogArray) else 1
+        dev = psi_img.mult.device
+        mult = torch.empty(ns, dtype=torch.float64, device=dev)
+        expo = torch.empty(ns, dtype=torch.float64, device=dev)
+        coef = torch.empty((ns, nsymm), dtype=torch.float64, device=dev) if want_coef else None
+        _lib.call("qtx_symm_combine", _lib.ptr(psi_img.mult.contiguous()), _lib.ptr(psi_img.expo.contiguous()), ns,
+                  nsymm, _lib.ptr(w), kind, _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(coef), _lib.stream())
+        psi = LogArray(mult, expo) if kind == 0 else ScaleArray(mult, expo)
+        return (psi, coef) if want_coef else psi
+
+    def __call__(self, s):
+        s = self._spins(s).reshape(-1, self.Nmodes)
+        if self._symm.is_identity:
+            return self._forward_model(s)
+        ns = s.shape[0]
+        chunk = max(1, (1 << 22) // max(self._symm.nsymm, 1))
+        if ns <= chunk:
+            return self._combine(self._forward_model(self._images(s)), ns)
+        parts = [self._combine(self._forward_model(self._images(s[lo:lo + chunk])), min(chunk, ns - lo))
+                 for lo in range(0, ns, chunk)]
+        cls = type(parts[0])
+        return cls(torch.cat([p.mult for p in parts]), torch.cat([p.expo for p in parts]))
 
     def init_internal(self, s):
         """theta = W s + b for RefModels, None otherwise (variational.py:349-356)."""
@@ -144,10 +185,10 @@ class Variational(State):
                     seed: int, step0: int, chain0: int, injected=None, record: bool = False):
         """Whole Metropolis sweep in one launch (RBM) -- see qtx_rbm_sweep."""
         m = self._model
-        if m.kind != "rbm":
-            from .resconv import resconv_sweep
+        if m.kind != "rbm" or not self._use_ref:
+            from .resconv import generic_sweep
 
-            return resconv_sweep(self, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed, step0, chain0,
+            return generic_sweep(self, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed, step0, chain0,
                                  injected, record)
         ns = spins.shape[0]
         dev = spins.device
@@ -203,23 +244,53 @@ class Variational(State):
         odt = get_default_dtype()
         if out is None:
             out = torch.empty((ns, m.nparams), dtype=odt, device=s.device)
-        if m.kind == "rbm":
+        if not self._symm.is_identity:
+            self._projected_jacobian(s, out)
+        elif m.kind == "rbm":
             _lib.call("qtx_rbm_jacobian", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
                       _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), _lib.ptr(col_mean),
                       _lib.ptr(row_scale), _lib.stream())
             return out
-        from .resconv import resconv_jacobian
-
-        resconv_jacobian(self, s, out)
+        else:
+            self._model_jacobian(s, out)
         if col_mean is not None or row_scale is not None:
             _lib.call("qtx_center_scale", _lib.dtype_code(out.dtype), _lib.ptr2d(out), ns, m.nparams, out.stride(0),
                       _lib.ptr(col_mean), _lib.ptr(row_scale), _lib.stream())
         return out
 
+    def _model_jacobian(self, s: torch.Tensor, out: torch.Tensor) -> None:
+        m = self._model
+        if m.kind == "rbm":
+            _lib.call("qtx_rbm_jacobian", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), s.shape[0],
+                      _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), None, None, _lib.stream())
+        else:
+            from .resconv import resconv_jacobian
+
+            resconv_jacobian(self, s, out)
+
+    def _projected_jacobian(self, s: torch.Tensor, out: torch.Tensor) -> None:
+        """O(s) = sum_g (w_g psi_g / psi) O(T_g s)  (variational.py:438-491), in sample chunks."""
+        m = self._model
+        nsymm = self._symm.nsymm
+        ns = s.shape[0]
+        esz = out.element_size()
+        chunk = max(1, min(ns, (2 << 30) // max(nsymm * m.nparams * esz, 1)))
+        if self._backward_chunk is not None:
+            chunk = max(1, min(chunk, self._backward_chunk // nsymm if self._backward_chunk >= nsymm else 1))
+        buf = torch.empty((chunk * nsymm, m.nparams), dtype=out.dtype, device=s.device)
+        for lo in range(0, ns, chunk):
+            hi = min(ns, lo + chunk)
+            img = self._images(s[lo:hi])
+            _, coef = self._combine(self._forward_model(img), hi - lo, want_coef=True)
+            J = buf[: (hi - lo) * nsymm]
+            self._model_jacobian(img, J)
+            _lib.call("qtx_weighted_rowsum", _lib.dtype_code(out.dtype), _lib.ptr2d(J), J.stride(0), _lib.ptr(coef),
+                      hi - lo, nsymm, m.nparams, _lib.ptr2d(out[lo:hi]), out.stride(0), _lib.stream())
+
     def jacobian_colmean(self, fock_states, weight=None) -> Optional[torch.Tensor]:
         """Column mean of the Jacobian without materialising it (RBM), else None."""
         m = self._model
-        if m.kind != "rbm":
+        if m.kind != "rbm" or not self._symm.is_identity:
             return None
         s = self._spins(fock_states)
         ns = s.shape[0]

@@ -142,6 +142,42 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
 
 
+def make_symm(sites):
+    """Generators of Translation / Flip / Rotation from the reference's NumPy code
+    (quantax/symmetry/translation.py:25-47, common_symmetries.py:104-205).  The group closure
+    (_get_perm) is jnp code and cannot run here, so Symmetry.__init__ is replaced by a recorder."""
+    for k in list(sys.modules):
+        if k.startswith("quantax.symmetry"):
+            del sys.modules[k]
+    symmod = importlib.import_module("quantax.symmetry.symmetry")
+
+    def fake_init(self, generator=None, sector=0, generator_sign=None, Z2_inversion=0, perm=None, character=None,
+                  perm_sign=None):
+        self.generator = None if generator is None else np.atleast_2d(np.asarray(generator))
+
+    symmod.Symmetry.__init__ = fake_init
+    tr = importlib.import_module("quantax.symmetry.translation")
+    cs = importlib.import_module("quantax.symmetry.common_symmetries")
+    out = {}
+    cases = {"square4": lambda: sites.Square(4), "square6": lambda: sites.Square(6), "square10": lambda: sites.Square(10),
+             "triangular6": lambda: sites.Triangular(6), "chain8": lambda: sites.Chain(8)}
+    for name, mk in cases.items():
+        sites.Sites._SITES = None
+        lat = mk()
+        nd = lat.ndim
+        c = np.zeros(nd) if name.startswith("tri") else None
+        out[f"{name}/trans"] = tr.Translation(np.eye(nd, dtype=int)).generator
+        out[f"{name}/flip0"] = cs.Flip(0, center=c).generator
+        if nd == 2:
+            ang = np.pi / 3 if name.startswith("tri") else np.pi / 2
+            out[f"{name}/rot"] = cs.Rotation(ang, center=c).generator
+            out[f"{name}/flip1"] = cs.Flip(1, center=c).generator
+    path = os.path.join(HERE, "ref_symm_generators.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, len(out), "arrays")
+
+
 if __name__ == "__main__":
     sys.path.insert(0, REF)
     main()
+    make_symm(sys.modules["quantax.sites"])

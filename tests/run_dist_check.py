@@ -39,19 +39,22 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     ok = True
-    for kind, ns in (("rbm", 64 * world), ("resconv", 32 * world)):
-        dist.init_process_group("nccl", device_id=dev)
+    cases = (("rbm", 64 * world), ("resconv", 32 * world))
+    dist.init_process_group("nccl", device_id=dev)
+    results = []
+    for kind, ns in cases:
         spins, e, v, step, spins2, params = vmc(kind, ns)
         g1 = [torch.empty_like(spins) for _ in range(world)]
         g2 = [torch.empty_like(spins2) for _ in range(world)]
         dist.all_gather(g1, spins)
         dist.all_gather(g2, spins2)
-        dist.barrier()
-        dist.destroy_process_group()
-        if rank == 0:
+        results.append((torch.cat(g1), torch.cat(g2), e, step, params))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        for (kind, ns), (s1, s2, e, step, params) in zip(cases, results):
             s_ref, e_ref, v_ref, step_ref, s2_ref, p_ref = vmc(kind, ns)  # world() == (0, 1) now
-            same1 = torch.equal(torch.cat(g1), s_ref)
-            same2 = torch.equal(torch.cat(g2), s2_ref)
+            same1, same2 = torch.equal(s1, s_ref), torch.equal(s2, s2_ref)
             de = abs(e - e_ref) / abs(e_ref)
             ds = float((step - step_ref).norm() / step_ref.norm())
             dp = float((params - p_ref).abs().max())

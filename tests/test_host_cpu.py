@@ -146,3 +146,50 @@ def test_no_cuda_means_loud_failure():
 
     with pytest.raises(_lib.QtxError):
         _lib.ptr(torch.zeros(4))
+
+
+SYMM_GOLD = np.load(os.path.join(ROOT, "tests", "golden", "ref_symm_generators.npz"))
+
+
+@pytest.mark.parametrize("name", ["square4", "square6", "square10", "triangular6", "chain8"])
+def test_symmetry_generators_match_reference(name):
+    """Translation / Flip / Rotation permutations equal those of the reference's own NumPy code
+    (quantax/symmetry/translation.py:25-47, common_symmetries.py:104-205)."""
+    from quantax_b200 import sites, symmetry
+
+    lat = {"square4": lambda: sites.Square(4), "square6": lambda: sites.Square(6), "square10": lambda: sites.Square(10),
+           "triangular6": lambda: sites.Triangular(6), "chain8": lambda: sites.Chain(8)}[name]()
+    nd = lat.ndim
+    c = np.zeros(nd) if name.startswith("tri") else None
+    assert np.array_equal(symmetry.Translation(np.eye(nd, dtype=int))._generator, SYMM_GOLD[f"{name}/trans"])
+    assert np.array_equal(symmetry.Flip(0, center=c)._generator, SYMM_GOLD[f"{name}/flip0"])
+    if nd == 2:
+        ang = np.pi / 3 if name.startswith("tri") else np.pi / 2
+        assert np.array_equal(symmetry.Rotation(ang, center=c)._generator, SYMM_GOLD[f"{name}/rot"])
+        assert np.array_equal(symmetry.Flip(1, center=c)._generator, SYMM_GOLD[f"{name}/flip1"])
+
+
+def test_symmetry_group_tables_match_oracle():
+    from oracle import symmetry as osym
+    from quantax_b200 import sites, symmetry
+
+    sites.Square(4, Nparticles=(8, 8))
+    olat = osites.Square(4)
+    full = symmetry.TransND() @ symmetry.Rotation(np.pi / 2) @ symmetry.Flip() @ symmetry.SpinInverse()
+    ofull = osym.TransND(olat) @ osym.Rotation(olat, np.pi / 2) @ osym.Flip(olat) @ osym.SpinInverse(olat)
+    assert full.nsymm == ofull.nsymm == 256
+    assert np.array_equal(full.perm, ofull.perm) and np.array_equal(full.character, ofull.character)
+    assert np.allclose(full.weights(), ofull.weights())
+    b1 = symmetry.C4v(repr="B1")
+    ob1 = osym.Rotation(olat, np.pi / 2, sector=2) @ osym.Flip(olat, sector=0)
+    assert np.array_equal(b1.perm, ob1.perm) and np.array_equal(b1.character, ob1.character)
+    assert set(b1.character) == {1.0, -1.0}
+    # group property: the permutation set is closed under composition
+    perms = {tuple(p) for p in b1.perm}
+    assert all(tuple(p[q]) in perms for p in b1.perm for q in b1.perm)
+    with pytest.raises(ValueError):
+        symmetry.Rotation(np.pi / 2, sector=1)  # complex character under a real default dtype
+    with pytest.raises(ValueError):
+        symmetry.Z2Inversion(1) @ symmetry.Z2Inversion(-1)
+    s = np.arange(16)
+    assert np.array_equal(symmetry.Identity().get_symm_spins(s), s[None])

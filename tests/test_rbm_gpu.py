@@ -245,3 +245,16 @@ def test_empty_and_tiny_batches(qtx):
     empty = torch.zeros((0, 8), dtype=torch.int8)
     assert state(empty).logabs.numel() == 0
     assert H.Oloc(state, empty).numel() == 0
+
+
+def test_jacobian_odd_site_count_and_wide_rows(qtx):
+    """N odd -> scalar-store path; N = 256 -> two hidden units per block iteration."""
+    for kind, L, N, M in (("chain", 9, 9, 20), ("square", 16, 256, 40)):
+        lattice_pair(qtx, kind, L)
+        model, net = make_rbm(qtx, N, M, torch.float32, seed=21)
+        state = qtx.state.Variational(model)
+        s = osmp.rand_states(33, N, seed=22)
+        st = torch.from_numpy(s)
+        Oo = net.jacobian(s)
+        assert np.abs(to_np(state.jacobian(st)) - Oo).max() <= 1e-5
+        assert np.abs(to_np(state.jacobian_colmean(st)) - Oo.mean(axis=0)).max() <= 1e-5
