@@ -10,6 +10,8 @@
 // 4 x 8 (position x out-channel) register tile.  Arithmetic stays in the model dtype (float32 by
 // default: the 1e-5 parity bar rules out single-pass TF32), so these kernels are bound by the FP32
 // FMA pipe, not by HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace qtx {
@@ -38,6 +40,7 @@ template <typename T>
 struct ConvParams {
   const T* in;      // [ns, cin, N]
   const T* w;       // [cout, cin, kh, kw]  (or pre-transposed for the backward-data pass)
+  const T* w_ctco;  // the same weights repacked as [cin, kh*kw, cout] (fast kernels, coalesced staging)
   const T* bias;    // [cout] or null
   const T* res;     // residual added after the multiply, [ns, res_ch, N], res_ch in {0, 1, cout}
   const T* mul;     // if non-null: out = (conv + bias) * mul_scale * gelu'(mul_alpha * mul[s,o,r]) + res
@@ -148,11 +151,204 @@ __global__ void __launch_bounds__(kConvThreads) conv_circ_kernel(ConvParams<T> p
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fast path: compile-time kernel size and out-channel register tile.  Per (channel, tap) step a
+// thread issues 4 scalar LDS (activations), TN/4 LDS.128 (weights) and 4*TN FFMA, so ~85% of the
+// inner-loop instructions are FMAs; staging indices are computed once per thread.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <typename T, int KH, int KW, int TN>
+__global__ void __launch_bounds__(kConvThreads, 2) conv_circ_fast_kernel(ConvParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int OT = 4 * TN, TAPS = KH * KW, PH = (KH - 1) / 2, PW = (KW - 1) / 2;
+  constexpr int WSZ = kCK * TAPS * OT;
+  const int N = p.lx * p.ly;
+  const int Hp = p.lx + KH - 1, Wp = p.ly + KW - 1, HW = Hp * Wp;
+  const int HWs = (HW + 3) & ~3;                               // image stride in smem
+  const int nimg = kCK * p.s_tile;
+  const int RSZ = (nimg * N + 3) & ~3;                         // raw (un-padded) chunk size
+  T* act_s = reinterpret_cast<T*>(smem_raw);                   // [kCK][s_tile][HWs]   transformed + halo
+  T* w_s = act_s + (size_t)nimg * HWs;                         // [2][kCK][TAPS][OT]   double buffered
+  T* raw_s = w_s + 2 * WSZ;                                    // [2][kCK][s_tile][N]  double buffered
+  int* qsrc_s = reinterpret_cast<int*>(raw_s + 2 * (size_t)RSZ);
+  const int tid = threadIdx.x;
+  const int og = tid >> 6, pg = tid & 63;
+  const int64_t s0 = (int64_t)blockIdx.x * p.s_tile;
+  const int o0 = blockIdx.y * OT;
+  const int pos0 = blockIdx.z * kPT;
+  const int P = p.s_tile * N;
+
+  int base[kTM];
+  bool pvalid[kTM];
+#pragma unroll
+  for (int t = 0; t < kTM; ++t) {
+    int pos = pos0 + pg + 64 * t;
+    pvalid[t] = pos < P && (s0 + pos / N) < p.ns;
+    int sl = pvalid[t] ? pos / N : 0, r = pvalid[t] ? pos % N : 0;
+    base[t] = sl * HWs + (r / p.ly) * Wp + (r % p.ly);
+  }
+  // staging map: padded position q of an image -> source position, -1 outside
+  for (int q = tid; q < HWs; q += kConvThreads) {
+    int hp = q / Wp, wp = q - hp * Wp;
+    int h = hp - PH, w = wp - PW;
+    h += (h < 0) ? p.lx : 0; h -= (h >= p.lx) ? p.lx : 0;
+    w += (w < 0) ? p.ly : 0; w -= (w >= p.ly) ? p.ly : 0;
+    qsrc_s[q] = (q < HW) ? h * p.ly + w : -1;
+  }
+  T acc[kTM][TN];
+#pragma unroll
+  for (int t = 0; t < kTM; ++t)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) acc[t][n] = 0;
+
+  // asynchronous (cp.async) fetch of the raw activations and the repacked weights of one channel chunk;
+  // issued one chunk ahead so that global-memory latency overlaps with the FMA loop of the current chunk.
+  auto fetch = [&](int c0, int buf) {
+    T* rdst = raw_s + (size_t)buf * RSZ;
+    for (int e = tid; e < nimg * N; e += kConvThreads) {
+      const int img = e / N, r = e - img * N;
+      const int ck = img / p.s_tile, sl = img - ck * p.s_tile;
+      const bool ok = c0 + ck < p.cin && s0 + sl < p.ns;
+      const T* src = ok ? p.in + ((s0 + sl) * p.cin + c0 + ck) * N + r : p.in;
+      if constexpr (sizeof(T) == 4) cp_async4(rdst + e, src, ok);
+      else cp_async8(rdst + e, src, ok);
+    }
+    T* wdst = w_s + (size_t)buf * WSZ;
+    for (int e = tid; e < WSZ; e += kConvThreads) {
+      const int o = e % OT, row = e / OT;  // row = ck * TAPS + tap
+      const bool ok = c0 + row / TAPS < p.cin && o0 + o < p.cout;
+      const T* src = ok ? p.w_ctco + ((size_t)c0 * TAPS + row) * p.cout + o0 + o : p.w_ctco;
+      if constexpr (sizeof(T) == 4) cp_async4(wdst + e, src, ok);
+      else cp_async8(wdst + e, src, ok);
+    }
+    cp_async_commit();
+  };
+  fetch(0, 0);
+  int buf = 0;
+  for (int c0 = 0; c0 < p.cin; c0 += kCK, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();  // chunk `buf` has landed; the previous FMA loop is done with act_s
+    const T* rsrc = raw_s + (size_t)buf * RSZ;
+    for (int e = tid; e < nimg * HWs; e += kConvThreads) {
+      const int img = e / HWs, q = e - img * HWs;
+      const int src = qsrc_s[q];
+      if (src >= 0) {
+        T v = p.alpha * rsrc[img * N + src];
+        if (p.in_act == 1) v = gelu_f(v);
+        act_s[e] = v;
+      }
+    }
+    __syncthreads();
+    if (c0 + kCK < p.cin) fetch(c0 + kCK, buf ^ 1);
+    const T* w_b = w_s + (size_t)buf * WSZ;
+#pragma unroll 2
+    for (int ck = 0; ck < kCK; ++ck) {
+      const T* a_c = act_s + (size_t)ck * p.s_tile * HWs;
+      const T* w_c = w_b + (size_t)ck * TAPS * OT + og * TN;
+#pragma unroll
+      for (int dy = 0; dy < KH; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < KW; ++dx) {
+          const int off = dy * Wp + dx;
+          T a[kTM], wv[TN];
+#pragma unroll
+          for (int t = 0; t < kTM; ++t) a[t] = a_c[base[t] + off];
+          const T* wr = w_c + (dy * KW + dx) * OT;
+          if constexpr (sizeof(T) == 4) {
+#pragma unroll
+            for (int n = 0; n < TN; n += 4) {
+              float4 q4 = *reinterpret_cast<const float4*>(wr + n);
+              wv[n] = q4.x; wv[n + 1] = q4.y; wv[n + 2] = q4.z; wv[n + 3] = q4.w;
+            }
+          } else {
+#pragma unroll
+            for (int n = 0; n < TN; n += 2) {
+              double2 q2 = *reinterpret_cast<const double2*>(wr + n);
+              wv[n] = q2.x; wv[n + 1] = q2.y;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < kTM; ++t)
+#pragma unroll
+            for (int n = 0; n < TN; ++n) acc[t][n] += a[t] * wv[n];
+        }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kTM; ++t) {
+    if (!pvalid[t]) continue;
+    int pos = pos0 + pg + 64 * t;
+    int64_t s = s0 + pos / N;
+    int r = pos % N;
+#pragma unroll
+    for (int n = 0; n < TN; ++n) {
+      int o = o0 + og * TN + n;
+      if (o >= p.cout) continue;
+      T v = acc[t][n];
+      if (p.bias) v += p.bias[o];
+      const int64_t oi = (s * p.cout + o) * N + r;
+      if (p.mul) v = v * (p.mul_scale * gelu_grad_f(p.mul_alpha * p.mul[oi]));
+      if (p.res_ch == p.cout) v += p.res[oi];
+      else if (p.res_ch == 1) v += p.res[s * N + r];
+      p.out[oi] = v;
+    }
+  }
+}
+
+template <typename T, int KH, int KW, int TN>
+static int launch_conv_fast(ConvParams<T> p, cudaStream_t st) {
+  const int N = p.lx * p.ly;
+  const int Hp = p.lx + KH - 1, Wp = p.ly + KW - 1, HWs = (Hp * Wp + 3) & ~3;
+  constexpr int OT = 4 * TN;
+  const int nimg = kCK * p.s_tile, RSZ = (nimg * N + 3) & ~3;
+  size_t smem = ((size_t)nimg * HWs + 2 * (size_t)kCK * KH * KW * OT + 2 * (size_t)RSZ) * sizeof(T) + (size_t)HWs * sizeof(int);
+  auto k = conv_circ_fast_kernel<T, KH, KW, TN>;
+  if (smem > 48 * 1024) QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int P = p.s_tile * N;
+  dim3 grid((unsigned)((p.ns + p.s_tile - 1) / p.s_tile), (unsigned)((p.cout + OT - 1) / OT),
+            (unsigned)((P + kPT - 1) / kPT));
+  k<<<grid, kConvThreads, smem, st>>>(p);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+template <typename T, int KH, int KW>
+static int launch_conv_fast_tn(ConvParams<T> p, cudaStream_t st) {
+  // out-channel tile 4*TN: pick the TN in {8, 12, 16} with the least padded work, larger tile on ties
+  int best = 8;
+  double best_eff = 0;
+  for (int tn : {8, 12, 16}) {
+    int ot = 4 * tn, tiles = (p.cout + ot - 1) / ot;
+    double eff = (double)p.cout / (tiles * ot) * (tn == 8 ? 0.93 : (tn == 12 ? 0.97 : 1.0));
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = tn; }
+  }
+  if (best == 8) return launch_conv_fast<T, KH, KW, 8>(p, st);
+  if (best == 12) return launch_conv_fast<T, KH, KW, 12>(p, st);
+  return launch_conv_fast<T, KH, KW, 16>(p, st);
+}
+
 template <typename T>
 static int launch_conv(ConvParams<T> p, cudaStream_t st) {
   const int N = p.lx * p.ly;
   p.s_tile = kPT / N > 0 ? kPT / N : 1;
   const int Hp = p.lx + p.kh - 1, Wp = p.ly + p.kw - 1;
+  if (Hp * Wp <= 384 && !getenv("QTX_CONV_GENERIC")) {
+    if (p.kh == 3 && p.kw == 3) return launch_conv_fast_tn<T, 3, 3>(p, st);
+    if (p.kh == 1 && p.kw == 3) return launch_conv_fast_tn<T, 1, 3>(p, st);
+  }
   size_t smem = ((size_t)kCK * p.s_tile * Hp * Wp + (size_t)kCK * p.kh * p.kw * kOT) * sizeof(T);
   QTX_REQUIRE(smem <= 200 * 1024, QTX_ERR_UNSUPPORTED, "resconv: lattice too large for the conv tile (%zu B smem)", smem);
   auto k = conv_circ_kernel<T>;
@@ -172,6 +368,24 @@ template <typename T>
 __global__ void spins_to_act_kernel(const int8_t* __restrict__ s, int64_t n, T* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = (T)s[i];
+}
+
+// out[c][tap][o] = w[o][c][tap]            (flip == 0: forward conv, cin = c, cout = o)
+// out[o][tap'][c] = w[o][c][flip(tap')]     (flip == 1: backward-data conv, cin' = o, cout' = c)
+template <typename T>
+__global__ void weight_repack_kernel(const T* __restrict__ w, int cout, int cin, int kh, int kw, int flip,
+                                     T* __restrict__ out) {
+  const int taps = kh * kw, n = cout * cin * taps;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    int tap = e % taps, c = (e / taps) % cin, o = e / (taps * cin);
+    if (!flip) {
+      out[((size_t)c * taps + tap) * cout + o] = w[e];
+    } else {
+      int dy = tap / kw, dx = tap % kw;
+      int tf = (kh - 1 - dy) * kw + (kw - 1 - dx);
+      out[((size_t)o * taps + tf) * cin + c] = w[e];
+    }
+  }
 }
 
 // wT[c][o][kh-1-dy][kw-1-dx] = w[o][c][dy][dx]   (backward-data pass = conv with these weights)
@@ -494,7 +708,14 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
   T* x0 = base;                       // [ns, 1, N]
   T* X = x0 + ns * N;                 // grad: (nb+1) buffers X_1..X_nb (+ scratch); else 1 buffer
   T* Hs = X + (grad ? (int64_t)nb * act : act);   // grad: nb buffers; else 1
-  T* scratch = Hs + (grad ? (int64_t)nb * act : act);  // grad only: 2 gradient buffers + transposed weights
+  T* scratch = Hs + (grad ? (int64_t)nb * act : act);  // grad: 2 gradient buffers + transposed weights; then repacked weights
+  const int64_t wsz = (int64_t)C * C * sh.kh * sh.kw;
+  T* wR = scratch + (grad ? 2 * act + wsz : 0);
+  auto repack = [&](const T* w, int cout, int cin, int flip) -> int {
+    weight_repack_kernel<T><<<64, 256, 0, st>>>(w, cout, cin, sh.kh, sh.kw, flip, wR);
+    QTX_LAUNCH_CHECK();
+    return QTX_OK;
+  };
   {
     int64_t n = ns * N;
     unsigned g = (unsigned)((n + 255) / 256);
@@ -527,12 +748,17 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
     p.alpha = (i == 0) ? (T)(1.0 / sqrt(2.0)) : (T)(1.0 / sqrt((double)(i + 1)));
     p.in_act = (i == 0) ? 0 : 1;
     p.res = nullptr; p.res_ch = 0; p.mul = nullptr; p.out = h;
-    int rc = launch_conv<T>(p, st);
+    int rc = repack(pw1[i], C, p.cin, 0);
+    if (rc) return rc;
+    p.w_ctco = wR;
+    rc = launch_conv<T>(p, st);
     if (rc) return rc;
     ConvParams<T> q{};
     q.ns = ns; q.lx = sh.lx; q.ly = sh.ly; q.kh = sh.kh; q.kw = sh.kw;
     q.in = h; q.cin = C; q.cout = C; q.w = pw2[i]; q.bias = pb2[i]; q.alpha = 1; q.in_act = 1;
     q.res = xin; q.res_ch = (i == 0) ? 1 : C; q.mul = nullptr; q.out = xout;
+    if ((rc = repack(pw2[i], C, C, 0))) return rc;
+    q.w_ctco = wR;
     rc = launch_conv<T>(q, st);
     if (rc) return rc;
   }
@@ -585,6 +811,8 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
     p.ns = ns; p.lx = sh.lx; p.ly = sh.ly; p.kh = sh.kh; p.kw = sh.kw;
     p.in = dX; p.cin = C; p.cout = C; p.w = wT; p.bias = nullptr; p.alpha = 1; p.in_act = 0;
     p.res = nullptr; p.res_ch = 0; p.mul = h; p.mul_alpha = 1; p.mul_scale = 1; p.out = tmp;
+    if ((rc = repack(pw2[i], C, C, 1))) return rc;
+    p.w_ctco = wR;
     if ((rc = launch_conv<T>(p, st))) return rc;
     // conv1: h = conv1(a1) + b1
     const T alpha1 = (i == 0) ? (T)(1.0 / sqrt(2.0)) : (T)(1.0 / sqrt((double)(i + 1)));
@@ -600,6 +828,8 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
       q.res = dX; q.res_ch = C; q.mul = xin; q.mul_alpha = alpha1; q.mul_scale = alpha1;
       // in-place on dX is safe: each thread reads res at exactly the index it writes
       q.out = dX;
+      if ((rc = repack(pw1[i], C, C, 1))) return rc;
+      q.w_ctco = wR;
       if ((rc = launch_conv<T>(q, st))) return rc;
     }
   }
@@ -611,8 +841,9 @@ static size_t resconv_ws(int dtype, int64_t ns, const NetShape& sh, bool grad) {
   size_t es = dtype == QTX_F64 ? 8 : 4;
   int64_t act = ns * sh.C * sh.N();
   int64_t elems = ns * sh.N();
-  if (grad) elems += (int64_t)(2 * sh.nblocks + 2) * act + (int64_t)sh.C * sh.C * sh.kh * sh.kw;
-  else elems += 2 * act;
+  const int64_t wsz = (int64_t)sh.C * sh.C * sh.kh * sh.kw;
+  if (grad) elems += (int64_t)(2 * sh.nblocks + 2) * act + 2 * wsz;
+  else elems += 2 * act + wsz;
   return (size_t)elems * es + 256;
 }
 
