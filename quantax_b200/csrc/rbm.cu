@@ -112,7 +112,6 @@ __global__ void __launch_bounds__(RMAX <= 8 ? 1024 : (sizeof(T) == 4 && RMAX <= 
   const int wpb = blockDim.x >> 5;
   const int64_t nwarps = (int64_t)gridDim.x * wpb;
   const int NW = (N + 31) >> 5;
-  const bool rw2 = (p.reweight == 2.0);
 
   for (int64_t chain = (int64_t)blockIdx.x * wpb + warp; chain < p.ns; chain += nwarps) {
     int8_t* sp = p.spins + chain * N;
@@ -148,28 +147,31 @@ __global__ void __launch_bounds__(RMAX <= 8 ? 1024 : (sizeof(T) == 4 && RMAX <= 
     double la = (double)warp_sum(lsum);
     int nacc = 0;
 
-    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;  // Philox outputs of step (t & ~31) + lane
+    // Acceptance is tested in the log domain: |psi'/psi|^n > 1 - u  <=>  n (la' - la) > log(1 - u).
+    // In Philox mode lane l draws the randoms of step (t & ~31) + l, so one float64 log per lane serves
+    // 32 steps of the chain (instead of one float64 exp per step).
+    uint32_t q0 = 0, q1 = 0;  // Philox outputs of step (t & ~31) + lane
+    double qthr = 0.0;        // log(1 - u) of that step
     for (int t = 0; t < p.nsweeps; ++t) {
       int pos, slot = 0;
-      double u;
+      double thr;
       if (p.inj_u) {
         size_t o = (size_t)t * p.ns + chain;
         pos = p.inj_pos[o];
         if (p.kind == QTX_SPIN_EXCHANGE) slot = p.inj_slot[o];
-        u = p.inj_u[o];
+        thr = log1p(-p.inj_u[o]);
       } else {
         if ((t & 31) == 0) {
           uint64_t step = p.step0 + (uint64_t)(t + lane);
+          uint32_t q2 = (uint32_t)(step >> 32), q3 = 0;
           q0 = (uint32_t)(p.chain0 + chain);
           q1 = (uint32_t)step;
-          q2 = (uint32_t)(step >> 32);
-          q3 = 0;
           philox4x32_10(q0, q1, q2, q3, p.seed_lo, p.seed_hi);
+          qthr = log1p(-((double)((((uint64_t)q2 << 32) | q3) >> 11) * 0x1.0p-53));
         }
         int src = t & 31;
         uint32_t r0 = __shfl_sync(FULL, q0, src), r1 = __shfl_sync(FULL, q1, src);
-        uint32_t r2 = __shfl_sync(FULL, q2, src), r3 = __shfl_sync(FULL, q3, src);
-        u = (double)((((uint64_t)r2 << 32) | r3) >> 11) * 0x1.0p-53;
+        thr = __shfl_sync(FULL, qthr, src);
         if (p.kind == QTX_LOCAL_FLIP) {
           pos = (int)__umulhi(r0, (uint32_t)N);
         } else {
@@ -226,9 +228,7 @@ __global__ void __launch_bounds__(RMAX <= 8 ? 1024 : (sizeof(T) == 4 && RMAX <= 
           }
         }
         double la_new = (double)warp_sum(ls);
-        double rate = exp(la_new - la);
-        rate = rw2 ? rate * rate : pow(rate, p.reweight);
-        acc = rate > 1.0 - u;  // |psi| == 0 cannot happen: log|cosh| >= 0
+        acc = p.reweight * (la_new - la) > thr;  // |psi| == 0 cannot happen: log|cosh| >= 0
         if (acc) {
 #pragma unroll
           for (int r = 0; r < RMAX; ++r) {
@@ -397,56 +397,90 @@ __global__ void __launch_bounds__(RMAX <= 8 ? 1024 : (sizeof(T) == 4 && RMAX <= 
       }
     }
     const double la = (double)warp_sum(lsum);
-    double e = 0.0;
+    double e = 0.0, ediag = 0.0;
     int nconn = 0;
-    for (int t = 0; t < p.nterms; ++t) {
-      double c = coef[t];
-      uint2 st = sites[t];
-      uint32_t op4 = ops[t];
-      int site[4] = {(int)(st.x & 0xffff), (int)(st.x >> 16), (int)(st.y & 0xffff), (int)(st.y >> 16)};
-      bool valid = true;
-      int nfl = 0;
-      const T* cp[4];
-      T sg[4];
+    // 32 terms are decoded at once (one per lane); the warp then visits only the valid off-diagonal ones
+    for (int t0 = 0; t0 < p.nterms; t0 += 32) {
+      const int t = t0 + lane;
+      double c = 0.0;
+      uint2 st = make_uint2(0u, 0u);
+      uint32_t flipmask = 0;  // bit k set: site k of the term is flipped
+      bool valid = false;
+      if (t < p.nterms) {
+        c = coef[t];
+        st = sites[t];
+        const uint32_t op4 = ops[t];
+        const int site[4] = {(int)(st.x & 0xffff), (int)(st.x >> 16), (int)(st.y & 0xffff), (int)(st.y >> 16)};
+        valid = true;
 #pragma unroll
-      for (int k = 3; k >= 0; --k) {  // right-most operator acts first (operator.py:107)
-        int op = (op4 >> (8 * k)) & 0xff;
-        cp[k] = nullptr;
-        sg[k] = 0;
-        if (op == QTX_OP_NONE || op == QTX_OP_I) continue;
-        int sk = myspins[site[k]];
-        if (op == QTX_OP_Z) {
-          c = c * sk / 2;
+        for (int k = 3; k >= 0; --k) {  // right-most operator acts first (operator.py:107)
+          const int op = (op4 >> (8 * k)) & 0xff;
+          if (op == QTX_OP_NONE || op == QTX_OP_I) continue;
+          const int sk = myspins[site[k]];
+          if (op == QTX_OP_Z) {
+            c = c * sk / 2;
+          } else {
+            if (op == QTX_OP_X) c = c / 2;
+            else if (op == QTX_OP_P) valid = valid && (sk < 0);
+            else valid = valid && (sk > 0);
+            flipmask |= 1u << k;
+          }
+        }
+        if (flipmask == 0) {
+          ediag += c;
+          valid = false;
         } else {
-          if (op == QTX_OP_X) c = c / 2;
-          else if (op == QTX_OP_P) valid = valid && (sk < 0);
-          else valid = valid && (sk > 0);
-          cp[k] = Wt + (size_t)site[k] * M;
-          sg[k] = (T)(-sk);  // new spin value at the flipped site
-          ++nfl;
+          valid = valid && fabs(c) > 1e-8;  // NaN or isclose(H, 0) (operator.py:154)
         }
       }
-      if (nfl == 0) {
-        e += c;
-        continue;
-      }
-      if (!valid || fabs(c) <= 1e-8) continue;  // NaN or isclose(H, 0) (operator.py:154)
-      ++nconn;
-      T ls = 0;
+      uint32_t todo = __ballot_sync(FULL, valid);
+      nconn += __popc(todo);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const double cc = __shfl_sync(FULL, c, src);
+        const uint32_t sx = __shfl_sync(FULL, st.x, src), sy = __shfl_sync(FULL, st.y, src);
+        const uint32_t fm = __shfl_sync(FULL, flipmask, src);
+        const int site[4] = {(int)(sx & 0xffff), (int)(sx >> 16), (int)(sy & 0xffff), (int)(sy >> 16)};
+        const T* cp[4];
+        T sg[4];
 #pragma unroll
-      for (int r = 0; r < RMAX; ++r) {
-        int i = r * 32 + lane;
-        if (i < M) {
-          T d = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (cp[k]) d += cp[k][i] * sg[k];
-          ls += lncosh(th[r] + T(2) * d);
+        for (int k = 0; k < 4; ++k) {
+          const bool f = (fm >> k) & 1u;
+          cp[k] = f ? Wt + (size_t)site[k] * M : nullptr;
+          sg[k] = f ? (T)(-myspins[site[k]]) : T(0);  // new spin value at the flipped site
         }
+        T ls = 0;
+        if (fm == 3u) {  // two-site exchange / hop terms (Heisenberg, J1-J2)
+#pragma unroll
+          for (int r = 0; r < RMAX; ++r) {
+            const int i = r * 32 + lane;
+            if (i < M) ls += lncosh(th[r] + T(2) * (cp[0][i] * sg[0] + cp[1][i] * sg[1]));
+          }
+        } else if (fm == 1u) {  // single-site flips (transverse field)
+#pragma unroll
+          for (int r = 0; r < RMAX; ++r) {
+            const int i = r * 32 + lane;
+            if (i < M) ls += lncosh(th[r] + T(2) * (cp[0][i] * sg[0]));
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RMAX; ++r) {
+            const int i = r * 32 + lane;
+            if (i < M) {
+              T d = 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (cp[k]) d += cp[k][i] * sg[k];
+              ls += lncosh(th[r] + T(2) * d);
+            }
+          }
+        }
+        const double la_new = (double)warp_sum(ls);
+        e += cc * exp(la_new - la);
       }
-      double la_new = (double)warp_sum(ls);
-      e += c * exp(la_new - la);
     }
+    e += warp_sum(ediag);
     if (lane == 0) {
       p.eloc[s] = e;
       if (p.nconn) p.nconn[s] = nconn;
