@@ -304,15 +304,27 @@ static int launch_sweep(const SweepParams<T>& p, cudaStream_t st) {
   return QTX_OK;
 }
 
+// hidden-unit registers per lane: the smallest instantiated value >= ceil(M / 32) (unused registers still
+// cost issue slots, so the grid of instantiations is fairly fine: M = 400 -> 13)
+#define QTX_RBM_DISPATCH(LAUNCH, T, p, st)                         \
+  do {                                                             \
+    const int nreg_ = ((p).M + 31) / 32;                           \
+    if (nreg_ <= 2) return LAUNCH<T, 2>(p, st);                    \
+    if (nreg_ <= 4) return LAUNCH<T, 4>(p, st);                    \
+    if (nreg_ <= 6) return LAUNCH<T, 6>(p, st);                    \
+    if (nreg_ <= 8) return LAUNCH<T, 8>(p, st);                    \
+    if (nreg_ <= 10) return LAUNCH<T, 10>(p, st);                  \
+    if (nreg_ <= 13) return LAUNCH<T, 13>(p, st);                  \
+    if (nreg_ <= 16) return LAUNCH<T, 16>(p, st);                  \
+    if (nreg_ <= 20) return LAUNCH<T, 20>(p, st);                  \
+    if (nreg_ <= 26) return LAUNCH<T, 26>(p, st);                  \
+    if (nreg_ <= 32) return LAUNCH<T, 32>(p, st);                  \
+  } while (0)
+
 template <typename T>
 static int sweep_dispatch(const SweepParams<T>& p, cudaStream_t st) {
-  const int M = p.M;
-  if (M <= 64) return launch_sweep<T, 2>(p, st);
-  if (M <= 128) return launch_sweep<T, 4>(p, st);
-  if (M <= 256) return launch_sweep<T, 8>(p, st);
-  if (M <= 512) return launch_sweep<T, 16>(p, st);
-  if (M <= 1024) return launch_sweep<T, 32>(p, st);
-  set_error("qtx_rbm_sweep: M=%d > 1024 hidden units is not supported", M);
+  QTX_RBM_DISPATCH(launch_sweep, T, p, st);
+  set_error("qtx_rbm_sweep: M=%d > 1024 hidden units is not supported", p.M);
   return QTX_ERR_UNSUPPORTED;
 }
 
@@ -520,13 +532,8 @@ static int launch_oloc(OlocParams<T> p, cudaStream_t st) {
 
 template <typename T>
 static int oloc_dispatch(const OlocParams<T>& p, cudaStream_t st) {
-  const int M = p.M;
-  if (M <= 64) return launch_oloc<T, 2>(p, st);
-  if (M <= 128) return launch_oloc<T, 4>(p, st);
-  if (M <= 256) return launch_oloc<T, 8>(p, st);
-  if (M <= 512) return launch_oloc<T, 16>(p, st);
-  if (M <= 1024) return launch_oloc<T, 32>(p, st);
-  set_error("qtx_rbm_oloc: M=%d > 1024 hidden units is not supported", M);
+  QTX_RBM_DISPATCH(launch_oloc, T, p, st);
+  set_error("qtx_rbm_oloc: M=%d > 1024 hidden units is not supported", p.M);
   return QTX_ERR_UNSUPPORTED;
 }
 
