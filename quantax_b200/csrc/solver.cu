@@ -2,6 +2,7 @@
 // The eigendecomposition is cuSOLVER syevd (a library call, reported separately in the bench);
 // the pseudo-inverse epilogue is three small kernels on the eigenvector matrix.
 #include <cusolverDn.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -103,7 +104,7 @@ extern "C" size_t qtx_pinv_eig_workspace_size(int64_t n) {
   int lwork = 0;
   if (n <= 0 || n > 46340 || syevd_lwork(n, &lwork)) return 0;
   // [lwork doubles | evals n | rho n]
-  return ((size_t)lwork + 2 * (size_t)n) * sizeof(double) + 256;
+  return ((size_t)lwork + 2 * (size_t)n) * sizeof(double) + 8192;
 }
 
 extern "C" int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double rtol, double atol, double* evals_out,
@@ -118,19 +119,38 @@ extern "C" int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double 
   int lwork = 0;
   rc = syevd_lwork(n, &lwork);
   if (rc) return rc;
-  QTX_REQUIRE(workspace_bytes >= ((size_t)lwork + 2 * (size_t)n) * sizeof(double), QTX_ERR_INVALID,
+  QTX_REQUIRE(workspace_bytes >= ((size_t)lwork + 2 * (size_t)n + 512) * sizeof(double), QTX_ERR_INVALID,
               "qtx_pinv_eig_solve: workspace too small");
   double* work = (double*)workspace;
-  double* evals = work + lwork;
+  double* evals = work + lwork + 512;  // 4 KB slack: the 64-bit API asks for slightly more than the legacy one
   double* rho = evals + n;
   if (rtol < 0) rtol = 1e-12;  // solver.py:12-21 for float64
   cusolverStatus_t s = cusolverDnSetStream(h, st);
   QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnSetStream failed (%d)", (int)s);
   // row-major symmetric == column-major symmetric; on exit T holds column-major eigenvectors,
   // i.e. row k of the buffer is eigenvector k.
-  s = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, T, (int)n, evals, work, lwork,
-                       info_out);
-  QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnDsyevd failed (%d)", (int)s);
+  static const int algo = getenv("QTX_EIGH_ALGO") ? atoi(getenv("QTX_EIGH_ALGO")) : 0;
+  if (algo == 1) {
+    // experiment: 64-bit generic API (needs host + device workspaces)
+    static thread_local cusolverDnParams_t params = nullptr;
+    if (!params) cusolverDnCreateParams(&params);
+    size_t dbytes = 0, hbytes = 0;
+    s = cusolverDnXsyevd_bufferSize(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, T, n,
+                                    CUDA_R_64F, evals, CUDA_R_64F, &dbytes, &hbytes);
+    QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "Xsyevd_bufferSize failed (%d)", (int)s);
+    QTX_REQUIRE(dbytes <= (size_t)lwork * sizeof(double) + 4096, QTX_ERR_SOLVER, "Xsyevd needs %zu B > %zu B", dbytes,
+                (size_t)lwork * sizeof(double));
+    static thread_local void* hbuf = nullptr;
+    static thread_local size_t hcap = 0;
+    if (hbytes > hcap) { free(hbuf); hbuf = malloc(hbytes); hcap = hbytes; }
+    s = cusolverDnXsyevd(h, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, T, n, CUDA_R_64F,
+                         evals, CUDA_R_64F, work, dbytes, hbuf, hbytes, info_out);
+    QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnXsyevd failed (%d)", (int)s);
+  } else {
+    s = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, T, (int)n, evals, work, lwork,
+                         info_out);
+    QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnDsyevd failed (%d)", (int)s);
+  }
   count_launch();
   rows_dot_kernel<<<(unsigned)n, 256, 0, st>>>(T, n, b, rho);
   QTX_LAUNCH_CHECK();
