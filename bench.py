@@ -326,7 +326,8 @@ def run_b200(args):
                          "note": ("achieved = float64-equivalent flops of the reference's full product 2 Ns^2 Np per launch / "
                                   "CUDA-event time (split + MMA kernels); peak = cuBLAS bf16 of MEASURED_PEAKS.json (burst). "
                                   "float64 accuracy costs s(s+1)/2 = %d exact int8 products, so this fraction is bounded by "
-                                  "2/%d = %.3f even at 100%% int8 tensor-pipe utilisation." % (pairs, pairs, 2.0 / max(pairs, 1))
+                                  "4/%d = %.3f even at 100%% int8 tensor-pipe utilisation (lower-triangular tiles only, int8 rate = 2x bf16)."
+                                  % (pairs, pairs, 4.0 / max(pairs, 1))
                                   if peaks else "fallback peak"),
                          "tensor_pipe": {"int8_top_s": int8_ach, "int8_peak_top_s": 2 * peak_tf,
                                          "frac": int8_ach / (2 * peak_tf),

@@ -136,10 +136,13 @@ int qtx_rbm_ref_forward(int model_dtype, const void* W, int N, int M, const void
  * computed in model dtype and cast to out_dtype (variational.py:491).
  * If col_mean (float64 [M*N+M]) is given the row is centred, and if row_scale (float64 [ns])
  * is given it is scaled: out = (O - mean) * scale, i.e. Obar of quantax/optimizer/sr.py:74-88
- * written in a single pass.  out [ns, ld] with ld >= M*N+M elements per row. */
+ * written in a single pass.  out [ns, ld] with ld >= M*N+M elements per row.
+ * tanh_table (nullable): tanh(theta) [ns, M] in model dtype as written by
+ * qtx_rbm_jacobian_colmean(tanh_out) for the same spins; skips the theta recomputation. */
 int qtx_rbm_jacobian(int model_dtype, const void* W, const void* b, int N, int M,
                      const int8_t* spins, int64_t ns, int out_dtype, void* out, int64_t ld,
-                     const double* col_mean, const double* row_scale, qtx_stream_t stream);
+                     const double* col_mean, const double* row_scale, const void* tanh_table,
+                     qtx_stream_t stream);
 
 /* Column mean of the RBM Jacobian without materialising it (mean over samples of
  * tanh(theta_i) s_j, optionally weighted by w[s]): the `jnp.mean(Omat, axis=0)` of
@@ -147,8 +150,8 @@ int qtx_rbm_jacobian(int model_dtype, const void* W, const void* b, int N, int M
 size_t qtx_rbm_colmean_workspace_size(int model_dtype, int N, int M, int64_t ns);
 int qtx_rbm_jacobian_colmean(int model_dtype, const void* W, const void* b, int N, int M,
                              const int8_t* spins, int64_t ns, const double* weight,
-                             double* mean_out, void* workspace, size_t workspace_bytes,
-                             qtx_stream_t stream);
+                             double* mean_out, void* tanh_out /* nullable, [ns, M] model dtype */,
+                             void* workspace, size_t workspace_bytes, qtx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * ResConv (quantax/model/conv_nets.py:26-183): pre-activation residual CNN with circular padding,

@@ -593,20 +593,26 @@ __global__ void __launch_bounds__(256) rbm_jacobian_kernel(const T* __restrict__
                                                            int M, const int8_t* __restrict__ spins, int64_t ns,
                                                            OutT* __restrict__ out, int64_t ld,
                                                            const double* __restrict__ col_mean,
-                                                           const double* __restrict__ row_scale) {
+                                                           const double* __restrict__ row_scale,
+                                                           const T* __restrict__ tanh_table) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* t_s = reinterpret_cast<T*>(smem_raw);          // [M] tanh(theta)
   T* s_s = t_s + ((M + 3) / 4 * 4);                  // [N] spins as T
   const int64_t s = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int8_t* sp = spins + s * N;
   for (int j = threadIdx.x; j < N; j += blockDim.x) s_s[j] = (T)sp[j];
   __syncthreads();
-  for (int i = warp; i < M; i += nw) {
-    T acc = 0;
-    for (int j = lane; j < N; j += 32) acc += W[(size_t)i * N + j] * s_s[j];
-    acc = warp_sum(acc) + b[i];
-    if (lane == 0) t_s[i] = tanh(acc);
+  if (tanh_table) {
+    for (int i = threadIdx.x; i < M; i += blockDim.x) t_s[i] = tanh_table[s * M + i];
+  } else {
+    // same summation order as rbm_tanh_kernel (sites ascending, bias last), so the rows written here are
+    // bitwise consistent with the column means of qtx_rbm_jacobian_colmean
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      const T* wr = W + (size_t)i * N;
+      T acc = 0;
+      for (int j = 0; j < N; ++j) acc += wr[j] * s_s[j];
+      t_s[i] = tanh(acc + b[i]);
+    }
   }
   __syncthreads();
   const double scale = row_scale ? row_scale[s] : 1.0;
@@ -860,30 +866,31 @@ extern "C" int qtx_rbm_ref_forward(int model_dtype, const void* W, int N, int M,
 
 template <typename T, typename OutT>
 static int jac_launch(const void* W, const void* b, int N, int M, const int8_t* spins, int64_t ns, void* out,
-                      int64_t ld, const double* mean, const double* scale, cudaStream_t st) {
+                      int64_t ld, const double* mean, const double* scale, const void* table, cudaStream_t st) {
   size_t smem = ((size_t)(M + 3) / 4 * 4 + N) * sizeof(T) + 16;
   QTX_REQUIRE(smem <= kSmemBudget, QTX_ERR_UNSUPPORTED, "qtx_rbm_jacobian: M+N too large for shared memory");
   auto k = rbm_jacobian_kernel<T, OutT>;
   if (smem > 48 * 1024) QTX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<(unsigned)ns, 256, smem, st>>>((const T*)W, (const T*)b, N, M, spins, ns, (OutT*)out, ld, mean, scale);
+  k<<<(unsigned)ns, 256, smem, st>>>((const T*)W, (const T*)b, N, M, spins, ns, (OutT*)out, ld, mean, scale,
+                                     (const T*)table);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }
 
 extern "C" int qtx_rbm_jacobian(int model_dtype, const void* W, const void* b, int N, int M, const int8_t* spins,
                                 int64_t ns, int out_dtype, void* out, int64_t ld, const double* col_mean,
-                                const double* row_scale, qtx_stream_t stream) {
+                                const double* row_scale, const void* tanh_table, qtx_stream_t stream) {
   QTX_REQUIRE(W && b && spins && out && N > 0 && M > 0 && ns >= 0, QTX_ERR_INVALID, "qtx_rbm_jacobian: bad argument");
   QTX_REQUIRE(ld >= (int64_t)M * N + M, QTX_ERR_INVALID, "qtx_rbm_jacobian: ld smaller than the parameter count");
   QTX_REQUIRE(ns < (1ll << 31), QTX_ERR_UNSUPPORTED, "qtx_rbm_jacobian: ns too large");
   if (ns == 0) return QTX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (model_dtype == QTX_F32 && out_dtype == QTX_F64)
-    return jac_launch<float, double>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, st);
+    return jac_launch<float, double>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, tanh_table, st);
   if (model_dtype == QTX_F32 && out_dtype == QTX_F32)
-    return jac_launch<float, float>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, st);
+    return jac_launch<float, float>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, tanh_table, st);
   if (model_dtype == QTX_F64 && out_dtype == QTX_F64)
-    return jac_launch<double, double>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, st);
+    return jac_launch<double, double>(W, b, N, M, spins, ns, out, ld, col_mean, row_scale, tanh_table, st);
   QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_rbm_jacobian: unsupported dtype pair (%d -> %d)", model_dtype, out_dtype);
 }
 
@@ -901,8 +908,8 @@ static int tanh_launch(const T* Wt, const T* b, int N, int M, const int8_t* spin
 
 template <typename T>
 static int colmean_impl(const void* W, const void* b, int N, int M, const int8_t* spins, int64_t ns,
-                        const double* weight, double* mean_out, void* ws, cudaStream_t st) {
-  T* t = (T*)ws;
+                        const double* weight, double* mean_out, void* tanh_out, void* ws, cudaStream_t st) {
+  T* t = tanh_out ? (T*)tanh_out : (T*)ws;
   T* Wt = (T*)((char*)ws + ((size_t)ns * M * sizeof(T) + 255) / 256 * 256);
   int rc = transpose_w<T>(W, Wt, N, M, st);
   if (rc) return rc;
@@ -930,13 +937,13 @@ static int colmean_impl(const void* W, const void* b, int N, int M, const int8_t
 
 extern "C" int qtx_rbm_jacobian_colmean(int model_dtype, const void* W, const void* b, int N, int M,
                                         const int8_t* spins, int64_t ns, const double* weight, double* mean_out,
-                                        void* workspace, size_t workspace_bytes, qtx_stream_t stream) {
+                                        void* tanh_out, void* workspace, size_t workspace_bytes, qtx_stream_t stream) {
   QTX_REQUIRE(W && b && spins && mean_out && N > 0 && M > 0 && ns > 0, QTX_ERR_INVALID,
               "qtx_rbm_jacobian_colmean: bad argument");
   QTX_REQUIRE(workspace && workspace_bytes >= qtx_rbm_colmean_workspace_size(model_dtype, N, M, ns), QTX_ERR_INVALID,
               "qtx_rbm_jacobian_colmean: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  if (model_dtype == QTX_F32) return colmean_impl<float>(W, b, N, M, spins, ns, weight, mean_out, workspace, st);
-  if (model_dtype == QTX_F64) return colmean_impl<double>(W, b, N, M, spins, ns, weight, mean_out, workspace, st);
+  if (model_dtype == QTX_F32) return colmean_impl<float>(W, b, N, M, spins, ns, weight, mean_out, tanh_out, workspace, st);
+  if (model_dtype == QTX_F64) return colmean_impl<double>(W, b, N, M, spins, ns, weight, mean_out, tanh_out, workspace, st);
   QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_rbm_jacobian_colmean: bad dtype %d", model_dtype);
 }

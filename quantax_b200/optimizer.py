@@ -251,14 +251,14 @@ class QNGD:
         rw = samples.reweight_factor
         scale = torch.sqrt(rw / ns_glob)
         ev = self._tic("jacobian")
-        mean = state.jacobian_colmean(samples.spins)
+        mean, table = state.jacobian_colmean(samples.spins, return_table=True)
         if mean is not None:
             # one-pass path: column means first (without materialising O), then write Obar directly
             if P > 1:
                 _dist().all_reduce(mean)
                 mean /= P
             self._Omean = mean  # == mean(O * rw) for reweight 2 (rw = 1)
-            Obar = state.jacobian(samples.spins, col_mean=mean, row_scale=scale)
+            Obar = state.jacobian(samples.spins, col_mean=mean, row_scale=scale, tanh_table=table)
         else:
             Omat = state.jacobian(samples.spins)
             mean = torch.empty(Omat.shape[1], dtype=torch.float64, device=Omat.device)

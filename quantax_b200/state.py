@@ -234,7 +234,8 @@ class Variational(State):
         return eloc
 
     # ---- jacobian (variational.py:424-511) ----------------------------------------------------
-    def jacobian(self, fock_states, out: Optional[torch.Tensor] = None, col_mean=None, row_scale=None):
+    def jacobian(self, fock_states, out: Optional[torch.Tensor] = None, col_mean=None, row_scale=None,
+                 tanh_table=None):
         r"""O[s, k] = (1/psi) d psi / d theta_k, [ns, nparams] in the default dtype; column order =
         ``get_params_flatten``.  With ``col_mean`` / ``row_scale`` the centred and scaled matrix
         Obar of sr.py:74-88 is written directly."""
@@ -249,7 +250,7 @@ class Variational(State):
         elif m.kind == "rbm":
             _lib.call("qtx_rbm_jacobian", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
                       _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), _lib.ptr(col_mean),
-                      _lib.ptr(row_scale), _lib.stream())
+                      _lib.ptr(row_scale), _lib.ptr(tanh_table), _lib.stream())
             return out
         else:
             self._model_jacobian(s, out)
@@ -262,7 +263,7 @@ class Variational(State):
         m = self._model
         if m.kind == "rbm":
             _lib.call("qtx_rbm_jacobian", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), s.shape[0],
-                      _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), None, None, _lib.stream())
+                      _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), None, None, None, _lib.stream())
         else:
             from .resconv import resconv_jacobian
 
@@ -287,19 +288,22 @@ class Variational(State):
             _lib.call("qtx_weighted_rowsum", _lib.dtype_code(out.dtype), _lib.ptr2d(J), J.stride(0), _lib.ptr(coef),
                       hi - lo, nsymm, m.nparams, _lib.ptr2d(out[lo:hi]), out.stride(0), _lib.stream())
 
-    def jacobian_colmean(self, fock_states, weight=None) -> Optional[torch.Tensor]:
-        """Column mean of the Jacobian without materialising it (RBM), else None."""
+    def jacobian_colmean(self, fock_states, weight=None, return_table: bool = False):
+        """Column mean of the Jacobian without materialising it (RBM), else None.  With ``return_table`` also
+        returns tanh(theta) [ns, M], which ``jacobian(..., tanh_table=)`` reuses so that the centred rows are
+        bitwise consistent with these means."""
         m = self._model
         if m.kind != "rbm" or not self._symm.is_identity:
-            return None
+            return (None, None) if return_table else None
         s = self._spins(fock_states)
         ns = s.shape[0]
         mean = torch.empty(m.nparams, dtype=torch.float64, device=s.device)
+        table = torch.empty((ns, m.M), dtype=m.dtype, device=s.device) if return_table else None
         wsz = _lib.lib().qtx_rbm_colmean_workspace_size(self._mdt(), m.N, m.M, ns)
         ws = self._workspace("colmean", wsz)
         _lib.call("qtx_rbm_jacobian_colmean", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
-                  _lib.ptr(weight), _lib.ptr(mean), _lib.ptr(ws), wsz, _lib.stream())
-        return mean
+                  _lib.ptr(weight), _lib.ptr(mean), _lib.ptr(table), _lib.ptr(ws), wsz, _lib.stream())
+        return (mean, table) if return_table else mean
 
     # ---- parameters (variational.py:545-587) ----------------------------------------------------
     def get_params_flatten(self) -> torch.Tensor:
