@@ -97,7 +97,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["sweep_oloc_s"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 model / f64 psi, Jacobian, solve",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU oracle port on a bounded sample"},
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "chains_per_gpu": NS, "sweep_steps": 2 * L * L, "minsr_rows_global": NS,
+                   "nparams": ALPHA * L * L * L * L + ALPHA * L * L, "note": "CPU oracle port on a bounded sample"},
         "minsr_step_ms": cb["minsr_step_ms_at_sample"], "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,

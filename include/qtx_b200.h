@@ -294,6 +294,23 @@ int qtx_matvec(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, con
 int qtx_apply_update(int model_dtype, void* params, const double* step, double lr, int64_t np,
                      int32_t* flag_out, qtx_stream_t stream);
 
+/* Vector helpers of the momentum optimizers SPRING / MARCH / AdamSR
+ * (quantax/optimizer/sr.py:198-429), all float64 device vectors:
+ *   axpby          y <- a x + b y
+ *   div_add        out <- x / d + c z            (z nullable)
+ *   second_moment  V <- beta V + (1 - beta) |x - y|^2   (y nullable)
+ *   fourth_root    out <- (v / corr)^(1/4) + eps
+ *   scale_columns  A[s, k] <- A[s, k] / d[k]     (Obar /= V[None, :], sr.py:304,409) */
+int qtx_axpby(int64_t n, double a, const double* x, double b, double* y, qtx_stream_t stream);
+int qtx_div_add(int64_t n, const double* x, const double* d, double c, const double* z, double* out,
+                qtx_stream_t stream);
+int qtx_second_moment(int64_t n, double beta, const double* x, const double* y, double* V,
+                      qtx_stream_t stream);
+int qtx_fourth_root(int64_t n, const double* v, double corr, double eps, double* out,
+                    qtx_stream_t stream);
+int qtx_scale_columns(int dtype, void* A, int64_t ns, int64_t np, int64_t ld, const double* d,
+                      qtx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

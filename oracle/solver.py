@@ -107,3 +107,50 @@ def update_params(params, step):
     if not np.all(np.isfinite(step)):
         return params
     return params + (-step.real).astype(params.dtype)
+
+
+# ---- momentum variants (quantax/optimizer/sr.py:198-429), real parameters -------------------------
+class SpringOracle:
+    def __init__(self, nparams, mu=0.9):
+        self.mu, self.last = mu, np.zeros(nparams)
+
+    def solve(self, Obar, Ebar):
+        Ebar = Ebar - self.mu * (Obar @ self.last)
+        step = auto_pinv_eig(Obar, Ebar) + self.mu * self.last
+        self.last = step
+        return step
+
+
+class MarchOracle:
+    def __init__(self, nparams, mu=0.95, beta=0.995):
+        self.mu, self.beta = mu, beta
+        self.last, self.V, self.t = np.zeros(nparams), np.zeros(nparams), 0
+
+    def solve(self, Obar, Ebar):
+        self.t += 1
+        Ebar = Ebar - self.mu * (Obar @ self.last)
+        if np.allclose(self.V, 0):
+            V = np.ones_like(self.V)
+        else:
+            V = (self.V / (1 - self.beta ** self.t)) ** 0.25 + 1e-8
+        step = auto_pinv_eig(Obar / V[None, :], Ebar)
+        step = step / V + self.mu * self.last
+        self.V = self.beta * self.V + (1 - self.beta) * np.abs(step - self.last) ** 2
+        self.last = step
+        return step
+
+
+class AdamSROracle:
+    def __init__(self, nparams, mu=0.95, beta=0.995):
+        self.mu, self.beta = mu, beta
+        self.m, self.v, self.t = np.zeros(nparams), np.zeros(nparams), 0
+
+    def solve(self, Obar, Ebar):
+        self.t += 1
+        g = auto_pinv_eig(Obar, Ebar)
+        self.m = self.mu * self.m + (1 - self.mu) * g
+        self.v = self.beta * self.v + (1 - self.beta) * np.abs(g) ** 2
+        m = self.m / (1 - self.mu ** self.t)
+        V = (self.v / (1 - self.beta ** self.t)) ** 0.25 + 1e-8
+        step = auto_pinv_eig(Obar / V[None, :], Ebar - Obar @ m)
+        return step / V + m

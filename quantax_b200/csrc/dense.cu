@@ -130,6 +130,40 @@ __global__ void apply_update_kernel(T* __restrict__ params, const double* __rest
     params[k] = params[k] + (T)(-(step[k] * lr));
 }
 
+
+// ---- vector helpers of the momentum optimizers (SPRING / MARCH / AdamSR, quantax/optimizer/sr.py:198-429) ----
+__global__ void axpby_kernel(int64_t n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    y[k] = a * x[k] + (b == 0.0 ? 0.0 : b * y[k]);
+}
+// out[k] = x[k] / d[k] + c * z[k]   (z nullable)
+__global__ void div_add_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ d, double c,
+                               const double* __restrict__ z, double* __restrict__ out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    out[k] = x[k] / d[k] + (z ? c * z[k] : 0.0);
+}
+// V[k] = beta V[k] + (1 - beta) |x[k] - y[k]|^2   (y nullable)
+__global__ void second_moment_kernel(int64_t n, double beta, const double* __restrict__ x, const double* __restrict__ y,
+                                     double* __restrict__ V) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const double d = x[k] - (y ? y[k] : 0.0);
+    V[k] = beta * V[k] + (1.0 - beta) * d * d;
+  }
+}
+// out[k] = (v[k] / corr)^(1/4) + eps
+__global__ void fourth_root_kernel(int64_t n, const double* __restrict__ v, double corr, double eps,
+                                   double* __restrict__ out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    out[k] = sqrt(sqrt(v[k] / corr)) + eps;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) scale_columns_kernel(T* __restrict__ A, int64_t np, int64_t ld,
+                                                            const double* __restrict__ d) {
+  T* row = A + (int64_t)blockIdx.y * ld;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x)
+    row[k] = (T)((double)row[k] / d[k]);
+}
+
 __global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
 
 template <typename T>
@@ -218,6 +252,61 @@ extern "C" int qtx_apply_update(int model_dtype, void* params, const double* ste
   else if (model_dtype == QTX_F64)
     apply_update_kernel<double><<<g, 256, 0, st>>>((double*)params, step, lr, np, flag_out);
   else QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_apply_update: bad dtype %d", model_dtype);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+static unsigned vec_grid(int64_t n) {
+  unsigned g = (unsigned)((n + 255) / 256);
+  unsigned cap = 8u * (unsigned)num_sms();
+  return g > cap ? cap : (g ? g : 1);
+}
+
+extern "C" int qtx_axpby(int64_t n, double a, const double* x, double b, double* y, qtx_stream_t stream) {
+  if (n == 0) return QTX_OK;
+  QTX_REQUIRE(x && y && n > 0, QTX_ERR_INVALID, "qtx_axpby: bad argument");
+  axpby_kernel<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_div_add(int64_t n, const double* x, const double* d, double c, const double* z, double* out,
+                           qtx_stream_t stream) {
+  if (n == 0) return QTX_OK;
+  QTX_REQUIRE(x && d && out && n > 0, QTX_ERR_INVALID, "qtx_div_add: bad argument");
+  div_add_kernel<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>(n, x, d, c, z, out);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_second_moment(int64_t n, double beta, const double* x, const double* y, double* V,
+                                 qtx_stream_t stream) {
+  if (n == 0) return QTX_OK;
+  QTX_REQUIRE(x && V && n > 0, QTX_ERR_INVALID, "qtx_second_moment: bad argument");
+  second_moment_kernel<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>(n, beta, x, y, V);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_fourth_root(int64_t n, const double* v, double corr, double eps, double* out, qtx_stream_t stream) {
+  if (n == 0) return QTX_OK;
+  QTX_REQUIRE(v && out && n > 0 && corr != 0.0, QTX_ERR_INVALID, "qtx_fourth_root: bad argument");
+  fourth_root_kernel<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>(n, v, corr, eps, out);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_scale_columns(int dtype, void* A, int64_t ns, int64_t np, int64_t ld, const double* d,
+                                 qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(A && d && np > 0 && ld >= np && ns <= 65535, QTX_ERR_INVALID, "qtx_scale_columns: bad argument");
+  unsigned gx = (unsigned)((np + 255) / 256);
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, (unsigned)ns);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == QTX_F64) scale_columns_kernel<double><<<grid, 256, 0, st>>>((double*)A, np, ld, d);
+  else if (dtype == QTX_F32) scale_columns_kernel<float><<<grid, 256, 0, st>>>((float*)A, np, ld, d);
+  else QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_scale_columns: bad dtype %d", dtype);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }

@@ -337,3 +337,110 @@ class MinSR(SR):
 
     def __init__(self, state: Variational, hamiltonian, imag_time: bool = True, solver: Optional[Callable] = None):
         super().__init__(state, hamiltonian, imag_time, minnorm_pinv_eig() if solver is None else solver)
+
+
+# ---- momentum variants (quantax/optimizer/sr.py:198-429) --------------------------------------------
+def _vec(n: int) -> torch.Tensor:
+    return torch.zeros(n, dtype=torch.float64, device=device())
+
+
+def _axpby(a: float, x: torch.Tensor, b: float, y: torch.Tensor) -> torch.Tensor:
+    """y <- a x + b y (in place on y)."""
+    _lib.call("qtx_axpby", x.numel(), float(a), _lib.ptr(x.contiguous()), float(b), _lib.ptr(y), _lib.stream())
+    return y
+
+
+def _scale_columns(A: torch.Tensor, d: torch.Tensor) -> None:
+    _lib.call("qtx_scale_columns", _lib.dtype_code(A.dtype), _lib.ptr2d(A), A.shape[0], A.shape[1], A.stride(0),
+              _lib.ptr(d), _lib.stream())
+
+
+class SPRING(SR):
+    """SR with momentum (sr.py:198-262): Ebar -= mu Obar step_prev; step = solve + mu step_prev."""
+
+    def __init__(self, state, hamiltonian, imag_time: bool = True, solver=None, mu: float = 0.9, file=None):
+        super().__init__(state, hamiltonian, imag_time, solver)
+        self._mu = mu
+        self._last_step = _vec(state.nparams)
+        if file is not None:
+            self.load(file)
+
+    def solve(self, Obar: torch.Tensor, Ebar: torch.Tensor) -> torch.Tensor:
+        Ebar = _axpby(-self._mu, matvec(Obar, self._last_step), 1.0, Ebar.clone())
+        step = super().solve(Obar, Ebar)
+        step = _axpby(self._mu, self._last_step, 1.0, step)
+        self._last_step = step.clone()
+        return step
+
+    def save(self, file) -> None:
+        import numpy as np
+
+        if world()[0] == 0:
+            np.savez(file, mu=self._mu, last_step=self._last_step.cpu().numpy())
+
+    def load(self, file) -> None:
+        import numpy as np
+
+        d = np.load(file)
+        self._mu = float(d["mu"])
+        self._last_step = torch.from_numpy(d["last_step"]).to(device())
+
+
+class MARCH(SR):
+    """SR with first and second order momentum (sr.py:265-349)."""
+
+    def __init__(self, state, hamiltonian, imag_time: bool = True, solver=None, mu: float = 0.95, beta: float = 0.995,
+                 file=None):
+        super().__init__(state, hamiltonian, imag_time, solver)
+        self._mu, self._beta = mu, beta
+        self._last_step = _vec(state.nparams)
+        self._V = _vec(state.nparams)
+        self._t = 0
+        self._V_is_zero = True
+
+    def solve(self, Obar: torch.Tensor, Ebar: torch.Tensor) -> torch.Tensor:
+        self._t += 1
+        n = self._last_step.numel()
+        Ebar = _axpby(-self._mu, matvec(Obar, self._last_step), 1.0, Ebar.clone())
+        V = torch.ones(n, dtype=torch.float64, device=Obar.device)
+        if not self._V_is_zero:  # `jnp.allclose(self._V, 0)` is true exactly before the first update (sr.py:298)
+            _lib.call("qtx_fourth_root", n, _lib.ptr(self._V), 1.0 - self._beta ** self._t, 1e-8, _lib.ptr(V),
+                      _lib.stream())
+        _scale_columns(Obar, V)
+        raw = super().solve(Obar, Ebar)
+        step = torch.empty_like(raw)
+        _lib.call("qtx_div_add", n, _lib.ptr(raw), _lib.ptr(V), float(self._mu), _lib.ptr(self._last_step),
+                  _lib.ptr(step), _lib.stream())
+        _lib.call("qtx_second_moment", n, float(self._beta), _lib.ptr(step), _lib.ptr(self._last_step),
+                  _lib.ptr(self._V), _lib.stream())
+        self._V_is_zero = False
+        self._last_step = step.clone()
+        return step
+
+
+class AdamSR(SR):
+    """Adam-like SR (sr.py:352-429); two solves per step."""
+
+    def __init__(self, state, hamiltonian, imag_time: bool = True, solver=None, mu: float = 0.95, beta: float = 0.995,
+                 file=None):
+        super().__init__(state, hamiltonian, imag_time, solver)
+        self._mu, self._beta = mu, beta
+        self._m = _vec(state.nparams)
+        self._v = _vec(state.nparams)
+        self._t = 0
+
+    def solve(self, Obar: torch.Tensor, Ebar: torch.Tensor) -> torch.Tensor:
+        self._t += 1
+        n = self._m.numel()
+        g = super().solve(Obar, Ebar)
+        _axpby(1.0 - self._mu, g, self._mu, self._m)
+        _lib.call("qtx_second_moment", n, float(self._beta), _lib.ptr(g), None, _lib.ptr(self._v), _lib.stream())
+        m = _axpby(1.0 / (1.0 - self._mu ** self._t), self._m, 0.0, torch.empty_like(self._m))
+        V = torch.empty_like(self._v)
+        _lib.call("qtx_fourth_root", n, _lib.ptr(self._v), 1.0 - self._beta ** self._t, 1e-8, _lib.ptr(V), _lib.stream())
+        Ebar = _axpby(-1.0, matvec(Obar, m), 1.0, Ebar.clone())
+        _scale_columns(Obar, V)
+        raw = super().solve(Obar, Ebar)
+        step = torch.empty_like(raw)
+        _lib.call("qtx_div_add", n, _lib.ptr(raw), _lib.ptr(V), 1.0, _lib.ptr(m), _lib.ptr(step), _lib.stream())
+        return step

@@ -158,3 +158,27 @@ def test_quick_start_converges_to_ed(qtx):
     e = np.mean(hist[-20:])
     assert e > e0 - 0.02 and abs(e - e0) < 0.01 * abs(e0), (e, e0)
     assert sampler.check_local_updates(samples) == 0
+
+
+@pytest.mark.parametrize("name", ["SPRING", "MARCH", "AdamSR"])
+def test_momentum_optimizers_match_oracle(qtx, name):
+    """SPRING / MARCH / AdamSR (quantax/optimizer/sr.py:198-429): three consecutive steps on fixed samples
+    must reproduce the oracle's momentum recursion."""
+    lat, olat = lattice_pair(qtx, "square", 4, (8, 8))
+    ns = 96
+    model, net = make_rbm(qtx, 16, 20, torch.float64, seed=41)
+    state = qtx.state.Variational(model)
+    H = qtx.operator.Heisenberg(msr=True)
+    aol = oop.to_array_op_list(oop.heisenberg_op_list(olat, msr=True))
+    opt = getattr(qtx.optimizer, name)(state, H)
+    orc = {"SPRING": osolver.SpringOracle, "MARCH": osolver.MarchOracle, "AdamSR": osolver.AdamSROracle}[name](model.nparams)
+    for it in range(3):
+        s = osmp.rand_states(ns, 16, 8, seed=50 + it)
+        st = torch.from_numpy(s).cuda()
+        samples = qtx.sampler.Samples(st, state(st), None, torch.ones(ns, dtype=torch.float64, device="cuda"))
+        step = to_np(opt.get_step(samples))
+        Eo = oop.oloc(aol, net.forward, s)
+        eb, _, _ = osolver.ebar(Eo, np.ones(ns))
+        ob, _ = osolver.obar(net.jacobian(s), np.ones(ns))
+        xo = orc.solve(ob, eb)
+        assert np.linalg.norm(step - xo) <= 1e-5 * np.linalg.norm(xo), (name, it)
