@@ -12,9 +12,17 @@
 // FMA pipe, not by HBM.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qtx {
+
+// tensor-core forward (resconv_tc.cu)
+bool resconv_tc_supported(int C, int lx, int ly, int kh, int kw);
+size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly);
+int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
+                       float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, cudaStream_t st);
 
 constexpr int kConvThreads = 256;
 constexpr int kOT = 32;   // out-channel tile per CTA
@@ -698,6 +706,16 @@ struct NetShape {
   }
 };
 
+static size_t resconv_ws_base(int dtype, int64_t ns, const NetShape& sh, bool grad) {
+  size_t es = dtype == QTX_F64 ? 8 : 4;
+  int64_t act = ns * sh.C * sh.N();
+  int64_t elems = ns * sh.N();
+  const int64_t wsz = (int64_t)sh.C * sh.C * sh.kh * sh.kw;
+  if (grad) elems += (int64_t)(2 * sh.nblocks + 2) * act + 2 * wsz;
+  else elems += 2 * act + wsz;
+  return ((size_t)elems * es + 511) & ~(size_t)255;
+}
+
 template <typename T>
 static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins, int64_t ns, double* sig_out,
                        double* exp_out, void* out, int out_dtype, int64_t ld, void* ws, cudaStream_t st) {
@@ -738,7 +756,18 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
     }
   }
   // ---- forward (conv_nets.py:78-92) ----
-  for (int i = 0; i < nb; ++i) {
+  bool tc_done = false;
+  if constexpr (std::is_same<T, float>::value) {
+    if (resconv_tc_supported(C, sh.lx, sh.ly, sh.kh, sh.kw)) {
+      // tensor-core tower (resconv_tc.cu); its workspace follows the regular one
+      const size_t base_bytes = resconv_ws_base(QTX_F32, ns, sh, grad);
+      int rc = resconv_tc_forward(nb, C, sh.lx, sh.ly, params, spins, ns, X, Hs, grad ? 1 : 0,
+                                  (unsigned char*)ws + base_bytes, resconv_tc_workspace(ns, nb, C, sh.lx, sh.ly), st);
+      if (rc) return rc;
+      tc_done = true;
+    }
+  }
+  for (int i = 0; i < nb && !tc_done; ++i) {
     const T* xin = (i == 0) ? x0 : (grad ? X + (int64_t)(i - 1) * act : X);
     T* h = grad ? Hs + (int64_t)i * act : Hs;
     T* xout = grad ? X + (int64_t)i * act : X;
@@ -838,13 +867,10 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
 }
 
 static size_t resconv_ws(int dtype, int64_t ns, const NetShape& sh, bool grad) {
-  size_t es = dtype == QTX_F64 ? 8 : 4;
-  int64_t act = ns * sh.C * sh.N();
-  int64_t elems = ns * sh.N();
-  const int64_t wsz = (int64_t)sh.C * sh.C * sh.kh * sh.kw;
-  if (grad) elems += (int64_t)(2 * sh.nblocks + 2) * act + 2 * wsz;
-  else elems += 2 * act + wsz;
-  return (size_t)elems * es + 256;
+  size_t b = resconv_ws_base(dtype, ns, sh, grad);
+  if (dtype == QTX_F32 && resconv_tc_supported(sh.C, sh.lx, sh.ly, sh.kh, sh.kw))
+    b += resconv_tc_workspace(ns, sh.nblocks, sh.C, sh.lx, sh.ly);
+  return b;
 }
 
 }  // namespace qtx

@@ -1,0 +1,611 @@
+// ResConv forward on the 5th-generation tensor cores (tcgen05 / TMEM), float32 models.
+//
+// quantax/model/conv_nets.py:78-92 — every 3x3 circular convolution of the residual tower is an
+// implicit GEMM  D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[cout, cin, tap]  with
+// M = pixels, N = cout, K = 9 * cin.  float32 accuracy (parity bar 1e-5) is kept with a two-term
+// binary16 split of both operands (x = hi + lo, |lo| <= 2^-11 |hi|) and three kind::f16 products
+// hi*hi + lo*hi + hi*lo accumulated in float32 in TMEM: the neglected lo*lo term and the rounding of
+// lo are ~2^-22 relative, below float32 GEMM rounding.  Operands are pre-scaled by powers of two
+// (activations x4, weights x256) so that `lo` stays a normal binary16 number for all values that
+// matter; the epilogue removes the exact factor 2^-10.  Range: |gelu output| < 16376.
+//
+// Layout ("raster"): the gelu'ed, split input of a convolution is stored per sample as a padded
+// raster of 16-byte slots (8 binary16 channels per slot), circular halo included, one plane per
+// 8-channel group:  act[kstep][hi|lo][plane-in-kstep][slot][8].  In the no-swizzle K-major UMMA
+// layout a core matrix is 8 rows x 16 B with the rows 16 B apart, so 8 consecutive slots of one plane
+// ARE a core matrix, and the operand tile of tap (dy, dx) is the same shared-memory tile addressed
+// (dy * row_pitch + dx) slots further: the nine taps re-read one staged tile, nothing is duplicated
+// in shared memory and no im2col is materialised.  Two rasters are used:
+//   SEG    (W % 8 == 0):  rows are cut into 8-pixel segments, each stored with its own left/right
+//          halo slot (10 slots); M rows = interior pixels only, stride-byte-offset = 10 slots
+//          -> no wasted MMA rows (16x16: one sample = two 128-row tiles);
+//   RASTER (any W):       plain (W+2)-pitch raster, M rows = consecutive slots from the first to the
+//          last interior pixel, halo columns compute garbage rows that the epilogue masks.
+//
+// One persistent kernel runs ALL tensor-core layers of the tower: a CTA owns its samples through the
+// whole depth (a layer's output of a sample depends only on that sample), keeps two work items in
+// flight (TMEM double buffer: the epilogue of one overlaps the MMAs of the other) and updates the
+// operand buffer in place, so activations stay L2-resident and only weights stream.
+//   warp 0    bulk-copy producer (cp.async.bulk, mbarrier complete_tx): activation k-step tiles and
+//             weight (k-step, kernel-row) tiles, two rings
+//   warp 1    MMA issuer (one thread), TMEM owner
+//   warps 2-9 epilogue: TMEM -> registers, bias / residual, raw float32 output (next residual, and the
+//             saved activations of the backward pass), gelu, split, operand store with halo copies
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "gram_tc_common.cuh"
+
+namespace qtx {
+
+constexpr int kTcThreads = 320;
+constexpr int kTcMaxLayers = 32;
+constexpr float kActScale = 4.0f;
+constexpr float kWScale = 256.0f;
+constexpr float kOutScale = 1.0f / (kActScale * kWScale);
+
+struct TcGeom {
+  int H, W, mode;  // mode 1 = SEG, 0 = RASTER
+  int nseg, RP, Ps, SB, TS;
+  int spi, tps;    // samples per item, tiles per sample (spi * tps == 2)
+  int64_t ns;      // samples
+  int64_t nitems;
+  int64_t slots;   // slots per plane (all samples + tail guard)
+};
+
+struct TcLayer {
+  int64_t wblob_off;       // in halfs
+  const float* bias;       // [C] or null
+  const float* res;        // raw residual [ns, C, N] or null
+  const int8_t* res_spin;  // block 0 residual: the spins, broadcast over channels, or null
+  float* raw_out;          // [ns, C, N] or null
+  float out_alpha;         // operand out = split(kActScale * gelu(out_alpha * v))
+  int write_act;
+};
+
+struct TcNetParams {
+  __half* act;
+  const __half* wblob;
+  TcGeom g;
+  int C, Np, KS;
+  int layer0, layer1;  // layers [layer0, layer1) are run by this launch
+  int act_stages, w_stages;
+  TcLayer layer[kTcMaxLayers];
+};
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// K-major, no swizzle: core matrix = 8 rows x 16 B (rows 16 B apart); LBO = distance between the two
+// core matrices of one K step, SBO = distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;
+}
+
+__device__ __forceinline__ float gelu_fast(float x) {
+  // x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)  ==  0.5 x (1 + tanh u)
+  const float u2 = -1.5957691216057308f * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.0f + __expf(u2));
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// the operand slots that hold pixel (y, x) of a sample: interior slot + halo copies
+struct PixSlots {
+  int row0, row1, col0, col1;  // row1 / col1 = -1 when there is no copy
+};
+__device__ __forceinline__ PixSlots pixel_slots(const TcGeom& g, int y, int x) {
+  PixSlots p;
+  p.row0 = y + 1;
+  p.row1 = (y == 0) ? g.H + 1 : ((y == g.H - 1) ? 0 : -1);
+  if (g.mode) {
+    const int seg = x >> 3, sl = (x & 7) + 1;
+    p.col0 = seg * 10 + sl;
+    p.col1 = (sl == 1) ? ((seg + g.nseg - 1) % g.nseg) * 10 + 9 : ((sl == 8) ? ((seg + 1) % g.nseg) * 10 : -1);
+  } else {
+    p.col0 = x + 1;
+    p.col1 = (x == 0) ? g.W + 1 : ((x == g.W - 1) ? 0 : -1);
+  }
+  return p;
+}
+
+// store 8 channels (one plane) of one pixel, hi and lo parts, into all of its slots
+__device__ __forceinline__ void store_plane(__half* act, const TcGeom& g, int plane, int64_t sample_slot0,
+                                            const PixSlots& ps, const float (&t)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half h0 = __float2half_rn(t[2 * j]), h1 = __float2half_rn(t[2 * j + 1]);
+    const __half l0 = __float2half_rn(t[2 * j] - __half2float(h0)), l1 = __float2half_rn(t[2 * j + 1] - __half2float(h1));
+    hi[j] = pack_h2(h0, h1);
+    lo[j] = pack_h2(l0, l1);
+  }
+  const int ks = plane >> 1, p2 = plane & 1;
+  uint4* base_hi = reinterpret_cast<uint4*>(act) + ((int64_t)(ks * 4 + p2) * g.slots + sample_slot0);
+  uint4* base_lo = base_hi + 2 * g.slots;
+  const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int row = a ? ps.row1 : ps.row0;
+    if (row < 0) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int col = b ? ps.col1 : ps.col0;
+      if (col < 0) continue;
+      const int o = row * g.RP + col;
+      base_hi[o] = vh;
+      base_lo[o] = vl;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight preparation: w [cout][cin][3][3] float32 -> blob [kstep][tap][hi|lo][p2][Np][8] binary16
+// ---------------------------------------------------------------------------------------------
+struct TcPrepParams {
+  const float* params;
+  __half* wblob;
+  int C, Np, KS, nconv;
+  int64_t w_off[kTcMaxLayers];   // offset of the conv weight in `params`
+  int64_t blob_off[kTcMaxLayers];
+};
+
+__global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
+  const int L = blockIdx.y;
+  const float* w = p.params + p.w_off[L];
+  __half* out = p.wblob + p.blob_off[L];
+  const int Kp = p.KS * 16;
+  const int n = 9 * Kp * p.Np;  // one entry per (tap, c, o)
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int o = e % p.Np, c = (e / p.Np) % Kp, tap = e / (p.Np * Kp);
+    float v = 0.f;
+    if (o < p.C && c < p.C) v = kWScale * w[((int64_t)o * p.C + c) * 9 + tap];
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const int ks = c >> 4, p2 = (c >> 3) & 1, j = c & 7;
+    const int64_t base = ((((int64_t)ks * 9 + tap) * 2 + 0) * 2 + p2) * p.Np + o;
+    out[base * 8 + j] = h;
+    out[(base + 2 * p.Np) * 8 + j] = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// first layer (conv1 of block 0, cin = 1; conv_nets.py:84-86): CUDA cores, writes the operand raster of
+// conv2_0 = split(4 * gelu(conv1_0(s / sqrt 2) + b)) and optionally the raw pre-activation.
+// thread per (sample, pixel, plane)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __restrict__ spins, const float* __restrict__ w,
+                                                             const float* __restrict__ b, TcGeom g, int C, int Np,
+                                                             __half* __restrict__ act, float* __restrict__ raw_out) {
+  const int N = g.H * g.W, planes = Np >> 3;
+  const int64_t total = g.ns * N * planes;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(e % N);
+    const int plane = (int)((e / N) % planes);
+    const int64_t s = e / ((int64_t)N * planes);
+    const int y = pix / g.W, x = pix % g.W;
+    float sv[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        int yy = y + dy - 1, xx = x + dx - 1;
+        yy += (yy < 0) ? g.H : 0; yy -= (yy >= g.H) ? g.H : 0;
+        xx += (xx < 0) ? g.W : 0; xx -= (xx >= g.W) ? g.W : 0;
+        sv[dy * 3 + dx] = 0.70710678118654752f * (float)spins[s * N + yy * g.W + xx];
+      }
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = plane * 8 + j;
+      float v = 0.f;
+      if (c < C) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) v += w[c * 9 + tap] * sv[tap];
+        v += b[c];
+        if (raw_out) raw_out[(s * C + c) * N + pix] = v;
+        v = kActScale * gelu_fast(v);
+      }
+      t[j] = v;
+    }
+    store_plane(act, g, plane, s * g.Ps, pixel_slots(g, y, x), t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the persistent tensor-core kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_constant__ TcNetParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const TcGeom& g = p.g;
+  const uint32_t run_bytes = (uint32_t)g.TS * 16u;           // one (hi|lo, p2) plane of the activation tile
+  const uint32_t act_stage_bytes = 4u * run_bytes;
+  const uint32_t w_tap_bytes = 4u * (uint32_t)p.Np * 16u;    // [hi|lo][p2][Np][16 B]
+  const uint32_t w_stage_bytes = 3u * w_tap_bytes;           // one kernel row (3 taps)
+  unsigned char* act_s = smem;
+  unsigned char* w_s = act_s + (size_t)p.act_stages * act_stage_bytes;
+  uint64_t* act_full = reinterpret_cast<uint64_t*>(w_s + (size_t)p.w_stages * w_stage_bytes);
+  uint64_t* act_empty = act_full + p.act_stages;
+  uint64_t* w_full = act_empty + p.act_stages;
+  uint64_t* w_empty = w_full + p.w_stages;
+  uint64_t* tmem_full = w_empty + p.w_stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint64_t* act_ready = tmem_empty + 2;         // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(act_ready + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.act_stages; ++i) { mbar_init(act_full + i, 1); mbar_init(act_empty + i, 1); }
+    for (int i = 0; i < p.w_stages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 8); mbar_init(act_ready + i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t col_stride = (uint32_t)((p.Np + 31) & ~31);  // accumulator column pitch
+
+  const int64_t nitems = g.nitems;
+  const int64_t nrounds = (nitems + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
+  const int nl = p.layer1 - p.layer0;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      uint32_t as = 0, pa = 0, ws = 0, pw = 0;
+      uint32_t cnt[2] = {0, 0};
+      for (int64_t r = 0; r < nrounds; ++r)
+        for (int li = 0; li < nl; ++li)
+          for (int j = 0; j < 2; ++j) {
+            const int64_t item = (2 * r + j) * gridDim.x + blockIdx.x;
+            if (item >= nitems) continue;
+            if (cnt[j] > 0) mbar_wait(act_ready + j, (cnt[j] - 1) & 1);  // the previous layer of this item is stored
+            ++cnt[j];
+            const TcLayer& L = p.layer[p.layer0 + li];
+            const int64_t slot0 = item * g.spi * g.Ps;
+            for (int ks = 0; ks < p.KS; ++ks) {
+              mbar_wait(act_empty + as, pa ^ 1);
+              mbar_expect_tx(act_full + as, act_stage_bytes);
+              unsigned char* dst = act_s + (size_t)as * act_stage_bytes;
+#pragma unroll
+              for (int run = 0; run < 4; ++run)
+                bulk_g2s(dst + (size_t)run * run_bytes, p.act + (((int64_t)ks * 4 + run) * g.slots + slot0) * 8, run_bytes,
+                         act_full + as);
+              if (++as == (uint32_t)p.act_stages) { as = 0; pa ^= 1; }
+              for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(w_empty + ws, pw ^ 1);
+                mbar_expect_tx(w_full + ws, w_stage_bytes);
+                bulk_g2s(w_s + (size_t)ws * w_stage_bytes,
+                         p.wblob + L.wblob_off + ((int64_t)ks * 9 + dy * 3) * (w_tap_bytes / 2), w_stage_bytes, w_full + ws);
+                if (++ws == (uint32_t)p.w_stages) { ws = 0; pw ^= 1; }
+              }
+            }
+          }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // D=F32, A=B=F16, K-major
+      const uint32_t a_lbo = run_bytes, a_sbo = (uint32_t)g.SB * 16u;
+      const uint32_t b_lbo = (uint32_t)p.Np * 16u, b_sbo = 128u;
+      const uint32_t act_base = smem_u32(act_s), w_base = smem_u32(w_s);
+      // per-tile slot offset inside the staged activation tile
+      uint32_t tile_off[2];
+      for (int t = 0; t < 2; ++t) {
+        const int sl = (g.tps == 1) ? t : 0, tis = (g.tps == 1) ? 0 : t;
+        tile_off[t] = (uint32_t)(sl * g.Ps + tis * 16 * g.SB) * 16u;
+      }
+      uint32_t as = 0, pa = 0, ws = 0, pw = 0, q = 0;
+      for (int64_t r = 0; r < nrounds; ++r)
+        for (int li = 0; li < nl; ++li)
+          for (int j = 0; j < 2; ++j) {
+            const int64_t item = (2 * r + j) * gridDim.x + blockIdx.x;
+            if (item >= nitems) continue;
+            const uint32_t buf = q & 1, use = q >> 1;
+            ++q;
+            mbar_wait(tmem_empty + buf, (use & 1) ^ 1);
+            tc_fence_after();
+            for (int ks = 0; ks < p.KS; ++ks) {
+              mbar_wait(act_full + as, pa);
+              const uint32_t a_stage = act_base + as * act_stage_bytes;
+              for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(w_full + ws, pw);
+                tc_fence_after();
+                const uint32_t w_stage = w_base + ws * w_stage_bytes;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  const uint32_t wt = w_stage + (uint32_t)dx * w_tap_bytes;
+                  const uint64_t db_hi = make_desc_nosw(wt, b_lbo, b_sbo);
+                  const uint64_t db_lo = make_desc_nosw(wt + 2u * b_lbo, b_lbo, b_sbo);
+                  const uint32_t shift = (uint32_t)(dy * g.RP + dx) * 16u;
+#pragma unroll
+                  for (int t = 0; t < 2; ++t) {
+                    const uint32_t a0 = a_stage + tile_off[t] + shift;
+                    const uint64_t da_hi = make_desc_nosw(a0, a_lbo, a_sbo);
+                    const uint64_t da_lo = make_desc_nosw(a0 + 2u * run_bytes, a_lbo, a_sbo);
+                    const uint32_t d = tmem_base + (buf * 2 + t) * col_stride;
+                    const uint32_t first = (ks == 0 && dy == 0 && dx == 0) ? 0u : 1u;
+                    umma_f16(d, da_hi, db_hi, idesc, first);
+                    umma_f16(d, da_lo, db_hi, idesc, 1u);
+                    umma_f16(d, da_hi, db_lo, idesc, 1u);
+                  }
+                }
+                umma_commit(w_empty + ws);
+                if (++ws == (uint32_t)p.w_stages) { ws = 0; pw ^= 1; }
+              }
+              umma_commit(act_empty + as);
+              if (++as == (uint32_t)p.act_stages) { as = 0; pa ^= 1; }
+            }
+            umma_commit(tmem_full + buf);
+          }
+    }
+  } else {
+    // ===== epilogue: warp (2..9) -> TMEM lane quarter warp % 4, plane parity (warp - 2) / 4 =====
+    const int lq = warp & 3, cg = (warp - 2) >> 2;
+    const int N = g.H * g.W, planes = p.Np >> 3;
+    uint32_t q = 0;
+    for (int64_t r = 0; r < nrounds; ++r)
+      for (int li = 0; li < nl; ++li)
+        for (int j = 0; j < 2; ++j) {
+          const int64_t item = (2 * r + j) * gridDim.x + blockIdx.x;
+          if (item >= nitems) continue;
+          const TcLayer& L = p.layer[p.layer0 + li];
+          const uint32_t buf = q & 1, use = q >> 1;
+          ++q;
+          mbar_wait(tmem_full + buf, use & 1);
+          tc_fence_after();
+          for (int t = 0; t < 2; ++t) {
+            // M row of this thread -> (sample, y, x)
+            const int m = lq * 32 + lane;
+            const int sl = (g.tps == 1) ? t : 0, tis = (g.tps == 1) ? 0 : t;
+            const int64_t s = item * g.spi + sl;
+            const int slot = g.RP + 1 + tis * 16 * g.SB + (m >> 3) * g.SB + (m & 7);  // within the sample raster
+            const int row = slot / g.RP, col = slot - row * g.RP;
+            const int y = row - 1;
+            int x;
+            bool okx;
+            if (g.mode) {
+              const int seg = col / 10, c10 = col - seg * 10;
+              x = seg * 8 + c10 - 1;
+              okx = c10 >= 1 && c10 <= 8;
+            } else {
+              x = col - 1;
+              okx = x >= 0 && x < g.W;
+            }
+            const bool valid = s < g.ns && y >= 0 && y < g.H && okx;
+            const int pix = valid ? y * g.W + x : 0;
+            const PixSlots ps = pixel_slots(g, valid ? y : 1, valid ? x : 1);
+            float resv = 0.f;
+            if (valid && L.res_spin) resv = (float)L.res_spin[s * N + pix];
+            const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16) + (buf * 2 + t) * col_stride;
+            for (int plane = cg; plane < planes; plane += 2) {
+              float v[8];
+              tmem_ld8(trow + plane * 8, v);
+              if (valid) {
+                float tt[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const int c = plane * 8 + jj;
+                  float val = 0.f;
+                  if (c < p.C) {
+                    val = v[jj] * kOutScale;
+                    if (L.bias) val += __ldg(L.bias + c);
+                    const int64_t oi = (s * p.C + c) * N + pix;
+                    if (L.res) val += L.res[oi];
+                    val += resv;
+                    if (L.raw_out) L.raw_out[oi] = val;
+                    val = kActScale * gelu_fast(L.out_alpha * val);
+                  }
+                  tt[jj] = val;
+                }
+                if (L.write_act) store_plane(p.act, g, plane, s * g.Ps, ps, tt);
+              }
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async_global();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(tmem_empty + buf);
+            mbar_arrive(act_ready + j);
+          }
+        }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool tc_geometry(int H, int W, int64_t ns, TcGeom& g) {
+  if (H < 2 || W < 2) return false;
+  g.H = H; g.W = W; g.ns = ns;
+  g.nseg = W / 8;
+  const bool seg_ok = (W % 8 == 0) && ((H * g.nseg) % 16 == 0) && (H * g.nseg / 16 <= 2);
+  if (seg_ok) {
+    g.mode = 1; g.RP = g.nseg * 10; g.SB = 10; g.tps = H * g.nseg / 16;
+  } else {
+    g.mode = 0; g.nseg = 0; g.RP = W + 2; g.SB = 8;
+    const int span = (H - 1) * g.RP + W;
+    g.tps = (span + 127) / 128;
+    if (g.tps > 2) return false;
+  }
+  g.Ps = (H + 2) * g.RP;
+  g.spi = 2 / g.tps;
+  int ts = 0;
+  for (int t = 0; t < 2; ++t) {
+    const int sl = (g.tps == 1) ? t : 0, tis = (g.tps == 1) ? 0 : t;
+    const int need = sl * g.Ps + tis * 16 * g.SB + 15 * g.SB + 7 + 2 * g.RP + 2 + 1;
+    if (need > ts) ts = need;
+  }
+  if (ts < g.spi * g.Ps) ts = g.spi * g.Ps;
+  g.TS = (ts + 1) & ~1;
+  g.nitems = (ns + g.spi - 1) / g.spi;
+  g.slots = g.nitems * g.spi * (int64_t)g.Ps + (g.TS - g.spi * g.Ps) + 16;
+  return true;
+}
+
+static bool tc_disabled() {
+  const char* e = getenv("QTX_RESCONV_TC");
+  return e && e[0] == '0';
+}
+
+bool resconv_tc_supported(int C, int lx, int ly, int kh, int kw) {
+  if (tc_disabled()) return false;
+  if (kh != 3 || kw != 3 || C < 1 || C > 128) return false;
+  TcGeom g;
+  return tc_geometry(lx, ly, 1, g);
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void tc_sizes(int nblocks, int C, int lx, int ly, int64_t ns, TcGeom& g, int& Np, int& KS, size_t& blob_halfs,
+                     size_t& act_bytes, size_t& wblob_bytes) {
+  tc_geometry(lx, ly, ns, g);
+  Np = (C + 15) & ~15;
+  KS = Np / 16;
+  blob_halfs = (size_t)KS * 9 * 4 * Np * 8;
+  wblob_bytes = align256((size_t)(2 * nblocks - 1) * blob_halfs * 2);
+  act_bytes = align256((size_t)KS * 4 * g.slots * 16);
+}
+
+size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly) {
+  TcGeom g;
+  int Np, KS;
+  size_t bh, ab, wb;
+  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, bh, ab, wb);
+  return ab + wb + 512;
+}
+
+// Forward through the tower.  X / Hs: raw float32 [.., ns, C, N] buffers of the caller.
+//   save_all == 0: X is ONE buffer holding the running residual stream (x_nblocks on return), Hs unused
+//   save_all == 1: X[i] = X + i*act holds x_{i+1}, Hs[i] = Hs + i*act holds the conv1 pre-activation of block i
+int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
+                       float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TcGeom g;
+  int Np, KS;
+  size_t blob_halfs, act_bytes, wblob_bytes;
+  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, blob_halfs, act_bytes, wblob_bytes);
+  QTX_REQUIRE(ws_bytes >= act_bytes + wblob_bytes + 256, QTX_ERR_INVALID, "resconv_tc: workspace too small");
+  QTX_REQUIRE(2 * nblocks - 1 <= kTcMaxLayers, QTX_ERR_UNSUPPORTED, "resconv_tc: too many blocks");
+  unsigned char* base = (unsigned char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  __half* act = reinterpret_cast<__half*>(base);
+  __half* wblob = reinterpret_cast<__half*>(base + act_bytes);
+  const int N = lx * ly;
+  const int64_t actsz = ns * C * N;
+
+  // parameter offsets (ravel_pytree order, see resconv.cu)
+  int64_t off = 0;
+  int64_t w1[64], b1[64], w2[64], b2[64];
+  for (int i = 0; i < nblocks; ++i) {
+    w1[i] = off; off += (int64_t)C * (i == 0 ? 1 : C) * 9;
+    b1[i] = off; off += C;
+    w2[i] = off; off += (int64_t)C * C * 9;
+    if (i == nblocks - 1) b2[i] = -1;
+    else { b2[i] = off; off += C; }
+  }
+
+  // tensor-core layers: conv2_0, then (conv1_i, conv2_i) for i >= 1
+  TcPrepParams pp{};
+  pp.params = params; pp.wblob = wblob; pp.C = C; pp.Np = Np; pp.KS = KS;
+  TcNetParams np{};
+  np.act = act; np.wblob = wblob; np.g = g; np.C = C; np.Np = Np; np.KS = KS;
+  int nl = 0;
+  for (int i = 0; i < nblocks; ++i) {
+    if (i > 0) {
+      TcLayer& L = np.layer[nl];
+      pp.w_off[nl] = w1[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
+      L.wblob_off = pp.blob_off[nl];
+      L.bias = params + b1[i]; L.res = nullptr; L.res_spin = nullptr;
+      L.raw_out = save_all ? Hs + (int64_t)i * actsz : nullptr;
+      L.out_alpha = 1.0f; L.write_act = 1;
+      ++nl;
+    }
+    TcLayer& L = np.layer[nl];
+    pp.w_off[nl] = w2[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
+    L.wblob_off = pp.blob_off[nl];
+    L.bias = b2[i] >= 0 ? params + b2[i] : nullptr;
+    L.res = (i == 0) ? nullptr : (save_all ? X + (int64_t)(i - 1) * actsz : X);
+    L.res_spin = (i == 0) ? spins : nullptr;
+    L.raw_out = save_all ? X + (int64_t)i * actsz : X;
+    L.out_alpha = (float)(1.0 / sqrt((double)(i + 2)));
+    L.write_act = (i < nblocks - 1) ? 1 : 0;
+    ++nl;
+  }
+  pp.nconv = nl;
+  {
+    const int n = 9 * KS * 16 * Np;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nl);
+    tc_weight_prep_kernel<<<grid, 256, 0, st>>>(pp);
+    QTX_LAUNCH_CHECK();
+  }
+  {
+    const int64_t total = ns * N * (Np >> 3);
+    unsigned gsz = (unsigned)((total + 255) / 256);
+    if (gsz > 16u * num_sms()) gsz = 16u * num_sms();
+    tc_first_layer_kernel<<<gsz, 256, 0, st>>>(spins, params + w1[0], params + b1[0], g, C, Np, act,
+                                                save_all ? Hs : nullptr);
+    QTX_LAUNCH_CHECK();
+  }
+  // shared memory: activation ring + weight ring + barriers
+  const size_t act_stage = (size_t)4 * g.TS * 16, w_stage = (size_t)3 * 4 * Np * 16;
+  int act_stages = 3, w_stages = 6;
+  const size_t cap = 227 * 1024 - 1024;
+  while (act_stages > 2 && act_stages * act_stage + w_stages * w_stage > cap) --act_stages;
+  while (w_stages > 2 && act_stages * act_stage + w_stages * w_stage > cap) --w_stages;
+  QTX_REQUIRE(act_stages * act_stage + w_stages * w_stage <= cap, QTX_ERR_UNSUPPORTED, "resconv_tc: tile does not fit");
+  if (const char* e = getenv("QTX_TC_WSTAGES")) { int v = atoi(e); if (v >= 2 && act_stages * act_stage + v * w_stage <= cap) w_stages = v; }
+  np.act_stages = act_stages; np.w_stages = w_stages;
+  const size_t smem = act_stages * act_stage + w_stages * w_stage + (2 * act_stages + 2 * w_stages + 6) * 8 + 16 + 128;
+  QTX_CUDA(cudaFuncSetAttribute(resconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = num_sms();
+  if ((int64_t)grid > g.nitems) grid = (int)g.nitems;
+  int per_launch = nl;
+  if (const char* e = getenv("QTX_TC_LAYERS_PER_LAUNCH")) { int v = atoi(e); if (v >= 1) per_launch = v; }
+  for (int l0 = 0; l0 < nl; l0 += per_launch) {
+    np.layer0 = l0;
+    np.layer1 = l0 + per_launch < nl ? l0 + per_launch : nl;
+    resconv_tc_kernel<<<grid, kTcThreads, smem, st>>>(np);
+    QTX_LAUNCH_CHECK();
+  }
+  return QTX_OK;
+}
+
+}  // namespace qtx
