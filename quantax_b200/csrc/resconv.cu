@@ -22,7 +22,8 @@ namespace qtx {
 bool resconv_tc_supported(int C, int lx, int ly, int kh, int kw);
 size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly);
 int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
-                       float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, cudaStream_t st);
+                       float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, const float** x_final,
+                       int* x_final_planes, cudaStream_t st);
 
 constexpr int kConvThreads = 256;
 constexpr int kOT = 32;   // out-channel tile per CTA
@@ -415,15 +416,22 @@ __global__ void weight_transpose_flip_kernel(const T* __restrict__ w, int cout, 
 template <typename T>
 __global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict__ x, int64_t ns, int C, int N,
                                                             T inv_norm, int final_act, double* __restrict__ sig_out,
-                                                            double* __restrict__ exp_out, T* __restrict__ dz) {
+                                                            double* __restrict__ exp_out, T* __restrict__ dz, int planes) {
   __shared__ T red[32];
   __shared__ T bc;
   const int64_t s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const T* xs = x + s * C * N;
   const int CN = C * N;
+  // planes > 0: x is the planar residual stream [ns, planes, N, 8] of the tensor-core forward (resconv_tc.cu)
+  const T* xs = x + s * (planes > 0 ? (int64_t)planes * N * 8 : (int64_t)CN);
+  auto at = [&](int c, int r) -> T { return planes > 0 ? xs[((c >> 3) * N + r) * 8 + (c & 7)] : xs[c * N + r]; };
   T m = 0;
-  for (int e = tid; e < CN; e += blockDim.x) m = fmax(m, fabs(xs[e] * inv_norm));
+  if (planes > 0) {
+    for (int e = tid; e < planes * N * 8; e += blockDim.x)
+      if (((e / (N * 8)) * 8 + (e & 7)) < C) m = fmax(m, fabs(xs[e] * inv_norm));
+  } else {
+    for (int e = tid; e < CN; e += blockDim.x) m = fmax(m, fabs(xs[e] * inv_norm));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
   if (lane == 0) red[warp] = m;
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict_
   for (int r = tid; r < N; r += blockDim.x) {
     T a = 0;
     for (int c = 0; c < C; ++c) {
-      T z = xs[c * N + r] * inv_norm;
+      T z = at(c, r) * inv_norm;
       T sg = exp(z - m);
       if (final_act == 1) sg = (sg - exp(-z - m)) / T(2) + em;
       a += sg;
@@ -757,12 +765,15 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
   }
   // ---- forward (conv_nets.py:78-92) ----
   bool tc_done = false;
+  const T* tc_xfinal = nullptr;
+  int tc_planes = 0;
   if constexpr (std::is_same<T, float>::value) {
     if (resconv_tc_supported(C, sh.lx, sh.ly, sh.kh, sh.kw)) {
       // tensor-core tower (resconv_tc.cu); its workspace follows the regular one
       const size_t base_bytes = resconv_ws_base(QTX_F32, ns, sh, grad);
       int rc = resconv_tc_forward(nb, C, sh.lx, sh.ly, params, spins, ns, X, Hs, grad ? 1 : 0,
-                                  (unsigned char*)ws + base_bytes, resconv_tc_workspace(ns, nb, C, sh.lx, sh.ly), st);
+                                  (unsigned char*)ws + base_bytes, resconv_tc_workspace(ns, nb, C, sh.lx, sh.ly),
+                                  &tc_xfinal, &tc_planes, st);
       if (rc) return rc;
       tc_done = true;
     }
@@ -791,12 +802,12 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
     rc = launch_conv<T>(q, st);
     if (rc) return rc;
   }
-  const T* xlast = grad ? X + (int64_t)(nb - 1) * act : X;
+  const T* xlast = tc_done ? tc_xfinal : (grad ? X + (int64_t)(nb - 1) * act : X);
   T* dA = grad ? scratch : nullptr;           // gradient w.r.t. the current block output
   T* dB = grad ? scratch + act : nullptr;
   T* wT = grad ? scratch + 2 * act : nullptr;
   resconv_final_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
-                                                        sh.final_act, sig_out, exp_out, dA);
+                                                        sh.final_act, sig_out, exp_out, dA, tc_planes);
   QTX_LAUNCH_CHECK();
   if (!grad) return QTX_OK;
 

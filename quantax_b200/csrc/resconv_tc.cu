@@ -22,15 +22,21 @@
 //   RASTER (any W):       plain (W+2)-pitch raster, M rows = consecutive slots from the first to the
 //          last interior pixel, halo columns compute garbage rows that the epilogue masks.
 //
+// Tensor-core accumulation truncates (round toward zero) at every accumulate, a systematic bias of
+// ~0.5 ulp per step; the hi*hi products go to one TMEM accumulator (54 steps at C = 88) and the two
+// small cross products to a second one, whose truncation is 2^-11 times smaller; the epilogue adds
+// the two in round-to-nearest float32.
+//
 // One persistent kernel runs ALL tensor-core layers of the tower: a CTA owns its samples through the
-// whole depth (a layer's output of a sample depends only on that sample), keeps two work items in
-// flight (TMEM double buffer: the epilogue of one overlaps the MMAs of the other) and updates the
-// operand buffer in place, so activations stay L2-resident and only weights stream.
-//   warp 0    bulk-copy producer (cp.async.bulk, mbarrier complete_tx): activation k-step tiles and
-//             weight (k-step, kernel-row) tiles, two rings
-//   warp 1    MMA issuer (one thread), TMEM owner
-//   warps 2-9 epilogue: TMEM -> registers, bias / residual, raw float32 output (next residual, and the
-//             saved activations of the backward pass), gelu, split, operand store with halo copies
+// whole depth (a layer's output of a sample depends only on that sample), alternates between two
+// work items (the epilogue of one overlaps the MMAs of the other: the accumulators are drained into
+// registers first and TMEM is released at once) and updates the operand buffer in place, so
+// activations stay L2-resident and only weights stream.
+//   warp 0     bulk-copy producer (cp.async.bulk, mbarrier complete_tx): activation k-step tiles and
+//              weight (k-step, kernel-row) tiles, two rings
+//   warp 1     MMA issuer (one thread), TMEM owner
+//   warps 2-13 epilogue: TMEM -> registers, bias / residual, raw float32 output (next residual, and
+//              the saved activations of the backward pass), gelu, split, operand store with halo copies
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -38,7 +44,9 @@
 
 namespace qtx {
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 448;
+constexpr int kEpiWarps = 12;
+constexpr int kColGroups = kEpiWarps / 4;
 constexpr int kTcMaxLayers = 32;
 constexpr float kActScale = 4.0f;
 constexpr float kWScale = 256.0f;
@@ -56,11 +64,12 @@ struct TcGeom {
 struct TcLayer {
   int64_t wblob_off;       // in halfs
   const float* bias;       // [C] or null
-  const float* res;        // raw residual [ns, C, N] or null
+  const float* res;        // raw residual or null
   const int8_t* res_spin;  // block 0 residual: the spins, broadcast over channels, or null
-  float* raw_out;          // [ns, C, N] or null
+  float* raw_out;          // raw output or null
   float out_alpha;         // operand out = split(kActScale * gelu(out_alpha * v))
   int write_act;
+  int planar;              // raw layout: 0 = [ns, C, N], 1 = [ns, Np/8, N, 8] (forward-only residual stream)
 };
 
 struct TcNetParams {
@@ -90,14 +99,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
+// no wait: the caller issues tcgen05.wait::ld once after a batch of loads
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
@@ -112,31 +118,60 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-__device__ __forceinline__ float gelu_fast(float x) {
-  // x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)  ==  0.5 x (1 + tanh u)
-  const float u2 = -1.5957691216057308f * (x + 0.044715f * x * x * x);
-  return __fdividef(x, 1.0f + __expf(u2));
+// kActScale * gelu(alpha * v) with the constants folded:
+//   gelu(x) = x * sigmoid(2 sqrt(2/pi) (x + 0.044715 x^3)) = x / (1 + 2^(x (a + b x^2)))
+struct GeluConst {
+  float a, b, c;  // exponent polynomial in v, output factor
+};
+__host__ __device__ inline GeluConst gelu_const(float alpha) {
+  GeluConst k;
+  const float l2e = 1.4426950408889634f, s = -1.5957691216057308f;
+  k.a = s * l2e * alpha;
+  k.b = s * l2e * 0.044715f * alpha * alpha * alpha;
+  k.c = kActScale * alpha;
+  return k;
+}
+__device__ __forceinline__ float gelu_scaled(float v, const GeluConst& k) {
+  const float t = v * fmaf(v * v, k.b, k.a);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return (k.c * v) * r;
 }
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+// x = hi + lo in binary16, two values at a time
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// the operand slots that hold pixel (y, x) of a sample: interior slot + halo copies
+// the operand slots (relative to the sample's raster) that hold pixel (y, x): interior + halo copies
 struct PixSlots {
-  int row0, row1, col0, col1;  // row1 / col1 = -1 when there is no copy
+  int n;
+  int o[4];
 };
 __device__ __forceinline__ PixSlots pixel_slots(const TcGeom& g, int y, int x) {
-  PixSlots p;
-  p.row0 = y + 1;
-  p.row1 = (y == 0) ? g.H + 1 : ((y == g.H - 1) ? 0 : -1);
+  int row1 = (y == 0) ? g.H + 1 : ((y == g.H - 1) ? 0 : -1);
+  int col0, col1;
   if (g.mode) {
     const int seg = x >> 3, sl = (x & 7) + 1;
-    p.col0 = seg * 10 + sl;
-    p.col1 = (sl == 1) ? ((seg + g.nseg - 1) % g.nseg) * 10 + 9 : ((sl == 8) ? ((seg + 1) % g.nseg) * 10 : -1);
+    col0 = seg * 10 + sl;
+    col1 = (sl == 1) ? ((seg + g.nseg - 1) % g.nseg) * 10 + 9 : ((sl == 8) ? ((seg + 1) % g.nseg) * 10 : -1);
   } else {
-    p.col0 = x + 1;
-    p.col1 = (x == 0) ? g.W + 1 : ((x == g.W - 1) ? 0 : -1);
+    col0 = x + 1;
+    col1 = (x == 0) ? g.W + 1 : ((x == g.W - 1) ? 0 : -1);
+  }
+  PixSlots p;
+  p.n = 1;
+  p.o[0] = (y + 1) * g.RP + col0;
+  p.o[1] = p.o[2] = p.o[3] = 0;
+  if (col1 >= 0) p.o[p.n++] = (y + 1) * g.RP + col1;
+  if (row1 >= 0) {
+    p.o[p.n++] = row1 * g.RP + col0;
+    if (col1 >= 0) p.o[p.n++] = row1 * g.RP + col1;
   }
   return p;
 }
@@ -144,29 +179,18 @@ __device__ __forceinline__ PixSlots pixel_slots(const TcGeom& g, int y, int x) {
 // store 8 channels (one plane) of one pixel, hi and lo parts, into all of its slots
 __device__ __forceinline__ void store_plane(__half* act, const TcGeom& g, int plane, int64_t sample_slot0,
                                             const PixSlots& ps, const float (&t)[8]) {
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const __half h0 = __float2half_rn(t[2 * j]), h1 = __float2half_rn(t[2 * j + 1]);
-    const __half l0 = __float2half_rn(t[2 * j] - __half2float(h0)), l1 = __float2half_rn(t[2 * j + 1] - __half2float(h1));
-    hi[j] = pack_h2(h0, h1);
-    lo[j] = pack_h2(l0, l1);
-  }
-  const int ks = plane >> 1, p2 = plane & 1;
-  uint4* base_hi = reinterpret_cast<uint4*>(act) + ((int64_t)(ks * 4 + p2) * g.slots + sample_slot0);
+  uint4 vh, vl;
+  split2(t[0], t[1], vh.x, vl.x);
+  split2(t[2], t[3], vh.y, vl.y);
+  split2(t[4], t[5], vh.z, vl.z);
+  split2(t[6], t[7], vh.w, vl.w);
+  uint4* base_hi = reinterpret_cast<uint4*>(act) + ((int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots + sample_slot0);
   uint4* base_lo = base_hi + 2 * g.slots;
-  const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    const int row = a ? ps.row1 : ps.row0;
-    if (row < 0) continue;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int col = b ? ps.col1 : ps.col0;
-      if (col < 0) continue;
-      const int o = row * g.RP + col;
-      base_hi[o] = vh;
-      base_lo[o] = vl;
+  for (int a = 0; a < 4; ++a) {
+    if (a < ps.n) {
+      base_hi[ps.o[a]] = vh;
+      base_lo[ps.o[a]] = vl;
     }
   }
 }
@@ -211,6 +235,7 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
                                                              __half* __restrict__ act, float* __restrict__ raw_out) {
   const int N = g.H * g.W, planes = Np >> 3;
   const int64_t total = g.ns * N * planes;
+  const GeluConst gk = gelu_const(1.0f);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int pix = (int)(e % N);
     const int plane = (int)((e / N) % planes);
@@ -236,7 +261,7 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
         for (int tap = 0; tap < 9; ++tap) v += w[c * 9 + tap] * sv[tap];
         v += b[c];
         if (raw_out) raw_out[(s * C + c) * N + pix] = v;
-        v = kActScale * gelu_fast(v);
+        v = gelu_scaled(v, gk);
       }
       t[j] = v;
     }
@@ -247,6 +272,8 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
 // ---------------------------------------------------------------------------------------------
 // the persistent tensor-core kernel
 // ---------------------------------------------------------------------------------------------
+// PL = planes (8-channel groups) per epilogue thread: Np <= 24 * PL
+template <int PL>
 __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_constant__ TcNetParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -261,16 +288,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
   uint64_t* act_empty = act_full + p.act_stages;
   uint64_t* w_full = act_empty + p.act_stages;
   uint64_t* w_empty = w_full + p.w_stages;
-  uint64_t* tmem_full = w_empty + p.w_stages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint64_t* act_ready = tmem_empty + 2;         // [2]
+  uint64_t* tmem_full = w_empty + p.w_stages;   // [1]
+  uint64_t* tmem_empty = tmem_full + 1;         // [1]
+  uint64_t* act_ready = tmem_empty + 1;         // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(act_ready + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.act_stages; ++i) { mbar_init(act_full + i, 1); mbar_init(act_empty + i, 1); }
     for (int i = 0; i < p.w_stages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 8); mbar_init(act_ready + i, 8); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kEpiWarps);
+    mbar_init(act_ready + 0, kEpiWarps);
+    mbar_init(act_ready + 1, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
@@ -278,7 +308,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const uint32_t col_stride = (uint32_t)((p.Np + 31) & ~31);  // accumulator column pitch
+  // accumulator columns: tile t -> main at (2t) * col_stride, cross terms at (2t + 1) * col_stride
+  const uint32_t col_stride = (uint32_t)((p.Np + 31) & ~31);
 
   const int64_t nitems = g.nitems;
   const int64_t nrounds = (nitems + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
@@ -296,7 +327,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
             if (item >= nitems) continue;
             if (cnt[j] > 0) mbar_wait(act_ready + j, (cnt[j] - 1) & 1);  // the previous layer of this item is stored
             ++cnt[j];
-            const TcLayer& L = p.layer[p.layer0 + li];
+            const int64_t wblob_off = p.layer[p.layer0 + li].wblob_off;
             const int64_t slot0 = item * g.spi * g.Ps;
             for (int ks = 0; ks < p.KS; ++ks) {
               mbar_wait(act_empty + as, pa ^ 1);
@@ -311,7 +342,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
                 mbar_wait(w_empty + ws, pw ^ 1);
                 mbar_expect_tx(w_full + ws, w_stage_bytes);
                 bulk_g2s(w_s + (size_t)ws * w_stage_bytes,
-                         p.wblob + L.wblob_off + ((int64_t)ks * 9 + dy * 3) * (w_tap_bytes / 2), w_stage_bytes, w_full + ws);
+                         p.wblob + wblob_off + ((int64_t)ks * 9 + dy * 3) * (w_tap_bytes / 2), w_stage_bytes, w_full + ws);
                 if (++ws == (uint32_t)p.w_stages) { ws = 0; pw ^= 1; }
               }
             }
@@ -336,9 +367,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
           for (int j = 0; j < 2; ++j) {
             const int64_t item = (2 * r + j) * gridDim.x + blockIdx.x;
             if (item >= nitems) continue;
-            const uint32_t buf = q & 1, use = q >> 1;
+            mbar_wait(tmem_empty, (q & 1) ^ 1);  // the epilogue has drained the previous item's accumulators
             ++q;
-            mbar_wait(tmem_empty + buf, (use & 1) ^ 1);
             tc_fence_after();
             for (int ks = 0; ks < p.KS; ++ks) {
               mbar_wait(act_full + as, pa);
@@ -353,16 +383,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
                   const uint64_t db_hi = make_desc_nosw(wt, b_lbo, b_sbo);
                   const uint64_t db_lo = make_desc_nosw(wt + 2u * b_lbo, b_lbo, b_sbo);
                   const uint32_t shift = (uint32_t)(dy * g.RP + dx) * 16u;
+                  const uint32_t acc = (ks == 0 && dy == 0 && dx == 0) ? 0u : 1u;
 #pragma unroll
                   for (int t = 0; t < 2; ++t) {
                     const uint32_t a0 = a_stage + tile_off[t] + shift;
                     const uint64_t da_hi = make_desc_nosw(a0, a_lbo, a_sbo);
                     const uint64_t da_lo = make_desc_nosw(a0 + 2u * run_bytes, a_lbo, a_sbo);
-                    const uint32_t d = tmem_base + (buf * 2 + t) * col_stride;
-                    const uint32_t first = (ks == 0 && dy == 0 && dx == 0) ? 0u : 1u;
-                    umma_f16(d, da_hi, db_hi, idesc, first);
-                    umma_f16(d, da_lo, db_hi, idesc, 1u);
-                    umma_f16(d, da_hi, db_lo, idesc, 1u);
+                    const uint32_t d_main = tmem_base + (uint32_t)(2 * t) * col_stride;
+                    const uint32_t d_cross = d_main + col_stride;
+                    umma_f16(d_main, da_hi, db_hi, idesc, acc);
+                    umma_f16(d_cross, da_lo, db_hi, idesc, acc);
+                    umma_f16(d_cross, da_hi, db_lo, idesc, 1u);
                   }
                 }
                 umma_commit(w_empty + ws);
@@ -371,13 +402,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
               umma_commit(act_empty + as);
               if (++as == (uint32_t)p.act_stages) { as = 0; pa ^= 1; }
             }
-            umma_commit(tmem_full + buf);
+            umma_commit(tmem_full);
           }
     }
   } else {
-    // ===== epilogue: warp (2..9) -> TMEM lane quarter warp % 4, plane parity (warp - 2) / 4 =====
-    const int lq = warp & 3, cg = (warp - 2) >> 2;
+    // ===== epilogue: warp -> TMEM lane quarter (warp % 4), column group (warp - 2) / 4 owns planes cgp, cgp + 3, ... =====
+    const int lq = warp & 3, cgp = (warp - 2) >> 2;
     const int N = g.H * g.W, planes = p.Np >> 3;
+    const int m = lq * 32 + lane;
     uint32_t q = 0;
     for (int64_t r = 0; r < nrounds; ++r)
       for (int li = 0; li < nl; ++li)
@@ -385,13 +417,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
           const int64_t item = (2 * r + j) * gridDim.x + blockIdx.x;
           if (item >= nitems) continue;
           const TcLayer& L = p.layer[p.layer0 + li];
-          const uint32_t buf = q & 1, use = q >> 1;
+          mbar_wait(tmem_full, q & 1);
           ++q;
-          mbar_wait(tmem_full + buf, use & 1);
           tc_fence_after();
+          // ---- drain: main + cross accumulators of both tiles into registers, then release TMEM ----
+          float acc[2][PL][8];
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int k = 0; k < PL; ++k) {
+              const int plane = cgp + kColGroups * k;
+              if (plane < planes) {
+                uint32_t rm[8], rc[8];
+                const uint32_t a = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(2 * t) * col_stride + plane * 8;
+                tmem_ld8_nowait(a, rm);
+                tmem_ld8_nowait(a + col_stride, rc);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[t][k][jj] = __uint_as_float(rm[jj]) + __uint_as_float(rc[jj]);
+              }
+            }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+          // ---- bias / residual / raw output / gelu / split / operand store ----
+          const GeluConst gk = gelu_const(L.out_alpha);
+#pragma unroll
           for (int t = 0; t < 2; ++t) {
-            // M row of this thread -> (sample, y, x)
-            const int m = lq * 32 + lane;
             const int sl = (g.tps == 1) ? t : 0, tis = (g.tps == 1) ? 0 : t;
             const int64_t s = item * g.spi + sl;
             const int slot = g.RP + 1 + tis * 16 * g.SB + (m >> 3) * g.SB + (m & 7);  // within the sample raster
@@ -408,42 +460,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
               okx = x >= 0 && x < g.W;
             }
             const bool valid = s < g.ns && y >= 0 && y < g.H && okx;
-            const int pix = valid ? y * g.W + x : 0;
-            const PixSlots ps = pixel_slots(g, valid ? y : 1, valid ? x : 1);
-            float resv = 0.f;
-            if (valid && L.res_spin) resv = (float)L.res_spin[s * N + pix];
-            const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16) + (buf * 2 + t) * col_stride;
-            for (int plane = cg; plane < planes; plane += 2) {
+            if (!valid) continue;
+            const int pix = y * g.W + x;
+            const PixSlots ps = pixel_slots(g, y, x);
+            const float resv = L.res_spin ? (float)L.res_spin[s * N + pix] : 0.f;
+#pragma unroll
+            for (int k = 0; k < PL; ++k) {
+              const int plane = cgp + kColGroups * k;
+              if (plane >= planes) continue;
               float v[8];
-              tmem_ld8(trow + plane * 8, v);
-              if (valid) {
+              const int c0 = plane * 8;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) v[jj] = acc[t][k][jj] * kOutScale + resv;
+              if (L.bias) {
+                if (c0 + 8 <= p.C) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(L.bias + c0));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(L.bias + c0) + 1);
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj)
+                    if (c0 + jj < p.C) v[jj] += __ldg(L.bias + c0 + jj);
+                }
+              }
+              if (L.planar) {
+                const int64_t oi = ((s * planes + plane) * N + pix) * 8;
+                if (L.res) {
+                  const float4 r0 = *reinterpret_cast<const float4*>(L.res + oi);
+                  const float4 r1 = *reinterpret_cast<const float4*>(L.res + oi + 4);
+                  v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                  v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                }
+                if (L.raw_out) {
+                  *reinterpret_cast<float4*>(L.raw_out + oi) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(L.raw_out + oi + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+              } else {
+                const int64_t oi = (s * p.C + c0) * N + pix;
+                if (L.res) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj)
+                    if (c0 + jj < p.C) v[jj] += L.res[oi + (int64_t)jj * N];
+                }
+                if (L.raw_out) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj)
+                    if (c0 + jj < p.C) L.raw_out[oi + (int64_t)jj * N] = v[jj];
+                }
+              }
+              if (L.write_act) {
                 float tt[8];
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  const int c = plane * 8 + jj;
-                  float val = 0.f;
-                  if (c < p.C) {
-                    val = v[jj] * kOutScale;
-                    if (L.bias) val += __ldg(L.bias + c);
-                    const int64_t oi = (s * p.C + c) * N + pix;
-                    if (L.res) val += L.res[oi];
-                    val += resv;
-                    if (L.raw_out) L.raw_out[oi] = val;
-                    val = kActScale * gelu_fast(L.out_alpha * val);
-                  }
-                  tt[jj] = val;
-                }
-                if (L.write_act) store_plane(p.act, g, plane, s * g.Ps, ps, tt);
+                for (int jj = 0; jj < 8; ++jj) tt[jj] = (c0 + jj < p.C) ? gelu_scaled(v[jj], gk) : 0.f;
+                store_plane(p.act, g, plane, s * g.Ps, ps, tt);
               }
             }
           }
-          tc_fence_before();
           fence_proxy_async_global();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(tmem_empty + buf);
-            mbar_arrive(act_ready + j);
-          }
+          if (lane == 0) mbar_arrive(act_ready + j);
         }
   }
   tc_fence_before();
@@ -455,6 +531,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
 // host side
 // ---------------------------------------------------------------------------------------------
 static bool tc_geometry(int H, int W, int64_t ns, TcGeom& g) {
+  memset(&g, 0, sizeof(g));
   if (H < 2 || W < 2) return false;
   g.H = H; g.W = W; g.ns = ns;
   g.nseg = W / 8;
@@ -497,37 +574,42 @@ bool resconv_tc_supported(int C, int lx, int ly, int kh, int kw) {
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static void tc_sizes(int nblocks, int C, int lx, int ly, int64_t ns, TcGeom& g, int& Np, int& KS, size_t& blob_halfs,
-                     size_t& act_bytes, size_t& wblob_bytes) {
+                     size_t& act_bytes, size_t& wblob_bytes, size_t& resid_bytes) {
   tc_geometry(lx, ly, ns, g);
   Np = (C + 15) & ~15;
   KS = Np / 16;
   blob_halfs = (size_t)KS * 9 * 4 * Np * 8;
   wblob_bytes = align256((size_t)(2 * nblocks - 1) * blob_halfs * 2);
   act_bytes = align256((size_t)KS * 4 * g.slots * 16);
+  resid_bytes = align256((size_t)ns * Np * lx * ly * 4);  // planar residual stream of the forward-only mode
 }
 
 size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly) {
   TcGeom g;
   int Np, KS;
-  size_t bh, ab, wb;
-  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, bh, ab, wb);
-  return ab + wb + 512;
+  size_t bh, ab, wb, rb;
+  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, bh, ab, wb, rb);
+  return ab + wb + rb + 512;
 }
 
-// Forward through the tower.  X / Hs: raw float32 [.., ns, C, N] buffers of the caller.
-//   save_all == 0: X is ONE buffer holding the running residual stream (x_nblocks on return), Hs unused
-//   save_all == 1: X[i] = X + i*act holds x_{i+1}, Hs[i] = Hs + i*act holds the conv1 pre-activation of block i
+// Forward through the tower.
+//   save_all == 0: *x_final receives the residual stream x_nblocks in the PLANAR layout [ns, Np/8, N, 8]
+//                  (it lives in the tensor-core workspace), X / Hs are not touched
+//   save_all == 1: X[i] = X + i*act holds x_{i+1}, Hs[i] = Hs + i*act the conv1 pre-activation of block i,
+//                  both [ns, C, N] (what the backward kernels of resconv.cu read); *x_final = X[nblocks-1]
 int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
-                       float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, cudaStream_t st) {
+                       float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, const float** x_final,
+                       int* x_final_planes, cudaStream_t st) {
   TcGeom g;
   int Np, KS;
-  size_t blob_halfs, act_bytes, wblob_bytes;
-  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, blob_halfs, act_bytes, wblob_bytes);
-  QTX_REQUIRE(ws_bytes >= act_bytes + wblob_bytes + 256, QTX_ERR_INVALID, "resconv_tc: workspace too small");
+  size_t blob_halfs, act_bytes, wblob_bytes, resid_bytes;
+  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, blob_halfs, act_bytes, wblob_bytes, resid_bytes);
+  QTX_REQUIRE(ws_bytes >= act_bytes + wblob_bytes + resid_bytes + 256, QTX_ERR_INVALID, "resconv_tc: workspace too small");
   QTX_REQUIRE(2 * nblocks - 1 <= kTcMaxLayers, QTX_ERR_UNSUPPORTED, "resconv_tc: too many blocks");
   unsigned char* base = (unsigned char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
   __half* act = reinterpret_cast<__half*>(base);
   __half* wblob = reinterpret_cast<__half*>(base + act_bytes);
+  float* resid = reinterpret_cast<float*>(base + act_bytes + wblob_bytes);
   const int N = lx * ly;
   const int64_t actsz = ns * C * N;
 
@@ -555,21 +637,30 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
       L.wblob_off = pp.blob_off[nl];
       L.bias = params + b1[i]; L.res = nullptr; L.res_spin = nullptr;
       L.raw_out = save_all ? Hs + (int64_t)i * actsz : nullptr;
-      L.out_alpha = 1.0f; L.write_act = 1;
+      L.out_alpha = 1.0f; L.write_act = 1; L.planar = 0;
       ++nl;
     }
     TcLayer& L = np.layer[nl];
     pp.w_off[nl] = w2[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
     L.wblob_off = pp.blob_off[nl];
     L.bias = b2[i] >= 0 ? params + b2[i] : nullptr;
-    L.res = (i == 0) ? nullptr : (save_all ? X + (int64_t)(i - 1) * actsz : X);
     L.res_spin = (i == 0) ? spins : nullptr;
-    L.raw_out = save_all ? X + (int64_t)i * actsz : X;
+    if (save_all) {
+      L.res = (i == 0) ? nullptr : X + (int64_t)(i - 1) * actsz;
+      L.raw_out = X + (int64_t)i * actsz;
+      L.planar = 0;
+    } else {
+      L.res = (i == 0) ? nullptr : resid;
+      L.raw_out = resid;
+      L.planar = 1;
+    }
     L.out_alpha = (float)(1.0 / sqrt((double)(i + 2)));
     L.write_act = (i < nblocks - 1) ? 1 : 0;
     ++nl;
   }
   pp.nconv = nl;
+  if (x_final) *x_final = save_all ? X + (int64_t)(nblocks - 1) * actsz : resid;
+  if (x_final_planes) *x_final_planes = save_all ? 0 : (Np >> 3);
   {
     const int n = 9 * KS * 16 * Np;
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)nl);
@@ -593,8 +684,18 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   QTX_REQUIRE(act_stages * act_stage + w_stages * w_stage <= cap, QTX_ERR_UNSUPPORTED, "resconv_tc: tile does not fit");
   if (const char* e = getenv("QTX_TC_WSTAGES")) { int v = atoi(e); if (v >= 2 && act_stages * act_stage + v * w_stage <= cap) w_stages = v; }
   np.act_stages = act_stages; np.w_stages = w_stages;
-  const size_t smem = act_stages * act_stage + w_stages * w_stage + (2 * act_stages + 2 * w_stages + 6) * 8 + 16 + 128;
-  QTX_CUDA(cudaFuncSetAttribute(resconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = act_stages * act_stage + w_stages * w_stage + (2 * act_stages + 2 * w_stages + 4) * 8 + 16 + 128;
+  const int PL = (Np / 8 + kColGroups - 1) / kColGroups;
+  void (*kern)(TcNetParams) = nullptr;
+  switch (PL) {
+    case 1: kern = resconv_tc_kernel<1>; break;
+    case 2: kern = resconv_tc_kernel<2>; break;
+    case 3: kern = resconv_tc_kernel<3>; break;
+    case 4: kern = resconv_tc_kernel<4>; break;
+    case 5: kern = resconv_tc_kernel<5>; break;
+    default: kern = resconv_tc_kernel<6>; break;
+  }
+  QTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = num_sms();
   if ((int64_t)grid > g.nitems) grid = (int)g.nitems;
   int per_launch = nl;
@@ -602,7 +703,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   for (int l0 = 0; l0 < nl; l0 += per_launch) {
     np.layer0 = l0;
     np.layer1 = l0 + per_launch < nl ? l0 + per_launch : nl;
-    resconv_tc_kernel<<<grid, kTcThreads, smem, st>>>(np);
+    kern<<<grid, kTcThreads, smem, st>>>(np);
     QTX_LAUNCH_CHECK();
   }
   return QTX_OK;

@@ -33,8 +33,22 @@ def main():
         psi = state(s)
         return (torch.log(psi.significand.abs()) + psi.exponent).cpu().numpy(), torch.sign(psi.significand).cpu().numpy()
 
+    if os.environ.get("TC_ONLY"):
+        os.environ["QTX_RESCONV_TC"] = "1"
+        for _ in range(3):
+            state(s)
+        torch.cuda.synchronize()
+        return
     os.environ["QTX_RESCONV_TC"] = "0"
     ref, sref = run()
+    if os.environ.get("TC_F64REF"):
+        m64 = qtx.model.ResConv(nb, C, 3, final_activation=fa, dtype=torch.float64, params=model.params.double())
+        st64 = qtx.state.Variational(m64)
+        p64 = st64(s)
+        ref64 = (torch.log(p64.significand.abs()) + p64.exponent).cpu().numpy()
+        d = np.abs(ref - ref64)
+        print(f"fp32 CUDA-core path vs float64 model: max={d.max():.3e} mean={d.mean():.3e} std of diff={np.std(ref - ref64):.3e}")
+        ref = ref64
     os.environ["QTX_RESCONV_TC"] = "1"
     for mode in (os.environ.get("TC_MODES", "1,all")).split(","):
         if mode == "all":
