@@ -79,8 +79,17 @@ struct TcNetParams {
   int C, Np, KS;
   int layer0, layer1;  // layers [layer0, layer1) are run by this launch
   int act_stages, w_stages;
+  unsigned long long* dbg;  // optional [grid][16] cycle counters (QTX_TC_DEBUG=1)
   TcLayer layer[kTcMaxLayers];
 };
+
+// wait on an mbarrier and charge the waiting time to a counter (profiling aid; `t` lives in a register)
+#define QTX_TIMED_WAIT(counter, bar, parity)        \
+  do {                                              \
+    const long long _t0 = clock64();                \
+    mbar_wait((bar), (parity));                     \
+    (counter) += (unsigned long long)(clock64() - _t0); \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // helpers
@@ -97,6 +106,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same, descriptors given as (low word, high word): the high word (SBO, version) is loop-invariant and the
+// low word (address, LBO) is advanced with one 32-bit add per operand
+__device__ __forceinline__ void umma_f16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // no wait: the caller issues tcgen05.wait::ld once after a batch of loads
@@ -320,17 +342,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
     if (lane == 0) {
       uint32_t as = 0, pa = 0, ws = 0, pw = 0;
       uint32_t cnt[2] = {0, 0};
+      unsigned long long t_ready = 0, t_aempty = 0, t_wempty = 0;
+      const long long t_begin = clock64();
       for (int64_t r = 0; r < nrounds; ++r)
         for (int li = 0; li < nl; ++li)
           for (int j = 0; j < 2; ++j) {
             const int64_t item = (2 * r + j) * gridDim.x + blockIdx.x;
             if (item >= nitems) continue;
-            if (cnt[j] > 0) mbar_wait(act_ready + j, (cnt[j] - 1) & 1);  // the previous layer of this item is stored
+            if (cnt[j] > 0) QTX_TIMED_WAIT(t_ready, act_ready + j, (cnt[j] - 1) & 1);  // the previous layer of this item is stored
             ++cnt[j];
             const int64_t wblob_off = p.layer[p.layer0 + li].wblob_off;
             const int64_t slot0 = item * g.spi * g.Ps;
             for (int ks = 0; ks < p.KS; ++ks) {
-              mbar_wait(act_empty + as, pa ^ 1);
+              QTX_TIMED_WAIT(t_aempty, act_empty + as, pa ^ 1);
               mbar_expect_tx(act_full + as, act_stage_bytes);
               unsigned char* dst = act_s + (size_t)as * act_stage_bytes;
 #pragma unroll
@@ -339,7 +363,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
                          act_full + as);
               if (++as == (uint32_t)p.act_stages) { as = 0; pa ^= 1; }
               for (int dy = 0; dy < 3; ++dy) {
-                mbar_wait(w_empty + ws, pw ^ 1);
+                QTX_TIMED_WAIT(t_wempty, w_empty + ws, pw ^ 1);
                 mbar_expect_tx(w_full + ws, w_stage_bytes);
                 bulk_g2s(w_s + (size_t)ws * w_stage_bytes,
                          p.wblob + wblob_off + ((int64_t)ks * 9 + dy * 3) * (w_tap_bytes / 2), w_stage_bytes, w_full + ws);
@@ -347,54 +371,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
               }
             }
           }
+      if (p.dbg) {
+        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+        d[0] = (unsigned long long)(clock64() - t_begin); d[1] = t_ready; d[2] = t_aempty; d[3] = t_wempty;
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // D=F32, A=B=F16, K-major
-      const uint32_t a_lbo = run_bytes, a_sbo = (uint32_t)g.SB * 16u;
-      const uint32_t b_lbo = (uint32_t)p.Np * 16u, b_sbo = 128u;
-      const uint32_t act_base = smem_u32(act_s), w_base = smem_u32(w_s);
+      // descriptors (make_desc_nosw) split into words; everything below is in 16-byte units
+      const uint32_t a_hi_w = (uint32_t)g.SB | (1u << 14);          // SBO = SB slots, version 1
+      const uint32_t b_hi_w = (128u >> 4) | (1u << 14);             // SBO = 8 rows x 16 B
+      const uint32_t run16 = run_bytes >> 4, np16 = (uint32_t)p.Np; // LBO of A (plane pitch) and B
+      const uint32_t act_base = (smem_u32(act_s) >> 4) | (run16 << 16);
+      const uint32_t w_base = (smem_u32(w_s) >> 4) | (np16 << 16);
+      const uint32_t act_stage16 = act_stage_bytes >> 4, w_stage16 = w_stage_bytes >> 4, w_tap16 = w_tap_bytes >> 4;
       // per-tile slot offset inside the staged activation tile
       uint32_t tile_off[2];
       for (int t = 0; t < 2; ++t) {
         const int sl = (g.tps == 1) ? t : 0, tis = (g.tps == 1) ? 0 : t;
-        tile_off[t] = (uint32_t)(sl * g.Ps + tis * 16 * g.SB) * 16u;
+        tile_off[t] = (uint32_t)(sl * g.Ps + tis * 16 * g.SB);
       }
+      const uint32_t d_main0 = tmem_base, d_cross0 = tmem_base + col_stride;
+      const uint32_t d_main1 = tmem_base + 2 * col_stride, d_cross1 = tmem_base + 3 * col_stride;
       uint32_t as = 0, pa = 0, ws = 0, pw = 0, q = 0;
+      unsigned long long t_tempty = 0, t_afull = 0, t_wfull = 0;
+      const long long t_begin = clock64();
       for (int64_t r = 0; r < nrounds; ++r)
         for (int li = 0; li < nl; ++li)
           for (int j = 0; j < 2; ++j) {
             const int64_t item = (2 * r + j) * gridDim.x + blockIdx.x;
             if (item >= nitems) continue;
-            mbar_wait(tmem_empty, (q & 1) ^ 1);  // the epilogue has drained the previous item's accumulators
+            QTX_TIMED_WAIT(t_tempty, tmem_empty, (q & 1) ^ 1);  // the epilogue has drained the previous item's accumulators
             ++q;
             tc_fence_after();
             for (int ks = 0; ks < p.KS; ++ks) {
-              mbar_wait(act_full + as, pa);
-              const uint32_t a_stage = act_base + as * act_stage_bytes;
+              QTX_TIMED_WAIT(t_afull, act_full + as, pa);
+              const uint32_t a_stage = act_base + as * act_stage16;
               for (int dy = 0; dy < 3; ++dy) {
-                mbar_wait(w_full + ws, pw);
+                QTX_TIMED_WAIT(t_wfull, w_full + ws, pw);
                 tc_fence_after();
-                const uint32_t w_stage = w_base + ws * w_stage_bytes;
+                const uint32_t w_stage = w_base + ws * w_stage16;
+                const uint32_t a_row0 = a_stage + tile_off[0] + (uint32_t)(dy * g.RP);
+                const uint32_t a_row1 = a_stage + tile_off[1] + (uint32_t)(dy * g.RP);
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                  const uint32_t wt = w_stage + (uint32_t)dx * w_tap_bytes;
-                  const uint64_t db_hi = make_desc_nosw(wt, b_lbo, b_sbo);
-                  const uint64_t db_lo = make_desc_nosw(wt + 2u * b_lbo, b_lbo, b_sbo);
-                  const uint32_t shift = (uint32_t)(dy * g.RP + dx) * 16u;
+                  const uint32_t b_h = w_stage + (uint32_t)dx * w_tap16, b_l = b_h + 2u * np16;
                   const uint32_t acc = (ks == 0 && dy == 0 && dx == 0) ? 0u : 1u;
-#pragma unroll
-                  for (int t = 0; t < 2; ++t) {
-                    const uint32_t a0 = a_stage + tile_off[t] + shift;
-                    const uint64_t da_hi = make_desc_nosw(a0, a_lbo, a_sbo);
-                    const uint64_t da_lo = make_desc_nosw(a0 + 2u * run_bytes, a_lbo, a_sbo);
-                    const uint32_t d_main = tmem_base + (uint32_t)(2 * t) * col_stride;
-                    const uint32_t d_cross = d_main + col_stride;
-                    umma_f16(d_main, da_hi, db_hi, idesc, acc);
-                    umma_f16(d_cross, da_lo, db_hi, idesc, acc);
-                    umma_f16(d_cross, da_hi, db_lo, idesc, 1u);
-                  }
+                  const uint32_t a0h = a_row0 + dx, a0l = a0h + 2u * run16;
+                  const uint32_t a1h = a_row1 + dx, a1l = a1h + 2u * run16;
+                  umma_f16_split(d_main0, a0h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                  umma_f16_split(d_main1, a1h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                  umma_f16_split(d_cross0, a0l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                  umma_f16_split(d_cross1, a1l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                  umma_f16_split(d_cross0, a0h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                  umma_f16_split(d_cross1, a1h, a_hi_w, b_l, b_hi_w, idesc, 1u);
                 }
                 umma_commit(w_empty + ws);
                 if (++ws == (uint32_t)p.w_stages) { ws = 0; pw ^= 1; }
@@ -404,20 +436,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
             }
             umma_commit(tmem_full);
           }
+      if (p.dbg) {
+        unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+        d[4] = (unsigned long long)(clock64() - t_begin); d[5] = t_tempty; d[6] = t_afull; d[7] = t_wfull;
+      }
     }
   } else {
     // ===== epilogue: warp -> TMEM lane quarter (warp % 4), column group (warp - 2) / 4 owns planes cgp, cgp + 3, ... =====
     const int lq = warp & 3, cgp = (warp - 2) >> 2;
     const int N = g.H * g.W, planes = p.Np >> 3;
     const int m = lq * 32 + lane;
+    // M row of this thread -> pixel and operand slots; the same for every item and layer
+    bool rvalid[2];
+    int rpix[2];
+    PixSlots rps[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int tis = (g.tps == 1) ? 0 : t;
+      const int slot = g.RP + 1 + tis * 16 * g.SB + (m >> 3) * g.SB + (m & 7);  // within the sample raster
+      const int row = slot / g.RP, col = slot - row * g.RP;
+      const int y = row - 1;
+      int x;
+      bool okx;
+      if (g.mode) {
+        const int seg = col / 10, c10 = col - seg * 10;
+        x = seg * 8 + c10 - 1;
+        okx = c10 >= 1 && c10 <= 8;
+      } else {
+        x = col - 1;
+        okx = x >= 0 && x < g.W;
+      }
+      rvalid[t] = y >= 0 && y < g.H && okx;
+      rpix[t] = rvalid[t] ? y * g.W + x : 0;
+      rps[t] = pixel_slots(g, rvalid[t] ? y : 0, rvalid[t] ? x : 0);
+    }
     uint32_t q = 0;
+    unsigned long long t_tfull = 0, t_drain = 0;
+    const long long t_begin = clock64();
     for (int64_t r = 0; r < nrounds; ++r)
       for (int li = 0; li < nl; ++li)
         for (int j = 0; j < 2; ++j) {
           const int64_t item = (2 * r + j) * gridDim.x + blockIdx.x;
           if (item >= nitems) continue;
           const TcLayer& L = p.layer[p.layer0 + li];
-          mbar_wait(tmem_full, q & 1);
+          if (lane == 0) QTX_TIMED_WAIT(t_tfull, tmem_full, q & 1);
+          __syncwarp();
+          const long long t_d0 = clock64();
           ++q;
           tc_fence_after();
           // ---- drain: main + cross accumulators of both tiles into registers, then release TMEM ----
@@ -440,29 +504,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty);
+          t_drain += (unsigned long long)(clock64() - t_d0);
           // ---- bias / residual / raw output / gelu / split / operand store ----
           const GeluConst gk = gelu_const(L.out_alpha);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const int sl = (g.tps == 1) ? t : 0, tis = (g.tps == 1) ? 0 : t;
-            const int64_t s = item * g.spi + sl;
-            const int slot = g.RP + 1 + tis * 16 * g.SB + (m >> 3) * g.SB + (m & 7);  // within the sample raster
-            const int row = slot / g.RP, col = slot - row * g.RP;
-            const int y = row - 1;
-            int x;
-            bool okx;
-            if (g.mode) {
-              const int seg = col / 10, c10 = col - seg * 10;
-              x = seg * 8 + c10 - 1;
-              okx = c10 >= 1 && c10 <= 8;
-            } else {
-              x = col - 1;
-              okx = x >= 0 && x < g.W;
-            }
-            const bool valid = s < g.ns && y >= 0 && y < g.H && okx;
-            if (!valid) continue;
-            const int pix = y * g.W + x;
-            const PixSlots ps = pixel_slots(g, y, x);
+            const int64_t s = item * g.spi + ((g.tps == 1) ? t : 0);
+            if (!rvalid[t] || s >= g.ns) continue;
+            const int pix = rpix[t];
+            const PixSlots& ps = rps[t];
             const float resv = L.res_spin ? (float)L.res_spin[s * N + pix] : 0.f;
 #pragma unroll
             for (int k = 0; k < PL; ++k) {
@@ -521,6 +571,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
           __syncwarp();
           if (lane == 0) mbar_arrive(act_ready + j);
         }
+    if (p.dbg && warp == 2 && lane == 0) {
+      unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
+      d[8] = (unsigned long long)(clock64() - t_begin); d[9] = t_tfull; d[10] = t_drain;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -700,11 +754,27 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   if ((int64_t)grid > g.nitems) grid = (int)g.nitems;
   int per_launch = nl;
   if (const char* e = getenv("QTX_TC_LAYERS_PER_LAUNCH")) { int v = atoi(e); if (v >= 1) per_launch = v; }
+  static unsigned long long* dbg_buf = nullptr;
+  const bool dbg = getenv("QTX_TC_DEBUG") != nullptr;
+  if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 256 * 16 * sizeof(unsigned long long));
+  np.dbg = dbg ? dbg_buf : nullptr;
   for (int l0 = 0; l0 < nl; l0 += per_launch) {
     np.layer0 = l0;
     np.layer1 = l0 + per_launch < nl ? l0 + per_launch : nl;
     kern<<<grid, kTcThreads, smem, st>>>(np);
     QTX_LAUNCH_CHECK();
+    if (dbg) {
+      static unsigned long long h[256 * 16];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      double a[16] = {0};
+      for (int b = 0; b < grid; ++b)
+        for (int i = 0; i < 16; ++i) a[i] += (double)h[b * 16 + i] / grid;
+      fprintf(stderr,
+              "[tc dbg] layers %d..%d items/cta %.1f | producer total %.0f wait: act_ready %.0f act_empty %.0f w_empty %.0f | "
+              "mma total %.0f wait: tmem_empty %.0f act_full %.0f w_full %.0f | epi total %.0f wait tmem_full %.0f drain %.0f\n",
+              np.layer0, np.layer1, (double)g.nitems / grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+    }
   }
   return QTX_OK;
 }

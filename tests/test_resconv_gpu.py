@@ -37,7 +37,18 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("kind,L,shape,nb,C,k,final", CASES)
+# lattices / widths that exercise both rasters of the tensor-core forward (csrc/resconv_tc.cu): SEG (16x16),
+# RASTER with one tile per sample (10x10) and two (12x12), channel counts off the 16-channel K step
+TC_CASES = [
+    ("square", 16, (16, 16), 2, 24, 3, "exp"),
+    ("square", 16, (16, 16), 3, 40, 3, "sinhp1"),
+    ("square", 12, (12, 12), 2, 20, 3, "exp"),
+    ("square", 10, (10, 10), 3, 32, 3, "sinhp1"),
+    ("square", 8, (8, 8), 2, 12, 3, "exp"),
+]
+
+
+@pytest.mark.parametrize("kind,L,shape,nb,C,k,final", CASES + TC_CASES)
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 2e-5)])
 def test_forward_matches_oracle(qtx, kind, L, shape, nb, C, k, final, dtype, tol):
     lattice_pair(qtx, kind, L)
@@ -54,7 +65,33 @@ def test_forward_matches_oracle(qtx, kind, L, shape, nb, C, k, final, dtype, tol
     assert np.allclose(to_np(psi.exponent), ex, rtol=tol, atol=tol)
 
 
-@pytest.mark.parametrize("kind,L,shape,nb,C,k,final", CASES[:5])
+def test_tensor_core_forward_is_used_and_matches_cuda_core_path(qtx, monkeypatch):
+    """float32 3x3 models run the tcgen05 tower; the CUDA-core float32 path (QTX_RESCONV_TC=0) must agree to
+    1e-5 in log psi on a batch large enough for several work items per CTA and a ragged tail."""
+    from quantax_b200 import _lib
+
+    lattice_pair(qtx, "square", 16)
+    model, net = make_resconv(qtx, (16, 16), 3, 88, 3, torch.float32, "exp", seed=11)
+    state = qtx.state.Variational(model)
+    s = torch.from_numpy(osmp.rand_states(701, 256, seed=12)).cuda()
+    n0 = _lib.lib().qtx_launch_count()
+    psi = state(s)
+    n_tc = _lib.lib().qtx_launch_count() - n0
+    monkeypatch.setenv("QTX_RESCONV_TC", "0")
+    n0 = _lib.lib().qtx_launch_count()
+    ref = state(s)
+    n_fp = _lib.lib().qtx_launch_count() - n0
+    monkeypatch.delenv("QTX_RESCONV_TC")
+    assert n_tc < n_fp  # one persistent kernel instead of one launch per convolution
+    lg = to_np(torch.log(psi.significand.abs()) + psi.exponent)
+    lr = to_np(torch.log(ref.significand.abs()) + ref.exponent)
+    assert np.abs(lg - lr).max() <= 1e-5 * max(1.0, np.abs(lr).max())
+    # and the oracle on a few of the samples
+    sig, ex = net.forward(to_np(s[:5]))
+    assert np.abs(lg[:5] - (np.log(np.abs(sig)) + ex)).max() <= 2e-5 * max(1.0, np.abs(lr).max())
+
+
+@pytest.mark.parametrize("kind,L,shape,nb,C,k,final", CASES[:5] + TC_CASES[:1] + TC_CASES[3:4])
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
 def test_jacobian_matches_oracle(qtx, kind, L, shape, nb, C, k, final, dtype, tol):
     lattice_pair(qtx, kind, L)
