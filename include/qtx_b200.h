@@ -311,6 +311,57 @@ int qtx_fourth_root(int64_t n, const double* v, double corr, double eps, double*
 int qtx_scale_columns(int dtype, void* A, int64_t ns, int64_t np, int64_t ld, const double* d,
                       qtx_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Complex-output states with real parameters (VS_TYPE.real_to_complex,
+ * quantax/state/variational.py:244-257): ResConv with out_dtype complex (pair_cpl,
+ * quantax/model/conv_nets.py:165-170, quantax/nn/activation.py:75-81), sign / phase layers
+ * (quantax/nn/sign.py:8-75), complex Oloc, symmetry projection and the stacked [Re; Im] rows that
+ * QNGD.solve builds for the real solver (quantax/optimizer/sr.py:99-104).
+ * Complex vectors are complex128, interleaved (re, im): "c128" in the parameter name.
+ * ------------------------------------------------------------------------------------------ */
+/* psi = ScaleArray(significand complex128 [ns], exponent float64 [ns]); channels must be even. */
+int qtx_resconv_forward_cplx(int model_dtype, const void* params, int nblocks, int channels, int lx,
+                             int ly, int kh, int kw, int final_act, const int8_t* spins, int64_t ns,
+                             double* significand_c128_out, double* exponent_out, void* workspace,
+                             size_t workspace_bytes, qtx_stream_t stream);
+/* out rows [0, ns) = Re O, rows [im_row_offset, im_row_offset + ns) = Im O  (variational.py:461-487:
+ * two backward passes seeded with d Re(log psi) and d Im(log psi)). */
+int qtx_resconv_jacobian_cplx(int model_dtype, const void* params, int nblocks, int channels, int lx,
+                              int ly, int kh, int kw, int final_act, const int8_t* spins, int64_t ns,
+                              int out_dtype, void* out, int64_t ld, int64_t im_row_offset,
+                              double* significand_c128_out, double* exponent_out, void* workspace,
+                              size_t workspace_bytes, qtx_stream_t stream);
+/* mult[s] *= exp(i * dot(kernel, s)), float32 dot product (sign.py:31,36: compute_sign "phase"). */
+int qtx_apply_sign_phase(const float* kernel, const int8_t* spins, int64_t ns, int N,
+                         double* mult_c128, qtx_stream_t stream);
+/* qtx_metropolis_accept with complex128 mult / mult_new. */
+int qtx_metropolis_accept_cplx(int8_t* spins, const int8_t* new_spins, const uint8_t* moved,
+                               int64_t ns, int N, double* mult_c128, double* expo,
+                               const double* mult_new_c128, const double* expo_new, double reweight,
+                               const double* inj_u, uint64_t seed, uint64_t step, uint64_t chain0,
+                               int32_t* naccept, uint8_t* accept_log, qtx_stream_t stream);
+/* qtx_oloc_reduce with complex128 amplitudes; eloc complex128 [ns], accumulated into. */
+int qtx_oloc_reduce_cplx(const int32_t* segment, const double* H, const double* mult_conn_c128,
+                         const double* expo_conn, int64_t nconn, const double* mult_c128,
+                         const double* expo, int64_t ns, double* eloc_c128_inout,
+                         qtx_stream_t stream);
+/* qtx_symm_combine for ScaleArray images with complex significands (real weights);
+ * coef_c128_out [ns, nsymm] nullable. */
+int qtx_symm_combine_cplx(const double* mult_c128, const double* expo, int64_t ns, int nsymm,
+                          const double* weights, double* mult_c128_out, double* expo_out,
+                          double* coef_c128_out, qtx_stream_t stream);
+/* Projected Jacobian of a complex-output state on stacked real matrices: J rows [0, ns*nsymm) = Re,
+ * [j_im_row_offset, ...) = Im of O(T_g s); out rows [0, ns) = Re, [out_im_row_offset, ...) = Im. */
+int qtx_weighted_rowsum_cplx(int dtype, const void* J, int64_t ldj, int64_t j_im_row_offset,
+                             const double* coef_c128, int64_t ns, int nsymm, int64_t np, void* out,
+                             int64_t ldo, int64_t out_im_row_offset, qtx_stream_t stream);
+/* SR.get_Ebar for complex local energies: stats = (Re <E rw>, <|E - <E rw>|^2 rw>); ebar stacked
+ * float64: [s] = Re, [im_offset + s] = Im of (E - <E>) sqrt(rw / ns)  (sr.py:102,180-195). */
+int qtx_ebar_cplx(const double* eloc_c128, const double* rw, int64_t ns, double* ebar_stacked_out,
+                  int64_t im_offset, double* stats_out, qtx_stream_t stream);
+/* out[i] = x[i] + 0i */
+int qtx_real_to_cplx(const double* x, int64_t n, double* out_c128, qtx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

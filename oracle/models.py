@@ -135,7 +135,12 @@ def conv_circ_bwd(x, W, dout, need_dx=True):
 class ResConv:
     """params: list over blocks of dict(w1, b1, w2, b2) (b2 is None in the last block)."""
 
-    def __init__(self, blocks, shape, final="exp"):
+    def __init__(self, blocks, shape, final="exp", out_complex=False, phase_kernel=None):
+        # out_complex: out_dtype = complex128 -> pair_cpl before the final activation (conv_nets.py:165-170,
+        # nn/activation.py:75-81); phase_kernel: float32 [N] of a trailing phase layer x * exp(i kernel.s)
+        # (nn/sign.py:8-43,62-75, tutorials/triangular.ipynb:120-128)
+        self.out_complex = out_complex
+        self.phase_kernel = None if phase_kernel is None else np.asarray(phase_kernel, dtype=np.float32)
         self.blocks = blocks
         self.shape = tuple(shape)  # (Lx, Ly); chains use (1, L)
         self.N = int(np.prod(shape))
@@ -146,7 +151,8 @@ class ResConv:
         self.nparams = sum(v.size for blk in blocks for v in blk.values() if v is not None)
 
     @staticmethod
-    def random(shape, nblocks, channels, kernel_size, dtype=np.float32, seed=0, final="exp", bias_std=0.0):
+    def random(shape, nblocks, channels, kernel_size, dtype=np.float32, seed=0, final="exp", bias_std=0.0,
+               out_complex=False, phase_kernel=None):
         """He truncated normal with fan_in = Cin*kh*kw, bias 0 (conv_nets.py:71,
         nn/initializers.py:91-119); bias_std > 0 only to make tests sensitive to the bias path."""
         rng = np.random.default_rng(seed)
@@ -161,7 +167,7 @@ class ResConv:
                 blk["w" + name] = (w * np.sqrt(2.0 / fan_in)).astype(dtype)
                 blk["b" + name] = None if last else (bias_std * rng.standard_normal(channels)).astype(dtype)
             blocks.append(blk)
-        return ResConv(blocks, shape, final)
+        return ResConv(blocks, shape, final, out_complex=out_complex, phase_kernel=phase_kernel)
 
     def params(self):
         out = []
@@ -199,6 +205,11 @@ class ResConv:
         """conv_nets.py:167-173 + activation.py:7-14,26-32 + nn/conv.py:61-68."""
         dt = self.dtype
         B = z.shape[0]
+        C = self.C
+        if self.out_complex:
+            z = (z[:, : C // 2] + 1j * z[:, C // 2:]).astype(np.complex128)  # pair_cpl, astype(out_dtype)
+            dt = np.dtype(np.complex128)
+            C = C // 2
         zf = z.reshape(B, -1)
         m = np.max(np.abs(zf), axis=1)
         if self.final == "exp":
@@ -207,7 +218,12 @@ class ResConv:
             sig = (np.exp(zf - m[:, None]) - np.exp(-zf - m[:, None])) / dt.type(2) + np.exp(-m)[:, None]
         else:
             raise ValueError(self.final)
-        a = sig.reshape(B, self.C, self.N).mean(axis=1, dtype=dt)  # reshape(-1, nsymm).mean(0)
+        a = sig.reshape(B, C, self.N).mean(axis=1, dtype=dt)  # reshape(-1, nsymm).mean(0)
+        if self.out_complex:
+            char = 1.0 / self.N  # character.astype(complex128); its ScaleArray exponent is real
+            e_char = np.log(char)
+            c1 = char * np.exp(0.0 - e_char)
+            return np.sum(a * c1, axis=1), m + e_char, sig
         char = dt.type(1.0 / self.N)  # symmetry.py:391, sector 0
         e_char = np.log(char)  # ScaleArray.from_value(character).normalize(): big_array.py:442-451
         c1 = char * np.exp(dt.type(0) - e_char)
@@ -215,9 +231,18 @@ class ResConv:
         exponent = m + e_char
         return significand, exponent, sig
 
+    def phase(self, s):
+        """exp(i * dot(kernel, s)) in float32 -> complex64 (nn/sign.py:31,36)."""
+        ph = np.asarray(s).reshape(-1, self.N).astype(np.float32) @ self.phase_kernel
+        return np.exp(1j * ph.astype(np.float32)).astype(np.complex64)
+
     def forward(self, s):
         z, _ = self._trunk(s)
         significand, exponent, _ = self._final(z)
+        if self.out_complex:
+            if self.phase_kernel is not None:
+                significand = significand * self.phase(s)
+            return significand.astype(np.complex128), exponent.astype(np.float64)
         return significand.astype(np.float64), exponent.astype(np.float64)
 
     # -- per-sample log-derivative --------------------------------------------
@@ -225,6 +250,22 @@ class ResConv:
         dt = self.dtype
         z, cache = self._trunk(s, keep=True)
         B = z.shape[0]
+        if self.out_complex:
+            # variational.py:461-487: grad of Re(out) and Im(out) w.r.t. the (real, imag) model outputs, then two
+            # backward passes; out = significand / sg(significand) + exponent, the phase layer has no parameters
+            C2 = self.C // 2
+            zc = (z[:, :C2] + 1j * z[:, C2:]).astype(np.complex128).reshape(B, -1)
+            _, _, sig = self._final(z)
+            if self.final == "exp":
+                dsig = sig
+            else:
+                m = np.max(np.abs(zc), axis=1)[:, None]
+                dsig = (np.exp(zc - m) + np.exp(-zc - m)) / 2
+            w = (dsig / sig.sum(axis=1, keepdims=True)).reshape(B, C2, *self.shape)
+            inv = 1.0 / np.sqrt(self.nblocks + 1)
+            seed_re = np.concatenate([w.real, -w.imag], axis=1) * inv
+            seed_im = np.concatenate([w.imag, w.real], axis=1) * inv
+            return self._backward(cache, seed_re.astype(dt)) + 1j * self._backward(cache, seed_im.astype(dt))
         zf = z.reshape(B, -1)
         _, _, sig = self._final(z)
         if self.final == "exp":
@@ -234,6 +275,11 @@ class ResConv:
             dsig = (np.exp(zf - m) + np.exp(-zf - m)) / dt.type(2)
         w = dsig / sig.sum(axis=1, keepdims=True, dtype=dt)
         dx = (w / dt.type(np.sqrt(self.nblocks + 1))).reshape(z.shape).astype(dt)
+        return self._backward(cache, dx)
+
+    def _backward(self, cache, dx):
+        dt = self.dtype
+        B = dx.shape[0]
         grads = [None] * self.nblocks
         for i in reversed(range(self.nblocks)):
             blk = self.blocks[i]

@@ -95,10 +95,14 @@ def minsr_pinv_eig(T, b, rtol=None, atol=0.0, tol_snr=0.0):
     return U @ (inv * rho)
 
 
-def sr_step(Omat, Eloc, rw, rtol=None, atol=0.0):
-    """optimizer/sr.py:115-123 for VS_TYPE.real_or_holomorphic, imag_time=True."""
+def sr_step(Omat, Eloc, rw, rtol=None, atol=0.0, real_to_complex=False):
+    """optimizer/sr.py:90-123, imag_time=True.  ``real_to_complex`` (real parameters, complex output,
+    sr.py:99-104): the real and imaginary parts of Obar and Ebar are stacked as 2 Ns rows."""
     eb, energy, var = ebar(Eloc, rw)
     ob, _ = obar(Omat, rw)
+    if real_to_complex:
+        ob = np.concatenate([ob.real, ob.imag], axis=0)
+        eb = np.concatenate([eb.real, eb.imag])
     return auto_pinv_eig(ob, eb, rtol, atol), energy, var
 
 

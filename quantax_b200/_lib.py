@@ -67,6 +67,18 @@ SIGNATURES = {
     "qtx_fourth_root": (_i32, [_i64, _vp, _f64, _f64, _vp, _vp]),
     "qtx_scale_columns": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp]),
     "qtx_apply_update": (_i32, [_i32, _vp, _vp, _f64, _i64, _vp, _vp]),
+    "qtx_resconv_forward_cplx": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp,
+                                        _sz, _vp]),
+    "qtx_resconv_jacobian_cplx": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _vp,
+                                         _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_apply_sign_phase": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "qtx_metropolis_accept_cplx": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f64, _vp, _u64, _u64, _u64,
+                                          _vp, _vp, _vp]),
+    "qtx_oloc_reduce_cplx": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "qtx_symm_combine_cplx": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qtx_weighted_rowsum_cplx": (_i32, [_i32, _vp, _i64, _i64, _vp, _i64, _i32, _i64, _vp, _i64, _i64, _vp]),
+    "qtx_ebar_cplx": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "qtx_real_to_cplx": (_i32, [_vp, _i64, _vp, _vp]),
 }
 
 _lib = None

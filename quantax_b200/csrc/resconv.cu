@@ -484,6 +484,98 @@ __global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict_
   }
 }
 
+// Complex-output final layer (conv_nets.py:165-173 with out_dtype complex: pair_cpl, nn/activation.py:75-81):
+//   z_c = (x_c + i x_{c + C/2}) / sqrt(nblocks+1), cast to complex128; m = max|z|; sig = exp(z - m) | sinh-plus-one
+//   a_r = mean_c sig; psi = ScaleArray(sum_r a_r * c1, m + log(1/N)), all in complex128 / float64.
+// Backward seeds (variational.py:461-478, real parameters / complex output): with w = dsig / sum(sig),
+//   d Re(log psi) -> dz_re[c] = Re w, dz_re[c + C/2] = -Im w;   d Im(log psi) -> dz_im[c] = Im w, dz_im[c + C/2] = Re w
+// (both times 1/sqrt(nblocks+1)).  One CTA per sample.
+template <typename T>
+__global__ void __launch_bounds__(256) resconv_final_cplx_kernel(const T* __restrict__ x, int64_t ns, int C, int N,
+                                                                 T inv_norm, int final_act, double2* __restrict__ sig_out,
+                                                                 double* __restrict__ exp_out, T* __restrict__ dz_re,
+                                                                 T* __restrict__ dz_im, int planes) {
+  __shared__ double red[3][8];
+  __shared__ double bc[3];
+  const int64_t s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C2 = C / 2, CN2 = C2 * N;
+  const T* xs = x + s * (planes > 0 ? (int64_t)planes * N * 8 : (int64_t)C * N);
+  auto at = [&](int c, int r) -> T { return planes > 0 ? xs[((c >> 3) * N + r) * 8 + (c & 7)] : xs[c * N + r]; };
+  double m = 0;
+  for (int e = tid; e < CN2; e += blockDim.x) {
+    const int c = e / N, r = e - c * N;
+    m = fmax(m, hypot((double)(at(c, r) * inv_norm), (double)(at(c + C2, r) * inv_norm)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+  if (lane == 0) red[0][warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    double mm = red[0][0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mm = fmax(mm, red[0][w]);
+    bc[0] = mm;
+  }
+  __syncthreads();
+  m = bc[0];
+  const double em = exp(-m);
+  double sre = 0, sim = 0;
+  for (int e = tid; e < CN2; e += blockDim.x) {
+    const int c = e / N, r = e - c * N;
+    const double zr = (double)(at(c, r) * inv_norm), zi = (double)(at(c + C2, r) * inv_norm);
+    double sn, cs;
+    sincos(zi, &sn, &cs);
+    const double ep = exp(zr - m);
+    double gr = ep * cs, gi = ep * sn;
+    if (final_act == 1) {
+      const double en = exp(-zr - m);
+      gr = (gr - en * cs) * 0.5 + em;
+      gi = (gi + en * sn) * 0.5;
+    }
+    sre += gr;
+    sim += gi;
+  }
+  __syncthreads();
+  sre = warp_sum(sre);
+  sim = warp_sum(sim);
+  if (lane == 0) { red[1][warp] = sre; red[2][warp] = sim; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += red[1][w]; b += red[2][w]; }
+    const double ch = 1.0 / (double)N, ech = log(ch), c1 = ch * exp(0.0 - ech);
+    if (sig_out) sig_out[s] = make_double2(a / C2 * c1, b / C2 * c1);
+    if (exp_out) exp_out[s] = m + ech;
+    bc[1] = a;
+    bc[2] = b;
+  }
+  if (dz_re) {
+    __syncthreads();
+    const double tr = bc[1], ti = bc[2], den = tr * tr + ti * ti;
+    T* dr = dz_re + s * C * N;
+    T* di = dz_im + s * C * N;
+    for (int e = tid; e < CN2; e += blockDim.x) {
+      const int c = e / N, r = e - c * N;
+      const double zr = (double)(at(c, r) * inv_norm), zi = (double)(at(c + C2, r) * inv_norm);
+      double sn, cs;
+      sincos(zi, &sn, &cs);
+      const double ep = exp(zr - m);
+      double gr = ep * cs, gi = ep * sn;
+      if (final_act == 1) {
+        const double en = exp(-zr - m);
+        gr = (gr + en * cs) * 0.5;
+        gi = (gi - en * sn) * 0.5;
+      }
+      // w = dsig / total
+      const double wr = (gr * tr + gi * ti) / den, wi = (gi * tr - gr * ti) / den;
+      dr[c * N + r] = (T)(wr * (double)inv_norm);
+      dr[(c + C2) * N + r] = (T)(-wi * (double)inv_norm);
+      di[c * N + r] = (T)(wi * (double)inv_norm);
+      di[(c + C2) * N + r] = (T)(wr * (double)inv_norm);
+    }
+  }
+}
+
 // per-sample weight gradient written straight into the Jacobian row:
 //   O[s, col0 + (o*cin + c)*taps + tap] = sum_r delta[s,o,r] * f(alpha * a[s,c,r+tap])
 // CTA per (sample, out-channel tile of 32); thread tile 4 (o) x 3 (q = flattened (c, tap)).
@@ -669,6 +761,8 @@ struct AcceptParams {
 };
 
 // metropolis.py:299-322: ratio = |psi'/psi|^n formed in the container then densified
+// CPL: mult / mult_new are complex128 (interleaved re, im)
+template <bool CPL>
 __global__ void __launch_bounds__(256) accept_kernel(AcceptParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -681,17 +775,33 @@ __global__ void __launch_bounds__(256) accept_kernel(AcceptParams p) {
     philox4x32_10(r0, r1, r2, r3, p.seed_lo, p.seed_hi);
     u = (double)((((uint64_t)r2 << 32) | r3) >> 11) * 0x1.0p-53;
   }
-  const double m0 = p.mult[chain], e0 = p.expo[chain], m1 = p.mult_new[chain], e1 = p.expo_new[chain];
-  double rate = fabs((m1 / m0) * exp(e1 - e0));
+  const double e0 = p.expo[chain], e1 = p.expo_new[chain];
+  double a0, a1, m1r, m1i = 0.0;
+  if constexpr (CPL) {
+    a0 = hypot(p.mult[2 * chain], p.mult[2 * chain + 1]);
+    m1r = p.mult_new[2 * chain];
+    m1i = p.mult_new[2 * chain + 1];
+    a1 = hypot(m1r, m1i);
+  } else {
+    a0 = fabs(p.mult[chain]);
+    m1r = p.mult_new[chain];
+    a1 = fabs(m1r);
+  }
+  double rate = (a1 / a0) * exp(e1 - e0);
   rate = (p.reweight == 2.0) ? rate * rate : pow(rate, p.reweight);
-  const bool zero_old = fabs(m0 * exp(e0)) == 0.0;
+  const bool zero_old = a0 * exp(e0) == 0.0;
   const bool acc = ((rate > 1.0 - u) || zero_old) && p.moved[chain];
   if (acc) {
     int8_t* sp = p.spins + chain * p.N;
     const int8_t* np_ = p.new_spins + chain * p.N;
     for (int j = lane; j < p.N; j += 32) sp[j] = np_[j];
     if (lane == 0) {
-      p.mult[chain] = m1;
+      if constexpr (CPL) {
+        p.mult[2 * chain] = m1r;
+        p.mult[2 * chain + 1] = m1i;
+      } else {
+        p.mult[chain] = m1r;
+      }
       p.expo[chain] = e1;
       if (p.naccept) p.naccept[chain] += 1;
     }
@@ -719,14 +829,15 @@ static size_t resconv_ws_base(int dtype, int64_t ns, const NetShape& sh, bool gr
   int64_t act = ns * sh.C * sh.N();
   int64_t elems = ns * sh.N();
   const int64_t wsz = (int64_t)sh.C * sh.C * sh.kh * sh.kw;
-  if (grad) elems += (int64_t)(2 * sh.nblocks + 2) * act + 2 * wsz;
+  if (grad) elems += (int64_t)(2 * sh.nblocks + 3) * act + 2 * wsz;
   else elems += 2 * act + wsz;
   return ((size_t)elems * es + 511) & ~(size_t)255;
 }
 
 template <typename T>
 static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins, int64_t ns, double* sig_out,
-                       double* exp_out, void* out, int out_dtype, int64_t ld, void* ws, cudaStream_t st) {
+                       double* exp_out, void* out, int out_dtype, int64_t ld, void* ws, cudaStream_t st, int cpl = 0,
+                       int64_t im_row_offset = 0) {
   const int N = sh.N(), C = sh.C, nb = sh.nblocks;
   const bool grad = out != nullptr;
   const int64_t act = ns * C * N;
@@ -734,9 +845,9 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
   T* x0 = base;                       // [ns, 1, N]
   T* X = x0 + ns * N;                 // grad: (nb+1) buffers X_1..X_nb (+ scratch); else 1 buffer
   T* Hs = X + (grad ? (int64_t)nb * act : act);   // grad: nb buffers; else 1
-  T* scratch = Hs + (grad ? (int64_t)nb * act : act);  // grad: 2 gradient buffers + transposed weights; then repacked weights
+  T* scratch = Hs + (grad ? (int64_t)nb * act : act);  // grad: 3 gradient buffers + transposed weights; then repacked weights
   const int64_t wsz = (int64_t)C * C * sh.kh * sh.kw;
-  T* wR = scratch + (grad ? 2 * act + wsz : 0);
+  T* wR = scratch + (grad ? 3 * act + wsz : 0);
   auto repack = [&](const T* w, int cout, int cin, int flip) -> int {
     weight_repack_kernel<T><<<64, 256, 0, st>>>(w, cout, cin, sh.kh, sh.kw, flip, wR);
     QTX_LAUNCH_CHECK();
@@ -805,9 +916,14 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
   const T* xlast = tc_done ? tc_xfinal : (grad ? X + (int64_t)(nb - 1) * act : X);
   T* dA = grad ? scratch : nullptr;           // gradient w.r.t. the current block output
   T* dB = grad ? scratch + act : nullptr;
-  T* wT = grad ? scratch + 2 * act : nullptr;
-  resconv_final_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
-                                                        sh.final_act, sig_out, exp_out, dA, tc_planes);
+  T* dC = grad ? scratch + 2 * act : nullptr; // complex output: seed of the imaginary-part pass
+  T* wT = grad ? scratch + 3 * act : nullptr;
+  if (cpl)
+    resconv_final_cplx_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
+                                                               sh.final_act, (double2*)sig_out, exp_out, dA, dC, tc_planes);
+  else
+    resconv_final_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
+                                                          sh.final_act, sig_out, exp_out, dA, tc_planes);
   QTX_LAUNCH_CHECK();
   if (!grad) return QTX_OK;
 
@@ -835,7 +951,13 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
     QTX_LAUNCH_CHECK();
     return QTX_OK;
   };
-  T* dX = dA;  // gradient w.r.t. X_{i+1}
+  // complex output: a second backward pass seeded with d Im(log psi) writes rows [im_row_offset, im_row_offset + ns)
+  for (int pass = 0; pass < (cpl ? 2 : 1); ++pass) {
+  if (pass == 1) {
+    const size_t esz = out_dtype == QTX_F64 ? 8 : 4;
+    out = (unsigned char*)out + (size_t)im_row_offset * ld * esz;
+  }
+  T* dX = pass == 0 ? dA : dC;  // gradient w.r.t. X_{i+1}
   T* tmp = dB;
   for (int i = nb - 1; i >= 0; --i) {
     const T* xin = (i == 0) ? x0 : X + (int64_t)(i - 1) * act;
@@ -872,6 +994,7 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
       q.w_ctco = wR;
       if ((rc = launch_conv<T>(q, st))) return rc;
     }
+  }
   }
   (void)taps;
   return QTX_OK;
@@ -949,6 +1072,53 @@ extern "C" int qtx_resconv_jacobian(int model_dtype, const void* params, int nbl
   QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_resconv_jacobian: bad dtype %d", model_dtype);
 }
 
+extern "C" int qtx_resconv_forward_cplx(int model_dtype, const void* params, int nblocks, int channels, int lx, int ly,
+                                        int kh, int kw, int final_act, const int8_t* spins, int64_t ns,
+                                        double* significand_c128_out, double* exponent_out, void* workspace,
+                                        size_t workspace_bytes, qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(params && spins && significand_c128_out && exponent_out && workspace, QTX_ERR_INVALID,
+              "qtx_resconv_forward_cplx: bad argument");
+  QTX_REQUIRE(shape_ok(nblocks, channels, lx, ly, kh, kw, final_act) && channels % 2 == 0, QTX_ERR_INVALID,
+              "qtx_resconv_forward_cplx: bad network shape (channels must be even)");
+  NetShape sh{nblocks, channels, lx, ly, kh, kw, final_act};
+  QTX_REQUIRE(workspace_bytes >= resconv_ws(model_dtype, ns, sh, false), QTX_ERR_INVALID,
+              "qtx_resconv_forward_cplx: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model_dtype == QTX_F32)
+    return resconv_run<float>(sh, (const float*)params, spins, ns, significand_c128_out, exponent_out, nullptr, 0, 0,
+                              workspace, st, 1, 0);
+  if (model_dtype == QTX_F64)
+    return resconv_run<double>(sh, (const double*)params, spins, ns, significand_c128_out, exponent_out, nullptr, 0, 0,
+                               workspace, st, 1, 0);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_resconv_forward_cplx: bad dtype %d", model_dtype);
+}
+
+extern "C" int qtx_resconv_jacobian_cplx(int model_dtype, const void* params, int nblocks, int channels, int lx, int ly,
+                                         int kh, int kw, int final_act, const int8_t* spins, int64_t ns, int out_dtype,
+                                         void* out, int64_t ld, int64_t im_row_offset, double* significand_c128_out,
+                                         double* exponent_out, void* workspace, size_t workspace_bytes,
+                                         qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(params && spins && out && workspace, QTX_ERR_INVALID, "qtx_resconv_jacobian_cplx: bad argument");
+  QTX_REQUIRE(shape_ok(nblocks, channels, lx, ly, kh, kw, final_act) && channels % 2 == 0, QTX_ERR_INVALID,
+              "qtx_resconv_jacobian_cplx: bad network shape (channels must be even)");
+  NetShape sh{nblocks, channels, lx, ly, kh, kw, final_act};
+  QTX_REQUIRE(ld >= sh.nparams(), QTX_ERR_INVALID, "qtx_resconv_jacobian_cplx: ld smaller than the parameter count");
+  QTX_REQUIRE(im_row_offset >= ns, QTX_ERR_INVALID, "qtx_resconv_jacobian_cplx: the imaginary block overlaps the real one");
+  QTX_REQUIRE(out_dtype == QTX_F32 || out_dtype == QTX_F64, QTX_ERR_INVALID, "qtx_resconv_jacobian_cplx: bad out dtype");
+  QTX_REQUIRE(workspace_bytes >= resconv_ws(model_dtype, ns, sh, true), QTX_ERR_INVALID,
+              "qtx_resconv_jacobian_cplx: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model_dtype == QTX_F32)
+    return resconv_run<float>(sh, (const float*)params, spins, ns, significand_c128_out, exponent_out, out, out_dtype, ld,
+                              workspace, st, 1, im_row_offset);
+  if (model_dtype == QTX_F64)
+    return resconv_run<double>(sh, (const double*)params, spins, ns, significand_c128_out, exponent_out, out, out_dtype,
+                               ld, workspace, st, 1, im_row_offset);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_resconv_jacobian_cplx: bad dtype %d", model_dtype);
+}
+
 extern "C" int qtx_metropolis_propose(int kind, const int8_t* spins, int64_t ns, int N, const int32_t* nbr_table,
                                       int max_nb, int hop, const int32_t* inj_pos, const int32_t* inj_slot,
                                       uint64_t seed, uint64_t step, uint64_t chain0, int8_t* new_spins,
@@ -978,7 +1148,51 @@ extern "C" int qtx_metropolis_accept(int8_t* spins, const int8_t* new_spins, con
   p.expo_new = expo_new; p.ns = ns; p.N = N; p.reweight = reweight; p.inj_u = inj_u;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.step = step; p.chain0 = chain0;
   p.naccept = naccept; p.accept_log = accept_log;
-  accept_kernel<<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+  accept_kernel<false><<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_metropolis_accept_cplx(int8_t* spins, const int8_t* new_spins, const uint8_t* moved, int64_t ns, int N,
+                                          double* mult, double* expo, const double* mult_new, const double* expo_new,
+                                          double reweight, const double* inj_u, uint64_t seed, uint64_t step,
+                                          uint64_t chain0, int32_t* naccept, uint8_t* accept_log, qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(spins && new_spins && moved && mult && expo && mult_new && expo_new && N > 0, QTX_ERR_INVALID,
+              "qtx_metropolis_accept_cplx: bad argument");
+  AcceptParams p;
+  p.spins = spins; p.new_spins = new_spins; p.moved = moved; p.mult = mult; p.expo = expo; p.mult_new = mult_new;
+  p.expo_new = expo_new; p.ns = ns; p.N = N; p.reweight = reweight; p.inj_u = inj_u;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.step = step; p.chain0 = chain0;
+  p.naccept = naccept; p.accept_log = accept_log;
+  accept_kernel<true><<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+// psi *= exp(i * sum_j kernel[j] * s_j)   (quantax/nn/sign.py:8-43 with output="phase"; the dot product is float32
+// like the reference's kernel.astype(float32)); warp per sample, mult is complex128
+__global__ void __launch_bounds__(256) sign_phase_kernel(const float* __restrict__ kernel, const int8_t* __restrict__ spins,
+                                                         int64_t ns, int N, double2* __restrict__ mult) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= ns) return;
+  float acc = 0.f;
+  for (int j = lane; j < N; j += 32) acc += kernel[j] * (float)spins[s * N + j];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float sn, cs;
+    sincosf(acc, &sn, &cs);
+    const double2 m = mult[s];
+    mult[s] = make_double2(m.x * (double)cs - m.y * (double)sn, m.x * (double)sn + m.y * (double)cs);
+  }
+}
+
+extern "C" int qtx_apply_sign_phase(const float* kernel, const int8_t* spins, int64_t ns, int N, double* mult_c128,
+                                    qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(kernel && spins && mult_c128 && N > 0, QTX_ERR_INVALID, "qtx_apply_sign_phase: bad argument");
+  sign_phase_kernel<<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(kernel, spins, ns, N, (double2*)mult_c128);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }

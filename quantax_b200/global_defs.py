@@ -15,11 +15,12 @@ _SUBKEY_COUNTER = 0
 
 
 def set_default_dtype(dtype) -> None:
-    """quantax/global_defs.py:16-30 (real dtypes only on this path)."""
+    """quantax/global_defs.py:16-30.  complex128 selects complex-output states with real parameters
+    (VS_TYPE.real_to_complex); complex64 is not provided."""
     global DTYPE
-    if dtype in (torch.complex64, torch.complex128):
-        raise NotImplementedError("complex default dtypes are outside the B200 hot path of this round")
-    if dtype not in (torch.float32, torch.float64):
+    if dtype == torch.complex64:
+        raise NotImplementedError("complex64 default dtype is not implemented (use complex128)")
+    if dtype not in (torch.float32, torch.float64, torch.complex128):
         raise ValueError("'dtype' should be float or complex types")
     DTYPE = dtype
 
@@ -29,11 +30,11 @@ def get_default_dtype():
 
 
 def get_real_dtype():
-    return DTYPE
+    return torch.float64 if DTYPE == torch.complex128 else DTYPE
 
 
 def is_default_cpl() -> bool:
-    return False
+    return DTYPE == torch.complex128
 
 
 def set_random_seed(seed: int) -> None:

@@ -95,8 +95,15 @@ class ResConv:
 
         if dtype not in (torch.float32, torch.float64):
             raise ValueError("`ResSum` doesn't support complex dtypes.")
-        if out_dtype is not None and out_dtype != dtype:
-            raise NotImplementedError("complex / mixed out_dtype is outside the B200 hot path of this round")
+        if out_dtype is None:
+            out_dtype = dtype
+        if out_dtype not in (dtype, torch.complex128):
+            raise NotImplementedError("out_dtype must equal dtype or be torch.complex128")
+        self.out_dtype = out_dtype
+        self.cplx = out_dtype == torch.complex128  # pair_cpl before the final activation (conv_nets.py:167-168)
+        if self.cplx and channels % 2:
+            raise ValueError("a complex-output ResConv needs an even number of channels (pair_cpl)")
+        self.raw_layers = ()
         if trans_symm is not None:
             raise NotImplementedError("only the default translation symmetry (sector 0) is implemented")
         lattice = get_lattice()
@@ -152,6 +159,12 @@ class ResConv:
     @property
     def nparams(self) -> int:
         return self._nparams
+
+    @property
+    def layers(self):
+        """The model as a tuple of layers, to be extended with RawInputLayers and re-assembled by
+        ``quantax_b200.nn.Sequential`` (tutorials/triangular.ipynb:120-128)."""
+        return (self,)
 
     def named_parameters(self):
         for name, o, shape in self.layout:

@@ -263,12 +263,17 @@ class Operator:
         if psi is None:
             psi = state(s)
         out = self.apply_diag(s)
+        cplx = psi.mult.is_complex()
+        if cplx:  # complex amplitudes: complex128 local energies
+            diag = out
+            out = torch.empty(diag.shape[0], dtype=torch.complex128, device=diag.device)
+            _lib.call("qtx_real_to_cplx", _lib.ptr(diag), diag.shape[0], _lib.ptr(out), _lib.stream())
         for nflips in self.group_tables:
             segment, _, s_conn, H, _ = self.get_conn(s, nflips)
             if segment.numel() == 0:
                 continue
             psi_conn = state.ref_forward(s_conn, s, nflips, segment, None)
-            _lib.call("qtx_oloc_reduce", _lib.ptr(segment), _lib.ptr(H), _lib.ptr(psi_conn.mult.contiguous()),
+            _lib.call("qtx_oloc_reduce_cplx" if cplx else "qtx_oloc_reduce", _lib.ptr(segment), _lib.ptr(H), _lib.ptr(psi_conn.mult.contiguous()),
                       _lib.ptr(psi_conn.expo.contiguous()), segment.numel(), _lib.ptr(psi.mult.contiguous()),
                       _lib.ptr(psi.expo.contiguous()), s.shape[0], _lib.ptr(out), _lib.stream())
         return out

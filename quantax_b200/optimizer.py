@@ -20,7 +20,7 @@ from typing import Callable, Optional
 import torch
 
 from . import _lib
-from .global_defs import device, get_default_dtype, world
+from .global_defs import device, get_default_dtype, get_real_dtype, world
 from .state import VS_TYPE, Variational
 
 
@@ -251,6 +251,24 @@ class QNGD:
         rw = samples.reweight_factor
         scale = torch.sqrt(rw / ns_glob)
         ev = self._tic("jacobian")
+        if state.vs_type == VS_TYPE.real_to_complex:
+            # complex O, real parameters: the solver sees [Re Obar; Im Obar] (sr.py:99-104); centring and scaling
+            # act on the real and the imaginary block separately ((O - <O>) sqrt(rw/Ns) is linear)
+            if P > 1:
+                raise NotImplementedError("complex-output states are single-process in this round")
+            nl = samples.nsamples
+            Omat = state.jacobian_stacked(samples.spins)
+            dt = _lib.dtype_code(Omat.dtype)
+            self._Omean = []
+            for blk in (Omat[:nl], Omat[nl:]):
+                mean = torch.empty(Omat.shape[1], dtype=torch.float64, device=Omat.device)
+                _lib.call("qtx_colmean", dt, _lib.ptr(blk), nl, blk.shape[1], blk.stride(0), None, _lib.ptr(mean),
+                          _lib.stream())
+                _lib.call("qtx_center_scale", dt, _lib.ptr(blk), nl, blk.shape[1], blk.stride(0), _lib.ptr(mean),
+                          _lib.ptr(scale), _lib.stream())
+                self._Omean.append(mean)
+            self._toc(ev)
+            return Omat
         mean, table = state.jacobian_colmean(samples.spins, return_table=True)
         if mean is not None:
             # one-pass path: column means first (without materialising O), then write Obar directly
@@ -280,7 +298,9 @@ class QNGD:
         ev = self._tic("solve")
         step = self._solver(Obar, Ebar)
         self._toc(ev)
-        return step.to(get_default_dtype())
+        # real parameters: the reference casts the step to the (complex) default dtype and update() takes its real
+        # part again (sr.py:110, variational.py:577); the real step is returned directly
+        return step.to(get_real_dtype())
 
     def get_step(self, samples, **kw) -> torch.Tensor:
         Ebar = self.get_Ebar(samples, **kw)
@@ -312,8 +332,21 @@ class SR(QNGD):
         rank, P = world()
         if Eloc is None:
             ev = self._tic("oloc")
-            Eloc = self._hamiltonian.Oloc(self._state, samples).to(torch.float64)
+            Eloc = self._hamiltonian.Oloc(self._state, samples)
             self._toc(ev)
+        if Eloc.is_complex():
+            if P > 1:
+                raise NotImplementedError("complex-output states are single-process in this round")
+            Eloc = Eloc.to(torch.complex128).contiguous()
+            nl = Eloc.shape[0]
+            ebar = torch.empty(2 * nl, dtype=torch.float64, device=Eloc.device)  # [Re; Im] (sr.py:102)
+            stats = torch.empty(2, dtype=torch.float64, device=Eloc.device)
+            _lib.call("qtx_ebar_cplx", _lib.ptr(Eloc), _lib.ptr(samples.reweight_factor.contiguous()), nl,
+                      _lib.ptr(ebar), nl, _lib.ptr(stats), _lib.stream())
+            self._stats = stats
+            self._Eloc = Eloc
+            return ebar
+        Eloc = Eloc.to(torch.float64)
         rw = samples.reweight_factor
         nl = Eloc.shape[0]
         if P > 1:

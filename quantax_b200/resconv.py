@@ -34,34 +34,47 @@ def resconv_forward(state, s: torch.Tensor) -> ScaleArray:
     m = state.model
     mdt = _lib.dtype_code(m.dtype)
     ns = s.shape[0]
-    sig = torch.empty(ns, dtype=torch.float64, device=s.device)
+    cplx = getattr(m, "cplx", False)
+    sig = torch.empty(ns, dtype=torch.complex128 if cplx else torch.float64, device=s.device)
     ex = torch.empty(ns, dtype=torch.float64, device=s.device)
     if ns == 0:
         return ScaleArray(sig, ex)
     chunk = _chunk(state, ns, False)
     wsz = _lib.lib().qtx_resconv_workspace_size(mdt, chunk, *_shape_args(m), 0)
     ws = state._workspace("resconv_fwd", wsz)
+    fn = "qtx_resconv_forward_cplx" if cplx else "qtx_resconv_forward"
     for lo in range(0, ns, chunk):
         hi = min(ns, lo + chunk)
-        _lib.call("qtx_resconv_forward", mdt, _lib.ptr(m.params), *_shape_args(m), m.final, _lib.ptr(s[lo:hi]),
+        _lib.call(fn, mdt, _lib.ptr(m.params), *_shape_args(m), m.final, _lib.ptr(s[lo:hi]),
                   hi - lo, _lib.ptr(sig[lo:hi]), _lib.ptr(ex[lo:hi]), _lib.ptr(ws), wsz, _lib.stream())
-    return ScaleArray(sig, ex)
+    psi = ScaleArray(sig, ex)
+    for layer in getattr(m, "raw_layers", ()):  # parameter-free layers acting on (psi, s), e.g. a phase layer
+        psi = layer(psi, s)
+    return psi
 
 
 def resconv_jacobian(state, s: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """Real-output model: out [ns, Np].  Complex-output model: out [2 ns, Np] holds Re O in rows [0, ns) and Im O in
+    rows [ns, 2 ns) (the stacking of sr.py:99-104).  Parameter-free phase layers do not change the log-derivative."""
     m = state.model
     mdt = _lib.dtype_code(m.dtype)
     ns = s.shape[0]
     if ns == 0:
         return out
+    cplx = getattr(m, "cplx", False)
     chunk = _chunk(state, ns, True)
     wsz = _lib.lib().qtx_resconv_workspace_size(mdt, chunk, *_shape_args(m), 1)
     ws = state._workspace("resconv_bwd", wsz)
     for lo in range(0, ns, chunk):
         hi = min(ns, lo + chunk)
-        _lib.call("qtx_resconv_jacobian", mdt, _lib.ptr(m.params), *_shape_args(m), m.final, _lib.ptr(s[lo:hi]),
-                  hi - lo, _lib.dtype_code(out.dtype), _lib.ptr2d(out[lo:hi]), out.stride(0), None, None,
-                  _lib.ptr(ws), wsz, _lib.stream())
+        if cplx:
+            _lib.call("qtx_resconv_jacobian_cplx", mdt, _lib.ptr(m.params), *_shape_args(m), m.final,
+                      _lib.ptr(s[lo:hi]), hi - lo, _lib.dtype_code(out.dtype), _lib.ptr2d(out[lo:]), out.stride(0), ns,
+                      None, None, _lib.ptr(ws), wsz, _lib.stream())
+        else:
+            _lib.call("qtx_resconv_jacobian", mdt, _lib.ptr(m.params), *_shape_args(m), m.final, _lib.ptr(s[lo:hi]),
+                      hi - lo, _lib.dtype_code(out.dtype), _lib.ptr2d(out[lo:hi]), out.stride(0), None, None,
+                      _lib.ptr(ws), wsz, _lib.stream())
     return out
 
 
@@ -73,6 +86,7 @@ def generic_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed,
     dev = spins.device
     psi = state(spins)  # bare model or symmetry-projected, LogArray or ScaleArray
     mult, expo = psi.mult.contiguous(), psi.expo.contiguous()
+    accept = "qtx_metropolis_accept_cplx" if mult.is_complex() else "qtx_metropolis_accept"
     new_spins = torch.empty_like(spins)
     moved = torch.empty(ns, dtype=torch.uint8, device=dev)
     nacc = torch.zeros(ns, dtype=torch.int32, device=dev)
@@ -90,7 +104,7 @@ def generic_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed,
                   None if pos is None else _lib.ptr(pos[t]), None if slot is None else _lib.ptr(slot[t]), seed,
                   int(step0) + t, int(chain0), _lib.ptr(new_spins), _lib.ptr(moved), st)
         psi_new = state(new_spins)
-        _lib.call("qtx_metropolis_accept", _lib.ptr(spins), _lib.ptr(new_spins), _lib.ptr(moved), ns, N,
+        _lib.call(accept, _lib.ptr(spins), _lib.ptr(new_spins), _lib.ptr(moved), ns, N,
                   _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(psi_new.mult.contiguous()), _lib.ptr(psi_new.expo.contiguous()),
                   float(reweight), None if u is None else _lib.ptr(u[t]), seed, int(step0) + t, int(chain0),
                   _lib.ptr(nacc), None if log is None else _lib.ptr(log[t]), st)

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .global_defs import device, get_default_dtype, get_sites
+from .global_defs import device, get_default_dtype, get_real_dtype, get_sites, is_default_cpl
 from .utils import LogArray, ScaleArray
 
 
@@ -62,7 +62,12 @@ class Variational(State):
         # local updates are implemented for the un-projected RefModel; a projected state evaluates
         # full forwards of all symmetry images (the reference's use_ref=False code path)
         self._use_ref = bool(use_ref) and getattr(model, "is_ref_model", False) and self._symm.is_identity
-        self._vs_type = VS_TYPE.real_or_holomorphic
+        cplx_model = bool(getattr(model, "cplx", False))
+        if cplx_model != is_default_cpl():
+            # variational.py:244-257 allows a real model under a complex default dtype (the output is cast); here the
+            # two must agree: complex-output model <-> complex128 default dtype
+            raise NotImplementedError("a complex-output model needs set_default_dtype(torch.complex128), and vice versa")
+        self._vs_type = VS_TYPE.real_to_complex if cplx_model else VS_TYPE.real_or_holomorphic
         self._ws = {}
 
     # ---- properties (variational.py:180-226) ------------------------------------------------
@@ -121,6 +126,14 @@ class Variational(State):
         nsymm = self._symm.nsymm
         kind = 0 if isinstance(psi_img, LogArray) else 1
         dev = psi_img.mult.device
+        if psi_img.mult.is_complex():
+            mult = torch.empty(ns, dtype=torch.complex128, device=dev)
+            expo = torch.empty(ns, dtype=torch.float64, device=dev)
+            coef = torch.empty((ns, nsymm), dtype=torch.complex128, device=dev) if want_coef else None
+            _lib.call("qtx_symm_combine_cplx", _lib.ptr(psi_img.mult.contiguous()), _lib.ptr(psi_img.expo.contiguous()),
+                      ns, nsymm, _lib.ptr(w), _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(coef), _lib.stream())
+            psi = ScaleArray(mult, expo)
+            return (psi, coef) if want_coef else psi
         mult = torch.empty(ns, dtype=torch.float64, device=dev)
         expo = torch.empty(ns, dtype=torch.float64, device=dev)
         coef = torch.empty((ns, nsymm), dtype=torch.float64, device=dev) if want_coef else None
@@ -242,6 +255,10 @@ class Variational(State):
         s = self._spins(fock_states)
         m = self._model
         ns = s.shape[0]
+        if self._vs_type == VS_TYPE.real_to_complex:
+            # complex [ns, Np], assembled from the stacked real matrix the optimizer works with
+            st = self.jacobian_stacked(s)
+            return torch.complex(st[:ns], st[ns:])
         odt = get_default_dtype()
         if out is None:
             out = torch.empty((ns, m.nparams), dtype=odt, device=s.device)
@@ -257,6 +274,20 @@ class Variational(State):
         if col_mean is not None or row_scale is not None:
             _lib.call("qtx_center_scale", _lib.dtype_code(out.dtype), _lib.ptr2d(out), ns, m.nparams, out.stride(0),
                       _lib.ptr(col_mean), _lib.ptr(row_scale), _lib.stream())
+        return out
+
+    def jacobian_stacked(self, fock_states, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Complex-output state with real parameters: [2 ns, Np] real, rows [0, ns) = Re O, rows [ns, 2 ns) = Im O --
+        the matrix QNGD.solve hands to the real solver (sr.py:99-104)."""
+        s = self._spins(fock_states)
+        m = self._model
+        ns = s.shape[0]
+        if out is None:
+            out = torch.empty((2 * ns, m.nparams), dtype=get_real_dtype(), device=s.device)
+        if self._symm.is_identity:
+            self._model_jacobian(s, out)
+        else:
+            self._projected_jacobian(s, out)
         return out
 
     def _model_jacobian(self, s: torch.Tensor, out: torch.Tensor) -> None:
@@ -275,14 +306,24 @@ class Variational(State):
         nsymm = self._symm.nsymm
         ns = s.shape[0]
         esz = out.element_size()
-        chunk = max(1, min(ns, (2 << 30) // max(nsymm * m.nparams * esz, 1)))
+        cplx = self._vs_type == VS_TYPE.real_to_complex
+        nre = 2 if cplx else 1
+        chunk = max(1, min(ns, (2 << 30) // max(nre * nsymm * m.nparams * esz, 1)))
         if self._backward_chunk is not None:
             chunk = max(1, min(chunk, self._backward_chunk // nsymm if self._backward_chunk >= nsymm else 1))
-        buf = torch.empty((chunk * nsymm, m.nparams), dtype=out.dtype, device=s.device)
+        buf = torch.empty((nre * chunk * nsymm, m.nparams), dtype=out.dtype, device=s.device)
         for lo in range(0, ns, chunk):
             hi = min(ns, lo + chunk)
             img = self._images(s[lo:hi])
             _, coef = self._combine(self._forward_model(img), hi - lo, want_coef=True)
+            if cplx:
+                nimg = (hi - lo) * nsymm
+                J = buf[: 2 * nimg]
+                self._model_jacobian(img, J)  # rows [0, nimg) = Re, [nimg, 2 nimg) = Im
+                _lib.call("qtx_weighted_rowsum_cplx", _lib.dtype_code(out.dtype), _lib.ptr2d(J), J.stride(0), nimg,
+                          _lib.ptr(coef), hi - lo, nsymm, m.nparams, _lib.ptr2d(out[lo:]), out.stride(0), ns,
+                          _lib.stream())
+                continue
             J = buf[: (hi - lo) * nsymm]
             self._model_jacobian(img, J)
             _lib.call("qtx_weighted_rowsum", _lib.dtype_code(out.dtype), _lib.ptr2d(J), J.stride(0), _lib.ptr(coef),

@@ -75,6 +75,15 @@ class ScaleArray:
     def __truediv__(self, other):
         return ScaleArray(self.significand / other.significand, self.exponent - other.exponent)
 
+    def __mul__(self, other):
+        from .nn import SignPhase
+
+        if isinstance(other, SignPhase):
+            if not self.significand.is_complex():
+                raise TypeError("a phase layer needs a complex-output model (out_dtype=torch.complex128)")
+            return ScaleArray(other.apply_(self.significand.contiguous()), self.exponent)
+        return NotImplemented
+
     def __array__(self, dtype=None):
         return np.asarray(self.value().cpu().numpy(), dtype)
 

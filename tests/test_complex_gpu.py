@@ -1,0 +1,151 @@
+"""Complex-output states with real parameters (VS_TYPE.real_to_complex):
+ResConv(out_dtype=complex128) + 120-degree Neel phase layer on the triangular lattice
+(tutorials/triangular.ipynb:100-128,236-239), against the NumPy oracle.  float64 models: 1e-10; float32: 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as omodels, operator as oop, sampler as osmp, sites as osites, solver as osolver
+from oracle import symmetry as osym
+from tests.gpu_util import lattice_pair, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def qtx():
+    import quantax_b200 as q
+
+    torch.cuda.set_device(0)
+    q.set_default_dtype(torch.complex128)
+    yield q
+    q.set_default_dtype(torch.float64)
+
+
+def neel120_kernel(Lx, Ly):
+    """nn/sign.py:62-75."""
+    x = 2 * np.arange(Lx)
+    y = np.arange(Ly)
+    k = (x[:, None] + y[None, :]) % 3
+    return (np.pi / 3 * k - np.pi / 6).astype(np.float32).ravel()
+
+
+def make_model(qtx, L, nb, C, dtype, final="exp", seed=0, phase=True):
+    npdt = np.float32 if dtype == torch.float32 else np.float64
+    net = omodels.ResConv.random((L, L), nb, C, 3, npdt, seed=seed, final=final, bias_std=0.1, out_complex=True,
+                                 phase_kernel=neel120_kernel(L, L) if phase else None)
+    fa = qtx.nn.exp_by_scale if final == "exp" else qtx.nn.sinhp1_by_scale
+    model0 = qtx.model.ResConv(nb, C, 3, final_activation=fa, dtype=dtype, out_dtype=torch.complex128,
+                               params=torch.from_numpy(net.params().copy()))
+    if not phase:
+        return model0, net
+
+    class PhaseLayer(qtx.nn.RawInputLayer):  # verbatim from tutorials/triangular.ipynb cell 9
+        def __call__(self, x, s):
+            phase = qtx.nn.neel120_phase(s)
+            return x * phase
+
+    model = qtx.nn.Sequential(model0.layers + (PhaseLayer(),))
+    return model, net
+
+
+def logpsi(psi):
+    m = to_np(psi.mult)
+    return np.log(np.abs(m)) + to_np(psi.expo), np.angle(m)
+
+
+def logpsi_np(sig, ex):
+    return np.log(np.abs(sig)) + ex, np.angle(sig)
+
+
+def angle_diff(a, b):
+    return np.abs(np.angle(np.exp(1j * (a - b))))
+
+
+def test_neel120_phase_matches_tutorial_formula(qtx):
+    """tutorials/triangular.ipynb cell 5: the reference checks neel120_phase against this product formula."""
+    lattice_pair(qtx, "triangular", 6, (18, 18))
+    s = osmp.rand_states(9, 36, 18, seed=1)
+    sub = ((np.arange(6) % 3)[:, None] + ((-np.arange(6)) % 3)[None, :]).ravel() % 3
+    ph = np.exp(1j * sub * 2 * np.pi / 3)
+    expect = np.prod(np.where(s > 0, 1.0, ph[None, :]), axis=1)
+    got = to_np(qtx.nn.neel120_phase(torch.from_numpy(s)).tensor())
+    assert np.abs(got - expect).max() < 1e-5  # float32 dot product inside (nn/sign.py:73)
+
+
+@pytest.mark.parametrize("final", ["exp", "sinhp1"])
+@pytest.mark.parametrize("dtype,tol,phase", [(torch.float64, 1e-10, False), (torch.float64, 2e-7, True),
+                                             (torch.float32, 2e-5, True)])
+def test_complex_forward_and_jacobian(qtx, final, dtype, tol, phase):
+    # with the phase layer |psi| itself carries complex64 rounding (|exp(i phi)| = 1 +- 6e-8 in the reference's
+    # float32 phase, nn/sign.py:36,73), so 1e-10 is only reachable without it
+    lattice_pair(qtx, "triangular", 6, (18, 18))
+    model, net = make_model(qtx, 6, 2, 8, dtype, final, seed=2, phase=phase)
+    state = qtx.state.Variational(model, max_parallel=(64, 7))
+    assert state.vs_type == qtx.state.VS_TYPE.real_to_complex
+    s = osmp.rand_states(23, 36, 18, seed=3)
+    la, ph = logpsi(state(torch.from_numpy(s)))
+    lo, po = logpsi_np(*net.forward(s))
+    assert np.abs(la - lo).max() <= tol * max(1.0, np.abs(lo).max())
+    assert angle_diff(ph, po).max() <= max(tol, 2e-6)  # the phase layer is float32 in the reference too
+    O = to_np(state.jacobian(torch.from_numpy(s)))
+    Oo = net.jacobian(s)
+    assert O.shape == Oo.shape and np.iscomplexobj(O)
+    assert np.abs(O - Oo).max() <= 10 * tol * np.abs(Oo).max()
+
+
+def test_complex_oloc_sweep_and_sr_step(qtx):
+    """Heisenberg on the 6x6 triangular lattice: exchange sweep with injected randoms (bit-exact accept pattern),
+    complex local energies, stacked [Re; Im] SR step (sr.py:99-104)."""
+    lat, olat = lattice_pair(qtx, "triangular", 6, (18, 18))
+    model, net = make_model(qtx, 6, 2, 4, torch.float64, "exp", seed=4)
+    state = qtx.state.Variational(model)
+    ns, T = 40, 25
+    sampler = qtx.sampler.SpinExchange(state, ns, thermal_steps=0)
+    spins0 = to_np(sampler._spins).copy()
+    rng = np.random.default_rng(5)
+    table = osites.site_neighbor_table(olat)
+    u = rng.random((T, ns)); pos = rng.integers(0, 36, size=(T, ns)); slot = rng.integers(0, table.shape[1], size=(T, ns))
+    sampler.inject(torch.from_numpy(pos), torch.from_numpy(u), torch.from_numpy(slot))
+    samples = sampler.sweep(T, record=True)
+    ref = osmp.sweep(osmp.FullForwardChainModel(net), spins0, T, "exchange", neighbors=table, pos=pos, slot=slot, u=u,
+                     record=True)
+    assert np.array_equal(to_np(sampler.last_accept_log), ref["accept_log"])
+    assert np.array_equal(to_np(samples.spins), ref["spins"])
+    s = ref["spins"]
+    H = qtx.operator.Heisenberg()
+    aol = oop.to_array_op_list(oop.heisenberg_op_list(olat))
+    Eo = oop.oloc(aol, net.forward, s)
+    assert np.iscomplexobj(Eo)
+    opt = qtx.optimizer.SR(state, H)
+    step = to_np(opt.get_step(samples))
+    assert np.abs(to_np(opt._Eloc) - Eo).max() <= 1e-6 * np.abs(Eo).max()  # complex64 phases in both
+    xo, eo, vo = osolver.sr_step(net.jacobian(s), Eo, np.ones(ns), real_to_complex=True)
+    assert abs(opt.energy - eo.real) <= 1e-6 * abs(eo) and abs(opt.VarE - vo) <= 1e-5 * abs(vo)
+    assert np.isrealobj(step) and np.linalg.norm(step - xo.real) <= 1e-5 * np.linalg.norm(xo)
+    p0 = to_np(state.get_params_flatten()).copy()
+    state.update(torch.from_numpy(step).cuda() * 0.01)
+    assert np.allclose(to_np(state.get_params_flatten()), p0 - 0.01 * step, rtol=1e-12, atol=1e-14)
+
+
+def test_complex_projected_state(qtx):
+    """tutorials/triangular.ipynb cell 17: D6(center=(0, 0)) @ SpinInverse() projection of the complex state."""
+    lat, olat = lattice_pair(qtx, "triangular", 6, (18, 18))
+    model, net = make_model(qtx, 6, 2, 4, torch.float64, "exp", seed=6)
+    S = qtx.symmetry
+    symm = S.D6(center=(0, 0)) @ S.SpinInverse()
+    osymm = osym.Rotation(olat, np.pi / 3, center=(0, 0)) @ osym.Flip(olat, center=(0, 0)) @ osym.SpinInverse(olat)
+    state = qtx.state.Variational(model, symm=symm, max_parallel=(4096, 48))
+    assert state.symm.nsymm == osymm.nsymm == 24
+    s = osmp.rand_states(7, 36, 18, seed=7)
+    _, _, (m, e, w, b, emax) = osym.project(osymm, net.forward, s)
+    psi = state(torch.from_numpy(s))
+    # the projection sums 24 images whose phases carry float32 rounding (in the reference too): compare the
+    # projected amplitude on the scale of the summands, sum_g |w_g psi_g|
+    got = to_np(psi.mult) * np.exp(to_np(psi.expo) - emax)
+    scale = np.sum(np.abs(m * w[None, :]) * np.exp(e - emax[:, None]), axis=1)
+    assert np.abs(got - b).max() <= 1e-6 * scale.max(), (np.abs(got - b).max(), scale.max(), np.abs(b).min())
+    O = to_np(state.jacobian(torch.from_numpy(s)))
+    Oo = osym.projected_jacobian(osymm, net.forward, net.jacobian, s)
+    amp = (scale / np.abs(b)).max()  # cancellation factor of the projection
+    assert np.abs(O - Oo).max() <= 1e-6 * amp * max(1.0, np.abs(Oo).max()), (np.abs(O - Oo).max(), amp)

@@ -179,3 +179,50 @@ def test_oracle_vmc_converges_to_ed_quick_start():
         hist.append(e)
     e0 = oop.ed_lowest(H, 8, k=1)[0]
     assert abs(np.mean(hist[-10:]) - e0) < 0.05 * abs(e0) and np.mean(hist[-10:]) > e0 - 0.05
+
+
+def test_complex_resconv_jacobian_is_the_log_derivative():
+    """Complex-output ResConv with a phase layer (conv_nets.py:165-170, nn/sign.py:62-75): the two-pass
+    Jacobian of variational.py:461-487 equals the finite-difference derivative of log psi (pins the oracle's
+    complex path, for which the reference holds no stored vectors)."""
+    from oracle import models as om
+
+    for final in ("exp", "sinhp1"):
+        net = om.ResConv.random((4, 4), 2, 4, 3, np.float64, seed=1, final=final, bias_std=0.1, out_complex=True,
+                                phase_kernel=np.linspace(0, 1, 16))
+        rng = np.random.default_rng(0)
+        s = (2 * rng.integers(0, 2, (3, 16)) - 1).astype(np.int8)
+        J = net.jacobian(s)
+        p0 = net.params()
+
+        def setp(p):
+            o = 0
+            for blk in net.blocks:
+                for k in ("w1", "b1", "w2", "b2"):
+                    if blk[k] is not None:
+                        n = blk[k].size
+                        blk[k] = p[o:o + n].reshape(blk[k].shape)
+                        o += n
+
+        for k in rng.integers(0, p0.size, 8):
+            h = 1e-6
+            pp = p0.copy(); pp[k] += h; setp(pp); s1, e1 = net.forward(s)
+            pm = p0.copy(); pm[k] -= h; setp(pm); s2, e2 = net.forward(s)
+            d = ((np.log(np.abs(s1)) + e1) - (np.log(np.abs(s2)) + e2)) / (2 * h) + 1j * np.angle(s1 / s2) / (2 * h)
+            assert np.abs(d - J[:, k]).max() < 1e-8
+        setp(p0)
+
+
+def test_sr_step_real_to_complex_stacking():
+    """sr.py:99-104: with real parameters and complex Obar the solver sees [Re; Im]; the solution solves the
+    complex least-squares problem restricted to real steps."""
+    from oracle import solver as osolver
+
+    rng = np.random.default_rng(3)
+    O = rng.standard_normal((12, 40)) + 1j * rng.standard_normal((12, 40))
+    E = rng.standard_normal(12) + 1j * rng.standard_normal(12)
+    x, e, v = osolver.sr_step(O, E, np.ones(12), real_to_complex=True)
+    ob, _ = osolver.obar(O, np.ones(12))
+    eb, _, _ = osolver.ebar(E, np.ones(12))
+    assert np.isrealobj(x)
+    assert np.allclose(ob @ x, eb, atol=1e-9)  # 24 real equations, 40 unknowns: exact min-norm solution
