@@ -254,8 +254,6 @@ class QNGD:
         if state.vs_type == VS_TYPE.real_to_complex:
             # complex O, real parameters: the solver sees [Re Obar; Im Obar] (sr.py:99-104); centring and scaling
             # act on the real and the imaginary block separately ((O - <O>) sqrt(rw/Ns) is linear)
-            if P > 1:
-                raise NotImplementedError("complex-output states are single-process in this round")
             nl = samples.nsamples
             Omat = state.jacobian_stacked(samples.spins)
             dt = _lib.dtype_code(Omat.dtype)
@@ -264,6 +262,9 @@ class QNGD:
                 mean = torch.empty(Omat.shape[1], dtype=torch.float64, device=Omat.device)
                 _lib.call("qtx_colmean", dt, _lib.ptr(blk), nl, blk.shape[1], blk.stride(0), None, _lib.ptr(mean),
                           _lib.stream())
+                if P > 1:
+                    _dist().all_reduce(mean)
+                    mean /= P
                 _lib.call("qtx_center_scale", dt, _lib.ptr(blk), nl, blk.shape[1], blk.stride(0), _lib.ptr(mean),
                           _lib.ptr(scale), _lib.stream())
                 self._Omean.append(mean)
@@ -335,16 +336,23 @@ class SR(QNGD):
             Eloc = self._hamiltonian.Oloc(self._state, samples)
             self._toc(ev)
         if Eloc.is_complex():
-            if P > 1:
-                raise NotImplementedError("complex-output states are single-process in this round")
             Eloc = Eloc.to(torch.complex128).contiguous()
             nl = Eloc.shape[0]
-            ebar = torch.empty(2 * nl, dtype=torch.float64, device=Eloc.device)  # [Re; Im] (sr.py:102)
+            rw = samples.reweight_factor.contiguous()
+            if P > 1:
+                full = torch.empty(nl * P, dtype=torch.complex128, device=Eloc.device)
+                _dist().all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(Eloc))
+                rwf = torch.empty(nl * P, dtype=torch.float64, device=Eloc.device)
+                _dist().all_gather_into_tensor(rwf, rw)
+                Eloc, rw = full, rwf
+            n = Eloc.shape[0]
+            ebar = torch.empty(2 * n, dtype=torch.float64, device=Eloc.device)  # [Re; Im] (sr.py:102)
             stats = torch.empty(2, dtype=torch.float64, device=Eloc.device)
-            _lib.call("qtx_ebar_cplx", _lib.ptr(Eloc), _lib.ptr(samples.reweight_factor.contiguous()), nl,
-                      _lib.ptr(ebar), nl, _lib.ptr(stats), _lib.stream())
+            _lib.call("qtx_ebar_cplx", _lib.ptr(Eloc), _lib.ptr(rw), n, _lib.ptr(ebar), n, _lib.ptr(stats), _lib.stream())
             self._stats = stats
             self._Eloc = Eloc
+            if P > 1:  # this rank's rows, stacked like its block of Obar
+                return torch.cat([ebar[rank * nl:(rank + 1) * nl], ebar[n + rank * nl:n + (rank + 1) * nl]])
             return ebar
         Eloc = Eloc.to(torch.float64)
         rw = samples.reweight_factor

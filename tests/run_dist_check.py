@@ -17,13 +17,27 @@ import quantax_b200 as qtx  # noqa: E402
 def vmc(model_kind, nsamples):
     qtx.set_random_seed(123)
     qtx.sites.Sites._SITES = None
-    qtx.sites.Square(4, Nparticles=(8, 8))
-    H = qtx.operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
+    qtx.set_default_dtype(torch.complex128 if model_kind == "cplx" else torch.float64)
+    if model_kind == "cplx":  # config D in miniature: triangular lattice, complex ResConv + Neel-120 phase, D6 x Z2
+        qtx.sites.Triangular(6, Nparticles=(18, 18))
+        H = qtx.operator.Heisenberg()
+    else:
+        qtx.sites.Square(4, Nparticles=(8, 8))
+        H = qtx.operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
+    symm = None
     if model_kind == "rbm":
         model = qtx.model.RBM_Dense(features=48, dtype=torch.float64)
+    elif model_kind == "cplx":
+        class PhaseLayer(qtx.nn.RawInputLayer):
+            def __call__(self, x, s):
+                return x * qtx.nn.neel120_phase(s)
+
+        model0 = qtx.model.ResConv(2, 4, 3, dtype=torch.float64, out_dtype=torch.complex128)
+        model = qtx.nn.Sequential(model0.layers + (PhaseLayer(),))
+        symm = qtx.symmetry.D6(center=(0, 0)) @ qtx.symmetry.SpinInverse()
     else:
         model = qtx.model.ResConv(2, 4, 3, dtype=torch.float64)
-    state = qtx.state.Variational(model)
+    state = qtx.state.Variational(model, symm=symm)
     sampler = qtx.sampler.SpinExchange(state, nsamples=nsamples, thermal_steps=40)
     opt = qtx.optimizer.SR(state, H)
     samples = sampler.sweep()
@@ -39,7 +53,7 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     ok = True
-    cases = (("rbm", 64 * world), ("resconv", 32 * world))
+    cases = (("rbm", 64 * world), ("resconv", 32 * world), ("cplx", 16 * world))
     dist.init_process_group("nccl", device_id=dev)
     results = []
     for kind, ns in cases:
