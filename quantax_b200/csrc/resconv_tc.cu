@@ -40,6 +40,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "gram_tc_common.cuh"
 
 namespace qtx {
@@ -63,7 +65,7 @@ struct TcGeom {
 
 struct TcLayer {
   int64_t wblob_off;       // in halfs
-  const float* bias;       // [C] or null
+  const float* bias;       // [Np] zero-padded copy in the workspace (zeros when the conv has no bias)
   const float* res;        // raw residual or null
   const int8_t* res_spin;  // block 0 residual: the spins, broadcast over channels, or null
   float* raw_out;          // raw output or null
@@ -120,6 +122,13 @@ __device__ __forceinline__ void umma_f16_split(uint32_t tmem_d, uint32_t a_lo, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp; ptxas keeps warp-uniform operands of the elected region in uniform registers
+// (UTCHMMA takes uniform-register operands: without this every MMA pays a vector->uniform election loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // no wait: the caller issues tcgen05.wait::ld once after a batch of loads
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
@@ -225,7 +234,9 @@ struct TcPrepParams {
   __half* wblob;
   int C, Np, KS, nconv;
   int64_t w_off[kTcMaxLayers];   // offset of the conv weight in `params`
+  int64_t b_off[kTcMaxLayers];   // offset of the conv bias in `params`, -1 = no bias
   int64_t blob_off[kTcMaxLayers];
+  float* bias_pad;               // [nconv][Np]
 };
 
 __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
@@ -233,6 +244,9 @@ __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
   const float* w = p.params + p.w_off[L];
   __half* out = p.wblob + p.blob_off[L];
   const int Kp = p.KS * 16;
+  if (blockIdx.x == 0)
+    for (int o = threadIdx.x; o < p.Np; o += blockDim.x)
+      p.bias_pad[L * p.Np + o] = (o < p.C && p.b_off[L] >= 0) ? p.params[p.b_off[L] + o] : 0.f;
   const int n = 9 * Kp * p.Np;  // one entry per (tap, c, o)
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const int o = e % p.Np, c = (e / p.Np) % Kp, tap = e / (p.Np * Kp);
@@ -294,6 +308,65 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
 // ---------------------------------------------------------------------------------------------
 // the persistent tensor-core kernel
 // ---------------------------------------------------------------------------------------------
+// One plane (8 channels) of one pixel: bias / residual / raw output / gelu / split / operand stores.
+// PLANAR (forward-only residual stream [ns, Np/8, N, 8]): every buffer is channel-padded, no per-channel guards;
+// otherwise raw / res are [C][N] slices (channel stride N) and channels >= nvalid are skipped.
+// The layer flags (res / raw null, write_act) are warp-uniform.
+template <bool PLANAR>
+__device__ __forceinline__ void epi_plane(const float (&a)[8], float resv, int nvalid, const float* __restrict__ bias,
+                                          const float* res, float* raw, int N, bool write_act, const GeluConst& gk,
+                                          uint4* act_hi, int64_t lo_off, const PixSlots& ps) {
+  float v[8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(a[j], kOutScale, resv + bb[j]);
+  }
+  if (PLANAR) {  // res / raw point at this pixel's 8-float group
+    if (res) {
+      const float4 r0 = *reinterpret_cast<const float4*>(res);
+      const float4 r1 = *reinterpret_cast<const float4*>(res + 4);
+      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+      v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    }
+    if (raw) {
+      *reinterpret_cast<float4*>(raw) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(raw + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  } else {
+    if (res) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) v[j] += res[(int64_t)j * N];
+    }
+    if (raw) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nvalid) raw[(int64_t)j * N] = v[j];
+    }
+  }
+  if (write_act) {
+    // channels >= C carry gelu(resv) at most: finite, and multiplied by zero weights in the next layer
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = gelu_scaled(v[j], gk);
+    uint4 vh, vl;
+    split2(t[0], t[1], vh.x, vl.x);
+    split2(t[2], t[3], vh.y, vl.y);
+    split2(t[4], t[5], vh.z, vl.z);
+    split2(t[6], t[7], vh.w, vl.w);
+    uint4* act_lo = act_hi + lo_off;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < ps.n) {
+        act_hi[ps.o[q]] = vh;
+        act_lo[ps.o[q]] = vl;
+      }
+  }
+}
+
 // PL = planes (8-channel groups) per epilogue thread: Np <= 24 * PL
 template <int PL>
 __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_constant__ TcNetParams p) {
@@ -377,8 +450,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
+    {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // D=F32, A=B=F16, K-major
       // descriptors (make_desc_nosw) split into words; everything below is in 16-byte units
       const uint32_t a_hi_w = (uint32_t)g.SB | (1u << 14);          // SBO = SB slots, version 1
@@ -388,11 +461,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
       const uint32_t w_base = (smem_u32(w_s) >> 4) | (np16 << 16);
       const uint32_t act_stage16 = act_stage_bytes >> 4, w_stage16 = w_stage_bytes >> 4, w_tap16 = w_tap_bytes >> 4;
       // per-tile slot offset inside the staged activation tile
-      uint32_t tile_off[2];
-      for (int t = 0; t < 2; ++t) {
-        const int sl = (g.tps == 1) ? t : 0, tis = (g.tps == 1) ? 0 : t;
-        tile_off[t] = (uint32_t)(sl * g.Ps + tis * 16 * g.SB);
-      }
+      const uint32_t tile_off0 = 0u;
+      const uint32_t tile_off1 = (g.tps == 1) ? (uint32_t)g.Ps : (uint32_t)(16 * g.SB);
       const uint32_t d_main0 = tmem_base, d_cross0 = tmem_base + col_stride;
       const uint32_t d_main1 = tmem_base + 2 * col_stride, d_cross1 = tmem_base + 3 * col_stride;
       uint32_t as = 0, pa = 0, ws = 0, pw = 0, q = 0;
@@ -413,30 +483,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
                 QTX_TIMED_WAIT(t_wfull, w_full + ws, pw);
                 tc_fence_after();
                 const uint32_t w_stage = w_base + ws * w_stage16;
-                const uint32_t a_row0 = a_stage + tile_off[0] + (uint32_t)(dy * g.RP);
-                const uint32_t a_row1 = a_stage + tile_off[1] + (uint32_t)(dy * g.RP);
+                const uint32_t a_row0 = a_stage + tile_off0 + (uint32_t)(dy * g.RP);
+                const uint32_t a_row1 = a_stage + tile_off1 + (uint32_t)(dy * g.RP);
+                const uint32_t acc0 = (ks == 0 && dy == 0) ? 0u : 1u;
+                if (elect_one()) {
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  const uint32_t b_h = w_stage + (uint32_t)dx * w_tap16, b_l = b_h + 2u * np16;
-                  const uint32_t acc = (ks == 0 && dy == 0 && dx == 0) ? 0u : 1u;
-                  const uint32_t a0h = a_row0 + dx, a0l = a0h + 2u * run16;
-                  const uint32_t a1h = a_row1 + dx, a1l = a1h + 2u * run16;
-                  umma_f16_split(d_main0, a0h, a_hi_w, b_h, b_hi_w, idesc, acc);
-                  umma_f16_split(d_main1, a1h, a_hi_w, b_h, b_hi_w, idesc, acc);
-                  umma_f16_split(d_cross0, a0l, a_hi_w, b_h, b_hi_w, idesc, acc);
-                  umma_f16_split(d_cross1, a1l, a_hi_w, b_h, b_hi_w, idesc, acc);
-                  umma_f16_split(d_cross0, a0h, a_hi_w, b_l, b_hi_w, idesc, 1u);
-                  umma_f16_split(d_cross1, a1h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                  for (int dx = 0; dx < 3; ++dx) {
+                    const uint32_t b_h = w_stage + (uint32_t)dx * w_tap16, b_l = b_h + 2u * np16;
+                    const uint32_t acc = (dx == 0) ? acc0 : 1u;
+                    const uint32_t a0h = a_row0 + dx, a0l = a0h + 2u * run16;
+                    const uint32_t a1h = a_row1 + dx, a1l = a1h + 2u * run16;
+                    umma_f16_split(d_main0, a0h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                    umma_f16_split(d_main1, a1h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                    umma_f16_split(d_cross0, a0l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                    umma_f16_split(d_cross1, a1l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                    umma_f16_split(d_cross0, a0h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                    umma_f16_split(d_cross1, a1h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                  }
+                  umma_commit(w_empty + ws);
+                  if (dy == 2) umma_commit(act_empty + as);
+                  if (dy == 2 && ks == p.KS - 1) umma_commit(tmem_full);
                 }
-                umma_commit(w_empty + ws);
+                __syncwarp();
                 if (++ws == (uint32_t)p.w_stages) { ws = 0; pw ^= 1; }
               }
-              umma_commit(act_empty + as);
               if (++as == (uint32_t)p.act_stages) { as = 0; pa ^= 1; }
             }
-            umma_commit(tmem_full);
           }
-      if (p.dbg) {
+      if (p.dbg && lane == 0) {
         unsigned long long* d = p.dbg + (size_t)blockIdx.x * 16;
         d[4] = (unsigned long long)(clock64() - t_begin); d[5] = t_tempty; d[6] = t_afull; d[7] = t_wfull;
       }
@@ -507,66 +581,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
           t_drain += (unsigned long long)(clock64() - t_d0);
           // ---- bias / residual / raw output / gelu / split / operand store ----
           const GeluConst gk = gelu_const(L.out_alpha);
+          const float* Lbias = L.bias;
+          const float* Lres = L.res;
+          float* Lraw = L.raw_out;
+          const int8_t* Lspin = L.res_spin;
+          const bool Lwrite = L.write_act != 0;
+          auto run = [&](auto planar_tag) {
+            constexpr bool PLANAR = decltype(planar_tag)::value;
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int64_t s = item * g.spi + ((g.tps == 1) ? t : 0);
-            if (!rvalid[t] || s >= g.ns) continue;
-            const int pix = rpix[t];
-            const PixSlots& ps = rps[t];
-            const float resv = L.res_spin ? (float)L.res_spin[s * N + pix] : 0.f;
+            for (int t = 0; t < 2; ++t) {
+              const int64_t s = item * g.spi + ((g.tps == 1) ? t : 0);
+              if (!rvalid[t] || s >= g.ns) continue;
+              const int pix = rpix[t];
+              const float resv = Lspin ? (float)Lspin[s * N + pix] : 0.f;
+              uint4* act_sample = reinterpret_cast<uint4*>(p.act) + s * g.Ps;
+              const int64_t raw_sample = PLANAR ? s * planes * N * 8 + (int64_t)pix * 8 : s * p.C * N + pix;
 #pragma unroll
-            for (int k = 0; k < PL; ++k) {
-              const int plane = cgp + kColGroups * k;
-              if (plane >= planes) continue;
-              float v[8];
-              const int c0 = plane * 8;
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) v[jj] = acc[t][k][jj] * kOutScale + resv;
-              if (L.bias) {
-                if (c0 + 8 <= p.C) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(L.bias + c0));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(L.bias + c0) + 1);
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                } else {
-#pragma unroll
-                  for (int jj = 0; jj < 8; ++jj)
-                    if (c0 + jj < p.C) v[jj] += __ldg(L.bias + c0 + jj);
-                }
-              }
-              if (L.planar) {
-                const int64_t oi = ((s * planes + plane) * N + pix) * 8;
-                if (L.res) {
-                  const float4 r0 = *reinterpret_cast<const float4*>(L.res + oi);
-                  const float4 r1 = *reinterpret_cast<const float4*>(L.res + oi + 4);
-                  v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-                  v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-                }
-                if (L.raw_out) {
-                  *reinterpret_cast<float4*>(L.raw_out + oi) = make_float4(v[0], v[1], v[2], v[3]);
-                  *reinterpret_cast<float4*>(L.raw_out + oi + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                }
-              } else {
-                const int64_t oi = (s * p.C + c0) * N + pix;
-                if (L.res) {
-#pragma unroll
-                  for (int jj = 0; jj < 8; ++jj)
-                    if (c0 + jj < p.C) v[jj] += L.res[oi + (int64_t)jj * N];
-                }
-                if (L.raw_out) {
-#pragma unroll
-                  for (int jj = 0; jj < 8; ++jj)
-                    if (c0 + jj < p.C) L.raw_out[oi + (int64_t)jj * N] = v[jj];
-                }
-              }
-              if (L.write_act) {
-                float tt[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) tt[jj] = (c0 + jj < p.C) ? gelu_scaled(v[jj], gk) : 0.f;
-                store_plane(p.act, g, plane, s * g.Ps, ps, tt);
+              for (int k = 0; k < PL; ++k) {
+                const int plane = cgp + kColGroups * k;
+                if (plane >= planes) continue;
+                const int c0 = plane * 8;
+                const int64_t roff = raw_sample + (PLANAR ? (int64_t)plane * N * 8 : (int64_t)c0 * N);
+                uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
+                epi_plane<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr,
+                                  Lraw ? Lraw + roff : nullptr, N, Lwrite, gk, act_hi, 2 * g.slots, rps[t]);
               }
             }
-          }
+          };
+          if (L.planar) run(std::true_type{});
+          else run(std::false_type{});
           fence_proxy_async_global();
           __syncwarp();
           if (lane == 0) mbar_arrive(act_ready + j);
@@ -633,7 +676,7 @@ static void tc_sizes(int nblocks, int C, int lx, int ly, int64_t ns, TcGeom& g, 
   Np = (C + 15) & ~15;
   KS = Np / 16;
   blob_halfs = (size_t)KS * 9 * 4 * Np * 8;
-  wblob_bytes = align256((size_t)(2 * nblocks - 1) * blob_halfs * 2);
+  wblob_bytes = align256((size_t)(2 * nblocks - 1) * blob_halfs * 2 + (size_t)(2 * nblocks - 1) * Np * 4);  // + padded biases
   act_bytes = align256((size_t)KS * 4 * g.slots * 16);
   resid_bytes = align256((size_t)ns * Np * lx * ly * 4);  // planar residual stream of the forward-only mode
 }
@@ -664,6 +707,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   __half* act = reinterpret_cast<__half*>(base);
   __half* wblob = reinterpret_cast<__half*>(base + act_bytes);
   float* resid = reinterpret_cast<float*>(base + act_bytes + wblob_bytes);
+  float* bias_pad = reinterpret_cast<float*>(wblob + (size_t)(2 * nblocks - 1) * blob_halfs);
   const int N = lx * ly;
   const int64_t actsz = ns * C * N;
 
@@ -689,7 +733,8 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
       TcLayer& L = np.layer[nl];
       pp.w_off[nl] = w1[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
       L.wblob_off = pp.blob_off[nl];
-      L.bias = params + b1[i]; L.res = nullptr; L.res_spin = nullptr;
+      pp.b_off[nl] = b1[i];
+      L.bias = bias_pad + (size_t)nl * Np; L.res = nullptr; L.res_spin = nullptr;
       L.raw_out = save_all ? Hs + (int64_t)i * actsz : nullptr;
       L.out_alpha = 1.0f; L.write_act = 1; L.planar = 0;
       ++nl;
@@ -697,7 +742,8 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
     TcLayer& L = np.layer[nl];
     pp.w_off[nl] = w2[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
     L.wblob_off = pp.blob_off[nl];
-    L.bias = b2[i] >= 0 ? params + b2[i] : nullptr;
+    pp.b_off[nl] = b2[i];
+    L.bias = bias_pad + (size_t)nl * Np;
     L.res_spin = (i == 0) ? spins : nullptr;
     if (save_all) {
       L.res = (i == 0) ? nullptr : X + (int64_t)(i - 1) * actsz;
@@ -713,6 +759,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
     ++nl;
   }
   pp.nconv = nl;
+  pp.bias_pad = bias_pad;
   if (x_final) *x_final = save_all ? X + (int64_t)(nblocks - 1) * actsz : resid;
   if (x_final_planes) *x_final_planes = save_all ? 0 : (Np >> 3);
   {

@@ -74,6 +74,13 @@ class RBM_Dense:
     def nparams(self) -> int:
         return self.M * self.N + self.M
 
+    def eqx_leaf_layout(self):
+        """Array leaves in equinox order: Linear.weight [M, N], Linear.bias [M] (shallow_nets.py:71)."""
+        return [("linear.weight", 0, (self.M, self.N)), ("linear.bias", self.M * self.N, (self.M,))]
+
+    def eqx_trailing_scalars(self):
+        return [False]  # Sequential.holomorphic (nn/modules.py:20-21)
+
     @property
     def W(self) -> torch.Tensor:
         return self.params[: self.M * self.N].view(self.M, self.N)
@@ -159,6 +166,25 @@ class ResConv:
     @property
     def nparams(self) -> int:
         return self._nparams
+
+    def eqx_leaf_layout(self):
+        """(name, offset, shape) of the array leaves as equinox stores them: Conv.weight [C, Cin, kh, kw] (2-D lattices)
+        or [C, Cin, kw] (chains), Conv.bias [C, 1, 1] / [C, 1]."""
+        one_d = self.Lx == 1 and self.kh == 1
+        out = []
+        for name, o, shape in self.layout:
+            if name.endswith("weight"):
+                out.append((name, o, (shape[0], shape[1], shape[3]) if one_d else shape))
+            else:
+                out.append((name, o, (shape[0], 1) if one_d else (shape[0], 1, 1)))
+        return out
+
+    def eqx_trailing_scalars(self):
+        """Non-array leaves equinox serialises after the layers: ``holomorphic`` for every Sequential; a bare ResConv
+        also carries nblocks, channels, kernel_size (dataclass field order, conv_nets.py:98-106)."""
+        if getattr(self, "raw_layers", ()):
+            return [False]
+        return [False, self.nblocks, self.channels, self.kernel_size]
 
     @property
     def layers(self):

@@ -366,8 +366,27 @@ class Variational(State):
         return ok
 
     def save(self, file) -> None:
-        np.save(file, self._model.params.detach().cpu().numpy())
+        """Write the model in the layout of ``eqx.tree_serialise_leaves`` (variational.py:581-587) so that the file
+        loads into the reference's ``Variational(model, param_file=...)`` and vice versa."""
+        from .utils import write_eqx_leaves
+
+        m = self._model
+        flat = m.params.detach().cpu().numpy()
+        arrays = [flat[o:o + int(np.prod(shape))].reshape(shape) for _, o, shape in m.eqx_leaf_layout()]
+        write_eqx_leaves(file, arrays, m.eqx_trailing_scalars())
 
     def load(self, file) -> None:
-        p = torch.from_numpy(np.load(file))
-        self._model.params.copy_(p.to(self._model.params))
+        """Read an equinox leaf file (or the flat .npy written by earlier versions of this package)."""
+        from .utils import read_eqx_leaves
+
+        leaves = read_eqx_leaves(file)
+        n = self._model.nparams
+        if len(leaves) == 1 and leaves[0].ndim == 1 and leaves[0].size == n:
+            flat = leaves[0]
+        else:
+            arrays = [a for a in leaves if a.ndim >= 1]
+            layout = self._model.eqx_leaf_layout()
+            if len(arrays) != len(layout) or any(a.size != int(np.prod(sh)) for a, (_, _, sh) in zip(arrays, layout)):
+                raise ValueError("parameter file does not match the model (leaf count / shapes)")
+            flat = np.concatenate([a.ravel() for a in arrays])
+        self._model.params.copy_(torch.from_numpy(np.ascontiguousarray(flat)).to(self._model.params))

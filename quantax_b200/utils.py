@@ -143,3 +143,41 @@ def rand_states(ns: Optional[int] = None, seed: Optional[int] = None) -> torch.T
         s = torch.where(order < nup, 1, -1).to(torch.int8)
     s = s.to(device())
     return s[0] if ns is None else s
+
+
+# ---- equinox leaf serialisation (eqx.tree_serialise_leaves / tree_deserialise_leaves) -----------------------
+# quantax saves a state with eqx.tree_serialise_leaves(file, model) (quantax/state/variational.py:581-587): every
+# array leaf, in jax.tree flatten order, is written back to back with np.save; Python bool / int / float leaves
+# (non-static dataclass fields such as ``holomorphic`` or ``nblocks``) are written the same way as 0-d arrays;
+# callables, dtypes and None are skipped.  (Restated from equinox's published behaviour, >= 0.11.4 -- equinox is
+# not installable here, so this interchange format is unpinned, see DESIGN.md.)
+def write_eqx_leaves(file, arrays, scalars=()):
+    def dump(f):
+        for a in arrays:
+            np.save(f, np.asarray(a))
+        for v in scalars:
+            np.save(f, np.asarray(v))
+
+    if hasattr(file, "write"):
+        dump(file)
+    else:
+        with open(file, "wb") as f:
+            dump(f)
+
+
+def read_eqx_leaves(file):
+    """All leaves of an equinox leaf file, in order (arrays and 0-d scalars)."""
+    def load(f):
+        out = []
+        while True:
+            pos = f.tell()
+            if not f.read(1):
+                break
+            f.seek(pos)
+            out.append(np.load(f, allow_pickle=False))
+        return out
+
+    if hasattr(file, "read"):
+        return load(file)
+    with open(file, "rb") as f:
+        return load(f)

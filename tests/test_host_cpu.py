@@ -193,3 +193,31 @@ def test_symmetry_group_tables_match_oracle():
         symmetry.Z2Inversion(1) @ symmetry.Z2Inversion(-1)
     s = np.arange(16)
     assert np.array_equal(symmetry.Identity().get_symm_spins(s), s[None])
+
+
+def test_eqx_leaf_file_roundtrip(tmp_path):
+    """The parameter files follow eqx.tree_serialise_leaves (variational.py:581-587): np.save blobs back to back,
+    arrays in flatten order, then the bool / int dataclass leaves."""
+    import io
+
+    import numpy as np
+
+    from quantax_b200.utils import read_eqx_leaves, write_eqx_leaves
+
+    rng = np.random.default_rng(0)
+    arrays = [rng.standard_normal((4, 1, 3, 3)).astype(np.float32), rng.standard_normal((4, 1, 1)).astype(np.float32),
+              rng.standard_normal((4, 4, 3, 3)).astype(np.float32)]
+    path = tmp_path / "model.eqx"
+    write_eqx_leaves(path, arrays, [False, 1, 4, 3])
+    leaves = read_eqx_leaves(path)
+    assert len(leaves) == 7
+    for a, b in zip(arrays, leaves[:3]):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    assert [l.ndim for l in leaves[3:]] == [0, 0, 0, 0] and int(leaves[5]) == 4
+    # the same bytes as a sequence of np.save calls (what jnp.save / np.save write for equinox)
+    buf = io.BytesIO()
+    for a in arrays:
+        np.save(buf, a)
+    for v in (False, 1, 4, 3):
+        np.save(buf, np.asarray(v))
+    assert path.read_bytes() == buf.getvalue()

@@ -179,3 +179,30 @@ def test_resconv_vmc_converges_on_4x4_heisenberg(qtx):
         hist.append(optimizer.energy)
     e = np.mean(hist[-10:])
     assert e > -44.913932833715506 - 0.3 and e < -44.913932833715506 * 0.99, (e, hist[::10])
+
+
+def test_state_save_load_eqx_layout(qtx, tmp_path):
+    """Variational.save / load (variational.py:162-163,581-587) through the equinox leaf layout."""
+    from quantax_b200.utils import read_eqx_leaves
+
+    lattice_pair(qtx, "square", 4)
+    model, net = make_resconv(qtx, (4, 4), 2, 4, 3, torch.float32, "exp", seed=21)
+    state = qtx.state.Variational(model)
+    f = tmp_path / "resconv.eqx"
+    state.save(f)
+    leaves = read_eqx_leaves(f)
+    shapes = [l.shape for l in leaves if l.ndim]
+    assert shapes == [(4, 1, 3, 3), (4, 1, 1), (4, 4, 3, 3), (4, 1, 1), (4, 4, 3, 3), (4, 1, 1), (4, 4, 3, 3)]
+    model2 = qtx.model.ResConv(2, 4, 3)
+    state2 = qtx.state.Variational(model2, param_file=f)
+    assert torch.equal(state2.get_params_flatten(), state.get_params_flatten())
+    lattice_pair(qtx, "chain", 8)
+    from tests.gpu_util import make_rbm
+
+    rbm, _ = make_rbm(qtx, 8, 16, torch.float32, seed=22)
+    st = qtx.state.Variational(rbm)
+    g = tmp_path / "rbm.eqx"
+    st.save(g)
+    assert [l.shape for l in read_eqx_leaves(g)] == [(16, 8), (16,), ()]
+    st2 = qtx.state.Variational(qtx.model.RBM_Dense(16), param_file=g)
+    assert torch.equal(st2.get_params_flatten(), st.get_params_flatten())
