@@ -57,7 +57,8 @@ constexpr float kOutScale = 1.0f / (kActScale * kWScale);
 struct TcGeom {
   int H, W, mode;  // mode 1 = SEG, 0 = RASTER
   int nseg, RP, Ps, SB, TS;
-  int spi, tps;    // samples per item, tiles per sample (spi * tps == 2)
+  int spi, tps;    // samples per item, tiles per sample (spi * tps == 2; == 4 for CTA pairs)
+  int pair, TSh;   // CTA-pair kernel: each CTA stages TSh slots per pair-tile
   int64_t ns;      // samples
   int64_t nitems;
   int64_t slots;   // slots per plane (all samples + tail guard)
@@ -233,6 +234,7 @@ struct TcPrepParams {
   const float* params;
   __half* wblob;
   int C, Np, KS, nconv;
+  int pair;                      // blob layout of the CTA-pair kernel: [kstep][dy][half][dx][hi|lo][p2][Np/2][8]
   int64_t w_off[kTcMaxLayers];   // offset of the conv weight in `params`
   int64_t b_off[kTcMaxLayers];   // offset of the conv bias in `params`, -1 = no bias
   int64_t blob_off[kTcMaxLayers];
@@ -255,9 +257,16 @@ __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn(v - __half2float(h));
     const int ks = c >> 4, p2 = (c >> 3) & 1, j = c & 7;
-    const int64_t base = ((((int64_t)ks * 9 + tap) * 2 + 0) * 2 + p2) * p.Np + o;
-    out[base * 8 + j] = h;
-    out[(base + 2 * p.Np) * 8 + j] = l;
+    if (p.pair) {
+      const int nh = p.Np >> 1, half = o / nh, ol = o - half * nh, dy = tap / 3, dx = tap - dy * 3;
+      const int64_t base = ((((((int64_t)ks * 3 + dy) * 2 + half) * 3 + dx) * 2 + 0) * 2 + p2) * nh + ol;
+      out[base * 8 + j] = h;
+      out[(base + 2 * nh) * 8 + j] = l;
+    } else {
+      const int64_t base = ((((int64_t)ks * 9 + tap) * 2 + 0) * 2 + p2) * p.Np + o;
+      out[base * 8 + j] = h;
+      out[(base + 2 * p.Np) * 8 + j] = l;
+    }
   }
 }
 
@@ -308,40 +317,42 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
 // ---------------------------------------------------------------------------------------------
 // the persistent tensor-core kernel
 // ---------------------------------------------------------------------------------------------
-// One plane (8 channels) of one pixel: bias / residual / raw output / gelu / split / operand stores.
+// Epilogue of one plane (8 channels) of one pixel:
+//   epi_load : a <- a * 2^-10 + bias + residual
+//   epi_store: raw output, gelu, binary16 split, operand stores with halo copies
 // PLANAR (forward-only residual stream [ns, Np/8, N, 8]): every buffer is channel-padded, no per-channel guards;
 // otherwise raw / res are [C][N] slices (channel stride N) and channels >= nvalid are skipped.
 // The layer flags (res / raw null, write_act) are warp-uniform.
 template <bool PLANAR>
-__device__ __forceinline__ void epi_plane(const float (&a)[8], float resv, int nvalid, const float* __restrict__ bias,
-                                          const float* res, float* raw, int N, bool write_act, const GeluConst& gk,
-                                          uint4* act_hi, int64_t lo_off, const PixSlots& ps) {
-  float v[8];
-  {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(a[j], kOutScale, resv + bb[j]);
-  }
-  if (PLANAR) {  // res / raw point at this pixel's 8-float group
-    if (res) {
+__device__ __forceinline__ void epi_load(float (&a)[8], float resv, int nvalid, const float* __restrict__ bias,
+                                         const float* res, int N) {
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
+  float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (res) {
+    if (PLANAR) {
       const float4 r0 = *reinterpret_cast<const float4*>(res);
       const float4 r1 = *reinterpret_cast<const float4*>(res + 4);
-      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-      v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-    }
-    if (raw) {
-      *reinterpret_cast<float4*>(raw) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(raw + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    }
-  } else {
-    if (res) {
+      r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+    } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (j < nvalid) v[j] += res[(int64_t)j * N];
+        if (j < nvalid) r[j] = res[(int64_t)j * N];
     }
-    if (raw) {
+  }
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], kOutScale, resv + bb[j]) + r[j];
+}
+
+template <bool PLANAR>
+__device__ __forceinline__ void epi_store(const float (&v)[8], int nvalid, float* raw, int N, bool write_act,
+                                          const GeluConst& gk, uint4* act_hi, int64_t lo_off, const PixSlots& ps) {
+  if (raw) {
+    if (PLANAR) {
+      *reinterpret_cast<float4*>(raw) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(raw + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (j < nvalid) raw[(int64_t)j * N] = v[j];
@@ -603,8 +614,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
                 const int c0 = plane * 8;
                 const int64_t roff = raw_sample + (PLANAR ? (int64_t)plane * N * 8 : (int64_t)c0 * N);
                 uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
-                epi_plane<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr,
-                                  Lraw ? Lraw + roff : nullptr, N, Lwrite, gk, act_hi, 2 * g.slots, rps[t]);
+                epi_load<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr, N);
+                epi_store<PLANAR>(acc[t][k], p.C - c0, Lraw ? Lraw + roff : nullptr, N, Lwrite, gk, act_hi, 2 * g.slots,
+                                  rps[t]);
               }
             }
           };
@@ -625,9 +637,405 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster 2x1x1, tcgen05.mma.cta_group::2, UMMA M = 256).  A work item is FOUR 128-row
+// tiles: pair-tile t in {0, 1} = rows of CTA 0 (tile 2t) and CTA 1 (tile 2t + 1).  Each CTA stages only the
+// activation slots of its own tiles and HALF of the weight rows (N/2 out-channels), so the shared-memory
+// operand reads per MMA drop from 4 + 3 KB to 4 + 1.5 KB per CTA (the single-CTA kernel is bound by exactly
+// these reads) and the weight stream from L2 is halved.
+//   - both CTAs run a TMA producer (cp.async.bulk.tensor ... .cta_group::2) signalling the LEADER's full barriers
+//   - the leader's elected lane issues the MMAs; tcgen05.commit ... multicast::cluster frees the stages and
+//     publishes the accumulators in both CTAs
+//   - epilogue warps of both CTAs drain their own TMEM lanes; operand stores of a sample cross the CTA boundary
+//     (halo rows), so "previous layer stored" is signalled to BOTH producers (remote mbarrier arrive, cluster scope)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc2_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tc2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tc2_mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tc2_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// no memory ordering: used where the data hand-over is TMEM (ordered by tcgen05.wait::ld + fence::before_thread_sync)
+__device__ __forceinline__ void tc2_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool tc2_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tc2_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!tc2_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 27)) __trap();
+  }
+}
+// TMA loads of a CTA pair: complete_tx goes to the barrier at the same offset in the LEADER CTA
+__device__ __forceinline__ void tc2_tma_3d(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
+                                           int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_tma_2d(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc2_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc2_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint64_t* bar) {  // arrives on `bar` of BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int PL>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    resconv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW,
+                       const __grid_constant__ TcNetParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const TcGeom& g = p.g;
+  const int Nh = p.Np >> 1;                                   // out-channels staged by this CTA
+  const uint32_t run_bytes = (uint32_t)g.TSh * 16u;           // one (hi|lo, p2) plane of one tile's slots
+  const uint32_t tile_bytes = 4u * run_bytes;
+  const uint32_t act_stage_bytes = 2u * tile_bytes;           // both pair-tiles
+  const uint32_t w_tap_bytes = 4u * (uint32_t)Nh * 16u;       // [hi|lo][p2][Nh][16 B]
+  const uint32_t w_stage_bytes = 3u * w_tap_bytes;
+  unsigned char* act_s = smem;
+  unsigned char* w_s = act_s + (size_t)p.act_stages * act_stage_bytes;
+  uint64_t* act_full = reinterpret_cast<uint64_t*>(w_s + (size_t)p.w_stages * w_stage_bytes);
+  uint64_t* act_empty = act_full + p.act_stages;
+  uint64_t* w_full = act_empty + p.act_stages;
+  uint64_t* w_empty = w_full + p.w_stages;
+  uint64_t* tmem_full = w_empty + p.w_stages;   // [1]
+  uint64_t* tmem_empty = tmem_full + 1;         // [1]  (leader's is used)
+  uint64_t* act_ready = tmem_empty + 1;         // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(act_ready + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc2_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.act_stages; ++i) { mbar_init(act_full + i, 1); mbar_init(act_empty + i, 1); }
+    for (int i = 0; i < p.w_stages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 2 * kEpiWarps);
+    mbar_init(act_ready + 0, 2 * kEpiWarps);
+    mbar_init(act_ready + 1, 2 * kEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tc2_tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc2_cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t col_stride = (uint32_t)((p.Np + 31) & ~31);
+
+  const int64_t nitems = g.nitems;
+  const int npairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  const int64_t nrounds = (nitems + 2 * (int64_t)npairs - 1) / (2 * (int64_t)npairs);
+  const int nl = p.layer1 - p.layer0;
+  // this CTA's tile of pair-tile t: tile index 2t + rank -> (sample in item, tile in sample)
+  int tsl[2], ttis[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int q = 2 * t + (int)rank;
+    tsl[t] = q / g.tps;
+    ttis[t] = q - tsl[t] * g.tps;
+  }
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      uint32_t as = 0, pa = 0, ws = 0, pw = 0;
+      uint32_t cnt[2] = {0, 0};
+      for (int64_t r = 0; r < nrounds; ++r)
+        for (int li = 0; li < nl; ++li)
+          for (int j = 0; j < 2; ++j) {
+            const int64_t item = (2 * r + j) * npairs + pair_id;
+            if (item >= nitems) continue;
+            if (cnt[j] > 0) {
+              tc2_wait_cluster(act_ready + j, (cnt[j] - 1) & 1);  // both CTAs stored the previous layer of this item
+              fence_proxy_async_global();
+            }
+            ++cnt[j];
+            const int layer = p.layer0 + li;
+            const int64_t slot0 = item * g.spi * g.Ps;
+            for (int ks = 0; ks < p.KS; ++ks) {
+              mbar_wait(act_empty + as, pa ^ 1);
+              const uint32_t lbar = smem_u32(act_full + as) & 0xFEFFFFFFu;
+              if (leader) mbar_expect_tx(act_full + as, 2u * act_stage_bytes);
+              unsigned char* dst = act_s + (size_t)as * act_stage_bytes;
+              // the map counts 8-byte elements (2 per slot); one box = half of one plane run (<= 256 elements)
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const int e0 = 2 * (int)(slot0 + (int64_t)tsl[t] * g.Ps + ttis[t] * 16 * g.SB);
+#pragma unroll
+                for (int run = 0; run < 4; ++run) {
+                  unsigned char* d = dst + (size_t)t * tile_bytes + (size_t)run * run_bytes;
+                  tc2_tma_2d(d, &tmapA, lbar, e0, ks * 4 + run);
+                  tc2_tma_2d(d + (run_bytes >> 1), &tmapA, lbar, e0 + g.TSh, ks * 4 + run);
+                }
+              }
+              if (++as == (uint32_t)p.act_stages) { as = 0; pa ^= 1; }
+              for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(w_empty + ws, pw ^ 1);
+                const uint32_t wbar = smem_u32(w_full + ws) & 0xFEFFFFFFu;
+                if (leader) mbar_expect_tx(w_full + ws, 2u * w_stage_bytes);
+                // blob [layer][kstep][dy][half] -> one contiguous stage = 6 map rows of 4 * Nh 8-byte elements
+                const int row0 = (((layer * p.KS + ks) * 3 + dy) * 2 + (int)rank) * 6;
+                tc2_tma_2d(w_s + (size_t)ws * w_stage_bytes, &tmapW, wbar, 0, row0);
+                if (++ws == (uint32_t)p.w_stages) { ws = 0; pw ^= 1; }
+              }
+            }
+          }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only; the whole warp runs the loop, one elected lane issues =====
+    if (leader) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M = 256
+      const uint32_t a_hi_w = (uint32_t)g.SB | (1u << 14);
+      const uint32_t b_hi_w = (128u >> 4) | (1u << 14);
+      const uint32_t run16 = run_bytes >> 4, nh16 = (uint32_t)Nh;
+      const uint32_t act_base = (smem_u32(act_s) >> 4) | (run16 << 16);
+      const uint32_t w_base = (smem_u32(w_s) >> 4) | (nh16 << 16);
+      const uint32_t act_stage16 = act_stage_bytes >> 4, w_stage16 = w_stage_bytes >> 4, w_tap16 = w_tap_bytes >> 4;
+      const uint32_t tile16 = tile_bytes >> 4;
+      const uint32_t d_main0 = tmem_base, d_cross0 = tmem_base + col_stride;
+      const uint32_t d_main1 = tmem_base + 2 * col_stride, d_cross1 = tmem_base + 3 * col_stride;
+      uint32_t as = 0, pa = 0, ws = 0, pw = 0, q = 0;
+      unsigned long long t_tempty = 0, t_afull = 0, t_wfull = 0;
+      const long long t_begin = clock64();
+      for (int64_t r = 0; r < nrounds; ++r)
+        for (int li = 0; li < nl; ++li)
+          for (int j = 0; j < 2; ++j) {
+            const int64_t item = (2 * r + j) * npairs + pair_id;
+            if (item >= nitems) continue;
+            {
+              const long long _t0 = clock64();
+              tc2_wait_cluster(tmem_empty, (q & 1) ^ 1);  // both CTAs' epilogues drained the previous item
+              t_tempty += (unsigned long long)(clock64() - _t0);
+            }
+            ++q;
+            tc_fence_after();
+            for (int ks = 0; ks < p.KS; ++ks) {
+              QTX_TIMED_WAIT(t_afull, act_full + as, pa);
+              const uint32_t a_stage = act_base + as * act_stage16;
+              for (int dy = 0; dy < 3; ++dy) {
+                QTX_TIMED_WAIT(t_wfull, w_full + ws, pw);
+                tc_fence_after();
+                const uint32_t w_stage = w_base + ws * w_stage16;
+                const uint32_t a_row0 = a_stage + (uint32_t)(dy * g.RP);
+                const uint32_t a_row1 = a_row0 + tile16;
+                const uint32_t acc0 = (ks == 0 && dy == 0) ? 0u : 1u;
+                if (elect_one()) {
+#pragma unroll
+                  for (int dx = 0; dx < 3; ++dx) {
+                    const uint32_t b_h = w_stage + (uint32_t)dx * w_tap16, b_l = b_h + 2u * nh16;
+                    const uint32_t acc = (dx == 0) ? acc0 : 1u;
+                    const uint32_t a0h = a_row0 + dx, a0l = a0h + 2u * run16;
+                    const uint32_t a1h = a_row1 + dx, a1l = a1h + 2u * run16;
+                    tc2_umma(d_main0, a0h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                    tc2_umma(d_main1, a1h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                    tc2_umma(d_cross0, a0l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                    tc2_umma(d_cross1, a1l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                    tc2_umma(d_cross0, a0h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                    tc2_umma(d_cross1, a1h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                  }
+                  tc2_commit(w_empty + ws);
+                  if (dy == 2) tc2_commit(act_empty + as);
+                  if (dy == 2 && ks == p.KS - 1) tc2_commit(tmem_full);
+                }
+                __syncwarp();
+                if (++ws == (uint32_t)p.w_stages) { ws = 0; pw ^= 1; }
+              }
+              if (++as == (uint32_t)p.act_stages) { as = 0; pa ^= 1; }
+            }
+          }
+      if (p.dbg && lane == 0) {
+        unsigned long long* d = p.dbg + (size_t)pair_id * 16;
+        d[4] = (unsigned long long)(clock64() - t_begin); d[5] = t_tempty; d[6] = t_afull; d[7] = t_wfull;
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): warp -> TMEM lane quarter (warp % 4), column group (warp - 2) / 4 =====
+    const int lq = warp & 3, cgp = (warp - 2) >> 2;
+    const int N = g.H * g.W, planes = p.Np >> 3;
+    const int m = lq * 32 + lane;
+    bool rvalid[2];
+    int rpix[2];
+    PixSlots rps[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int slot = g.RP + 1 + ttis[t] * 16 * g.SB + (m >> 3) * g.SB + (m & 7);  // within the sample raster
+      const int row = slot / g.RP, col = slot - row * g.RP;
+      const int y = row - 1;
+      int x;
+      bool okx;
+      if (g.mode) {
+        const int seg = col / 10, c10 = col - seg * 10;
+        x = seg * 8 + c10 - 1;
+        okx = c10 >= 1 && c10 <= 8;
+      } else {
+        x = col - 1;
+        okx = x >= 0 && x < g.W;
+      }
+      rvalid[t] = y >= 0 && y < g.H && okx;
+      rpix[t] = rvalid[t] ? y * g.W + x : 0;
+      rps[t] = pixel_slots(g, rvalid[t] ? y : 0, rvalid[t] ? x : 0);
+    }
+    const uint32_t tmem_empty_leader = tc2_mapa(smem_u32(tmem_empty), 0);
+    uint32_t ready_addr[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) ready_addr[j][c] = tc2_mapa(smem_u32(act_ready + j), (uint32_t)c);
+    uint32_t q = 0;
+    unsigned long long t_tfull = 0, t_drain = 0;
+    const long long t_begin = clock64();
+    for (int64_t r = 0; r < nrounds; ++r)
+      for (int li = 0; li < nl; ++li)
+        for (int j = 0; j < 2; ++j) {
+          const int64_t item = (2 * r + j) * npairs + pair_id;
+          if (item >= nitems) continue;
+          const TcLayer& L = p.layer[p.layer0 + li];
+          if (lane == 0) QTX_TIMED_WAIT(t_tfull, tmem_full, q & 1);
+          __syncwarp();
+          const long long t_d0 = clock64();
+          ++q;
+          tc_fence_after();
+          float acc[2][PL][8];
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int k = 0; k < PL; ++k) {
+              const int plane = cgp + kColGroups * k;
+              if (plane < planes) {
+                uint32_t rm[8], rc[8];
+                const uint32_t a = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(2 * t) * col_stride + plane * 8;
+                tmem_ld8_nowait(a, rm);
+                tmem_ld8_nowait(a + col_stride, rc);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[t][k][jj] = __uint_as_float(rm[jj]) + __uint_as_float(rc[jj]);
+              }
+            }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc2_arrive_remote_relaxed(tmem_empty_leader);
+          t_drain += (unsigned long long)(clock64() - t_d0);
+          const GeluConst gk = gelu_const(L.out_alpha);
+          const float* Lbias = L.bias;
+          const float* Lres = L.res;
+          float* Lraw = L.raw_out;
+          const int8_t* Lspin = L.res_spin;
+          const bool Lwrite = L.write_act != 0;
+          auto run = [&](auto planar_tag) {
+            constexpr bool PLANAR = decltype(planar_tag)::value;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int64_t s = item * g.spi + tsl[t];
+              if (!rvalid[t] || s >= g.ns) continue;
+              const int pix = rpix[t];
+              const float resv = Lspin ? (float)Lspin[s * N + pix] : 0.f;
+              uint4* act_sample = reinterpret_cast<uint4*>(p.act) + s * g.Ps;
+              const int64_t raw_sample = PLANAR ? s * planes * N * 8 + (int64_t)pix * 8 : s * p.C * N + pix;
+#pragma unroll
+              for (int k = 0; k < PL; ++k) {
+                const int plane = cgp + kColGroups * k;
+                if (plane >= planes) continue;
+                const int c0 = plane * 8;
+                const int64_t roff = raw_sample + (PLANAR ? (int64_t)plane * N * 8 : (int64_t)c0 * N);
+                uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
+                epi_load<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr, N);
+                epi_store<PLANAR>(acc[t][k], p.C - c0, Lraw ? Lraw + roff : nullptr, N, Lwrite, gk, act_hi, 2 * g.slots,
+                                  rps[t]);
+              }
+            }
+          };
+          if (L.planar) run(std::true_type{});
+          else run(std::false_type{});
+          // the next layer's TMA loads (either CTA) must see these stores: proxy fence by every writer, warp
+          // barrier (orders the lanes' stores before lane 0), then cluster-scope release arrives on both CTAs
+          fence_proxy_async_global();
+          __syncwarp();
+          if (lane == 0) {
+            tc2_arrive_remote(ready_addr[j][0]);
+            tc2_arrive_remote(ready_addr[j][1]);
+          }
+        }
+    if (p.dbg && leader && warp == 2 && lane == 0) {
+      unsigned long long* d = p.dbg + (size_t)pair_id * 16;
+      d[8] = (unsigned long long)(clock64() - t_begin); d[9] = t_tfull; d[10] = t_drain;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc2_cluster_sync();  // the peer must not exit (or free TMEM) while the leader still reads its smem / TMEM
+  if (warp == 1) tc2_tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static bool tc_geometry(int H, int W, int64_t ns, TcGeom& g) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tc_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static bool tc_geometry(int H, int W, int64_t ns, TcGeom& g, bool pair = false) {
   memset(&g, 0, sizeof(g));
   if (H < 2 || W < 2) return false;
   g.H = H; g.W = W; g.ns = ns;
@@ -642,11 +1050,16 @@ static bool tc_geometry(int H, int W, int64_t ns, TcGeom& g) {
     if (g.tps > 2) return false;
   }
   g.Ps = (H + 2) * g.RP;
-  g.spi = 2 / g.tps;
+  g.pair = pair ? 1 : 0;
+  const int ntile = pair ? 4 : 2;  // 128-row tiles per work item
+  g.spi = ntile / g.tps;
+  // slots read by one 128-row tile (all nine taps); a multiple of 16 so that half a plane run (TSh * 8 B, one TMA
+  // box of the CTA-pair kernel) stays 128-byte aligned in shared memory
+  g.TSh = (15 * g.SB + 7 + 2 * g.RP + 2 + 1 + 15) & ~15;
   int ts = 0;
-  for (int t = 0; t < 2; ++t) {
-    const int sl = (g.tps == 1) ? t : 0, tis = (g.tps == 1) ? 0 : t;
-    const int need = sl * g.Ps + tis * 16 * g.SB + 15 * g.SB + 7 + 2 * g.RP + 2 + 1;
+  for (int q = 0; q < ntile; ++q) {
+    const int sl = q / g.tps, tis = q % g.tps;
+    const int need = sl * g.Ps + tis * 16 * g.SB + g.TSh;
     if (need > ts) ts = need;
   }
   if (ts < g.spi * g.Ps) ts = g.spi * g.Ps;
@@ -670,9 +1083,14 @@ bool resconv_tc_supported(int C, int lx, int ly, int kh, int kw) {
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static bool tc_use_pair() {
+  const char* e = getenv("QTX_TC_2CTA");
+  return e ? atoi(e) != 0 : true;
+}
+
 static void tc_sizes(int nblocks, int C, int lx, int ly, int64_t ns, TcGeom& g, int& Np, int& KS, size_t& blob_halfs,
                      size_t& act_bytes, size_t& wblob_bytes, size_t& resid_bytes) {
-  tc_geometry(lx, ly, ns, g);
+  tc_geometry(lx, ly, ns, g, tc_use_pair());
   Np = (C + 15) & ~15;
   KS = Np / 16;
   blob_halfs = (size_t)KS * 9 * 4 * Np * 8;
@@ -724,7 +1142,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
 
   // tensor-core layers: conv2_0, then (conv1_i, conv2_i) for i >= 1
   TcPrepParams pp{};
-  pp.params = params; pp.wblob = wblob; pp.C = C; pp.Np = Np; pp.KS = KS;
+  pp.params = params; pp.wblob = wblob; pp.C = C; pp.Np = Np; pp.KS = KS; pp.pair = g.pair;
   TcNetParams np{};
   np.act = act; np.wblob = wblob; np.g = g; np.C = C; np.Np = Np; np.KS = KS;
   int nl = 0;
@@ -777,8 +1195,9 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
     QTX_LAUNCH_CHECK();
   }
   // shared memory: activation ring + weight ring + barriers
-  const size_t act_stage = (size_t)4 * g.TS * 16, w_stage = (size_t)3 * 4 * Np * 16;
-  int act_stages = 3, w_stages = 6;
+  const size_t act_stage = g.pair ? (size_t)2 * 4 * g.TSh * 16 : (size_t)4 * g.TS * 16;
+  const size_t w_stage = g.pair ? (size_t)3 * 4 * (Np / 2) * 16 : (size_t)3 * 4 * Np * 16;
+  int act_stages = 3, w_stages = g.pair ? 9 : 6;
   const size_t cap = 227 * 1024 - 1024;
   while (act_stages > 2 && act_stages * act_stage + w_stages * w_stage > cap) --act_stages;
   while (w_stages > 2 && act_stages * act_stage + w_stages * w_stage > cap) --w_stages;
@@ -787,6 +1206,85 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   np.act_stages = act_stages; np.w_stages = w_stages;
   const size_t smem = act_stages * act_stage + w_stages * w_stage + (2 * act_stages + 2 * w_stages + 4) * 8 + 16 + 128;
   const int PL = (Np / 8 + kColGroups - 1) / kColGroups;
+  int per_launch = nl;
+  if (const char* e = getenv("QTX_TC_LAYERS_PER_LAUNCH")) { int v = atoi(e); if (v >= 1) per_launch = v; }
+  static unsigned long long* dbg_buf = nullptr;
+  const bool dbg = getenv("QTX_TC_DEBUG") != nullptr;
+  if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 256 * 16 * sizeof(unsigned long long));
+  np.dbg = dbg ? dbg_buf : nullptr;
+  auto report = [&](int units) {
+    static unsigned long long h[256 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    double a[16] = {0};
+    for (int b2 = 0; b2 < units; ++b2)
+      for (int i = 0; i < 16; ++i) a[i] += (double)h[b2 * 16 + i] / units;
+    fprintf(stderr,
+            "[tc dbg%s] layers %d..%d items/unit %.1f | producer total %.0f wait: act_ready %.0f act_empty %.0f w_empty %.0f | "
+            "mma total %.0f wait: tmem_empty %.0f act_full %.0f w_full %.0f | epi total %.0f wait tmem_full %.0f drain %.0f\n",
+            g.pair ? " 2cta" : "", np.layer0, np.layer1, (double)g.nitems / units, a[0], a[1], a[2], a[3], a[4], a[5], a[6],
+            a[7], a[8], a[9], a[10]);
+  };
+  if (g.pair) {
+    EncodeTiledFn encode = tc_encode_fn();
+    QTX_REQUIRE(encode != nullptr, QTX_ERR_CUDA, "resconv_tc: cuTensorMapEncodeTiled is unavailable");
+    CUtensorMap tmA, tmW;
+    {
+      // operand rasters as 8-byte elements: (2 * slot, plane = kstep * 4 + hi|lo * 2 + p2); box = half a plane run
+      cuuint64_t gdim[2] = {(cuuint64_t)g.slots * 2, (cuuint64_t)KS * 4};
+      cuuint64_t gstride[1] = {(cuuint64_t)g.slots * 16};
+      cuuint32_t box[2] = {(cuuint32_t)g.TSh, 1};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult cr = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, act, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      QTX_REQUIRE(cr == CUDA_SUCCESS, QTX_ERR_CUDA, "resconv_tc: cuTensorMapEncodeTiled (activations) failed (%d)", (int)cr);
+    }
+    {
+      // weight blobs: rows of 4 * Np/2 8-byte elements; one (layer, kstep, dy, half) stage = 6 rows
+      const cuuint64_t rowel = (cuuint64_t)4 * (Np / 2);
+      cuuint64_t gdim[2] = {rowel, (cuuint64_t)nl * KS * 36};
+      cuuint64_t gstride[1] = {rowel * 8};
+      cuuint32_t box[2] = {(cuuint32_t)rowel, 6};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult cr = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, wblob, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      QTX_REQUIRE(cr == CUDA_SUCCESS, QTX_ERR_CUDA, "resconv_tc: cuTensorMapEncodeTiled (weights) failed (%d)", (int)cr);
+    }
+    void (*kern)(CUtensorMap, CUtensorMap, TcNetParams) = nullptr;
+    switch (PL) {
+      case 1: kern = resconv_tc2_kernel<1>; break;
+      case 2: kern = resconv_tc2_kernel<2>; break;
+      case 3: kern = resconv_tc2_kernel<3>; break;
+      case 4: kern = resconv_tc2_kernel<4>; break;
+      case 5: kern = resconv_tc2_kernel<5>; break;
+      default: kern = resconv_tc2_kernel<6>; break;
+    }
+    QTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int npairs = num_sms() / 2;
+    if ((int64_t)npairs > g.nitems) npairs = (int)g.nitems;
+    for (int l0 = 0; l0 < nl; l0 += per_launch) {
+      np.layer0 = l0;
+      np.layer1 = l0 + per_launch < nl ? l0 + per_launch : nl;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(2 * npairs));
+      cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      QTX_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, np));
+      count_launch();
+      if (dbg) report(npairs);
+    }
+    return QTX_OK;
+  }
   void (*kern)(TcNetParams) = nullptr;
   switch (PL) {
     case 1: kern = resconv_tc_kernel<1>; break;
@@ -799,29 +1297,12 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   QTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = num_sms();
   if ((int64_t)grid > g.nitems) grid = (int)g.nitems;
-  int per_launch = nl;
-  if (const char* e = getenv("QTX_TC_LAYERS_PER_LAUNCH")) { int v = atoi(e); if (v >= 1) per_launch = v; }
-  static unsigned long long* dbg_buf = nullptr;
-  const bool dbg = getenv("QTX_TC_DEBUG") != nullptr;
-  if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 256 * 16 * sizeof(unsigned long long));
-  np.dbg = dbg ? dbg_buf : nullptr;
   for (int l0 = 0; l0 < nl; l0 += per_launch) {
     np.layer0 = l0;
     np.layer1 = l0 + per_launch < nl ? l0 + per_launch : nl;
     kern<<<grid, kTcThreads, smem, st>>>(np);
     QTX_LAUNCH_CHECK();
-    if (dbg) {
-      static unsigned long long h[256 * 16];
-      cudaStreamSynchronize(st);
-      cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-      double a[16] = {0};
-      for (int b = 0; b < grid; ++b)
-        for (int i = 0; i < 16; ++i) a[i] += (double)h[b * 16 + i] / grid;
-      fprintf(stderr,
-              "[tc dbg] layers %d..%d items/cta %.1f | producer total %.0f wait: act_ready %.0f act_empty %.0f w_empty %.0f | "
-              "mma total %.0f wait: tmem_empty %.0f act_full %.0f w_full %.0f | epi total %.0f wait tmem_full %.0f drain %.0f\n",
-              np.layer0, np.layer1, (double)g.nitems / grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
-    }
+    if (dbg) report(grid);
   }
   return QTX_OK;
 }
