@@ -359,6 +359,19 @@ int qtx_weighted_rowsum_cplx(int dtype, const void* J, int64_t ldj, int64_t j_im
  * float64: [s] = Re, [im_offset + s] = Im of (E - <E>) sqrt(rw / ns)  (sr.py:102,180-195). */
 int qtx_ebar_cplx(const double* eloc_c128, const double* rw, int64_t ns, double* ebar_stacked_out,
                   int64_t im_offset, double* stats_out, qtx_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * RBM_Conv / SingleConv (quantax/model/shallow_nets.py:129-190): one full-lattice circular
+ * convolution followed by prod cosh = a dense RBM with M = channels * N tied hidden units.
+ *   expand   : kernel [channels, lx*ly] (Conv.weight [C,1,Lx,Ly]), bias [channels] (nullable) ->
+ *              W [M, N] row-major and b [M] for the qtx_rbm_* entry points
+ *   jacobian : theta [ns, M] (qtx_rbm_forward) -> out[s, c*N + d] = sum_r tanh(theta_{c,r}) s[(r+d-lo) mod L],
+ *              out[s, channels*N + c] = sum_r tanh(theta_{c,r})  (parameter order: weight, bias)
+ * ------------------------------------------------------------------------------------------ */
+int qtx_rbm_conv_expand(int model_dtype, const void* kernel, const void* bias, int channels, int lx,
+                        int ly, void* W_out, void* b_out, qtx_stream_t stream);
+int qtx_rbm_conv_jacobian(int model_dtype, const void* theta, const int8_t* spins, int64_t ns,
+                          int channels, int lx, int ly, int out_dtype, void* out, int64_t ld,
+                          qtx_stream_t stream);
 /* out[i] = x[i] + 0i */
 int qtx_real_to_cplx(const double* x, int64_t n, double* out_c128, qtx_stream_t stream);
 

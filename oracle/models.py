@@ -300,6 +300,59 @@ class ResConv:
         return np.concatenate(cols, axis=1).astype(np.float64)
 
 
+class RBMConv:
+    """RBM_Conv / SingleConv (shallow_nets.py:129-190): psi = prod cosh(Conv(s) + b) with a full-lattice circular
+    convolution, eqx.nn.Conv(kernel_size = lattice extent, padding="SAME", padding_mode="CIRCULAR") = wrap-pad by
+    ((L-1)//2, L//2) then VALID cross-correlation.  Parameters: K [C, 1, Lx, Ly], b [C]."""
+
+    def __init__(self, K, b, shape):
+        self.K, self.b, self.shape = K, b, tuple(shape)
+        self.C = K.shape[0]
+        self.N = int(np.prod(shape))
+        self.dtype = K.dtype
+        self.nparams = K.size + b.size
+
+    @staticmethod
+    def random(shape, channels, dtype=np.float32, seed=0, scale=0.3):
+        rng = np.random.default_rng(seed)
+        K = (rng.standard_normal((channels, 1) + tuple(shape)) * scale / np.sqrt(np.prod(shape))).astype(dtype)
+        b = (0.1 * rng.standard_normal(channels)).astype(dtype)
+        return RBMConv(K, b, shape)
+
+    def params(self):
+        return np.concatenate([self.K.ravel(), self.b.ravel()])
+
+    def theta(self, s):
+        """[B, C, Lx, Ly] by the direct definition (not through the dense expansion the product uses)."""
+        x = np.asarray(s).astype(self.dtype).reshape(-1, 1, *self.shape)
+        Lx, Ly = self.shape
+        lox, loy = (Lx - 1) // 2, (Ly - 1) // 2
+        out = np.zeros((x.shape[0], self.C, Lx, Ly), dtype=self.dtype)
+        for dx in range(Lx):
+            for dy in range(Ly):
+                xs = np.roll(x[:, 0], (lox - dx, loy - dy), axis=(1, 2))  # xs[r] = x[r + d - lo]
+                out += self.K[None, :, 0, dx, dy, None, None] * xs[:, None]
+        return out + self.b.reshape(1, -1, 1, 1)
+
+    def forward(self, s):
+        th = self.theta(s).reshape(len(np.atleast_2d(s)), -1)
+        logabs = np.sum(np.log(np.cosh(th)), axis=1, dtype=self.dtype)  # LogArray(sign = 1, logabs)
+        return np.ones(th.shape[0]), logabs.astype(np.float64)
+
+    def jacobian(self, s):
+        x = np.asarray(s).astype(self.dtype).reshape(-1, 1, *self.shape)
+        t = np.tanh(self.theta(s))
+        Lx, Ly = self.shape
+        lox, loy = (Lx - 1) // 2, (Ly - 1) // 2
+        dK = np.zeros((x.shape[0], self.C, Lx, Ly), dtype=self.dtype)
+        for dx in range(Lx):
+            for dy in range(Ly):
+                xs = np.roll(x[:, 0], (lox - dx, loy - dy), axis=(1, 2))
+                dK[:, :, dx, dy] = np.einsum("bcxy,bxy->bc", t, xs)
+        db = t.sum(axis=(2, 3))
+        return np.concatenate([dK.reshape(x.shape[0], -1), db], axis=1).astype(np.float64)
+
+
 def dense_value(psi):
     mult, expo = psi
     return mult * np.exp(expo)

@@ -50,7 +50,7 @@ def philox_draws(seed, step, chain_ids):
 
 
 def mulhi32(r, n):
-    return ((r.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
+    return ((r.astype(np.uint64) * np.asarray(n).astype(np.uint64)) >> np.uint64(32)).astype(np.int64)
 
 
 def kth_hop_site(spins, hop, k):
@@ -65,7 +65,7 @@ def philox_proposal(kind, seed, step, chain_ids, spins, hop=1, max_nb=0):
     N = spins.shape[1]
     if kind == "localflip":
         return mulhi32(r0, N), None, u
-    nhop = int((spins[0] == hop).sum())
+    nhop = (spins == hop).sum(axis=1)  # per chain: a MixSampler with LocalFlip does not conserve the magnetisation
     pos = kth_hop_site(spins, hop, mulhi32(r0, nhop))
     return pos, mulhi32(r1, max_nb), u
 
@@ -169,6 +169,35 @@ def sweep(model, spins, nsweeps, kind, reweight=2.0, neighbors=None, hop=1,
         naccept += acc
     psi_final = model.final_psi(spins, psi)
     return dict(spins=spins, psi=psi_final, psi_chain=psi, naccept=naccept, accept_log=log, margin=margin)
+
+
+def mix_sweep(model, spins, choice, kinds, neighbors, hops, reweight=2.0, pos=None, slot=None, u=None, seed=None,
+              step0=0, chain0=0, record=False):
+    """MixSampler._partial_sweep (metropolis.py:411-428): step t is proposed by component ``choice[t]`` and applied to
+    all chains.  ``kinds`` / ``neighbors`` / ``hops`` are per-component lists.  Runs of equal components are one
+    ``sweep`` call (with a RefModel the cached internals are re-initialised at run boundaries, which does not change
+    the chains: psi(local update) == psi(direct), tutorials/local_updates.ipynb:189)."""
+    spins = np.array(spins, dtype=np.int8)
+    logs, t, out = [], 0, None
+    nacc = np.zeros(spins.shape[0], dtype=np.int64)
+    choice = np.asarray(choice)
+    while t < len(choice):
+        i, n = int(choice[t]), 1
+        while t + n < len(choice) and int(choice[t + n]) == i:
+            n += 1
+        sl = slice(t, t + n)
+        out = sweep(model, spins, n, kinds[i], reweight, neighbors[i], hops[i],
+                    None if pos is None else pos[sl], None if (slot is None or kinds[i] == "localflip") else slot[sl],
+                    None if u is None else u[sl], seed, step0 + t, chain0, record)
+        spins = out["spins"]
+        nacc += out["naccept"]
+        if record:
+            logs.append(out["accept_log"])
+        t += n
+    out = dict(out)
+    out["naccept"] = nacc
+    out["accept_log"] = np.concatenate(logs, axis=0) if record else None
+    return out
 
 
 def reweight_factor(psi, reweight):

@@ -79,6 +79,8 @@ SIGNATURES = {
     "qtx_weighted_rowsum_cplx": (_i32, [_i32, _vp, _i64, _i64, _vp, _i64, _i32, _i64, _vp, _i64, _i64, _vp]),
     "qtx_ebar_cplx": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "qtx_real_to_cplx": (_i32, [_vp, _i64, _vp, _vp]),
+    "qtx_rbm_conv_expand": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "qtx_rbm_conv_jacobian": (_i32, [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
 }
 
 _lib = None

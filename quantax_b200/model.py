@@ -90,6 +90,74 @@ class RBM_Dense:
         return self.params[self.M * self.N:]
 
 
+class RBM_Conv:
+    r"""psi(s) = prod cosh(Conv(s)) with one full-lattice circular convolution (quantax/model/shallow_nets.py:129-190).
+    Evaluated as a dense RBM with M = channels * N tied hidden units: ``W`` / ``b`` are the expanded weights
+    (rebuilt from the convolution kernel on every access, qtx_rbm_conv_expand), so the fused sweep / Oloc / forward
+    kernels of RBM_Dense apply; the log-derivative has its own kernel (qtx_rbm_conv_jacobian)."""
+
+    is_ref_model = True  # local updates of the equivalent dense RBM (same amplitudes as the full forward)
+    kind = "rbm"
+    tied = True
+
+    def __init__(self, channels: int, use_bias: bool = True, dtype=torch.float32, params: Optional[torch.Tensor] = None):
+        if dtype not in (torch.float32, torch.float64):
+            raise NotImplementedError("complex RBM parameters are outside the B200 hot path")
+        if not use_bias:
+            raise NotImplementedError("RBM_Conv(use_bias=False) is not implemented")
+        lattice = get_lattice()
+        if lattice.shape[0] != 1 or lattice.ndim > 2:
+            raise NotImplementedError("RBM_Conv is implemented for 1-D and 2-D lattices with one site per cell")
+        if not all(bc != 0 for bc in lattice.boundary):
+            raise NotImplementedError("open boundaries are outside the B200 hot path")
+        ext = lattice.shape[1:]
+        self.Lx, self.Ly = (1, ext[0]) if len(ext) == 1 else (ext[0], ext[1])
+        self.channels = int(channels)
+        self.N = lattice.Nsites
+        self.M = self.channels * self.N
+        self.dtype = dtype
+        self.holomorphic = False
+        if params is None:
+            rng = np.random.default_rng(get_subkeys() & 0xFFFFFFFF)
+            w = _truncated_normal(rng, (self.channels, self.N)) / np.sqrt(self.N)  # LeCun normal, fan_in = 1 * prod(kernel)
+            w *= _get_scale(self.M, lattice.Nsites)
+            params = torch.from_numpy(np.concatenate([w.ravel(), np.zeros(self.channels)]))
+        self.params = params.to(device=device(), dtype=dtype).contiguous()
+        assert self.params.numel() == self.nparams
+        self._W = torch.empty((self.M, self.N), dtype=dtype, device=self.params.device)
+        self._b = torch.empty(self.M, dtype=dtype, device=self.params.device)
+
+    @property
+    def nparams(self) -> int:
+        return self.channels * self.N + self.channels
+
+    def _expand(self):
+        from . import _lib
+
+        _lib.call("qtx_rbm_conv_expand", _lib.dtype_code(self.dtype), _lib.ptr(self.params),
+                  _lib.ptr(self.params[self.channels * self.N:]), self.channels, self.Lx, self.Ly, _lib.ptr(self._W),
+                  _lib.ptr(self._b), _lib.stream())
+
+    @property
+    def W(self) -> torch.Tensor:
+        self._expand()
+        return self._W
+
+    @property
+    def b(self) -> torch.Tensor:
+        return self._b  # filled by the W access that precedes every use
+
+    def eqx_leaf_layout(self):
+        """Conv.weight [C, 1, Lx, Ly] (chains: [C, 1, L]), Conv.bias [C, 1, 1] ([C, 1])."""
+        one_d = self.Lx == 1
+        wshape = (self.channels, 1, self.Ly) if one_d else (self.channels, 1, self.Lx, self.Ly)
+        bshape = (self.channels, 1) if one_d else (self.channels, 1, 1)
+        return [("conv.weight", 0, wshape), ("conv.bias", self.channels * self.N, bshape)]
+
+    def eqx_trailing_scalars(self):
+        return [False]
+
+
 class ResConv:
     """Deep convolutional residual network (quantax/model/conv_nets.py:95-183)."""
 

@@ -215,4 +215,83 @@ class SpinExchange(Metropolis):
         return self._neighbors, self._neighbors.shape[1], self._hopping_particle
 
 
+class MixSampler(Metropolis):
+    """A mixture of Metropolis samplers (quantax/sampler/metropolis.py:325-428): every sweep step is proposed by
+    ONE component sampler, drawn with probability proportional to its ``nsamples``, and applied to all chains.
+    Consecutive steps of the same component run as one fused sweep.  The component choice comes from a NumPy Philox
+    stream keyed on (seed, step) -- the same on every rank -- or from ``inject_choice`` (parity hook)."""
+
+    def __init__(self, samplers: Sequence[Metropolis], reweight: float = 2.0, thermal_steps: Optional[int] = None,
+                 sweep_steps: Optional[int] = None, initial_spins: Optional[torch.Tensor] = None):
+        state = samplers[0].state
+        for sampler in samplers[1:]:
+            if sampler.state is not state:
+                raise ValueError("The states of component samplers should be the same in `MixSampler`.")
+        self._samplers = tuple(samplers)
+        nsamples = np.array([sampler.nsamples for sampler in samplers])
+        total = int(nsamples.sum())
+        self._ratio = nsamples / total
+        self._choice = None
+        super().__init__(state, total, reweight, thermal_steps, sweep_steps, initial_spins)
+
+    @property
+    def nflips(self) -> Optional[int]:
+        nflips = tuple(sampler.nflips for sampler in self._samplers)
+        return None if None in nflips else max(nflips)
+
+    def reset(self) -> None:
+        """metropolis.py:364-375: the first reset concatenates the (thermalised) chains of the components."""
+        if hasattr(self, "_spins") or self._initial_spins is not None:
+            super().reset()
+            return
+        self._spins = torch.cat([spl._spins for spl in self._samplers], dim=0).contiguous()
+        if self._thermal_steps > 0:
+            self.sweep(self._thermal_steps)
+
+    def inject_choice(self, idx) -> None:
+        """Parity hook: component index of every step of the NEXT sweep."""
+        self._choice = np.asarray(idx, dtype=np.int64)
+
+    def _draw_choice(self, nsweeps: int) -> np.ndarray:
+        rng = np.random.Generator(np.random.Philox(key=int(self._seed) & 0xFFFFFFFFFFFFFFFF, counter=int(self._step)))
+        return rng.choice(len(self._samplers), size=nsweeps, p=self._ratio)
+
+    def sweep(self, nsweeps: Optional[int] = None, record: bool = False) -> Samples:
+        if nsweeps is None:
+            nsweeps = self._sweep_steps
+        choice, self._choice = self._choice, None
+        if choice is None:
+            choice = self._draw_choice(nsweeps)
+        if len(choice) != nsweeps:
+            raise ValueError("inject_choice needs one component index per sweep step")
+        injected, self._injected = self._injected, None
+        state = self._state
+        logs, nacc_tot, psi, psi_chain = [], None, None, None
+        t = 0
+        while t < nsweeps:
+            i = int(choice[t])
+            n = 1
+            while t + n < nsweeps and int(choice[t + n]) == i:
+                n += 1
+            spl = self._samplers[i]
+            nbr, max_nb, hop = spl._proposal_tables()
+            inj = None
+            if injected is not None:
+                pos, slot, u = injected
+                inj = (pos[t:t + n], None if (slot is None or spl._kind == _lib.QTX_LOCAL_FLIP) else slot[t:t + n],
+                       u[t:t + n])
+            psi, psi_chain, nacc, log = state.fused_sweep(self._spins, n, spl._kind, nbr, max_nb, hop, self._reweight,
+                                                           self._seed, self._step, self._rank * self._nlocal, inj, record)
+            self._step += n
+            nacc_tot = nacc if nacc_tot is None else nacc_tot + nacc
+            if record:
+                logs.append(log)
+            t += n
+        if psi is None:  # nsweeps == 0
+            psi = psi_chain = state(self._spins)
+        self.last_accept_log = torch.cat(logs, dim=0) if record and logs else None
+        self.last_naccept, self.last_psi_chain = nacc_tot, psi_chain
+        return Samples(self._spins.clone(), psi, None, self._get_reweight_factor(psi))
+
+
 NeighborExchange = SpinExchange  # pre-0.2 name (docs/.doctrees/sampler/quantax.sampler.NeighborExchange)

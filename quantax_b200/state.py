@@ -264,7 +264,7 @@ class Variational(State):
             out = torch.empty((ns, m.nparams), dtype=odt, device=s.device)
         if not self._symm.is_identity:
             self._projected_jacobian(s, out)
-        elif m.kind == "rbm":
+        elif m.kind == "rbm" and not getattr(m, "tied", False):
             _lib.call("qtx_rbm_jacobian", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), ns,
                       _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), _lib.ptr(col_mean),
                       _lib.ptr(row_scale), _lib.ptr(tanh_table), _lib.stream())
@@ -292,7 +292,14 @@ class Variational(State):
 
     def _model_jacobian(self, s: torch.Tensor, out: torch.Tensor) -> None:
         m = self._model
-        if m.kind == "rbm":
+        if m.kind == "rbm" and getattr(m, "tied", False):
+            # RBM_Conv: theta of the equivalent dense RBM, then the tied-weight contraction (shallow_nets.py:129-173)
+            theta = torch.empty((s.shape[0], m.M), dtype=m.dtype, device=s.device)
+            _lib.call("qtx_rbm_forward", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), s.shape[0],
+                      _lib.ptr(theta), None, _lib.stream())
+            _lib.call("qtx_rbm_conv_jacobian", self._mdt(), _lib.ptr(theta), _lib.ptr(s), s.shape[0], m.channels, m.Lx,
+                      m.Ly, _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), _lib.stream())
+        elif m.kind == "rbm":
             _lib.call("qtx_rbm_jacobian", self._mdt(), _lib.ptr(m.W), _lib.ptr(m.b), m.N, m.M, _lib.ptr(s), s.shape[0],
                       _lib.dtype_code(out.dtype), _lib.ptr2d(out), out.stride(0), None, None, None, _lib.stream())
         else:
@@ -334,7 +341,7 @@ class Variational(State):
         returns tanh(theta) [ns, M], which ``jacobian(..., tanh_table=)`` reuses so that the centred rows are
         bitwise consistent with these means."""
         m = self._model
-        if m.kind != "rbm" or not self._symm.is_identity:
+        if m.kind != "rbm" or getattr(m, "tied", False) or not self._symm.is_identity:
             return (None, None) if return_table else None
         s = self._spins(fock_states)
         ns = s.shape[0]

@@ -258,3 +258,86 @@ def test_jacobian_odd_site_count_and_wide_rows(qtx):
         Oo = net.jacobian(s)
         assert np.abs(to_np(state.jacobian(st)) - Oo).max() <= 1e-5
         assert np.abs(to_np(state.jacobian_colmean(st)) - Oo.mean(axis=0)).max() <= 1e-5
+
+
+def test_mix_sampler_matches_oracle(qtx):
+    """MixSampler (quantax/sampler/metropolis.py:325-428, tutorials/samples.ipynb): a LocalFlip + SpinExchange mixture;
+    with injected component choices and randoms the accept pattern and the chains equal the oracle's bit for bit,
+    and the production streams reproduce the oracle's restatement."""
+    lat, olat = lattice_pair(qtx, "square", 4, (8, 8))
+    model, net = make_rbm(qtx, 16, 24, torch.float64, seed=51)
+    state = qtx.state.Variational(model)
+    a = qtx.sampler.LocalFlip(state, 24, thermal_steps=0)
+    b = qtx.sampler.SpinExchange(state, 40, thermal_steps=0)
+    mix = qtx.sampler.MixSampler([a, b], thermal_steps=0)
+    assert mix.nsamples == 64 and mix.nflips == 2
+    with pytest.raises(ValueError):
+        qtx.sampler.MixSampler([a, qtx.sampler.LocalFlip(qtx.state.Variational(model), 8, thermal_steps=0)])
+    spins0 = to_np(mix._spins).copy()
+    assert np.array_equal(spins0, np.concatenate([to_np(a._spins), to_np(b._spins)]))
+    T, ns = 37, 64
+    rng = np.random.default_rng(52)
+    table = osites.site_neighbor_table(olat)
+    choice = rng.integers(0, 2, size=T)
+    u = rng.random((T, ns)); pos = rng.integers(0, 16, size=(T, ns)); slot = rng.integers(0, 4, size=(T, ns))
+    mix.inject_choice(choice)
+    mix.inject(torch.from_numpy(pos), torch.from_numpy(u), torch.from_numpy(slot))
+    samples = mix.sweep(T, record=True)
+    ref = osmp.mix_sweep(osmp.RBMChainModel(net), spins0, choice, ["localflip", "exchange"], [None, table], [1, 1],
+                         pos=pos, slot=slot, u=u, record=True)
+    assert np.array_equal(to_np(mix.last_accept_log), ref["accept_log"])
+    assert np.array_equal(to_np(samples.spins), ref["spins"])
+    assert np.array_equal(to_np(mix.last_naccept), ref["naccept"])
+    # production streams: component choice from the sampler's NumPy Philox stream, proposals from the device Philox
+    spins1 = to_np(mix._spins).copy()
+    choice2 = mix._draw_choice(20)
+    samples2 = mix.sweep(20)
+    ref2 = osmp.mix_sweep(osmp.RBMChainModel(net), spins1, choice2, ["localflip", "exchange"], [None, table], [1, 1],
+                          seed=mix._seed, step0=T)
+    assert np.array_equal(to_np(samples2.spins), ref2["spins"])
+    assert abs(np.mean(choice2) - 40 / 64) < 0.35
+
+
+@pytest.mark.parametrize("kind,L,shape,nup", [("square", 4, (4, 4), (8, 8)), ("chain", 10, (1, 10), (5, 5))])
+def test_rbm_conv_matches_oracle(qtx, kind, L, shape, nup, tmp_path):
+    """RBM_Conv (quantax/model/shallow_nets.py:129-190, the model of examples/RBM.ipynb): full-lattice circular
+    convolution + prod cosh, evaluated through the equivalent tied dense RBM.  Forward, log-derivatives, an exchange
+    sweep with injected randoms (against the oracle's FULL-forward Metropolis: the reference has no local updates for
+    this model), Oloc and the SR step."""
+    lat, olat = lattice_pair(qtx, kind, L, nup)
+    N = shape[0] * shape[1]
+    net = omodels.RBMConv.random(shape, 3, np.float64, seed=61)
+    model = qtx.model.RBM_Conv(3, dtype=torch.float64, params=torch.from_numpy(net.params().copy()))
+    assert model.nparams == net.nparams == 3 * N + 3
+    state = qtx.state.Variational(model)
+    s = osmp.rand_states(21, N, nup[0], seed=62)
+    psi = state(torch.from_numpy(s))
+    assert np.allclose(to_np(psi.logabs), net.forward(s)[1], rtol=1e-12, atol=1e-12)
+    O = to_np(state.jacobian(torch.from_numpy(s)))
+    assert np.abs(O - net.jacobian(s)).max() <= 1e-11 * np.abs(net.jacobian(s)).max()
+    ns, T = 32, 30
+    sampler = qtx.sampler.SpinExchange(state, ns, thermal_steps=0)
+    spins0 = to_np(sampler._spins).copy()
+    rng = np.random.default_rng(63)
+    table = osites.site_neighbor_table(olat)
+    u = rng.random((T, ns)); pos = rng.integers(0, N, size=(T, ns)); slot = rng.integers(0, table.shape[1], size=(T, ns))
+    sampler.inject(torch.from_numpy(pos), torch.from_numpy(u), torch.from_numpy(slot))
+    samples = sampler.sweep(T, record=True)
+    ref = osmp.sweep(osmp.FullForwardChainModel(net), spins0, T, "exchange", neighbors=table, pos=pos, slot=slot, u=u,
+                     record=True)
+    assert np.array_equal(to_np(sampler.last_accept_log), ref["accept_log"])
+    assert np.array_equal(to_np(samples.spins), ref["spins"])
+    H = qtx.operator.Heisenberg(msr=(kind == "square"))
+    aol = oop.to_array_op_list(oop.heisenberg_op_list(olat, msr=(kind == "square")))
+    sc = ref["spins"]
+    Eo = oop.oloc(aol, net.forward, sc)
+    opt = qtx.optimizer.SR(state, H)
+    step = to_np(opt.get_step(samples))
+    assert np.abs(to_np(opt._Eloc) - Eo).max() <= 1e-10 * np.abs(Eo).max()
+    xo, eo, vo = osolver.sr_step(net.jacobian(sc), Eo, np.ones(ns))
+    assert abs(opt.energy - eo) <= 1e-10 * abs(eo)
+    assert np.linalg.norm(step - xo) <= 1e-5 * np.linalg.norm(xo)
+    f = tmp_path / "rbmconv.eqx"
+    state.save(f)
+    state2 = qtx.state.Variational(qtx.model.RBM_Conv(3, dtype=torch.float64), param_file=f)
+    assert torch.equal(state2.get_params_flatten(), state.get_params_flatten())
