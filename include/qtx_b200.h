@@ -302,6 +302,8 @@ int qtx_apply_update(int model_dtype, void* params, const double* step, double l
  *   fourth_root    out <- (v / corr)^(1/4) + eps
  *   scale_columns  A[s, k] <- A[s, k] / d[k]     (Obar /= V[None, :], sr.py:304,409) */
 int qtx_axpby(int64_t n, double a, const double* x, double b, double* y, qtx_stream_t stream);
+/* S[i, j] += alpha x[i] x[j], S float64 [n, n]  (TimeEvol, quantax/optimizer/time_evol.py:113-114) */
+int qtx_rank1_update(int64_t n, double alpha, const double* x, double* S, qtx_stream_t stream);
 int qtx_div_add(int64_t n, const double* x, const double* d, double c, const double* z, double* out,
                 qtx_stream_t stream);
 int qtx_second_moment(int64_t n, double beta, const double* x, const double* y, double* V,

@@ -106,6 +106,38 @@ def sr_step(Omat, Eloc, rw, rtol=None, atol=0.0, real_to_complex=False):
     return auto_pinv_eig(ob, eb, rtol, atol), energy, var
 
 
+def pinvh_solve(H, b, rtol=None, atol=0.0):
+    """solver.py:104-111."""
+    vals, U = np.linalg.eigh(H)
+    return U @ (eigs_inv(vals, rtol, atol) * (U.conj().T @ b))
+
+
+def time_evol_step(Omat, Eloc, max_parallel=None, rtol=None, atol=0.0):
+    """TimeEvol.get_step (optimizer/time_evol.py:55-134) for real parameters / complex output
+    (VS_TYPE.real_to_complex): S = Re(Obar^+ Obar), F = -Im(Obar^+ Ebar), step = pinvh(S) F.
+    ``max_parallel``: the chunked accumulation of time_evol.py:76-115 (un-centred sums, corrected at the end)."""
+    ns = Eloc.shape[0]
+    if max_parallel is None or ns <= max_parallel:
+        eb, energy, var = ebar(Eloc, np.ones(ns))
+        ob, _ = obar(Omat, np.ones(ns))
+        S, F = ob.conj().T @ ob, ob.conj().T @ eb
+    else:
+        Emean = np.mean(Eloc)
+        energy, var = float(Emean.real), float(np.mean(np.abs(Eloc - Emean) ** 2))
+        S = np.zeros((Omat.shape[1],) * 2, dtype=complex)
+        F = np.zeros(Omat.shape[1], dtype=complex)
+        Om = np.zeros(Omat.shape[1], dtype=complex)
+        for lo in range(0, ns, max_parallel):
+            O, e = Omat[lo:lo + max_parallel], Eloc[lo:lo + max_parallel]
+            Om += O.sum(axis=0)
+            S += O.conj().T @ O
+            F += O.conj().T @ e
+        S, F, Om = S / ns, F / ns, Om / ns
+        S = S - np.outer(Om.conj(), Om)
+        F = F - Om.conj() * Emean
+    return pinvh_solve(S.real, -F.imag, rtol, atol), energy, var, S.real, -F.imag
+
+
 def update_params(params, step):
     """variational.py:570-579."""
     if not np.all(np.isfinite(step)):

@@ -62,6 +62,7 @@ SIGNATURES = {
     "qtx_matvec_t": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "qtx_matvec": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "qtx_axpby": (_i32, [_i64, _f64, _vp, _f64, _vp, _vp]),
+    "qtx_rank1_update": (_i32, [_i64, _f64, _vp, _vp, _vp]),
     "qtx_div_add": (_i32, [_i64, _vp, _vp, _f64, _vp, _vp, _vp]),
     "qtx_second_moment": (_i32, [_i64, _f64, _vp, _vp, _vp, _vp]),
     "qtx_fourth_root": (_i32, [_i64, _vp, _f64, _f64, _vp, _vp]),

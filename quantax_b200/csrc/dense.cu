@@ -131,6 +131,13 @@ __global__ void apply_update_kernel(T* __restrict__ params, const double* __rest
 }
 
 
+// S[i, j] += alpha * x[i] * x[j]   (TimeEvol: S - outer(conj(Omean), Omean), quantax/optimizer/time_evol.py:113)
+__global__ void rank1_update_kernel(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ S) {
+  const int64_t total = n * n;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    S[e] += alpha * x[e / n] * x[e % n];
+}
+
 // ---- vector helpers of the momentum optimizers (SPRING / MARCH / AdamSR, quantax/optimizer/sr.py:198-429) ----
 __global__ void axpby_kernel(int64_t n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
@@ -260,6 +267,14 @@ static unsigned vec_grid(int64_t n) {
   unsigned g = (unsigned)((n + 255) / 256);
   unsigned cap = 8u * (unsigned)num_sms();
   return g > cap ? cap : (g ? g : 1);
+}
+
+extern "C" int qtx_rank1_update(int64_t n, double alpha, const double* x, double* S, qtx_stream_t stream) {
+  if (n == 0) return QTX_OK;
+  QTX_REQUIRE(x && S && n > 0, QTX_ERR_INVALID, "qtx_rank1_update: bad argument");
+  rank1_update_kernel<<<vec_grid(n * n), 256, 0, (cudaStream_t)stream>>>(n, alpha, x, S);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
 }
 
 extern "C" int qtx_axpby(int64_t n, double a, const double* x, double b, double* y, qtx_stream_t stream) {

@@ -761,8 +761,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     for (int i = 0; i < p.w_stages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 2 * kEpiWarps);
-    mbar_init(act_ready + 0, 2 * kEpiWarps);
-    mbar_init(act_ready + 1, 2 * kEpiWarps);
+    mbar_init(act_ready + 0, 2);  // one signalling thread per CTA
+    mbar_init(act_ready + 1, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tc2_tmem_alloc(tmem_holder, 512);
@@ -997,11 +997,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           };
           if (L.planar) run(std::true_type{});
           else run(std::false_type{});
-          // the next layer's TMA loads (either CTA) must see these stores: proxy fence by every writer, warp
-          // barrier (orders the lanes' stores before lane 0), then cluster-scope release arrives on both CTAs
+          // the next layer's TMA loads (either CTA) must see these stores: proxy fence by every writer, a named
+          // barrier over the epilogue warps (orders all their stores before the signalling thread), then ONE thread
+          // pays the cluster-scope release (it waits for the stores to be performed) while the other warps move on
           fence_proxy_async_global();
-          __syncwarp();
-          if (lane == 0) {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (warp == 2 && lane == 0) {
             tc2_arrive_remote(ready_addr[j][0]);
             tc2_arrive_remote(ready_addr[j][1]);
           }

@@ -214,8 +214,8 @@ class QNGD:
     """Quantum natural gradient descent base class (sr.py:17-128)."""
 
     def __init__(self, state: Variational, imag_time: bool = True, solver: Optional[Callable] = None):
-        if not imag_time:
-            raise NotImplementedError("real-time evolution needs a complex default dtype (outside the hot path)")
+        if not imag_time and state.vs_type != VS_TYPE.real_to_complex:
+            raise NotImplementedError("real-time evolution needs a complex-output state (set_default_dtype(complex128))")
         self._state = state
         self._imag_time = imag_time
         self._solver = auto_pinv_eig() if solver is None else solver
@@ -370,6 +370,176 @@ class SR(QNGD):
         self._stats = stats
         self._Eloc = Eloc
         return ebar[rank * nl:(rank + 1) * nl].contiguous() if P > 1 else ebar
+
+
+def pinvh_solve(rtol: Optional[float] = None, atol: float = 0.0):
+    """x = H^+ b for a Hermitian H through eigh and the soft cut-off (solver.py:104-111)."""
+    return minsr_pinv_eig(rtol, atol)
+
+
+def _axpby(a: float, x: torch.Tensor, b: float, y: torch.Tensor) -> torch.Tensor:
+    """y <- a x + b y on float64 device vectors (qtx_axpby)."""
+    _lib.call("qtx_axpby", x.numel(), float(a), _lib.ptr(x.contiguous()), float(b), _lib.ptr(y), _lib.stream())
+    return y
+
+
+class TimeEvol(SR):
+    r"""Real-time evolution (TDVP), quantax/optimizer/time_evol.py:26-134, for states with real parameters and complex
+    output (VS_TYPE.real_to_complex): S = Re(Obar^+ Obar) and F = -Im(Obar^+ Ebar) (time_evol.py:121-122) are
+    A^T A and A^T b of the stacked real matrix A = [Re Obar; Im Obar] with b = [-Im Ebar; Re Ebar].  Assumes more
+    samples than parameters.  With ``max_parallel`` (the state's backward chunk) smaller than the sample count S and
+    F are accumulated chunk by chunk from un-centred Jacobians (time_evol.py:76-115)."""
+
+    def __init__(self, state: Variational, hamiltonian, solver: Optional[Callable] = None):
+        super().__init__(state, hamiltonian, imag_time=False, solver=pinvh_solve() if solver is None else solver)
+        self._max_parallel = state.backward_chunk
+
+    def _stats_ebar(self, samples):
+        """Stacked Ebar [Re; Im] of the GLOBAL samples' statistics, local rows (SR.get_Ebar)."""
+        return self.get_Ebar(samples)
+
+    def get_SF(self, samples):
+        """(S float64 [Np, Np], F float64 [Np]) with F = -Im(Obar^+ Ebar) already taken."""
+        rank, P = world()
+        nl = samples.nsamples
+        np_ = self._state.nparams
+        if self._max_parallel is None or nl <= self._max_parallel:
+            eb = self.get_Ebar(samples)          # [Re; Im], centred and scaled by sqrt(1/Ns)
+            A = self.get_Obar(samples)           # [Re Obar; Im Obar]
+            b = torch.cat([-eb[nl:], eb[:nl]])
+            S = gram(A.t().contiguous())
+            F = matvec_t(A, b)
+        else:
+            # chunked: S = sum_c O_c^+ O_c / Ns - outer(conj(Om), Om),  F = sum_c O_c^+ E_c / Ns - conj(Om) <E>
+            Eloc = self._hamiltonian.Oloc(self._state, samples).to(torch.complex128).contiguous()
+            ns_glob = nl * P
+            stats = torch.empty(2, dtype=torch.float64, device=Eloc.device)
+            Eg = Eloc
+            if P > 1:
+                Eg = torch.empty(ns_glob, dtype=torch.complex128, device=Eloc.device)
+                _dist().all_gather_into_tensor(torch.view_as_real(Eg), torch.view_as_real(Eloc))
+            _lib.call("qtx_ebar_cplx", _lib.ptr(Eg), None, ns_glob, None, ns_glob, _lib.ptr(stats), _lib.stream())
+            self._stats, self._Eloc = stats, Eg
+            S = torch.zeros((np_, np_), dtype=torch.float64, device=Eloc.device)
+            F = torch.zeros(np_, dtype=torch.float64, device=Eloc.device)
+            msum = torch.zeros((2, np_), dtype=torch.float64, device=Eloc.device)  # sum Re O, sum Im O
+            er = torch.view_as_real(Eloc)
+            for lo in range(0, nl, self._max_parallel):
+                hi = min(nl, lo + self._max_parallel)
+                n = hi - lo
+                A = self._state.jacobian_stacked(samples.spins[lo:hi])  # [2 n, Np]
+                gram(A.t().contiguous(), out=S, accumulate=True)
+                b = torch.cat([-er[lo:hi, 1], er[lo:hi, 0]]).contiguous()
+                _lib.call("qtx_matvec_t", _lib.dtype_code(A.dtype), _lib.ptr2d(A), 2 * n, np_, A.stride(0), _lib.ptr(b),
+                          _lib.ptr(F), 1, _lib.stream())
+                ones = torch.ones(n, dtype=torch.float64, device=A.device)
+                for k in range(2):
+                    _lib.call("qtx_matvec_t", _lib.dtype_code(A.dtype), _lib.ptr2d(A[k * n:(k + 1) * n]), n, np_,
+                              A.stride(0), _lib.ptr(ones), _lib.ptr(msum[k]), 1, _lib.stream())
+            if P > 1:
+                _dist().all_reduce(S)
+                _dist().all_reduce(F)
+                _dist().all_reduce(msum)
+            S /= ns_glob
+            F /= ns_glob
+            msum /= ns_glob
+            self._Omean = [msum[0], msum[1]]
+            for k in range(2):  # Re outer(conj(Om), Om) = mr mr^T + mi mi^T
+                _lib.call("qtx_rank1_update", np_, -1.0, _lib.ptr(msum[k]), _lib.ptr(S), _lib.stream())
+            # -Im(conj(Om) <E>) = -(mr Ei - mi Er): F holds -Im(sum O^+ E)/Ns already
+            Em = torch.view_as_real(Eg).mean(dim=0)
+            _axpby(float(Em[1]), msum[0], 1.0, F)
+            _axpby(-float(Em[0]), msum[1], 1.0, F)
+            return S, F
+        if P > 1:
+            _dist().all_reduce(S)
+            _dist().all_reduce(F)
+        return S, F
+
+    def solve(self, Smat: torch.Tensor, Fvec: torch.Tensor) -> torch.Tensor:
+        ev = self._tic("solve")
+        step = self._solver(Smat, Fvec)
+        self._toc(ev)
+        return step.to(get_real_dtype())
+
+    def get_step(self, samples, **kw) -> torch.Tensor:
+        if not torch.allclose(samples.reweight_factor, torch.ones_like(samples.reweight_factor)):
+            raise ValueError("TimeEvol is only for non-reweighted samples")
+        Smat, Fvec = self.get_SF(samples)
+        return self.solve(Smat, Fvec)
+
+
+class Driver:
+    """quantax/optimizer/driver.py:10-29."""
+
+    def __init__(self, state, sampler, optimizer, step_length: float):
+        from .utils import DataTracer
+
+        self._state, self._sampler, self._optimizer = state, sampler, optimizer
+        self._step_length = step_length
+        self._time = 0.0
+        self.energy = DataTracer()
+        self.VarE = DataTracer()
+
+    def step(self) -> None:
+        raise NotImplementedError
+
+
+class Euler(Driver):
+    """First order Euler driver (driver.py:32-41)."""
+
+    def step(self) -> None:
+        samples = self._sampler.sweep()
+        step = self._optimizer.get_step(samples)
+        self._state.update(step * self._step_length)
+        self._time += self._step_length
+        self.energy.append(self._optimizer.energy, self._time)
+        self.VarE.append(self._optimizer.VarE, self._time)
+
+
+class AdaptiveHeunEvolution(Driver):
+    """Adaptive second order Heun driver for unitary time evolution (driver.py:44-102)."""
+
+    def __init__(self, state, sampler, tdvp: TimeEvol, step_length: float = 1e-3, integ_threshold: float = 1e-3):
+        from .utils import DataTracer
+
+        super().__init__(state, sampler, tdvp, step_length)
+        self._integ_threshold = integ_threshold
+        self.step_size = DataTracer()
+
+    def step(self) -> None:
+        import numpy as np
+
+        tdvp, dt, st, spl = self._optimizer, self._step_length, self._state, self._sampler
+
+        def comb(pairs):  # sum_i a_i x_i on the device
+            acc = torch.zeros_like(pairs[0][1])
+            for a, x in pairs:
+                _axpby(a, x, 1.0, acc)
+            return acc
+
+        stepi = tdvp.get_step(spl.sweep())
+        st.update(stepi, lr=dt)
+        stepf = tdvp.get_step(spl.sweep())
+        step1 = comb([(0.5, stepi), (0.5, stepf)])
+        st.update(stepi, lr=-dt / 2)
+        stepm = tdvp.get_step(spl.sweep())
+        st.update(comb([(1.0, stepm), (-1.0, stepi)]), lr=dt / 4)
+        stepmm = tdvp.get_step(spl.sweep())
+        st.update(stepmm, lr=dt / 2)
+        Smat, Fvec = tdvp.get_SF(spl.sweep())
+        stepff = tdvp.solve(Smat, Fvec)
+        st.update(comb([(1.0, stepff), (-1.0, stepmm)]), lr=dt / 4)
+        step2 = comb([(0.25, stepi), (0.25, stepm), (0.25, stepmm), (0.25, stepff)])
+        diff = comb([(1.0, step1), (-1.0, step2)])
+        new_err = float(np.sqrt(max(float(torch.dot(diff, matvec(Smat, diff))), 0.0))) * dt
+        ratio = np.clip((self._integ_threshold / max(new_err, 1e-300)) ** (1 / 3), 0.2, 2)
+        new_step_length = float(np.clip(dt * ratio, 1e-4, 1e-2))
+        self._time += new_step_length
+        self._step_length = new_step_length
+        self.step_size.append(new_step_length, self._time)
+        self.energy.append(tdvp.energy, self._time)
+        self.VarE.append(tdvp.VarE, self._time)
 
 
 class MinSR(SR):

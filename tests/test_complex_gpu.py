@@ -149,3 +149,41 @@ def test_complex_projected_state(qtx):
     Oo = osym.projected_jacobian(osymm, net.forward, net.jacobian, s)
     amp = (scale / np.abs(b)).max()  # cancellation factor of the projection
     assert np.abs(O - Oo).max() <= 1e-6 * amp * max(1.0, np.abs(Oo).max()), (np.abs(O - Oo).max(), amp)
+
+
+def test_time_evol_step_and_heun_driver(qtx):
+    """TimeEvol (quantax/optimizer/time_evol.py:26-134) for the complex state: S = Re(Obar^+ Obar), F = -Im(Obar^+ Ebar),
+    direct and chunked accumulation, against the oracle; then one adaptive Heun step (driver.py:44-102) runs and
+    keeps the parameters finite."""
+    lat, olat = lattice_pair(qtx, "triangular", 6, (18, 18))
+    model, net = make_model(qtx, 6, 1, 2, torch.float64, "exp", seed=8, phase=False)
+    ns = 160
+    assert ns > model.nparams
+    s = osmp.rand_states(ns, 36, 18, seed=9)
+    H = qtx.operator.Heisenberg()
+    aol = oop.to_array_op_list(oop.heisenberg_op_list(olat))
+    Eo = oop.oloc(aol, net.forward, s)
+    Oo = net.jacobian(s)
+    for mp in (None, 48):
+        state = qtx.state.Variational(model, max_parallel=(4096, mp) if mp else None)
+        st = torch.from_numpy(s).cuda()
+        samples = qtx.sampler.Samples(st, state(st), None, torch.ones(ns, dtype=torch.float64, device="cuda"))
+        tdvp = qtx.optimizer.TimeEvol(state, H)
+        S, F = tdvp.get_SF(samples)
+        xo, eo, vo, So, Fo = osolver.time_evol_step(Oo, Eo, max_parallel=mp)
+        assert np.abs(to_np(S) - So).max() <= 1e-10 * np.abs(So).max()
+        assert np.abs(to_np(F) - Fo).max() <= 1e-10 * np.abs(Fo).max()
+        assert abs(tdvp.energy - eo) <= 1e-10 * abs(eo) and abs(tdvp.VarE - vo) <= 1e-9 * abs(vo)
+        step = to_np(tdvp.get_step(samples))
+        assert np.linalg.norm(step - xo) <= 1e-6 * np.linalg.norm(xo)
+    with pytest.raises(ValueError):
+        bad = qtx.sampler.Samples(st, state(st), None, torch.full((ns,), 2.0, dtype=torch.float64, device="cuda"))
+        tdvp.get_step(bad)
+    state = qtx.state.Variational(model)
+    sampler = qtx.sampler.SpinExchange(state, 256, thermal_steps=20)
+    drv = qtx.optimizer.AdaptiveHeunEvolution(state, sampler, qtx.optimizer.TimeEvol(state, H), step_length=1e-3)
+    p0 = to_np(state.get_params_flatten()).copy()
+    drv.step()
+    p1 = to_np(state.get_params_flatten())
+    assert np.all(np.isfinite(p1)) and not np.array_equal(p0, p1)
+    assert 1e-4 <= drv._step_length <= 1e-2 and len(drv.energy) == 1
