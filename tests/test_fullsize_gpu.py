@@ -81,3 +81,34 @@ def test_resconv_translation_invariance_full_size(qtx, L, C, nb, ns):
         Ja, Jb = state.jacobian(s[:16]), state.jacobian(shifted[:16])
         assert (Ja - Jb).abs().max().item() < 1e-3 * Ja.abs().max().item()
         assert Ja.shape == (16, model.nparams)
+
+
+def test_config_e_slice_tensor_core_tower(qtx, monkeypatch):
+    """Config E network (16x16, ResConv 8 blocks x 88 channels, sinh+1, 1 047 552 parameters) on one GPU's 2048 chains:
+    the CTA-pair tensor-core tower, the single-CTA tower and (on a subset) the float64 model agree within the float32
+    bar; a short exchange sweep conserves Sz and carries the same psi as a direct forward of the final chains."""
+    qtx.set_random_seed(13)
+    qtx.sites.Sites._SITES = None
+    qtx.sites.Square(16, Nparticles=(128, 128))
+    model = qtx.model.ResConv(8, 88, 3, final_activation=qtx.nn.sinhp1_by_scale)
+    assert model.nparams == 1047552
+    state = qtx.state.Variational(model)
+    s = qtx.utils.rand_states(2048)
+    lg = lambda psi: torch.log(psi.significand.abs()) + psi.exponent
+    a = state(s)
+    monkeypatch.setenv("QTX_TC_2CTA", "0")
+    b = state(s)
+    monkeypatch.delenv("QTX_TC_2CTA")
+    assert bool(torch.isfinite(lg(a)).all())
+    assert (lg(a) - lg(b)).abs().max().item() < 2e-6  # same arithmetic, different tiling
+    assert bool((torch.sign(a.significand) == torch.sign(b.significand)).all())
+    m64 = qtx.model.ResConv(8, 88, 3, final_activation=qtx.nn.sinhp1_by_scale, dtype=torch.float64,
+                            params=model.params.double())
+    c = qtx.state.Variational(m64)(s[:48])
+    assert (lg(a)[:48] - lg(c)).abs().max().item() < 1e-5 * max(1.0, lg(c).abs().max().item())
+    sampler = qtx.sampler.SpinExchange(state, nsamples=2048, thermal_steps=0, initial_spins=s)
+    samples = sampler.sweep(8)
+    assert bool((samples.spins.sum(dim=1) == 0).all())
+    direct = state(samples.spins)
+    assert (lg(samples.psi) - lg(direct)).abs().max().item() < 1e-6
+    assert 0 < int(sampler.last_naccept.sum().item()) < 8 * 2048
