@@ -301,7 +301,7 @@ def run_b200(args):
         # lower-triangular tiles, so its tensor-pipe work is pairs * Ns(Ns+1) * Np int8 op.
         from quantax_b200.optimizer import DEFAULT_NSLICES as _S
 
-        s_eff = 8 if _S == 0 else _S
+        s_eff = 7 if _S == 0 else _S
         pairs = s_eff * (s_eff + 1) // 2 if s_eff > 0 else 0
         gram_flops = 2.0 * ns_g * ns_g * np_g
         ach = gram_flops / (gram_ms * 1e-3) / 1e12

@@ -16,7 +16,7 @@ def _rel_err(T, A):
 
 
 @pytest.mark.parametrize("ns,npar", [(128, 64), (100, 333), (257, 1000), (1, 7), (130, 4099), (64, 70001)])
-@pytest.mark.parametrize("nslices,tol", [(8, 2e-13), (0, 2e-13), (7, 1e-11), (4, 2e-6), (2, 5e-2)])
+@pytest.mark.parametrize("nslices,tol", [(8, 2e-13), (0, 2e-12), (7, 1e-11), (4, 2e-6), (2, 5e-2)])
 def test_gram_tc_f64(ns, npar, nslices, tol):
     from quantax_b200.optimizer import gram
 
