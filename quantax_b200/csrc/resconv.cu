@@ -446,16 +446,28 @@ __global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict_
   const T em = exp(-m);
   // thread owns positions r = tid, tid+blockDim, ...: channel mean first, then the sum over positions
   T part = 0, tot = 0;
-  for (int r = tid; r < N; r += blockDim.x) {
-    T a = 0;
-    for (int c = 0; c < C; ++c) {
-      T z = at(c, r) * inv_norm;
+  if (planes > 0) {
+    // planar stream: sum_r mean_c sig = (sum over all valid elements) / C, read contiguously
+    for (int e = tid; e < planes * N * 8; e += blockDim.x) {
+      if (((e / (N * 8)) * 8 + (e & 7)) >= C) continue;
+      T z = xs[e] * inv_norm;
       T sg = exp(z - m);
       if (final_act == 1) sg = (sg - exp(-z - m)) / T(2) + em;
-      a += sg;
+      tot += sg;
     }
-    tot += a;
-    part += a / (T)C;
+    part = tot / (T)C;
+  } else {
+    for (int r = tid; r < N; r += blockDim.x) {
+      T a = 0;
+      for (int c = 0; c < C; ++c) {
+        T z = at(c, r) * inv_norm;
+        T sg = exp(z - m);
+        if (final_act == 1) sg = (sg - exp(-z - m)) / T(2) + em;
+        a += sg;
+      }
+      tot += a;
+      part += a / (T)C;
+    }
   }
   __syncthreads();
   T p1 = warp_sum(part), p2 = warp_sum(tot);
@@ -853,7 +865,9 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
     QTX_LAUNCH_CHECK();
     return QTX_OK;
   };
-  {
+  bool tc_path = false;
+  if constexpr (std::is_same<T, float>::value) tc_path = resconv_tc_supported(C, sh.lx, sh.ly, sh.kh, sh.kw);
+  if (grad || !tc_path) {  // x0 feeds the CUDA-core first layer and the backward pass
     int64_t n = ns * N;
     unsigned g = (unsigned)((n + 255) / 256);
     if (g > 8u * num_sms()) g = 8u * num_sms();

@@ -22,7 +22,9 @@ def _shape_args(m):
 def _chunk(state, ns, grad):
     m = state.model
     mdt = _lib.dtype_code(m.dtype)
-    per = _lib.lib().qtx_resconv_workspace_size(mdt, 1, *_shape_args(m), int(grad))
+    # marginal bytes per sample (the size-1 query also holds the fixed part: repacked weights, guards)
+    ws = _lib.lib().qtx_resconv_workspace_size
+    per = (ws(mdt, 1025, *_shape_args(m), int(grad)) - ws(mdt, 1, *_shape_args(m), int(grad))) // 1024
     cap = max(1, (_BWD_BUDGET if grad else _FWD_BUDGET) // max(per, 1))
     user = state.backward_chunk if grad else state.forward_chunk
     if user is not None:
