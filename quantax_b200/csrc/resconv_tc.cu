@@ -137,6 +137,7 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // K-major, no swizzle: core matrix = 8 rows x 16 B (rows 16 B apart); LBO = distance between the two
@@ -614,6 +615,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
                 const int c0 = plane * 8;
                 const int64_t roff = raw_sample + (PLANAR ? (int64_t)plane * N * 8 : (int64_t)c0 * N);
                 uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
+                if (PLANAR && Lres && plane + kColGroups < planes)  // next plane's residual -> L1 while this one computes
+                  prefetch_l1(Lres + roff + (int64_t)kColGroups * N * 8);
                 epi_load<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr, N);
                 epi_store<PLANAR>(acc[t][k], p.C - c0, Lraw ? Lraw + roff : nullptr, N, Lwrite, gk, act_hi, 2 * g.slots,
                                   rps[t]);
@@ -941,6 +944,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const int64_t item = (2 * r + j) * npairs + pair_id;
           if (item >= nitems) continue;
           const TcLayer& L = p.layer[p.layer0 + li];
+          if (L.planar && L.res) {  // first residual plane of both tiles -> L1 while the MMAs finish
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int64_t s = item * g.spi + tsl[t];
+              if (rvalid[t] && s < g.ns && cgp < planes)
+                prefetch_l1(L.res + s * planes * N * 8 + ((int64_t)cgp * N + rpix[t]) * 8);
+            }
+          }
           if (lane == 0) QTX_TIMED_WAIT(t_tfull, tmem_full, q & 1);
           __syncwarp();
           const long long t_d0 = clock64();
@@ -989,6 +1000,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int c0 = plane * 8;
                 const int64_t roff = raw_sample + (PLANAR ? (int64_t)plane * N * 8 : (int64_t)c0 * N);
                 uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
+                if (PLANAR && Lres && plane + kColGroups < planes)  // next plane's residual -> L1 while this one computes
+                  prefetch_l1(Lres + roff + (int64_t)kColGroups * N * 8);
                 epi_load<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr, N);
                 epi_store<PLANAR>(acc[t][k], p.C - c0, Lraw ? Lraw + roff : nullptr, N, Lwrite, gk, act_hi, 2 * g.slots,
                                   rps[t]);
