@@ -427,8 +427,21 @@ __global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict_
   auto at = [&](int c, int r) -> T { return planes > 0 ? xs[((c >> 3) * N + r) * 8 + (c & 7)] : xs[c * N + r]; };
   T m = 0;
   if (planes > 0) {
-    for (int e = tid; e < planes * N * 8; e += blockDim.x)
-      if (((e / (N * 8)) * 8 + (e & 7)) < C) m = fmax(m, fabs(xs[e] * inv_norm));
+    if constexpr (sizeof(T) == 4) {
+      // 16-byte loads: 4 consecutive channels of one pixel
+      const float4* x4 = reinterpret_cast<const float4*>(xs);
+      for (int e4 = tid; e4 < planes * N * 2; e4 += blockDim.x) {
+        const int c0 = (e4 / (N * 2)) * 8 + (e4 & 1) * 4;
+        const float4 q = x4[e4];
+        if (c0 + 0 < C) m = fmax(m, fabs(q.x * inv_norm));
+        if (c0 + 1 < C) m = fmax(m, fabs(q.y * inv_norm));
+        if (c0 + 2 < C) m = fmax(m, fabs(q.z * inv_norm));
+        if (c0 + 3 < C) m = fmax(m, fabs(q.w * inv_norm));
+      }
+    } else {
+      for (int e = tid; e < planes * N * 8; e += blockDim.x)
+        if (((e / (N * 8)) * 8 + (e & 7)) < C) m = fmax(m, fabs(xs[e] * inv_norm));
+    }
   } else {
     for (int e = tid; e < CN; e += blockDim.x) m = fmax(m, fabs(xs[e] * inv_norm));
   }
@@ -448,12 +461,29 @@ __global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict_
   T part = 0, tot = 0;
   if (planes > 0) {
     // planar stream: sum_r mean_c sig = (sum over all valid elements) / C, read contiguously
-    for (int e = tid; e < planes * N * 8; e += blockDim.x) {
-      if (((e / (N * 8)) * 8 + (e & 7)) >= C) continue;
-      T z = xs[e] * inv_norm;
+    auto term = [&](T xv) -> T {
+      T z = xv * inv_norm;
       T sg = exp(z - m);
       if (final_act == 1) sg = (sg - exp(-z - m)) / T(2) + em;
-      tot += sg;
+      return sg;
+    };
+    if constexpr (sizeof(T) == 4) {
+      const float4* x4 = reinterpret_cast<const float4*>(xs);
+      T t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      for (int e4 = tid; e4 < planes * N * 2; e4 += blockDim.x) {
+        const int c0 = (e4 / (N * 2)) * 8 + (e4 & 1) * 4;
+        const float4 q = x4[e4];
+        if (c0 + 0 < C) t0 += term(q.x);
+        if (c0 + 1 < C) t1 += term(q.y);
+        if (c0 + 2 < C) t2 += term(q.z);
+        if (c0 + 3 < C) t3 += term(q.w);
+      }
+      tot = (t0 + t1) + (t2 + t3);
+    } else {
+      for (int e = tid; e < planes * N * 8; e += blockDim.x) {
+        if (((e / (N * 8)) * 8 + (e & 7)) >= C) continue;
+        tot += term(xs[e]);
+      }
     }
     part = tot / (T)C;
   } else {

@@ -274,18 +274,24 @@ __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
 // ---------------------------------------------------------------------------------------------
 // first layer (conv1 of block 0, cin = 1; conv_nets.py:84-86): CUDA cores, writes the operand raster of
 // conv2_0 = split(4 * gelu(conv1_0(s / sqrt 2) + b)) and optionally the raw pre-activation.
-// thread per (sample, pixel, plane)
+// thread per (sample, pixel)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __restrict__ spins, const float* __restrict__ w,
                                                              const float* __restrict__ b, TcGeom g, int C, int Np,
                                                              __half* __restrict__ act, float* __restrict__ raw_out) {
+  // thread per (sample, pixel): the nine neighbour spins are read once and reused for all channels; the weights
+  // [C][9] and biases sit in shared memory (broadcast reads)
+  extern __shared__ float wb_s[];  // [Np * 9] weights (zero padded), [Np] biases
   const int N = g.H * g.W, planes = Np >> 3;
-  const int64_t total = g.ns * N * planes;
+  for (int e = threadIdx.x; e < Np * 9; e += blockDim.x) wb_s[e] = (e / 9 < C) ? w[e] : 0.f;
+  for (int e = threadIdx.x; e < Np; e += blockDim.x) wb_s[Np * 9 + e] = (e < C) ? b[e] : 0.f;
+  __syncthreads();
+  const float* bs = wb_s + Np * 9;
   const GeluConst gk = gelu_const(1.0f);
+  const int64_t total = g.ns * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int pix = (int)(e % N);
-    const int plane = (int)((e / N) % planes);
-    const int64_t s = e / ((int64_t)N * planes);
+    const int64_t s = e / N;
     const int y = pix / g.W, x = pix % g.W;
     float sv[9];
 #pragma unroll
@@ -297,21 +303,20 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
         xx += (xx < 0) ? g.W : 0; xx -= (xx >= g.W) ? g.W : 0;
         sv[dy * 3 + dx] = 0.70710678118654752f * (float)spins[s * N + yy * g.W + xx];
       }
-    float t[8];
+    const PixSlots ps = pixel_slots(g, y, x);
+    for (int plane = 0; plane < planes; ++plane) {
+      float t[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = plane * 8 + j;
-      float v = 0.f;
-      if (c < C) {
+      for (int j = 0; j < 8; ++j) {
+        const int c = plane * 8 + j;
+        float v = bs[c];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) v += w[c * 9 + tap] * sv[tap];
-        v += b[c];
-        if (raw_out) raw_out[(s * C + c) * N + pix] = v;
-        v = gelu_scaled(v, gk);
+        for (int tap = 0; tap < 9; ++tap) v = fmaf(wb_s[c * 9 + tap], sv[tap], v);
+        if (raw_out && c < C) raw_out[(s * C + c) * N + pix] = v;
+        t[j] = (c < C) ? gelu_scaled(v, gk) : 0.f;
       }
-      t[j] = v;
+      store_plane(act, g, plane, s * g.Ps, ps, t);
     }
-    store_plane(act, g, plane, s * g.Ps, pixel_slots(g, y, x), t);
   }
 }
 
@@ -1201,11 +1206,11 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
     QTX_LAUNCH_CHECK();
   }
   {
-    const int64_t total = ns * N * (Np >> 3);
+    const int64_t total = ns * N;
     unsigned gsz = (unsigned)((total + 255) / 256);
     if (gsz > 16u * num_sms()) gsz = 16u * num_sms();
-    tc_first_layer_kernel<<<gsz, 256, 0, st>>>(spins, params + w1[0], params + b1[0], g, C, Np, act,
-                                                save_all ? Hs : nullptr);
+    tc_first_layer_kernel<<<gsz, 256, (size_t)Np * 10 * sizeof(float), st>>>(spins, params + w1[0], params + b1[0], g, C,
+                                                                             Np, act, save_all ? Hs : nullptr);
     QTX_LAUNCH_CHECK();
   }
   // shared memory: activation ring + weight ring + barriers
