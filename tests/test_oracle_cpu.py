@@ -226,3 +226,55 @@ def test_sr_step_real_to_complex_stacking():
     eb, _, _ = osolver.ebar(E, np.ones(12))
     assert np.isrealobj(x)
     assert np.allclose(ob @ x, eb, atol=1e-9)  # 24 real equations, 40 unknowns: exact min-norm solution
+
+
+def test_rbm_conv_oracle_is_the_same_convolution_as_resconv_layers():
+    """RBM_Conv (shallow_nets.py:129-173) uses eqx.nn.Conv with the lattice-sized kernel, SAME + CIRCULAR padding:
+    the oracle's direct definition equals the generic circular cross-correlation restated for ResConv, and its
+    log-derivative equals finite differences of log psi."""
+    from oracle import models as om
+
+    net = om.RBMConv.random((4, 6), 3, np.float64, seed=1)
+    rng = np.random.default_rng(0)
+    s = (2 * rng.integers(0, 2, (5, 24)) - 1).astype(np.int8)
+    x = s.astype(np.float64).reshape(-1, 1, 4, 6)
+    assert np.abs(net.theta(s) - om.conv_circ(x, net.K, net.b)).max() < 1e-14
+    J, p0 = net.jacobian(s), net.params()
+    for k in rng.integers(0, p0.size, 8):
+        def logpsi(p):
+            return om.RBMConv(p[:net.K.size].reshape(net.K.shape), p[net.K.size:], net.shape).forward(s)[1]
+        pp, pm = p0.copy(), p0.copy()
+        pp[k] += 1e-6
+        pm[k] -= 1e-6
+        assert np.abs((logpsi(pp) - logpsi(pm)) / 2e-6 - J[:, k]).max() < 1e-8
+
+
+def test_time_evol_chunked_accumulation_equals_direct():
+    """time_evol.py:55-115: the chunked S / F accumulation (un-centred sums corrected by the means) equals the direct
+    Obar^+ Obar, Obar^+ Ebar; and S, F are the stacked-real products used by the B200 path."""
+    from oracle import solver as osolver
+
+    rng = np.random.default_rng(5)
+    O = rng.standard_normal((90, 12)) + 1j * rng.standard_normal((90, 12))
+    E = rng.standard_normal(90) + 1j * rng.standard_normal(90)
+    x1, e1, v1, S1, F1 = osolver.time_evol_step(O, E)
+    x2, e2, v2, S2, F2 = osolver.time_evol_step(O, E, max_parallel=32)
+    assert np.allclose(S1, S2, atol=1e-12) and np.allclose(F1, F2, atol=1e-12) and np.allclose(x1, x2, atol=1e-9)
+    assert abs(e1 - e2) < 1e-12 and abs(v1 - v2) < 1e-12
+    ob, _ = osolver.obar(O, np.ones(90))
+    eb, _, _ = osolver.ebar(E, np.ones(90))
+    A = np.concatenate([ob.real, ob.imag], axis=0)
+    b = np.concatenate([-eb.imag, eb.real])
+    assert np.allclose(A.T @ A, S1, atol=1e-12) and np.allclose(A.T @ b, F1, atol=1e-12)
+
+
+def test_mix_sweep_reduces_to_plain_sweep_for_one_component():
+    from oracle import models as om, sampler as osmp, sites as osites
+
+    lat = osites.Square(4, Nparticles=(8, 8))
+    net = om.RBM.random(16, 8, np.float64, seed=2, scale=0.5)
+    spins = osmp.rand_states(12, 16, 8, seed=3)
+    table = osites.site_neighbor_table(lat)
+    a = osmp.sweep(osmp.RBMChainModel(net), spins, 9, "exchange", neighbors=table, seed=11, step0=4)
+    b = osmp.mix_sweep(osmp.RBMChainModel(net), spins, [0] * 9, ["exchange"], [table], [1], seed=11, step0=4)
+    assert np.array_equal(a["spins"], b["spins"]) and np.array_equal(a["naccept"], b["naccept"])
