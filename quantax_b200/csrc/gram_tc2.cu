@@ -23,6 +23,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ bool elect_one_lane() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -162,8 +167,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread of the leader CTA =====
-    if (leader && lane == 0) {
+    // ===== MMA issuer: the whole warp of the leader CTA runs the (warp-uniform) loop and one elected lane issues,
+    // so that ptxas keeps the descriptors in uniform registers (UTCIMMA takes uniform-register operands; with a
+    // lane-0 branch every MMA paid a vector->uniform election loop, ~70 cycles per MMA of 64 tensor cycles) =====
+    if (leader) {
       uint32_t stage = 0, phase = 0, tphase = 0;
       const uint64_t desc0 = make_desc_sw32(smem_u32(smem));
       const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
@@ -177,12 +184,15 @@ __global__ void __launch_bounds__(kThreads, 1)
             tc_fence_after();
             const uint32_t desc_lo = desc_lo0 + stage * (stage_bytes >> 4);
             const uint32_t acc_first = kb > 0 ? 1u : 0u;
-            if (pass == 0) issue_kblock2<S, 0>(tmem_base, desc_lo, desc_hi, acc_first);
-            else issue_kblock2<S, (npasses > 1 ? 1 : 0)>(tmem_base, desc_lo, desc_hi, acc_first);
-            umma_commit_2sm(empty_bar + stage);
+            if (elect_one_lane()) {
+              if (pass == 0) issue_kblock2<S, 0>(tmem_base, desc_lo, desc_hi, acc_first);
+              else issue_kblock2<S, (npasses > 1 ? 1 : 0)>(tmem_base, desc_lo, desc_hi, acc_first);
+              umma_commit_2sm(empty_bar + stage);
+              if (kb == p.nkb - 1) umma_commit_2sm(tmem_full);
+            }
+            __syncwarp();
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit_2sm(tmem_full);
           tphase ^= 1;
         }
       }
