@@ -164,6 +164,8 @@ int qtx_rbm_jacobian_colmean(int model_dtype, const void* W, const void* b, int 
  *   (quantax/state/variational.py:262-266 with the Identity symmetry).
  * ------------------------------------------------------------------------------------------ */
 int64_t qtx_resconv_nparams(int nblocks, int channels, int lx, int ly, int kh, int kw);
+/* 1 if the float32 tensor-core tower (csrc/resconv_tc.cu) serves this shape, else 0 (CUDA-core path). */
+int qtx_resconv_tc_available(int model_dtype, int channels, int lx, int ly, int kh, int kw);
 size_t qtx_resconv_workspace_size(int model_dtype, int64_t ns, int nblocks, int channels, int lx,
                                   int ly, int kh, int kw, int need_grad);
 /* Batched direct forward: Variational.__call__ / _fulljit_forward (variational.py:268-274,325-347). */
@@ -199,6 +201,29 @@ int qtx_metropolis_accept(int8_t* spins, const int8_t* new_spins, const uint8_t*
                           const double* expo_new, double reweight, const double* inj_u,
                           uint64_t seed, uint64_t step, uint64_t chain0, int32_t* naccept,
                           uint8_t* accept_log, qtx_stream_t stream);
+
+/* Moved proposals only.  The reference evaluates psi(s') of every proposal, including the no-op
+ * exchanges of equal spins that `updated = any(s' != s)` can never accept (metropolis.py:262-275,
+ * 314-316); here they are skipped:
+ *   compact_moved : rank_out int32 [ns] (index among the moved chains, -1 otherwise), the moved rows
+ *                   of new_spins gathered into compact_spins_out, the count in count_out int64 [1]
+ *   forward_n     : qtx_resconv_forward[_cplx] of the first *ns_dev <= ns_max samples, the count
+ *                   read on the device (float32 tensor-core towers; QTX_ERR_UNSUPPORTED otherwise)
+ *   accept_compact: qtx_metropolis_accept[_cplx] with psi_new of chain c at index rank[c] */
+int qtx_compact_moved(const uint8_t* moved, const int8_t* new_spins, int64_t ns, int N,
+                      int32_t* rank_out, int8_t* compact_spins_out, int64_t* count_out,
+                      qtx_stream_t stream);
+int qtx_resconv_forward_n(int model_dtype, const void* params, int nblocks, int channels, int lx,
+                          int ly, int kh, int kw, int final_act, int out_complex,
+                          const int8_t* spins, int64_t ns_max, const int64_t* ns_dev,
+                          double* significand_out, double* exponent_out, void* workspace,
+                          size_t workspace_bytes, qtx_stream_t stream);
+int qtx_metropolis_accept_compact(int8_t* spins, const int8_t* new_spins, const uint8_t* moved,
+                                  const int32_t* rank, int64_t ns, int N, double* mult, double* expo,
+                                  const double* mult_new, const double* expo_new, int mult_complex,
+                                  double reweight, const double* inj_u, uint64_t seed, uint64_t step,
+                                  uint64_t chain0, int32_t* naccept, uint8_t* accept_log,
+                                  qtx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * State-level symmetry projection psi(s) = sum_g w_g psi(T_g s), w_g = chi_g chi_0 / |G|

@@ -34,6 +34,7 @@ SIGNATURES = {
     "qtx_rbm_jacobian": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "qtx_rbm_colmean_workspace_size": (_sz, [_i32, _i32, _i32, _i64]),
     "qtx_rbm_jacobian_colmean": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_resconv_tc_available": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "qtx_resconv_nparams": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "qtx_resconv_workspace_size": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "qtx_resconv_forward": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz,
@@ -44,6 +45,11 @@ SIGNATURES = {
                                       _vp]),
     "qtx_metropolis_accept": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f64, _vp, _u64, _u64, _u64, _vp,
                                      _vp, _vp]),
+    "qtx_compact_moved": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "qtx_resconv_forward_n": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp,
+                                     _vp, _sz, _vp]),
+    "qtx_metropolis_accept_compact": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _vp, _u64,
+                                             _u64, _u64, _vp, _vp, _vp]),
     "qtx_symm_images": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
     "qtx_symm_combine": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "qtx_weighted_rowsum": (_i32, [_i32, _vp, _i64, _vp, _i64, _i32, _i64, _vp, _i64, _vp]),

@@ -23,7 +23,7 @@ bool resconv_tc_supported(int C, int lx, int ly, int kh, int kw);
 size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly);
 int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
                        float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, const float** x_final,
-                       int* x_final_planes, cudaStream_t st);
+                       int* x_final_planes, const long long* ns_dev, cudaStream_t st);
 
 constexpr int kConvThreads = 256;
 constexpr int kOT = 32;   // out-channel tile per CTA
@@ -416,10 +416,12 @@ __global__ void weight_transpose_flip_kernel(const T* __restrict__ w, int cout, 
 template <typename T>
 __global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict__ x, int64_t ns, int C, int N,
                                                             T inv_norm, int final_act, double* __restrict__ sig_out,
-                                                            double* __restrict__ exp_out, T* __restrict__ dz, int planes) {
+                                                            double* __restrict__ exp_out, T* __restrict__ dz, int planes,
+                                                            const long long* __restrict__ ns_dev) {
   __shared__ T red[32];
   __shared__ T bc;
   const int64_t s = blockIdx.x;
+  if (ns_dev && s >= *ns_dev) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int CN = C * N;
   // planes > 0: x is the planar residual stream [ns, planes, N, 8] of the tensor-core forward (resconv_tc.cu)
@@ -536,10 +538,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) resconv_final_cplx_kernel(const T* __restrict__ x, int64_t ns, int C, int N,
                                                                  T inv_norm, int final_act, double2* __restrict__ sig_out,
                                                                  double* __restrict__ exp_out, T* __restrict__ dz_re,
-                                                                 T* __restrict__ dz_im, int planes) {
+                                                                 T* __restrict__ dz_im, int planes,
+                                                                 const long long* __restrict__ ns_dev) {
   __shared__ double red[3][8];
   __shared__ double bc[3];
   const int64_t s = blockIdx.x;
+  if (ns_dev && s >= *ns_dev) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C2 = C / 2, CN2 = C2 * N;
   const T* xs = x + s * (planes > 0 ? (int64_t)planes * N * 8 : (int64_t)C * N);
@@ -800,6 +804,7 @@ struct AcceptParams {
   uint64_t step, chain0;
   int32_t* naccept;         // [ns] incremented (nullable)
   uint8_t* accept_log;      // [ns] for this step (nullable)
+  const int32_t* rank;      // nullable: psi_new of chain c sits at index rank[c] (compacted batch of moved chains)
 };
 
 // metropolis.py:299-322: ratio = |psi'/psi|^n formed in the container then densified
@@ -817,22 +822,26 @@ __global__ void __launch_bounds__(256) accept_kernel(AcceptParams p) {
     philox4x32_10(r0, r1, r2, r3, p.seed_lo, p.seed_hi);
     u = (double)((((uint64_t)r2 << 32) | r3) >> 11) * 0x1.0p-53;
   }
-  const double e0 = p.expo[chain], e1 = p.expo_new[chain];
+  // unmoved proposals are never accepted (metropolis.py:314-316): their psi_new is not needed (and, with a
+  // compacted batch, not computed)
+  const bool moved = p.moved[chain] != 0;
+  const int64_t cn = p.rank ? (moved ? (int64_t)p.rank[chain] : 0) : chain;
+  const double e0 = p.expo[chain], e1 = p.expo_new[cn];
   double a0, a1, m1r, m1i = 0.0;
   if constexpr (CPL) {
     a0 = hypot(p.mult[2 * chain], p.mult[2 * chain + 1]);
-    m1r = p.mult_new[2 * chain];
-    m1i = p.mult_new[2 * chain + 1];
+    m1r = p.mult_new[2 * cn];
+    m1i = p.mult_new[2 * cn + 1];
     a1 = hypot(m1r, m1i);
   } else {
     a0 = fabs(p.mult[chain]);
-    m1r = p.mult_new[chain];
+    m1r = p.mult_new[cn];
     a1 = fabs(m1r);
   }
   double rate = (a1 / a0) * exp(e1 - e0);
   rate = (p.reweight == 2.0) ? rate * rate : pow(rate, p.reweight);
   const bool zero_old = a0 * exp(e0) == 0.0;
-  const bool acc = ((rate > 1.0 - u) || zero_old) && p.moved[chain];
+  const bool acc = ((rate > 1.0 - u) || zero_old) && moved;
   if (acc) {
     int8_t* sp = p.spins + chain * p.N;
     const int8_t* np_ = p.new_spins + chain * p.N;
@@ -879,7 +888,7 @@ static size_t resconv_ws_base(int dtype, int64_t ns, const NetShape& sh, bool gr
 template <typename T>
 static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins, int64_t ns, double* sig_out,
                        double* exp_out, void* out, int out_dtype, int64_t ld, void* ws, cudaStream_t st, int cpl = 0,
-                       int64_t im_row_offset = 0) {
+                       int64_t im_row_offset = 0, const long long* ns_dev = nullptr) {
   const int N = sh.N(), C = sh.C, nb = sh.nblocks;
   const bool grad = out != nullptr;
   const int64_t act = ns * C * N;
@@ -928,7 +937,7 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
       const size_t base_bytes = resconv_ws_base(QTX_F32, ns, sh, grad);
       int rc = resconv_tc_forward(nb, C, sh.lx, sh.ly, params, spins, ns, X, Hs, grad ? 1 : 0,
                                   (unsigned char*)ws + base_bytes, resconv_tc_workspace(ns, nb, C, sh.lx, sh.ly),
-                                  &tc_xfinal, &tc_planes, st);
+                                  &tc_xfinal, &tc_planes, ns_dev, st);
       if (rc) return rc;
       tc_done = true;
     }
@@ -964,10 +973,10 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
   T* wT = grad ? scratch + 3 * act : nullptr;
   if (cpl)
     resconv_final_cplx_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
-                                                               sh.final_act, (double2*)sig_out, exp_out, dA, dC, tc_planes);
+                                                               sh.final_act, (double2*)sig_out, exp_out, dA, dC, tc_planes, ns_dev);
   else
     resconv_final_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
-                                                          sh.final_act, sig_out, exp_out, dA, tc_planes);
+                                                          sh.final_act, sig_out, exp_out, dA, tc_planes, ns_dev);
   QTX_LAUNCH_CHECK();
   if (!grad) return QTX_OK;
 
@@ -1060,6 +1069,10 @@ static bool shape_ok(int nblocks, int C, int lx, int ly, int kh, int kw, int fin
          (final_act == 0 || final_act == 1);
 }
 
+extern "C" int qtx_resconv_tc_available(int model_dtype, int channels, int lx, int ly, int kh, int kw) {
+  return (model_dtype == QTX_F32 && resconv_tc_supported(channels, lx, ly, kh, kw)) ? 1 : 0;
+}
+
 extern "C" int64_t qtx_resconv_nparams(int nblocks, int channels, int lx, int ly, int kh, int kw) {
   NetShape sh{nblocks, channels, lx, ly, kh, kw, 0};
   return sh.nparams();
@@ -1114,6 +1127,101 @@ extern "C" int qtx_resconv_jacobian(int model_dtype, const void* params, int nbl
     return resconv_run<double>(sh, (const double*)params, spins, ns, significand_out, exponent_out, out, out_dtype,
                                ld, workspace, st);
   QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_resconv_jacobian: bad dtype %d", model_dtype);
+}
+
+// ---- batches of MOVED proposals only (the reference evaluates psi of every proposal, also of the no-ops that can
+// never be accepted, metropolis.py:262-275,314-316): rank[c] = index of chain c among the moved chains (or -1),
+// their proposed configurations gathered contiguously, the count left on the device ----
+__global__ void __launch_bounds__(1024) compact_moved_kernel(const uint8_t* __restrict__ moved, int64_t ns,
+                                                             int32_t* __restrict__ rank, long long* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < ns; base += blockDim.x) {
+    const int64_t c = base + tid;
+    const int f = (c < ns && moved[c]) ? 1 : 0;
+    int incl = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+    const int carry = carry_s;
+    if (c < ns) rank[c] = f ? carry + woff + incl - 1 : -1;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry_s = carry + woff + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *count = carry_s;
+}
+
+__global__ void __launch_bounds__(256) gather_moved_kernel(const int8_t* __restrict__ new_spins, const int32_t* __restrict__ rank,
+                                                           int64_t ns, int N, int8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chain >= ns) return;
+  const int r = rank[chain];
+  if (r < 0) return;
+  for (int j = lane; j < N; j += 32) out[(int64_t)r * N + j] = new_spins[chain * N + j];
+}
+
+extern "C" int qtx_compact_moved(const uint8_t* moved, const int8_t* new_spins, int64_t ns, int N, int32_t* rank_out,
+                                 int8_t* compact_spins_out, int64_t* count_out, qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(moved && new_spins && rank_out && compact_spins_out && count_out && N > 0, QTX_ERR_INVALID,
+              "qtx_compact_moved: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  compact_moved_kernel<<<1, 1024, 0, st>>>(moved, ns, rank_out, (long long*)count_out);
+  QTX_LAUNCH_CHECK();
+  gather_moved_kernel<<<(unsigned)((ns + 7) / 8), 256, 0, st>>>(new_spins, rank_out, ns, N, compact_spins_out);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_metropolis_accept_compact(int8_t* spins, const int8_t* new_spins, const uint8_t* moved,
+                                             const int32_t* rank, int64_t ns, int N, double* mult, double* expo,
+                                             const double* mult_new, const double* expo_new, int mult_complex,
+                                             double reweight, const double* inj_u, uint64_t seed, uint64_t step,
+                                             uint64_t chain0, int32_t* naccept, uint8_t* accept_log,
+                                             qtx_stream_t stream) {
+  if (ns == 0) return QTX_OK;
+  QTX_REQUIRE(spins && new_spins && moved && rank && mult && expo && mult_new && expo_new && N > 0, QTX_ERR_INVALID,
+              "qtx_metropolis_accept_compact: bad argument");
+  AcceptParams p;
+  p.spins = spins; p.new_spins = new_spins; p.moved = moved; p.mult = mult; p.expo = expo; p.mult_new = mult_new;
+  p.expo_new = expo_new; p.ns = ns; p.N = N; p.reweight = reweight; p.inj_u = inj_u;
+  p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.step = step; p.chain0 = chain0;
+  p.naccept = naccept; p.accept_log = accept_log; p.rank = rank;
+  if (mult_complex) accept_kernel<true><<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+  else accept_kernel<false><<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+// Forward of the first *ns_dev (<= ns_max) samples, the count living on the device (no host synchronisation between
+// the proposal and the forward).  Float32 3x3 towers on the tensor-core path only; QTX_ERR_UNSUPPORTED otherwise.
+extern "C" int qtx_resconv_forward_n(int model_dtype, const void* params, int nblocks, int channels, int lx, int ly,
+                                     int kh, int kw, int final_act, int out_complex, const int8_t* spins, int64_t ns_max,
+                                     const int64_t* ns_dev, double* significand_out, double* exponent_out,
+                                     void* workspace, size_t workspace_bytes, qtx_stream_t stream) {
+  if (ns_max == 0) return QTX_OK;
+  QTX_REQUIRE(params && spins && ns_dev && significand_out && exponent_out && workspace, QTX_ERR_INVALID,
+              "qtx_resconv_forward_n: bad argument");
+  QTX_REQUIRE(shape_ok(nblocks, channels, lx, ly, kh, kw, final_act) && (!out_complex || channels % 2 == 0),
+              QTX_ERR_INVALID, "qtx_resconv_forward_n: bad network shape");
+  QTX_REQUIRE(model_dtype == QTX_F32 && resconv_tc_supported(channels, lx, ly, kh, kw), QTX_ERR_UNSUPPORTED,
+              "qtx_resconv_forward_n: needs the float32 tensor-core tower");
+  NetShape sh{nblocks, channels, lx, ly, kh, kw, final_act};
+  QTX_REQUIRE(workspace_bytes >= resconv_ws(model_dtype, ns_max, sh, false), QTX_ERR_INVALID,
+              "qtx_resconv_forward_n: workspace too small");
+  return resconv_run<float>(sh, (const float*)params, spins, ns_max, significand_out, exponent_out, nullptr, 0, 0,
+                            workspace, (cudaStream_t)stream, out_complex ? 1 : 0, 0, (const long long*)ns_dev);
 }
 
 extern "C" int qtx_resconv_forward_cplx(int model_dtype, const void* params, int nblocks, int channels, int lx, int ly,
@@ -1191,7 +1299,7 @@ extern "C" int qtx_metropolis_accept(int8_t* spins, const int8_t* new_spins, con
   p.spins = spins; p.new_spins = new_spins; p.moved = moved; p.mult = mult; p.expo = expo; p.mult_new = mult_new;
   p.expo_new = expo_new; p.ns = ns; p.N = N; p.reweight = reweight; p.inj_u = inj_u;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.step = step; p.chain0 = chain0;
-  p.naccept = naccept; p.accept_log = accept_log;
+  p.naccept = naccept; p.accept_log = accept_log; p.rank = nullptr;
   accept_kernel<false><<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
@@ -1208,7 +1316,7 @@ extern "C" int qtx_metropolis_accept_cplx(int8_t* spins, const int8_t* new_spins
   p.spins = spins; p.new_spins = new_spins; p.moved = moved; p.mult = mult; p.expo = expo; p.mult_new = mult_new;
   p.expo_new = expo_new; p.ns = ns; p.N = N; p.reweight = reweight; p.inj_u = inj_u;
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32); p.step = step; p.chain0 = chain0;
-  p.naccept = naccept; p.accept_log = accept_log;
+  p.naccept = naccept; p.accept_log = accept_log; p.rank = nullptr;
   accept_kernel<true><<<(unsigned)((ns + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p);
   QTX_LAUNCH_CHECK();
   return QTX_OK;

@@ -83,6 +83,7 @@ struct TcNetParams {
   int layer0, layer1;  // layers [layer0, layer1) are run by this launch
   int act_stages, w_stages;
   unsigned long long* dbg;  // optional [grid][16] cycle counters (QTX_TC_DEBUG=1)
+  const long long* ns_dev;  // optional device-side sample count (<= g.ns): batches whose size is decided on the device
   TcLayer layer[kTcMaxLayers];
 };
 
@@ -278,7 +279,8 @@ __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __restrict__ spins, const float* __restrict__ w,
                                                              const float* __restrict__ b, TcGeom g, int C, int Np,
-                                                             __half* __restrict__ act, float* __restrict__ raw_out) {
+                                                             __half* __restrict__ act, float* __restrict__ raw_out,
+                                                             const long long* __restrict__ ns_dev) {
   // thread per (sample, pixel): the nine neighbour spins are read once and reused for all channels; the weights
   // [C][9] and biases sit in shared memory (broadcast reads)
   extern __shared__ float wb_s[];  // [Np * 9] weights (zero padded), [Np] biases
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
   __syncthreads();
   const float* bs = wb_s + Np * 9;
   const GeluConst gk = gelu_const(1.0f);
-  const int64_t total = g.ns * N;
+  const int64_t total = (ns_dev ? (int64_t)*ns_dev : g.ns) * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int pix = (int)(e % N);
     const int64_t s = e / N;
@@ -423,7 +425,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
   // accumulator columns: tile t -> main at (2t) * col_stride, cross terms at (2t + 1) * col_stride
   const uint32_t col_stride = (uint32_t)((p.Np + 31) & ~31);
 
-  const int64_t nitems = g.nitems;
+  const int64_t ns_rt = p.ns_dev ? (int64_t)*p.ns_dev : g.ns;  // runtime sample count
+  const int64_t nitems = (ns_rt + g.spi - 1) / g.spi;
   const int64_t nrounds = (nitems + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
   const int nl = p.layer1 - p.layer0;
 
@@ -608,7 +611,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
               const int64_t s = item * g.spi + ((g.tps == 1) ? t : 0);
-              if (!rvalid[t] || s >= g.ns) continue;
+              if (!rvalid[t] || s >= ns_rt) continue;
               const int pix = rpix[t];
               const float resv = Lspin ? (float)Lspin[s * N + pix] : 0.f;
               uint4* act_sample = reinterpret_cast<uint4*>(p.act) + s * g.Ps;
@@ -781,7 +784,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t col_stride = (uint32_t)((p.Np + 31) & ~31);
 
-  const int64_t nitems = g.nitems;
+  const int64_t ns_rt = p.ns_dev ? (int64_t)*p.ns_dev : g.ns;  // runtime sample count
+  const int64_t nitems = (ns_rt + g.spi - 1) / g.spi;
   const int npairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
   const int64_t nrounds = (nitems + 2 * (int64_t)npairs - 1) / (2 * (int64_t)npairs);
   const int nl = p.layer1 - p.layer0;
@@ -953,7 +957,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
               const int64_t s = item * g.spi + tsl[t];
-              if (rvalid[t] && s < g.ns && cgp < planes)
+              if (rvalid[t] && s < ns_rt && cgp < planes)
                 prefetch_l1(L.res + s * planes * N * 8 + ((int64_t)cgp * N + rpix[t]) * 8);
             }
           }
@@ -993,7 +997,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
               const int64_t s = item * g.spi + tsl[t];
-              if (!rvalid[t] || s >= g.ns) continue;
+              if (!rvalid[t] || s >= ns_rt) continue;
               const int pix = rpix[t];
               const float resv = Lspin ? (float)Lspin[s * N + pix] : 0.f;
               uint4* act_sample = reinterpret_cast<uint4*>(p.act) + s * g.Ps;
@@ -1133,7 +1137,7 @@ size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly) {
 //                  both [ns, C, N] (what the backward kernels of resconv.cu read); *x_final = X[nblocks-1]
 int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
                        float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, const float** x_final,
-                       int* x_final_planes, cudaStream_t st) {
+                       int* x_final_planes, const long long* ns_dev, cudaStream_t st) {
   TcGeom g;
   int Np, KS;
   size_t blob_halfs, act_bytes, wblob_bytes, resid_bytes;
@@ -1210,7 +1214,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
     unsigned gsz = (unsigned)((total + 255) / 256);
     if (gsz > 16u * num_sms()) gsz = 16u * num_sms();
     tc_first_layer_kernel<<<gsz, 256, (size_t)Np * 10 * sizeof(float), st>>>(spins, params + w1[0], params + b1[0], g, C,
-                                                                             Np, act, save_all ? Hs : nullptr);
+                                                                             Np, act, save_all ? Hs : nullptr, ns_dev);
     QTX_LAUNCH_CHECK();
   }
   // shared memory: activation ring + weight ring + barriers
@@ -1231,6 +1235,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   const bool dbg = getenv("QTX_TC_DEBUG") != nullptr;
   if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 256 * 16 * sizeof(unsigned long long));
   np.dbg = dbg ? dbg_buf : nullptr;
+  np.ns_dev = ns_dev;
   auto report = [&](int units) {
     static unsigned long long h[256 * 16];
     cudaStreamSynchronize(st);

@@ -55,6 +55,39 @@ def resconv_forward(state, s: torch.Tensor) -> ScaleArray:
     return psi
 
 
+def _moved_only_ok(state, ns: int) -> bool:
+    """The sweep may evaluate only the MOVED proposals when the state is a bare float32 ResConv served by the
+    tensor-core tower and the batch fits one launch (the batch size then stays on the device)."""
+    import os
+
+    m = state.model
+    if os.environ.get("QTX_SWEEP_COMPACT", "1") == "0":  # dev knob: evaluate every proposal like the reference
+        return False
+    if getattr(m, "kind", None) != "resconv" or not state.symm.is_identity:
+        return False
+    if not _lib.lib().qtx_resconv_tc_available(_lib.dtype_code(m.dtype), m.channels, m.Lx, m.Ly, m.kh, m.kw):
+        return False
+    return _chunk(state, ns, False) >= ns
+
+
+def resconv_forward_n(state, s: torch.Tensor, count: torch.Tensor) -> ScaleArray:
+    """psi of the first ``count`` (device int64 [1]) rows of ``s``; the other entries of the result are undefined."""
+    m = state.model
+    mdt = _lib.dtype_code(m.dtype)
+    ns = s.shape[0]
+    cplx = getattr(m, "cplx", False)
+    sig = torch.empty(ns, dtype=torch.complex128 if cplx else torch.float64, device=s.device)
+    ex = torch.empty(ns, dtype=torch.float64, device=s.device)
+    wsz = _lib.lib().qtx_resconv_workspace_size(mdt, ns, *_shape_args(m), 0)
+    ws = state._workspace("resconv_fwd", wsz)
+    _lib.call("qtx_resconv_forward_n", mdt, _lib.ptr(m.params), *_shape_args(m), m.final, int(cplx), _lib.ptr(s), ns,
+              _lib.ptr(count), _lib.ptr(sig), _lib.ptr(ex), _lib.ptr(ws), wsz, _lib.stream())
+    psi = ScaleArray(sig, ex)
+    for layer in getattr(m, "raw_layers", ()):
+        psi = layer(psi, s)
+    return psi
+
+
 def resconv_jacobian(state, s: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """Real-output model: out [ns, Np].  Complex-output model: out [2 ns, Np] holds Re O in rows [0, ns) and Im O in
     rows [ns, 2 ns) (the stacking of sr.py:99-104).  Parameter-free phase layers do not change the log-derivative."""
@@ -101,10 +134,27 @@ def generic_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed,
         u = u.to(device=dev, dtype=torch.float64).contiguous()
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     st = _lib.stream()
+    # exchange proposals of two equal spins are no-ops that can never be accepted (metropolis.py:314-316); the
+    # reference still evaluates their psi.  Evaluate the moved proposals only when the forward allows it.
+    compact = int(kind) == _lib.QTX_SPIN_EXCHANGE and _moved_only_ok(state, ns)
+    if compact:
+        rank = torch.empty(ns, dtype=torch.int32, device=dev)
+        cspins = torch.zeros_like(spins)
+        count = torch.empty(1, dtype=torch.int64, device=dev)
     for t in range(nsweeps):
         _lib.call("qtx_metropolis_propose", int(kind), _lib.ptr(spins), ns, N, _lib.ptr(nbr), int(max_nb), int(hop),
                   None if pos is None else _lib.ptr(pos[t]), None if slot is None else _lib.ptr(slot[t]), seed,
                   int(step0) + t, int(chain0), _lib.ptr(new_spins), _lib.ptr(moved), st)
+        if compact:
+            _lib.call("qtx_compact_moved", _lib.ptr(moved), _lib.ptr(new_spins), ns, N, _lib.ptr(rank), _lib.ptr(cspins),
+                      _lib.ptr(count), st)
+            psi_new = resconv_forward_n(state, cspins, count)
+            _lib.call("qtx_metropolis_accept_compact", _lib.ptr(spins), _lib.ptr(new_spins), _lib.ptr(moved),
+                      _lib.ptr(rank), ns, N, _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(psi_new.mult.contiguous()),
+                      _lib.ptr(psi_new.expo.contiguous()), int(mult.is_complex()), float(reweight),
+                      None if u is None else _lib.ptr(u[t]), seed, int(step0) + t, int(chain0), _lib.ptr(nacc),
+                      None if log is None else _lib.ptr(log[t]), st)
+            continue
         psi_new = state(new_spins)
         _lib.call(accept, _lib.ptr(spins), _lib.ptr(new_spins), _lib.ptr(moved), ns, N,
                   _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(psi_new.mult.contiguous()), _lib.ptr(psi_new.expo.contiguous()),

@@ -206,3 +206,44 @@ def test_state_save_load_eqx_layout(qtx, tmp_path):
     assert [l.shape for l in read_eqx_leaves(g)] == [(16, 8), (16,), ()]
     st2 = qtx.state.Variational(qtx.model.RBM_Dense(16), param_file=g)
     assert torch.equal(st2.get_params_flatten(), st.get_params_flatten())
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_sweep_of_moved_proposals_only_equals_full_sweep(qtx, monkeypatch, cplx):
+    """Exchange proposals of two equal spins can never be accepted (metropolis.py:314-316); the float32 tensor-core
+    path evaluates psi of the moved proposals only (device-side batch size).  Chains, accept pattern and carried psi
+    must be identical to the sweep that evaluates every proposal, and match the oracle away from near-ties."""
+    if cplx:
+        qtx.set_default_dtype(torch.complex128)
+    try:
+        lat, olat = lattice_pair(qtx, "square", 6, (18, 18))
+        net = omodels.ResConv.random((6, 6), 2, 8, 3, np.float32, seed=71, bias_std=0.1, out_complex=cplx)
+        model = qtx.model.ResConv(2, 8, 3, out_dtype=torch.complex128 if cplx else None,
+                                  params=torch.from_numpy(net.params().copy()))
+        state = qtx.state.Variational(model)
+        ns, T = 96, 24
+        rng = np.random.default_rng(72)
+        table = osites.site_neighbor_table(olat)
+        u = rng.random((T, ns)); pos = rng.integers(0, 36, size=(T, ns)); slot = rng.integers(0, 4, size=(T, ns))
+        out = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("QTX_SWEEP_COMPACT", mode)
+            sampler = qtx.sampler.SpinExchange(state, ns, thermal_steps=0,
+                                               initial_spins=torch.from_numpy(osmp.rand_states(ns, 36, 18, seed=73)))
+            spins0 = to_np(sampler._spins).copy()
+            sampler.inject(torch.from_numpy(pos), torch.from_numpy(u), torch.from_numpy(slot))
+            samples = sampler.sweep(T, record=True)
+            out[mode] = (to_np(samples.spins), to_np(sampler.last_accept_log), to_np(samples.psi.mult), to_np(samples.psi.expo))
+        monkeypatch.delenv("QTX_SWEEP_COMPACT")
+        for a, b in zip(out["1"], out["0"]):
+            assert np.array_equal(a, b)
+        assert 0.2 < out["1"][1].mean() < 0.9
+        ref = osmp.sweep(osmp.FullForwardChainModel(net), spins0, T, "exchange", neighbors=table, pos=pos, slot=slot, u=u,
+                         record=True)
+        same = (ref["spins"] == out["1"][0]).all(axis=1)
+        assert same.mean() > 0.9  # float32 model: chains can only differ after a provable near-tie
+        first = np.array([np.argmax(ref["accept_log"][:, c] != out["1"][1][:, c]) for c in np.flatnonzero(~same)])
+        for c, t in zip(np.flatnonzero(~same), first):
+            assert ref["margin"][t, c] < 1e-3
+    finally:
+        qtx.set_default_dtype(torch.float64)
