@@ -63,11 +63,21 @@ def _moved_only_ok(state, ns: int) -> bool:
     m = state.model
     if os.environ.get("QTX_SWEEP_COMPACT", "1") == "0":  # dev knob: evaluate every proposal like the reference
         return False
-    if getattr(m, "kind", None) != "resconv" or not state.symm.is_identity:
+    if getattr(m, "kind", None) != "resconv":
         return False
     if not _lib.lib().qtx_resconv_tc_available(_lib.dtype_code(m.dtype), m.channels, m.Lx, m.Ly, m.kh, m.kw):
         return False
-    return _chunk(state, ns, False) >= ns
+    nimg = ns * (1 if state.symm.is_identity else state.symm.nsymm)  # a projected state forwards all symmetry images
+    return _chunk(state, nimg, False) >= nimg
+
+
+def state_forward_n(state, s: torch.Tensor, count: torch.Tensor):
+    """psi(s[:count]) of a (possibly symmetry-projected) ResConv state with the batch size on the device; entries
+    beyond ``count`` are undefined."""
+    if state.symm.is_identity:
+        return resconv_forward_n(state, s, count)
+    img = state._images(s)  # [ns * nsymm, N]: the images of sample i are rows i*nsymm .. (i+1)*nsymm - 1
+    return state._combine(resconv_forward_n(state, img, count * state.symm.nsymm), s.shape[0])
 
 
 def resconv_forward_n(state, s: torch.Tensor, count: torch.Tensor) -> ScaleArray:
@@ -148,7 +158,7 @@ def generic_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed,
         if compact:
             _lib.call("qtx_compact_moved", _lib.ptr(moved), _lib.ptr(new_spins), ns, N, _lib.ptr(rank), _lib.ptr(cspins),
                       _lib.ptr(count), st)
-            psi_new = resconv_forward_n(state, cspins, count)
+            psi_new = state_forward_n(state, cspins, count)
             _lib.call("qtx_metropolis_accept_compact", _lib.ptr(spins), _lib.ptr(new_spins), _lib.ptr(moved),
                       _lib.ptr(rank), ns, N, _lib.ptr(mult), _lib.ptr(expo), _lib.ptr(psi_new.mult.contiguous()),
                       _lib.ptr(psi_new.expo.contiguous()), int(mult.is_complex()), float(reweight),

@@ -208,6 +208,31 @@ def test_state_save_load_eqx_layout(qtx, tmp_path):
     assert torch.equal(st2.get_params_flatten(), st.get_params_flatten())
 
 
+def test_projected_sweep_of_moved_proposals_only_equals_full_sweep(qtx, monkeypatch):
+    """The same for a symmetry-projected float32 ResConv (C4v x Z2, 16 images per proposal): only the images of the
+    moved chains are forwarded."""
+    lat, olat = lattice_pair(qtx, "square", 6, (18, 18))
+    model, net = make_resconv(qtx, (6, 6), 2, 8, 3, torch.float32, "sinhp1", seed=81)
+    S = qtx.symmetry
+    state = qtx.state.Variational(model, symm=S.C4v() @ S.SpinInverse())
+    assert state.symm.nsymm == 16
+    ns, T = 64, 12
+    rng = np.random.default_rng(82)
+    u = rng.random((T, ns)); pos = rng.integers(0, 36, size=(T, ns)); slot = rng.integers(0, 4, size=(T, ns))
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("QTX_SWEEP_COMPACT", mode)
+        sampler = qtx.sampler.SpinExchange(state, ns, thermal_steps=0,
+                                           initial_spins=torch.from_numpy(osmp.rand_states(ns, 36, 18, seed=83)))
+        sampler.inject(torch.from_numpy(pos), torch.from_numpy(u), torch.from_numpy(slot))
+        samples = sampler.sweep(T, record=True)
+        out[mode] = (to_np(samples.spins), to_np(sampler.last_accept_log), to_np(samples.psi.mult), to_np(samples.psi.expo))
+    monkeypatch.delenv("QTX_SWEEP_COMPACT")
+    for a, b in zip(out["1"], out["0"]):
+        assert np.array_equal(a, b)
+    assert 0.1 < out["1"][1].mean() < 0.9
+
+
 @pytest.mark.parametrize("cplx", [False, True])
 def test_sweep_of_moved_proposals_only_equals_full_sweep(qtx, monkeypatch, cplx):
     """Exchange proposals of two equal spins can never be accepted (metropolis.py:314-316); the float32 tensor-core
