@@ -308,6 +308,37 @@ int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double rtol, doubl
                        double* evals_out, double* y_out, int32_t* info_out, void* workspace,
                        size_t workspace_bytes, qtx_stream_t stream);
 
+/* Same with the signal-to-noise damping of `_sum_without_noise` (solver.py:114-125): rho_k = U_k^T b is
+ * divided by 1 + (tol_snr / snr_k)^6, snr_k = |mean_t r_tk| / sqrt(mean_t |r_tk - mean|^2 / n),
+ * r_tk = U[t,k] b[t].  tol_snr <= 1e-6 is the plain sum (the reference's `cond`). */
+int qtx_pinv_eig_solve_snr(double* T, int64_t n, const double* b, double rtol, double atol,
+                           double tol_snr, double* evals_out, double* y_out, int32_t* info_out,
+                           void* workspace, size_t workspace_bytes, qtx_stream_t stream);
+/* The three stages separately, for solvers whose rho is not U^T b (lstsq_pinv_eig with tol_snr,
+ * solver.py:156-162: rho_sk = (A V)[s,k] b[s]).  qtx_eigh: T -> row-major U^T, evals_out [n]
+ * (workspace of qtx_pinv_eig_workspace_size).  qtx_rows_dot_snr: rho[k] = sum_without_noise_i
+ * (M[k,i] b[i]) for M [nrows, ld].  qtx_pinv_apply: y = U (lambda^+ o rho); rho is overwritten
+ * by lambda^+ o rho. */
+int qtx_eigh(double* T, int64_t n, double* evals_out, int32_t* info_out, void* workspace,
+             size_t workspace_bytes, qtx_stream_t stream);
+int qtx_rows_dot_snr(const double* M, int64_t nrows, int64_t n, int64_t ld, const double* b,
+                     double tol_snr, double* rho_out, qtx_stream_t stream);
+int qtx_pinv_apply(const double* Ut, int64_t n, const double* evals, double* rho_inout, double rtol,
+                   double atol, double* y_out, qtx_stream_t stream);
+
+/* y = (T + shift I)^-1 b, shift = rshift * trace(T) + ashift, by Cholesky (minnorm_shift_eig /
+ * lstsq_shift_eig, solver.py:50-77; `solve(assume_a="pos")`).  rshift < 0 selects the dtype
+ * default (1e-12).  T [n, n] float64 symmetric is overwritten by its factor; info_out int32 [1]
+ * device (0 = positive definite).  potrf / potrs are cuSOLVER library calls. */
+size_t qtx_shift_chol_workspace_size(int64_t n);
+int qtx_shift_chol_solve(double* T, int64_t n, const double* b, double rshift, double ashift,
+                         double* y_out, int32_t* info_out, void* workspace, size_t workspace_bytes,
+                         qtx_stream_t stream);
+
+/* out[k] = sum_s A[s,k]^2  (diagonal of S = A^T A in lstsq_shift_cg, solver.py:35) */
+int qtx_col_sumsq(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, double* out,
+                  qtx_stream_t stream);
+
 /* x[k] = sum_s A[s,k] y[s]  (the final A^dagger y of solver.py:146); x_out float64 [np] */
 int qtx_matvec_t(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, const double* y,
                  double* x_out, int accumulate, qtx_stream_t stream);

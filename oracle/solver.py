@@ -8,6 +8,8 @@ Restates
   quantax/optimizer/solver.py:152-164 (lstsq_pinv_eig, SR),
   quantax/optimizer/solver.py:167-201 (auto_pinv_eig),
   quantax/optimizer/solver.py:262-294 (minsr_pinv_eig),
+  quantax/optimizer/solver.py:24-90 (lstsq_shift_cg, minnorm/lstsq/auto_shift_eig), :114-125 (_sum_without_noise),
+  quantax/optimizer/solver.py:204-259 (block_pinv_eig), :297-302 (sgd_solver),
   quantax/state/variational.py:558-579 (update: theta <- theta - step, skip if non-finite).
 ``eigh`` is LAPACK syevd here and cuSOLVER/XLA in the reference (third party, unpinned):
 eigenvectors are only defined up to sign / rotation inside degenerate subspaces, so parity
@@ -93,6 +95,78 @@ def minsr_pinv_eig(T, b, rtol=None, atol=0.0, tol_snr=0.0):
     inv = eigs_inv(vals, rtol, atol)
     rho = _sum_without_noise(U.conj() * b[:, None], tol_snr)
     return U @ (inv * rho)
+
+
+def _shift(trace, rshift, ashift):
+    rel = get_rtol(np.asarray(trace).dtype) if rshift is None else rshift
+    return rel * trace + ashift
+
+
+def minnorm_shift_eig(A, b, rshift=None, ashift=1e-4):
+    """solver.py:50-62: x = A^+ (A A^+ + shift I)^-1 b, shift = rshift tr(T) + ashift (Cholesky solve in the
+    reference; any exact solve of the SPD system is the same restatement)."""
+    T = A @ A.conj().T
+    T = T + _shift(np.trace(T).real, rshift, ashift) * np.identity(T.shape[0], T.dtype)
+    return A.conj().T @ np.linalg.solve(T, b)
+
+
+def lstsq_shift_eig(A, b, rshift=None, ashift=1e-4):
+    """solver.py:65-77."""
+    S = A.conj().T @ A
+    F = A.conj().T @ b
+    S = S + _shift(np.trace(S).real, rshift, ashift) * np.identity(S.shape[0], S.dtype)
+    return np.linalg.solve(S, F)
+
+
+def auto_shift_eig(A, b, rshift=None, ashift=1e-4):
+    """solver.py:80-90."""
+    if A.shape[0] < A.shape[1]:
+        return minnorm_shift_eig(A, b, rshift, ashift)
+    return lstsq_shift_eig(A, b, rshift, ashift)
+
+
+def lstsq_shift_cg(A, b, diag_shift=0.01, rtol=1e-5, atol=0.0, maxiter=None, return_iterations=False):
+    """solver.py:24-47 for real A.  ``jax.scipy.sparse.linalg.cg`` (third party, unpinned; restated from its
+    published algorithm): x0 = 0, no preconditioner, loop while |r|^2 > max(tol^2 |b|^2, atol^2) and k < maxiter,
+    maxiter defaults to 10 * size."""
+    diag = np.einsum("sk,sk->k", A, A)
+
+    def S_apply(x):
+        return A.T @ (A @ x) + diag_shift * diag * x
+
+    F = A.conj().T @ b
+    if maxiter is None:
+        maxiter = 10 * F.size
+    atol2 = max(rtol ** 2 * float(F @ F), atol ** 2)
+    x = np.zeros_like(F)
+    r = F.copy()
+    p = r.copy()
+    gamma = float(r @ r)
+    k = 0
+    while gamma > atol2 and k < maxiter:
+        Ap = S_apply(p)
+        alpha = gamma / float(p @ Ap)
+        x = x + alpha * p
+        r = r - alpha * Ap
+        gamma_new = float(r @ r)
+        p = r + (gamma_new / gamma) * p
+        gamma = gamma_new
+        k += 1
+    return (x, k) if return_iterations else x
+
+
+def block_pinv_eig(Obar, Ebar, layer_sizes, rtol=None, atol=0.0, tol_snr=0.0):
+    """solver.py:204-259: split the parameter axis at the layer boundaries, solve every block with
+    auto_pinv_eig against Ebar / nlayers, concatenate."""
+    sizes = [n for n in layer_sizes if n > 0]
+    cuts = np.cumsum(sizes)[:-1]
+    Eb = Ebar / len(sizes)
+    return np.concatenate([auto_pinv_eig(Oi, Eb, rtol, atol, tol_snr) for Oi in np.split(Obar, cuts, axis=1)])
+
+
+def sgd_solver(A, b):
+    """solver.py:297-302."""
+    return A.conj().T @ b / b.shape[0]
 
 
 def sr_step(Omat, Eloc, rw, rtol=None, atol=0.0, real_to_complex=False):

@@ -65,6 +65,13 @@ SIGNATURES = {
     "qtx_gram": (_i32, [_i32, _vp, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _sz, _vp]),
     "qtx_pinv_eig_workspace_size": (_sz, [_i64]),
     "qtx_pinv_eig_solve": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_pinv_eig_solve_snr": (_i32, [_vp, _i64, _vp, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_eigh": (_i32, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_rows_dot_snr": (_i32, [_vp, _i64, _i64, _i64, _vp, _f64, _vp, _vp]),
+    "qtx_pinv_apply": (_i32, [_vp, _i64, _vp, _vp, _f64, _f64, _vp, _vp]),
+    "qtx_shift_chol_workspace_size": (_sz, [_i64]),
+    "qtx_shift_chol_solve": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _sz, _vp]),
+    "qtx_col_sumsq": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp]),
     "qtx_matvec_t": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp]),
     "qtx_matvec": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "qtx_axpby": (_i32, [_i64, _f64, _vp, _f64, _vp, _vp]),

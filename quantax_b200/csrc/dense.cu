@@ -11,7 +11,7 @@ template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
 // out[k] (+)= alpha * sum_s w[s] A[s,k]; thread owns 2 adjacent columns, grid.y splits the rows
-template <typename T>
+template <typename T, bool SQ = false>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ A, int64_t ns, int64_t np, int64_t ld,
                                                      const double* __restrict__ w, double alpha,
                                                      double* __restrict__ out, bool vec) {
@@ -27,14 +27,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ A, in
     for (int64_t s = s0; s < s1; ++s) {
       V v = *reinterpret_cast<const V*>(A + s * ld + k);
       double ws = w ? w[s] : 1.0;
-      a0 += ws * (double)v.x;
-      a1 += ws * (double)v.y;
+      double x0 = (double)v.x, x1 = (double)v.y;
+      if (SQ) { x0 *= x0; x1 *= x1; }
+      a0 += ws * x0;
+      a1 += ws * x1;
     }
   } else {
     for (int64_t s = s0; s < s1; ++s) {
       double ws = w ? w[s] : 1.0;
-      a0 += ws * (double)A[s * ld + k];
-      if (two) a1 += ws * (double)A[s * ld + k + 1];
+      double x0 = (double)A[s * ld + k], x1 = two ? (double)A[s * ld + k + 1] : 0.0;
+      if (SQ) { x0 *= x0; x1 *= x1; }
+      a0 += ws * x0;
+      if (two) a1 += ws * x1;
     }
   }
   atomicAdd(out + k, alpha * a0);
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(256) scale_columns_kernel(T* __restrict__ A, i
 
 __global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
 
-template <typename T>
+template <typename T, bool SQ = false>
 static int colsum_launch(const void* A, int64_t ns, int64_t np, int64_t ld, const double* w, double alpha,
                          double* out, bool accumulate, cudaStream_t st) {
   if (!accumulate) QTX_CUDA(cudaMemsetAsync(out, 0, np * sizeof(double), st));
@@ -183,7 +187,7 @@ static int colsum_launch(const void* A, int64_t ns, int64_t np, int64_t ld, cons
   if (split > ns) split = ns;
   if (split > 1024) split = 1024;
   bool vec = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) % (2 * sizeof(T))) == 0);
-  colsum_kernel<T><<<dim3(gx, (unsigned)split), 256, 0, st>>>((const T*)A, ns, np, ld, w, alpha, out, vec);
+  colsum_kernel<T, SQ><<<dim3(gx, (unsigned)split), 256, 0, st>>>((const T*)A, ns, np, ld, w, alpha, out, vec);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }
@@ -199,6 +203,15 @@ extern "C" int qtx_colmean(int dtype, const void* A, int64_t ns, int64_t np, int
   if (dtype == QTX_F64) return colsum_launch<double>(A, ns, np, ld, weight, 1.0 / (double)ns, mean_out, false, st);
   if (dtype == QTX_F32) return colsum_launch<float>(A, ns, np, ld, weight, 1.0 / (double)ns, mean_out, false, st);
   QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_colmean: bad dtype %d", dtype);
+}
+
+extern "C" int qtx_col_sumsq(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, double* out,
+                             qtx_stream_t stream) {
+  QTX_REQUIRE(A && out && ns > 0 && np > 0 && ld >= np, QTX_ERR_INVALID, "qtx_col_sumsq: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == QTX_F64) return colsum_launch<double, true>(A, ns, np, ld, nullptr, 1.0, out, false, st);
+  if (dtype == QTX_F32) return colsum_launch<float, true>(A, ns, np, ld, nullptr, 1.0, out, false, st);
+  QTX_REQUIRE(false, QTX_ERR_INVALID, "qtx_col_sumsq: bad dtype %d", dtype);
 }
 
 extern "C" int qtx_matvec_t(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, const double* y,

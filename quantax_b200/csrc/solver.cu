@@ -82,6 +82,66 @@ __global__ void __launch_bounds__(256) cols_comb_kernel(const double* __restrict
   atomicAdd(y + i, acc);
 }
 
+// rho[k] = sum_without_noise_i(M[k, i] b[i])  (solver.py:114-125): the plain sum x, damped by
+// 1 / (1 + (tol_snr / snr)^6) with snr = |mean| / sqrt(mean_i |r_i - mean|^2 / n).  CTA per row k; the
+// second pass re-reads the row (L2-resident) so that the variance is formed from centred terms like the reference.
+__global__ void __launch_bounds__(256) rows_dot_snr_kernel(const double* __restrict__ M, int64_t n, int64_t ld,
+                                                           const double* __restrict__ b, double tol_snr,
+                                                           double* __restrict__ rho) {
+  __shared__ double red[8];
+  __shared__ double bc;
+  const int64_t k = blockIdx.x;
+  const double* row = M + k * ld;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += row[i] * b[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    bc = t;
+  }
+  __syncthreads();
+  const double x = bc, mean = x / (double)n;
+  double var = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = row[i] * b[i] - mean;
+    var += d * d;
+  }
+  var = warp_sum(var);
+  __syncthreads();  // red is reused
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = var;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const double sd = sqrt(t / (double)n / (double)n);
+    const double snr = fabs(mean) / sd;
+    const double q = tol_snr / snr, q2 = q * q;
+    rho[k] = tol_snr > 1e-6 ? x / (1.0 + q2 * q2 * q2) : x;  // cond(tol_snr > 1e-6, ...) of solver.py:124
+  }
+}
+
+// T += (rshift * trace(T) + ashift) I   (minnorm_shift_eig / lstsq_shift_eig, solver.py:50-77); one CTA
+__global__ void __launch_bounds__(1024) trace_shift_kernel(double* __restrict__ T, int64_t n, double rshift,
+                                                           double ashift) {
+  __shared__ double red[32];
+  __shared__ double bc;
+  double tr = 0.0;
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) tr += T[k * n + k];
+  tr = warp_sum(tr);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tr;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tr = warp_sum(red[threadIdx.x]);
+    if (threadIdx.x == 0) bc = rshift * tr + ashift;
+  }
+  __syncthreads();
+  const double shift = bc;
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) T[k * n + k] += shift;
+}
+
 }  // namespace qtx
 
 using namespace qtx;
@@ -107,11 +167,12 @@ extern "C" size_t qtx_pinv_eig_workspace_size(int64_t n) {
   return ((size_t)lwork + 2 * (size_t)n) * sizeof(double) + 8192;
 }
 
-extern "C" int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double rtol, double atol, double* evals_out,
-                                  double* y_out, int32_t* info_out, void* workspace, size_t workspace_bytes,
-                                  qtx_stream_t stream) {
-  QTX_REQUIRE(T && b && y_out && info_out && workspace && n > 0 && n <= 46340, QTX_ERR_INVALID,
-              "qtx_pinv_eig_solve: bad argument");
+// eigh(T) [+ rho = U^T b (optionally SNR-damped) + y = U (lambda^+ o rho) when b != nullptr]
+static int pinv_eig_impl(double* T, int64_t n, const double* b, double rtol, double atol, double tol_snr,
+                         double* evals_out, double* y_out, int32_t* info_out, void* workspace, size_t workspace_bytes,
+                         qtx_stream_t stream) {
+  QTX_REQUIRE(T && info_out && workspace && n > 0 && n <= 46340 && (!b || y_out) && (b || evals_out), QTX_ERR_INVALID,
+              "qtx_pinv_eig_solve / qtx_eigh: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   cusolverDnHandle_t h;
   int rc = solver_handle(&h);
@@ -152,7 +213,10 @@ extern "C" int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double 
     QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnDsyevd failed (%d)", (int)s);
   }
   count_launch();
-  rows_dot_kernel<<<(unsigned)n, 256, 0, st>>>(T, n, b, rho);
+  if (evals_out) QTX_CUDA(cudaMemcpyAsync(evals_out, evals, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (!b) return QTX_OK;  // qtx_eigh: decomposition only
+  if (tol_snr > 1e-6) rows_dot_snr_kernel<<<(unsigned)n, 256, 0, st>>>(T, n, n, b, tol_snr, rho);
+  else rows_dot_kernel<<<(unsigned)n, 256, 0, st>>>(T, n, b, rho);
   QTX_LAUNCH_CHECK();
   pinv_coef_kernel<<<1, 1024, 0, st>>>(evals, n, rtol, atol, rho);
   QTX_LAUNCH_CHECK();
@@ -163,6 +227,101 @@ extern "C" int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double 
   if (split < 1) split = 1;
   cols_comb_kernel<<<dim3(gx, (unsigned)split), 256, 0, st>>>(T, n, rho, y_out);
   QTX_LAUNCH_CHECK();
-  if (evals_out) QTX_CUDA(cudaMemcpyAsync(evals_out, evals, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return QTX_OK;
+}
+
+extern "C" int qtx_pinv_eig_solve(double* T, int64_t n, const double* b, double rtol, double atol, double* evals_out,
+                                  double* y_out, int32_t* info_out, void* workspace, size_t workspace_bytes,
+                                  qtx_stream_t stream) {
+  QTX_REQUIRE(b && y_out, QTX_ERR_INVALID, "qtx_pinv_eig_solve: bad argument");
+  return pinv_eig_impl(T, n, b, rtol, atol, 0.0, evals_out, y_out, info_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int qtx_pinv_eig_solve_snr(double* T, int64_t n, const double* b, double rtol, double atol, double tol_snr,
+                                      double* evals_out, double* y_out, int32_t* info_out, void* workspace,
+                                      size_t workspace_bytes, qtx_stream_t stream) {
+  QTX_REQUIRE(b && y_out && tol_snr >= 0.0, QTX_ERR_INVALID, "qtx_pinv_eig_solve_snr: bad argument");
+  return pinv_eig_impl(T, n, b, rtol, atol, tol_snr, evals_out, y_out, info_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int qtx_eigh(double* T, int64_t n, double* evals_out, int32_t* info_out, void* workspace,
+                        size_t workspace_bytes, qtx_stream_t stream) {
+  QTX_REQUIRE(evals_out, QTX_ERR_INVALID, "qtx_eigh: bad argument");
+  return pinv_eig_impl(T, n, nullptr, 0.0, 0.0, 0.0, evals_out, nullptr, info_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int qtx_rows_dot_snr(const double* M, int64_t nrows, int64_t n, int64_t ld, const double* b, double tol_snr,
+                                double* rho_out, qtx_stream_t stream) {
+  QTX_REQUIRE(M && b && rho_out && nrows > 0 && n > 0 && ld >= n && tol_snr >= 0.0, QTX_ERR_INVALID,
+              "qtx_rows_dot_snr: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  rows_dot_snr_kernel<<<(unsigned)nrows, 256, 0, st>>>(M, n, ld, b, tol_snr, rho_out);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_pinv_apply(const double* Ut, int64_t n, const double* evals, double* rho_inout, double rtol,
+                              double atol, double* y_out, qtx_stream_t stream) {
+  QTX_REQUIRE(Ut && evals && rho_inout && y_out && n > 0, QTX_ERR_INVALID, "qtx_pinv_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rtol < 0) rtol = 1e-12;
+  pinv_coef_kernel<<<1, 1024, 0, st>>>(evals, n, rtol, atol, rho_inout);
+  QTX_LAUNCH_CHECK();
+  QTX_CUDA(cudaMemsetAsync(y_out, 0, n * sizeof(double), st));
+  unsigned gx = (unsigned)((n + 255) / 256);
+  int64_t split = (4ll * num_sms() + gx - 1) / gx;
+  if (split > n) split = n;
+  if (split < 1) split = 1;
+  cols_comb_kernel<<<dim3(gx, (unsigned)split), 256, 0, st>>>(Ut, n, rho_inout, y_out);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+// ---- diagonal-shift solvers: (T + shift I)^-1 b by Cholesky (cuSOLVER potrf / potrs, library calls) ----------
+static int potrf_lwork(int64_t n, int* lwork) {
+  cusolverDnHandle_t h;
+  int rc = solver_handle(&h);
+  if (rc) return rc;
+  cusolverStatus_t s = cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, (int)n, nullptr, (int)n, lwork);
+  if (s != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cusolverDnDpotrf_bufferSize failed with status %d", (int)s);
+    return QTX_ERR_SOLVER;
+  }
+  return QTX_OK;
+}
+
+extern "C" size_t qtx_shift_chol_workspace_size(int64_t n) {
+  int lwork = 0;
+  if (n <= 0 || n > 46340 || potrf_lwork(n, &lwork)) return 0;
+  return (size_t)lwork * sizeof(double) + 4096;  // [potrf work | 4 KB: potrs info]
+}
+
+extern "C" int qtx_shift_chol_solve(double* T, int64_t n, const double* b, double rshift, double ashift, double* y_out,
+                                    int32_t* info_out, void* workspace, size_t workspace_bytes, qtx_stream_t stream) {
+  QTX_REQUIRE(T && b && y_out && info_out && workspace && n > 0 && n <= 46340, QTX_ERR_INVALID,
+              "qtx_shift_chol_solve: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cusolverDnHandle_t h;
+  int rc = solver_handle(&h);
+  if (rc) return rc;
+  int lwork = 0;
+  rc = potrf_lwork(n, &lwork);
+  if (rc) return rc;
+  QTX_REQUIRE(workspace_bytes >= (size_t)lwork * sizeof(double) + 4096, QTX_ERR_INVALID,
+              "qtx_shift_chol_solve: workspace too small");
+  double* work = (double*)workspace;
+  int32_t* info2 = (int32_t*)((char*)workspace + (((size_t)lwork * sizeof(double) + 255) & ~(size_t)255));
+  if (rshift < 0) rshift = 1e-12;  // solver.py:12-21 for float64
+  cusolverStatus_t s = cusolverDnSetStream(h, st);
+  QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnSetStream failed (%d)", (int)s);
+  trace_shift_kernel<<<1, 1024, 0, st>>>(T, n, rshift, ashift);
+  QTX_LAUNCH_CHECK();
+  // row-major symmetric == column-major symmetric; the lower triangle is factorised in place
+  s = cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, (int)n, T, (int)n, work, lwork, info_out);
+  QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnDpotrf failed (%d)", (int)s);
+  QTX_CUDA(cudaMemcpyAsync(y_out, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  s = cusolverDnDpotrs(h, CUBLAS_FILL_MODE_LOWER, (int)n, 1, T, (int)n, y_out, (int)n, info2);
+  QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnDpotrs failed (%d)", (int)s);
+  count_launch(2);
   return QTX_OK;
 }

@@ -74,6 +74,12 @@ class RBM_Dense:
     def nparams(self) -> int:
         return self.M * self.N + self.M
 
+    @property
+    def layer_param_sizes(self):
+        """Parameter count of every ``Sequential`` layer that has parameters (block_pinv_eig, solver.py:241-249):
+        one Linear layer."""
+        return [self.nparams]
+
     def eqx_leaf_layout(self):
         """Array leaves in equinox order: Linear.weight [M, N], Linear.bias [M] (shallow_nets.py:71)."""
         return [("linear.weight", 0, (self.M, self.N)), ("linear.bias", self.M * self.N, (self.M,))]
@@ -130,6 +136,11 @@ class RBM_Conv:
     @property
     def nparams(self) -> int:
         return self.channels * self.N + self.channels
+
+    @property
+    def layer_param_sizes(self):
+        """One Conv layer carries all parameters (block_pinv_eig, solver.py:241-249)."""
+        return [self.nparams]
 
     def _expand(self):
         from . import _lib
@@ -234,6 +245,15 @@ class ResConv:
     @property
     def nparams(self) -> int:
         return self._nparams
+
+    @property
+    def layer_param_sizes(self):
+        """Parameter count per ``Sequential`` layer with parameters = per residual block (conv_nets.py:164-181:
+        ReshapeConv, the blocks, final_layer and ConvSymmetrize; only the blocks have parameters), in flat order."""
+        sizes = [0] * self.nblocks
+        for name, _, shape in self.layout:
+            sizes[int(name.split(".")[0][len("block"):])] += int(np.prod(shape))
+        return sizes
 
     def eqx_leaf_layout(self):
         """(name, offset, shape) of the array leaves as equinox stores them: Conv.weight [C, Cin, kh, kw] (2-D lattices)

@@ -65,19 +65,82 @@ def gram(A: torch.Tensor, out: Optional[torch.Tensor] = None, nslices: Optional[
     return out
 
 
-def pinv_eig_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol: float, want_evals: bool = False):
-    """y = U (lambda^+ o U^T b) from eigh(T); T is overwritten by the eigenvectors (qtx_pinv_eig_solve)."""
+def _eig_workspace(n: int):
+    wsz = _lib.lib().qtx_pinv_eig_workspace_size(n)
+    if wsz == 0:
+        raise _lib.QtxError(f"qtx_pinv_eig_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
+    return _WS.get("eig", wsz), wsz
+
+
+def pinv_eig_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol: float, want_evals: bool = False,
+                   tol_snr: float = 0.0):
+    """y = U (lambda^+ o rho) from eigh(T), rho = U^T b, optionally damped by the signal-to-noise ratio
+    (``_sum_without_noise``, solver.py:114-125); T is overwritten by the eigenvectors
+    (qtx_pinv_eig_solve / qtx_pinv_eig_solve_snr)."""
     n = T.shape[0]
     y = torch.empty(n, dtype=torch.float64, device=T.device)
     evals = torch.empty(n, dtype=torch.float64, device=T.device) if want_evals else None
     info = torch.empty(1, dtype=torch.int32, device=T.device)
-    wsz = _lib.lib().qtx_pinv_eig_workspace_size(n)
-    if wsz == 0:
-        raise _lib.QtxError(f"qtx_pinv_eig_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
-    ws = _WS.get("eig", wsz)
-    _lib.call("qtx_pinv_eig_solve", _lib.ptr(T), n, _lib.ptr(b.contiguous()), -1.0 if rtol is None else float(rtol),
-              float(atol), _lib.ptr(evals), _lib.ptr(y), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+    ws, wsz = _eig_workspace(n)
+    rt = -1.0 if rtol is None else float(rtol)
+    if tol_snr > 1e-6:
+        _lib.call("qtx_pinv_eig_solve_snr", _lib.ptr(T), n, _lib.ptr(b.contiguous()), rt, float(atol), float(tol_snr),
+                  _lib.ptr(evals), _lib.ptr(y), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+    else:
+        _lib.call("qtx_pinv_eig_solve", _lib.ptr(T), n, _lib.ptr(b.contiguous()), rt, float(atol), _lib.ptr(evals),
+                  _lib.ptr(y), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
     return (y, evals, info) if want_evals else (y, info)
+
+
+def eigh(T: torch.Tensor):
+    """(evals, info) = eigh(T); T [n, n] float64 is overwritten by the eigenvectors as ROWS (qtx_eigh)."""
+    n = T.shape[0]
+    evals = torch.empty(n, dtype=torch.float64, device=T.device)
+    info = torch.empty(1, dtype=torch.int32, device=T.device)
+    ws, wsz = _eig_workspace(n)
+    _lib.call("qtx_eigh", _lib.ptr(T), n, _lib.ptr(evals), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+    return evals, info
+
+
+def rows_dot_snr(M: torch.Tensor, b: torch.Tensor, tol_snr: float) -> torch.Tensor:
+    """rho[k] = sum_without_noise_i(M[k, i] b[i]) (solver.py:114-125) for a float64 matrix M [nrows, n]."""
+    nrows, n = M.shape
+    rho = torch.empty(nrows, dtype=torch.float64, device=M.device)
+    _lib.call("qtx_rows_dot_snr", _lib.ptr2d(M), nrows, n, M.stride(0), _lib.ptr(b.contiguous()), float(tol_snr),
+              _lib.ptr(rho), _lib.stream())
+    return rho
+
+
+def pinv_apply(Ut: torch.Tensor, evals: torch.Tensor, rho: torch.Tensor, rtol: Optional[float], atol: float):
+    """y = U (lambda^+ o rho) for eigenvectors stored as rows (qtx_pinv_apply); rho is overwritten."""
+    n = Ut.shape[0]
+    y = torch.empty(n, dtype=torch.float64, device=Ut.device)
+    _lib.call("qtx_pinv_apply", _lib.ptr(Ut), n, _lib.ptr(evals), _lib.ptr(rho), -1.0 if rtol is None else float(rtol),
+              float(atol), _lib.ptr(y), _lib.stream())
+    return y
+
+
+def shift_chol_solve(T: torch.Tensor, b: torch.Tensor, rshift: Optional[float], ashift: float):
+    """y = (T + (rshift tr T + ashift) I)^-1 b by Cholesky; T is overwritten (qtx_shift_chol_solve)."""
+    n = T.shape[0]
+    y = torch.empty(n, dtype=torch.float64, device=T.device)
+    info = torch.empty(1, dtype=torch.int32, device=T.device)
+    wsz = _lib.lib().qtx_shift_chol_workspace_size(n)
+    if wsz == 0:
+        raise _lib.QtxError(f"qtx_shift_chol_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
+    ws = _WS.get("chol", wsz)
+    _lib.call("qtx_shift_chol_solve", _lib.ptr(T), n, _lib.ptr(b.contiguous()), -1.0 if rshift is None else float(rshift),
+              float(ashift), _lib.ptr(y), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+    return y, info
+
+
+def col_sumsq(A: torch.Tensor) -> torch.Tensor:
+    """out[k] = sum_s A[s, k]^2 (float64 [np])."""
+    ns, npar = A.shape
+    out = torch.empty(npar, dtype=torch.float64, device=A.device)
+    _lib.call("qtx_col_sumsq", _lib.dtype_code(A.dtype), _lib.ptr2d(A), ns, npar, A.stride(0), _lib.ptr(out),
+              _lib.stream())
+    return out
 
 
 def matvec_t(A: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
@@ -111,12 +174,13 @@ class _CudaOps:
     matvec_t = staticmethod(matvec_t)
 
 
-def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops):
+def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops, tsolve=None):
     """MinSR solve with the rows of A sharded over the ranks (solver.py:131-147 under GSPMD):
     row-sharded -> column-sharded all-to-all (the parameter axis is zero-padded to a multiple of
     the world size like ``array_extend(Adag, ndevices)``, solver.py:136), local Gram of the column
     shard, all-reduce of the partial Ns x Ns Grams, replicated eigh + pseudo-inverse, column shard
-    of x = A^T y, all-gather.  Returns (x [Np], info)."""
+    of x = A^T y, all-gather.  ``tsolve(T, b_full) -> (y, info)`` replaces the eigh pseudo-inverse (SNR damping,
+    diagonal-shift Cholesky).  Returns (x [Np], info)."""
     dist = _dist()
     P = dist.get_world_size()
     nl, npar = A.shape
@@ -134,7 +198,7 @@ def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops):
     dist.all_reduce(T)
     bfull = torch.empty(P * nl, dtype=b.dtype, device=b.device)
     dist.all_gather_into_tensor(bfull, b.contiguous())
-    y, info = ops.pinv_eig_solve(T, bfull, rtol, atol)
+    y, info = ops.pinv_eig_solve(T, bfull, rtol, atol) if tsolve is None else tsolve(T, bfull)
     xc = ops.matvec_t(Ac, y)
     x = torch.empty(P * npc, dtype=xc.dtype, device=xc.device)
     dist.all_gather_into_tensor(x, xc.contiguous())
@@ -142,23 +206,23 @@ def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops):
 
 
 # ---- solvers (callables (A, b) -> x; A is the rank-local row block of Obar) -----------------------
-def _check_snr(tol_snr: float):
+def _snr_tsolve(rtol, atol, tol_snr):
     if tol_snr > 1e-6:
-        raise NotImplementedError("SNR regularisation (tol_snr > 0) is not implemented")
+        return lambda T, bfull: pinv_eig_solve(T, bfull, rtol, atol, tol_snr=tol_snr)
+    return None
 
 
 def minnorm_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0, nslices: Optional[int] = None):
     """x = A^+ b through T = A A^+ (MinSR, solver.py:128-149)."""
-    _check_snr(tol_snr)
 
     def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         rank, P = world()
         if P == 1:
             T = gram(A, nslices=nslices)
-            y, info = pinv_eig_solve(T, b, rtol, atol)
+            y, info = pinv_eig_solve(T, b, rtol, atol, tol_snr=tol_snr)
             solve.last_info = info
             return matvec_t(A, y)
-        x, info = distributed_minnorm(A, b, rtol, atol, _CudaOps(nslices))
+        x, info = distributed_minnorm(A, b, rtol, atol, _CudaOps(nslices), _snr_tsolve(rtol, atol, tol_snr))
         solve.last_info = info
         return x
 
@@ -166,19 +230,40 @@ def minnorm_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: f
     return solve
 
 
+def _gather_rows_as_columns(M: torch.Tensor) -> torch.Tensor:
+    """[k, nl] per rank -> [k, P nl] with rank-major columns (the global sample order)."""
+    dist = _dist()
+    P = dist.get_world_size()
+    buf = torch.empty((P,) + tuple(M.shape), dtype=M.dtype, device=M.device)
+    dist.all_gather_into_tensor(buf, M.contiguous())
+    return buf.permute(1, 0, 2).reshape(M.shape[0], P * M.shape[1]).contiguous()
+
+
 def lstsq_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0, nslices: Optional[int] = None):
     """x = (A^+ A)^-1 A^+ b through S = A^+ A (SR, solver.py:152-164)."""
-    _check_snr(tol_snr)
 
     def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         rank, P = world()
         At = A.t().contiguous()  # [np, nl]: S = At At^T sums over the local samples
         S = gram(At, nslices=nslices)
-        F = matvec_t(A, b)
         if P > 1:
             _dist().all_reduce(S)
-            _dist().all_reduce(F)
-        x, info = pinv_eig_solve(S, F, rtol, atol)
+        if tol_snr > 1e-6:
+            # rho_sk = (A V)[s, k] b[s] is damped per eigen-direction k over ALL samples s (solver.py:160-161)
+            evals, info = eigh(S)  # S now holds V^T (eigenvectors as rows)
+            M = torch.matmul(S, At.to(torch.float64))  # [np, nl] = (A V)^T, library GEMM (np is small here)
+            bl = b
+            if P > 1:
+                M = _gather_rows_as_columns(M)
+                bl = torch.empty(P * b.shape[0], dtype=b.dtype, device=b.device)
+                _dist().all_gather_into_tensor(bl, b.contiguous())
+            rho = rows_dot_snr(M, bl, tol_snr)
+            x = pinv_apply(S, evals, rho, rtol, atol)
+        else:
+            F = matvec_t(A, b)
+            if P > 1:
+                _dist().all_reduce(F)
+            x, info = pinv_eig_solve(S, F, rtol, atol)
         solve.last_info = info
         return x
 
@@ -200,11 +285,147 @@ def auto_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: floa
 
 def minsr_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0):
     """Solver of T x = b for a given Hermitian T (solver.py:262-294)."""
-    _check_snr(tol_snr)
 
     def solve(T: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-        y, _ = pinv_eig_solve(T.clone(), b, rtol, atol)
+        y, _ = pinv_eig_solve(T.clone(), b, rtol, atol, tol_snr=tol_snr)
         return y
+
+    return solve
+
+
+def minnorm_shift_eig(rshift: Optional[float] = None, ashift: float = 1e-4, nslices: Optional[int] = None):
+    """x = A^+ (A A^+ + shift I)^-1 b, shift = rshift tr(T) + ashift, by Cholesky (solver.py:50-62)."""
+
+    def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        rank, P = world()
+        if P == 1:
+            T = gram(A, nslices=nslices)
+            y, info = shift_chol_solve(T, b, rshift, ashift)
+            solve.last_info = info
+            return matvec_t(A, y)
+        x, info = distributed_minnorm(A, b, None, 0.0, _CudaOps(nslices),
+                                      lambda T, bfull: shift_chol_solve(T, bfull, rshift, ashift))
+        solve.last_info = info
+        return x
+
+    solve.last_info = None
+    return solve
+
+
+def lstsq_shift_eig(rshift: Optional[float] = None, ashift: float = 1e-4, nslices: Optional[int] = None):
+    """x = (A^+ A + shift I)^-1 A^+ b by Cholesky (solver.py:65-77)."""
+
+    def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        rank, P = world()
+        S = gram(A.t().contiguous(), nslices=nslices)
+        F = matvec_t(A, b)
+        if P > 1:
+            _dist().all_reduce(S)
+            _dist().all_reduce(F)
+        x, info = shift_chol_solve(S, F, rshift, ashift)
+        solve.last_info = info
+        return x
+
+    solve.last_info = None
+    return solve
+
+
+def auto_shift_eig(rshift: Optional[float] = None, ashift: float = 1e-4, nslices: Optional[int] = None):
+    """Diagonal-shift SR when Ns >= Np, MinSR otherwise (solver.py:80-90); Ns is the GLOBAL sample count."""
+    mn = minnorm_shift_eig(rshift, ashift, nslices)
+    ls = lstsq_shift_eig(rshift, ashift, nslices)
+
+    def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        _, P = world()
+        return mn(A, b) if A.shape[0] * P < A.shape[1] else ls(A, b)
+
+    return solve
+
+
+def _dot(x: torch.Tensor, y: torch.Tensor) -> float:
+    """x . y on the device (one row of qtx_matvec), read back for the CG recurrence."""
+    return float(matvec(x.view(1, -1), y)[0])
+
+
+class lstsq_shift_cg:
+    """Conjugate-gradient solve of (A^+ A + diag_shift diag(A^+ A)) x = A^+ b (solver.py:24-47).  The iteration
+    is ``jax.scipy.sparse.linalg.cg`` with x0 = 0 and no preconditioner: stop when |r|^2 <= max(rtol^2 |F|^2,
+    atol^2) or after ``maxiter`` (default 10 Np) iterations.  S is never formed: two passes over A per iteration."""
+
+    def __init__(self, diag_shift: float = 0.01, rtol: float = 1e-5, atol: float = 0.0, maxiter: Optional[int] = None):
+        self.diag_shift, self.rtol, self.atol, self.maxiter = diag_shift, rtol, atol, maxiter
+        self.last_iterations = None
+
+    def S_apply(self, A: torch.Tensor, x: torch.Tensor, diag: torch.Tensor) -> torch.Tensor:
+        _, P = world()
+        out = matvec_t(A, matvec(A, x))
+        if P > 1:
+            _dist().all_reduce(out)
+        return out.add_(diag * x, alpha=self.diag_shift)
+
+    def __call__(self, A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        _, P = world()
+        F = matvec_t(A, b)
+        diag = col_sumsq(A)
+        if P > 1:
+            _dist().all_reduce(F)
+            _dist().all_reduce(diag)
+        maxiter = 10 * F.numel() if self.maxiter is None else self.maxiter
+        x = torch.zeros_like(F)
+        r = F.clone()
+        p = r.clone()
+        gamma = _dot(r, r)
+        atol2 = max(self.rtol ** 2 * _dot(F, F), self.atol ** 2)
+        k = 0
+        while gamma > atol2 and k < maxiter:
+            Ap = self.S_apply(A, p, diag)
+            alpha = gamma / _dot(p, Ap)
+            _axpby(alpha, p, 1.0, x)
+            _axpby(-alpha, Ap, 1.0, r)
+            gamma_new = _dot(r, r)
+            _axpby(1.0, r, gamma_new / gamma, p)
+            gamma = gamma_new
+            k += 1
+        self.last_iterations = k
+        return x
+
+
+def block_pinv_eig(state: Variational, rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0,
+                   nslices: Optional[int] = None):
+    """Layer-wise solver (solver.py:204-259): the parameter axis is cut at the layer boundaries of a
+    ``Sequential`` model, every block is solved with ``auto_pinv_eig`` against Ebar / nlayers and the block
+    solutions are concatenated."""
+    sizes = getattr(state.model, "layer_param_sizes", None)
+    if sizes is None:
+        raise ValueError("`block_pinv_eig` solver only works for `Sequential` models.")
+    sizes = [int(n) for n in sizes if int(n) > 0]
+    bounds = [0]
+    for n in sizes:
+        bounds.append(bounds[-1] + n)
+    if bounds[-1] != state.nparams:
+        raise ValueError("layer_param_sizes do not add up to the number of parameters")
+    nlayers = len(sizes)
+    solver0 = auto_pinv_eig(rtol, atol, tol_snr, nslices)
+
+    def solve(Obar: torch.Tensor, Ebar: torch.Tensor) -> torch.Tensor:
+        Eb = _axpby(1.0 / nlayers, Ebar, 0.0, torch.empty_like(Ebar))
+        parts = []
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            parts.append(solver0(Obar[:, lo:hi].contiguous(), Eb))
+        return torch.cat(parts)
+
+    return solve
+
+
+def sgd_solver():
+    """x = A^+ b / Ns (solver.py:297-302; Ns is the global sample count)."""
+
+    def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        _, P = world()
+        x = matvec_t(A, b)
+        if P > 1:
+            _dist().all_reduce(x)
+        return _axpby(1.0 / (A.shape[0] * P), x, 0.0, torch.empty_like(x))
 
     return solve
 
@@ -553,12 +774,6 @@ class MinSR(SR):
 # ---- momentum variants (quantax/optimizer/sr.py:198-429) --------------------------------------------
 def _vec(n: int) -> torch.Tensor:
     return torch.zeros(n, dtype=torch.float64, device=device())
-
-
-def _axpby(a: float, x: torch.Tensor, b: float, y: torch.Tensor) -> torch.Tensor:
-    """y <- a x + b y (in place on y)."""
-    _lib.call("qtx_axpby", x.numel(), float(a), _lib.ptr(x.contiguous()), float(b), _lib.ptr(y), _lib.stream())
-    return y
 
 
 def _scale_columns(A: torch.Tensor, d: torch.Tensor) -> None:

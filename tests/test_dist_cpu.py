@@ -36,7 +36,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ns, npar, out):
+def _worker(rank, world, port, ns, npar, out, shift=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -50,8 +50,17 @@ def _worker(rank, world, port, ns, npar, out):
         nl = ns // world
         Al = torch.from_numpy(A[rank * nl:(rank + 1) * nl].copy())
         bl = torch.from_numpy(b[rank * nl:(rank + 1) * nl].copy())
-        x, _ = distributed_minnorm(Al, bl, None, 0.0, CpuOps)
-        xo = osolver.minnorm_pinv_eig(A, b)
+        if shift:
+            # pluggable T-solver (diagonal-shift Cholesky on the GPU; a dense solve stands in here)
+            def tsolve(T, bfull):
+                lam = 1e-3 * torch.trace(T) + 1e-4
+                return torch.linalg.solve(T + lam * torch.eye(T.shape[0], dtype=T.dtype), bfull), None
+
+            x, _ = distributed_minnorm(Al, bl, None, 0.0, CpuOps, tsolve)
+            xo = osolver.minnorm_shift_eig(A, b, 1e-3, 1e-4)
+        else:
+            x, _ = distributed_minnorm(Al, bl, None, 0.0, CpuOps)
+            xo = osolver.minnorm_pinv_eig(A, b)
         err = float(np.linalg.norm(x.numpy() - xo) / np.linalg.norm(xo))
         # every rank must hold the same full step
         gathered = [torch.empty_like(x) for _ in range(world)]
@@ -78,6 +87,20 @@ def test_distributed_minnorm_two_ranks(ns, npar):
     assert shape == (npar,)
     assert same
     assert err < 1e-8, err
+
+
+def test_distributed_minnorm_with_shift_solver_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 16, 41, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    err, same, shape = q.get(timeout=10)
+    assert shape == (41,) and same and err < 1e-9, err
 
 
 def test_sampler_rejects_indivisible_sample_count(monkeypatch):

@@ -278,3 +278,61 @@ def test_mix_sweep_reduces_to_plain_sweep_for_one_component():
     a = osmp.sweep(osmp.RBMChainModel(net), spins, 9, "exchange", neighbors=table, seed=11, step0=4)
     b = osmp.mix_sweep(osmp.RBMChainModel(net), spins, [0] * 9, ["exchange"], [table], [1], seed=11, step0=4)
     assert np.array_equal(a["spins"], b["spins"]) and np.array_equal(a["naccept"], b["naccept"])
+
+
+# ---- solver variants (quantax/optimizer/solver.py:24-90,114-125,204-259,297-302) ---------------------------
+def _lsq_problem(ns, npar, seed=0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((ns, npar)) * np.exp(0.5 * rng.standard_normal((1, npar)))
+    A -= A.mean(axis=0, keepdims=True)
+    return A / np.sqrt(ns), rng.standard_normal(ns) / np.sqrt(ns)
+
+
+@pytest.mark.parametrize("ns,npar", [(24, 60), (60, 24)])
+def test_oracle_shift_solvers_solve_the_shifted_normal_equations(ns, npar):
+    A, b = _lsq_problem(ns, npar)
+    x = osolver.auto_shift_eig(A, b, rshift=1e-3, ashift=1e-4)
+    # both branches are the ridge solution with lambda = rshift tr + ashift; tr(A A^T) == tr(A^T A)
+    lam = 1e-3 * np.trace(A @ A.T) + 1e-4
+    ref = np.linalg.solve(A.T @ A + lam * np.eye(npar), A.T @ b)
+    assert np.allclose(x, ref, rtol=1e-9, atol=1e-12)
+    assert np.allclose(osolver.minnorm_shift_eig(A, b, 1e-3, 1e-4), osolver.lstsq_shift_eig(A, b, 1e-3, 1e-4), rtol=1e-9)
+
+
+def test_oracle_cg_converges_to_the_direct_solution():
+    A, b = _lsq_problem(80, 30, seed=1)
+    x, k = osolver.lstsq_shift_cg(A, b, diag_shift=0.01, rtol=1e-10, return_iterations=True)
+    S = A.T @ A
+    ref = np.linalg.solve(S + 0.01 * np.diag(np.diag(S)), A.T @ b)
+    assert 0 < k <= 300
+    assert np.allclose(x, ref, rtol=1e-7, atol=1e-10)
+    # loose tolerance stops early; maxiter caps the iteration count
+    _, k2 = osolver.lstsq_shift_cg(A, b, rtol=1e-2, return_iterations=True)
+    assert k2 < k
+    assert osolver.lstsq_shift_cg(A, b, rtol=1e-12, maxiter=3, return_iterations=True)[1] == 3
+
+
+def test_oracle_block_solver_and_sgd():
+    A, b = _lsq_problem(20, 45, seed=2)
+    sizes = [10, 0, 20, 15]
+    x = osolver.block_pinv_eig(A, b, sizes)
+    assert x.shape == (45,)
+    assert np.allclose(x[:10], osolver.auto_pinv_eig(A[:, :10], b / 3))
+    assert np.allclose(x[30:], osolver.auto_pinv_eig(A[:, 30:], b / 3))
+    assert np.allclose(osolver.block_pinv_eig(A, b, [45]), osolver.auto_pinv_eig(A, b))
+    assert np.allclose(osolver.sgd_solver(A, b), A.T @ b / 20)
+
+
+def test_oracle_snr_damping_limits():
+    A, b = _lsq_problem(16, 50, seed=3)
+    x0 = osolver.minnorm_pinv_eig(A, b)
+    assert np.allclose(osolver.minnorm_pinv_eig(A, b, tol_snr=1e-7), x0)  # below the reference's 1e-6 switch
+    xs = osolver.minnorm_pinv_eig(A, b, tol_snr=1.0)
+    assert np.linalg.norm(xs) < np.linalg.norm(x0)  # every eigen-direction is damped by a factor in (0, 1]
+    # the damping factor per direction, recomputed independently
+    vals, U = np.linalg.eigh(A @ A.T)
+    r = U * b[:, None]
+    mean = r.mean(axis=0)
+    snr = np.abs(mean) / np.sqrt(((r - mean) ** 2).mean(axis=0) / 16)
+    rho = r.sum(axis=0) / (1 + (1.0 / snr) ** 6)
+    assert np.allclose(xs, A.T @ (U @ (osolver.eigs_inv(vals) * rho)), rtol=1e-9, atol=1e-12)

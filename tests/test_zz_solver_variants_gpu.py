@@ -1,0 +1,146 @@
+"""GPU parity tests of the remaining solver factories of quantax/optimizer/solver.py against the CPU oracle:
+signal-to-noise damping (tol_snr), diagonal-shift Cholesky solvers, conjugate gradients, the layer-wise block
+solver and the plain gradient.  (Named zz so that it runs after the hot-path suites.)"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import solver as osolver
+from tests.gpu_util import to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qtx():
+    import quantax_b200 as q
+
+    torch.cuda.set_device(0)
+    return q
+
+
+def _problem(ns, npar, seed=0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((ns, npar)) * np.exp(0.5 * rng.standard_normal((1, npar)))
+    A -= A.mean(axis=0, keepdims=True)
+    return A / np.sqrt(ns), rng.standard_normal(ns) / np.sqrt(ns)
+
+
+def _rel(x, ref):
+    return float(np.linalg.norm(x - ref) / np.linalg.norm(ref))
+
+
+@pytest.mark.parametrize("ns,npar", [(96, 700), (130, 333), (200, 64)])
+@pytest.mark.parametrize("tol_snr", [0.5, 2.0])
+def test_snr_damped_solvers(qtx, ns, npar, tol_snr):
+    A, b = _problem(ns, npar, seed=ns)
+    At, bt = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    x = to_np(qtx.optimizer.auto_pinv_eig(rtol=1e-10, tol_snr=tol_snr)(At.clone(), bt))
+    ref = osolver.auto_pinv_eig(A, b, rtol=1e-10, tol_snr=tol_snr)
+    assert _rel(x, ref) < 1e-8
+    if ns < npar:
+        T = A @ A.T
+        y = to_np(qtx.optimizer.minsr_pinv_eig(rtol=1e-10, tol_snr=tol_snr)(torch.from_numpy(T).cuda(), bt))
+        assert _rel(y, osolver.minsr_pinv_eig(T, b, rtol=1e-10, tol_snr=tol_snr)) < 1e-8
+
+
+def test_rows_dot_snr_kernel(qtx):
+    from quantax_b200.optimizer import rows_dot_snr
+
+    rng = np.random.default_rng(5)
+    M = rng.standard_normal((37, 501))
+    b = rng.standard_normal(501)
+    pad = torch.zeros((37, 512), dtype=torch.float64, device="cuda")
+    pad[:, :501] = torch.from_numpy(M).cuda()
+    for tol in (0.0, 1.0):
+        rho = to_np(rows_dot_snr(pad[:, :501], torch.from_numpy(b).cuda(), tol))  # padded rows: ld = 512
+        ref = osolver._sum_without_noise((M * b[None, :]).T, tol)
+        assert np.allclose(rho, ref, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("ns,npar", [(96, 700), (257, 1000), (200, 64), (2, 5)])
+def test_shift_cholesky_solvers(qtx, ns, npar):
+    A, b = _problem(ns, npar, seed=ns + 1)
+    At, bt = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    for rshift, ashift in ((None, 1e-4), (1e-3, 0.0)):
+        solver = qtx.optimizer.auto_shift_eig(rshift, ashift)
+        x = to_np(solver(At.clone(), bt))
+        assert _rel(x, osolver.auto_shift_eig(A, b, rshift, ashift)) < 1e-9
+    mn, ls = qtx.optimizer.minnorm_shift_eig(1e-3, 1e-4), qtx.optimizer.lstsq_shift_eig(1e-3, 1e-4)
+    assert _rel(to_np(mn(At.clone(), bt)), to_np(ls(At.clone(), bt))) < 1e-8
+    assert int(mn.last_info.item()) == 0
+
+
+def test_shift_cholesky_reports_indefinite_matrix(qtx):
+    from quantax_b200.optimizer import shift_chol_solve
+
+    T = torch.tensor([[1.0, 2.0], [2.0, 1.0]], dtype=torch.float64, device="cuda")
+    _, info = shift_chol_solve(T, torch.ones(2, dtype=torch.float64, device="cuda"), 0.0, 0.0)
+    assert int(info.item()) > 0
+
+
+def test_col_sumsq(qtx):
+    from quantax_b200.optimizer import col_sumsq
+
+    rng = np.random.default_rng(7)
+    for dt, tol in ((torch.float64, 1e-13), (torch.float32, 1e-6)):
+        for ns, npar in ((37, 101), (64, 1000), (5, 3)):
+            At = torch.from_numpy(rng.standard_normal((ns, npar))).to("cuda", dt)
+            ref = (to_np(At).astype(np.float64) ** 2).sum(axis=0)
+            assert np.allclose(to_np(col_sumsq(At)), ref, rtol=tol * 10, atol=tol)
+
+
+def test_conjugate_gradient_solver(qtx):
+    A, b = _problem(300, 80, seed=11)
+    At, bt = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    cg = qtx.optimizer.lstsq_shift_cg(diag_shift=0.01, rtol=1e-10)
+    x = to_np(cg(At, bt))
+    ref, k = osolver.lstsq_shift_cg(A, b, 0.01, 1e-10, return_iterations=True)
+    assert _rel(x, ref) < 1e-7
+    assert abs(cg.last_iterations - k) <= 2
+    S = A.T @ A
+    direct = np.linalg.solve(S + 0.01 * np.diag(np.diag(S)), A.T @ b)
+    assert _rel(x, direct) < 1e-6
+    capped = qtx.optimizer.lstsq_shift_cg(rtol=1e-12, maxiter=3)
+    capped(At, bt)
+    assert capped.last_iterations == 3
+
+
+def test_block_solver_and_sgd(qtx):
+    qtx.sites.Sites._SITES = None
+    qtx.sites.Square(4, Nparticles=(8, 8))
+    model = qtx.model.ResConv(3, 4, 3, dtype=torch.float64)
+    state = qtx.state.Variational(model)
+    sizes = model.layer_param_sizes
+    assert len(sizes) == 3 and sum(sizes) == model.nparams
+    assert sizes[0] == 4 * 1 * 9 + 4 + 4 * 4 * 9 + 4 and sizes[2] == 2 * 4 * 4 * 9 + 4
+    A, b = _problem(48, model.nparams, seed=13)
+    At, bt = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    x = to_np(qtx.optimizer.block_pinv_eig(state, rtol=1e-10)(At, bt))
+    assert _rel(x, osolver.block_pinv_eig(A, b, sizes, rtol=1e-10)) < 1e-8
+    g = to_np(qtx.optimizer.sgd_solver()(At, bt))
+    assert np.allclose(g, osolver.sgd_solver(A, b), rtol=1e-12, atol=1e-14)
+    rbm = qtx.state.Variational(qtx.model.RBM_Dense(8))
+    assert rbm.model.layer_param_sizes == [rbm.nparams]
+
+
+def test_sr_with_shift_solver_runs_a_vmc_step(qtx):
+    """The solver argument of SR is any callable (sr.py:32,106): a VMC step with auto_shift_eig against the oracle."""
+    from oracle import models as omodels, operator as oop, sites as osites
+    from tests.gpu_util import lattice_pair, make_rbm
+
+    lat, olat = lattice_pair(qtx, "square", 4, (8, 8))
+    model, net = make_rbm(qtx, 16, 24, torch.float64, seed=3)
+    state = qtx.state.Variational(model)
+    H = qtx.operator.Heisenberg(msr=True)
+    sampler = qtx.sampler.SpinExchange(state, nsamples=128)
+    opt = qtx.optimizer.SR(state, H, solver=qtx.optimizer.auto_shift_eig(1e-3, 1e-4))
+    samples = sampler.sweep()
+    step = to_np(opt.get_step(samples))
+    s = to_np(samples.spins)
+    oH = oop.to_array_op_list(oop.heisenberg_op_list(olat, msr=True))
+    Eo = oop.oloc(oH, net.forward, s)
+    rw = np.ones(len(s))
+    ob, _ = osolver.obar(net.jacobian(s), rw)
+    eb, _, _ = osolver.ebar(Eo, rw)
+    assert _rel(step, osolver.auto_shift_eig(ob, eb, 1e-3, 1e-4)) < 1e-8
