@@ -63,6 +63,7 @@ void qtx_launch_count_reset(void);
  * 5 'I'.  Terms are stored in op-list order; `nflips[t]` is the number of x/+/- factors.
  * ------------------------------------------------------------------------------------------ */
 #define QTX_MAX_TERM_SITES 4
+#define QTX_MAX_PEERS 8 /* ranks of one NVSwitch node in the fused Gram + exchange path */
 enum qtx_opcode { QTX_OP_NONE = 0, QTX_OP_Z = 1, QTX_OP_X = 2, QTX_OP_P = 3, QTX_OP_M = 4, QTX_OP_I = 5 };
 
 /* ------------------------------------------------------------------------------------------

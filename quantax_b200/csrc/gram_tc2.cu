@@ -100,9 +100,17 @@ __device__ __forceinline__ void tile2_from_index(int t, int& I2, int& J) {
   J = t - i * (i + 1);
 }
 
-template <int S>
-__global__ void __launch_bounds__(kThreads, 1)
-    gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, GramTcParams p) {
+// Peers of the fused Gram + exchange path (peer.cu): slot[q] is where rank q expects THIS rank's partial T
+// ([ns, ns] float64, only j <= i is written); slot[rank] is unused (the own partial stays in p.T).
+struct GramPushParams {
+  int nranks;
+  int rank;
+  double* slot[QTX_MAX_PEERS];
+};
+
+template <int S, bool PUSH>
+__device__ __forceinline__ void gram_tc2_body(const CUtensorMap& tmapA, const CUtensorMap& tmapB, const GramTcParams& p,
+                                              const GramPushParams& pp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t stage_bytes = (uint32_t)S * (kSliceBytes + kSliceBytesB2);
@@ -248,6 +256,29 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(tmem_empty);
         tphase ^= 1;
+        if constexpr (PUSH) {
+          // The tile is final after the last pass: copy this warp's 32 rows (lower triangle only) from the local T
+          // (L2-hot; written by the lanes of this warp, ordered by the __syncwarp above) into every peer's staging
+          // slot.  Lanes walk a row, so every store instruction is one contiguous 256-byte run over NVLink, and the
+          // MMA warp is already working on the next tile (TMEM was released above).
+          if (pass == npasses - 1 && any) {
+            const int64_t row0 = (int64_t)I2 * 256 + (int64_t)rank * kTile + lg * 32;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int64_t r = row0 + rr;
+              if (r >= p.ns) break;
+              const double* srow = p.T + r * p.ns;
+#pragma unroll
+              for (int e = 0; e < kTile / 32; ++e) {
+                const int64_t c = (int64_t)J * kTile + lane + 32 * e;
+                if (c <= r) {
+                  const double v = __ldcg(srow + c);
+                  for (int q = 0; q < pp.nranks; ++q)
+                    if (q != pp.rank) pp.slot[q][r * p.ns + c] = v;
+                }
+              }
+            }
+          }
+        }
       }
     }
   }
@@ -258,9 +289,26 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 template <int S>
+__global__ void __launch_bounds__(kThreads, 1)
+    gram_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, GramTcParams p) {
+  gram_tc2_body<S, false>(tmapA, tmapB, p, GramPushParams{});
+}
+
+// last K chunk of the fused Gram + exchange path: same kernel, finished tiles are also stored to the peers
+template <int S>
+__global__ void __launch_bounds__(kThreads, 1)
+    gram_tc2_push_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                         GramTcParams p, const __grid_constant__ GramPushParams pp) {
+  gram_tc2_body<S, true>(tmapA, tmapB, p, pp);
+}
+
+template <int S>
 static int launch_gram_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GramTcParams& p, int grid, size_t smem,
-                           cudaStream_t st) {
-  QTX_CUDA(cudaFuncSetAttribute(gram_tc2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                           cudaStream_t st, const GramPushParams* push) {
+  if (push)
+    QTX_CUDA(cudaFuncSetAttribute(gram_tc2_push_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else
+    QTX_CUDA(cudaFuncSetAttribute(gram_tc2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
@@ -273,23 +321,39 @@ static int launch_gram_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  QTX_CUDA(cudaLaunchKernelEx(&cfg, gram_tc2_kernel<S>, tmA, tmB, p));
+  if (push) QTX_CUDA(cudaLaunchKernelEx(&cfg, gram_tc2_push_kernel<S>, tmA, tmB, p, *push));
+  else QTX_CUDA(cudaLaunchKernelEx(&cfg, gram_tc2_kernel<S>, tmA, tmB, p));
   count_launch();
   return QTX_OK;
 }
 
+static int gram_tc2_dispatch(int s, const CUtensorMap& tmA, const CUtensorMap& tmB, const GramTcParams& p, int grid,
+                             size_t smem, cudaStream_t st, const GramPushParams* push) {
+  switch (s) {
+    case 1: return launch_gram_tc2<1>(tmA, tmB, p, grid, smem, st, push);
+    case 2: return launch_gram_tc2<2>(tmA, tmB, p, grid, smem, st, push);
+    case 3: return launch_gram_tc2<3>(tmA, tmB, p, grid, smem, st, push);
+    case 4: return launch_gram_tc2<4>(tmA, tmB, p, grid, smem, st, push);
+    case 5: return launch_gram_tc2<5>(tmA, tmB, p, grid, smem, st, push);
+    case 6: return launch_gram_tc2<6>(tmA, tmB, p, grid, smem, st, push);
+    case 7: return launch_gram_tc2<7>(tmA, tmB, p, grid, smem, st, push);
+    default: return launch_gram_tc2<8>(tmA, tmB, p, grid, smem, st, push);
+  }
+}
+
 int gram_tc2_launch(int s, const CUtensorMap& tmA, const CUtensorMap& tmB, const GramTcParams& p, int grid, size_t smem,
                     cudaStream_t st) {
-  switch (s) {
-    case 1: return launch_gram_tc2<1>(tmA, tmB, p, grid, smem, st);
-    case 2: return launch_gram_tc2<2>(tmA, tmB, p, grid, smem, st);
-    case 3: return launch_gram_tc2<3>(tmA, tmB, p, grid, smem, st);
-    case 4: return launch_gram_tc2<4>(tmA, tmB, p, grid, smem, st);
-    case 5: return launch_gram_tc2<5>(tmA, tmB, p, grid, smem, st);
-    case 6: return launch_gram_tc2<6>(tmA, tmB, p, grid, smem, st);
-    case 7: return launch_gram_tc2<7>(tmA, tmB, p, grid, smem, st);
-    default: return launch_gram_tc2<8>(tmA, tmB, p, grid, smem, st);
-  }
+  return gram_tc2_dispatch(s, tmA, tmB, p, grid, smem, st, nullptr);
+}
+
+// last K chunk of qtx_gram_push: slots[q] = staging slot of this rank's partial on rank q (device pointers)
+int gram_tc2_launch_push(int s, const CUtensorMap& tmA, const CUtensorMap& tmB, const GramTcParams& p, int grid,
+                         size_t smem, cudaStream_t st, int nranks, int rank, double* const* slots) {
+  GramPushParams pp{};
+  pp.nranks = nranks;
+  pp.rank = rank;
+  for (int q = 0; q < nranks; ++q) pp.slot[q] = slots[q];
+  return gram_tc2_dispatch(s, tmA, tmB, p, grid, smem, st, &pp);
 }
 
 }  // namespace qtx
