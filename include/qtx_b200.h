@@ -298,6 +298,34 @@ int qtx_gram(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int n
              double* T_out, int T_accum, void* workspace, size_t workspace_bytes,
              qtx_stream_t stream);
 
+/* ---- fused Gram + exchange over peer memory (distributed MinSR, solver.py:134-139) --------------
+ * The reference sums the partial Gram matrices of the column shards through XLA's GSPMD
+ * all-reduce.  Here every rank owns a staging area stage[P][ns][ns] (float64) and a flag array
+ * flags[P] (uint64), allocated with qtx_peer_alloc, exported with qtx_peer_export (64-byte CUDA
+ * IPC handle) and mapped by the other ranks of the node with qtx_peer_open.
+ *   qtx_gram_push   : qtx_gram whose epilogue also stores every finished tile (j <= i) into
+ *                     peer_slots[q] = stage_q + rank * ns * ns for all q != rank (NVLink stores
+ *                     overlapped with the MMAs of the next tile);
+ *   qtx_peer_signal : flags_q[rank] = epoch on every rank q (release at system scope), enqueued
+ *                     after the push;
+ *   qtx_gram_reduce : waits (bounded by timeout_s, default 60 s; traps on expiry) until
+ *                     my_flags[q] >= epoch for all q, then T_out[i,j] = T_out[j,i] =
+ *                     sum_q partials[q][i,j] in rank order (bit-identical on all ranks);
+ *                     partials[rank] may alias T_out.  my_flags = NULL skips the wait.
+ * Host pointer arrays (peer_slots, peer_flags, partials) hold nranks device pointers. */
+int qtx_peer_alloc(size_t bytes, void** ptr_out);
+int qtx_peer_free(void* ptr);
+int qtx_peer_export(void* ptr, void* handle64_out);
+int qtx_peer_open(const void* handle64, void** ptr_out);
+int qtx_peer_close(void* ptr);
+int qtx_gram_push(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int nslices,
+                  double* T_out, int nranks, int rank, void* const* peer_slots, void* workspace,
+                  size_t workspace_bytes, qtx_stream_t stream);
+int qtx_peer_signal(void* const* peer_flags, int nranks, int rank, uint64_t epoch,
+                    qtx_stream_t stream);
+int qtx_gram_reduce(const void* const* partials, int nranks, int64_t ns, double* T_out,
+                    const void* my_flags, uint64_t epoch, double timeout_s, qtx_stream_t stream);
+
 /* (lambda, U) = eigh(T); y = U (lambda^+ o (U^T b)) with the soft pseudo-inverse
  * lambda^+ = 1 / (lambda (1 + ((rtol max|lambda| + atol)/|lambda|)^6)), 0 where lambda == 0
  * (solver.py:94-101,142-146; minsr_pinv_eig solver.py:262-294).  rtol < 0 selects the dtype

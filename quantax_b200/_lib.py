@@ -63,6 +63,14 @@ SIGNATURES = {
     "qtx_ebar": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "qtx_gram_workspace_size": (_sz, [_i32, _i64, _i64, _i32]),
     "qtx_gram": (_i32, [_i32, _vp, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "qtx_peer_alloc": (_i32, [_sz, _vp]),
+    "qtx_peer_free": (_i32, [_vp]),
+    "qtx_peer_export": (_i32, [_vp, _vp]),
+    "qtx_peer_open": (_i32, [_vp, _vp]),
+    "qtx_peer_close": (_i32, [_vp]),
+    "qtx_gram_push": (_i32, [_i32, _vp, _i64, _i64, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "qtx_peer_signal": (_i32, [_vp, _i32, _i32, _u64, _vp]),
+    "qtx_gram_reduce": (_i32, [_vp, _i32, _i64, _vp, _vp, _u64, _f64, _vp]),
     "qtx_pinv_eig_workspace_size": (_sz, [_i64]),
     "qtx_pinv_eig_solve": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qtx_pinv_eig_solve_snr": (_i32, [_vp, _i64, _vp, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _sz, _vp]),

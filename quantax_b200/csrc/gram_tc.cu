@@ -296,6 +296,8 @@ static EncodeTiledFn get_encode_fn() {
 
 int gram_tc2_launch(int s, const CUtensorMap& tmA, const CUtensorMap& tmB, const GramTcParams& p, int grid, size_t smem,
                     cudaStream_t st);
+int gram_tc2_launch_push(int s, const CUtensorMap& tmA, const CUtensorMap& tmB, const GramTcParams& p, int grid,
+                         size_t smem, cudaStream_t st, int nranks, int rank, double* const* slots);
 
 static bool use_2cta() {
   const char* e = getenv("QTX_GRAM_2CTA");
@@ -322,8 +324,11 @@ size_t gram_tc_workspace(int dtype, int64_t ns, int64_t np, int nslices) {
   return (size_t)s * ns_pad * kc_pad + (size_t)ns_pad * sizeof(double) + 1024;
 }
 
-int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int nslices, double* Tout, int accum,
-            void* ws, size_t ws_bytes, cudaStream_t st) {
+// push_slots != nullptr: fused Gram + exchange (qtx_gram_push) -- the last K chunk runs the PUSH kernel, which also
+// stores every finished tile into push_slots[q] (q != push_rank), the staging slots of the peers.
+static int gram_tc_impl(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int nslices, double* Tout,
+                        int accum, void* ws, size_t ws_bytes, cudaStream_t st, int push_nranks, int push_rank,
+                        double* const* push_slots) {
   int s;
   int64_t ns_pad, kc, kc_pad;
   gram_tc_sizes(dtype, ns, np, nslices, s, ns_pad, kc, kc_pad);
@@ -348,6 +353,7 @@ int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int ns
   QTX_REQUIRE(cr == CUDA_SUCCESS, QTX_ERR_CUDA, "qtx_gram: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
   const bool pair = use_2cta();
+  QTX_REQUIRE(pair || !push_slots, QTX_ERR_UNSUPPORTED, "qtx_gram_push needs the CTA-pair kernel (QTX_GRAM_2CTA=1)");
   CUtensorMap tmapB;  // 64-row boxes: each CTA of a pair stages half of the J panel
   if (pair) {
     cuuint32_t boxB[3] = {kBK, kTile / 2, 1};
@@ -396,7 +402,10 @@ int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int ns
     p.accum = (accum != 0 || chunk > 0) ? 1 : 0;
     int rc = QTX_OK;
     if (pair) {
-      rc = gram_tc2_launch(s, tmap, tmapB, p, grid, smem, st);
+      if (push_slots && k0 + kc >= np)
+        rc = gram_tc2_launch_push(s, tmap, tmapB, p, grid, smem, st, push_nranks, push_rank, push_slots);
+      else
+        rc = gram_tc2_launch(s, tmap, tmapB, p, grid, smem, st);
       if (rc) return rc;
       continue;
     }
@@ -413,6 +422,16 @@ int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int ns
     if (rc) return rc;
   }
   return QTX_OK;
+}
+
+int gram_tc(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int nslices, double* Tout, int accum,
+            void* ws, size_t ws_bytes, cudaStream_t st) {
+  return gram_tc_impl(dtype, A, ns, np, ld, nslices, Tout, accum, ws, ws_bytes, st, 0, 0, nullptr);
+}
+
+int gram_tc_push(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, int nslices, double* Tout, void* ws,
+                 size_t ws_bytes, cudaStream_t st, int nranks, int rank, double* const* slots) {
+  return gram_tc_impl(dtype, A, ns, np, ld, nslices, Tout, 0, ws, ws_bytes, st, nranks, rank, slots);
 }
 
 }  // namespace qtx

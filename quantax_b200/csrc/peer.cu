@@ -51,7 +51,7 @@ struct ReduceSrc {
 // CTA (blockIdx.x enumerates bi >= bj); the mirrored block is written through shared memory so that both stores
 // are coalesced.  Thread 0 first waits until every rank has published `epoch`; the wait is bounded (trap
 // instead of a hang if a peer died).
-__global__ void __launch_bounds__(256) gram_reduce_kernel(ReduceSrc srcs, int nranks, int64_t ns, double* __restrict__ T,
+__global__ void __launch_bounds__(256) gram_reduce_kernel(ReduceSrc srcs, int nranks, int64_t ns, double* T,
                                                           const uint64_t* __restrict__ flags, uint64_t epoch,
                                                           uint64_t timeout_ns) {
   __shared__ double tile[32][33];

@@ -170,6 +170,18 @@ class _CudaOps:
     def gram(self, A):
         return gram(A, nslices=self.nslices)
 
+    def gram_allreduce(self, A):
+        """Sum over the ranks of the Gram matrices of the column shards.  QTX_GRAM_P2P=1: one fused kernel pushes
+        the tiles over NVLink peer memory and a rank-ordered reduce follows (peer.py); otherwise Gram + NCCL
+        all-reduce."""
+        if os.environ.get("QTX_GRAM_P2P", "0") == "1":
+            from .peer import peer_gram
+
+            return peer_gram(A.shape[0]).gram_allreduce(A, self.nslices)
+        T = gram(A, nslices=self.nslices)
+        _dist().all_reduce(T)
+        return T
+
     pinv_eig_solve = staticmethod(pinv_eig_solve)
     matvec_t = staticmethod(matvec_t)
 
@@ -194,8 +206,11 @@ def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops, tsolv
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send)
     Ac = recv.view(P * nl, npc)  # all Ns rows (rank-major = global sample order), this rank's columns
-    T = ops.gram(Ac)
-    dist.all_reduce(T)
+    if hasattr(ops, "gram_allreduce"):
+        T = ops.gram_allreduce(Ac)
+    else:
+        T = ops.gram(Ac)
+        dist.all_reduce(T)
     bfull = torch.empty(P * nl, dtype=b.dtype, device=b.device)
     dist.all_gather_into_tensor(bfull, b.contiguous())
     y, info = ops.pinv_eig_solve(T, bfull, rtol, atol) if tsolve is None else tsolve(T, bfull)
