@@ -47,13 +47,13 @@ struct ReduceSrc {
   const double* src[QTX_MAX_PEERS];  // src[q] = partial of rank q as seen by this rank ([ns, ns], j <= i valid)
 };
 
-// T[i, j] = T[j, i] = sum_q src[q][i, j] for j <= i, in rank order.  One 32 x 32 block of the lower triangle per
-// CTA (blockIdx.x enumerates bi >= bj); the mirrored block is written through shared memory so that both stores
+// T[i, j] = T[j, i] = sum_q src[q][i, j] for j <= i, in rank order.  Persistent CTAs walk the 32 x 32 blocks of the
+// lower triangle (t enumerates bi >= bj); the mirrored block is written through shared memory so that both stores
 // are coalesced.  Thread 0 first waits until every rank has published `epoch`; the wait is bounded (trap
 // instead of a hang if a peer died).
 __global__ void __launch_bounds__(256) gram_reduce_kernel(ReduceSrc srcs, int nranks, int64_t ns, double* T,
                                                           const uint64_t* __restrict__ flags, uint64_t epoch,
-                                                          uint64_t timeout_ns) {
+                                                          uint64_t timeout_ns, int64_t nblocks) {
   __shared__ double tile[32][33];
   if (threadIdx.x == 0 && flags) {
     const uint64_t t0 = global_timer_ns();
@@ -65,32 +65,39 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(ReduceSrc srcs, int nr
     }
   }
   __syncthreads();
-  // block index -> (bi, bj), bj <= bi
-  const int64_t t = blockIdx.x;
-  int64_t bi = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-  while (bi * (bi + 1) / 2 > t) --bi;
-  const int64_t bj = t - bi * (bi + 1) / 2;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const bool diag = bi == bj;
+  for (int64_t t = blockIdx.x; t < nblocks; t += gridDim.x) {
+    // block index -> (bi, bj), bj <= bi
+    int64_t bi = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    while (bi * (bi + 1) / 2 > t) --bi;
+    const int64_t bj = t - bi * (bi + 1) / 2;
+    const bool diag = bi == bj;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int q = 0; q < nranks; ++q) {  // rank order; the four rows of a thread are independent loads
+      const double* src = srcs.src[q];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int li = ty + 8 * r;
-    const int64_t i = bi * 32 + li, j = bj * 32 + tx;
-    double acc = 0.0;
-    if (i < ns && j <= i) {
-      for (int q = 0; q < nranks; ++q) acc += __ldcg(srcs.src[q] + i * ns + j);
-      T[i * ns + j] = acc;
+      for (int r = 0; r < 4; ++r) {
+        const int64_t i = bi * 32 + ty + 8 * r, j = bj * 32 + tx;
+        if (i < ns && j <= i) acc[r] += __ldcg(src + i * ns + j);
+      }
     }
-    tile[li][tx] = acc;
-  }
-  __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int lj = ty + 8 * r;  // row of the mirrored block = column of the source block
-    const int64_t jj = bj * 32 + lj, ii = bi * 32 + tx;
-    // mirrored element T[jj, ii] = value(ii, jj); on a diagonal block only the strict upper part is missing
-    if (ii < ns && jj < ns && (diag ? jj < ii : true)) T[jj * ns + ii] = tile[tx][lj];
+    for (int r = 0; r < 4; ++r) {
+      const int li = ty + 8 * r;
+      const int64_t i = bi * 32 + li, j = bj * 32 + tx;
+      if (i < ns && j <= i) T[i * ns + j] = acc[r];
+      tile[li][tx] = acc[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int lj = ty + 8 * r;  // row of the mirrored block = column of the source block
+      const int64_t jj = bj * 32 + lj, ii = bi * 32 + tx;
+      // mirrored element T[jj, ii] = value(ii, jj); on a diagonal block only the strict upper part is missing
+      if (ii < ns && jj < ns && (diag ? jj < ii : true)) T[jj * ns + ii] = tile[tx][lj];
+    }
+    __syncthreads();  // the tile is reused by the next block of this CTA
   }
 }
 
@@ -161,9 +168,10 @@ extern "C" int qtx_gram_reduce(const void* const* partials, int nranks, int64_t 
   const int64_t nblocks = nb * (nb + 1) / 2;
   QTX_REQUIRE(nblocks < (int64_t)1 << 31, QTX_ERR_UNSUPPORTED, "qtx_gram_reduce: ns too large");
   if (timeout_s <= 0) timeout_s = 60.0;
-  gram_reduce_kernel<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(rs, nranks, ns, T_out,
-                                                                          (const uint64_t*)my_flags, epoch,
-                                                                          (uint64_t)(timeout_s * 1e9));
+  const int64_t grid = nblocks < 8ll * num_sms() ? nblocks : 8ll * num_sms();  // persistent CTAs: one flag wait each
+  gram_reduce_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(rs, nranks, ns, T_out,
+                                                                       (const uint64_t*)my_flags, epoch,
+                                                                       (uint64_t)(timeout_s * 1e9), nblocks);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }
