@@ -279,6 +279,25 @@ def run_b200(args):
     h2d = NS * N + Np * 4
     d2h = NS * N + NS * 8
 
+    # informational, last GPU work of the run and guarded: the diagonal-shift solver family (auto_shift_eig,
+    # solver.py:50-90) replaces eigh by a Cholesky factorisation of the same Gram matrix
+    chol_ms = None
+    if world == 1:
+        try:
+            from quantax_b200.optimizer import shift_chol_solve
+
+            Tc = gram(torch.randn((NS, 4096), dtype=torch.float64, device=dev) / 64)
+            shift_chol_solve(Tc.clone(), b, None, 1e-4)
+            c0, c1 = ev(), ev()
+            Tc2 = Tc.clone()
+            c0.record()
+            shift_chol_solve(Tc2, b, None, 1e-4)
+            c1.record()
+            torch.cuda.synchronize()
+            chol_ms = c0.elapsed_time(c1)
+        except Exception:
+            chol_ms = None
+
     def allmax(x):
         if world == 1:
             return x
@@ -316,7 +335,8 @@ def run_b200(args):
                        "nparams": Np, "l2": "256 MiB buffer written before every step (L2 flush)",
                        "gram_nslices": s_eff},
             "sweep_oloc_ms": sweep_oloc_ms / args.steps, "minsr_step_ms": minsr_ms / args.steps,
-            "minsr_phases_ms": {**phase, "gram_alone(split+mma)": gram_ms, "eigh_pinv_alone(cuSOLVER)": eigh_ms},
+            "minsr_phases_ms": {**phase, "gram_alone(split+mma)": gram_ms, "eigh_pinv_alone(cuSOLVER)": eigh_ms,
+                                "shift_cholesky_alone(cuSOLVER potrf+potrs, auto_shift_eig)": chol_ms},
             "e2e": {"value": NS * world * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk,
