@@ -5,7 +5,7 @@ This package is a NumPy restatement of the reference algorithm
 Variational.jacobian -> SR/MinSR solve.  Every function cites the reference
 file:line it follows.
 
-Rules (enforced by tests/test_layout.py):
+Rules (enforced by tests/test_host_cpu.py::test_product_never_imports_oracle):
   * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
     ``cpu_baseline`` / ``--impl reference`` legs may import this package;
   * the product (``quantax_b200``) never imports it and has no CPU fallback.
@@ -18,6 +18,12 @@ Pinning status (see DESIGN.md "Oracle"):
     checked against the ED energies the reference prints in its tutorials;
   * local-update psi == direct psi and Oloc(local updates) == Oloc(direct)
     follow the reference's notebook asserts;
+  * enumeration / compaction / Oloc reduction, the solver formulas, group
+    closure, neighbour tables, phase kernels, final activations, proposals and
+    accept/reject are checked against outputs of the reference's OWN modules
+    executed under a NumPy stand-in for jax (tests/golden/minijax.py,
+    tests/golden/make_golden_hotpath.py -> tests/golden/ref_hotpath.npz,
+    tests/test_golden_hotpath_cpu.py);
   * everything that lives in un-vendored third-party code (jax PRNG streams,
     ``jax.nn.gelu`` form, ``equinox.nn.Conv`` padding semantics,
     ``ravel_pytree`` leaf order, ``eigh``) is restated from its published

@@ -88,6 +88,20 @@ _K0 = 0.7978845608028654  # sqrt(2/pi)
 _K1 = 0.044715
 
 
+def exp_by_scale(zf):
+    """nn/activation.py:26-32 for a batch [B, n] of per-sample inputs: (significand [B, n], exponent [B]) with
+    exponent = max |x| over the sample."""
+    m = np.max(np.abs(zf), axis=1)
+    return np.exp(zf - m[:, None]), m
+
+
+def sinhp1_by_scale(zf):
+    """nn/activation.py:7-14 (sinh(x) + 1 in ScaleArray form) for a batch [B, n]."""
+    m = np.max(np.abs(zf), axis=1)
+    sig = (np.exp(zf - m[:, None]) - np.exp(-zf - m[:, None])) / zf.dtype.type(2) + np.exp(-m)[:, None]
+    return sig, m
+
+
 def gelu(x):
     dt = x.dtype
     u = dt.type(_K0) * (x + dt.type(_K1) * x * x * x)
@@ -211,11 +225,10 @@ class ResConv:
             dt = np.dtype(np.complex128)
             C = C // 2
         zf = z.reshape(B, -1)
-        m = np.max(np.abs(zf), axis=1)
         if self.final == "exp":
-            sig = np.exp(zf - m[:, None])
+            sig, m = exp_by_scale(zf)
         elif self.final == "sinhp1":
-            sig = (np.exp(zf - m[:, None]) - np.exp(-zf - m[:, None])) / dt.type(2) + np.exp(-m)[:, None]
+            sig, m = sinhp1_by_scale(zf)
         else:
             raise ValueError(self.final)
         a = sig.reshape(B, C, self.N).mean(axis=1, dtype=dt)  # reshape(-1, nsymm).mean(0)
@@ -356,3 +369,33 @@ class RBMConv:
 def dense_value(psi):
     mult, expo = psi
     return mult * np.exp(expo)
+
+
+# ---- parameter-free sign / phase layers (quantax/nn/sign.py:8-75) ---------------------------------------------------
+def neel120_kernel(Lx, Ly, triangular_b=False):
+    """nn/sign.py:62-75: float32 kernel of the 120-degree Neel phase, flattened in site order."""
+    x = 2 * np.arange(Lx)
+    y = np.zeros(Ly, dtype=x.dtype) if triangular_b else np.arange(Ly)
+    k = (x[:, None] + y[None, :]) % 3
+    return (np.pi / 3 * k - np.pi / 6).astype(np.float32).ravel()
+
+
+def compute_sign(kernel, s, output, neg=False):
+    """nn/sign.py:8-43 for a batch of configurations s [ns, N]: phase = dot(kernel, s) in float32."""
+    phase = np.asarray(s).astype(np.float32) @ np.asarray(kernel, dtype=np.float32).ravel()
+    if output == "sign":
+        out = np.sign(np.cos(phase))
+    elif output == "phase":
+        out = np.exp(1j * phase).astype(np.complex64)
+    elif output == "cos":
+        out = np.cos(phase)
+    else:
+        raise ValueError(f"Unknown output type: {output}")
+    return -out if neg else out
+
+
+def neel120_phase(lattice, s):
+    """nn/sign.py:62-75."""
+    Lx, Ly = lattice.shape[1:]
+    return compute_sign(neel120_kernel(Lx, Ly), s, "phase")
+

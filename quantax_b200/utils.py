@@ -13,17 +13,78 @@ import numpy as np
 import torch
 
 
+def _t(x, like: torch.Tensor) -> torch.Tensor:
+    """Dense operand -> tensor on the device of ``like`` (Python scalars keep the dtype of ``like``)."""
+    if isinstance(x, torch.Tensor):
+        return x
+    if isinstance(x, (int, float)):
+        return torch.tensor(x, dtype=like.dtype if like.is_floating_point() or like.is_complex() else torch.float64,
+                            device=like.device)
+    return torch.as_tensor(np.asarray(x), device=like.device)
+
+
+def _real_dtype(dt):
+    return {torch.complex128: torch.float64, torch.complex64: torch.float32}.get(dt, dt)
+
+
+def _addexp(x1, x2, b1, b2):
+    """b1 exp(x1) + b2 exp(x2) as (x, b) (big_array.py:14-26): the larger exponent is factored out exactly."""
+    xmax = torch.maximum(x1, x2)
+    r1 = torch.where(x1 != xmax, torch.exp(x1 - xmax), torch.ones_like(xmax))
+    r2 = torch.where(x2 != xmax, torch.exp(x2 - xmax), torch.ones_like(xmax))
+    return xmax, b1 * r1 + b2 * r2
+
+
+def _sumexp(x, b, axis, keepdims, mean):
+    """sum_i b_i exp(x_i) over ``axis`` as (x, b) (big_array.py:46-148)."""
+    if axis is None:
+        axis = tuple(range(x.ndim))
+    elif isinstance(axis, int):
+        axis = (axis,)
+    if x.ndim == 0:
+        return x, b
+    xmax = torch.amax(x, dim=axis, keepdim=True)
+    r = torch.where(x != xmax, torch.exp(x - xmax), torch.ones_like(x))
+    bs = torch.sum(b * r, dim=axis, keepdim=True)
+    if mean:
+        n = 1
+        for a in axis:
+            n *= x.shape[a]
+        xmax = xmax - float(np.log(n))
+    if not keepdims:
+        for a in sorted((a % x.ndim for a in axis), reverse=True):
+            xmax, bs = xmax.squeeze(a), bs.squeeze(a)
+    return xmax, bs
+
+
 @dataclass
 class LogArray:
-    """quantax/utils/big_array.py:154-402."""
+    """value = sign * exp(logabs) (quantax/utils/big_array.py:154-402); zero is sign = 0, logabs = -inf."""
 
     sign: torch.Tensor
     logabs: torch.Tensor
 
+    __array_priority__ = 1000
     mult = property(lambda self: self.sign)
     expo = property(lambda self: self.logabs)
     shape = property(lambda self: self.sign.shape)
-    dtype = property(lambda self: self.logabs.dtype)
+    dtype = property(lambda self: self.sign.dtype)
+    ndim = property(lambda self: self.sign.ndim)
+    size = property(lambda self: self.sign.numel())
+
+    @staticmethod
+    def from_value(x) -> "LogArray":
+        if isinstance(x, LogArray):
+            return x
+        if isinstance(x, ScaleArray):
+            return LogArray(torch.sgn(x.significand), torch.log(x.significand.abs()) + x.exponent)
+        x = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float64))
+        return LogArray(torch.sgn(x), torch.log(x.abs()))
+
+    def _other(self, other) -> "LogArray":
+        if isinstance(other, (LogArray, ScaleArray)):
+            return LogArray.from_value(other)
+        return LogArray.from_value(_t(other, self.logabs))
 
     def value(self) -> torch.Tensor:
         return self.sign * torch.exp(self.logabs)
@@ -34,13 +95,86 @@ class LogArray:
     def __len__(self):
         return self.sign.shape[0]
 
+    def reshape(self, *shape):
+        return LogArray(self.sign.reshape(*shape), self.logabs.reshape(*shape))
+
+    def flatten(self):
+        return LogArray(self.sign.flatten(), self.logabs.flatten())
+
+    def __neg__(self):
+        return LogArray(-self.sign, self.logabs)
+
+    def conj(self):
+        return LogArray(torch.conj(self.sign).resolve_conj(), self.logabs)
+
     def abs(self):
-        return LogArray(torch.ones_like(self.sign), self.logabs)
+        return LogArray(torch.ones_like(self.logabs), self.logabs)
 
     __abs__ = abs
 
+    @property
+    def real(self):
+        if not self.sign.is_complex():
+            return self
+        re = self.sign.real
+        return LogArray(torch.sgn(re), self.logabs + torch.log(re.abs()))
+
+    @property
+    def imag(self):
+        if not self.sign.is_complex():
+            return LogArray(torch.zeros_like(self.sign), torch.full_like(self.logabs, -float("inf")))
+        im = self.sign.imag
+        return LogArray(torch.sgn(im), self.logabs + torch.log(im.abs()))
+
+    def astype(self, dtype):
+        return LogArray(self.sign.to(dtype), self.logabs.to(_real_dtype(dtype)))
+
+    def __mul__(self, other):
+        o = self._other(other)
+        return LogArray(self.sign * o.sign, self.logabs + o.logabs)
+
+    __rmul__ = __mul__
+
     def __truediv__(self, other):
-        return LogArray(self.sign / other.sign, self.logabs - other.logabs)
+        o = self._other(other)
+        return LogArray(self.sign / o.sign, self.logabs - o.logabs)
+
+    def __rtruediv__(self, other):
+        o = self._other(other)
+        return LogArray(o.sign / self.sign, o.logabs - self.logabs)
+
+    def __pow__(self, p):
+        p = _t(p, self.logabs)
+        return LogArray(torch.pow(self.sign, p), self.logabs * p)
+
+    def __add__(self, other):
+        o = self._other(other)
+        x, b = _addexp(self.logabs, o.logabs, self.sign, o.sign)
+        return LogArray(torch.sgn(b), x + torch.log(b.abs()))
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self.__add__(-self._other(other))
+
+    def __rsub__(self, other):
+        return self._other(other).__add__(-self)
+
+    def sum(self, axis=None, keepdims: bool = False):
+        x, b = _sumexp(self.logabs, self.sign, axis, keepdims, mean=False)
+        return LogArray(torch.sgn(b), x + torch.log(b.abs()))
+
+    def mean(self, axis=None, keepdims: bool = False):
+        x, b = _sumexp(self.logabs, self.sign, axis, keepdims, mean=True)
+        return LogArray(torch.sgn(b), x + torch.log(b.abs()))
+
+    def prod(self, axis=None, keepdims: bool = False):
+        if axis is None:
+            sign, logabs = torch.prod(self.sign.flatten()), torch.sum(self.logabs)
+            if keepdims:
+                sign, logabs = sign.reshape([1] * self.ndim), logabs.reshape([1] * self.ndim)
+            return LogArray(sign, logabs)
+        return LogArray(torch.prod(self.sign, dim=axis, keepdim=keepdims), torch.sum(self.logabs, dim=axis, keepdim=keepdims))
 
     def __array__(self, dtype=None):
         return np.asarray(self.value().cpu().numpy(), dtype)
@@ -48,32 +182,83 @@ class LogArray:
 
 @dataclass
 class ScaleArray:
-    """quantax/utils/big_array.py:407-688."""
+    """value = significand * exp(exponent) (quantax/utils/big_array.py:407-688); the exponent is a scalar or has
+    the shape of the significand."""
 
     significand: torch.Tensor
     exponent: torch.Tensor
 
+    __array_priority__ = 2000
     mult = property(lambda self: self.significand)
     expo = property(lambda self: self.exponent)
     shape = property(lambda self: self.significand.shape)
     dtype = property(lambda self: self.significand.dtype)
+    ndim = property(lambda self: self.significand.ndim)
+    size = property(lambda self: self.significand.numel())
+
+    def normalize(self) -> "ScaleArray":
+        """Largest |significand| becomes 1 relative to the largest exponent (big_array.py:442-451)."""
+        max_sig = self.significand.abs().max()
+        max_exp = self.exponent.max()
+        exponent = max_exp + torch.log(max_sig)
+        exponent = torch.where(torch.isfinite(exponent), exponent, max_exp)
+        diff = torch.where(self.exponent != exponent, self.exponent - exponent, torch.zeros_like(exponent))
+        return ScaleArray(self.significand * torch.exp(diff), exponent)
+
+    @staticmethod
+    def from_value(x) -> "ScaleArray":
+        if isinstance(x, ScaleArray):
+            return x
+        if isinstance(x, LogArray):
+            return ScaleArray(x.sign, x.logabs)
+        x = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+        zero = torch.zeros((), dtype=_real_dtype(x.dtype) if x.is_floating_point() or x.is_complex() else torch.float64,
+                           device=x.device)
+        return ScaleArray(x, zero).normalize()
+
+    def _other(self, other) -> "ScaleArray":
+        if isinstance(other, (LogArray, ScaleArray)):
+            return ScaleArray.from_value(other)
+        return ScaleArray.from_value(_t(other, self.exponent))
 
     def value(self) -> torch.Tensor:
         return self.significand * torch.exp(self.exponent)
 
     def __getitem__(self, idx):
-        return ScaleArray(self.significand[idx], self.exponent[idx])
+        return ScaleArray(self.significand[idx], self.exponent[idx] if self.exponent.ndim else self.exponent)
 
     def __len__(self):
         return self.significand.shape[0]
+
+    def reshape(self, *shape):
+        return ScaleArray(self.significand.reshape(*shape),
+                          self.exponent.reshape(*shape) if self.exponent.ndim else self.exponent)
+
+    def flatten(self):
+        return ScaleArray(self.significand.flatten(), self.exponent.flatten() if self.exponent.ndim else self.exponent)
+
+    def __neg__(self):
+        return ScaleArray(-self.significand, self.exponent)
+
+    def conj(self):
+        return ScaleArray(torch.conj(self.significand).resolve_conj(), self.exponent)
 
     def abs(self):
         return ScaleArray(self.significand.abs(), self.exponent)
 
     __abs__ = abs
 
-    def __truediv__(self, other):
-        return ScaleArray(self.significand / other.significand, self.exponent - other.exponent)
+    @property
+    def real(self):
+        return ScaleArray(self.significand.real if self.significand.is_complex() else self.significand, self.exponent)
+
+    @property
+    def imag(self):
+        sig = self.significand.imag if self.significand.is_complex() else torch.zeros_like(self.significand)
+        return ScaleArray(sig, self.exponent)
+
+    def astype(self, dtype):
+        return ScaleArray(self.significand.to(dtype), self.exponent.to(_real_dtype(dtype)))
 
     def __mul__(self, other):
         from .nn import SignPhase
@@ -82,10 +267,94 @@ class ScaleArray:
             if not self.significand.is_complex():
                 raise TypeError("a phase layer needs a complex-output model (out_dtype=torch.complex128)")
             return ScaleArray(other.apply_(self.significand.contiguous()), self.exponent)
-        return NotImplemented
+        o = self._other(other)
+        return ScaleArray(self.significand * o.significand, self.exponent + o.exponent)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        o = self._other(other)
+        return ScaleArray(self.significand / o.significand, self.exponent - o.exponent)
+
+    def __rtruediv__(self, other):
+        o = self._other(other)
+        return ScaleArray(o.significand / self.significand, o.exponent - self.exponent)
+
+    def __pow__(self, p):
+        p = _t(p, self.exponent)
+        return ScaleArray(torch.pow(self.significand, p), self.exponent * p)
+
+    def __add__(self, other):
+        o = self._other(other)
+        exponent, significand = _addexp(self.exponent, o.exponent, self.significand, o.significand)
+        return ScaleArray(significand, exponent)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self.__add__(-self._other(other))
+
+    def __rsub__(self, other):
+        return self._other(other).__add__(-self)
+
+    def _reduce(self, axis, keepdims, mean):
+        if self.exponent.ndim == 0:
+            red = torch.mean if mean else torch.sum
+            if axis is None:
+                sig = red(self.significand)
+                sig = sig.reshape([1] * self.ndim) if keepdims else sig
+            else:
+                sig = red(self.significand, dim=axis, keepdim=keepdims)
+            return ScaleArray(sig, self.exponent)
+        if self.exponent.shape != self.significand.shape:
+            raise ValueError(f"Cannot reduce ScaleArray with significand shape {tuple(self.significand.shape)} "
+                             f"and exponent shape {tuple(self.exponent.shape)}")
+        exponent, significand = _sumexp(self.exponent, self.significand, axis, keepdims, mean)
+        return ScaleArray(significand, exponent)
+
+    def sum(self, axis=None, keepdims: bool = False):
+        return self._reduce(axis, keepdims, mean=False)
+
+    def mean(self, axis=None, keepdims: bool = False):
+        return self._reduce(axis, keepdims, mean=True)
+
+    def prod(self, axis=None, keepdims: bool = False):
+        """big_array.py:654-685 for an exponent of the significand's shape."""
+        if self.exponent.shape != self.significand.shape:
+            raise NotImplementedError("ScaleArray.prod with a scalar exponent is not implemented")
+        sign, logabs = torch.sgn(self.significand), torch.log(self.significand.abs())
+        finite = torch.isfinite(logabs)
+        logabs = torch.where(finite, logabs, torch.zeros_like(logabs))
+        sig = torch.where(finite, sign, self.significand)
+        exponent = self.exponent + logabs
+        if axis is None:
+            sig, exponent = torch.prod(sig.flatten()), torch.sum(exponent)
+            if keepdims:
+                sig, exponent = sig.reshape([1] * self.ndim), exponent.reshape([1] * self.ndim)
+            return ScaleArray(sig, exponent)
+        return ScaleArray(torch.prod(sig, dim=axis, keepdim=keepdims), torch.sum(exponent, dim=axis, keepdim=keepdims))
 
     def __array__(self, dtype=None):
         return np.asarray(self.value().cpu().numpy(), dtype)
+
+
+PsiArray = (torch.Tensor, LogArray, ScaleArray)  # quantax/utils/big_array.py:692
+
+
+def where(cond, x, y):
+    """Element-wise selection that keeps the container type (big_array.py:749-767)."""
+    if isinstance(x, ScaleArray) or isinstance(y, ScaleArray):
+        ref = x if isinstance(x, ScaleArray) else y
+        x, y = ref._other(x), ref._other(y)
+        exponent = torch.where(cond, x.exponent, y.exponent)
+        significand = torch.where(cond, x.significand, y.significand)
+        max_exp = exponent.max()
+        return ScaleArray(significand * torch.exp(exponent - max_exp), max_exp)
+    if isinstance(x, LogArray) or isinstance(y, LogArray):
+        ref = x if isinstance(x, LogArray) else y
+        x, y = ref._other(x), ref._other(y)
+        return LogArray(torch.where(cond, x.sign, y.sign), torch.where(cond, x.logabs, y.logabs))
+    return torch.where(cond, x, y)
 
 
 def log_abs(psi) -> torch.Tensor:

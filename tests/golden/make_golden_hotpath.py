@@ -1,0 +1,401 @@
+"""Golden vectors of the hot path produced by the REFERENCE'S OWN code under a NumPy stand-in for jax.
+
+Run in the build container only (needs /root/reference; it is never read by the tests):
+    python tests/golden/make_golden_hotpath.py
+
+jax is not installable here, so ``tests/golden/minijax.py`` provides eager NumPy restatements of the jax
+functions the reference's hot-path modules call (see its header for what that does and does not pin).  The
+reference modules themselves are imported UNMODIFIED from /root/reference:
+
+  quantax/operator/operator.py      _apply_diag, _apply_off_diag, _get_conn_size, _get_conn, _get_Olocx,
+                                    Operator.jax_op_list (lines 30-184, 221-238)
+  quantax/operator/common_operators.py, site_operator.py   Heisenberg / Ising op lists
+  quantax/optimizer/solver.py       _get_eigs_inv, _sum_without_noise, pinvh_solve, minnorm/lstsq/auto/minsr_pinv_eig,
+                                    minnorm/lstsq/auto_shift_eig, sgd_solver (lines 50-201, 262-302)
+  quantax/symmetry/symmetry.py      _get_perm (group closure, characters; lines 11-57)
+  quantax/sampler/common_samplers.py  _get_site_neighbors (lines 36-55)
+  quantax/nn/sign.py                neel120_phase, marshall_sign, stripe_sign kernels
+  quantax/utils/array.py            array_extend, local_to_replicate, to_distribute_array
+
+Inputs are seeded NumPy arrays stored next to the outputs in ``tests/golden/ref_hotpath.npz``.
+"""
+import enum
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import minijax  # noqa: E402
+
+
+def install_reference():
+    jax, jnp = minijax.install()
+    jax.lax.with_sharding_constraint = lambda x, s: x
+    pkg = types.ModuleType("quantax")
+    pkg.__path__ = [os.path.join(REF, "quantax")]
+    sys.modules["quantax"] = pkg
+
+    gd = types.ModuleType("quantax.global_defs")
+
+    class PARTICLE_TYPE(enum.Enum):
+        spin = 0
+        spinful_fermion = 1
+        spinless_fermion = 2
+
+    state = {"dtype": np.float64}
+    gd.PARTICLE_TYPE = PARTICLE_TYPE
+    gd.get_default_dtype = lambda: state["dtype"]
+    gd.get_real_dtype = lambda: np.float64
+    gd.is_default_cpl = lambda: np.issubdtype(state["dtype"], np.complexfloating)
+    gd.set_default_dtype = lambda dt: state.__setitem__("dtype", dt)
+    gd.get_subkeys = lambda num=None: None  # PRNG keys are never consumed: random draws are injected
+    sys.modules["quantax.global_defs"] = gd
+    pkg.global_defs = gd
+    sites = importlib.import_module("quantax.sites")  # pure NumPy reference code
+    gd.get_sites = lambda: sites.Sites._SITES
+    gd.get_lattice = lambda: sites.Sites._SITES
+
+    # quantax.utils: the real array helpers, the rest inert
+    utils = minijax._AnyModule("quantax.utils")
+    utils.__path__ = [os.path.join(REF, "quantax", "utils")]
+    sys.modules["quantax.utils"] = utils
+    importlib.import_module("quantax.utils.sharding")
+    arr = importlib.import_module("quantax.utils.array")
+    for name in ("local_to_replicate", "to_distribute_array", "to_replicate_array", "to_replicate_numpy", "array_extend"):
+        setattr(utils, name, getattr(arr, name))
+    tree = importlib.import_module("quantax.utils.tree")        # filter_tree_map
+    big = importlib.import_module("quantax.utils.big_array")    # LogArray / ScaleArray / where (plain dataclasses)
+    utils.filter_tree_map = tree.filter_tree_map
+    utils.LogArray, utils.ScaleArray, utils.PsiArray, utils.where = big.LogArray, big.ScaleArray, big.PsiArray, big.where
+    for sub in ("state", "sampler", "nn"):
+        sys.modules[f"quantax.{sub}"] = minijax._AnyModule(f"quantax.{sub}")
+    symm_pkg = minijax._AnyModule("quantax.symmetry")
+    symm_pkg.__path__ = [os.path.join(REF, "quantax", "symmetry")]
+    sys.modules["quantax.symmetry"] = symm_pkg
+    operator = importlib.import_module("quantax.operator")
+    opmod = importlib.import_module("quantax.operator.operator")
+    symmod = importlib.import_module("quantax.symmetry.symmetry")
+    opt_pkg = minijax._AnyModule("quantax.optimizer")
+    opt_pkg.__path__ = [os.path.join(REF, "quantax", "optimizer")]
+    sys.modules["quantax.optimizer"] = opt_pkg
+    solver = importlib.import_module("quantax.optimizer.solver")
+    smp_pkg = minijax._AnyModule("quantax.sampler")
+    smp_pkg.__path__ = [os.path.join(REF, "quantax", "sampler")]
+    sys.modules["quantax.sampler"] = smp_pkg
+    for sub in ("sampler", "samples", "metropolis"):
+        sys.modules[f"quantax.sampler.{sub}"] = minijax._AnyModule(f"quantax.sampler.{sub}")
+    csamp = importlib.import_module("quantax.sampler.common_samplers")
+    nn_pkg = minijax._AnyModule("quantax.nn")
+    nn_pkg.__path__ = [os.path.join(REF, "quantax", "nn")]
+    sys.modules["quantax.nn"] = nn_pkg
+    sys.modules["quantax.nn.modules"] = minijax._AnyModule("quantax.nn.modules")
+    sign = importlib.import_module("quantax.nn.sign")
+    act = importlib.import_module("quantax.nn.activation")
+    # the real Samples / Metropolis classes (only _update is called, unbound, with a stand-in self)
+    for sub in ("sampler", "samples", "metropolis"):
+        del sys.modules[f"quantax.sampler.{sub}"]
+    samples = importlib.import_module("quantax.sampler.samples")
+    metro = importlib.import_module("quantax.sampler.metropolis")
+    return dict(gd=gd, sites=sites, operator=operator, opmod=opmod, symmod=symmod, solver=solver, csamp=csamp, sign=sign,
+                act=act, big=big, samples=samples, metro=metro, jax=jax)
+
+
+def rand_spins(rng, ns, N, nup=None):
+    if nup is None:
+        return (2 * rng.integers(0, 2, size=(ns, N)) - 1).astype(np.int8)
+    s = -np.ones((ns, N), dtype=np.int8)
+    for r in range(ns):
+        s[r, rng.permutation(N)[:nup]] = 1
+    return s
+
+
+def gen_operator(ref, out):
+    sites, operator, opmod = ref["sites"], ref["operator"], ref["opmod"]
+    rng = np.random.default_rng(20261017)
+    cases = {
+        "chain8_ising": (lambda: sites.Chain(8), lambda: operator.Ising(h=1.0), None, 12),
+        "chain8_ising_h0.5_J2": (lambda: sites.Chain(8), lambda: operator.Ising(h=0.5, J=2.0), None, 12),
+        "square4_heis_msr": (lambda: sites.Square(4, Nparticles=(8, 8)), lambda: operator.Heisenberg(msr=True), 8, 16),
+        "square4_j1j2_msr": (lambda: sites.Square(4, Nparticles=(8, 8)),
+                             lambda: operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True), 8, 16),
+        "square6_j1j2_msr": (lambda: sites.Square(6, Nparticles=(18, 18)),
+                             lambda: operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True), 18, 8),
+        "triangular6_heis": (lambda: sites.Triangular(6, Nparticles=(18, 18)), lambda: operator.Heisenberg(), 18, 8),
+        "square4_heis_unconstrained": (lambda: sites.Square(4), lambda: operator.Heisenberg(), None, 8),
+    }
+    for name, (mk_lat, mk_op, nup, ns) in cases.items():
+        sites.Sites._SITES = None
+        lat = mk_lat()
+        H = mk_op()
+        s = rand_spins(rng, ns, lat.Nsites, nup)
+        sj = minijax.wrap(s.copy())
+        jl = H.jax_op_list
+        out[f"op/{name}/spins"] = s
+        out[f"op/{name}/diag"] = np.asarray(opmod._apply_diag(sj, jl), dtype=np.float64)
+        off = opmod._apply_off_diag(sj, jl)
+        out[f"op/{name}/nflips"] = np.array(sorted(off.keys()), dtype=np.int64)
+        for nflips, (s_conn, H_conn) in off.items():
+            out[f"op/{name}/{nflips}/H_raw"] = np.asarray(H_conn, dtype=np.float64)
+            for chunk in (None, 16):
+                size = int(opmod._get_conn_size(H_conn, chunk))
+                seg, sc, Hc = opmod._get_conn(s_conn, H_conn, size)
+                tag = "none" if chunk is None else str(chunk)
+                out[f"op/{name}/{nflips}/chunk_{tag}/segment"] = np.asarray(seg, dtype=np.int64)
+                out[f"op/{name}/{nflips}/chunk_{tag}/s_conn"] = np.asarray(sc, dtype=np.int8)
+                out[f"op/{name}/{nflips}/chunk_{tag}/H"] = np.asarray(Hc, dtype=np.float64)
+            # _get_Olocx with a synthetic amplitude table psi(s) = exp(sum_i a_i s_i) (dense arrays, not PsiArray)
+            a = rng.standard_normal(lat.Nsites) * 0.3
+            psi = np.exp(s @ a)
+            size = int(opmod._get_conn_size(H_conn, None))
+            seg, sc, Hc = opmod._get_conn(s_conn, H_conn, size)
+            psi_conn = np.exp(np.asarray(sc, dtype=np.float64) @ a)
+            out[f"op/{name}/{nflips}/amp_a"] = a
+            out[f"op/{name}/{nflips}/Olocx"] = np.asarray(
+                opmod._get_Olocx(minijax.wrap(psi), seg, minijax.wrap(psi_conn), Hc), dtype=np.float64)
+
+
+def gen_solver(ref, out):
+    solver = ref["solver"]
+    rng = np.random.default_rng(7)
+    vals = np.concatenate([[0.0, 1e-30, -1e-14, 3e-13], np.exp(rng.uniform(-30, 2, size=20)), -np.exp(rng.uniform(-20, 0, 4))])
+    out["solver/eigs_inv/vals"] = vals
+    for tag, rtol, atol in (("default", None, 0.0), ("r1e-8_a1e-10", 1e-8, 1e-10)):
+        out[f"solver/eigs_inv/{tag}"] = np.asarray(solver._get_eigs_inv(minijax.wrap(vals.copy()), rtol, atol))
+    inputs = rng.standard_normal((17, 9)) * np.exp(rng.standard_normal((1, 9)))
+    out["solver/snr/inputs"] = inputs
+    for tol in (0.0, 1e-7, 0.5, 3.0):
+        out[f"solver/snr/tol_{tol}"] = np.asarray(solver._sum_without_noise(minijax.wrap(inputs.copy()), tol))
+    for tag, (ns, npar) in {"minnorm": (12, 40), "lstsq": (40, 12)}.items():
+        A = rng.standard_normal((ns, npar)) * np.exp(0.5 * rng.standard_normal((1, npar)))
+        A -= A.mean(axis=0, keepdims=True)
+        A /= np.sqrt(ns)
+        b = rng.standard_normal(ns) / np.sqrt(ns)
+        out[f"solver/{tag}/A"], out[f"solver/{tag}/b"] = A, b
+        Aj, bj = minijax.wrap(A.copy()), minijax.wrap(b.copy())
+        for tol_snr in (0.0, 1.0):
+            out[f"solver/{tag}/auto_pinv_eig_snr{tol_snr}"] = np.asarray(
+                solver.auto_pinv_eig(rtol=1e-10, tol_snr=tol_snr)(Aj, bj))
+        out[f"solver/{tag}/auto_pinv_eig_default"] = np.asarray(solver.auto_pinv_eig()(Aj, bj))
+        out[f"solver/{tag}/auto_shift_eig_default"] = np.asarray(solver.auto_shift_eig()(Aj, bj))
+        out[f"solver/{tag}/auto_shift_eig_r1e-3_a0"] = np.asarray(solver.auto_shift_eig(1e-3, 0.0)(Aj, bj))
+        out[f"solver/{tag}/sgd"] = np.asarray(solver.sgd_solver()(Aj, bj))
+        T = A @ A.T
+        out[f"solver/{tag}/minsr_pinv_eig_T"] = np.asarray(solver.minsr_pinv_eig(rtol=1e-10)(minijax.wrap(T.copy()), bj))
+        out[f"solver/{tag}/pinvh_T"] = np.asarray(solver.pinvh_solve(rtol=1e-10)(minijax.wrap(T.copy()), bj))
+
+
+def gen_symmetry(ref, out):
+    sites, symmod, gd = ref["sites"], ref["symmod"], ref["gd"]
+    gens = np.load(os.path.join(HERE, "ref_symm_generators.npz"))  # generators from the reference's NumPy code
+    for lat_name, mk in {"square4": lambda: sites.Square(4), "square6": lambda: sites.Square(6),
+                         "triangular6": lambda: sites.Triangular(6), "chain8": lambda: sites.Chain(8)}.items():
+        sites.Sites._SITES = None
+        mk()
+        combos = {"trans": ["trans"], "flip0": ["flip0"]}
+        if f"{lat_name}/rot" in gens:
+            combos["rot"] = ["rot"]
+            combos["rot_flip0"] = ["rot", "flip0"]
+        for cname, parts in combos.items():
+            g = np.concatenate([np.atleast_2d(gens[f"{lat_name}/{p}"]) for p in parts], axis=0)
+            for sec in (0, 1):
+                sector = [sec if i == 0 else 0 for i in range(g.shape[0])]
+                try:
+                    perm, character, perm_sign = symmod._get_perm(g, sector, np.ones(g.shape[0], dtype=np.int8))
+                except ValueError:
+                    continue  # complex characters with the real default dtype
+                key = f"symm/{lat_name}/{cname}/sec{sec}"
+                out[f"{key}/generator"] = g.astype(np.int64)
+                out[f"{key}/perm"] = np.asarray(perm, dtype=np.int64)
+                out[f"{key}/character"] = np.asarray(character, dtype=np.float64)
+
+
+def gen_sampler_tables(ref, out):
+    sites, csamp = ref["sites"], ref["csamp"]
+    for lat_name, mk in {"chain8": lambda: sites.Chain(8), "square4": lambda: sites.Square(4),
+                         "square10": lambda: sites.Square(10), "triangular6": lambda: sites.Triangular(6)}.items():
+        for nn_arg, tag in ((1, "n1"), ([1, 2], "n12")):
+            sites.Sites._SITES = None
+            mk()
+            out[f"nbr/{lat_name}/{tag}"] = np.asarray(csamp._get_site_neighbors(nn_arg), dtype=np.int64)
+
+
+def gen_sign(ref, out):
+    sites, sign = ref["sites"], ref["sign"]
+    rng = np.random.default_rng(5)
+    sites.Sites._SITES = None
+    lat = sites.Triangular(6)
+    s = rand_spins(rng, 6, lat.Nsites, 18)
+    out["sign/triangular6/spins"] = s
+    out["sign/triangular6/neel120_phase"] = np.stack([np.asarray(sign.neel120_phase(minijax.wrap(r.copy()))) for r in s])
+
+
+def _parts(x):
+    """(first, second) leaves of a LogArray / ScaleArray as plain arrays."""
+    a, b = x.tree_flatten()[0]
+    return np.asarray(a), np.asarray(b)
+
+
+def gen_containers(ref, out):
+    """utils/big_array.py: arithmetic of the psi containers (the Oloc ratio, the Metropolis rate, symmetrize)."""
+    big = ref["big"]
+    rng = np.random.default_rng(11)
+    n = 13
+    W = minijax.wrap
+    sa, sb = rng.choice([-1.0, 1.0], n), rng.choice([-1.0, 1.0], n)
+    la, lb = rng.standard_normal(n) * 300, rng.standard_normal(n) * 300
+    lb[:4] = la[:4] + rng.standard_normal(4)  # comparable magnitudes: additions that do not degenerate
+    out["cont/log/a_sign"], out["cont/log/a_logabs"], out["cont/log/b_sign"], out["cont/log/b_logabs"] = sa, la, sb, lb
+    A, B = big.LogArray(W(sa.copy()), W(la.copy())), big.LogArray(W(sb.copy()), W(lb.copy()))
+    dense = rng.standard_normal(n)
+    out["cont/dense"] = dense
+    ops = {"div": A / B, "mul": A * B, "add": A + B, "sub": A - B, "neg": -A, "abs": abs(A), "pow2": A ** 2, "pow1.3": abs(A) ** 1.3,
+           "mul_dense": A * W(dense.copy()), "rdiv": 2.0 / A,
+           "sum": A.sum(), "mean": A.mean(), "prod": A.prod(), "from_value": big.LogArray.from_value(W(dense.copy())),
+           "where": big.where(W(dense > 0), A, B)}
+    for k, v in ops.items():
+        out[f"cont/log/{k}/0"], out[f"cont/log/{k}/1"] = _parts(v)
+    # per sample: sum over the image axis with characters, as symmetrize does (symmetry.py:386-392)
+    s2, l2 = rng.choice([-1.0, 1.0], (5, 4)), rng.standard_normal((5, 4)) * 40
+    chi = np.array([1.0, -1.0, 1.0, -1.0])
+    out["cont/log/img_sign"], out["cont/log/img_logabs"], out["cont/chi"] = s2, l2, chi
+    char = chi * chi[0] / chi.size  # symmetry.py:391
+    rows = [_parts((big.LogArray(W(s2[r].copy()), W(l2[r].copy())) * W(char.copy())).sum()) for r in range(5)]
+    out["cont/log/proj/0"], out["cont/log/proj/1"] = np.array([r[0] for r in rows]), np.array([r[1] for r in rows])
+
+    ma, mb = rng.standard_normal(n), rng.standard_normal(n)
+    ea, eb = rng.standard_normal(n) * 200, rng.standard_normal(n) * 200
+    eb[:4] = ea[:4] + rng.standard_normal(4)
+    out["cont/scale/a_sig"], out["cont/scale/a_exp"], out["cont/scale/b_sig"], out["cont/scale/b_exp"] = ma, ea, mb, eb
+    A, B = big.ScaleArray(W(ma.copy()), W(ea.copy())), big.ScaleArray(W(mb.copy()), W(eb.copy()))
+    ops = {"div": A / B, "mul": A * B, "add": A + B, "sub": A - B, "neg": -A, "abs": abs(A), "pow2": A ** 2,
+           "pow1.3": abs(A) ** 1.3, "mul_dense": A * W(dense.copy()), "rdiv": 2.0 / A, "sum": A.sum(), "mean": A.mean(),
+           "prod": A.prod(), "normalize": A.normalize(), "from_value": big.ScaleArray.from_value(W(dense.copy())),
+           "where": big.where(W(dense > 0), A, B), "to_log": big.LogArray.from_value(A)}
+    for k, v in ops.items():
+        out[f"cont/scale/{k}/0"], out[f"cont/scale/{k}/1"] = _parts(v)
+    m2, e2 = rng.standard_normal((5, 4)), rng.standard_normal((5, 4)) * 40
+    out["cont/scale/img_sig"], out["cont/scale/img_exp"] = m2, e2
+    rows = [_parts((big.ScaleArray(W(m2[r].copy()), W(e2[r].copy())) * W(char.copy())).sum()) for r in range(5)]
+    out["cont/scale/proj/0"], out["cont/scale/proj/1"] = np.array([r[0] for r in rows]), np.array([r[1] for r in rows])
+    # complex significands (config D)
+    mc = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    out["cont/scale/c_sig"] = mc
+    C = big.ScaleArray(W(mc.copy()), W(ea.copy()))
+    for k, v in {"cdiv": C / A, "cabs": abs(C), "cconj": C.conj(), "csum": C.sum()}.items():
+        out[f"cont/scale/{k}/0"], out[f"cont/scale/{k}/1"] = _parts(v)
+
+
+def gen_activations(ref, out):
+    """nn/activation.py: final activations of ResConv / RBM in container form."""
+    act = ref["act"]
+    rng = np.random.default_rng(13)
+    for dt in (np.float32, np.float64):
+        x = (rng.standard_normal((6, 16)) * 30).astype(dt)
+        tag = np.dtype(dt).name
+        out[f"act/{tag}/x"] = x
+        for name in ("exp_by_scale", "sinhp1_by_scale"):
+            r = getattr(act, name)(minijax.wrap(x.copy()))
+            out[f"act/{tag}/{name}/0"], out[f"act/{tag}/{name}/1"] = _parts(r)
+        th = (rng.standard_normal(24) * 3).astype(dt)
+        out[f"act/{tag}/theta"] = th
+        r = act.prod_by_log(minijax.wrap(np.cosh(th)))
+        out[f"act/{tag}/prod_by_log_cosh/0"], out[f"act/{tag}/prod_by_log_cosh/1"] = _parts(r)
+        xc = (rng.standard_normal((8, 5)) * 3).astype(dt)
+        out[f"act/{tag}/pair_in"] = xc
+        out[f"act/{tag}/pair_cpl"] = np.asarray(act.pair_cpl(minijax.wrap(xc.copy())))
+
+
+def gen_sampler_steps(ref, out):
+    """common_samplers.py:28-33,58-82 (proposals) and metropolis.py:291-322 (_update) on INJECTED picks / uniforms:
+    ``jr.split`` hands out the injected numbers, ``jr.choice(key, n, p=...)`` returns the injected index,
+    ``jr.choice(key, array)`` the array element at the injected index, ``jr.uniform`` the injected uniforms -- the
+    mapping from PRNG bits to these numbers is third-party code and stays unpinned."""
+    sites, csamp, metro, samples, big = ref["sites"], ref["csamp"], ref["metro"], ref["samples"], ref["big"]
+    W = minijax.wrap
+    rng = np.random.default_rng(17)
+
+    def choice(key, a, shape=None, p=None, **kw):
+        if np.ndim(a) == 0:
+            return key
+        return W(np.asarray(a))[key]
+
+    for mod in (csamp, metro):
+        mod.jr.split = lambda key, n: key
+        mod.jr.choice = choice
+        mod.jr.uniform = lambda key, shape=None, dtype=None, **kw: key
+    sites.Sites._SITES = None
+    lat = sites.Square(4, Nparticles=(8, 8))
+    N, ns = lat.Nsites, 40
+    s = rand_spins(rng, ns, N, 8)
+    nbr = np.asarray(csamp._get_site_neighbors([1, 2]))
+    nbr[::3, -1] = -1  # some empty table slots, as on lattices with fewer neighbours
+    pos = np.array([rng.choice(np.flatnonzero(r == 1)) for r in s])
+    slot = rng.integers(0, nbr.shape[1], ns)
+    key = W(np.concatenate([pos, slot]))
+    new = csamp._propose_exchange(key, W(s.copy()), 1, W(nbr.copy()))
+    out["smp/exchange/spins"], out["smp/exchange/nbr"], out["smp/exchange/pos"], out["smp/exchange/slot"] = s, nbr, pos, slot
+    out["smp/exchange/new"] = np.asarray(new, dtype=np.int8)
+    s1 = rand_spins(rng, ns, N)
+    pos1 = rng.integers(0, N, ns)
+    out["smp/localflip/spins"], out["smp/localflip/pos"] = s1, pos1
+    out["smp/localflip/new"] = np.asarray(csamp.LocalFlip.propose(None, W(pos1.copy()), W(s1.copy())), dtype=np.int8)
+
+    # _update: LogArray amplitudes with cached internals, several reweight exponents; rows with a zero old
+    # amplitude, with an unmoved proposal, and with an exact tie rate == 1 - u
+    import types as _t
+
+    new_s = np.asarray(new, dtype=np.int8)
+    for rw in (2.0, 1.3):
+        sg0, sg1 = rng.choice([-1.0, 1.0], ns), rng.choice([-1.0, 1.0], ns)
+        l0 = rng.standard_normal(ns) * 2
+        l1 = l0 + rng.standard_normal(ns) * 0.7
+        u = rng.random(ns)
+        moved = np.flatnonzero((new_s != s).any(axis=1))
+        i_zero, i_same, i_tie = int(moved[0]), int(moved[1]), int(moved[2])
+        l0[i_zero], sg0[i_zero] = -np.inf, 0.0            # |psi_old| == 0 -> accepted whatever u is
+        u[i_zero] = 0.0
+        new_s2 = new_s.copy()
+        new_s2[i_same] = s[i_same]                        # unmoved -> never accepted
+        l1[i_same], u[i_same] = l0[i_same] + 5.0, 0.999
+        l1[i_tie] = l0[i_tie]
+        u[i_tie] = 0.0                                    # rate = 1 == 1 - u: strict '>' rejects
+        th0, th1 = rng.standard_normal((ns, 5)), rng.standard_normal((ns, 5))
+        old = samples.Samples(W(s.copy()), big.LogArray(W(sg0.copy()), W(l0.copy())), W(th0.copy()))
+        prop = samples.Samples(W(new_s2.copy()), big.LogArray(W(sg1.copy()), W(l1.copy())), W(th1.copy()))
+        res = metro.Metropolis._update(_t.SimpleNamespace(_reweight=rw), W(u.copy()), None, old, prop)
+        k = f"smp/update/rw{rw}"
+        out[f"{k}/old_spins"], out[f"{k}/new_spins"] = s, new_s2
+        out[f"{k}/special_rows"] = np.array([i_zero, i_same, i_tie])
+        out[f"{k}/old_sign"], out[f"{k}/old_logabs"], out[f"{k}/new_sign"], out[f"{k}/new_logabs"] = sg0, l0, sg1, l1
+        out[f"{k}/u"], out[f"{k}/old_theta"], out[f"{k}/new_theta"] = u, th0, th1
+        out[f"{k}/res_spins"] = np.asarray(res.spins, dtype=np.int8)
+        out[f"{k}/res_sign"], out[f"{k}/res_logabs"] = _parts(res.psi)
+        out[f"{k}/res_theta"] = np.asarray(res.state_internal)
+
+
+def main():
+    import warnings
+
+    warnings.simplefilter("ignore")
+    ref = install_reference()
+    out = {}
+    gen_operator(ref, out)
+    gen_solver(ref, out)
+    gen_symmetry(ref, out)
+    gen_sampler_tables(ref, out)
+    gen_sign(ref, out)
+    gen_containers(ref, out)
+    gen_activations(ref, out)
+    gen_sampler_steps(ref, out)
+    path = os.path.join(HERE, "ref_hotpath.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()
