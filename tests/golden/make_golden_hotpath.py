@@ -101,8 +101,51 @@ def install_reference():
         del sys.modules[f"quantax.sampler.{sub}"]
     samples = importlib.import_module("quantax.sampler.samples")
     metro = importlib.import_module("quantax.sampler.metropolis")
+
+    class VS_TYPE(enum.Enum):  # state/variational.py:40-62 (the module itself needs equinox)
+        real_or_holomorphic = 0
+        non_holomorphic = 1
+        real_to_complex = 2
+
+    sys.modules["quantax.state"].VS_TYPE = VS_TYPE
+    srmod = importlib.import_module("quantax.optimizer.sr")
+    shallow = None
+    try:
+        model_pkg = minijax._AnyModule("quantax.model")
+        model_pkg.__path__ = [os.path.join(REF, "quantax", "model")]
+        sys.modules["quantax.model"] = model_pkg
+        nn_pkg.prod_by_log = act.prod_by_log
+        nn_pkg.Sequential, nn_pkg.RefModel = type("Sequential", (), {}), type("RefModel", (), {})  # base classes only
+        shallow = importlib.import_module("quantax.model.shallow_nets")
+    except Exception as exc:  # class machinery of equinox: the local-update vectors are then skipped
+        print("shallow_nets not importable under the stand-in:", exc)
+    # ResConv: the reference's own model / layer / symmetry classes on the equinox stand-ins of minijax
+    convnets = None
+    try:
+        for name in ("translation", "common_symmetries"):
+            m = importlib.import_module(f"quantax.symmetry.{name}")
+            for attr in ("Translation", "TransND", "Identity", "Z2Inversion", "SpinInverse", "LinearTransform", "Flip",
+                         "Rotation", "C4v", "D6"):
+                if hasattr(m, attr):
+                    setattr(symm_pkg, attr, getattr(m, attr))
+        symm_pkg.Symmetry = symmod.Symmetry
+        del sys.modules["quantax.nn.modules"]
+        modules = importlib.import_module("quantax.nn.modules")
+        nn_pkg.Sequential, nn_pkg.RefModel, nn_pkg.RawInputLayer = modules.Sequential, modules.RefModel, modules.RawInputLayer
+        nnconv = importlib.import_module("quantax.nn.conv")
+        for attr in ("ReshapeConv", "ConvSymmetrize", "Reshape_TriangularB", "ReshapeTo_TriangularB", "Gconv"):
+            setattr(nn_pkg, attr, getattr(nnconv, attr))
+        nn_pkg.apply_he_normal = lambda key, conv: conv  # weights are injected after construction
+        nn_pkg.exp_by_scale, nn_pkg.sinhp1_by_scale, nn_pkg.pair_cpl = act.exp_by_scale, act.sinhp1_by_scale, act.pair_cpl
+        convnets = importlib.import_module("quantax.model.conv_nets")
+    except Exception as exc:
+        import traceback
+
+        traceback.print_exc()
+        print("conv_nets not importable under the stand-in:", exc)
     return dict(gd=gd, sites=sites, operator=operator, opmod=opmod, symmod=symmod, solver=solver, csamp=csamp, sign=sign,
-                act=act, big=big, samples=samples, metro=metro, jax=jax)
+                convnets=convnets, symm_pkg=symm_pkg,
+                act=act, big=big, samples=samples, metro=metro, jax=jax, srmod=srmod, VS_TYPE=VS_TYPE, shallow=shallow)
 
 
 def rand_spins(rng, ns, N, nup=None):
@@ -378,6 +421,167 @@ def gen_sampler_steps(ref, out):
         out[f"{k}/res_theta"] = np.asarray(res.state_internal)
 
 
+def gen_optimizer(ref, out):
+    """optimizer/sr.py: SR.get_step (Ebar, Obar, _Omean, energy, VarE, real_to_complex stacking) with a stand-in
+    state / Hamiltonian that return given Jacobians and local energies, and three consecutive solves of SPRING,
+    MARCH and AdamSR (lines 74-123, 180-195, 247-255, 321-341, 405-421)."""
+    import types as _t
+
+    srmod, solver, samples, VS = ref["srmod"], ref["solver"], ref["samples"], ref["VS_TYPE"]
+    W = minijax.wrap
+    rng = np.random.default_rng(23)
+    ns, npar = 14, 37
+
+    def make(cls, vs_type, Omat, Eloc, **attrs):
+        opt = object.__new__(cls)
+        opt._state = _t.SimpleNamespace(jacobian=lambda spins: W(Omat.copy()), vs_type=vs_type, _holomorphic=False)
+        opt._hamiltonian = _t.SimpleNamespace(Oloc=lambda state, smp: W(Eloc.copy()))
+        opt._imag_time, opt._solver = True, solver.auto_pinv_eig(rtol=1e-10)
+        opt._energy = opt._VarE = None
+        for k, v in attrs.items():
+            setattr(opt, k, v)
+        return opt
+
+    rw = rng.random(ns) + 0.5
+    rw /= rw.mean()
+    spins = rand_spins(rng, ns, 8)
+    for tag, cplx in (("real", False), ("real_to_complex", True)):
+        Omat = rng.standard_normal((ns, npar))
+        Eloc = rng.standard_normal(ns) * 2 - 7
+        if cplx:
+            Omat = Omat + 1j * rng.standard_normal((ns, npar))
+            Eloc = Eloc + 1j * rng.standard_normal(ns)
+            ref["gd"].set_default_dtype(np.complex128)
+        smp = samples.Samples(W(spins.copy()), W(np.ones(ns)), None, W(rw.copy()))
+        opt = make(srmod.SR, VS.real_to_complex if cplx else VS.real_or_holomorphic, Omat, Eloc)
+        step = opt.get_step(smp)
+        k = f"opt/sr_{tag}"
+        out[f"{k}/Omat"], out[f"{k}/Eloc"], out[f"{k}/rw"] = Omat, Eloc, rw
+        out[f"{k}/Ebar"] = np.asarray(opt.get_Ebar(smp))
+        out[f"{k}/Obar"] = np.asarray(opt.get_Obar(smp))
+        out[f"{k}/Omean"] = np.asarray(opt._Omean)
+        out[f"{k}/energy"], out[f"{k}/VarE"] = np.asarray(opt._energy), np.asarray(opt._VarE)
+        out[f"{k}/step"] = np.asarray(step)
+        ref["gd"].set_default_dtype(np.float64)
+    Obars = rng.standard_normal((3, ns, npar)) / np.sqrt(ns)
+    Ebars = rng.standard_normal((3, ns)) / np.sqrt(ns)
+    out["opt/momentum/Obar"], out["opt/momentum/Ebar"] = Obars, Ebars
+    zeros = lambda: W(np.zeros(npar))
+    opts = {"spring": make(srmod.SPRING, VS.real_or_holomorphic, Obars[0], Ebars[0], _mu=0.9, _last_step=zeros()),
+            "march": make(srmod.MARCH, VS.real_or_holomorphic, Obars[0], Ebars[0], _mu=0.95, _beta=0.995,
+                          _last_step=zeros(), _V=zeros(), _t=0),
+            "adamsr": make(srmod.AdamSR, VS.real_or_holomorphic, Obars[0], Ebars[0], _mu=0.95, _beta=0.995, _m=zeros(),
+                           _v=zeros(), _t=0)}
+    for name, opt in opts.items():
+        out[f"opt/momentum/{name}"] = np.stack([np.asarray(opt.solve(W(Obars[i].copy()), W(Ebars[i].copy())))
+                                                for i in range(3)])
+
+
+def gen_local_updates(ref, out):
+    """model/shallow_nets.py:87-108: SingleDense.ref_forward (local update of theta from the flipped sites, then
+    prod_by_log(cosh(theta))), called unbound with a stand-in that carries the weight matrix."""
+    import types as _t
+
+    shallow, act = ref["shallow"], ref["act"]
+    if shallow is None:
+        return
+    W = minijax.wrap
+    rng = np.random.default_rng(29)
+    N, M = 16, 12
+    import jax.numpy as jnp
+
+    for dt in (np.float32, np.float64):
+        Wm = (rng.standard_normal((M, N)) * 0.4).astype(dt)
+        b = (rng.standard_normal(M) * 0.1).astype(dt)
+        stub = _t.SimpleNamespace(layers=[_t.SimpleNamespace(weight=W(Wm.copy())), lambda x: jnp.cosh(x), act.prod_by_log])
+        tag = np.dtype(dt).name
+        out[f"rbm/{tag}/W"], out[f"rbm/{tag}/b"] = Wm, b
+        for nflips in (1, 2):
+            s_old = rand_spins(rng, 9, N, 8)
+            s_new = s_old.copy()
+            for r in range(9):
+                if nflips == 1:
+                    s_new[r, rng.integers(N)] *= -1
+                else:
+                    i, j = rng.choice(np.flatnonzero(s_old[r] == 1)), rng.choice(np.flatnonzero(s_old[r] == -1))
+                    s_new[r, i], s_new[r, j] = -1, 1
+            theta = (s_old.astype(dt) @ Wm.T + b).astype(dt)
+            signs, logs, thetas = [], [], []
+            for r in range(9):
+                psi, th = shallow.SingleDense.ref_forward(stub, W(s_new[r].copy()), W(s_old[r].copy()), nflips,
+                                                          W(theta[r].copy()), return_update=True)
+                sg, lg = _parts(psi)
+                signs.append(sg), logs.append(lg), thetas.append(np.asarray(th))
+            k = f"rbm/{tag}/nflips{nflips}"
+            out[f"{k}/s_old"], out[f"{k}/s_new"], out[f"{k}/theta_old"] = s_old, s_new, theta
+            out[f"{k}/sign"], out[f"{k}/logabs"], out[f"{k}/theta_new"] = np.array(signs), np.array(logs), np.array(thetas)
+
+
+def gen_resconv(ref, out):
+    """model/conv_nets.py:26-183 + nn/conv.py:13-68 + nn/activation.py + symmetry.symmetrize: the reference's ResConv
+    forward (block scalings, gelu placement, residual tiling, bias on all but the last convolution, final scaling,
+    pair_cpl, final activation, channel mean, translation sum) with injected weights, per sample; and the
+    symmetry-projected amplitude  symmetrize(vmap(model)(get_symm_spins(s)))  of state/variational.py:262-266.
+    equinox.nn.Conv and jax.nn.gelu are the documented stand-ins of minijax (third party)."""
+    convnets, sites, act, symm_pkg, gd = ref["convnets"], ref["sites"], ref["act"], ref["symm_pkg"], ref["gd"]
+    if convnets is None:
+        return
+    W = minijax.wrap
+    rng = np.random.default_rng(31)
+    cases = {
+        "sq4_f64_exp": dict(lat=lambda: sites.Square(4, Nparticles=(8, 8)), nb=2, C=4, k=3, dt=np.float64, final="exp", cplx=False),
+        "sq4_f64_sinhp1": dict(lat=lambda: sites.Square(4, Nparticles=(8, 8)), nb=3, C=4, k=3, dt=np.float64, final="sinhp1", cplx=False),
+        "sq6_f32_sinhp1": dict(lat=lambda: sites.Square(6, Nparticles=(18, 18)), nb=2, C=8, k=3, dt=np.float32, final="sinhp1", cplx=False),
+        "chain8_f64_exp": dict(lat=lambda: sites.Chain(8), nb=2, C=4, k=3, dt=np.float64, final="exp", cplx=False),
+        "tri6_f64_cplx": dict(lat=lambda: sites.Triangular(6, Nparticles=(18, 18)), nb=2, C=4, k=3, dt=np.float64, final="exp", cplx=True),
+    }
+    for name, c in cases.items():
+        sites.Sites._SITES = None
+        lat = c["lat"]()
+        gd.set_default_dtype(np.complex128 if c["cplx"] else np.float64)
+        fa = act.exp_by_scale if c["final"] == "exp" else act.sinhp1_by_scale
+        model = convnets.ResConv(c["nb"], c["C"], c["k"], final_activation=fa, dtype=c["dt"],
+                                 out_dtype=np.complex128 if c["cplx"] else None)
+        blocks = [l for l in model.layers if isinstance(l, convnets._ConvBlock)]
+        assert len(blocks) == c["nb"]
+        for i, blk in enumerate(blocks):
+            for cname in ("conv1", "conv2"):
+                conv = getattr(blk, cname)
+                fan_in = int(np.prod(conv.weight.shape[1:]))
+                conv.weight = W((rng.standard_normal(conv.weight.shape) * np.sqrt(2.0 / fan_in)).astype(c["dt"]))
+                out[f"resconv/{name}/block{i}.{cname}.weight"] = np.asarray(conv.weight)
+                if conv.bias is not None:
+                    conv.bias = W((rng.standard_normal(conv.bias.shape) * 0.1).astype(c["dt"]))
+                    out[f"resconv/{name}/block{i}.{cname}.bias"] = np.asarray(conv.bias).reshape(-1)
+        nup = None if name.startswith("chain") else lat.Nsites // 2
+        s = rand_spins(rng, 6, lat.Nsites, nup)
+        out[f"resconv/{name}/spins"] = s
+        res = [_parts(model(W(r.copy()))) for r in s]
+        out[f"resconv/{name}/significand"] = np.array([r[0] for r in res])
+        out[f"resconv/{name}/exponent"] = np.array([r[1] for r in res])
+        # symmetry-projected amplitude
+        if name == "sq4_f64_exp":
+            symm = symm_pkg.Rotation(np.pi / 2, sector=2) @ symm_pkg.Flip() @ symm_pkg.SpinInverse(-1)
+        elif name == "tri6_f64_cplx":
+            symm = symm_pkg.D6(center=(0, 0)) @ symm_pkg.SpinInverse()
+        else:
+            symm = None
+        if symm is not None:
+            import jax
+
+            rows = []
+            for r in s:
+                imgs = symm.get_symm_spins(W(r.copy()))
+                psi = jax.vmap(model)(imgs)
+                rows.append(_parts(symm.symmetrize(psi, W(r.copy()))))
+            out[f"resconv/{name}/symm_perm"] = np.asarray(symm._perm, dtype=np.int64)
+            out[f"resconv/{name}/symm_character"] = np.asarray(symm._character)
+            out[f"resconv/{name}/symm_Z2"] = np.asarray(symm.Z2_inversion)
+            out[f"resconv/{name}/proj_significand"] = np.array([r[0] for r in rows])
+            out[f"resconv/{name}/proj_exponent"] = np.array([r[1] for r in rows])
+        gd.set_default_dtype(np.float64)
+
+
 def main():
     import warnings
 
@@ -392,6 +596,9 @@ def main():
     gen_containers(ref, out)
     gen_activations(ref, out)
     gen_sampler_steps(ref, out)
+    gen_optimizer(ref, out)
+    gen_local_updates(ref, out)
+    gen_resconv(ref, out)
     path = os.path.join(HERE, "ref_hotpath.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -103,6 +103,16 @@ def _flatnonzero(a, size=None, fill_value=None):
     return _nonzero(np.ravel(np.asarray(a)), size=size, fill_value=fill_value)[0]
 
 
+def _argwhere(a, size=None, fill_value=None):
+    idx = np.argwhere(np.asarray(a))
+    if size is None:
+        return idx.view(Arr)
+    out = np.full((size, idx.shape[1]), 0 if fill_value is None else fill_value, dtype=idx.dtype)
+    n = min(size, idx.shape[0])
+    out[:n] = idx[:n]
+    return out.view(Arr)
+
+
 def _cumulative_sum(x, axis=None, dtype=None, include_initial=False):
     x = np.asarray(x)
     if axis is None:
@@ -144,6 +154,7 @@ def make_jnp():
         setattr(jnp, name, _drop_device(getattr(np, name)))
     jnp.nonzero = _nonzero
     jnp.flatnonzero = _flatnonzero
+    jnp.argwhere = _argwhere
     jnp.cumulative_sum = _cumulative_sum
     jnp.argsort = _argsort
     jnp.bool_ = np.bool_
@@ -346,6 +357,59 @@ class _AnyModule(types.ModuleType):
         return _Anything()
 
 
+# ---- equinox stand-ins (third-party semantics restated from the equinox documentation) --------------------------------
+class Module:
+    """equinox.Module for classes that define their own __init__: a plain mutable base class."""
+
+    def __init__(self, *a, **k):
+        pass
+
+
+class Conv(Module):
+    """equinox.nn.Conv: cross-correlation over [channels, *spatial] inputs (no batch axis), weight
+    [out, in, *kernel], bias [out, 1, ...]; padding="SAME" with padding_mode "CIRCULAR" (wrap) or "ZEROS"."""
+
+    def __init__(self, num_spatial_dims, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 use_bias=True, padding_mode="ZEROS", dtype=None, *, key=None):
+        nd = num_spatial_dims
+        k = (kernel_size,) * nd if isinstance(kernel_size, int) else tuple(kernel_size)
+        dtype = np.float32 if dtype is None else dtype
+        if padding != "SAME" or stride != 1 or dilation != 1 or groups != 1:
+            raise NotImplementedError("only the configuration the reference's ResConv uses")
+        self.num_spatial_dims, self.kernel_size, self.padding_mode = nd, k, padding_mode
+        self.weight = np.zeros((out_channels, in_channels) + k, dtype=dtype).view(Arr)
+        self.bias = np.zeros((out_channels,) + (1,) * nd, dtype=dtype).view(Arr) if use_bias else None
+
+    def __call__(self, x, *, key=None):
+        import itertools
+
+        x = np.asarray(x)
+        k, nd = self.kernel_size, self.num_spatial_dims
+        pads = [(0, 0)] + [((kk - 1) // 2, kk - 1 - (kk - 1) // 2) for kk in k]
+        xp = np.pad(x, pads, mode="wrap" if self.padding_mode == "CIRCULAR" else "constant")
+        w = np.asarray(self.weight)
+        out = np.zeros((w.shape[0],) + x.shape[1:], dtype=np.result_type(x.dtype, w.dtype))
+        for tap in itertools.product(*[range(kk) for kk in k]):
+            sl = (slice(None),) + tuple(slice(t, t + n) for t, n in zip(tap, x.shape[1:]))
+            out += np.tensordot(w[(slice(None), slice(None)) + tap], xp[sl], axes=([1], [0]))
+        if self.bias is not None:
+            out = out + np.asarray(self.bias)
+        return out.view(Arr)
+
+
+class EqxSequential(Module):
+    def __init__(self, layers):
+        self.layers = tuple(layers)
+
+
+class Lambda(Module):
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self, x, *, key=None):
+        return self.fn(x)
+
+
 def install():
     """Put the stand-ins into sys.modules under the names the reference imports."""
     jnp = make_jnp()
@@ -396,5 +460,9 @@ def install():
     eqx.is_array_like = lambda x: isinstance(x, (int, float, complex, np.number))
     eqx.is_array = lambda x: isinstance(x, np.ndarray)
     eqx.filter_jit = jit
+    eqx.Module = Module
+    eqx.field = lambda **k: None
+    eqx.nn = mods["equinox.nn"]
+    eqx.nn.Conv, eqx.nn.Sequential, eqx.nn.Lambda = Conv, EqxSequential, Lambda
     sys.modules.update(mods)
     return jax, jnp
