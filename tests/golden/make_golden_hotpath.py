@@ -109,6 +109,7 @@ def install_reference():
 
     sys.modules["quantax.state"].VS_TYPE = VS_TYPE
     srmod = importlib.import_module("quantax.optimizer.sr")
+    temod = importlib.import_module("quantax.optimizer.time_evol")
     shallow = None
     try:
         model_pkg = minijax._AnyModule("quantax.model")
@@ -144,7 +145,7 @@ def install_reference():
         traceback.print_exc()
         print("conv_nets not importable under the stand-in:", exc)
     return dict(gd=gd, sites=sites, operator=operator, opmod=opmod, symmod=symmod, solver=solver, csamp=csamp, sign=sign,
-                convnets=convnets, symm_pkg=symm_pkg,
+                convnets=convnets, symm_pkg=symm_pkg, temod=temod,
                 act=act, big=big, samples=samples, metro=metro, jax=jax, srmod=srmod, VS_TYPE=VS_TYPE, shallow=shallow)
 
 
@@ -477,6 +478,39 @@ def gen_optimizer(ref, out):
                                                 for i in range(3)])
 
 
+def gen_time_evol(ref, out):
+    """optimizer/time_evol.py:55-134: TimeEvol.get_step for a real-parameter / complex-output state, direct
+    (S = Obar^+ Obar, F = Obar^+ Ebar) and chunked (_get_SF_indirect: un-centred sums corrected at the end)."""
+    import types as _t
+
+    temod, solver, samples, VS, gd = ref["temod"], ref["solver"], ref["samples"], ref["VS_TYPE"], ref["gd"]
+    W = minijax.wrap
+    rng = np.random.default_rng(37)
+    ns, npar, N = 12, 7, 10
+    spins = rand_spins(rng, ns, N)
+    while len({r.tobytes() for r in spins}) < ns:
+        spins = rand_spins(rng, ns, N)
+    Omat = rng.standard_normal((ns, npar)) + 1j * rng.standard_normal((ns, npar))
+    Eloc = rng.standard_normal(ns) * 2 - 5 + 1j * rng.standard_normal(ns)
+    row = {r.tobytes(): i for i, r in enumerate(spins)}
+    gd.set_default_dtype(np.complex128)
+    out["tevol/Omat"], out["tevol/Eloc"] = Omat, Eloc
+    for tag, maxp in (("direct", None), ("chunked", 4)):
+        opt = object.__new__(temod.TimeEvol)
+        opt._state = _t.SimpleNamespace(
+            jacobian=lambda s: W(Omat[[row[np.asarray(r, dtype=np.int8).tobytes()] for r in np.asarray(s)]].copy()),
+            vs_type=VS.real_to_complex, _holomorphic=False, nparams=npar)
+        opt._hamiltonian = _t.SimpleNamespace(Oloc=lambda state, smp: W(Eloc.copy()))
+        opt._imag_time, opt._solver, opt._max_parallel = False, solver.pinvh_solve(rtol=1e-10), maxp
+        opt._energy = opt._VarE = None
+        smp = samples.Samples(W(spins.copy()), W(np.ones(ns)), None, W(np.ones(ns)))
+        S, F = opt.get_SF(smp)
+        out[f"tevol/{tag}/S"], out[f"tevol/{tag}/F"] = np.asarray(S), np.asarray(F)
+        out[f"tevol/{tag}/energy"], out[f"tevol/{tag}/VarE"] = np.asarray(opt._energy), np.asarray(opt._VarE)
+        out[f"tevol/{tag}/step"] = np.asarray(opt.get_step(smp))
+    gd.set_default_dtype(np.float64)
+
+
 def gen_local_updates(ref, out):
     """model/shallow_nets.py:87-108: SingleDense.ref_forward (local update of theta from the flipped sites, then
     prod_by_log(cosh(theta))), called unbound with a stand-in that carries the weight matrix."""
@@ -599,6 +633,7 @@ def main():
     gen_optimizer(ref, out)
     gen_local_updates(ref, out)
     gen_resconv(ref, out)
+    gen_time_evol(ref, out)
     path = os.path.join(HERE, "ref_hotpath.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -408,3 +408,17 @@ def test_symmetry_projected_amplitude_matches_reference_code(name):
         mine = d6 @ osym.SpinInverse(olat)
     assert np.array_equal(mine.perm, lat_perm)
     assert np.array_equal(mine.character, GOLD[f"resconv/{name}/symm_character"].real) and mine.Z2 == symm.Z2
+
+
+# ---- real-time TDVP (quantax/optimizer/time_evol.py) --------------------------------------------------------------------
+@pytest.mark.parametrize("tag,maxp", [("direct", None), ("chunked", 4)])
+def test_time_evol_matches_reference_code(tag, maxp):
+    Omat, Eloc = GOLD["tevol/Omat"], GOLD["tevol/Eloc"]
+    step, energy, var, S, F = osolver.time_evol_step(Omat, Eloc, max_parallel=maxp, rtol=1e-10)
+    g = lambda k: GOLD[f"tevol/{tag}/{k}"]
+    assert np.allclose(S, g("S").real, rtol=1e-12, atol=1e-13)  # TimeEvol.solve keeps Re S and -Im F (time_evol.py:119-120)
+    assert np.allclose(F, -g("F").imag, rtol=1e-12, atol=1e-13)
+    assert np.isclose(energy, g("energy"), rtol=1e-13) and np.isclose(var, g("VarE"), rtol=1e-12)
+    ref = g("step")
+    assert np.abs(ref.imag).max() == 0.0
+    assert np.linalg.norm(step - ref.real) <= 1e-8 * np.linalg.norm(ref)
