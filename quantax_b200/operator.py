@@ -217,6 +217,27 @@ class Operator:
                   _lib.ptr(t.ops), t.nterms, _lib.ptr(out), _lib.stream())
         return out
 
+    def apply_off_diag(self, s: torch.Tensor) -> dict:
+        """Off-diagonal elements in the reference's dense layout (operator.py:96-119,493-497):
+        ``{nflips: [s_conn int8 [ns, nconn, N], H_conn f64 [ns, nconn]]}`` with ``nconn`` = the number of terms of
+        the group and ``H_conn = NaN`` where a term does not connect.  Built by scattering the compacted
+        enumeration of ``get_conn`` (the hot path never materialises this tensor); entries the reference keeps with
+        |H| <= 1e-8 are NaN here, and the configuration stored under a NaN entry is the input configuration --
+        both are dropped by every consumer (operator.py:152-153)."""
+        s = _as_spins(s)
+        ns, N = s.shape
+        out = {}
+        for nflips, t in self.group_tables.items():
+            segment, conn_idx, s_compact, H, _ = self.get_conn(s, nflips)
+            H_conn = torch.full((ns, t.nterms), float("nan"), dtype=torch.float64, device=s.device)
+            s_conn = s[:, None, :].repeat(1, t.nterms, 1)
+            if segment.numel() > 0:
+                seg, ci = segment.long(), conn_idx.long()
+                H_conn[seg, ci] = H
+                s_conn[seg, ci] = s_compact
+            out[nflips] = [s_conn, H_conn]
+        return out
+
     def get_conn(self, s: torch.Tensor, nflips: int, conn_size: Optional[int] = None, with_spins: bool = True):
         """Compacted connected configurations of one nflips group: the device-side equivalent of
         _apply_off_diag + _get_conn_size + _get_conn (operator.py:96-165) for ONE device range.

@@ -539,6 +539,9 @@ class QNGD:
         # part again (sr.py:110, variational.py:577); the real step is returned directly
         return step.to(get_real_dtype())
 
+    def save(self, file) -> None:
+        """Save the optimizer internal quantities (sr.py:125-128): plain SR has none."""
+
     def get_step(self, samples, **kw) -> torch.Tensor:
         Ebar = self.get_Ebar(samples, **kw)
         Obar = self.get_Obar(samples)

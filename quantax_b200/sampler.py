@@ -129,6 +129,26 @@ class Metropolis(Sampler):
         if self._thermal_steps > 0:
             self.sweep(self._thermal_steps)
 
+    def propose(self, key, old_spins: torch.Tensor) -> torch.Tensor:
+        """Propose new configurations for a batch of chains (metropolis.py:277-289, common_samplers.py:28-33,
+        157-162).  ``key`` is a ``(seed, step)`` pair -- or an int seed with step 0 -- naming the Philox
+        counter the draw comes from (the reference passes a jax PRNG key); row r uses chain id r.  One launch
+        of qtx_metropolis_propose; ``sweep`` does not go through this method (its proposals are drawn inside
+        the fused sweep kernels from the same stream)."""
+        from . import _lib
+
+        if self._kind is None:
+            raise NotImplementedError
+        seed, step = (key, 0) if isinstance(key, int) else key
+        s = old_spins.to(device=device(), dtype=torch.int8).contiguous()
+        ns, N = s.shape
+        nbr, max_nb, hop = self._proposal_tables()
+        new = torch.empty_like(s)
+        moved = torch.empty(ns, dtype=torch.uint8, device=s.device)
+        _lib.call("qtx_metropolis_propose", int(self._kind), _lib.ptr(s), ns, N, _lib.ptr(nbr), int(max_nb), int(hop), None,
+                  None, int(seed), int(step), 0, _lib.ptr(new), _lib.ptr(moved), _lib.stream())
+        return new
+
     def inject(self, pos: torch.Tensor, u: torch.Tensor, slot: Optional[torch.Tensor] = None) -> None:
         """Parity hook: the NEXT sweep uses these proposal sites [nsweeps, nlocal], neighbour-table
         columns (exchange) and acceptance uniforms instead of the Philox stream."""

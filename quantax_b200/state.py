@@ -46,6 +46,15 @@ class State:
         return None
 
 
+    def ref_forward_with_updates(self, s, s_old, nflips: int, internal):
+        """psi(s) from psi(s_old) and its internal quantities, returning the updated internals (state.py:77-88)."""
+        raise NotImplementedError
+
+    def ref_forward(self, s, s_old, nflips: int, idx_segment, internal):
+        """psi of connected configurations s that differ from s_old[idx_segment] by nflips sites (state.py:90-100)."""
+        raise NotImplementedError
+
+
 class Variational(State):
     def __init__(self, model, param_file=None, symm=None, max_parallel=None, use_ref: bool = True):
         super().__init__(symm)

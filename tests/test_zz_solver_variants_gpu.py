@@ -144,3 +144,50 @@ def test_sr_with_shift_solver_runs_a_vmc_step(qtx):
     ob, _ = osolver.obar(net.jacobian(s), rw)
     eb, _, _ = osolver.ebar(Eo, rw)
     assert _rel(step, osolver.auto_shift_eig(ob, eb, 1e-3, 1e-4)) < 1e-8
+
+
+# ---- API surface added without GPU access; enable with QTX_UNVERIFIED=1 on the first GPU session -------------------
+import os  # noqa: E402
+
+unverified = pytest.mark.skipif(os.environ.get("QTX_UNVERIFIED") != "1",
+                                reason="written after the round's GPU budget ended: first run pending (QTX_UNVERIFIED=1)")
+
+
+@unverified
+def test_apply_off_diag_dense_layout(qtx):
+    from oracle import operator as oop, sampler as osmp
+    from tests.gpu_util import lattice_pair
+
+    lat, olat = lattice_pair(qtx, "square", 4, (8, 8))
+    H = qtx.operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
+    aop = oop.to_array_op_list(oop.heisenberg_op_list(olat, J=[1, 0.5], n_neighbor=[1, 2], msr=True))
+    s = osmp.rand_states(20, 16, 8, seed=5)
+    got = H.apply_off_diag(torch.from_numpy(s).cuda())
+    ref = oop.apply_off_diag(s, aop)
+    assert sorted(got) == sorted(ref)
+    for nflips, (sc, Hc) in got.items():
+        sc, Hc = to_np(sc), to_np(Hc)
+        rs, rH = ref[nflips]
+        assert np.array_equal(np.isnan(Hc), np.isnan(rH))
+        ok = ~np.isnan(rH)
+        assert np.array_equal(Hc[ok], rH[ok]) and np.array_equal(sc[ok], rs[ok])
+
+
+@unverified
+def test_propose_method_draws_from_the_sweep_stream(qtx):
+    from oracle import sampler as osmp, sites as osites
+    from tests.gpu_util import lattice_pair, make_rbm
+
+    lat, olat = lattice_pair(qtx, "square", 4, (8, 8))
+    model, _ = make_rbm(qtx, 16, 8, torch.float64)
+    state = qtx.state.Variational(model)
+    sampler = qtx.sampler.SpinExchange(state, nsamples=64, thermal_steps=0)
+    s = osmp.rand_states(64, 16, 8, seed=9)
+    new = to_np(sampler.propose((1234, 7), torch.from_numpy(s)))
+    table = osites.site_neighbor_table(olat)
+    pos, slot, _ = osmp.philox_proposal("exchange", 1234, 7, np.arange(64), s, 1, table.shape[1])
+    assert np.array_equal(new, osmp.propose_exchange(s, pos, slot, table))
+    flip = qtx.sampler.LocalFlip(qtx.state.Variational(model), nsamples=64, thermal_steps=0)
+    s1 = (2 * np.random.default_rng(3).integers(0, 2, (64, 16)) - 1).astype(np.int8)
+    pos, _, _ = osmp.philox_proposal("localflip", 99, 0, np.arange(64), s1, 1, 0)
+    assert np.array_equal(to_np(flip.propose(99, torch.from_numpy(s1))), osmp.propose_localflip(s1, pos))
