@@ -81,6 +81,21 @@ class Sampler:
         return w / (tot / self._nsamples)
 
 
+class RandomSampler(Sampler):
+    r"""Random configurations with equal probability (quantax/sampler/sampler.py:125-143): the reweight exponent is
+    0, so the samples carry the factor |psi|^2 / <|psi|^2>.  One batched forward of the state per call."""
+
+    def __init__(self, state, nsamples: int):
+        super().__init__(state, nsamples, reweight=0.0)
+
+    def sweep(self) -> Samples:
+        full = rand_states(self.nsamples)
+        lo = self._rank * self._nlocal
+        spins = full[lo:lo + self._nlocal].contiguous()
+        psi = self._state(spins)
+        return Samples(spins, psi, None, self._get_reweight_factor(psi))
+
+
 class Metropolis(Sampler):
     """quantax/sampler/metropolis.py:76-322."""
 

@@ -191,3 +191,19 @@ def test_propose_method_draws_from_the_sweep_stream(qtx):
     s1 = (2 * np.random.default_rng(3).integers(0, 2, (64, 16)) - 1).astype(np.int8)
     pos, _, _ = osmp.philox_proposal("localflip", 99, 0, np.arange(64), s1, 1, 0)
     assert np.array_equal(to_np(flip.propose(99, torch.from_numpy(s1))), osmp.propose_localflip(s1, pos))
+
+
+@unverified
+def test_random_sampler_reweighting(qtx):
+    from tests.gpu_util import lattice_pair, make_rbm
+
+    lat, olat = lattice_pair(qtx, "square", 4, (8, 8))
+    model, net = make_rbm(qtx, 16, 8, torch.float64)
+    state = qtx.state.Variational(model)
+    smp = qtx.sampler.RandomSampler(state, 128).sweep()
+    s = to_np(smp.spins)
+    assert (s.sum(axis=1) == 0).all()  # Nparticles = (8, 8)
+    sign, logabs = net.forward(s)
+    w = np.exp(2 * logabs)
+    assert np.allclose(to_np(smp.reweight_factor), w / w.mean(), rtol=1e-10)
+    assert np.allclose(to_np(smp.psi.logabs), logabs, rtol=1e-10, atol=1e-10)
