@@ -96,6 +96,16 @@ def Triangular(L, boundary=1, Nparticles=None):
     return Lattice(ext, np.array([[1, 0], [0.5, np.sqrt(0.75)]]), boundary, Nparticles)
 
 
+def TriangularB(L, boundary=1, Nparticles=None):
+    """common_lattices.py:118-139."""
+    return Lattice([3 * L, L], np.array([[1, 0], [1.5, np.sqrt(0.75)]]), boundary, Nparticles)
+
+
+def Cube(L, boundary=1, Nparticles=None):
+    """common_lattices.py:51-57."""
+    return Lattice([L, L, L], np.eye(3), boundary, Nparticles)
+
+
 def site_neighbor_table(lattice, n_neighbor=1):
     """sampler/common_samplers.py:36-51: [N, max_nb] int32 table of neighbours of each
     site in ascending site order, padded with -1 (``flatnonzero(size=, fill_value=-1)``)."""

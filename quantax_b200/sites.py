@@ -174,3 +174,12 @@ class Triangular(Lattice):
             extent = [extent] * 2
         super().__init__(extent, np.array([[1, 0], [0.5, np.sqrt(0.75)]]), None, boundary, particle_type,
                          Nparticles, double_occ)
+
+
+class TriangularB(Lattice):
+    """2D triangular lattice of type B, N = 3 extent^2 sites (quantax/sites/common_lattices.py:118-139)."""
+
+    def __init__(self, extent: int, boundary=1, particle_type=PARTICLE_TYPE.spin, Nparticles=None, double_occ=None):
+        super().__init__([extent * 3, extent], np.array([[1, 0], [1.5, np.sqrt(0.75)]]), None, boundary, particle_type,
+                         Nparticles, double_occ)
+

@@ -268,6 +268,22 @@ def gen_sampler_tables(ref, out):
             out[f"nbr/{lat_name}/{tag}"] = np.asarray(csamp._get_site_neighbors(nn_arg), dtype=np.int64)
 
 
+def gen_more_lattices(ref, out):
+    """sites/common_lattices.py: TriangularB and Cube geometry, neighbour shells and Heisenberg op lists from the
+    reference's own NumPy code (the other lattices are in ref_tables.npz)."""
+    sites, operator = ref["sites"], ref["operator"]
+    for name, mk in {"triangularB2": lambda: sites.TriangularB(2), "cube3": lambda: sites.Cube(3)}.items():
+        sites.Sites._SITES = None
+        lat = mk()
+        out[f"lat/{name}/coord"] = lat.coord
+        for n in (1, 2):
+            out[f"lat/{name}/nb{n}"] = np.asarray(lat.get_neighbor(n), dtype=np.int64)
+        H = operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2])
+        out[f"lat/{name}/j1j2/names"] = np.array([o for o, _ in H.op_list])
+        out[f"lat/{name}/j1j2/J"] = np.array([t[0] for _, ts in H.op_list for t in ts], dtype=np.float64)
+        out[f"lat/{name}/j1j2/idx"] = np.array([list(t[1:]) for _, ts in H.op_list for t in ts], dtype=np.int64)
+
+
 def gen_sign(ref, out):
     sites, sign = ref["sites"], ref["sign"]
     rng = np.random.default_rng(5)
@@ -276,6 +292,11 @@ def gen_sign(ref, out):
     s = rand_spins(rng, 6, lat.Nsites, 18)
     out["sign/triangular6/spins"] = s
     out["sign/triangular6/neel120_phase"] = np.stack([np.asarray(sign.neel120_phase(minijax.wrap(r.copy()))) for r in s])
+    sites.Sites._SITES = None
+    lat = sites.TriangularB(2)
+    s = rand_spins(rng, 6, lat.Nsites, 6)
+    out["sign/triangularB2/spins"] = s
+    out["sign/triangularB2/neel120_phase"] = np.stack([np.asarray(sign.neel120_phase(minijax.wrap(r.copy()))) for r in s])
 
 
 def _parts(x):
@@ -627,6 +648,7 @@ def main():
     gen_symmetry(ref, out)
     gen_sampler_tables(ref, out)
     gen_sign(ref, out)
+    gen_more_lattices(ref, out)
     gen_containers(ref, out)
     gen_activations(ref, out)
     gen_sampler_steps(ref, out)

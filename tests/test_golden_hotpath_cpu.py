@@ -422,3 +422,30 @@ def test_time_evol_matches_reference_code(tag, maxp):
     ref = g("step")
     assert np.abs(ref.imag).max() == 0.0
     assert np.linalg.norm(step - ref.real) <= 1e-8 * np.linalg.norm(ref)
+
+
+# ---- further lattices (quantax/sites/common_lattices.py) ------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["triangularB2", "cube3"])
+def test_more_lattices_match_reference_code(name):
+    from quantax_b200 import operator, sites
+
+    sites.Sites._SITES = None
+    lat = sites.TriangularB(2) if name == "triangularB2" else sites.Cube(3)
+    olat = osites.TriangularB(2) if name == "triangularB2" else osites.Cube(3)
+    for L in (lat, olat):
+        assert np.allclose(L.coord, GOLD[f"lat/{name}/coord"])
+        for n in (1, 2):
+            assert np.array_equal(L.get_neighbor(n), GOLD[f"lat/{name}/nb{n}"])
+    for ol in (operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2]).op_list,
+               oop.heisenberg_op_list(olat, J=[1, 0.5], n_neighbor=[1, 2])):
+        assert [o for o, _ in ol] == list(GOLD[f"lat/{name}/j1j2/names"])
+        assert np.array_equal(np.array([t[0] for _, ts in ol for t in ts], dtype=np.float64), GOLD[f"lat/{name}/j1j2/J"])
+        assert np.array_equal(np.array([list(t[1:]) for _, ts in ol for t in ts]), GOLD[f"lat/{name}/j1j2/idx"])
+
+
+def test_neel120_phase_on_triangular_b_matches_reference_code():
+    from oracle import models
+
+    s = GOLD["sign/triangularB2/spins"]
+    got = models.compute_sign(models.neel120_kernel(6, 2, triangular_b=True), s, "phase")
+    assert np.allclose(got, GOLD["sign/triangularB2/neel120_phase"], rtol=0, atol=2e-6)
