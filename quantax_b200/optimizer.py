@@ -49,6 +49,25 @@ _WS = _Workspaces()
 DEFAULT_NSLICES = int(os.environ.get("QTX_GRAM_NSLICES", "0"))
 
 
+# Per-kernel timing inside a running step (bench.py): when PHASE_EVENTS is a dict, the dense building blocks record
+# a CUDA-event pair around their launches on the current stream; nothing is recorded (and nothing costs) otherwise.
+PHASE_EVENTS = None
+
+
+def _phase_tic(name: str):
+    if PHASE_EVENTS is None:
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return name, e0, e1
+
+
+def _phase_toc(t) -> None:
+    if t is not None and PHASE_EVENTS is not None:
+        t[2].record()
+        PHASE_EVENTS.setdefault(t[0], []).append((t[1], t[2]))
+
+
 # ---- dense building blocks -----------------------------------------------------------------------
 def gram(A: torch.Tensor, out: Optional[torch.Tensor] = None, nslices: Optional[int] = None, accumulate: bool = False):
     """T = A A^T (float64 [ns, ns]) on the tensor cores (qtx_gram)."""
@@ -60,8 +79,10 @@ def gram(A: torch.Tensor, out: Optional[torch.Tensor] = None, nslices: Optional[
     dt = _lib.dtype_code(A.dtype)
     wsz = _lib.lib().qtx_gram_workspace_size(dt, ns, npar, nslices)
     ws = _WS.get("gram", wsz)
+    t = _phase_tic("gram")
     _lib.call("qtx_gram", dt, _lib.ptr2d(A), ns, npar, A.stride(0), int(nslices), _lib.ptr(out), int(accumulate),
               _lib.ptr(ws), wsz, _lib.stream())
+    _phase_toc(t)
     return out
 
 
@@ -83,12 +104,14 @@ def pinv_eig_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol
     info = torch.empty(1, dtype=torch.int32, device=T.device)
     ws, wsz = _eig_workspace(n)
     rt = -1.0 if rtol is None else float(rtol)
+    t = _phase_tic("eigh_pinv")
     if tol_snr > 1e-6:
         _lib.call("qtx_pinv_eig_solve_snr", _lib.ptr(T), n, _lib.ptr(b.contiguous()), rt, float(atol), float(tol_snr),
                   _lib.ptr(evals), _lib.ptr(y), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
     else:
         _lib.call("qtx_pinv_eig_solve", _lib.ptr(T), n, _lib.ptr(b.contiguous()), rt, float(atol), _lib.ptr(evals),
                   _lib.ptr(y), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+    _phase_toc(t)
     return (y, evals, info) if want_evals else (y, info)
 
 
