@@ -272,9 +272,10 @@ def _gather_rows_as_columns(M: torch.Tensor) -> torch.Tensor:
     """[k, nl] per rank -> [k, P nl] with rank-major columns (the global sample order)."""
     dist = _dist()
     P = dist.get_world_size()
-    buf = torch.empty((P,) + tuple(M.shape), dtype=M.dtype, device=M.device)
+    k, nl = M.shape
+    buf = torch.empty((P * k, nl), dtype=M.dtype, device=M.device)  # concatenation along dim 0 (any backend)
     dist.all_gather_into_tensor(buf, M.contiguous())
-    return buf.permute(1, 0, 2).reshape(M.shape[0], P * M.shape[1]).contiguous()
+    return buf.view(P, k, nl).permute(1, 0, 2).reshape(k, P * nl).contiguous()
 
 
 def lstsq_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: float = 0.0, nslices: Optional[int] = None):

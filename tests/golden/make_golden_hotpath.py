@@ -284,6 +284,41 @@ def gen_more_lattices(ref, out):
         out[f"lat/{name}/j1j2/idx"] = np.array([list(t[1:]) for _, ts in H.op_list for t in ts], dtype=np.int64)
 
 
+ALGEBRA_EXPRESSIONS = {
+    # name -> expression over the module `O` (the reference's or the product's `operator` package)
+    "pm": "O.sigma_p(0) @ O.sigma_m(1)",
+    "pm_H": "(O.sigma_p(0) @ O.sigma_m(1)).H",
+    "mixed": "2 * (O.sigma_p(0) @ O.sigma_m(1)) + O.sigma_z(2) @ O.sigma_z(3) - O.sigma_p(0) @ O.sigma_m(1)",
+    "scaled": "(O.S_x(1) @ O.S_x(2) + 0.5 * O.S_z(3)) / 4",
+    "neg": "-(O.sigma_x(1, 2) + O.sigma_z(0, 3))",
+    "coord_wrap": "O.sigma_z(5, 1) @ O.sigma_z(-1, 0)",
+    "triple": "O.S_p(0) @ O.S_m(5) @ O.S_z(10)",
+    "sum_same_opstr": "O.sigma_z(0) @ O.sigma_z(1) + O.sigma_z(1) @ O.sigma_z(2) + O.sigma_z(2) @ O.sigma_z(3)",
+    "heis_plus_field": "O.Heisenberg(msr=True) + 0.3 * sum((O.sigma_z(i) for i in range(16)), start=0 * O.sigma_z(0))",
+    "rsub": "O.Ising(h=1.0) - O.Heisenberg()",
+}
+
+
+def _op_list_arrays(op_list):
+    names = np.array([o for o, _ in op_list])
+    width = np.array([len(ts) for _, ts in op_list], dtype=np.int64)
+    J = np.array([complex(t[0]) for _, ts in op_list for t in ts])
+    idx = np.array([list(t[1:]) + [-1] * (4 - len(t[1:])) for _, ts in op_list for t in ts], dtype=np.int64)
+    return names, width, J, idx
+
+
+def gen_operator_algebra(ref, out):
+    """operator/operator.py:325-470 (`@ + - * / .H` of Operator) and site_operator.py: op lists of compound
+    expressions from the reference's own pure-Python algebra on a 4x4 square lattice."""
+    sites, O = ref["sites"], ref["operator"]
+    sites.Sites._SITES = None
+    sites.Square(4)
+    for name, expr in ALGEBRA_EXPRESSIONS.items():
+        names, width, J, idx = _op_list_arrays(eval(expr, {"O": O, "sum": sum, "range": range}).op_list)
+        out[f"algebra/{name}/names"], out[f"algebra/{name}/width"] = names, width
+        out[f"algebra/{name}/J"], out[f"algebra/{name}/idx"] = J, idx
+
+
 def gen_sign(ref, out):
     sites, sign = ref["sites"], ref["sign"]
     rng = np.random.default_rng(5)
@@ -649,6 +684,7 @@ def main():
     gen_sampler_tables(ref, out)
     gen_sign(ref, out)
     gen_more_lattices(ref, out)
+    gen_operator_algebra(ref, out)
     gen_containers(ref, out)
     gen_activations(ref, out)
     gen_sampler_steps(ref, out)

@@ -103,6 +103,37 @@ def test_distributed_minnorm_with_shift_solver_two_ranks():
     assert shape == (41,) and same and err < 1e-9, err
 
 
+def _gather_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from quantax_b200.optimizer import _gather_rows_as_columns
+
+        k, nl = 3, 4
+        full = torch.arange(k * nl * world, dtype=torch.float64).reshape(k, nl * world)  # columns = global samples
+        mine = full[:, rank * nl:(rank + 1) * nl].contiguous()
+        got = _gather_rows_as_columns(mine)
+        if rank == 0:
+            out.put(bool(torch.equal(got, full)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_rows_as_columns_restores_the_global_sample_order():
+    """lstsq_pinv_eig(tol_snr > 0) on several ranks: (A V)^T [np, nl] per rank -> [np, Ns] with rank-major columns."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10)
+
+
 def test_sampler_rejects_indivisible_sample_count(monkeypatch):
     """sampler.py:29-33: nsamples must be a multiple of the device count."""
     from quantax_b200 import global_defs, sampler, sites

@@ -449,3 +449,32 @@ def test_neel120_phase_on_triangular_b_matches_reference_code():
     s = GOLD["sign/triangularB2/spins"]
     got = models.compute_sign(models.neel120_kernel(6, 2, triangular_b=True), s, "phase")
     assert np.allclose(got, GOLD["sign/triangularB2/neel120_phase"], rtol=0, atol=2e-6)
+
+
+# ---- operator algebra (quantax/operator/operator.py:325-470, site_operator.py) ------------------------------------------
+def _algebra_expressions():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_hotpath", os.path.join(os.path.dirname(__file__), "golden", "make_golden_hotpath.py"))
+    src = open(spec.origin).read()
+    start = src.index("ALGEBRA_EXPRESSIONS = {")
+    end = src.index("}\n", start) + 1
+    ns = {}
+    exec(src[start:end], ns)  # the dictionary literal only: the generator itself needs /root/reference
+    return ns["ALGEBRA_EXPRESSIONS"]
+
+
+@pytest.mark.parametrize("name", sorted(_algebra_expressions()))
+def test_product_operator_algebra_matches_reference_code(name):
+    from quantax_b200 import operator as O, sites
+
+    sites.Sites._SITES = None
+    sites.Square(4)
+    op_list = eval(_algebra_expressions()[name], {"O": O, "sum": sum, "range": range}).op_list
+    assert [o for o, _ in op_list] == list(GOLD[f"algebra/{name}/names"])
+    assert [len(ts) for _, ts in op_list] == list(GOLD[f"algebra/{name}/width"])
+    J = np.array([complex(t[0]) for _, ts in op_list for t in ts])
+    assert np.allclose(J, GOLD[f"algebra/{name}/J"], rtol=1e-15, atol=0)
+    idx = [list(t[1:]) for _, ts in op_list for t in ts]
+    assert idx == [[v for v in row if v >= 0] for row in GOLD[f"algebra/{name}/idx"].tolist()]
