@@ -478,6 +478,97 @@ def gen_sampler_steps(ref, out):
         out[f"{k}/res_theta"] = np.asarray(res.state_internal)
 
 
+def gen_full_sweep(ref, out):
+    """sampler/metropolis.py:246-322 + common_samplers.py:14-162: the reference's own sweep loop
+    (_partial_sweep -> _single_sweep -> propose -> ref_forward_with_updates -> _update -> _get_reweight_factor) for
+    SpinExchange and LocalFlip on a stand-in state with a closed-form RBM amplitude.  Random draws are served
+    by the stand-ins below and LOGGED (site picked among the allowed ones, neighbour-table slot, uniform), so that
+    the oracle can replay exactly the same draws."""
+    import types as _t
+
+    sites, big, samples_mod, gd = ref["sites"], ref["big"], ref["samples"], ref["gd"]
+    W = minijax.wrap
+    sys.modules.pop("quantax.sampler.common_samplers", None)
+    cs = importlib.import_module("quantax.sampler.common_samplers")  # now on top of the real Metropolis class
+    rng = np.random.default_rng(41)
+
+    class State:
+        use_ref = True
+
+        def __init__(self, Wm, b):
+            self.Wm, self.b = Wm, b
+
+        def _psi(self, theta):
+            c = np.cosh(theta)
+            return big.LogArray(W(np.prod(np.sign(c), axis=-1)), W(np.sum(np.log(np.abs(c)), axis=-1)))
+
+        def init_internal(self, s):
+            return W(np.asarray(s, dtype=np.float64) @ self.Wm.T + self.b)
+
+        def __call__(self, s):
+            return self._psi(np.asarray(self.init_internal(s)))
+
+        def ref_forward_with_updates(self, s, s_old, nflips, internal):
+            theta = self.init_internal(s)  # direct evaluation: the local-update formula is pinned separately
+            return self._psi(np.asarray(theta)), theta
+
+    for kind, reweight in (("exchange", 2.0), ("exchange", 1.5), ("localflip", 2.0)):
+        sites.Sites._SITES = None
+        lat = sites.Square(4, Nparticles=(8, 8)) if kind == "exchange" else sites.Chain(10)
+        N, ns, nsweeps = lat.Nsites, 12, 25
+        Wm, b = rng.standard_normal((6, N)) * 0.4, rng.standard_normal(6) * 0.1
+        spins = rand_spins(rng, ns, N, 8 if kind == "exchange" else None)
+        draws = {"pos": rng.integers(0, 1 << 30, (nsweeps, ns)), "slot": rng.integers(0, 1 << 30, (nsweeps, ns)),
+                 "u": rng.random((nsweeps, ns))}
+        log = {"pos": [], "slot": []}
+        calls = {"n": 0}
+
+        def get_subkeys(num=None):
+            calls["n"] += 1
+            if calls["n"] % 2 == 1:  # keys_propose, then keys_update (metropolis.py:253-254)
+                if kind == "exchange":
+                    return [W(np.concatenate([draws["pos"][t], draws["slot"][t]])) for t in range(num)]
+                return [W(draws["pos"][t].copy()) for t in range(num)]
+            return [W(draws["u"][t].copy()) for t in range(num)]
+
+        def choice(key, a, shape=None, p=None, **kw):
+            if np.ndim(a) == 0:
+                if shape is not None:  # LocalFlip: one site per chain in one call
+                    val = np.asarray(key) % int(a)
+                    log["pos"].extend(val.tolist())
+                    return W(val)
+                valid = np.flatnonzero(np.asarray(p))
+                val = int(valid[int(key) % valid.size])
+                log["pos"].append(val)
+                return np.int64(val)
+            idx = int(key) % len(a)
+            log["slot"].append(idx)
+            return W(np.asarray(a))[idx]
+
+        metro = ref["metro"]
+        for mod in (cs, metro):
+            mod.jr.split = lambda key, n: key
+            mod.jr.choice = choice
+            mod.jr.uniform = lambda key, shape=None, dtype=None, **kw: key
+            mod.get_subkeys = get_subkeys
+        cls = cs.SpinExchange if kind == "exchange" else cs.LocalFlip
+        smp = object.__new__(cls)
+        smp._state, smp._nsamples, smp._reweight = State(Wm, b), ns, W(np.asarray(reweight))
+        if kind == "exchange":
+            smp._hopping_particle, smp._neighbors = 1, cs._get_site_neighbors(1)
+        res = smp._partial_sweep(nsweeps, W(spins.copy()))
+        k = f"sweep/{kind}_rw{reweight}"
+        out[f"{k}/W"], out[f"{k}/b"], out[f"{k}/spins0"] = Wm, b, spins
+        out[f"{k}/pos"] = np.array(log["pos"], dtype=np.int64).reshape(nsweeps, ns)
+        if kind == "exchange":
+            out[f"{k}/slot"] = np.array(log["slot"], dtype=np.int64).reshape(nsweeps, ns)
+        out[f"{k}/u"] = draws["u"]
+        out[f"{k}/spins"] = np.asarray(res.spins, dtype=np.int8)
+        out[f"{k}/sign"], out[f"{k}/logabs"] = _parts(res.psi)
+        out[f"{k}/reweight_factor"] = np.asarray(res.reweight_factor)
+        assert res.state_internal is None
+
+
 def gen_optimizer(ref, out):
     """optimizer/sr.py: SR.get_step (Ebar, Obar, _Omean, energy, VarE, real_to_complex stacking) with a stand-in
     state / Hamiltonian that return given Jacobians and local energies, and three consecutive solves of SPRING,
@@ -692,6 +783,7 @@ def main():
     gen_local_updates(ref, out)
     gen_resconv(ref, out)
     gen_time_evol(ref, out)
+    gen_full_sweep(ref, out)
     path = os.path.join(HERE, "ref_hotpath.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

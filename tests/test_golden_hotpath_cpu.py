@@ -478,3 +478,24 @@ def test_product_operator_algebra_matches_reference_code(name):
     assert np.allclose(J, GOLD[f"algebra/{name}/J"], rtol=1e-15, atol=0)
     idx = [list(t[1:]) for _, ts in op_list for t in ts]
     assert idx == [[v for v in row if v >= 0] for row in GOLD[f"algebra/{name}/idx"].tolist()]
+
+
+# ---- the whole sweep loop (quantax/sampler/metropolis.py:246-322) replayed on the logged draws ---------------------
+@pytest.mark.parametrize("tag", ["exchange_rw2.0", "exchange_rw1.5", "localflip_rw2.0"])
+def test_sweep_loop_matches_reference_code(tag):
+    from oracle import models, sampler as osmp
+
+    g = lambda k: GOLD[f"sweep/{tag}/{k}"]
+    kind, rw = tag.split("_rw")[0], float(tag.split("_rw")[1])
+    net = models.RBM(g("W"), g("b"))
+    nbr = osites.site_neighbor_table(osites.Square(4), 1) if kind == "exchange" else None
+    pos, u = g("pos"), g("u")
+    res = osmp.sweep(osmp.RBMChainModel(net), g("spins0"), pos.shape[0], kind, reweight=rw, neighbors=nbr, hop=1, pos=pos,
+                     slot=g("slot") if kind == "exchange" else None, u=u)
+    assert np.array_equal(res["spins"], g("spins"))          # 25 steps x 12 chains: identical accept / reject history
+    assert not np.array_equal(res["spins"], g("spins0"))
+    sign, logabs = res["psi_chain"]                          # amplitude carried through the local updates
+    assert np.array_equal(sign, g("sign")) and np.allclose(logabs, g("logabs"), rtol=1e-12, atol=1e-12)
+    assert np.allclose(osmp.reweight_factor(res["psi_chain"], rw), g("reweight_factor"), rtol=1e-12)
+    if rw != 2.0:
+        assert np.ptp(g("reweight_factor")) > 1e-3
