@@ -499,3 +499,23 @@ def test_sweep_loop_matches_reference_code(tag):
     assert np.allclose(osmp.reweight_factor(res["psi_chain"], rw), g("reweight_factor"), rtol=1e-12)
     if rw != 2.0:
         assert np.ptp(g("reweight_factor")) > 1e-3
+
+
+def test_product_symmetry_composition_matches_reference_code():
+    """`Rotation @ Flip @ SpinInverse(-1)` on the square lattice and `D6 @ SpinInverse` on the triangular lattice: the
+    product's host-side group tables equal those of the reference's own classes (order of elements included)."""
+    from quantax_b200 import sites, symmetry
+
+    sites.Sites._SITES = None
+    sites.Square(4, Nparticles=(8, 8))
+    symm = symmetry.Rotation(np.pi / 2, sector=2) @ symmetry.Flip() @ symmetry.SpinInverse(-1)
+    assert np.array_equal(np.asarray(symm.perm), GOLD["resconv/sq4_f64_exp/symm_perm"])
+    assert np.array_equal(np.asarray(symm.character), GOLD["resconv/sq4_f64_exp/symm_character"].real)
+    assert symm.Z2_inversion == int(GOLD["resconv/sq4_f64_exp/symm_Z2"]) == -1
+    sites.Sites._SITES = None
+    sites.Triangular(6, Nparticles=(18, 18))
+    symm = symmetry.D6(center=(0, 0)) @ symmetry.SpinInverse()
+    assert np.array_equal(np.asarray(symm.perm), GOLD["resconv/tri6_f64_cplx/symm_perm"])
+    assert np.array_equal(np.asarray(symm.character), GOLD["resconv/tri6_f64_cplx/symm_character"].real)
+    assert symm.Z2_inversion == int(GOLD["resconv/tri6_f64_cplx/symm_Z2"]) == 1
+    assert symm.nsymm == 24
