@@ -66,7 +66,8 @@ def install_reference():
     sys.modules["quantax.utils"] = utils
     importlib.import_module("quantax.utils.sharding")
     arr = importlib.import_module("quantax.utils.array")
-    for name in ("local_to_replicate", "to_distribute_array", "to_replicate_array", "to_replicate_numpy", "array_extend"):
+    for name in ("local_to_replicate", "to_distribute_array", "to_replicate_array", "to_replicate_numpy", "array_extend",
+                 "array_set"):
         setattr(utils, name, getattr(arr, name))
     tree = importlib.import_module("quantax.utils.tree")        # filter_tree_map
     big = importlib.import_module("quantax.utils.big_array")    # LogArray / ScaleArray / where (plain dataclasses)
@@ -569,6 +570,102 @@ def gen_full_sweep(ref, out):
         assert res.state_internal is None
 
 
+def gen_chunk_and_mix_sweeps(ref, out):
+    """sampler/metropolis.py:217-244 (_chunk_sweep: states without local updates evaluate psi only for the chains whose
+    proposal moved, through _get_update_size / _get_updated_spins / _get_new_psi) and :325-428 (MixSampler: every
+    step is proposed by a randomly chosen component).  Draws are served and logged as in gen_full_sweep."""
+    sites, big, metro = ref["sites"], ref["big"], ref["metro"]
+    W = minijax.wrap
+    cs = sys.modules["quantax.sampler.common_samplers"]
+    rng = np.random.default_rng(43)
+    sites.Sites._SITES = None
+    lat = sites.Square(4, Nparticles=(8, 8))
+    N, ns, nsweeps = lat.Nsites, 12, 20
+    Wm, b = rng.standard_normal((6, N)) * 0.4, rng.standard_normal(6) * 0.1
+
+    class State:
+        use_ref = False
+        forward_calls = []
+
+        def __call__(self, s):
+            s = np.asarray(s, dtype=np.float64)
+            State.forward_calls.append(s.shape[0])
+            c = np.cosh(s @ Wm.T + b)
+            return big.LogArray(W(np.prod(np.sign(c), axis=-1)), W(np.sum(np.log(np.abs(c)), axis=-1)))
+
+        def init_internal(self, s):
+            return None
+
+        def ref_forward_with_updates(self, s, s_old, nflips, internal):
+            return self(s), None
+
+    for scenario in ("chunk", "mix"):
+        spins = rand_spins(rng, ns, N, 8)
+        draws = {"pos": rng.integers(0, 1 << 30, (nsweeps, ns)), "slot": rng.integers(0, 1 << 30, (nsweeps, ns)),
+                 "u": rng.random((nsweeps, ns)), "comp": rng.integers(0, 1 << 30, nsweeps)}
+        log = {"pos": [], "slot": [], "comp": []}
+        order = (["comp"] if scenario == "mix" else []) + ["propose", "update"]
+        calls = {"n": 0}
+
+        def get_subkeys(num=None):
+            what = order[calls["n"] % len(order)]
+            calls["n"] += 1
+            if what == "comp":
+                return W(draws["comp"].copy())
+            if what == "propose":
+                return [W(np.concatenate([draws["pos"][t], draws["slot"][t]])) for t in range(num)]
+            return [W(draws["u"][t].copy()) for t in range(num)]
+
+        def choice(key, a, shape=None, p=None, **kw):
+            if np.ndim(a) == 0 and shape is not None:  # MixSampler._rand_sampler_idx
+                val = np.asarray(key) % int(a)
+                log["comp"].extend(val.tolist())
+                return W(val)
+            if np.ndim(a) == 0:
+                valid = np.flatnonzero(np.asarray(p))
+                val = int(valid[int(key) % valid.size])
+                log["pos"].append(val)
+                return np.int64(val)
+            idx = int(key) % len(a)
+            log["slot"].append(idx)
+            return W(np.asarray(a))[idx]
+
+        for mod in (cs, metro):
+            mod.jr.split = lambda key, n: key
+            mod.jr.choice = choice
+            mod.jr.uniform = lambda key, shape=None, dtype=None, **kw: key
+            mod.get_subkeys = get_subkeys
+        state = State()
+        State.forward_calls = []
+
+        def component(n_neighbor):
+            c = object.__new__(cs.SpinExchange)
+            c._state, c._nsamples, c._reweight = state, ns, W(np.asarray(2.0))
+            c._hopping_particle, c._neighbors = 1, cs._get_site_neighbors(n_neighbor)
+            return c
+
+        k = f"sweep/{scenario}"
+        if scenario == "chunk":
+            smp = component(1)
+            smp._spins = W(spins.copy())
+            res = smp._chunk_sweep(nsweeps, 4)
+            out[f"{k}/forward_batch_sizes"] = np.array(State.forward_calls, dtype=np.int64)
+        else:
+            comps = (component(1), component(2))
+            smp = object.__new__(metro.MixSampler)
+            smp._state, smp._nsamples, smp._reweight = state, ns, W(np.asarray(2.0))
+            smp._samplers, smp._ratio = comps, W(np.array([0.5, 0.5]))
+            res = smp._partial_sweep(nsweeps, W(spins.copy()))
+            out[f"{k}/comp"] = np.array(log["comp"], dtype=np.int64)
+            out[f"{k}/nbr2"] = np.asarray(cs._get_site_neighbors(2), dtype=np.int64)
+        out[f"{k}/W"], out[f"{k}/b"], out[f"{k}/spins0"] = Wm, b, spins
+        out[f"{k}/pos"] = np.array(log["pos"], dtype=np.int64).reshape(nsweeps, ns)
+        out[f"{k}/slot"] = np.array(log["slot"], dtype=np.int64).reshape(nsweeps, ns)
+        out[f"{k}/u"] = draws["u"]
+        out[f"{k}/spins"] = np.asarray(res.spins, dtype=np.int8)
+        out[f"{k}/sign"], out[f"{k}/logabs"] = _parts(res.psi)
+
+
 def gen_optimizer(ref, out):
     """optimizer/sr.py: SR.get_step (Ebar, Obar, _Omean, energy, VarE, real_to_complex stacking) with a stand-in
     state / Hamiltonian that return given Jacobians and local energies, and three consecutive solves of SPRING,
@@ -784,6 +881,7 @@ def main():
     gen_resconv(ref, out)
     gen_time_evol(ref, out)
     gen_full_sweep(ref, out)
+    gen_chunk_and_mix_sweeps(ref, out)
     path = os.path.join(HERE, "ref_hotpath.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -519,3 +519,35 @@ def test_product_symmetry_composition_matches_reference_code():
     assert np.array_equal(np.asarray(symm.character), GOLD["resconv/tri6_f64_cplx/symm_character"].real)
     assert symm.Z2_inversion == int(GOLD["resconv/tri6_f64_cplx/symm_Z2"]) == 1
     assert symm.nsymm == 24
+
+
+def test_chunked_moved_only_sweep_matches_reference_code():
+    """metropolis.py:217-244: for states without local updates the reference itself forwards only the chains whose
+    proposal moved (padded to the chunk size); the chains equal a sweep that evaluates every proposal."""
+    from oracle import models, sampler as osmp
+
+    g = lambda k: GOLD[f"sweep/chunk/{k}"]
+    net = models.RBM(g("W"), g("b"))
+    nbr = osites.site_neighbor_table(osites.Square(4), 1)
+    res = osmp.sweep(osmp.FullForwardChainModel(net), g("spins0"), g("pos").shape[0], "exchange", neighbors=nbr, hop=1,
+                     pos=g("pos"), slot=g("slot"), u=g("u"))
+    assert np.array_equal(res["spins"], g("spins"))
+    assert np.array_equal(res["psi"][0], g("sign")) and np.allclose(res["psi"][1], g("logabs"), rtol=1e-12, atol=1e-12)
+    sizes = g("forward_batch_sizes")  # first the full batch, then per step the moved chains rounded up to the chunk of 4
+    assert sizes[0] == 12 and (sizes[1:] % 4 == 0).all() and sizes[1:].max() <= 12 and sizes[1:].min() < 12
+
+
+def test_mix_sampler_sweep_matches_reference_code():
+    from oracle import models, sampler as osmp
+
+    g = lambda k: GOLD[f"sweep/mix/{k}"]
+    net = models.RBM(g("W"), g("b"))
+    lat = osites.Square(4)
+    nbrs = [osites.site_neighbor_table(lat, 1), osites.site_neighbor_table(lat, 2)]
+    assert np.array_equal(nbrs[1], g("nbr2"))
+    comp = g("comp")
+    assert 0 < comp.sum() < comp.size  # both components were used
+    res = osmp.mix_sweep(osmp.FullForwardChainModel(net), g("spins0"), comp, ["exchange", "exchange"], nbrs, [1, 1],
+                         pos=g("pos"), slot=g("slot"), u=g("u"))
+    assert np.array_equal(res["spins"], g("spins"))
+    assert np.array_equal(res["psi"][0], g("sign")) and np.allclose(res["psi"][1], g("logabs"), rtol=1e-12, atol=1e-12)
