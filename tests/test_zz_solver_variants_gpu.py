@@ -207,3 +207,25 @@ def test_random_sampler_reweighting(qtx):
     w = np.exp(2 * logabs)
     assert np.allclose(to_np(smp.reweight_factor), w / w.mean(), rtol=1e-10)
     assert np.allclose(to_np(smp.psi.logabs), logabs, rtol=1e-10, atol=1e-10)
+
+
+@unverified
+@pytest.mark.parametrize("ns,npar,dtype,nslices", [(100, 333, np.float64, 0), (257, 1000, np.float64, 8),
+                                                   (130, 4099, np.float64, 7), (64, 70001, np.float64, 8),
+                                                   (200, 500, np.float32, 0), (300, 777, np.float64, 5)])
+def test_gram_kernel_equals_its_digit_arithmetic_bit_for_bit(qtx, ns, npar, dtype, nslices):
+    """oracle/gram_digits.py restates the digit split, the exact integer level sums and the order of the rounded
+    additions of gram_split_kernel + gram_tc2_kernel: the tensor-core result must equal it exactly (including two
+    K chunks at 70001 columns and 8 digits)."""
+    from oracle import gram_digits as gd
+    from quantax_b200.optimizer import gram
+
+    rng = np.random.default_rng(ns + npar)
+    A = (rng.standard_normal((ns, npar)) * np.exp(3 * rng.standard_normal((ns, 1)))).astype(dtype)
+    A[:, ::7] *= 1e-3
+    A[2] = 0.0
+    T = to_np(gram(torch.from_numpy(A).cuda(), nslices=nslices))
+    ref = gd.gram(A, nslices)
+    assert np.array_equal(T, ref), float(np.abs(T - ref).max())
+    T2 = to_np(gram(torch.from_numpy(A).cuda(), out=torch.from_numpy(ref.copy()).cuda(), nslices=nslices, accumulate=True))
+    assert np.array_equal(T2, gd.gram(A, nslices, T=ref))
