@@ -128,6 +128,30 @@ def test_c_abi_exports_every_declared_symbol():
     assert handle.qtx_abi_version() == 1
 
 
+def test_c_abi_rejects_null_pointers_with_a_status_and_a_message():
+    """Error behaviour of the boundary (include/qtx_b200.h conventions): every int-returning entry point validates
+    its arguments before touching the device -- null pointers with non-empty sizes give a negative qtx_status and a
+    message from qtx_last_error(); empty batches are no-ops or rejected, never a crash.  No compute call is made."""
+    from quantax_b200 import _lib
+
+    L = _lib.lib()
+    no_pointer_check = {"qtx_peer_free", "qtx_peer_close"}  # free / close of NULL is a no-op, like cudaFree(0)
+    checked = 0
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if res is not ctypes.c_int or ctypes.c_void_p not in args:
+            continue
+        for fill in (1, 0):
+            vals = [None if a is ctypes.c_void_p else (0.0 if a is ctypes.c_double else fill) for a in args]
+            rc = getattr(L, name)(*vals)
+            if fill == 1 and name not in no_pointer_check:
+                assert rc in (-1, -3), f"{name}(null pointers) returned {rc}"
+                assert name in L.qtx_last_error().decode(), f"{name}: message does not name the entry point"
+                checked += 1
+            else:
+                assert rc <= 0
+    assert checked >= 55
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "quantax_b200")
     for dirpath, _, files in os.walk(pkg):
