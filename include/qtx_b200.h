@@ -355,6 +355,31 @@ int qtx_rows_dot_snr(const double* M, int64_t nrows, int64_t n, int64_t ld, cons
 int qtx_pinv_apply(const double* Ut, int64_t n, const double* evals, double* rho_inout, double rtol,
                    double atol, double* y_out, qtx_stream_t stream);
 
+/* The same soft pseudo-inverse y = f(T) b, f(lambda) = lambda^5 / (lambda^6 + c^6), c = rtol max|lambda| + atol
+ * (solver.py:94-111,142-146 after `eigh`), WITHOUT an eigendecomposition: by partial fractions over the roots
+ * z_k = c exp(i pi (2k+1)/6) of lambda^6 + c^6,  f(T) b = (1/3) Re sum_{k=0,1,2} (T - z_k I)^-1 b  exactly.
+ *   qtx_sym_absmax_eig        : lam_out [1] device = max|lambda| of the symmetric T [n, n] from `steps` Lanczos
+ *                               steps (three-term recurrence + bisection; steps <= 1024).
+ *   qtx_pinv_rational_partial : for every k in shift_mask (bit k), complex LU of T - z_k I (cuSOLVER Zgetrf /
+ *                               Zgetrs, library calls), `refine_steps` refinement steps with the residual in
+ *                               double-double arithmetic, and ydd (+)= Re x_k as a double-double vector
+ *                               ydd_inout float64 [2][n] = (hi, lo).  T is NOT overwritten.  The ranks of a
+ *                               distributed solve take different shifts.  rtol < 0 selects 1e-12; rtol = atol = 0
+ *                               is QTX_ERR_UNSUPPORTED (plain inverse: use qtx_pinv_eig_solve).
+ *                               info_out int32 [1] device (0 = all factorizations succeeded).
+ *   qtx_dd_sum_scale          : y_out [n] = scale * sum_q ydd[q] for `count` double-double vectors
+ *                               ydd float64 [count][2][n], summed in order and rounded once (scale = 1/3).
+ * All three use the workspace of qtx_pinv_rational_workspace_size (0 on failure). */
+size_t qtx_pinv_rational_workspace_size(int64_t n);
+int qtx_sym_absmax_eig(const double* T, int64_t n, int steps, double* lam_out, void* workspace,
+                       size_t workspace_bytes, qtx_stream_t stream);
+int qtx_pinv_rational_partial(const double* T, int64_t n, const double* b, double rtol, double atol,
+                              const double* lam, int shift_mask, int refine_steps, double* ydd_inout,
+                              int accumulate, int32_t* info_out, void* workspace, size_t workspace_bytes,
+                              qtx_stream_t stream);
+int qtx_dd_sum_scale(const double* ydd, int count, int64_t n, double scale, double* y_out,
+                     qtx_stream_t stream);
+
 /* y = (T + shift I)^-1 b, shift = rshift * trace(T) + ashift, by Cholesky (minnorm_shift_eig /
  * lstsq_shift_eig, solver.py:50-77; `solve(assume_a="pos")`).  rshift < 0 selects the dtype
  * default (1e-12).  T [n, n] float64 symmetric is overwritten by its factor; info_out int32 [1]

@@ -10,7 +10,7 @@ namespace qtx {
 
 static thread_local cusolverDnHandle_t g_solver = nullptr;
 
-static int solver_handle(cusolverDnHandle_t* h) {
+int solver_handle(cusolverDnHandle_t* h) {  // shared with pinv_rational.cu
   if (!g_solver) {
     cusolverStatus_t s = cusolverDnCreate(&g_solver);
     if (s != CUSOLVER_STATUS_SUCCESS) {

@@ -93,11 +93,85 @@ def _eig_workspace(n: int):
     return _WS.get("eig", wsz), wsz
 
 
+# How the soft pseudo-inverse y = f(T) b is evaluated when no eigen-quantity is asked for:
+#   "eigh"     (default) cuSOLVER syevd + the pseudo-inverse epilogue (qtx_pinv_eig_solve)
+#   "rational" three complex shifted LU solves refined in double-double (qtx_pinv_rational_partial): the same
+#              function of T by partial fractions, no eigendecomposition.  Opt-in until its first GPU session.
+PINV_METHOD = os.environ.get("QTX_PINV", "eigh")
+LANCZOS_STEPS = int(os.environ.get("QTX_LANCZOS_STEPS", "128"))
+REFINE_STEPS = int(os.environ.get("QTX_PINV_REFINE", "4"))
+
+
+def sym_absmax_eig(T: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
+    """max|lambda| of a symmetric float64 matrix as a device scalar [1] (Lanczos, qtx_sym_absmax_eig)."""
+    n = T.shape[0]
+    wsz = _lib.lib().qtx_pinv_rational_workspace_size(n)
+    if wsz == 0:
+        raise _lib.QtxError(f"qtx_pinv_rational_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
+    ws = _WS.get("rational", wsz)
+    lam = torch.empty(1, dtype=torch.float64, device=T.device)
+    _lib.call("qtx_sym_absmax_eig", _lib.ptr(T), n, int(LANCZOS_STEPS if steps is None else steps), _lib.ptr(lam),
+              _lib.ptr(ws), wsz, _lib.stream())
+    return lam
+
+
+def rational_shift_masks(P: int):
+    """Which of the three shifts every rank of a replicated solve takes (bit k = shift k)."""
+    if P <= 1:
+        return [7]
+    if P == 2:
+        return [0b101, 0b010]
+    return [1, 2, 4] + [0] * (P - 3)
+
+
+def pinv_rational_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol: float, replicated: bool = False):
+    """y = f(T) b, f(lambda) = lambda^5 / (lambda^6 + c^6), c = rtol max|lambda| + atol -- the soft pseudo-inverse
+    of solver.py:94-111 -- as (1/3) Re sum_k (T - z_k I)^-1 b over the three roots of lambda^6 + c^6 in the upper
+    half plane (exact partial fractions).  T is not overwritten.  ``replicated=True`` states that T and b are
+    identical on every rank of the default process group: the ranks then take different shifts and exchange the
+    double-double partial sums (one all-gather of 2 n doubles); otherwise every process does all three."""
+    n = T.shape[0]
+    wsz = _lib.lib().qtx_pinv_rational_workspace_size(n)
+    if wsz == 0:
+        raise _lib.QtxError(f"qtx_pinv_rational_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
+    ws = _WS.get("rational", wsz)
+    rank, P = world() if replicated else (0, 1)
+    mask = rational_shift_masks(P)[rank]
+    t = _phase_tic("eigh_pinv")
+    lam = sym_absmax_eig(T)
+    ydd = torch.zeros((2, n), dtype=torch.float64, device=T.device)
+    info = torch.zeros(1, dtype=torch.int32, device=T.device)
+    if mask:
+        _lib.call("qtx_pinv_rational_partial", _lib.ptr(T), n, _lib.ptr(b.contiguous()),
+                  -1.0 if rtol is None else float(rtol), float(atol), _lib.ptr(lam), int(mask), int(REFINE_STEPS),
+                  _lib.ptr(ydd), 0, _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+    count = 1
+    if P > 1:
+        allydd = torch.empty((P, 2, n), dtype=torch.float64, device=T.device)
+        _dist().all_gather_into_tensor(allydd.view(P * 2, n), ydd)
+        _dist().all_reduce(info, op=_dist().ReduceOp.MAX)
+        ydd, count = allydd, P
+    y = torch.empty(n, dtype=torch.float64, device=T.device)
+    _lib.call("qtx_dd_sum_scale", _lib.ptr(ydd), count, n, 1.0 / 3.0, _lib.ptr(y), _lib.stream())
+    _phase_toc(t)
+    return y, info
+
+
+def _use_rational(rtol, atol, tol_snr, want_evals) -> bool:
+    if PINV_METHOD != "rational" or want_evals or tol_snr > 1e-6:
+        return False
+    return not (rtol is not None and float(rtol) == 0.0 and float(atol) == 0.0)  # plain inverse: eigenvalue route
+
+
 def pinv_eig_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol: float, want_evals: bool = False,
-                   tol_snr: float = 0.0):
+                   tol_snr: float = 0.0, replicated: bool = False, rational_ok: bool = False):
     """y = U (lambda^+ o rho) from eigh(T), rho = U^T b, optionally damped by the signal-to-noise ratio
     (``_sum_without_noise``, solver.py:114-125); T is overwritten by the eigenvectors
-    (qtx_pinv_eig_solve / qtx_pinv_eig_solve_snr)."""
+    (qtx_pinv_eig_solve / qtx_pinv_eig_solve_snr).  With ``QTX_PINV=rational`` the plain (no SNR, no eigenvalues)
+    case of the callers that pass ``rational_ok`` (the SR / MinSR solves, whose result x = A^T y or f(S) A^T b has no
+    component along null directions of T) goes through ``pinv_rational_solve`` instead and T is left untouched."""
+    if rational_ok and _use_rational(rtol, atol, tol_snr, want_evals):
+        return pinv_rational_solve(T, b, rtol, atol, replicated=replicated)
     n = T.shape[0]
     y = torch.empty(n, dtype=torch.float64, device=T.device)
     evals = torch.empty(n, dtype=torch.float64, device=T.device) if want_evals else None
@@ -205,7 +279,11 @@ class _CudaOps:
         _dist().all_reduce(T)
         return T
 
-    pinv_eig_solve = staticmethod(pinv_eig_solve)
+    @staticmethod
+    def pinv_eig_solve(T, b, rtol, atol):
+        # T (all-reduced Gram) and b (all-gathered) are identical on every rank here
+        return pinv_eig_solve(T, b, rtol, atol, replicated=True, rational_ok=True)
+
     matvec_t = staticmethod(matvec_t)
 
 
@@ -257,7 +335,7 @@ def minnorm_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: f
         rank, P = world()
         if P == 1:
             T = gram(A, nslices=nslices)
-            y, info = pinv_eig_solve(T, b, rtol, atol, tol_snr=tol_snr)
+            y, info = pinv_eig_solve(T, b, rtol, atol, tol_snr=tol_snr, rational_ok=True)
             solve.last_info = info
             return matvec_t(A, y)
         x, info = distributed_minnorm(A, b, rtol, atol, _CudaOps(nslices), _snr_tsolve(rtol, atol, tol_snr))
@@ -302,7 +380,8 @@ def lstsq_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: flo
             F = matvec_t(A, b)
             if P > 1:
                 _dist().all_reduce(F)
-            x, info = pinv_eig_solve(S, F, rtol, atol)
+            # S, F are all-reduced (the same on all ranks) and F = A^T b lies in the range of S
+            x, info = pinv_eig_solve(S, F, rtol, atol, replicated=True, rational_ok=True)
         solve.last_info = info
         return x
 

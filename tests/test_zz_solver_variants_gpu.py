@@ -229,3 +229,82 @@ def test_gram_kernel_equals_its_digit_arithmetic_bit_for_bit(qtx, ns, npar, dtyp
     assert np.array_equal(T, ref), float(np.abs(T - ref).max())
     T2 = to_np(gram(torch.from_numpy(A).cuda(), out=torch.from_numpy(ref.copy()).cuda(), nslices=nslices, accumulate=True))
     assert np.array_equal(T2, gd.gram(A, nslices, T=ref))
+
+
+# ---- eigendecomposition-free pseudo-inverse (csrc/pinv_rational.cu, QTX_PINV=rational) -----------------------------
+@unverified
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (7, 2), (130, 3), (1000, 4)])
+def test_lanczos_absmax_eigenvalue(qtx, n, seed):
+    from oracle import pinv_rational as pr
+    from quantax_b200.optimizer import sym_absmax_eig
+
+    rng = np.random.default_rng(seed)
+    B = rng.standard_normal((n, n))
+    for T in (B @ B.T, -(B @ B.T), B + B.T, np.zeros((n, n)), np.eye(n) * 3.0):
+        ref = np.abs(np.linalg.eigvalsh(T)).max()
+        lam = float(sym_absmax_eig(torch.from_numpy(np.ascontiguousarray(T)).cuda()).item())
+        assert abs(lam - ref) <= 1e-12 * max(ref, 1e-300)
+        assert abs(lam - pr.abs_max_eigenvalue(T, steps=128)) <= 1e-12 * max(ref, 1e-300)
+
+
+def _centred_problem(ns, npar, decay, kind, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "svd":
+        U, _ = np.linalg.qr(rng.standard_normal((ns, ns)))
+        V, _ = np.linalg.qr(rng.standard_normal((npar, ns)))
+        A = (U * np.exp(-decay * np.arange(ns) / ns)) @ V.T
+    else:
+        A = rng.standard_normal((ns, npar)) * np.exp(-decay * rng.random((1, npar)))
+    A -= A.mean(axis=0, keepdims=True)
+    return A / np.sqrt(ns), rng.standard_normal(ns) / np.sqrt(ns)
+
+
+@unverified
+@pytest.mark.parametrize("ns,npar,decay,kind,rtol", [(96, 700, 3, "col", None), (130, 333, 1, "col", 1e-10),
+                                                     (64, 640, 6, "svd", 1e-8), (300, 1200, 2, "svd", 1e-3)])
+def test_rational_pseudo_inverse_equals_the_eigenvalue_route(qtx, ns, npar, decay, kind, rtol):
+    from oracle import pinv_rational as pr
+    from quantax_b200.optimizer import pinv_eig_solve, pinv_rational_solve
+
+    A, b = _centred_problem(ns, npar, decay, kind, ns)
+    T = A @ A.T
+    Tt, bt = torch.from_numpy(T).cuda(), torch.from_numpy(b).cuda()
+    y, info = pinv_rational_solve(Tt, bt, rtol, 0.0)
+    assert int(info.item()) == 0
+    assert np.array_equal(to_np(Tt), T)  # T is not overwritten
+    y = to_np(y)
+    y_eig = to_np(pinv_eig_solve(Tt.clone(), bt, rtol, 0.0)[0])
+    y_ref = osolver.minsr_pinv_eig(T, b, rtol=rtol)
+    assert _rel(A.T @ y, A.T @ y_ref) < 1e-10 and _rel(A.T @ y, A.T @ y_eig) < 1e-10
+    assert _rel(A.T @ y, A.T @ pr.pinv_rational_solve(T, b, rtol=rtol)) < 1e-10
+
+
+@unverified
+def test_rational_pseudo_inverse_at_the_cutoff_beats_eigh(qtx):
+    """Against the exact f(T) b (50 digits) of a spectrum running through the default cut-off."""
+    from quantax_b200.optimizer import pinv_eig_solve, pinv_rational_solve
+    from tests.test_pinv_rational_cpu import _exact
+
+    A, b = _centred_problem(60, 240, 20, "svd", 11)
+    T = A @ A.T
+    xt = A.T @ _exact(T, b, 1e-12)
+    Tt, bt = torch.from_numpy(T).cuda(), torch.from_numpy(b).cuda()
+    e_rat = _rel(A.T @ to_np(pinv_rational_solve(Tt, bt, None, 0.0)[0]), xt)
+    e_eig = _rel(A.T @ to_np(pinv_eig_solve(Tt.clone(), bt, None, 0.0)[0]), xt)
+    assert e_rat < 1e-8 and e_rat < e_eig
+
+
+@unverified
+def test_minsr_step_through_the_rational_route(qtx, monkeypatch):
+    import quantax_b200.optimizer as qopt
+
+    A, b = _problem(200, 3000, seed=5)
+    At, bt = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    x_eig = to_np(qopt.auto_pinv_eig(rtol=1e-10)(At.clone(), bt))
+    monkeypatch.setattr(qopt, "PINV_METHOD", "rational")
+    x_rat = to_np(qopt.auto_pinv_eig(rtol=1e-10)(At.clone(), bt))
+    ref = osolver.auto_pinv_eig(A, b, rtol=1e-10)
+    assert _rel(x_rat, ref) < 1e-9 and _rel(x_rat, x_eig) < 1e-9
+    # SNR damping needs the eigen-directions: it stays on the eigenvalue route
+    x_snr = to_np(qopt.auto_pinv_eig(rtol=1e-10, tol_snr=1.0)(At.clone(), bt))
+    assert _rel(x_snr, osolver.auto_pinv_eig(A, b, rtol=1e-10, tol_snr=1.0)) < 1e-8
