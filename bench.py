@@ -374,9 +374,24 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_probe:
+            line["experimental"] = unverified_probe()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def unverified_probe(timeout_s=420):
+    """First GPU run of code written after the round's GPU budget ended (tools/unverified_probe.py), in a
+    subprocess with a time-out and AFTER every measurement: informational, never part of the metric, and a failure
+    there cannot touch this process."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "unverified_probe.py")], cwd=ROOT,
+                           capture_output=True, text=True, timeout=timeout_s)
+        last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        return json.loads(last[-1]) if last else {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -520,6 +535,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-probe", action="store_true", help="skip the first-run probe of unverified code (tools/unverified_probe.py)")
     ap.add_argument("--workload", default="B", choices=["B", "E"],
                     help="B = BASELINE.json configs[1] (the driver's line); E = per-GPU slice of configs[4] (ResConv)")
     args = ap.parse_args()

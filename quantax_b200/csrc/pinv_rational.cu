@@ -191,28 +191,28 @@ struct ShiftParams {
 
 __device__ __forceinline__ double cutoff_of(const double* lam, const ShiftParams& p) { return p.rtol * lam[0] + p.atol; }
 
-// M = T - z I (complex128), rhs = b, x = 0.  A zero cut-off with a zero matrix (c == 0) gives M = I, rhs = 0.
+// M = T - z I (complex128), rhs = b.  A zero cut-off (only possible for T = 0: rtol = atol = 0 is refused) gives
+// M = I, rhs = 0, i.e. y = 0 like the reference's where(|lambda| > 0, ., 0); a NaN cut-off propagates.
 __global__ void __launch_bounds__(256) shift_build_kernel(const double* __restrict__ T, int64_t n,
                                                           const double* __restrict__ b,
                                                           const double* __restrict__ lam, ShiftParams p,
                                                           cuDoubleComplex* __restrict__ M,
                                                           cuDoubleComplex* __restrict__ rhs) {
   const double c = cutoff_of(lam, p);
-  const bool degenerate = !(c > 0.0);
+  const bool degenerate = (c == 0.0);
   const double zr = c * p.cs, zi = c * p.sn;
-  const int64_t total = n * n;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = e / n, j = e - i * n;
-    double re = T[e], im = 0.0;
-    if (i == j) {
-      re -= zr;
-      im = -zi;
-      if (degenerate) re = 1.0;
-    } else if (degenerate) {
-      re = 0.0;
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const double* row = T + i * n;
+    cuDoubleComplex* out = M + i * n;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+      double re = degenerate ? 0.0 : row[j], im = 0.0;
+      if (i == j) {
+        re = degenerate ? 1.0 : re - zr;
+        im = degenerate ? 0.0 : -zi;
+      }
+      out[j] = make_cuDoubleComplex(re, im);
     }
-    M[e] = make_cuDoubleComplex(re, im);
-    if (j == 0) rhs[i] = make_cuDoubleComplex(degenerate ? 0.0 : b[i], 0.0);
+    if (threadIdx.x == 0) rhs[i] = make_cuDoubleComplex(degenerate ? 0.0 : b[i], 0.0);
   }
 }
 
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) dd_residual_kernel(const double* __restri
       ti = dd_add(ti, {red[w][2], red[w][3]});
     }
     const double c = cutoff_of(lam, p);
-    if (!(c > 0.0)) {  // degenerate system M = I, rhs = 0
+    if (c == 0.0) {  // degenerate system M = I, rhs = 0
       r[i] = make_cuDoubleComplex(-xrh[i], -xih[i]);
       return;
     }
@@ -438,7 +438,7 @@ extern "C" int qtx_pinv_rational_partial(const double* T, int64_t n, const doubl
   for (int k = 0; k < 3; ++k) {
     if (!((shift_mask >> k) & 1)) continue;
     ShiftParams p = {rtol, atol, kCos[k], kSin[k]};
-    unsigned gb = 8u * (unsigned)num_sms();
+    const unsigned gb = n < 16 * (int64_t)num_sms() ? (unsigned)n : 16u * (unsigned)num_sms();
     shift_build_kernel<<<gb, 256, 0, st>>>(T, n, b, lam, p, M, rhs);
     QTX_LAUNCH_CHECK();
     // the matrix is complex SYMMETRIC, so its row-major image is its column-major image
