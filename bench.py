@@ -381,7 +381,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def unverified_probe(timeout_s=420):
+def unverified_probe(timeout_s=300):
     """First GPU run of code written after the round's GPU budget ended (tools/unverified_probe.py), in a
     subprocess with a time-out and AFTER every measurement: informational, never part of the metric, and a failure
     there cannot touch this process."""

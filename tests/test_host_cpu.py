@@ -245,3 +245,14 @@ def test_eqx_leaf_file_roundtrip(tmp_path):
     for v in (False, 1, 4, 3):
         np.save(buf, np.asarray(v))
     assert path.read_bytes() == buf.getvalue()
+
+
+def test_rational_shift_masks_cover_every_shift_once():
+    """Rank split of the eigendecomposition-free pseudo-inverse (optimizer.rational_shift_masks)."""
+    from quantax_b200.optimizer import rational_shift_masks
+
+    for P in range(1, 9):
+        masks = rational_shift_masks(P)
+        assert len(masks) == P and all(0 <= m < 8 for m in masks)
+        assert sum(masks) == 7 and all((a & b) == 0 for i, a in enumerate(masks) for b in masks[i + 1:])
+        assert max(bin(m).count("1") for m in masks) == -(-3 // min(P, 3))  # balanced: ceil(3 / min(P, 3)) shifts

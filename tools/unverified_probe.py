@@ -73,7 +73,7 @@ def main():
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zz_solver_variants_gpu.py"),
                             "-m", "gpu", "-q", "--no-header", "-p", "no:cacheprovider", "-k",
                             "apply_off_diag or propose_method or random_sampler or bit_for_bit or lanczos or rational",
-                            "--tb=line"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=200)
+                            "--tb=line"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=150)
         tail = [ln for ln in r.stdout.strip().splitlines() if ln.strip()][-12:]
         res["unverified_tests"] = {"rc": r.returncode, "tail": [ln[:300] for ln in tail]}
     except Exception as e:  # noqa: BLE001
