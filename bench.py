@@ -376,9 +376,34 @@ def run_b200(args):
             line["cpu_baseline"] = cpu_baseline()
         if world == 1 and not args.no_probe:
             line["experimental"] = unverified_probe()
+    if world > 1 and not args.no_probe:
+        exp = multi_gpu_probe(rank, local_rank, world)  # every rank starts its own subprocess
+        if rank == 0:
+            line["experimental"] = exp
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_probe(rank, local_rank, world, timeout_s=180):
+    """tools/multi_gpu_probe.py as one subprocess per rank with its own rendezvous port, after every measurement of
+    this process: fused Gram + exchange and the rank-split pseudo-inverse at this world size.  Informational."""
+    try:
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(local_rank), WORLD_SIZE=str(world),
+                   MASTER_ADDR=os.environ.get("MASTER_ADDR", "127.0.0.1"),
+                   MASTER_PORT=str((int(os.environ.get("MASTER_PORT", "29500")) + 17 - 1024) % 64000 + 1024),
+                   QTX_P2P_TIMEOUT_S="20")
+        for k in ("TORCHELASTIC_RUN_ID", "TORCHELASTIC_USE_AGENT_STORE", "GROUP_RANK", "ROLE_RANK"):
+            env.pop(k, None)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "multi_gpu_probe.py")], cwd=ROOT, env=env,
+                           capture_output=True, text=True, timeout=timeout_s)
+        last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        if rank != 0:
+            return None
+        return json.loads(last[-1]) if last else {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def unverified_probe(timeout_s=300):
