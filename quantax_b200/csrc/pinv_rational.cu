@@ -19,6 +19,7 @@
 #include <cusolverDn.h>
 
 #include "common.cuh"
+#include "dd_math.cuh"
 
 namespace qtx {
 
@@ -26,43 +27,7 @@ int solver_handle(cusolverDnHandle_t* h);  // solver.cu
 
 constexpr int kLanczosMaxSteps = 1024;
 
-// ---- double-double helpers (error-free transformations; the intrinsics keep nvcc from contracting them) --------
-struct dd {
-  double hi, lo;
-};
-__device__ __forceinline__ dd two_sum(double a, double b) {
-  const double s = __dadd_rn(a, b);
-  const double bb = __dsub_rn(s, a);
-  const double e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
-  return {s, e};
-}
-__device__ __forceinline__ dd quick_two_sum(double a, double b) {  // |a| >= |b|
-  const double s = __dadd_rn(a, b);
-  return {s, __dsub_rn(b, __dsub_rn(s, a))};
-}
-__device__ __forceinline__ dd two_prod(double a, double b) {
-  const double p = __dmul_rn(a, b);
-  return {p, __fma_rn(a, b, -p)};
-}
-__device__ __forceinline__ dd dd_add(dd a, dd b) {
-  dd s = two_sum(a.hi, b.hi);
-  const dd t = two_sum(a.lo, b.lo);
-  s.lo = __dadd_rn(s.lo, t.hi);
-  s = quick_two_sum(s.hi, s.lo);
-  s.lo = __dadd_rn(s.lo, t.lo);
-  return quick_two_sum(s.hi, s.lo);
-}
-__device__ __forceinline__ dd dd_add_d(dd a, double b) {
-  dd s = two_sum(a.hi, b);
-  s.lo = __dadd_rn(s.lo, a.lo);
-  return quick_two_sum(s.hi, s.lo);
-}
-__device__ __forceinline__ dd dd_mul_d(dd a, double b) {
-  dd p = two_prod(a.hi, b);
-  p.lo = __fma_rn(a.lo, b, p.lo);
-  return quick_two_sum(p.hi, p.lo);
-}
-__device__ __forceinline__ dd dd_neg(dd a) { return {-a.hi, -a.lo}; }
+// ---- double-double helpers: dd_math.cuh (shared with the CPU test of the same arithmetic) ----------------------
 __device__ __forceinline__ dd dd_shfl_xor(dd a, int o) {
   return {__shfl_xor_sync(FULL, a.hi, o), __shfl_xor_sync(FULL, a.lo, o)};
 }
@@ -146,39 +111,12 @@ __global__ void __launch_bounds__(1024) lanczos_step_kernel(int64_t n, double* _
   }
 }
 
-__device__ int sturm_count(const double* alpha, const double* beta, int m, double x) {
-  int cnt = 0;
-  double d = 1.0;
-  for (int i = 0; i < m; ++i) {
-    const double off = i > 0 ? beta[i - 1] * beta[i - 1] : 0.0;
-    d = (alpha[i] - x) - off / d;
-    if (d == 0.0) d = 1e-300;
-    if (d < 0.0) ++cnt;
-  }
-  return cnt;
-}
-
 // lane 0: smallest, lane 1: largest eigenvalue of the tridiagonal matrix (bisection on the Sturm count)
 __global__ void __launch_bounds__(32) tridiag_absmax_kernel(const double* __restrict__ alpha,
                                                             const double* __restrict__ beta, int m,
                                                             double* __restrict__ lam_out) {
-  double lo = alpha[0], hi = alpha[0];
-  for (int i = 0; i < m; ++i) {
-    const double r = (i > 0 ? fabs(beta[i - 1]) : 0.0) + (i < m - 1 ? fabs(beta[i]) : 0.0);
-    lo = fmin(lo, alpha[i] - r);
-    hi = fmax(hi, alpha[i] + r);
-  }
-  const int target = threadIdx.x == 0 ? 1 : m;
   double ev = 0.0;
-  if (threadIdx.x < 2) {
-    for (int it = 0; it < 200; ++it) {
-      const double mid = 0.5 * (lo + hi);
-      if (mid <= lo || mid >= hi) break;
-      if (sturm_count(alpha, beta, m, mid) >= target) hi = mid;
-      else lo = mid;
-    }
-    ev = fabs(0.5 * (lo + hi));
-  }
+  if (threadIdx.x < 2) ev = fabs(tridiag_eigenvalue(alpha, beta, m, threadIdx.x == 0 ? 1 : m));
   const double other = __shfl_xor_sync(FULL, ev, 1);
   if (threadIdx.x == 0) lam_out[0] = fmax(ev, other);
 }
@@ -253,12 +191,8 @@ __global__ void __launch_bounds__(256) dd_residual_kernel(const double* __restri
   dd sr = {0.0, 0.0}, si = {0.0, 0.0};
   for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
     const double t = row[j];
-    dd pr = two_prod(t, xrh[j]);
-    pr.lo = __fma_rn(t, xrl[j], pr.lo);
-    dd pi = two_prod(t, xih[j]);
-    pi.lo = __fma_rn(t, xil[j], pi.lo);
-    sr = dd_add(sr, pr);
-    si = dd_add(si, pi);
+    sr = dd_fma_acc(sr, t, xrh[j], xrl[j]);
+    si = dd_fma_acc(si, t, xih[j], xil[j]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
