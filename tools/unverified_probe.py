@@ -48,6 +48,11 @@ def rational_probe(n=4096, npar=8192):
     lam, out["lanczos_ms"] = timed(lambda: qopt.sym_absmax_eig(T))
     out["lanczos_rel_err"] = float((lam[0] - evals.abs().max()).abs() / evals.abs().max())
     (y_r, info_r), out["rational_route_ms"] = timed(lambda: qopt.pinv_rational_solve(T, b, None, 0.0))
+    keep = qopt.REFINE_STEPS
+    qopt.REFINE_STEPS = 0  # Lanczos + 3 x (build, Zgetrf, one Zgetrs): what the refinement adds is the difference
+    _, out["rational_route_no_refinement_ms"] = timed(lambda: qopt.pinv_rational_solve(T, b, None, 0.0))
+    qopt.REFINE_STEPS = keep
+    out["refine_steps"] = keep
     out["info"] = [int(info_e.item()), int(info_r.item())]
     x_e, x_r = qopt.matvec_t(A, y_e), qopt.matvec_t(A, y_r)
     out["x_rel_diff_default_rtol"] = float((x_e - x_r).norm() / x_e.norm())
