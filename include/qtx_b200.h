@@ -359,7 +359,10 @@ int qtx_pinv_apply(const double* Ut, int64_t n, const double* evals, double* rho
  * (solver.py:94-111,142-146 after `eigh`), WITHOUT an eigendecomposition: by partial fractions over the roots
  * z_k = c exp(i pi (2k+1)/6) of lambda^6 + c^6,  f(T) b = (1/3) Re sum_{k=0,1,2} (T - z_k I)^-1 b  exactly.
  *   qtx_sym_absmax_eig        : lam_out [1] device = max|lambda| of the symmetric T [n, n] from `steps` Lanczos
- *                               steps (three-term recurrence + bisection; steps <= 1024).
+ *                               steps (three-term recurrence + bisection; steps <= 1024).  first_step = 0 starts
+ *                               the recurrence; first_step = the `steps` of the previous call continues it from
+ *                               the state kept in the (untouched) workspace, so a caller can double the number
+ *                               of steps until the value settles.
  *   qtx_pinv_rational_partial : for every k in shift_mask (bit k), complex LU of T - z_k I (cuSOLVER Zgetrf /
  *                               Zgetrs, library calls), `refine_steps` refinement steps with the residual in
  *                               double-double arithmetic, and ydd (+)= Re x_k as a double-double vector
@@ -371,8 +374,8 @@ int qtx_pinv_apply(const double* Ut, int64_t n, const double* evals, double* rho
  *                               ydd float64 [count][2][n], summed in order and rounded once (scale = 1/3).
  * All three use the workspace of qtx_pinv_rational_workspace_size (0 on failure). */
 size_t qtx_pinv_rational_workspace_size(int64_t n);
-int qtx_sym_absmax_eig(const double* T, int64_t n, int steps, double* lam_out, void* workspace,
-                       size_t workspace_bytes, qtx_stream_t stream);
+int qtx_sym_absmax_eig(const double* T, int64_t n, int first_step, int steps, double* lam_out,
+                       void* workspace, size_t workspace_bytes, qtx_stream_t stream);
 int qtx_pinv_rational_partial(const double* T, int64_t n, const double* b, double rtol, double atol,
                               const double* lam, int shift_mask, int refine_steps, double* ydd_inout,
                               int accumulate, int32_t* info_out, void* workspace, size_t workspace_bytes,

@@ -14,7 +14,7 @@ the same ``eps |T| / c`` sensitivity the eigenvalue route has for eigenvalues ne
 """
 import numpy as np
 
-LANCZOS_STEPS = 128  # quantax_b200/optimizer.py LANCZOS_STEPS
+LANCZOS_STEPS = 512  # quantax_b200/optimizer.py LANCZOS_STEPS: upper bound of the adaptive run
 REFINE_STEPS = 4  # quantax_b200/optimizer.py REFINE_STEPS
 
 
@@ -96,10 +96,36 @@ def tridiagonal_extremes(alpha, beta):
     return out[0], out[1]
 
 
-def abs_max_eigenvalue(T: np.ndarray, steps: int = LANCZOS_STEPS) -> float:
-    alpha, beta = lanczos_tridiagonal(T, steps)
-    lo, hi = tridiagonal_extremes(alpha, beta)
-    return max(abs(lo), abs(hi))
+def lanczos_stages(n: int, max_steps: int = LANCZOS_STEPS):
+    """quantax_b200.optimizer.lanczos_stages: 64, 128, 256, ... capped by n and max_steps."""
+    out, k = [], 64
+    cap = max(1, min(n, max_steps))
+    while k < cap:
+        out.append(k)
+        k *= 2
+    out.append(cap)
+    return out
+
+
+def abs_max_eigenvalue(T: np.ndarray, steps=None) -> float:
+    """max|lambda|.  ``steps=None``: the recurrence is evaluated after 64, 128, 256, ... steps until two consecutive
+    values agree to 1e-14 (quantax_b200.optimizer.sym_absmax_eig); the recurrence is deterministic, so evaluating its
+    first k steps equals running k steps."""
+    n = T.shape[0]
+    if steps is not None:
+        alpha, beta = lanczos_tridiagonal(T, steps)
+        lo, hi = tridiagonal_extremes(alpha, beta)
+        return max(abs(lo), abs(hi))
+    stages = lanczos_stages(n)
+    alpha, beta = lanczos_tridiagonal(T, stages[-1])
+    prev = None
+    for k in stages:
+        lo, hi = tridiagonal_extremes(alpha[:k], beta[:k])
+        cur = max(abs(lo), abs(hi))
+        if prev is not None and abs(cur - prev) <= 1e-14 * abs(cur):
+            break
+        prev = cur
+    return cur
 
 
 def shifts(c: float):

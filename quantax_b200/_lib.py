@@ -78,7 +78,7 @@ SIGNATURES = {
     "qtx_rows_dot_snr": (_i32, [_vp, _i64, _i64, _i64, _vp, _f64, _vp, _vp]),
     "qtx_pinv_apply": (_i32, [_vp, _i64, _vp, _vp, _f64, _f64, _vp, _vp]),
     "qtx_pinv_rational_workspace_size": (_sz, [_i64]),
-    "qtx_sym_absmax_eig": (_i32, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "qtx_sym_absmax_eig": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "qtx_pinv_rational_partial": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "qtx_dd_sum_scale": (_i32, [_vp, _i32, _i64, _f64, _vp, _vp]),
     "qtx_shift_chol_workspace_size": (_sz, [_i64]),

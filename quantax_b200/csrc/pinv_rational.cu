@@ -306,9 +306,10 @@ extern "C" size_t qtx_pinv_rational_workspace_size(int64_t n) {
   return L.total;
 }
 
-extern "C" int qtx_sym_absmax_eig(const double* T, int64_t n, int steps, double* lam_out, void* workspace,
-                                  size_t workspace_bytes, qtx_stream_t stream) {
-  QTX_REQUIRE(T && lam_out && workspace && n > 0 && n <= 46340 && steps > 0 && steps <= kLanczosMaxSteps,
+extern "C" int qtx_sym_absmax_eig(const double* T, int64_t n, int first_step, int steps, double* lam_out,
+                                  void* workspace, size_t workspace_bytes, qtx_stream_t stream) {
+  QTX_REQUIRE(T && lam_out && workspace && n > 0 && n <= 46340 && steps > 0 && steps <= kLanczosMaxSteps &&
+                  first_step >= 0 && first_step < steps,
               QTX_ERR_INVALID, "qtx_sym_absmax_eig: bad argument");
   RationalLayout L;
   int rc = rational_layout(n, &L);
@@ -320,9 +321,11 @@ extern "C" int qtx_sym_absmax_eig(const double* T, int64_t n, int steps, double*
   double *v = w + n, *vprev = v + n, *alpha = vprev + n, *beta = alpha + kLanczosMaxSteps,
          *state = beta + kLanczosMaxSteps;
   const int m = steps < n ? steps : (int)n;
-  lanczos_init_kernel<<<1, 1024, 0, st>>>(n, v, vprev, state);
-  QTX_LAUNCH_CHECK();
-  for (int j = 0; j < m; ++j) {
+  if (first_step == 0) {  // otherwise the recurrence continues from the state left in the workspace
+    lanczos_init_kernel<<<1, 1024, 0, st>>>(n, v, vprev, state);
+    QTX_LAUNCH_CHECK();
+  }
+  for (int j = first_step; j < m; ++j) {
     rc = qtx_matvec(QTX_F64, T, n, n, n, v, w, stream);
     if (rc) return rc;
     lanczos_step_kernel<<<1, 1024, 0, st>>>(n, w, v, vprev, alpha, beta, j, state);

@@ -98,21 +98,44 @@ def _eig_workspace(n: int):
 #   "rational" three complex shifted LU solves refined in double-double (qtx_pinv_rational_partial): the same
 #              function of T by partial fractions, no eigendecomposition.  Opt-in until its first GPU session.
 PINV_METHOD = os.environ.get("QTX_PINV", "eigh")
-LANCZOS_STEPS = int(os.environ.get("QTX_LANCZOS_STEPS", "128"))
+LANCZOS_STEPS = int(os.environ.get("QTX_LANCZOS_STEPS", "512"))  # upper bound of the adaptive run (<= 1024)
 REFINE_STEPS = int(os.environ.get("QTX_PINV_REFINE", "4"))
 
 
 def sym_absmax_eig(T: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
-    """max|lambda| of a symmetric float64 matrix as a device scalar [1] (Lanczos, qtx_sym_absmax_eig)."""
+    """max|lambda| of a symmetric float64 matrix as a device scalar [1] (Lanczos, qtx_sym_absmax_eig).  With
+    ``steps=None`` the recurrence is continued to 64, 128, 256, ... steps (at most QTX_LANCZOS_STEPS) until two
+    consecutive values agree to 1e-14 -- the error after 2k steps is about the square of the error after k -- which
+    costs one scalar read-back per stage; an explicit ``steps`` runs exactly that many without synchronising."""
     n = T.shape[0]
     wsz = _lib.lib().qtx_pinv_rational_workspace_size(n)
     if wsz == 0:
         raise _lib.QtxError(f"qtx_pinv_rational_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
     ws = _WS.get("rational", wsz)
     lam = torch.empty(1, dtype=torch.float64, device=T.device)
-    _lib.call("qtx_sym_absmax_eig", _lib.ptr(T), n, int(LANCZOS_STEPS if steps is None else steps), _lib.ptr(lam),
-              _lib.ptr(ws), wsz, _lib.stream())
+    if steps is not None:
+        _lib.call("qtx_sym_absmax_eig", _lib.ptr(T), n, 0, int(steps), _lib.ptr(lam), _lib.ptr(ws), wsz, _lib.stream())
+        return lam
+    done, prev = 0, None
+    for upto in lanczos_stages(n, LANCZOS_STEPS):
+        _lib.call("qtx_sym_absmax_eig", _lib.ptr(T), n, done, upto, _lib.ptr(lam), _lib.ptr(ws), wsz, _lib.stream())
+        done = upto
+        cur = float(lam.item())
+        if prev is not None and abs(cur - prev) <= 1e-14 * abs(cur):
+            break
+        prev = cur
     return lam
+
+
+def lanczos_stages(n: int, max_steps: int):
+    """Step counts at which the adaptive Lanczos run is evaluated: 64, 128, 256, ... capped by n and max_steps."""
+    out, k = [], 64
+    cap = max(1, min(n, max_steps))
+    while k < cap:
+        out.append(k)
+        k *= 2
+    out.append(cap)
+    return out
 
 
 def rational_shift_masks(P: int):

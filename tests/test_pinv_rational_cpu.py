@@ -108,3 +108,20 @@ def test_degenerate_inputs():
     T = np.diag([4.0, 1.0, 1e-3, 0.0, 2.0])
     y = pr.pinv_rational_solve(T, b, rtol=0.0, atol=1e-2)
     assert np.allclose(y, osolver.eigs_inv(np.diag(T), rtol=0.0, atol=1e-2) * b, rtol=1e-13, atol=1e-13)
+
+
+def test_adaptive_lanczos_on_a_dense_spectral_edge():
+    """Wishart matrix: the largest eigenvalues are packed at the edge (relative gaps ~ n^-2/3), where 64 steps are not
+    enough; the staged run continues until two consecutive stages agree."""
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((700, 1400))
+    T = B @ B.T
+    ref = np.linalg.eigvalsh(T).max()
+    assert abs(pr.abs_max_eigenvalue(T, steps=32) - ref) > 1e-9 * ref  # too few steps: not converged
+    assert abs(pr.abs_max_eigenvalue(T) - ref) <= 1e-12 * ref
+    assert pr.lanczos_stages(700) == [64, 128, 256, 512] and pr.lanczos_stages(50) == [50]
+    assert pr.lanczos_stages(64) == [64] and pr.lanczos_stages(5000, 100) == [64, 100]
+    from quantax_b200.optimizer import lanczos_stages
+
+    for n, mx in ((700, 512), (50, 512), (64, 512), (5000, 100), (1, 512), (4096, 1024)):
+        assert lanczos_stages(n, mx) == pr.lanczos_stages(n, mx)
