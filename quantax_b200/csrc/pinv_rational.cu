@@ -15,15 +15,21 @@
 // Against an exact evaluation of f(T) b for the same float64 T this is MORE accurate than the eigenvalue route
 // when eigenvalues lie near the cut-off (oracle/pinv_rational.py, tests/test_pinv_rational_cpu.py).
 // max|lambda| comes from a Lanczos recurrence (three-term, no reorthogonalisation) and bisection on the Sturm count.
+#ifdef QTX_HOST_EMULATION  // tests/native: the kernels below run unmodified on the CPU (threads = std::thread)
+#include "cuda_emu.h"
+#else
 #include <cuComplex.h>
 #include <cusolverDn.h>
 
 #include "common.cuh"
+#endif
 #include "dd_math.cuh"
 
 namespace qtx {
 
+#ifndef QTX_HOST_EMULATION
 int solver_handle(cusolverDnHandle_t* h);  // solver.cu
+#endif
 
 constexpr int kLanczosMaxSteps = 1024;
 
@@ -259,6 +265,7 @@ __global__ void max_info_kernel(int32_t* __restrict__ info, const int32_t* __res
 }
 __global__ void zero_info_kernel(int32_t* __restrict__ info) { info[0] = 0; }
 
+#ifndef QTX_HOST_EMULATION
 struct RationalLayout {
   size_t M, rhs, ipiv, work, x, lanczos, info, total;
   int lwork;
@@ -296,8 +303,11 @@ static int rational_layout(int64_t n, RationalLayout* L) {
   return QTX_OK;
 }
 
+#endif  // QTX_HOST_EMULATION
+
 }  // namespace qtx
 
+#ifndef QTX_HOST_EMULATION
 using namespace qtx;
 
 extern "C" size_t qtx_pinv_rational_workspace_size(int64_t n) {
@@ -409,3 +419,4 @@ extern "C" int qtx_dd_sum_scale(const double* ydd, int count, int64_t n, double 
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }
+#endif  // QTX_HOST_EMULATION
