@@ -349,6 +349,7 @@ def run_b200(args):
                        "nparams": Np, "l2": "256 MiB buffer written before every step (L2 flush)",
                        "gram_nslices": s_eff},
             "sweep_oloc_ms": sweep_oloc_ms / args.steps, "minsr_step_ms": minsr_ms / args.steps,
+            "pinv_method": _optmod.PINV_METHOD,  # "eigh" (cuSOLVER syevd) or "rational" (QTX_PINV)
             "minsr_phases_ms": {**phase, "gram_in_step(split+mma)": gram_in_step_ms,
                                 "eigh_pinv_in_step(cuSOLVER)": eigh_in_step_ms,
                                 "gram_alone(split+mma)": gram_ms, "eigh_pinv_alone(cuSOLVER)": eigh_ms,
