@@ -149,3 +149,108 @@ def test_sampler_rejects_indivisible_sample_count(monkeypatch):
         sampler.Sampler(FakeState(), 7)
     s = sampler.Sampler(FakeState(), 8)
     assert s.nlocal == 4 and s._rank == 1
+
+
+# ---- rank split of the eigendecomposition-free pseudo-inverse (optimizer.pinv_rational_solve) ---------
+class _FakeLib:
+    """CPU stand-ins for the three C entry points, taking the arguments in the order of include/qtx_b200.h, built on
+    the oracle restatement (test infrastructure): what is under test is the Python glue -- shift masks per rank,
+    all-gather of the double-double partial sums, rank-ordered final sum."""
+
+    QtxError = RuntimeError
+
+    def __init__(self):
+        from oracle import pinv_rational as pr
+
+        self.pr = pr
+        self.calls = []
+
+    def lib(self):
+        class L:
+            @staticmethod
+            def qtx_pinv_rational_workspace_size(n):
+                return 64
+
+        return L()
+
+    @staticmethod
+    def ptr(t):
+        return t
+
+    @staticmethod
+    def stream():
+        return 0
+
+    def call(self, name, *a):
+        pr = self.pr
+        self.calls.append(name)
+        if name == "qtx_sym_absmax_eig":
+            T, n, first, steps, lam, ws, wsz, stream = a
+            assert T.shape == (n, n) and 0 <= first < steps
+            lam[0] = pr.abs_max_eigenvalue(T.numpy(), steps=steps)
+        elif name == "qtx_pinv_rational_partial":
+            T, n, b, rtol, atol, lam, mask, refine, ydd, accumulate, info, ws, wsz, stream = a
+            assert ydd.shape == (2, n) and accumulate == 0 and 0 < mask < 8
+            which = [k for k in range(3) if (mask >> k) & 1]
+            yh, yl = pr.pinv_rational_partial(T.numpy(), b.numpy(), None if rtol < 0 else rtol, atol, float(lam[0]), which,
+                                              refine)
+            ydd[0], ydd[1] = torch.from_numpy(yh), torch.from_numpy(yl)
+            info[0] = 0
+        elif name == "qtx_dd_sum_scale":
+            ydd, count, n, scale, y, stream = a
+            parts = ydd.reshape(count, 2, n).numpy()
+            y.copy_(torch.from_numpy(pr.dd_sum_scale([(p[0], p[1]) for p in parts], scale)))
+        else:
+            raise AssertionError(name)
+
+
+def _rational_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pinv_rational as pr
+        from quantax_b200 import optimizer as qopt
+
+        fake = _FakeLib()
+        qopt._lib = fake
+
+        class WS:
+            @staticmethod
+            def get(key, nbytes):
+                return torch.empty(nbytes, dtype=torch.uint8)
+
+        qopt._WS = WS
+        rng = np.random.default_rng(3)  # the same replicated T, b on every rank
+        B = rng.standard_normal((24, 90)) * np.exp(-6 * rng.random((1, 90)))
+        B -= B.mean(axis=0, keepdims=True)
+        T, b = B @ B.T, rng.standard_normal(24)
+        y, info = qopt.pinv_rational_solve(torch.from_numpy(T), torch.from_numpy(b), 1e-9, 0.0, replicated=True)
+        y_single = pr.pinv_rational_solve(T, b, rtol=1e-9)
+        err = float(np.linalg.norm(B.T @ (y.numpy() - y_single)) / np.linalg.norm(B.T @ y_single))
+        gathered = [torch.empty_like(y) for _ in range(world)]
+        dist.all_gather(gathered, y)
+        same = all(torch.equal(g, gathered[0]) for g in gathered)
+        nparts = fake.calls.count("qtx_pinv_rational_partial")
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([nparts]))
+        if rank == 0:
+            out.put((err, same, [int(c.item()) for c in counts], int(info.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_rational_pseudo_inverse_rank_split(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rational_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    err, same, calls, info = q.get(timeout=10)
+    assert same and info == 0 and err < 1e-12, err
+    assert calls == ([1, 1] if world == 2 else [1, 1, 1, 0])  # every rank with a non-empty mask makes one call
