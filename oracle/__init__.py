@@ -24,6 +24,9 @@ Pinning status (see DESIGN.md "Oracle"):
     executed under a NumPy stand-in for jax (tests/golden/minijax.py,
     tests/golden/make_golden_hotpath.py -> tests/golden/ref_hotpath.npz,
     tests/test_golden_hotpath_cpu.py);
+  * ``gram_digits`` and ``pinv_rational`` restate the ARITHMETIC of two product kernels (the int8 digit scheme of
+    the tensor-core Gram, the eigendecomposition-free pseudo-inverse) so that their accuracy claims are checked on
+    the CPU; the reference formulas they reproduce are solver.py:139 and solver.py:94-111;
   * everything that lives in un-vendored third-party code (jax PRNG streams,
     ``jax.nn.gelu`` form, ``equinox.nn.Conv`` padding semantics,
     ``ravel_pytree`` leaf order, ``eigh``) is restated from its published
