@@ -376,11 +376,15 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         if world == 1 and not args.no_probe:
+            t_probe = time.perf_counter()
             line["experimental"] = unverified_probe()
+            line["experimental"]["wall_s_outside_the_measurement"] = round(time.perf_counter() - t_probe, 1)
     if world > 1 and not args.no_probe:
+        t_probe = time.perf_counter()
         exp = multi_gpu_probe(rank, local_rank, world)  # every rank starts its own subprocess
         if rank == 0:
             line["experimental"] = exp
+            line["experimental"]["wall_s_outside_the_measurement"] = round(time.perf_counter() - t_probe, 1)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
