@@ -25,7 +25,7 @@ void emu_sym_absmax_eig(const double* T, int64_t n, int first_step, int steps, u
     }
     emu_launch(1, block, [&] { lanczos_step_kernel(n, w, v, vprev, alpha, beta, j, state); });
   }
-  emu_launch(1, 32, [&] { tridiag_absmax_kernel(alpha, beta, m, lam_out); });
+  emu_launch(1, 64, [&] { tridiag_absmax_kernel(alpha, beta, m, lam_out); });
 }
 
 void emu_shift_build(const double* T, int64_t n, const double* b, const double* lam, double rtol, double atol, double cs,
