@@ -15,21 +15,21 @@
 // Against an exact evaluation of f(T) b for the same float64 T this is MORE accurate than the eigenvalue route
 // when eigenvalues lie near the cut-off (oracle/pinv_rational.py, tests/test_pinv_rational_cpu.py).
 // max|lambda| comes from a Lanczos recurrence (three-term, no reorthogonalisation) and bisection on the Sturm count.
-#ifdef QTX_HOST_EMULATION  // tests/native: the kernels below run unmodified on the CPU (threads = std::thread)
-#include "cuda_emu.h"
+#ifdef QTX_HOST_EMULATION  // tests/native: this file runs unmodified on the CPU (CUDA threads = std::thread,
+#include "cuda_emu.h"       // cuSOLVER = a LAPACK-style stand-in); see tests/test_pinv_rational_emu_cpu.py
+#include "cuda_emu_host.h"
 #else
 #include <cuComplex.h>
 #include <cusolverDn.h>
 
 #include "common.cuh"
+#define QTX_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 #include "dd_math.cuh"
 
 namespace qtx {
 
-#ifndef QTX_HOST_EMULATION
-int solver_handle(cusolverDnHandle_t* h);  // solver.cu
-#endif
+int solver_handle(cusolverDnHandle_t* h);  // solver.cu (tests/native/pinv_rational_emu.cpp under emulation)
 
 constexpr int kLanczosMaxSteps = 1024;
 
@@ -303,7 +303,6 @@ __global__ void max_info_kernel(int32_t* __restrict__ info, const int32_t* __res
 }
 __global__ void zero_info_kernel(int32_t* __restrict__ info) { info[0] = 0; }
 
-#ifndef QTX_HOST_EMULATION
 struct RationalLayout {
   size_t M, rhs, ipiv, work, x, lanczos, info, total;
   int lwork;
@@ -341,11 +340,8 @@ static int rational_layout(int64_t n, RationalLayout* L) {
   return QTX_OK;
 }
 
-#endif  // QTX_HOST_EMULATION
-
 }  // namespace qtx
 
-#ifndef QTX_HOST_EMULATION
 using namespace qtx;
 
 extern "C" size_t qtx_pinv_rational_workspace_size(int64_t n) {
@@ -370,16 +366,16 @@ extern "C" int qtx_sym_absmax_eig(const double* T, int64_t n, int first_step, in
          *state = beta + kLanczosMaxSteps;
   const int m = steps < n ? steps : (int)n;
   if (first_step == 0) {  // otherwise the recurrence continues from the state left in the workspace
-    lanczos_init_kernel<<<1, 1024, 0, st>>>(n, v, vprev, state);
+    QTX_LAUNCH(lanczos_init_kernel, 1, 1024, st, n, v, vprev, state);
     QTX_LAUNCH_CHECK();
   }
   for (int j = first_step; j < m; ++j) {
     rc = qtx_matvec(QTX_F64, T, n, n, n, v, w, stream);
     if (rc) return rc;
-    lanczos_step_kernel<<<1, 1024, 0, st>>>(n, w, v, vprev, alpha, beta, j, state);
+    QTX_LAUNCH(lanczos_step_kernel, 1, 1024, st, n, w, v, vprev, alpha, beta, j, state);
     QTX_LAUNCH_CHECK();
   }
-  tridiag_absmax_kernel<<<1, 64, 0, st>>>(alpha, beta, m, lam_out);
+  QTX_LAUNCH(tridiag_absmax_kernel, 1, 64, st, alpha, beta, m, lam_out);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }
@@ -412,10 +408,10 @@ extern "C" int qtx_pinv_rational_partial(const double* T, int64_t n, const doubl
   double* x = (double*)(base + L.x);
   int32_t* step_info = (int32_t*)(base + L.info);
   const unsigned gn = (unsigned)((n + 255) / 256);
-  zero_info_kernel<<<1, 1, 0, st>>>(info_out);
+  QTX_LAUNCH(zero_info_kernel, 1, 1, st, info_out);
   QTX_LAUNCH_CHECK();
   if (!accumulate) {
-    dd_zero_kernel<<<(unsigned)((2 * n + 255) / 256), 256, 0, st>>>(2 * n, ydd_inout);
+    QTX_LAUNCH(dd_zero_kernel, (unsigned)((2 * n + 255) / 256), 256, st, 2 * n, ydd_inout);
     QTX_LAUNCH_CHECK();
   }
   static const double kCos[3] = {0.86602540378443864676, 0.0, -0.86602540378443864676};  // cos(pi (2k+1)/6)
@@ -424,27 +420,27 @@ extern "C" int qtx_pinv_rational_partial(const double* T, int64_t n, const doubl
     if (!((shift_mask >> k) & 1)) continue;
     ShiftParams p = {rtol, atol, kCos[k], kSin[k]};
     const unsigned gb = n < 16 * (int64_t)num_sms() ? (unsigned)n : 16u * (unsigned)num_sms();
-    shift_build_kernel<<<gb, 256, 0, st>>>(T, n, b, lam, p, M, rhs);
+    QTX_LAUNCH(shift_build_kernel, gb, 256, st, T, n, b, lam, p, M, rhs);
     QTX_LAUNCH_CHECK();
     // the matrix is complex SYMMETRIC, so its row-major image is its column-major image
     s = cusolverDnZgetrf(h, (int)n, (int)n, M, (int)n, work, ipiv, step_info);
     QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnZgetrf failed (%d)", (int)s);
     count_launch();
-    max_info_kernel<<<1, 1, 0, st>>>(info_out, step_info);
+    QTX_LAUNCH(max_info_kernel, 1, 1, st, info_out, step_info);
     QTX_LAUNCH_CHECK();
     for (int it = 0; it <= refine_steps; ++it) {
       if (it > 0) {
-        dd_residual_kernel<<<(unsigned)n, 256, 0, st>>>(T, n, b, lam, p, x, rhs);
+        QTX_LAUNCH(dd_residual_kernel, (unsigned)n, 256, st, T, n, b, lam, p, x, rhs);
         QTX_LAUNCH_CHECK();
       }
       s = cusolverDnZgetrs(h, CUBLAS_OP_N, (int)n, 1, M, (int)n, ipiv, rhs, (int)n, step_info);
       QTX_REQUIRE(s == CUSOLVER_STATUS_SUCCESS, QTX_ERR_SOLVER, "cusolverDnZgetrs failed (%d)", (int)s);
       count_launch();
-      if (it == 0) dd_set_kernel<<<gn, 256, 0, st>>>(n, rhs, x);
-      else dd_correct_kernel<<<gn, 256, 0, st>>>(n, rhs, x);
+      if (it == 0) QTX_LAUNCH(dd_set_kernel, gn, 256, st, n, rhs, x);
+      else QTX_LAUNCH(dd_correct_kernel, gn, 256, st, n, rhs, x);
       QTX_LAUNCH_CHECK();
     }
-    dd_accum_real_kernel<<<gn, 256, 0, st>>>(n, x, ydd_inout, 1);
+    QTX_LAUNCH(dd_accum_real_kernel, gn, 256, st, n, x, ydd_inout, 1);
     QTX_LAUNCH_CHECK();
   }
   return QTX_OK;
@@ -453,8 +449,7 @@ extern "C" int qtx_pinv_rational_partial(const double* T, int64_t n, const doubl
 extern "C" int qtx_dd_sum_scale(const double* ydd, int count, int64_t n, double scale, double* y_out,
                                 qtx_stream_t stream) {
   QTX_REQUIRE(ydd && y_out && count > 0 && n > 0, QTX_ERR_INVALID, "qtx_dd_sum_scale: bad argument");
-  dd_sum_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ydd, count, n, scale, y_out);
+  QTX_LAUNCH(dd_sum_scale_kernel, (unsigned)((n + 255) / 256), 256, (cudaStream_t)stream, ydd, count, n, scale, y_out);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }
-#endif  // QTX_HOST_EMULATION

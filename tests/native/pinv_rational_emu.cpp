@@ -1,10 +1,30 @@
-// Runs the KERNELS of quantax_b200/csrc/pinv_rational.cu on the CPU through tests/native/cuda_emu.h (one std::thread
-// per CUDA thread).  Launch geometry and kernel order follow qtx_sym_absmax_eig / qtx_pinv_rational_partial; the
-// cuSOLVER LU between the kernels is done by the Python test with SciPy.  TEST INFRASTRUCTURE ONLY.
+// Compiles quantax_b200/csrc/pinv_rational.cu for the CPU (tests/native/cuda_emu.h: one std::thread per CUDA thread;
+// cuda_emu_host.h: launch macro, error macros, a LAPACK-style stand-in for cuSOLVER), so that the ENTRY POINTS
+// qtx_sym_absmax_eig / qtx_pinv_rational_partial / qtx_dd_sum_scale run as they are; the emu_* wrappers below run
+// single kernels with a chosen launch geometry.  TEST INFRASTRUCTURE ONLY.
 #define QTX_HOST_EMULATION 1
 #include "pinv_rational.cu"
 
-using namespace qtx;
+// what the entry points of pinv_rational.cu link against inside the library
+namespace qtx {
+int solver_handle(cusolverDnHandle_t* h) {
+  static EmuSolver solver;
+  *h = &solver;
+  return QTX_OK;
+}
+}  // namespace qtx
+extern "C" int qtx_matvec(int dtype, const void* A, int64_t ns, int64_t np, int64_t ld, const double* x, double* v_out,
+                          qtx_stream_t) {
+  if (dtype != QTX_F64 || !A || !x || !v_out) return QTX_ERR_INVALID;
+  const double* a = (const double*)A;
+  for (int64_t r = 0; r < ns; ++r) {
+    double acc = 0.0;
+    for (int64_t k = 0; k < np; ++k) acc += a[r * ld + k] * x[k];
+    v_out[r] = acc;
+  }
+  return QTX_OK;
+}
+extern "C" const char* emu_last_error() { return qtx::g_emu_error; }
 
 extern "C" {
 

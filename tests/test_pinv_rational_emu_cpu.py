@@ -186,3 +186,92 @@ def test_kernel_chain_degenerate_zero_matrix(emu):
     b = np.arange(1.0, n + 1)
     y = _solve(emu, T, b, 1e-12, lam=0.0)
     assert not y.any()
+
+
+# ---- the ENTRY POINTS themselves (host orchestration, workspace layout, cuSOLVER call sequence) --------------------
+def _entry(emu):
+    vp, d, i64, i32, sz = C.c_void_p, C.c_double, C.c_int64, C.c_int, C.c_size_t
+    emu.qtx_pinv_rational_workspace_size.restype = sz
+    emu.qtx_pinv_rational_workspace_size.argtypes = [i64]
+    emu.qtx_sym_absmax_eig.argtypes = [vp, i64, i32, i32, vp, vp, sz, vp]
+    emu.qtx_pinv_rational_partial.argtypes = [vp, i64, vp, d, d, vp, i32, i32, vp, i32, vp, vp, sz, vp]
+    emu.qtx_dd_sum_scale.argtypes = [vp, i32, i64, d, vp, vp]
+    emu.emu_last_error.restype = C.c_char_p
+    return emu
+
+
+def _vp(a):
+    return a.ctypes.data
+
+
+def _entry_solve(emu, T, b, rtol, atol=0.0, masks=(7,), refine=4, accumulate_split=False):
+    """quantax_b200.optimizer.pinv_rational_solve through the C entry points of the emulated library."""
+    n = T.shape[0]
+    wsz = emu.qtx_pinv_rational_workspace_size(n)
+    assert wsz > 0
+    ws = np.full(wsz + 8, 0x5A, dtype=np.uint8)  # guard bytes behind the promised size
+    lam = np.zeros(1)
+    done = 0
+    for upto in pr.lanczos_stages(n):
+        assert emu.qtx_sym_absmax_eig(_vp(T), n, done, upto, _vp(lam), _vp(ws), wsz, None) == 0, emu.emu_last_error()
+        done = upto
+    parts = np.zeros((len(masks), 2, n))
+    info = np.full(1, 77, dtype=np.int32)
+    for q, mask in enumerate(masks):
+        if mask == 0:
+            continue
+        if accumulate_split:  # one call per shift, accumulating into the same double-double vector
+            first = True
+            for k in range(3):
+                if (mask >> k) & 1:
+                    rc = emu.qtx_pinv_rational_partial(_vp(T), n, _vp(b), rtol, atol, _vp(lam), 1 << k, refine,
+                                                       _vp(parts[q]), 0 if first else 1, _vp(info), _vp(ws), wsz, None)
+                    assert rc == 0, emu.emu_last_error()
+                    first = False
+        else:
+            parts[q] = 1e300  # accumulate = 0 must overwrite
+            rc = emu.qtx_pinv_rational_partial(_vp(T), n, _vp(b), rtol, atol, _vp(lam), mask, refine, _vp(parts[q]), 0,
+                                               _vp(info), _vp(ws), wsz, None)
+            assert rc == 0, emu.emu_last_error()
+        assert info[0] == 0
+    assert (ws[wsz:] == 0x5A).all(), "wrote behind the workspace"
+    y = np.zeros(n)
+    assert emu.qtx_dd_sum_scale(_vp(parts), len(masks), n, 1.0 / 3.0, _vp(y), None) == 0
+    return y, float(lam[0])
+
+
+@pytest.mark.parametrize("ns,npar,decay,rtol", [(40, 300, 3, -1.0), (33, 333, 1, 1e-10), (17, 100, 6, 1e-8)])
+def test_entry_points_equal_oracle_and_eigenvalue_route(emu, ns, npar, decay, rtol):
+    emu = _entry(emu)
+    A, b = _problem(ns, npar, decay, seed=ns + 1)
+    T = np.ascontiguousarray(A @ A.T)
+    y, lam = _entry_solve(emu, T, b, rtol)
+    r = None if rtol < 0 else rtol  # rtol < 0 selects the float64 default 1e-12
+    assert abs(lam - np.abs(np.linalg.eigvalsh(T)).max()) <= 1e-12 * lam
+    assert _rel(A.T @ y, A.T @ pr.pinv_rational_solve(T, b, rtol=r)) < 1e-11
+    assert _rel(A.T @ y, A.T @ osolver.minsr_pinv_eig(T, b, rtol=r)) < (1e-10 if rtol > 0 else 1e-9)
+
+
+def test_entry_points_rank_split_accumulate_and_errors(emu):
+    emu = _entry(emu)
+    A, b = _problem(20, 100, 4, seed=3)
+    T = np.ascontiguousarray(A @ A.T)
+    y1, _ = _entry_solve(emu, T, b, 1e-12)
+    y2, _ = _entry_solve(emu, T, b, 1e-12, masks=(0b101, 0b010))
+    y8, _ = _entry_solve(emu, T, b, 1e-12, masks=(1, 2, 4, 0, 0, 0, 0, 0))
+    ya, _ = _entry_solve(emu, T, b, 1e-12, accumulate_split=True)
+    assert _rel(A.T @ y2, A.T @ y1) < 1e-13 and _rel(A.T @ y8, A.T @ y1) < 1e-13 and np.array_equal(ya, y1)
+    # error behaviour: plain inverse refused, small workspace refused, bad mask refused
+    n = T.shape[0]
+    wsz = emu.qtx_pinv_rational_workspace_size(n)
+    ws, lam, ydd, info = np.zeros(wsz, dtype=np.uint8), np.ones(1), np.zeros((2, n)), np.zeros(1, dtype=np.int32)
+    args = lambda rtol, atol, mask, size: (_vp(T), n, _vp(b), rtol, atol, _vp(lam), mask, 4, _vp(ydd), 0, _vp(info),
+                                           _vp(ws), size, None)
+    assert emu.qtx_pinv_rational_partial(*args(0.0, 0.0, 7, wsz)) == -3 and b"plain inverse" in emu.emu_last_error()
+    assert emu.qtx_pinv_rational_partial(*args(1e-12, 0.0, 7, wsz - 1)) == -1 and b"workspace" in emu.emu_last_error()
+    assert emu.qtx_pinv_rational_partial(*args(1e-12, 0.0, 8, wsz)) == -1
+    assert emu.qtx_sym_absmax_eig(_vp(T), n, 5, 5, _vp(lam), _vp(ws), wsz, None) == -1
+    # zero matrix: zero cut-off, y = 0, info = 0
+    Z = np.zeros((6, 6))
+    yz, lz = _entry_solve(emu, Z, np.arange(1.0, 7.0), 1e-12)
+    assert lz == 0.0 and not yz.any()
