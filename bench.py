@@ -187,9 +187,10 @@ def run_b200(args):
 
     def vmc_step(timed):
         flush.fill_(1)
-        e = [ev() for _ in range(4)]
+        e = [ev() for _ in range(5)]
         e[0].record()
         samples = sampler.sweep()
+        e[4].record()  # sweep | Oloc boundary (informational split of the timed region e[0]..e[1])
         Eloc_all = H.Oloc(state, samples)
         e[1].record()
         sub = qtx.sampler.Samples(samples.spins[:rows], samples.psi[:rows], None, samples.reweight_factor[:rows])
@@ -229,6 +230,7 @@ def run_b200(args):
     clk = clocks.stop()
     sweep_oloc_ms = sum(e[0].elapsed_time(e[1]) for e in timed)
     minsr_ms = sum(e[2].elapsed_time(e[3]) for e in timed)
+    sweep_only_ms = sum(e[0].elapsed_time(e[4]) for e in timed) / max(len(timed), 1)
     total_ms = t_all0.elapsed_time(t_all1)
     phase = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in optimizer.timers.items()}
     optimizer.timers = None
@@ -349,6 +351,13 @@ def run_b200(args):
                        "nparams": Np, "l2": "256 MiB buffer written before every step (L2 flush)",
                        "gram_nslices": s_eff},
             "sweep_oloc_ms": sweep_oloc_ms / args.steps, "minsr_step_ms": minsr_ms / args.steps,
+            # split of the timed region of `value` (this rank): SURVEY 8(d) asks for the sweep's HBM-equivalent rate --
+            # the bytes a per-proposal unfused evaluation would move (2 W columns + theta read/write + the spin pair,
+            # 4M*2 + 8M + 2 B) -- next to the fact that the fused kernel keeps theta in registers and W^T in shared
+            # memory, so it is issue / MUFU bound (ncu: 0.6 MB of DRAM traffic per sweep), not HBM bound
+            "value_path": {"sweep_ms": sweep_only_ms, "oloc_ms": sweep_oloc_ms / args.steps - sweep_only_ms,
+                           "proposals_per_s": NS * 2 * N / (sweep_only_ms * 1e-3),
+                           "unfused_hbm_equivalent_GBps": NS * 2 * N * (4 * M * 2 + 8 * M + 2) / (sweep_only_ms * 1e-3) / 1e9},
             "pinv_method": _optmod.PINV_METHOD,  # "eigh" (cuSOLVER syevd) or "rational" (QTX_PINV)
             "minsr_phases_ms": {**phase, "gram_in_step(split+mma)": gram_in_step_ms,
                                 "eigh_pinv_in_step(cuSOLVER)": eigh_in_step_ms,
