@@ -125,3 +125,20 @@ def test_adaptive_lanczos_on_a_dense_spectral_edge():
 
     for n, mx in ((700, 512), (50, 512), (64, 512), (5000, 100), (1, 512), (4096, 1024)):
         assert lanczos_stages(n, mx) == pr.lanczos_stages(n, mx)
+
+
+GOLD = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "ref_hotpath.npz"))
+
+
+@pytest.mark.parametrize("rtol,key,tol", [(1e-10, "auto_pinv_eig_snr0.0", 1e-9), (None, "auto_pinv_eig_default", 1e-6)])
+def test_against_the_references_own_solver_code(rtol, key, tol):
+    """The MinSR / SR steps the reference's OWN `minnorm_pinv_eig` / `lstsq_pinv_eig` produced
+    (tests/golden/make_golden_hotpath.py) from the shifted solves: x = A^T f(A A^T) b and x = f(A^T A) A^T b."""
+    A, b = GOLD["solver/minnorm/A"], GOLD["solver/minnorm/b"]
+    x = A.T @ pr.pinv_rational_solve(A @ A.T, b, rtol=rtol)
+    ref = GOLD[f"solver/minnorm/{key}"]
+    assert np.linalg.norm(x - ref) <= tol * np.linalg.norm(ref)
+    A, b = GOLD["solver/lstsq/A"], GOLD["solver/lstsq/b"]
+    x = pr.pinv_rational_solve(A.T @ A, A.T @ b, rtol=rtol)
+    ref = GOLD[f"solver/lstsq/{key}"]
+    assert np.linalg.norm(x - ref) <= tol * np.linalg.norm(ref)

@@ -275,3 +275,16 @@ def test_entry_points_rank_split_accumulate_and_errors(emu):
     Z = np.zeros((6, 6))
     yz, lz = _entry_solve(emu, Z, np.arange(1.0, 7.0), 1e-12)
     assert lz == 0.0 and not yz.any()
+
+
+def test_entry_points_against_the_references_own_solver_code(emu):
+    """Kernel source + host orchestration of csrc/pinv_rational.cu (emulated) against the steps the reference's own
+    `minnorm_pinv_eig` / `lstsq_pinv_eig` code produced (tests/golden/ref_hotpath.npz, rtol = 1e-10)."""
+    emu = _entry(emu)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_hotpath.npz"))
+    A, b = gold["solver/minnorm/A"], gold["solver/minnorm/b"]
+    y, _ = _entry_solve(emu, np.ascontiguousarray(A @ A.T), np.ascontiguousarray(b), 1e-10)
+    assert _rel(A.T @ y, gold["solver/minnorm/auto_pinv_eig_snr0.0"]) < 1e-9
+    A, b = gold["solver/lstsq/A"], gold["solver/lstsq/b"]
+    x, _ = _entry_solve(emu, np.ascontiguousarray(A.T @ A), np.ascontiguousarray(A.T @ b), 1e-10)
+    assert _rel(x, gold["solver/lstsq/auto_pinv_eig_snr0.0"]) < 1e-9
