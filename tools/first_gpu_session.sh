@@ -22,6 +22,9 @@ if [ "$N" -gt 1 ]; then
       tools/multi_gpu_probe.py > "$OUT/multi_gpu_probe_n$N.json" 2> "$OUT/multi_gpu_probe_n$N.err"
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29612 \
       tests/run_p2p_gram_check.py > "$OUT/p2p_gram_check_n$N.log" 2>&1
+  # the distributed VMC steps (RBM, ResConv, complex ResConv) must equal the single-GPU step with the shifts split over ranks
+  QTX_PINV=rational timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
+      --master-port 29614 tests/run_dist_check.py > "$OUT/dist_check_rational_n$N.log" 2>&1
   QTX_PINV=rational timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
       --master-port 29613 bench.py --gpus "$N" --steps 5 --warmup 3 --no-probe > "$OUT/bench_rational_n$N.json" 2> "$OUT/bench_rational_n$N.err"
 fi
