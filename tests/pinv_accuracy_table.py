@@ -3,7 +3,8 @@
 the same float64 T = A A^T, for (a) the eigenvalue route (LAPACK syevd, the reference's formula), (b) a second LAPACK
 driver (syevr) -- how reproducible the eigenvalue route is --, (c) the three shifted LU solves in plain float64,
 (d) the same with refinement in double-double (the product's arithmetic, oracle/pinv_rational.py).
-Writes profiles/r1_cpu_pinv_rational_accuracy.md.  Needs mpmath; runs in about a minute."""
+Writes profiles/r1_cpu_pinv_rational_accuracy.md.  Needs mpmath; runs in about a minute.  (Lives under tests/ because it
+uses the oracle, which only test code may import.)"""
 import os
 import sys
 
@@ -55,7 +56,7 @@ def main():
         rows.append((decay, rtol, int((w < rtol * lam).sum()), err(eig_route(T, b, rtol, "evd")),
                      err(eig_route(T, b, rtol, "evr")), err(pr.pinv_rational_solve(T, b, rtol=rtol, lam=lam, refine_steps=0)),
                      err(y_ref), corr[:4]))
-    out = ["# Accuracy of the soft pseudo-inverse routes (CPU, `tools/pinv_accuracy_table.py`)", "",
+    out = ["# Accuracy of the soft pseudo-inverse routes (CPU, `tests/pinv_accuracy_table.py`)", "",
            "Relative error of the MinSR step `x = Aᵀ f(AAᵀ) b` against a 50-digit evaluation of `f(T) b` for the same float64",
            "`T` (60 × 60, singular values of `A` = exp(−decay·i/60), centred columns).  `eigh` = the reference's formula on",
            "LAPACK `syevd`; `syevr` = a second LAPACK driver; `LU` = three shifted complex LU solves in float64; `LU + dd` = the",
