@@ -98,7 +98,7 @@ def _eig_workspace(n: int):
 #   "rational" three complex shifted LU solves refined in double-double (qtx_pinv_rational_partial): the same
 #              function of T by partial fractions, no eigendecomposition.  Opt-in until its first GPU session.
 PINV_METHOD = os.environ.get("QTX_PINV", "eigh")
-LANCZOS_STEPS = int(os.environ.get("QTX_LANCZOS_STEPS", "512"))  # upper bound of the adaptive run (<= 1024)
+LANCZOS_STEPS = max(1, min(1024, int(os.environ.get("QTX_LANCZOS_STEPS", "512"))))  # upper bound of the adaptive run
 REFINE_STEPS = int(os.environ.get("QTX_PINV_REFINE", "4"))
 
 
