@@ -230,7 +230,7 @@ def run_b200(args):
     clk = clocks.stop()
     sweep_oloc_ms = sum(e[0].elapsed_time(e[1]) for e in timed)
     minsr_ms = sum(e[2].elapsed_time(e[3]) for e in timed)
-    sweep_only_ms = sum(e[0].elapsed_time(e[4]) for e in timed) / max(len(timed), 1)
+    sweep_only_ms = max(sum(e[0].elapsed_time(e[4]) for e in timed) / max(len(timed), 1), 1e-9)
     total_ms = t_all0.elapsed_time(t_all1)
     phase = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in optimizer.timers.items()}
     optimizer.timers = None
