@@ -32,6 +32,13 @@ namespace qtx {
 int solver_handle(cusolverDnHandle_t* h);  // solver.cu (tests/native/pinv_rational_emu.cpp under emulation)
 
 constexpr int kLanczosMaxSteps = 1024;
+#ifdef QTX_HOST_EMULATION
+constexpr unsigned kLanczosThreads = 128;  // fewer std::threads per launch; the kernels take any multiple of 32
+constexpr unsigned kRowThreads = 64;
+#else
+constexpr unsigned kLanczosThreads = 1024;
+constexpr unsigned kRowThreads = 256;  // dd_residual_kernel: threads per matrix row
+#endif
 
 // ---- double-double helpers: dd_math.cuh (shared with the CPU test of the same arithmetic) ----------------------
 __device__ __forceinline__ dd dd_shfl_xor(dd a, int o) {
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(256) dd_residual_kernel(const double* __restri
                                                           const double* __restrict__ lam, ShiftParams p,
                                                           const double* __restrict__ x,
                                                           cuDoubleComplex* __restrict__ r) {
-  __shared__ double red[8][4];
+  __shared__ double red[32][4];
   const int64_t i = blockIdx.x;
   const double* row = T + i * n;
   const double *xrh = x, *xrl = x + n, *xih = x + 2 * n, *xil = x + 3 * n;
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(256) dd_residual_kernel(const double* __restri
   __syncthreads();
   if (threadIdx.x == 0) {
     dd tr = {0.0, 0.0}, ti = {0.0, 0.0};
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
       tr = dd_add(tr, {red[w][0], red[w][1]});
       ti = dd_add(ti, {red[w][2], red[w][3]});
     }
@@ -366,13 +373,13 @@ extern "C" int qtx_sym_absmax_eig(const double* T, int64_t n, int first_step, in
          *state = beta + kLanczosMaxSteps;
   const int m = steps < n ? steps : (int)n;
   if (first_step == 0) {  // otherwise the recurrence continues from the state left in the workspace
-    QTX_LAUNCH(lanczos_init_kernel, 1, 1024, st, n, v, vprev, state);
+    QTX_LAUNCH(lanczos_init_kernel, 1, kLanczosThreads, st, n, v, vprev, state);
     QTX_LAUNCH_CHECK();
   }
   for (int j = first_step; j < m; ++j) {
     rc = qtx_matvec(QTX_F64, T, n, n, n, v, w, stream);
     if (rc) return rc;
-    QTX_LAUNCH(lanczos_step_kernel, 1, 1024, st, n, w, v, vprev, alpha, beta, j, state);
+    QTX_LAUNCH(lanczos_step_kernel, 1, kLanczosThreads, st, n, w, v, vprev, alpha, beta, j, state);
     QTX_LAUNCH_CHECK();
   }
   QTX_LAUNCH(tridiag_absmax_kernel, 1, 64, st, alpha, beta, m, lam_out);
@@ -430,7 +437,7 @@ extern "C" int qtx_pinv_rational_partial(const double* T, int64_t n, const doubl
     QTX_LAUNCH_CHECK();
     for (int it = 0; it <= refine_steps; ++it) {
       if (it > 0) {
-        QTX_LAUNCH(dd_residual_kernel, (unsigned)n, 256, st, T, n, b, lam, p, x, rhs);
+        QTX_LAUNCH(dd_residual_kernel, (unsigned)n, kRowThreads, st, T, n, b, lam, p, x, rhs);
         QTX_LAUNCH_CHECK();
       }
       s = cusolverDnZgetrs(h, CUBLAS_OP_N, (int)n, 1, M, (int)n, ipiv, rhs, (int)n, step_info);

@@ -65,7 +65,7 @@ void emu_dd_correct(int64_t n, const double* d_c128, double* x) {
 void emu_dd_residual(const double* T, int64_t n, const double* b, const double* lam, double rtol, double atol, double cs,
                      double sn, const double* x, double* r_c128) {
   ShiftParams p = {rtol, atol, cs, sn};
-  emu_launch((unsigned)n, 256, [&] { dd_residual_kernel(T, n, b, lam, p, x, (cuDoubleComplex*)r_c128); });
+  emu_launch((unsigned)n, 256, [&] { dd_residual_kernel(T, n, b, lam, p, x, (cuDoubleComplex*)r_c128); });  // library size
 }
 
 void emu_dd_zero(int64_t n2, double* ydd) {
