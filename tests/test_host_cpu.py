@@ -256,3 +256,43 @@ def test_rational_shift_masks_cover_every_shift_once():
         assert len(masks) == P and all(0 <= m < 8 for m in masks)
         assert sum(masks) == 7 and all((a & b) == 0 for i, a in enumerate(masks) for b in masks[i + 1:])
         assert max(bin(m).count("1") for m in masks) == -(-3 // min(P, 3))  # balanced: ceil(3 / min(P, 3)) shifts
+
+
+def test_apply_off_diag_scatter_logic_on_cpu(monkeypatch):
+    """Operator.apply_off_diag (the reference's dense layout, operator.py:96-119) scatters the compacted enumeration
+    of get_conn back to [ns, nterms]; here get_conn is replaced by a compaction of the ORACLE's dense tensors, so the
+    Python scatter is checked without a GPU (the GPU test of the same method is gated until its first run)."""
+    import types
+
+    import torch
+
+    from oracle import operator as oop, sampler as osmp, sites as osites
+    from quantax_b200 import operator as qop, sites
+
+    sites.Sites._SITES = None
+    sites.Square(4, Nparticles=(8, 8))
+    olat = osites.Square(4, Nparticles=(8, 8))
+    H = qop.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
+    aop = oop.to_array_op_list(oop.heisenberg_op_list(olat, J=[1, 0.5], n_neighbor=[1, 2], msr=True))
+    s = osmp.rand_states(12, 16, 8, seed=5)
+    ref = oop.apply_off_diag(s, aop)
+
+    def fake_get_conn(spins, nflips, conn_size=None, with_spins=True):
+        sc, Hc = ref[nflips]
+        keep = ~np.isnan(Hc) & (np.abs(Hc) > 1e-8)
+        seg, idx = np.nonzero(keep)
+        return (torch.from_numpy(seg.astype(np.int32)), torch.from_numpy(idx.astype(np.int32)),
+                torch.from_numpy(sc[seg, idx]), torch.from_numpy(Hc[seg, idx]), int(keep.sum()))
+
+    monkeypatch.setattr(qop, "_as_spins", lambda x: torch.as_tensor(np.asarray(x), dtype=torch.int8))
+    H._group_tables = {nf: types.SimpleNamespace(nterms=ref[nf][1].shape[1]) for nf in ref}
+    monkeypatch.setattr(H, "get_conn", fake_get_conn)
+    got = H.apply_off_diag(s)
+    assert sorted(got) == sorted(ref)
+    for nflips, (sc, Hc) in got.items():
+        sc, Hc = sc.numpy(), Hc.numpy()
+        rs, rH = ref[nflips]
+        ok = ~np.isnan(rH) & (np.abs(rH) > 1e-8)
+        assert np.array_equal(np.isnan(Hc), ~ok)
+        assert np.array_equal(Hc[ok], rH[ok]) and np.array_equal(sc[ok], rs[ok])
+        assert np.array_equal(sc[~ok], np.repeat(s[:, None, :], rH.shape[1], axis=1)[~ok])
