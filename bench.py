@@ -1,25 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the VMC hot path (BASELINE.json): VMC samples/s for sweep + Oloc, and MinSR step ms.
 
-Workload (N=1): BASELINE.json configs[1] -- 10x10 Heisenberg (Marshall sign), RBM_Dense alpha=4
-(M=400, Np=40400, float32 parameters, float64 Jacobian / Gram / eigh as the reference's default
-dtype), SpinExchange (= NeighborExchange), Ns=4096, MinSR.  A "step" is one VMC step:
-sweep (2N = 200 proposals per chain) -> Oloc -> Jacobian (centred, scaled) -> Gram -> eigh +
-pseudo-inverse -> A^T y -> parameter update, on synthetic random-init weights and thermalised
-random chains.
+Default workload = the per-GPU slice of BASELINE.json configs[4], the configuration the metric is quoted on
+(the north-star target): 16x16 J1-J2 (J2 = 0.5, Marshall sign), ResConv(8 blocks, C = 88, 3x3, sinh+1 final
+activation, 1 047 552 float32 parameters), SpinExchange, MinSR, Ns = 16384 over 8 GPUs = 2048 chains per GPU.
+At N = 1 the line is that single-GPU slice (2048 chains, 2048 MinSR rows); at N = 8 it IS configs[4] (16384 chains,
+16384 x 1 047 552 MinSR system sharded over the 8 GPUs).  A "step" is one VMC step: sweep (2N = 512 proposals per
+chain, a full forward of the network per moved proposal) -> Oloc (one forward per connected configuration) ->
+Jacobian (centred, scaled) -> Gram -> soft pseudo-inverse -> A^T y -> parameter update, on synthetic random-init
+weights and thermalised random chains.
 
   value     = chains processed by (sweep + Oloc) per second, inputs resident in HBM, max over ranks
-  e2e       = the same through the public API with HOST buffers: every step copies the chains and
-              the parameters host->device from pinned memory, runs sweep + Oloc, and copies the
-              new chains and the local energies device->host.
-  N > 1     = weak scaling of the partitioned part: every GPU owns 4096 chains (no data-path
-              collective in sweep + Oloc); the MinSR part of the step is the named config's
-              Ns=4096 system with its rows sharded over the N GPUs (4096/N rows each), which
-              exercises the all-to-all / all-reduce / all-gather of the distributed solve.
+  e2e       = the same through the public API with HOST buffers: every step copies the chains and the parameters
+              host->device from pinned memory, runs sweep + Oloc, and copies the new chains and the local
+              energies device->host
+  roofline  = the tensor-core forward tower (resconv_tc kernel), timed with CUDA events INSIDE the timed steps:
+              float32 flops of the reference forward x connected configurations of the Oloc phase / its duration
+  config_B  = BASELINE.json configs[1] (10x10 Heisenberg, RBM_Dense alpha=4, Ns=4096, MinSR) measured in the same
+              run: sweep+Oloc samples/s, the MinSR step with its phases and collectives (the 4096-row system is
+              sharded over the N GPUs: strong scaling of the part of the step that communicates)
 
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/, NumPy on the
-host cores; the reference itself needs jax, which is not installable here) on a bounded sample
-of the same workload.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, torch CPU convolutions on all
+host threads; the reference itself needs jax, which is not installable here) on a bounded sample of the same
+workload (a few whole chains: full 512-proposal sweep + Oloc).
 """
 import argparse
 import json
@@ -32,75 +35,145 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-L, ALPHA, NS = 10, 4, 4096
 METRIC = "vmc_samples_per_sec_sweep_oloc"
-WORKLOAD = "heisenberg10x10_msr_rbm_dense_alpha4_spinexchange_ns4096_minsr"
+# config E slice
+LE, NB, CH, NSG = 16, 8, 88, 2048
+WORKLOAD_E = "j1j2_16x16_resconv8x88_sinhp1_spinexchange_minsr__2048_chains_per_gpu_slice_of_ns16384_over_8_gpus"
+# config B
+LB, ALPHA, NSB = 10, 4, 4096
+WORKLOAD_B = "heisenberg10x10_msr_rbm_dense_alpha4_spinexchange_ns4096_minsr"
+
+
+def forward_flops_E():
+    """float32 flops of one reference forward (2 N (9 C + 15 * 9 C^2), conv_nets.py:78-92)."""
+    N = LE * LE
+    return 2.0 * N * (9 * CH + (2 * NB - 1) * 9 * CH * CH)
+
+
+def config_E(world):
+    N = LE * LE
+    return {"workload": WORKLOAD_E, "chains_per_gpu": NSG, "sweep_steps": 2 * N, "minsr_rows_global": NSG * world,
+            "nparams": 9 * CH + CH + (2 * NB - 1) * (9 * CH * CH) + (2 * NB - 2) * CH,
+            "l2": "per-step working set (2048 x 1.05 M float64 Jacobian = 17 GB, 283 MB operand rasters) exceeds the "
+                  "126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference algorithm)
+# CPU legs (oracle port of the reference algorithm)
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(ns_sweep=512, ns_minsr=1024, steps=1, warmup=0):
+def _cpu_threads():
+    import torch
+
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return n
+
+
+class _CpuE:
+    """Config E on the host cores: oracle sweep + Oloc with the torch-CPU forward (oracle/resconv_torch.py)."""
+
+    def __init__(self):
+        import numpy as np
+
+        from oracle import models as om, operator as oop, sampler as osmp, sites as osites
+        from oracle.resconv_torch import TorchResConv
+
+        self.cores = _cpu_threads()
+        N = LE * LE
+        lat = osites.Square(LE, Nparticles=(N // 2, N // 2))
+        self.H = oop.to_array_op_list(oop.heisenberg_op_list(lat, J=[1, 0.5], n_neighbor=[1, 2], msr=True))
+        self.net = TorchResConv(om.ResConv.random((LE, LE), NB, CH, 3, np.float32, seed=1, final="sinhp1"))
+        self.table = osites.site_neighbor_table(lat)
+        self.cm = osmp.FullForwardChainModel(self.net)
+        self.osmp, self.oop, self.N = osmp, oop, N
+
+    def forward_seconds(self, batch=64):
+        s = self.osmp.rand_states(batch, self.N, self.N // 2, seed=5)
+        self.net.forward(s)
+        t0 = time.perf_counter()
+        self.net.forward(s)
+        return (time.perf_counter() - t0) / batch
+
+    def chains(self, n):
+        return self.osmp.rand_states(n, self.N, self.N // 2, seed=2)
+
+    def step(self, spins, it):
+        """One sweep (2N proposals, every proposal evaluated like the reference's unchunked sweep) + Oloc."""
+        t0 = time.perf_counter()
+        out = self.osmp.sweep(self.cm, spins, 2 * self.N, "exchange", neighbors=self.table, seed=7, step0=it * 2 * self.N)
+        E = self.oop.oloc(self.H, self.net.forward, out["spins"], out["psi"])
+        return out["spins"], E, time.perf_counter() - t0
+
+
+def cpu_baseline_E(budget_s=20.0, steps=1, warmup=0, total_budget_s=None):
+    """sweep + Oloc of a few whole chains of config E on the host cores.  The sample (number of chains) is sized
+    from a calibration forward so that one step costs about ``budget_s`` seconds (or the whole warmup + steps run
+    about ``total_budget_s``)."""
+    import numpy as np
+
+    cpu = _CpuE()
+    fwd = cpu.forward_seconds()
+    per_chain = fwd * (2 * cpu.N + 2 * cpu.N) * 1.8  # 512 sweep forwards + ~512 connected configurations
+    if total_budget_s is not None:
+        budget_s = total_budget_s / max(1, steps + warmup)
+    ns = int(max(1, min(64, budget_s / per_chain)))
+    spins = cpu.chains(ns)
+    ts = []
+    for it in range(warmup + steps):
+        spins, E, dt = cpu.step(spins, it)
+        if it >= warmup:
+            ts.append(dt)
+    sw = float(np.mean(ts))
+    return {"value": ns / sw, "unit": "samples/s", "cores": cpu.cores, "kind": "port",
+            "sample": f"oracle port (restated reference, not quantax/jax itself; torch CPU convolutions on {cpu.cores} "
+                      f"threads): full 512-proposal sweep + Oloc of {ns} of {NSG} chains of the workload per step, "
+                      f"{steps} step(s) after {warmup} warm-up",
+            "sweep_oloc_s": sw, "chains": ns, "forward_ms_per_sample": fwd * 1e3}
+
+
+def cpu_baseline_B(ns_sweep=512, ns_minsr=1024):
+    """Config B on the host cores (NumPy oracle): sweep + Oloc on a chain sample, MinSR on a row sample."""
     import numpy as np
 
     from oracle import models as om, operator as oop, sampler as osmp, sites as osites, solver as osolver
 
-    try:
-        import torch
-
-        torch.set_num_threads(os.cpu_count() or 1)
-    except Exception:
-        pass
-    N, M = L * L, ALPHA * L * L
-    lat = osites.Square(L, Nparticles=(N // 2, N // 2))
+    cores = _cpu_threads()
+    N, M = LB * LB, ALPHA * LB * LB
+    lat = osites.Square(LB, Nparticles=(N // 2, N // 2))
     H = oop.to_array_op_list(oop.heisenberg_op_list(lat, msr=True))
     net = om.RBM.random(N, M, np.float32, seed=1, scale=0.3)
     table = osites.site_neighbor_table(lat)
     cm = osmp.RBMChainModel(net)
     spins = osmp.rand_states(ns_sweep, N, N // 2, seed=2)
-    t_sw, t_ms = [], []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        out = osmp.sweep(cm, spins, 2 * N, "exchange", neighbors=table, seed=7, step0=it * 2 * N)
-        spins = out["spins"]
-        E = oop.oloc(H, net.forward, spins, out["psi"])
-        t1 = time.perf_counter()
-        sm = osmp.rand_states(ns_minsr, N, N // 2, seed=3)
-        Em = oop.oloc(H, net.forward, sm)
-        t2 = time.perf_counter()
-        x, e, v = osolver.sr_step(net.jacobian(sm), Em, np.ones(ns_minsr))
-        t3 = time.perf_counter()
-        if it >= warmup:
-            t_sw.append(t1 - t0)
-            t_ms.append(t3 - t2)
-    sw = float(np.mean(t_sw))
-    return {
-        "value": ns_sweep / sw,
-        "unit": "samples/s",
-        "cores": os.cpu_count(),
-        "kind": "port",
-        "sample": f"NumPy oracle (restated reference, not quantax/jax itself): sweep+Oloc on {ns_sweep} of {NS} chains "
-                  f"(full 200-step sweep), MinSR (Jacobian+Gram+eigh+A^T y) on {ns_minsr} of {NS} rows x 40400 params",
-        "sweep_oloc_s": sw,
-        "minsr_step_ms_at_sample": float(np.mean(t_ms)) * 1e3,
-        "minsr_rows": ns_minsr,
-    }
+    t0 = time.perf_counter()
+    out = osmp.sweep(cm, spins, 2 * N, "exchange", neighbors=table, seed=7, step0=0)
+    oop.oloc(H, net.forward, out["spins"], out["psi"])
+    t1 = time.perf_counter()
+    sm = osmp.rand_states(ns_minsr, N, N // 2, seed=3)
+    Em = oop.oloc(H, net.forward, sm)
+    t2 = time.perf_counter()
+    osolver.sr_step(net.jacobian(sm), Em, np.ones(ns_minsr))
+    t3 = time.perf_counter()
+    return {"value": ns_sweep / (t1 - t0), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"NumPy oracle: sweep+Oloc on {ns_sweep} of {NSB} chains (full 200-step sweep), MinSR "
+                      f"(Jacobian+Gram+eigh+A^T y) on {ns_minsr} of {NSB} rows x 40400 params",
+            "minsr_step_ms_at_sample": (t3 - t2) * 1e3, "minsr_rows": ns_minsr}
 
 
 def run_reference(args):
+    """The reference arm: the CPU port of the reference path on the box's host cores, on this arm's config, metric
+    and unit; every step a bounded sample (whole chains) sized so that warmup + steps finish in a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    cb = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1))
+    cb = cpu_baseline_E(steps=args.steps, warmup=args.warmup, total_budget_s=float(os.environ.get("QTX_REF_BUDGET_S", "150")))
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["sweep_oloc_s"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 model / f64 psi, Jacobian, solve",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "chains_per_gpu": NS, "sweep_steps": 2 * L * L, "minsr_rows_global": NS,
-                   "nparams": ALPHA * L * L * L * L + ALPHA * L * L, "note": "CPU oracle port on a bounded sample"},
-        "minsr_step_ms": cb["minsr_step_ms_at_sample"], "cpu_baseline": cb,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sweep_oloc_s"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_E(args.gpus),
+        "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
@@ -121,7 +194,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -148,49 +221,267 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _load_json(path):
+    try:
+        with open(os.path.join(ROOT, path)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def measure_pipe_peaks(dev):
+    """Peaks of the pipes the fractions in this file are quoted against, measured here with library GEMMs (the
+    way MEASURED_PEAKS.json measures bf16): int8 (cuBLASLt s8 x s8 -> s32), fp16, FP32 FMA (cuBLAS SGEMM, TF32 off),
+    FP64 (cuBLAS DGEMM), best of 5 after warm-up, burst figures."""
+    import torch
+
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def best(fn, flop, reps=5):
+        fn(); fn()
+        b = None
+        for _ in range(reps):
+            e0, e1 = ev(), ev()
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            b = ms if b is None else min(b, ms)
+        return flop / (b * 1e-3) / 1e12
+
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        n = 8192
+        a8 = torch.randint(-64, 64, (n, n), dtype=torch.int8, device=dev)
+        b8 = torch.randint(-64, 64, (n, n), dtype=torch.int8, device=dev)
+        try:
+            out["int8_tops"] = best(lambda: torch._int_mm(a8, b8), 2.0 * n ** 3)
+        except Exception as e:  # noqa: BLE001
+            out["int8_tops"] = None
+            out["int8_error"] = str(e)[:120]
+        del a8, b8
+        ah = torch.randn((n, n), dtype=torch.float16, device=dev)
+        out["fp16_tflops"] = best(lambda: torch.matmul(ah, ah), 2.0 * n ** 3)
+        del ah
+        torch.backends.cuda.matmul.allow_tf32 = False
+        n = 8192
+        af = torch.randn((n, n), dtype=torch.float32, device=dev)
+        out["fp32_fma_tflops"] = best(lambda: torch.matmul(af, af), 2.0 * n ** 3, reps=3)
+        del af
+        n = 4096
+        ad = torch.randn((n, n), dtype=torch.float64, device=dev)
+        out["fp64_tflops"] = best(lambda: torch.matmul(ad, ad), 2.0 * n ** 3, reps=3)
+        del ad
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    out["how"] = "library GEMMs in this process (torch._int_mm / torch.matmul), best of 3-5, CUDA events"
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.dist, self.torch = dist, torch
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def allmax(self, x):
+        if self.world == 1 or x is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t)
+        return float(t.item())
+
+
+def _phase_avg(events, steps):
+    return {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in (events or {}).items()}
+
+
+def measure_E(ctx, args):
+    """The default line: the per-GPU slice of config E."""
     import quantax_b200 as qtx
-    from quantax_b200 import _lib
+    from quantax_b200 import _lib, optimizer as optmod
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    import warnings
-
-    warnings.simplefilter("ignore")
-
-    N, M = L * L, ALPHA * L * L
+    torch, world, rank, dev = ctx.torch, ctx.world, ctx.rank, ctx.dev
+    N = LE * LE
+    qtx.sites.Sites._SITES = None
     qtx.set_random_seed(42)
-    qtx.sites.Square(L, Nparticles=(N // 2, N // 2))
+    qtx.sites.Square(LE, Nparticles=(N // 2, N // 2))
+    H = qtx.operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
+    model = qtx.model.ResConv(NB, CH, 3, final_activation=qtx.nn.sinhp1_by_scale)
+    state = qtx.state.Variational(model)
+    sampler = qtx.sampler.SpinExchange(state, nsamples=NSG * world, thermal_steps=2 * N)
+    optimizer = qtx.optimizer.SR(state, H)
+    Np = model.nparams
+
+    def vmc_step(timed):
+        e = [ctx.ev() for _ in range(5)]
+        e[0].record()
+        samples = sampler.sweep()
+        e[4].record()  # sweep | Oloc boundary
+        Eloc = H.Oloc(state, samples)
+        e[1].record()
+        nconn = H.last_conn_count
+        e[2].record()
+        Ebar = optimizer.get_Ebar(samples, Eloc=Eloc)
+        Obar = optimizer.get_Obar(samples)
+        step = optimizer.solve(Obar, Ebar)
+        state.update(step * 1e-3)
+        e[3].record()
+        if timed is not None:
+            timed.append((e, nconn))
+
+    for _ in range(args.warmup):
+        vmc_step(None)
+    ctx.sync()
+    optimizer.timers = {}
+    optmod.PHASE_EVENTS = {}
+    clocks = ClockSampler(ctx.local_rank)
+    clocks.start()
+    _lib.lib().qtx_launch_count_reset()
+    timed = []
+    t0, t1 = ctx.ev(), ctx.ev()
+    t0.record()
+    for _ in range(args.steps):
+        vmc_step(timed)
+    t1.record()
+    ctx.sync()
+    launches = int(_lib.lib().qtx_launch_count())
+    clk = clocks.stop()
+    K = args.steps
+    sweep_oloc_ms = sum(e[0].elapsed_time(e[1]) for e, _ in timed)
+    sweep_ms = sum(e[0].elapsed_time(e[4]) for e, _ in timed) / K
+    oloc_ms = sum(e[4].elapsed_time(e[1]) for e, _ in timed) / K
+    minsr_ms = sum(e[2].elapsed_time(e[3]) for e, _ in timed)
+    total_ms = t0.elapsed_time(t1)
+    nconn = sum(n for _, n in timed) / K
+    phase = _phase_avg(optimizer.timers, K)
+    inner = _phase_avg(optmod.PHASE_EVENTS, K)
+    optimizer.timers, optmod.PHASE_EVENTS = None, None
+
+    # e2e: host buffers, copies inside the timed region
+    spins_host = torch.empty((NSG, N), dtype=torch.int8).pin_memory()
+    params_host = torch.empty(Np, dtype=model.params.dtype).pin_memory()
+    eloc_host = torch.empty(NSG, dtype=torch.float64).pin_memory()
+    spins_host.copy_(sampler._spins)
+    params_host.copy_(model.params)
+    torch.cuda.synchronize()
+    e2e_steps = max(2, min(args.steps, 5))
+    for it in range(1 + e2e_steps):
+        if it == 1:
+            ctx.sync()
+            te = time.perf_counter()
+        sampler._spins.copy_(spins_host, non_blocking=True)
+        model.params.copy_(params_host, non_blocking=True)
+        samples = sampler.sweep()
+        El = H.Oloc(state, samples)
+        spins_host.copy_(samples.spins, non_blocking=True)
+        eloc_host.copy_(El, non_blocking=True)
+        torch.cuda.synchronize()
+    if world > 1:
+        ctx.dist.barrier()
+    e2e_s = time.perf_counter() - te
+    h2d = NSG * N + Np * model.params.element_size()
+    d2h = NSG * N + NSG * 8
+
+    sweep_oloc_ms, minsr_ms, total_ms, e2e_s, oloc_ms_mx = (ctx.allmax(v) for v in
+                                                            (sweep_oloc_ms, minsr_ms, total_ms, e2e_s, oloc_ms))
+    nconn_all = ctx.allsum(nconn)
+    inner = {k: ctx.allmax(v) for k, v in sorted(inner.items())}
+    phase = {k: ctx.allmax(v) for k, v in sorted(phase.items())}
+    if rank != 0:
+        return None
+    peaks = _load_json("MEASURED_PEAKS.json")
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+    flops = forward_flops_E()
+    cp = (CH + 15) // 16 * 16
+    f16_flops = 3 * 2.0 * N * (2 * NB - 1) * 9 * cp * cp  # executed per forward: 3 binary16 products, padded channels
+    ach = flops * nconn / (oloc_ms * 1e-3) / 1e12  # this rank's Oloc phase
+    prof = _load_json("profiles/r2_ncu_resconv_tc_E.json")
+    line = {
+        "metric": METRIC, "value": NSG * world * K / (sweep_oloc_ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_E(world),
+        "dtype_note": "float32 model as the reference's default (binary16 x3 split products on tcgen05 with float32 "
+                      "accumulation, 3e-6 from the float64 model); float64 psi, Jacobian, Gram, pseudo-inverse",
+        "sweep_oloc_ms": sweep_oloc_ms / K, "minsr_step_ms": minsr_ms / K,
+        "value_path": {"sweep_ms": sweep_ms, "oloc_ms": oloc_ms, "connected_configs_per_step": nconn,
+                       "oloc_forwards_per_s": nconn / (oloc_ms * 1e-3)},
+        "minsr_phases_ms": {**phase, **{"in_step." + k: v for k, v in inner.items()}},
+        "pinv_method": optmod.PINV_METHOD,
+        "e2e": {"value": NSG * world * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clk,
+        "roofline": {
+            "kernel": "resconv_tc2_kernel (15 tensor-core convolutions per forward, one persistent launch per batch) "
+                      "+ first / final layer kernels, over the Oloc phase of the timed steps",
+            "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "traffic": prof.get("dram_bytes_per_launch"),
+            "traffic_note": prof.get("note", "no ncu --set full capture committed for this kernel yet"),
+            "note": "achieved = float32 flops of the reference forward (2 N (9 C + 15 * 9 C^2) = 0.536 GFLOP) x connected "
+                    "configurations evaluated in the Oloc phase / CUDA-event duration of that phase inside the timed "
+                    "steps (enumeration and reduction kernels included); peak = cuBLAS bf16 of MEASURED_PEAKS.json "
+                    "(sustained figure: the kernel runs inside a seconds-long step).  float32 accuracy costs 3 binary16 "
+                    "products on channels padded 88 -> 96, so this fraction is bounded by (88/96)^2 / 3 = 0.28",
+            "tensor_pipe": {"f16_tflops": f16_flops * nconn / (oloc_ms * 1e-3) / 1e12, "peak": peak_tf,
+                            "frac": f16_flops * nconn / (oloc_ms * 1e-3) / 1e12 / peak_tf,
+                            "note": "executed binary16 tensor work (3 products, 96 channels) vs the same peak"}},
+    }
+    return line
+
+
+def measure_B(ctx, args):
+    """Config B in the same run (extra keys): sweep + Oloc on 4096 chains per GPU, the MinSR step of the 4096-row
+    system sharded over the N GPUs (strong scaling of the communicating part), its phases and collectives."""
+    import quantax_b200 as qtx
+    from quantax_b200 import optimizer as optmod
+
+    torch, world, rank, dev = ctx.torch, ctx.world, ctx.rank, ctx.dev
+    N, M = LB * LB, ALPHA * LB * LB
+    qtx.sites.Sites._SITES = None
+    qtx.set_random_seed(42)
+    qtx.sites.Square(LB, Nparticles=(N // 2, N // 2))
     H = qtx.operator.Heisenberg(msr=True)
     model = qtx.model.RBM_Dense(features=M)
     state = qtx.state.Variational(model)
-    # weak scaling of the partitioned part: NS chains on every GPU
-    sampler = qtx.sampler.SpinExchange(state, nsamples=NS * world)
+    sampler = qtx.sampler.SpinExchange(state, nsamples=NSB * world)
     optimizer = qtx.optimizer.SR(state, H)
-    rows = NS // world  # MinSR rows of this rank (global NS rows as in the named config)
+    rows = NSB // world
     Np = model.nparams
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def vmc_step(timed):
         flush.fill_(1)
-        e = [ev() for _ in range(5)]
+        e = [ctx.ev() for _ in range(5)]
         e[0].record()
         samples = sampler.sweep()
-        e[4].record()  # sweep | Oloc boundary (informational split of the timed region e[0]..e[1])
+        e[4].record()
         Eloc_all = H.Oloc(state, samples)
         e[1].record()
         sub = qtx.sampler.Samples(samples.spins[:rows], samples.psi[:rows], None, samples.reweight_factor[:rows])
@@ -202,366 +493,82 @@ def run_b200(args):
         e[3].record()
         if timed is not None:
             timed.append(e)
-        return samples
 
-    for _ in range(args.warmup):
+    steps, warm = max(3, min(args.steps, 10)), max(3, min(args.warmup, 3))
+    for _ in range(warm):
         vmc_step(None)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    ctx.sync()
     optimizer.timers = {}
-    from quantax_b200 import optimizer as _optmod
-
-    _optmod.PHASE_EVENTS = {}  # CUDA-event pairs around qtx_gram / eigh inside the timed steps
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    _lib.lib().qtx_launch_count_reset()
+    optmod.PHASE_EVENTS = {}
     timed = []
-    torch.cuda.synchronize()
-    t_all0 = ev(); t_all1 = ev()
-    t_all0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         vmc_step(timed)
-    t_all1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches = int(_lib.lib().qtx_launch_count())
-    clk = clocks.stop()
-    sweep_oloc_ms = sum(e[0].elapsed_time(e[1]) for e in timed)
-    minsr_ms = sum(e[2].elapsed_time(e[3]) for e in timed)
-    sweep_only_ms = max(sum(e[0].elapsed_time(e[4]) for e in timed) / max(len(timed), 1), 1e-9)
-    total_ms = t_all0.elapsed_time(t_all1)
-    phase = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in optimizer.timers.items()}
-    optimizer.timers = None
-    in_step, _optmod.PHASE_EVENTS = _optmod.PHASE_EVENTS, None
-    try:  # average launch duration inside the timed region
-        gram_in_step_ms = sum(a.elapsed_time(b) for a, b in in_step["gram"]) / len(in_step["gram"])
-        eigh_in_step_ms = sum(a.elapsed_time(b) for a, b in in_step["eigh_pinv"]) / len(in_step["eigh_pinv"])
-    except Exception:
-        gram_in_step_ms = eigh_in_step_ms = None
-
-    # kernel-level timing of the dominant own kernel (Gram) and of eigh, on the launching stream
-    from quantax_b200.optimizer import gram, pinv_eig_solve, matvec_t, DEFAULT_NSLICES
-
-    A = torch.randn((NS if world == 1 else NS, Np // world if world > 1 else Np), dtype=torch.float64, device=dev) / 64
-    for _ in range(2):
-        T = gram(A)
-    g0, g1 = ev(), ev()
-    reps = 3
-    flush.fill_(2)
-    g0.record()
-    for _ in range(reps):
-        T = gram(A)
-    g1.record()
-    torch.cuda.synchronize()
-    gram_ms = g0.elapsed_time(g1) / reps
-    b = torch.randn(NS, dtype=torch.float64, device=dev)
-    h0, h1 = ev(), ev()
-    h0.record()
-    y, info = pinv_eig_solve(T.clone(), b, None, 0.0)
-    h1.record()
-    torch.cuda.synchronize()
-    eigh_ms = h0.elapsed_time(h1)
-    del A, T
-
-    # e2e: host buffers, copies inside the timed region
-    spins_host = torch.empty((NS, N), dtype=torch.int8).pin_memory()
-    params_host = torch.empty(Np, dtype=torch.float32).pin_memory()
-    eloc_host = torch.empty(NS, dtype=torch.float64).pin_memory()
-    spins_host.copy_(sampler._spins)
-    params_host.copy_(model.params)
-    torch.cuda.synchronize()
-    e2e_steps = max(3, args.steps)
-    for it in range(2 + e2e_steps):
-        if it == 2:
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-        sampler._spins.copy_(spins_host, non_blocking=True)
-        model.params.copy_(params_host, non_blocking=True)
-        samples = sampler.sweep()
-        El = H.Oloc(state, samples)
-        spins_host.copy_(samples.spins, non_blocking=True)
-        eloc_host.copy_(El, non_blocking=True)
-        torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    h2d = NS * N + Np * 4
-    d2h = NS * N + NS * 8
-
-    # informational, last GPU work of the run and guarded: the diagonal-shift solver family (auto_shift_eig,
-    # solver.py:50-90) replaces eigh by a Cholesky factorisation of the same Gram matrix
-    chol_ms = None
-    if world == 1:
-        try:
-            from quantax_b200.optimizer import shift_chol_solve
-
-            Tc = gram(torch.randn((NS, 4096), dtype=torch.float64, device=dev) / 64)
-            shift_chol_solve(Tc.clone(), b, None, 1e-4)
-            c0, c1 = ev(), ev()
-            Tc2 = Tc.clone()
-            c0.record()
-            shift_chol_solve(Tc2, b, None, 1e-4)
-            c1.record()
-            torch.cuda.synchronize()
-            chol_ms = c0.elapsed_time(c1)
-        except Exception:
-            chol_ms = None
-
-    def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sweep_oloc_ms, minsr_ms, total_ms, e2e_s, gram_ms, eigh_ms = (allmax(v) for v in (sweep_oloc_ms, minsr_ms, total_ms,
-                                                                                      e2e_s, gram_ms, eigh_ms))
-    if gram_in_step_ms is not None:
-        gram_in_step_ms, eigh_in_step_ms = allmax(gram_in_step_ms), allmax(eigh_in_step_ms)
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak_tf = peaks.get("bf16_tflops", 1590.0)
-        ns_g, np_g = NS, (Np // world if world > 1 else Np)
-        # Algorithmic work of the reference's Gram (solver.py:139 computes the FULL product in float64):
-        # 2 Ns^2 Np flop per launch.  The kernel gets float64 accuracy from s(s+1)/2 exact int8 products on the
-        # lower-triangular tiles, so its tensor-pipe work is pairs * Ns(Ns+1) * Np int8 op.
-        from quantax_b200.optimizer import DEFAULT_NSLICES as _S
-
-        s_eff = 7 if _S == 0 else _S
-        pairs = s_eff * (s_eff + 1) // 2 if s_eff > 0 else 0
-        gram_flops = 2.0 * ns_g * ns_g * np_g
-        # the roofline uses the launch duration measured INSIDE the timed steps (after the L2 flush of every step);
-        # the back-to-back figure measured after the loop is reported beside it
-        gram_roof_ms = gram_in_step_ms if gram_in_step_ms else gram_ms
-        ach = gram_flops / (gram_roof_ms * 1e-3) / 1e12
-        int8_ops = pairs * float(ns_g) * (ns_g + 1) * np_g
-        int8_ach = int8_ops / (gram_roof_ms * 1e-3) / 1e12
-        value = NS * world * args.steps / (sweep_oloc_ms * 1e-3)
-        line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 model / f64 psi, Jacobian, Gram, eigh", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "chains_per_gpu": NS, "sweep_steps": 2 * N, "minsr_rows_global": NS,
-                       "nparams": Np, "l2": "256 MiB buffer written before every step (L2 flush)",
-                       "gram_nslices": s_eff},
-            "sweep_oloc_ms": sweep_oloc_ms / args.steps, "minsr_step_ms": minsr_ms / args.steps,
-            # split of the timed region of `value` (this rank): SURVEY 8(d) asks for the sweep's HBM-equivalent rate --
-            # the bytes a per-proposal unfused evaluation would move (2 W columns + theta read/write + the spin pair,
-            # 4M*2 + 8M + 2 B) -- next to the fact that the fused kernel keeps theta in registers and W^T in shared
-            # memory, so it is issue / MUFU bound (ncu: 0.6 MB of DRAM traffic per sweep), not HBM bound
-            "value_path": {"sweep_ms": sweep_only_ms, "oloc_ms": sweep_oloc_ms / args.steps - sweep_only_ms,
-                           "proposals_per_s": NS * 2 * N / (sweep_only_ms * 1e-3),
-                           "unfused_hbm_equivalent_GBps": NS * 2 * N * (4 * M * 2 + 8 * M + 2) / (sweep_only_ms * 1e-3) / 1e9},
-            "pinv_method": _optmod.PINV_METHOD,  # "eigh" (cuSOLVER syevd) or "rational" (QTX_PINV)
-            "minsr_phases_ms": {**phase, "gram_in_step(split+mma)": gram_in_step_ms,
-                                "eigh_pinv_in_step(cuSOLVER)": eigh_in_step_ms,
-                                "gram_alone(split+mma)": gram_ms, "eigh_pinv_alone(cuSOLVER)": eigh_ms,
-                                "shift_cholesky_alone(cuSOLVER potrf+potrs, auto_shift_eig)": chol_ms},
-            "e2e": {"value": NS * world * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clk,
-            "roofline": {"kernel": "qtx_gram: gram_split_kernel + gram_tc2_kernel (T = Obar Obar^T)", "bound": "tensor",
-                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of gram_tc2_kernel, one ncu --set full capture
-                         # (profiles/r1_ncu_gram_tc2_summary.csv); algorithmic operand bytes are s * Ns * Np = 1.32e9
-                         "traffic": 8.744e9 if world == 1 else None,
-                         "note": ("achieved = float64-equivalent flops of the reference's full product 2 Ns^2 Np per launch / "
-                                  "average CUDA-event time of qtx_gram (split + MMA kernels) inside the timed steps; peak = cuBLAS bf16 of MEASURED_PEAKS.json (burst). "
-                                  "float64 accuracy costs s(s+1)/2 = %d exact int8 products, so this fraction is bounded by "
-                                  "4/%d = %.3f even at 100%% int8 tensor-pipe utilisation (lower-triangular tiles only, int8 rate = 2x bf16)."
-                                  % (pairs, pairs, 4.0 / max(pairs, 1))
-                                  if peaks else "fallback peak"),
-                         "tensor_pipe": {"int8_top_s": int8_ach, "int8_peak_top_s": 2 * peak_tf,
-                                         "frac": int8_ach / (2 * peak_tf),
-                                         "note": "executed int8 tensor ops (pairs * Ns(Ns+1) * Np) / time vs 2 x measured bf16 "
-                                                 "peak; ncu: sm__ops_path_tensor_op_utcimma 72% of peak, profiles/"}},
-        }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline()
-        if world == 1 and not args.no_probe:
-            t_probe = time.perf_counter()
-            line["experimental"] = unverified_probe()
-            line["experimental"]["wall_s_outside_the_measurement"] = round(time.perf_counter() - t_probe, 1)
-    if world > 1 and not args.no_probe:
-        t_probe = time.perf_counter()
-        exp = multi_gpu_probe(rank, local_rank, world)  # every rank starts its own subprocess
-        if rank == 0:
-            line["experimental"] = exp
-            line["experimental"]["wall_s_outside_the_measurement"] = round(time.perf_counter() - t_probe, 1)
-    if rank == 0:
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.sync()
+    sweep_oloc_ms = sum(e[0].elapsed_time(e[1]) for e in timed) / steps
+    sweep_ms = sum(e[0].elapsed_time(e[4]) for e in timed) / steps
+    minsr_ms = sum(e[2].elapsed_time(e[3]) for e in timed) / steps
+    phase = _phase_avg(optimizer.timers, steps)
+    inner = _phase_avg(optmod.PHASE_EVENTS, steps)
+    optimizer.timers, optmod.PHASE_EVENTS = None, None
+    sweep_oloc_ms, sweep_ms, minsr_ms = (ctx.allmax(v) for v in (sweep_oloc_ms, sweep_ms, minsr_ms))
+    inner = {k: ctx.allmax(v) for k, v in sorted(inner.items())}
+    phase = {k: ctx.allmax(v) for k, v in sorted(phase.items())}
+    del flush
+    if rank != 0:
+        return None
+    peaks = _load_json("MEASURED_PEAKS.json")
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    s_eff = optmod.gram_nslices_for(torch.float64)
+    pairs = s_eff * (s_eff + 1) // 2
+    np_g = Np // world if world > 1 else Np
+    gram_ms = inner.get("gram")
+    out = {
+        "workload": WORKLOAD_B, "chains_per_gpu": NSB, "minsr_rows_global": NSB, "nparams": Np, "steps": steps,
+        "l2": "256 MiB buffer written before every step (L2 flush)",
+        "value": NSB * world / (sweep_oloc_ms * 1e-3), "unit": "samples/s",
+        "sweep_oloc_ms": sweep_oloc_ms, "sweep_ms": sweep_ms, "oloc_ms": sweep_oloc_ms - sweep_ms,
+        "minsr_step_ms": minsr_ms, "pinv_method": optmod.PINV_METHOD,
+        "minsr_phases_ms": {**phase, **{"in_step." + k: v for k, v in inner.items()}},
+        "proposals_per_s": NSB * 2 * N / (sweep_ms * 1e-3),
+    }
+    if gram_ms:
+        ach = 2.0 * NSB * NSB * np_g / (gram_ms * 1e-3) / 1e12
+        int8_ach = pairs * float(NSB) * (NSB + 1) * np_g / (gram_ms * 1e-3) / 1e12
+        out["gram_roofline"] = {
+            "kernel": "qtx_gram: digit split + gram_tc2_kernel (T = Obar Obar^T), in-step CUDA events",
+            "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s (float64-equivalent 2 Ns^2 Np)",
+            "frac": ach / peak_tf, "nslices": s_eff, "int8_tops_executed": int8_ach,
+            "note": "float64 accuracy costs s(s+1)/2 = %d exact int8 products on the lower-triangular tiles" % pairs}
+    return out
 
 
-def multi_gpu_probe(rank, local_rank, world, timeout_s=180):
-    """tools/multi_gpu_probe.py as one subprocess per rank with its own rendezvous port, after every measurement of
-    this process: fused Gram + exchange and the rank-split pseudo-inverse at this world size.  Informational."""
-    try:
-        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(local_rank), WORLD_SIZE=str(world),
-                   MASTER_ADDR=os.environ.get("MASTER_ADDR", "127.0.0.1"),
-                   MASTER_PORT=str((int(os.environ.get("MASTER_PORT", "29500")) + 17 - 1024) % 64000 + 1024),
-                   QTX_P2P_TIMEOUT_S="20")
-        for k in ("TORCHELASTIC_RUN_ID", "TORCHELASTIC_USE_AGENT_STORE", "GROUP_RANK", "ROLE_RANK"):
-            env.pop(k, None)
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "multi_gpu_probe.py")], cwd=ROOT, env=env,
-                           capture_output=True, text=True, timeout=timeout_s)
-        last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
-        if rank != 0:
-            return None
-        return json.loads(last[-1]) if last else {"error": (r.stderr or r.stdout)[-300:]}
-    except Exception as e:  # noqa: BLE001
-        return {"error": f"{type(e).__name__}: {e}"[:300]}
-
-
-def unverified_probe(timeout_s=300):
-    """First GPU run of code written after the round's GPU budget ended (tools/unverified_probe.py), in a
-    subprocess with a time-out and AFTER every measurement: informational, never part of the metric, and a failure
-    there cannot touch this process."""
-    try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "unverified_probe.py")], cwd=ROOT,
-                           capture_output=True, text=True, timeout=timeout_s)
-        last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
-        return json.loads(last[-1]) if last else {"error": (r.stderr or r.stdout)[-300:]}
-    except Exception as e:  # noqa: BLE001
-        return {"error": f"{type(e).__name__}: {e}"[:300]}
-
-
-# ------------------------------------------------------------------------------------------------
-# config E (BASELINE.json configs[4], the north-star target): 16x16 J1-J2 ResConv(8 blocks, C=88, 3x3,
-# sinhp1 final activation, ~1.05 M parameters), SpinExchange, Ns = 16384 sharded over 8 GPUs = 2048 chains
-# per GPU.  `--workload E` runs this per-GPU slice on every rank: sweep (2N = 512 full forwards per chain)
-# + Oloc, then the MinSR step with 2048 * world rows.  Not the driver's default line (that is config B).
-# ------------------------------------------------------------------------------------------------
-def run_b200_resconv(args):
-    import torch
-    import torch.distributed as dist
-
-    import quantax_b200 as qtx
-    from quantax_b200 import _lib
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+def run_b200(args):
+    ctx = Ctx()
     import warnings
 
     warnings.simplefilter("ignore")
-    LE, NB, CH, NSG = 16, 8, 88, 2048
-    N = LE * LE
-    qtx.set_random_seed(42)
-    qtx.sites.Square(LE, Nparticles=(N // 2, N // 2))
-    H = qtx.operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
-    model = qtx.model.ResConv(NB, CH, 3, final_activation=qtx.nn.sinhp1_by_scale)
-    state = qtx.state.Variational(model)
-    sampler = qtx.sampler.SpinExchange(state, nsamples=NSG * world, thermal_steps=2 * N)
-    optimizer = qtx.optimizer.SR(state, H)
-    Np = model.nparams
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def vmc_step(timed):
-        e = [ev() for _ in range(4)]
-        e[0].record()
-        samples = sampler.sweep()
-        Eloc = H.Oloc(state, samples)
-        e[1].record()
-        e[2].record()
-        Ebar = optimizer.get_Ebar(samples, Eloc=Eloc)
-        Obar = optimizer.get_Obar(samples)
-        step = optimizer.solve(Obar, Ebar)
-        state.update(step * 1e-3)
-        e[3].record()
-        if timed is not None:
-            timed.append(e)
-
-    for _ in range(args.warmup):
-        vmc_step(None)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    optimizer.timers = {}
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    _lib.lib().qtx_launch_count_reset()
-    timed = []
-    t0, t1 = ev(), ev()
-    t0.record()
-    for _ in range(args.steps):
-        vmc_step(timed)
-    t1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches = int(_lib.lib().qtx_launch_count())
-    clk = clocks.stop()
-    sweep_oloc_ms = sum(e[0].elapsed_time(e[1]) for e in timed)
-    minsr_ms = sum(e[2].elapsed_time(e[3]) for e in timed)
-    total_ms = t0.elapsed_time(t1)
-    phase = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in optimizer.timers.items()}
-    # the dominant kernel: one batched forward of the chains (tensor-core tower + first/final layers)
-    s = sampler._spins
-    for _ in range(2):
-        state(s)
-    f0, f1 = ev(), ev()
-    reps = 10
-    f0.record()
-    for _ in range(reps):
-        state(s)
-    f1.record()
-    torch.cuda.synchronize()
-    fwd_ms = f0.elapsed_time(f1) / reps
-
-    def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sweep_oloc_ms, minsr_ms, total_ms, fwd_ms = (allmax(v) for v in (sweep_oloc_ms, minsr_ms, total_ms, fwd_ms))
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak_tf = peaks.get("bf16_tflops", 1590.0)
-        flops = 2.0 * NSG * N * (9 * CH + (2 * NB - 1) * 9 * CH * CH)          # float32 flops of the reference forward
-        cp = (CH + 15) // 16 * 16
-        f16_flops = 3 * 2.0 * NSG * N * (2 * NB - 1) * 9 * cp * cp             # executed: 3 binary16 products, padded
-        ach = flops / (fwd_ms * 1e-3) / 1e12
-        line = {
-            "metric": METRIC, "value": NSG * world * args.steps / (sweep_oloc_ms * 1e-3), "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 model (binary16 x3 split on tcgen05, f32 accumulate) / f64 psi, Jacobian, Gram, eigh",
-            "data": "synthetic",
-            "config": {"workload": "j1j2_16x16_resconv8x88_sinhp1_spinexchange_2048_chains_per_gpu_minsr",
-                       "chains_per_gpu": NSG, "sweep_steps": 2 * N, "minsr_rows_global": NSG * world, "nparams": Np,
-                       "l2": "inputs (2048 x 1.05 M Jacobian, 283 MB operand rasters) exceed L2"},
-            "sweep_oloc_ms": sweep_oloc_ms / args.steps, "minsr_step_ms": minsr_ms / args.steps,
-            "minsr_phases_ms": phase, "forward_2048_ms": fwd_ms, "gpu_launches": launches, "clocks": clk,
-            "roofline": {"kernel": "resconv_tc_kernel (15 tensor-core convolutions, one persistent launch) + first/final layer",
-                         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         "traffic": None,
-                         "note": "achieved = float32 flops of the reference forward (2 N (9 C + 15 * 9 C^2) per sample) x 2048 "
-                                 "samples / CUDA-event time of one batched forward; float32 accuracy costs 3 binary16 products "
-                                 "on channels padded 88 -> 96, so the fraction is bounded by (88/96)^2 / 3 = 0.28",
-                         "tensor_pipe": {"f16_tflops": f16_flops / (fwd_ms * 1e-3) / 1e12, "peak": peak_tf,
-                                         "frac": f16_flops / (fwd_ms * 1e-3) / 1e12 / peak_tf}},
-        }
+    line = measure_E(ctx, args) if args.workload in ("E", "all") else None
+    extra = measure_B(ctx, args) if args.workload in ("B", "all") else None
+    if ctx.rank == 0:
+        if line is None:  # --workload B: config B as the line (development)
+            line = {"metric": METRIC, "value": extra["value"], "unit": "samples/s", "n_gpus": ctx.world,
+                    "steps": extra["steps"], "warmup": 3, "ms_per_step": extra["sweep_oloc_ms"] + extra["minsr_step_ms"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": WORKLOAD_B}}
+        if extra is not None:
+            line["config_B"] = extra
+        if ctx.world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_E() if args.workload != "B" else cpu_baseline_B()
+            if args.workload == "all":
+                line["config_B"]["cpu_baseline"] = cpu_baseline_B()
+        if ctx.world == 1 and not args.no_peaks:
+            try:
+                line["pipe_peaks_measured_here"] = measure_pipe_peaks(ctx.dev)
+            except Exception as e:  # noqa: BLE001
+                line["pipe_peaks_measured_here"] = {"error": str(e)[:200]}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -570,18 +577,17 @@ def main():
         os.environ.pop("NCCL_DEBUG")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-probe", action="store_true", help="skip the first-run probe of unverified code (tools/unverified_probe.py)")
-    ap.add_argument("--workload", default="B", choices=["B", "E"],
-                    help="B = BASELINE.json configs[1] (the driver's line); E = per-GPU slice of configs[4] (ResConv)")
+    ap.add_argument("--no-peaks", action="store_true", help="skip the library-GEMM pipe peak measurements")
+    ap.add_argument("--workload", default="all", choices=["all", "E", "B"],
+                    help="all = config-E slice as the line + config B as extra keys (the driver's line); "
+                         "E / B = only that part (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "E":
-        run_b200_resconv(args)
     else:
         run_b200(args)
 

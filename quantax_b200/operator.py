@@ -70,6 +70,7 @@ class Operator:
         self._table = None
         self._group_tables = None
         self._connectivity = None
+        self.last_conn_count = 0
 
     @property
     def op_list(self) -> list:
@@ -289,10 +290,12 @@ class Operator:
             diag = out
             out = torch.empty(diag.shape[0], dtype=torch.complex128, device=diag.device)
             _lib.call("qtx_real_to_cplx", _lib.ptr(diag), diag.shape[0], _lib.ptr(out), _lib.stream())
+        self.last_conn_count = 0  # connected configurations forwarded by this call (bench.py)
         for nflips in self.group_tables:
             segment, _, s_conn, H, _ = self.get_conn(s, nflips)
             if segment.numel() == 0:
                 continue
+            self.last_conn_count += segment.numel()
             psi_conn = state.ref_forward(s_conn, s, nflips, segment, None)
             _lib.call("qtx_oloc_reduce_cplx" if cplx else "qtx_oloc_reduce", _lib.ptr(segment), _lib.ptr(H), _lib.ptr(psi_conn.mult.contiguous()),
                       _lib.ptr(psi_conn.expo.contiguous()), segment.numel(), _lib.ptr(psi.mult.contiguous()),

@@ -49,6 +49,13 @@ _WS = _Workspaces()
 DEFAULT_NSLICES = int(os.environ.get("QTX_GRAM_NSLICES", "0"))
 
 
+def gram_nslices_for(dtype) -> int:
+    """Digit count qtx_gram uses for an input of ``dtype`` (csrc/gram_tc.cu default_slices unless overridden)."""
+    if DEFAULT_NSLICES > 0:
+        return DEFAULT_NSLICES
+    return 7 if dtype == torch.float64 else 4
+
+
 # Per-kernel timing inside a running step (bench.py): when PHASE_EVENTS is a dict, the dense building blocks record
 # a CUDA-event pair around their launches on the current stream; nothing is recorded (and nothing costs) otherwise.
 PHASE_EVENTS = None
@@ -299,7 +306,9 @@ class _CudaOps:
 
             return peer_gram(A.shape[0]).gram_allreduce(A, self.nslices)
         T = gram(A, nslices=self.nslices)
+        t = _phase_tic("comm.all_reduce_T")
         _dist().all_reduce(T)
+        _phase_toc(t)
         return T
 
     @staticmethod
@@ -328,19 +337,29 @@ def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops, tsolv
         flat[:, :npar] = A
         send = flat.view(nl, P, npc).permute(1, 0, 2).contiguous()
     recv = torch.empty_like(send)
+    t = _phase_tic("comm.all_to_all_Obar")
     dist.all_to_all_single(recv, send)
+    _phase_toc(t)
     Ac = recv.view(P * nl, npc)  # all Ns rows (rank-major = global sample order), this rank's columns
     if hasattr(ops, "gram_allreduce"):
         T = ops.gram_allreduce(Ac)
     else:
         T = ops.gram(Ac)
+        t = _phase_tic("comm.all_reduce_T")
         dist.all_reduce(T)
+        _phase_toc(t)
     bfull = torch.empty(P * nl, dtype=b.dtype, device=b.device)
+    t = _phase_tic("comm.all_gather_b")
     dist.all_gather_into_tensor(bfull, b.contiguous())
+    _phase_toc(t)
     y, info = ops.pinv_eig_solve(T, bfull, rtol, atol) if tsolve is None else tsolve(T, bfull)
+    t = _phase_tic("matvec_t")
     xc = ops.matvec_t(Ac, y)
+    _phase_toc(t)
     x = torch.empty(P * npc, dtype=xc.dtype, device=xc.device)
+    t = _phase_tic("comm.all_gather_x")
     dist.all_gather_into_tensor(x, xc.contiguous())
+    _phase_toc(t)
     return x[:npar].contiguous(), info
 
 
