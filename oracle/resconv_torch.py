@@ -14,12 +14,14 @@ import torch.nn.functional as F
 
 class TorchResConv:
     def __init__(self, net, threads=None):
-        """``net``: an ``oracle.models.ResConv`` with real output and float32 parameters."""
-        if net.out_complex or net.dtype != np.float32:
-            raise ValueError("TorchResConv covers real-output float32 networks (configs C and E)")
+        """``net``: an ``oracle.models.ResConv`` with real output (float32 or float64 parameters)."""
+        if net.out_complex:
+            raise ValueError("TorchResConv covers real-output networks (configs C and E)")
         if threads:
             torch.set_num_threads(int(threads))
         self.net = net
+        self.tdt = torch.float32 if net.dtype == np.float32 else torch.float64
+        self.npdt = np.dtype(net.dtype).type
         self.shape, self.N, self.C, self.nblocks, self.final = net.shape, net.N, net.C, net.nblocks, net.final
         t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a))
         self.blocks = [{k: t(v) for k, v in blk.items()} for blk in net.blocks]
@@ -31,25 +33,25 @@ class TorchResConv:
 
     def forward(self, s):
         with torch.no_grad():
-            x = torch.from_numpy(np.ascontiguousarray(s)).to(torch.float32).reshape(-1, 1, *self.shape)
+            x = torch.from_numpy(np.ascontiguousarray(s)).to(self.tdt).reshape(-1, 1, *self.shape)
             for i, blk in enumerate(self.blocks):
                 res = x
-                x = x / np.float32(np.sqrt(i + 1))
-                a1 = x / np.float32(np.sqrt(2)) if i == 0 else F.gelu(x, approximate="tanh")
+                x = x / self.npdt(np.sqrt(i + 1))
+                a1 = x / self.npdt(np.sqrt(2)) if i == 0 else F.gelu(x, approximate="tanh")
                 h = self._conv(a1, blk["w1"], blk["b1"])
                 y = self._conv(F.gelu(h, approximate="tanh"), blk["w2"], blk["b2"])
                 if y.shape[1] > res.shape[1]:
                     res = res.repeat_interleave(y.shape[1] // res.shape[1], dim=1)
                 x = y + res
-            z = (x / np.float32(np.sqrt(self.nblocks + 1))).reshape(x.shape[0], -1)
+            z = (x / self.npdt(np.sqrt(self.nblocks + 1))).reshape(x.shape[0], -1)
             m = z.abs().amax(dim=1)
             if self.final == "exp":
                 sig = torch.exp(z - m[:, None])
             else:
                 sig = (torch.exp(z - m[:, None]) - torch.exp(-z - m[:, None])) / 2 + torch.exp(-m)[:, None]
             a = sig.reshape(-1, self.C, self.N).mean(dim=1)
-            char = np.float32(1.0 / self.N)
+            char = self.npdt(1.0 / self.N)
             e_char = np.log(char)
-            significand = (a * (char * np.exp(np.float32(0) - e_char))).sum(dim=1)
+            significand = (a * (char * np.exp(self.npdt(0) - e_char))).sum(dim=1)
             exponent = m + e_char
         return significand.double().numpy(), exponent.double().numpy()

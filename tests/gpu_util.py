@@ -24,6 +24,24 @@ def lattice_pair(qtx, kind, L, nparticles=None):
     raise ValueError(kind)
 
 
+def check(label, err, tol):
+    """Assert ``err <= tol`` and append the measured pair to gpurun_out/parity_report.jsonl (the evidence file of
+    the parity bar: float64 1e-10, float32 1e-5 -- BASELINE.json north_star)."""
+    import json
+    import os
+
+    err, tol = float(err), float(tol)
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "what": label,
+                                "err": err, "tol": tol, "ok": bool(err <= tol)}) + "\n")
+    except OSError:
+        pass
+    assert err <= tol, f"{label}: {err:.3e} > {tol:.1e}"
+
+
 def to_np(t):
     return t.detach().cpu().numpy()
 

@@ -1,0 +1,206 @@
+"""Oracle-vs-CUDA parity AT the BASELINE.json shapes (configs B, C, D, E) on sample subsets the NumPy oracle finishes
+in seconds: the kernels run the same instantiations (lattice size, channel count, tile layout, symmetry group) as the
+benchmark, only the number of chains / samples is reduced.  float32 models: 1e-5, float64: 1e-10, chains bit-exact
+(float32 models: except at provable near-ties of the accept test)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as omodels, operator as oop, sampler as osmp, sites as osites, solver as osolver
+from oracle import symmetry as osym
+from tests.gpu_util import check, lattice_pair, make_rbm, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qtx():
+    import quantax_b200 as q
+
+    torch.cuda.set_device(0)
+    return q
+
+
+def _logpsi(mult, expo):
+    return np.log(np.abs(mult)) + expo
+
+
+def _resconv_pair(qtx, shape, nb, C, dtype, final, seed, **kw):
+    npdt = np.float32 if dtype == torch.float32 else np.float64
+    net = omodels.ResConv.random(shape, nb, C, 3, npdt, seed=seed, final=final, **kw)
+    fa = qtx.nn.exp_by_scale if final == "exp" else qtx.nn.sinhp1_by_scale
+    model = qtx.model.ResConv(nb, C, 3, final_activation=fa, dtype=dtype, params=torch.from_numpy(net.params().copy()))
+    return model, net
+
+
+def _fast(net):
+    """The oracle forward through torch's CPU convolution (oracle/resconv_torch.py, held to the NumPy oracle by
+    tests/test_oracle_cpu.py): the einsum oracle needs 65 ms per 16x16 C=88 forward, Oloc needs thousands."""
+    from oracle.resconv_torch import TorchResConv
+
+    return TorchResConv(net).forward
+
+
+def _f64_twin(net):
+    """The same network evaluated in float64 (the float32 weights, exactly): the truth both float32 evaluations --
+    the oracle's and the kernels' -- approximate."""
+    blocks = [{k: (None if v is None else v.astype(np.float64)) for k, v in blk.items()} for blk in net.blocks]
+    return omodels.ResConv(blocks, net.shape, net.final)
+
+
+def test_config_e_forward_and_jacobian_vs_oracle(qtx):
+    """BASELINE configs[4]: 16x16, ResConv(8, C=88, 3x3), sinh+1, float32 -- the benchmark's network on 16 samples."""
+    lattice_pair(qtx, "square", 16, (128, 128))
+    model, net = _resconv_pair(qtx, (16, 16), 8, 88, torch.float32, "sinhp1", seed=11)
+    assert model.nparams == 1047552
+    state = qtx.state.Variational(model)
+    s = osmp.rand_states(16, 256, 128, seed=12)
+    st = torch.from_numpy(s).cuda()
+    psi = state(st)
+    sig, ex = net.forward(s)
+    sig64, ex64 = _f64_twin(net).forward(s)
+    lg, lo, l64 = _logpsi(to_np(psi.significand), to_np(psi.exponent)), _logpsi(sig, ex), _logpsi(sig64, ex64)
+    assert np.array_equal(np.sign(sig), np.sign(to_np(psi.significand)))
+    scale = max(1.0, np.abs(lo).max())
+    check("E forward log psi vs float32 oracle", np.abs(lg - lo).max() / scale, 1e-5)
+    check("E forward log psi vs float64 evaluation of the same weights", np.abs(lg - l64).max() / scale, 1e-5)
+    O = to_np(state.jacobian(st))
+    Oo = net.jacobian(s)
+    assert O.shape == Oo.shape == (16, 1047552)
+    check("E jacobian vs float32 oracle", np.abs(O - Oo).max() / np.abs(Oo).max(), 1e-5)
+
+
+def test_config_e_sweep_and_oloc_vs_oracle(qtx):
+    """Config E network and Hamiltonian (J1-J2, J2 = 0.5, Marshall sign): a 24-step exchange sweep of 8 chains on
+    the production Philox stream, then Oloc over all connected configurations, against the oracle."""
+    lat, olat = lattice_pair(qtx, "square", 16, (128, 128))
+    model, net = _resconv_pair(qtx, (16, 16), 8, 88, torch.float32, "sinhp1", seed=13)
+    state = qtx.state.Variational(model)
+    ns, T = 8, 24
+    sampler = qtx.sampler.SpinExchange(state, ns, thermal_steps=0)
+    spins0 = to_np(sampler._spins).copy()
+    samples = sampler.sweep(T, record=True)
+    table = osites.site_neighbor_table(olat)
+    ref = osmp.sweep(osmp.FullForwardChainModel(net), spins0, T, "exchange", neighbors=table, seed=sampler._seed,
+                     step0=0, record=True)
+    got_log, ref_log = to_np(sampler.last_accept_log), ref["accept_log"]
+    for c in range(ns):  # float32 model: a chain may only leave the oracle's at a near-tie of the accept test
+        d = np.nonzero(got_log[:, c] != ref_log[:, c])[0]
+        if d.size:
+            assert ref["margin"][d[0], c] < 1e-4, f"chain {c} diverged at step {d[0]} with margin {ref['margin'][d[0], c]}"
+    same = (to_np(samples.spins) == ref["spins"]).all(axis=1)
+    assert same.mean() >= 0.75
+    s = to_np(samples.spins)[:4]
+    H = qtx.operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
+    aol = oop.to_array_op_list(oop.heisenberg_op_list(olat, J=[1, 0.5], n_neighbor=[1, 2], msr=True))
+    E = to_np(H.Oloc(state, samples.spins[:4]))
+    Eo = oop.oloc(aol, _fast(net), s)
+    E64 = oop.oloc(aol, _fast(_f64_twin(net)), s)
+    scale = np.abs(Eo).max()
+    noise = np.abs(Eo - E64).max() / scale  # what float32 rounding alone does to the oracle's own local energies
+    err = np.abs(E - E64).max() / scale
+    check("E Oloc vs float64 evaluation (bar: 1e-5 or the float32 oracle's own distance from it)", err,
+          max(1e-5, 2 * noise))
+    check("E Oloc vs float32 oracle", np.abs(E - Eo).max() / scale, max(1e-5, 3 * noise))
+
+
+def test_config_b_sweep_and_oloc_vs_oracle(qtx):
+    """BASELINE configs[1]: 10x10 Heisenberg (Marshall sign), RBM_Dense alpha = 4 (M = 400), SpinExchange: the full
+    200-step sweep of 64 chains on the production Philox stream, then Oloc, against the oracle."""
+    lat, olat = lattice_pair(qtx, "square", 10, (50, 50))
+    table = osites.site_neighbor_table(olat)
+    aol = oop.to_array_op_list(oop.heisenberg_op_list(olat, msr=True))
+    H = qtx.operator.Heisenberg(msr=True)
+    for dtype in (torch.float64, torch.float32):
+        model, net = make_rbm(qtx, 100, 400, dtype, seed=21, scale=0.3)
+        state = qtx.state.Variational(model)
+        ns, T = 64, 200
+        sampler = qtx.sampler.SpinExchange(state, ns, thermal_steps=0)
+        spins0 = to_np(sampler._spins).copy()
+        samples = sampler.sweep(T, record=True)
+        ref = osmp.sweep(osmp.RBMChainModel(net), spins0, T, "exchange", neighbors=table, hop=1, seed=sampler._seed,
+                         step0=0, chain0=0, record=True)
+        got_log, ref_log = to_np(sampler.last_accept_log), ref["accept_log"]
+        if dtype == torch.float64:
+            assert np.array_equal(got_log, ref_log)
+            assert np.array_equal(to_np(samples.spins), ref["spins"])
+        else:
+            for c in range(ns):
+                d = np.nonzero(got_log[:, c] != ref_log[:, c])[0]
+                if d.size:
+                    assert ref["margin"][d[0], c] < 1e-4
+            assert (to_np(samples.spins) == ref["spins"]).all(axis=1).mean() >= 0.9
+        s = to_np(samples.spins)
+        E = to_np(H.Oloc(state, samples))
+        Eo = oop.oloc(aol, net.forward, s)
+        check(f"B Oloc {dtype}", np.abs(E - Eo).max() / np.abs(Eo).max(), 1e-10 if dtype == torch.float64 else 1e-5)
+        if dtype == torch.float64:
+            O = to_np(state.jacobian(samples.spins))
+            check("B jacobian float64", np.abs(O - net.jacobian(s)).max(), 1e-12)
+            opt = qtx.optimizer.SR(state, H)
+            step = to_np(opt.get_step(samples))
+            xo, eo, vo = osolver.sr_step(net.jacobian(s), Eo, np.ones(ns))
+            w = np.linalg.eigvalsh(osolver.obar(net.jacobian(s), np.ones(ns))[0] @ osolver.obar(net.jacobian(s), np.ones(ns))[0].T)
+            assert w[1] > 1e-6 * w[-1]  # gapped at the default cut-off (one exact null direction from the centring)
+            check("B MinSR step (64 rows x 40400 parameters)", np.linalg.norm(step - xo) / np.linalg.norm(xo), 1e-10)
+
+
+def test_config_c_forward_jacobian_oloc_vs_oracle(qtx):
+    """BASELINE configs[2]: 10x10 J1-J2 (J2 = 0.5), ResConv with 8 blocks (C = 32; BASELINE leaves the width open),
+    translation symmetry through the network's own ConvSymmetrize, float32."""
+    lat, olat = lattice_pair(qtx, "square", 10, (50, 50))
+    model, net = _resconv_pair(qtx, (10, 10), 8, 32, torch.float32, "sinhp1", seed=31)
+    state = qtx.state.Variational(model)
+    s = osmp.rand_states(24, 100, 50, seed=32)
+    st = torch.from_numpy(s).cuda()
+    psi = state(st)
+    sig, ex = net.forward(s)
+    lg, lo = _logpsi(to_np(psi.significand), to_np(psi.exponent)), _logpsi(sig, ex)
+    check("C forward log psi", np.abs(lg - lo).max() / max(1.0, np.abs(lo).max()), 1e-5)
+    # translation invariance of the symmetrised amplitude (sector 0)
+    sh = np.roll(s.reshape(-1, 10, 10), (3, 7), axis=(1, 2)).reshape(-1, 100)
+    psh = state(torch.from_numpy(np.ascontiguousarray(sh)).cuda())
+    check("C translation invariance", np.abs(_logpsi(to_np(psh.significand), to_np(psh.exponent)) - lg).max(), 2e-5)
+    O = to_np(state.jacobian(st[:8]))
+    Oo = net.jacobian(s[:8])
+    check("C jacobian", np.abs(O - Oo).max() / np.abs(Oo).max(), 1e-5)
+    H = qtx.operator.Heisenberg(J=[1, 0.5], n_neighbor=[1, 2], msr=True)
+    aol = oop.to_array_op_list(oop.heisenberg_op_list(olat, J=[1, 0.5], n_neighbor=[1, 2], msr=True))
+    E = to_np(H.Oloc(state, st))
+    Eo = oop.oloc(aol, _fast(net), s)
+    E64 = oop.oloc(aol, _fast(_f64_twin(net)), s)
+    scale = np.abs(Eo).max()
+    noise = np.abs(Eo - E64).max() / scale
+    check("C Oloc vs float64 evaluation", np.abs(E - E64).max() / scale, max(1e-5, 2 * noise))
+
+
+def test_config_d_projected_complex_state_vs_oracle(qtx):
+    """BASELINE configs[3] / tutorials/triangular.ipynb:236-239,329: 12x12 triangular Heisenberg, ResConv(4, 8, 3)
+    float32 with complex128 output and the Neel-120 phase layer, projected with D6(center=(0, 0)) @ SpinInverse()
+    (24 images): amplitude, local energies and the stacked Jacobian on a few samples."""
+    from tests.test_complex_gpu import make_model
+
+    lat, olat = lattice_pair(qtx, "triangular", 12, (72, 72))
+    model, net = make_model(qtx, 12, 4, 8, torch.float32, "exp", seed=41)
+    S = qtx.symmetry
+    symm = S.D6(center=(0, 0)) @ S.SpinInverse()
+    osymm = osym.Rotation(olat, np.pi / 3, center=(0, 0)) @ osym.Flip(olat, center=(0, 0)) @ osym.SpinInverse(olat)
+    state = qtx.state.Variational(model, symm=symm, max_parallel=2048)
+    assert state.symm.nsymm == osymm.nsymm == 24
+    s = osmp.rand_states(6, 144, 72, seed=42)
+    st = torch.from_numpy(s).cuda()
+    _, _, (m, e, w, b, emax) = osym.project(osymm, net.forward, s)
+    psi = state(st)
+    got = to_np(psi.mult) * np.exp(to_np(psi.expo) - emax)
+    scale = np.sum(np.abs(m * w[None, :]) * np.exp(e - emax[:, None]), axis=1)
+    check("D projected amplitude (scale of the 24 summands)", np.abs(got - b).max() / scale.max(), 2e-5)
+    H = qtx.operator.Heisenberg()
+    aol = oop.to_array_op_list(oop.heisenberg_op_list(olat))
+    fwd = lambda x: osym.project(osymm, net.forward, x)[:2]
+    E = to_np(H.Oloc(state, st[:2]))
+    Eo = oop.oloc(aol, fwd, s[:2])
+    amp = (scale / np.abs(b)).max()  # cancellation factor of the projection
+    check("D projected Oloc", np.abs(E - Eo).max() / np.abs(Eo).max(), 1e-5 * max(1.0, amp))
+    O = to_np(state.jacobian(st[:2]))
+    Oo = osym.projected_jacobian(osymm, net.forward, net.jacobian, s[:2])
+    check("D projected jacobian", np.abs(O - Oo).max() / max(1.0, np.abs(Oo).max()), 1e-5 * max(1.0, amp))

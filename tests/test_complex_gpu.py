@@ -7,7 +7,7 @@ import torch
 
 from oracle import models as omodels, operator as oop, sampler as osmp, sites as osites, solver as osolver
 from oracle import symmetry as osym
-from tests.gpu_util import lattice_pair, to_np
+from tests.gpu_util import check, lattice_pair, to_np
 
 pytestmark = pytest.mark.gpu
 
@@ -94,11 +94,13 @@ def test_complex_forward_and_jacobian(qtx, final, dtype, tol, phase):
     assert np.abs(O - Oo).max() <= 10 * tol * np.abs(Oo).max()
 
 
-def test_complex_oloc_sweep_and_sr_step(qtx):
+@pytest.mark.parametrize("phase,tol", [(True, 1e-6), (False, 1e-10)])
+def test_complex_oloc_sweep_and_sr_step(qtx, phase, tol):
     """Heisenberg on the 6x6 triangular lattice: exchange sweep with injected randoms (bit-exact accept pattern),
-    complex local energies, stacked [Re; Im] SR step (sr.py:99-104)."""
+    complex local energies, stacked [Re; Im] SR step (sr.py:99-104).  With the phase layer the reference's own
+    phases are complex64 (nn/sign.py:36,73), which bounds the agreement at 1e-6; without it the float64 bar holds."""
     lat, olat = lattice_pair(qtx, "triangular", 6, (18, 18))
-    model, net = make_model(qtx, 6, 2, 4, torch.float64, "exp", seed=4)
+    model, net = make_model(qtx, 6, 2, 4, torch.float64, "exp", seed=4, phase=phase)
     state = qtx.state.Variational(model)
     ns, T = 40, 25
     sampler = qtx.sampler.SpinExchange(state, ns, thermal_steps=0)
@@ -119,10 +121,11 @@ def test_complex_oloc_sweep_and_sr_step(qtx):
     assert np.iscomplexobj(Eo)
     opt = qtx.optimizer.SR(state, H)
     step = to_np(opt.get_step(samples))
-    assert np.abs(to_np(opt._Eloc) - Eo).max() <= 1e-6 * np.abs(Eo).max()  # complex64 phases in both
+    check(f"complex Oloc phase={phase}", np.abs(to_np(opt._Eloc) - Eo).max() / np.abs(Eo).max(), tol)
     xo, eo, vo = osolver.sr_step(net.jacobian(s), Eo, np.ones(ns), real_to_complex=True)
-    assert abs(opt.energy - eo.real) <= 1e-6 * abs(eo) and abs(opt.VarE - vo) <= 1e-5 * abs(vo)
-    assert np.isrealobj(step) and np.linalg.norm(step - xo.real) <= 1e-5 * np.linalg.norm(xo)
+    assert abs(opt.energy - eo.real) <= tol * abs(eo) and abs(opt.VarE - vo) <= 10 * tol * abs(vo)
+    assert np.isrealobj(step)
+    check(f"complex stacked SR step phase={phase}", np.linalg.norm(step - xo.real) / np.linalg.norm(xo), 10 * tol)
     p0 = to_np(state.get_params_flatten()).copy()
     state.update(torch.from_numpy(step).cuda() * 0.01)
     assert np.allclose(to_np(state.get_params_flatten()), p0 - 0.01 * step, rtol=1e-12, atol=1e-14)
@@ -175,7 +178,7 @@ def test_time_evol_step_and_heun_driver(qtx):
         assert np.abs(to_np(F) - Fo).max() <= 1e-10 * np.abs(Fo).max()
         assert abs(tdvp.energy - eo) <= 1e-10 * abs(eo) and abs(tdvp.VarE - vo) <= 1e-9 * abs(vo)
         step = to_np(tdvp.get_step(samples))
-        assert np.linalg.norm(step - xo) <= 1e-6 * np.linalg.norm(xo)
+        check("TimeEvol step", np.linalg.norm(step - xo) / np.linalg.norm(xo), 1e-10)
     with pytest.raises(ValueError):
         bad = qtx.sampler.Samples(st, state(st), None, torch.full((ns,), 2.0, dtype=torch.float64, device="cuda"))
         tdvp.get_step(bad)

@@ -336,3 +336,17 @@ def test_oracle_snr_damping_limits():
     snr = np.abs(mean) / np.sqrt(((r - mean) ** 2).mean(axis=0) / 16)
     rho = r.sum(axis=0) / (1 + (1.0 / snr) ** 6)
     assert np.allclose(xs, A.T @ (U @ (osolver.eigs_inv(vals) * rho)), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype,final", [(np.float32, "sinhp1"), (np.float64, "exp")])
+def test_torch_cpu_resconv_equals_the_numpy_oracle(dtype, final):
+    """oracle/resconv_torch.py (the timed CPU leg of bench.py and the fast oracle of the BASELINE-shape GPU tests)
+    against the einsum oracle."""
+    from oracle.resconv_torch import TorchResConv
+
+    net = models.ResConv.random((6, 6), 3, 10, 3, dtype, seed=3, final=final, bias_std=0.2)
+    s = osmp.rand_states(9, 36, 18, seed=4)
+    a, b = net.forward(s), TorchResConv(net).forward(s)
+    tol = 2e-6 if dtype == np.float32 else 1e-13
+    assert np.array_equal(np.sign(a[0]), np.sign(b[0]))
+    assert np.abs(np.log(np.abs(a[0])) + a[1] - np.log(np.abs(b[0])) - b[1]).max() < tol

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import models as omodels, operator as oop, sampler as osmp, sites as osites, solver as osolver
-from tests.gpu_util import lattice_pair, make_rbm, to_np
+from tests.gpu_util import check, lattice_pair, make_rbm, to_np
 
 pytestmark = pytest.mark.gpu
 
@@ -120,11 +120,13 @@ def test_sr_step_matches_oracle(qtx, case):
     xo, eo, vo = osolver.sr_step(net.jacobian(s), Eo, np.ones(ns))
     assert (ns < model.nparams) == (case == "minsr")
     assert abs(opt.energy - eo) <= 1e-10 * abs(eo) and abs(opt.VarE - vo) <= 1e-9 * abs(vo)
-    assert np.linalg.norm(step - xo) <= 1e-6 * np.linalg.norm(xo)
+    # the spectrum of this system has a gap at the default cut-off (smallest non-zero eigenvalue 1.6e-3 lambda_max,
+    # exact null directions at 1e-17): the float64 bar of 1e-10 applies
+    check(f"{case} step vs oracle", np.linalg.norm(step - xo) / np.linalg.norm(xo), 1e-10)
     # MinSR alias forces the Ns x Ns solver
     if case == "minsr":
         step2 = to_np(qtx.optimizer.MinSR(state, H).get_step(samples))
-        assert np.linalg.norm(step2 - xo) <= 1e-6 * np.linalg.norm(xo)
+        check("MinSR alias step vs oracle", np.linalg.norm(step2 - xo) / np.linalg.norm(xo), 1e-10)
     p0 = to_np(model.params).copy()
     state.update(torch.from_numpy(step).cuda() * 0.01)
     assert np.allclose(to_np(model.params), osolver.update_params(p0, step * 0.01), rtol=1e-14)

@@ -5,7 +5,7 @@ import torch
 
 from oracle import models as omodels, operator as oop, sampler as osmp, sites as osites, solver as osolver
 from oracle import symmetry as osym
-from tests.gpu_util import lattice_pair, make_rbm, to_np
+from tests.gpu_util import check, lattice_pair, make_rbm, to_np
 from tests.test_resconv_gpu import make_resconv
 
 pytestmark = pytest.mark.gpu
@@ -60,7 +60,7 @@ def test_projected_amplitude_and_jacobian(qtx, which, model_kind):
         assert np.array_equal(sign_g[ok], sign[ok] * np.sign(osymm.character[g]))
     O = to_np(state.jacobian(torch.from_numpy(s)))
     Oo = osym.projected_jacobian(osymm, net.forward, net.jacobian, s)
-    assert np.abs(O[ok] - Oo[ok]).max() <= 1e-9 * max(1.0, np.abs(Oo[ok]).max())
+    check("projected jacobian", np.abs(O[ok] - Oo[ok]).max() / max(1.0, np.abs(Oo[ok]).max()), 1e-10)
 
 
 def test_projected_state_full_step(qtx):
@@ -94,8 +94,8 @@ def test_projected_state_full_step(qtx):
     Eo = oop.oloc(aol, fwd, s)
     opt = qtx.optimizer.SR(state, H)
     step = to_np(opt.get_step(samples))
-    assert np.abs(to_np(opt._Eloc) - Eo).max() <= 1e-9 * np.abs(Eo).max()
+    check("projected Oloc", np.abs(to_np(opt._Eloc) - Eo).max() / np.abs(Eo).max(), 1e-10)
     Oo = osym.projected_jacobian(osymm, net.forward, net.jacobian, s)
     xo, eo, vo = osolver.sr_step(Oo, Eo, np.ones(ns))
     assert abs(opt.energy - eo) <= 1e-10 * abs(eo)
-    assert np.linalg.norm(step - xo) <= 1e-5 * np.linalg.norm(xo)
+    check("projected SR step", np.linalg.norm(step - xo) / np.linalg.norm(xo), 1e-10)
