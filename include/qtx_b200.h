@@ -383,6 +383,23 @@ int qtx_pinv_rational_partial(const double* T, int64_t n, const double* b, doubl
 int qtx_dd_sum_scale(const double* ydd, int count, int64_t n, double scale, double* y_out,
                      qtx_stream_t stream);
 
+/* The same partial sums with the library's OWN kernels and no cuSOLVER call -- the default soft pseudo-inverse of
+ * the SR / MinSR solve (replaces `eigh` + `_get_eigs_inv`, solver.py:94-111,142-146): T - z_k I is complex
+ * symmetric with its field of values off the origin, so it is factorised as L D L^T WITHOUT pivoting (csrc/zldlt.cu:
+ * blocked right-looking, FP64 FMA trailing updates, wavefront triangular solves), refined with double-double
+ * residuals like qtx_pinv_rational_partial.  Several shifts of one call run concurrently on side streams that are
+ * forked from and joined back into `stream`.  info_out: 0 = ok, > 0 = 1-based index of a zero pivot, < 0 = -(k+1):
+ * the refinement of shift k did not contract.
+ *   qtx_pinv_ldlt_workspace_size(n, nshifts) : bytes for a call that takes `nshifts` (1..3) shifts (0 on failure)
+ *   qtx_sym_absmax_eig_ws                    : qtx_sym_absmax_eig inside that workspace (same continuation protocol) */
+size_t qtx_pinv_ldlt_workspace_size(int64_t n, int nshifts);
+int qtx_sym_absmax_eig_ws(const double* T, int64_t n, int first_step, int steps, double* lam_out,
+                          void* workspace, size_t workspace_bytes, int nshifts, qtx_stream_t stream);
+int qtx_pinv_ldlt_partial(const double* T, int64_t n, const double* b, double rtol, double atol,
+                          const double* lam, int shift_mask, int refine_steps, double* ydd_inout,
+                          int accumulate, int32_t* info_out, void* workspace, size_t workspace_bytes,
+                          qtx_stream_t stream);
+
 /* y = (T + shift I)^-1 b, shift = rshift * trace(T) + ashift, by Cholesky (minnorm_shift_eig /
  * lstsq_shift_eig, solver.py:50-77; `solve(assume_a="pos")`).  rshift < 0 selects the dtype
  * default (1e-12).  T [n, n] float64 symmetric is overwritten by its factor; info_out int32 [1]

@@ -81,6 +81,9 @@ SIGNATURES = {
     "qtx_sym_absmax_eig": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "qtx_pinv_rational_partial": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "qtx_dd_sum_scale": (_i32, [_vp, _i32, _i64, _f64, _vp, _vp]),
+    "qtx_pinv_ldlt_workspace_size": (_sz, [_i64, _i32]),
+    "qtx_sym_absmax_eig_ws": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _i32, _vp]),
+    "qtx_pinv_ldlt_partial": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "qtx_shift_chol_workspace_size": (_sz, [_i64]),
     "qtx_shift_chol_solve": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _vp, _vp, _sz, _vp]),
     "qtx_col_sumsq": (_i32, [_i32, _vp, _i64, _i64, _i64, _vp, _vp]),

@@ -26,6 +26,7 @@
 #define QTX_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 #include "dd_math.cuh"
+#include "zldlt.cuh"
 
 namespace qtx {
 
@@ -310,6 +311,64 @@ __global__ void max_info_kernel(int32_t* __restrict__ info, const int32_t* __res
 }
 __global__ void zero_info_kernel(int32_t* __restrict__ info) { info[0] = 0; }
 
+// lower triangle of M = T - z I only (zldlt reads nothing else), rhs = b; same degenerate / NaN rules as above
+__global__ void __launch_bounds__(256) shift_build_lower_kernel(const double* __restrict__ T, int64_t n,
+                                                                const double* __restrict__ b,
+                                                                const double* __restrict__ lam, ShiftParams p,
+                                                                cuDoubleComplex* __restrict__ M,
+                                                                cuDoubleComplex* __restrict__ rhs) {
+  const double c = cutoff_of(lam, p);
+  const bool degenerate = (c == 0.0);
+  const double zr = c * p.cs, zi = c * p.sn;
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const double* row = T + i * n;
+    cuDoubleComplex* out = M + i * n;
+    for (int64_t j = threadIdx.x; j <= i; j += blockDim.x) {
+      double re = degenerate ? 0.0 : row[j], im = 0.0;
+      if (i == j) {
+        re = degenerate ? 1.0 : re - zr;
+        im = degenerate ? 0.0 : -zi;
+      }
+      out[j] = make_cuDoubleComplex(re, im);
+    }
+    if (threadIdx.x == 0) rhs[i] = make_cuDoubleComplex(degenerate ? 0.0 : b[i], 0.0);
+  }
+}
+
+// after the last refinement step: the correction d must be small against the solution x, otherwise the factors are
+// useless (the refinement did not contract) and info = code (< 0) says so.  One CTA.
+__global__ void __launch_bounds__(256) refine_check_kernel(int64_t n, const cuDoubleComplex* __restrict__ d,
+                                                           const double* __restrict__ x, int32_t* __restrict__ info,
+                                                           int32_t code) {
+  __shared__ double red[2][8];
+  double md = 0.0, mx = 0.0;
+  bool bad = false;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double a = fmax(fabs(d[i].x), fabs(d[i].y)), v = fmax(fabs(x[i]), fabs(x[2 * n + i]));
+    bad = bad || !(a == a) || !(v == v);
+    md = fmax(md, a);
+    mx = fmax(mx, v);
+  }
+  if (bad) md = 1e300;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    md = fmax(md, __shfl_xor_sync(FULL, md, o));
+    mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = md;
+    red[1][threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      md = fmax(md, red[0][w]);
+      mx = fmax(mx, red[1][w]);
+    }
+    if (md > 1e-2 * mx && info[0] == 0) info[0] = code;
+  }
+}
+
 struct RationalLayout {
   size_t M, rhs, ipiv, work, x, lanczos, info, total;
   int lwork;
@@ -448,6 +507,196 @@ extern "C" int qtx_pinv_rational_partial(const double* T, int64_t n, const doubl
       QTX_LAUNCH_CHECK();
     }
     QTX_LAUNCH(dd_accum_real_kernel, gn, 256, st, n, x, ydd_inout, 1);
+    QTX_LAUNCH_CHECK();
+  }
+  return QTX_OK;
+}
+
+// ---- the same partial sums with OWN kernels: complex-symmetric LDL^T (zldlt.cu) instead of cuSOLVER's LU -----------
+namespace qtx {
+
+struct LdltLayout {
+  size_t M, rhs, x, scratch, info, slot, lanczos, total;  // offsets inside a shift slot; slot = its size
+};
+
+static LdltLayout ldlt_layout(int64_t n, int nslots) {
+  LdltLayout L;
+  size_t off = 0;
+  L.M = off;
+  off += align_up((size_t)n * n * sizeof(cuDoubleComplex));
+  L.rhs = off;
+  off += align_up((size_t)n * sizeof(cuDoubleComplex));
+  L.x = off;
+  off += align_up(4 * (size_t)n * sizeof(double));
+  L.scratch = off;
+  off += align_up(zldlt_scratch_bytes(n));
+  L.info = off;
+  off += 256;
+  L.slot = off;
+  L.lanczos = (size_t)nslots * L.slot;  // [w | v | vprev | alpha | beta | state(2)]: the layout qtx_sym_absmax_eig uses
+  L.total = L.lanczos + align_up((3 * (size_t)n + 2 * kLanczosMaxSteps + 2) * sizeof(double)) + 256;
+  return L;
+}
+
+#ifndef QTX_HOST_EMULATION
+// two side streams for running the three shifts of one call concurrently (fork / join with events on the caller's
+// stream: the call still only ENQUEUES work that is ordered after, and joined back into, `stream`)
+struct ShiftStreams {
+  int device = -1;
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+static thread_local ShiftStreams g_shift_streams;
+
+static int shift_streams(ShiftStreams** out) {
+  int dev = 0;
+  QTX_CUDA(cudaGetDevice(&dev));
+  ShiftStreams& s = g_shift_streams;
+  if (s.device != dev) {
+    for (int i = 0; i < 2; ++i) {
+      QTX_CUDA(cudaStreamCreateWithFlags(&s.side[i], cudaStreamNonBlocking));
+      QTX_CUDA(cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming));
+    }
+    QTX_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    s.device = dev;
+  }
+  *out = &s;
+  return QTX_OK;
+}
+#endif
+
+// one shift on one stream: build, factor, solve + refine; leaves the double-double solution in slot.x
+static int ldlt_one_shift(const double* T, int64_t n, const double* b, const double* lam, ShiftParams p, int k,
+                          int refine_steps, char* slot, const LdltLayout& L, cudaStream_t st) {
+  cuDoubleComplex* M = (cuDoubleComplex*)(slot + L.M);
+  cuDoubleComplex* rhs = (cuDoubleComplex*)(slot + L.rhs);
+  double* x = (double*)(slot + L.x);
+  void* scratch = slot + L.scratch;
+  int32_t* info = (int32_t*)(slot + L.info);
+  const unsigned gn = (unsigned)((n + 255) / 256);
+  QTX_LAUNCH(zero_info_kernel, 1, 1, st, info);
+  QTX_LAUNCH_CHECK();
+  const unsigned gb = n < 16 * (int64_t)num_sms() ? (unsigned)n : 16u * (unsigned)num_sms();
+  QTX_LAUNCH(shift_build_lower_kernel, gb, 256, st, T, n, b, lam, p, M, rhs);
+  QTX_LAUNCH_CHECK();
+  int rc = zldlt_factor(M, n, scratch, info, st);
+  if (rc) return rc;
+  for (int it = 0; it <= refine_steps; ++it) {
+    if (it > 0) {
+      QTX_LAUNCH(dd_residual_kernel, (unsigned)n, kRowThreads, st, T, n, b, lam, p, x, rhs);
+      QTX_LAUNCH_CHECK();
+    }
+    rc = zldlt_solve(M, n, rhs, scratch, st);
+    if (rc) return rc;
+    if (it == 0) QTX_LAUNCH(dd_set_kernel, gn, 256, st, n, rhs, x);
+    else QTX_LAUNCH(dd_correct_kernel, gn, 256, st, n, rhs, x);
+    QTX_LAUNCH_CHECK();
+    if (it == refine_steps && it > 0) {
+      QTX_LAUNCH(refine_check_kernel, 1, 256, st, n, rhs, x, info, -(k + 1));
+      QTX_LAUNCH_CHECK();
+    }
+  }
+  return QTX_OK;
+}
+
+}  // namespace qtx
+
+extern "C" size_t qtx_pinv_ldlt_workspace_size(int64_t n, int nshifts) {
+  if (n <= 0 || n > 46340 || nshifts < 1 || nshifts > 3) return 0;
+  return ldlt_layout(n, nshifts).total;
+}
+
+// Lanczos for max|lambda| in the workspace of qtx_pinv_ldlt_workspace_size(n, nshifts) (same recurrence, same
+// continuation protocol as qtx_sym_absmax_eig)
+extern "C" int qtx_sym_absmax_eig_ws(const double* T, int64_t n, int first_step, int steps, double* lam_out,
+                                     void* workspace, size_t workspace_bytes, int nshifts, qtx_stream_t stream) {
+  QTX_REQUIRE(T && lam_out && workspace && n > 0 && n <= 46340 && steps > 0 && steps <= kLanczosMaxSteps &&
+                  first_step >= 0 && first_step < steps && nshifts >= 1 && nshifts <= 3,
+              QTX_ERR_INVALID, "qtx_sym_absmax_eig_ws: bad argument");
+  const LdltLayout L = ldlt_layout(n, nshifts);
+  QTX_REQUIRE(workspace_bytes >= L.total, QTX_ERR_INVALID, "qtx_sym_absmax_eig_ws: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)align_up((size_t)workspace);
+  double* w = (double*)(base + L.lanczos);
+  double *v = w + n, *vprev = v + n, *alpha = vprev + n, *beta = alpha + kLanczosMaxSteps,
+         *state = beta + kLanczosMaxSteps;
+  const int m = steps < n ? steps : (int)n;
+  if (first_step == 0) {
+    QTX_LAUNCH(lanczos_init_kernel, 1, kLanczosThreads, st, n, v, vprev, state);
+    QTX_LAUNCH_CHECK();
+  }
+  for (int j = first_step; j < m; ++j) {
+    int rc = qtx_matvec(QTX_F64, T, n, n, n, v, w, stream);
+    if (rc) return rc;
+    QTX_LAUNCH(lanczos_step_kernel, 1, kLanczosThreads, st, n, w, v, vprev, alpha, beta, j, state);
+    QTX_LAUNCH_CHECK();
+  }
+  QTX_LAUNCH(tridiag_absmax_kernel, 1, 64, st, alpha, beta, m, lam_out);
+  QTX_LAUNCH_CHECK();
+  return QTX_OK;
+}
+
+extern "C" int qtx_pinv_ldlt_partial(const double* T, int64_t n, const double* b, double rtol, double atol,
+                                     const double* lam, int shift_mask, int refine_steps, double* ydd_inout,
+                                     int accumulate, int32_t* info_out, void* workspace, size_t workspace_bytes,
+                                     qtx_stream_t stream) {
+  QTX_REQUIRE(T && b && lam && ydd_inout && info_out && workspace && n > 0 && n <= 46340 && shift_mask >= 0 &&
+                  shift_mask < 8 && refine_steps >= 0 && refine_steps <= 16 && atol >= 0.0,
+              QTX_ERR_INVALID, "qtx_pinv_ldlt_partial: bad argument");
+  if (rtol < 0) rtol = 1e-12;  // solver.py:12-21 for float64
+  QTX_REQUIRE(rtol > 0.0 || atol > 0.0, QTX_ERR_UNSUPPORTED,
+              "qtx_pinv_ldlt_partial: rtol = atol = 0 is the plain inverse, use qtx_pinv_eig_solve");
+  int nshifts = 0;
+  for (int k = 0; k < 3; ++k) nshifts += (shift_mask >> k) & 1;
+  const LdltLayout L = ldlt_layout(n, nshifts > 0 ? nshifts : 1);
+  QTX_REQUIRE(workspace_bytes >= L.total, QTX_ERR_INVALID, "qtx_pinv_ldlt_partial: workspace too small for %d shifts",
+              nshifts);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)align_up((size_t)workspace);
+  const unsigned gn = (unsigned)((n + 255) / 256);
+  QTX_LAUNCH(zero_info_kernel, 1, 1, st, info_out);
+  QTX_LAUNCH_CHECK();
+  if (!accumulate) {
+    QTX_LAUNCH(dd_zero_kernel, (unsigned)((2 * n + 255) / 256), 256, st, 2 * n, ydd_inout);
+    QTX_LAUNCH_CHECK();
+  }
+  if (nshifts == 0) return QTX_OK;
+  static const double kCos[3] = {0.86602540378443864676, 0.0, -0.86602540378443864676};  // cos(pi (2k+1)/6)
+  static const double kSin[3] = {0.5, 1.0, 0.5};
+#ifndef QTX_HOST_EMULATION
+  ShiftStreams* ss = nullptr;
+  if (nshifts > 1) {
+    int rc = shift_streams(&ss);
+    if (rc) return rc;
+    QTX_CUDA(cudaEventRecord(ss->fork, st));
+  }
+#endif
+  int slot = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (!((shift_mask >> k) & 1)) continue;
+    const ShiftParams p = {rtol, atol, kCos[k], kSin[k]};
+    cudaStream_t sk = st;
+#ifndef QTX_HOST_EMULATION
+    if (slot > 0) {
+      sk = ss->side[slot - 1];
+      QTX_CUDA(cudaStreamWaitEvent(sk, ss->fork, 0));
+    }
+#endif
+    int rc = ldlt_one_shift(T, n, b, lam, p, k, refine_steps, base + (size_t)slot * L.slot, L, sk);
+    if (rc) return rc;
+#ifndef QTX_HOST_EMULATION
+    if (slot > 0) {
+      QTX_CUDA(cudaEventRecord(ss->join[slot - 1], sk));
+      QTX_CUDA(cudaStreamWaitEvent(st, ss->join[slot - 1], 0));
+    }
+#endif
+    ++slot;
+  }
+  for (int q = 0; q < nshifts; ++q) {  // the shifts are summed in a fixed order on the caller's stream
+    char* sl = base + (size_t)q * L.slot;
+    QTX_LAUNCH(dd_accum_real_kernel, gn, 256, st, n, (const double*)(sl + L.x), ydd_inout, 1);
+    QTX_LAUNCH_CHECK();
+    QTX_LAUNCH(max_info_kernel, 1, 1, st, info_out, (const int32_t*)(sl + L.info));
     QTX_LAUNCH_CHECK();
   }
   return QTX_OK;

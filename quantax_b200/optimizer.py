@@ -101,31 +101,59 @@ def _eig_workspace(n: int):
 
 
 # How the soft pseudo-inverse y = f(T) b is evaluated when no eigen-quantity is asked for:
-#   "eigh"     (default) cuSOLVER syevd + the pseudo-inverse epilogue (qtx_pinv_eig_solve)
-#   "rational" three complex shifted LU solves refined in double-double (qtx_pinv_rational_partial): the same
-#              function of T by partial fractions, no eigendecomposition.  Opt-in until its first GPU session.
-PINV_METHOD = os.environ.get("QTX_PINV", "eigh")
+#   "ldlt"     (default) three complex-symmetric shifted solves by the library's OWN blocked LDL^T kernels
+#              (csrc/zldlt.cu, qtx_pinv_ldlt_partial), refined in double-double: the same function of T by partial
+#              fractions, no eigendecomposition, no cuSOLVER call on the step
+#   "rational" the same identity with cuSOLVER's complex LU (qtx_pinv_rational_partial; cross-check)
+#   "eigh"     cuSOLVER syevd + the pseudo-inverse epilogue (qtx_pinv_eig_solve; cross-check, and what the
+#              eigen-quantity callers -- SNR damping, minsr_pinv_eig / pinvh_solve, rtol = atol = 0 -- keep using)
+PINV_METHOD = os.environ.get("QTX_PINV", "ldlt")
 LANCZOS_STEPS = max(1, min(1024, int(os.environ.get("QTX_LANCZOS_STEPS", "512"))))  # upper bound of the adaptive run
-REFINE_STEPS = int(os.environ.get("QTX_PINV_REFINE", "4"))
+REFINE_STEPS = int(os.environ.get("QTX_PINV_REFINE", "3"))
 
 
-def sym_absmax_eig(T: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
-    """max|lambda| of a symmetric float64 matrix as a device scalar [1] (Lanczos, qtx_sym_absmax_eig).  With
+def _shift_count(mask: int) -> int:
+    return max(1, bin(int(mask)).count("1"))
+
+
+def _pinv_workspace(n: int, method: str, nshifts: int):
+    """(buffer, bytes) of the shifted-solve workspace of ``method`` ("ldlt": own kernels, "rational": cuSOLVER LU)."""
+    if method == "ldlt":
+        wsz = _lib.lib().qtx_pinv_ldlt_workspace_size(n, nshifts)
+        what = "qtx_pinv_ldlt_workspace_size"
+    else:
+        wsz = _lib.lib().qtx_pinv_rational_workspace_size(n)
+        what = "qtx_pinv_rational_workspace_size"
+    if wsz == 0:
+        raise _lib.QtxError(f"{what} failed: {_lib.lib().qtx_last_error().decode()}")
+    return _WS.get("pinv_" + method, wsz), wsz
+
+
+def sym_absmax_eig(T: torch.Tensor, steps: Optional[int] = None, method: Optional[str] = None,
+                   nshifts: int = 3) -> torch.Tensor:
+    """max|lambda| of a symmetric float64 matrix as a device scalar [1] (Lanczos, qtx_sym_absmax_eig[_ws]).  With
     ``steps=None`` the recurrence is continued to 64, 128, 256, ... steps (at most QTX_LANCZOS_STEPS) until two
     consecutive values agree to 1e-14 -- the error after 2k steps is about the square of the error after k -- which
     costs one scalar read-back per stage; an explicit ``steps`` runs exactly that many without synchronising."""
     n = T.shape[0]
-    wsz = _lib.lib().qtx_pinv_rational_workspace_size(n)
-    if wsz == 0:
-        raise _lib.QtxError(f"qtx_pinv_rational_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
-    ws = _WS.get("rational", wsz)
+    method = "rational" if method is None and PINV_METHOD == "rational" else ("ldlt" if method is None else method)
+    ws, wsz = _pinv_workspace(n, method, nshifts)
     lam = torch.empty(1, dtype=torch.float64, device=T.device)
+
+    def run(first, upto):
+        if method == "ldlt":
+            _lib.call("qtx_sym_absmax_eig_ws", _lib.ptr(T), n, first, int(upto), _lib.ptr(lam), _lib.ptr(ws), wsz,
+                      int(nshifts), _lib.stream())
+        else:
+            _lib.call("qtx_sym_absmax_eig", _lib.ptr(T), n, first, int(upto), _lib.ptr(lam), _lib.ptr(ws), wsz,
+                      _lib.stream())
+
     if steps is not None:
-        _lib.call("qtx_sym_absmax_eig", _lib.ptr(T), n, 0, int(steps), _lib.ptr(lam), _lib.ptr(ws), wsz, _lib.stream())
+        run(0, steps)
         return lam
     done, prev = 0, None
     for upto in lanczos_stages(n, LANCZOS_STEPS):
-        _lib.call("qtx_sym_absmax_eig", _lib.ptr(T), n, done, upto, _lib.ptr(lam), _lib.ptr(ws), wsz, _lib.stream())
+        run(done, upto)
         done = upto
         cur = float(lam.item())
         if prev is not None and abs(cur - prev) <= 1e-14 * abs(cur):
@@ -154,32 +182,41 @@ def rational_shift_masks(P: int):
     return [1, 2, 4] + [0] * (P - 3)
 
 
-def pinv_rational_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol: float, replicated: bool = False):
+def pinv_rational_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol: float, replicated: bool = False,
+                        method: Optional[str] = None):
     """y = f(T) b, f(lambda) = lambda^5 / (lambda^6 + c^6), c = rtol max|lambda| + atol -- the soft pseudo-inverse
     of solver.py:94-111 -- as (1/3) Re sum_k (T - z_k I)^-1 b over the three roots of lambda^6 + c^6 in the upper
     half plane (exact partial fractions).  T is not overwritten.  ``replicated=True`` states that T and b are
     identical on every rank of the default process group: the ranks then take different shifts and exchange the
-    double-double partial sums (one all-gather of 2 n doubles); otherwise every process does all three."""
+    double-double partial sums (one all-gather of 2 n doubles); otherwise every process does all three.
+    ``method``: "ldlt" (own kernels, default) or "rational" (cuSOLVER LU)."""
     n = T.shape[0]
-    wsz = _lib.lib().qtx_pinv_rational_workspace_size(n)
-    if wsz == 0:
-        raise _lib.QtxError(f"qtx_pinv_rational_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
-    ws = _WS.get("rational", wsz)
+    if method is None:
+        method = "rational" if PINV_METHOD == "rational" else "ldlt"
     rank, P = world() if replicated else (0, 1)
     mask = rational_shift_masks(P)[rank]
-    t = _phase_tic("eigh_pinv")
-    lam = sym_absmax_eig(T)
+    nsh = _shift_count(mask)
+    ws, wsz = _pinv_workspace(n, method, nsh)
+    t = _phase_tic("pinv")
+    tl = _phase_tic("pinv.lanczos")
+    lam = sym_absmax_eig(T, method=method, nshifts=nsh)
+    _phase_toc(tl)
     ydd = torch.zeros((2, n), dtype=torch.float64, device=T.device)
     info = torch.zeros(1, dtype=torch.int32, device=T.device)
     if mask:
-        _lib.call("qtx_pinv_rational_partial", _lib.ptr(T), n, _lib.ptr(b.contiguous()),
-                  -1.0 if rtol is None else float(rtol), float(atol), _lib.ptr(lam), int(mask), int(REFINE_STEPS),
-                  _lib.ptr(ydd), 0, _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+        tf = _phase_tic("pinv.shifted_solves")
+        _lib.call("qtx_pinv_ldlt_partial" if method == "ldlt" else "qtx_pinv_rational_partial", _lib.ptr(T), n,
+                  _lib.ptr(b.contiguous()), -1.0 if rtol is None else float(rtol), float(atol), _lib.ptr(lam), int(mask),
+                  int(REFINE_STEPS), _lib.ptr(ydd), 0, _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())
+        _phase_toc(tf)
     count = 1
     if P > 1:
+        tc = _phase_tic("comm.all_gather_ydd")
         allydd = torch.empty((P, 2, n), dtype=torch.float64, device=T.device)
         _dist().all_gather_into_tensor(allydd.view(P * 2, n), ydd)
+        info = info.abs()  # > 0: zero pivot, < 0: refinement did not contract -- any non-zero is a failure
         _dist().all_reduce(info, op=_dist().ReduceOp.MAX)
+        _phase_toc(tc)
         ydd, count = allydd, P
     y = torch.empty(n, dtype=torch.float64, device=T.device)
     _lib.call("qtx_dd_sum_scale", _lib.ptr(ydd), count, n, 1.0 / 3.0, _lib.ptr(y), _lib.stream())
@@ -188,7 +225,7 @@ def pinv_rational_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float],
 
 
 def _use_rational(rtol, atol, tol_snr, want_evals) -> bool:
-    if PINV_METHOD != "rational" or want_evals or tol_snr > 1e-6:
+    if PINV_METHOD not in ("ldlt", "rational") or want_evals or tol_snr > 1e-6:
         return False
     return not (rtol is not None and float(rtol) == 0.0 and float(atol) == 0.0)  # plain inverse: eigenvalue route
 
@@ -208,7 +245,7 @@ def pinv_eig_solve(T: torch.Tensor, b: torch.Tensor, rtol: Optional[float], atol
     info = torch.empty(1, dtype=torch.int32, device=T.device)
     ws, wsz = _eig_workspace(n)
     rt = -1.0 if rtol is None else float(rtol)
-    t = _phase_tic("eigh_pinv")
+    t = _phase_tic("pinv")
     if tol_snr > 1e-6:
         _lib.call("qtx_pinv_eig_solve_snr", _lib.ptr(T), n, _lib.ptr(b.contiguous()), rt, float(atol), float(tol_snr),
                   _lib.ptr(evals), _lib.ptr(y), _lib.ptr(info), _lib.ptr(ws), wsz, _lib.stream())

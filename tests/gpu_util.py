@@ -42,6 +42,21 @@ def check(label, err, tol):
     assert err <= tol, f"{label}: {err:.3e} > {tol:.1e}"
 
 
+def sr_step_tolerance(ob, rtol=1e-12):
+    """Tolerance of a float64 SR / MinSR step against the oracle: the bar is 1e-10 on a spectrum with a GAP at the
+    cut-off rtol * lambda_max (asserted here: no eigenvalue within a factor 1000 of it); both sides then carry the
+    eigenvalue error eps * lambda_max on 1 / lambda_k, i.e. eps * lambda_max / lambda_min(kept) relative, which
+    exceeds 1e-10 only for kept eigenvalues below 2e-6 lambda_max."""
+    ob = np.asarray(ob)
+    T = ob @ ob.T if ob.shape[0] < ob.shape[1] else ob.T @ ob
+    w = np.linalg.eigvalsh(T)
+    lam = np.abs(w).max()
+    cut = rtol * lam
+    assert not ((np.abs(w) > cut / 1e3) & (np.abs(w) < cut * 1e3)).any(), "spectrum has no gap at the cut-off"
+    kept = np.abs(w)[np.abs(w) >= cut * 1e3]
+    return max(1e-10, 200 * np.finfo(np.float64).eps * lam / kept.min())
+
+
 def to_np(t):
     return t.detach().cpu().numpy()
 

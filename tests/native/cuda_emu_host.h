@@ -12,6 +12,8 @@
 typedef void* cudaStream_t;
 
 #define QTX_LAUNCH(kernel, grid, block, stream, ...) emu_launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define QTX_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+  emu_launch((grid), (block), [&] { kernel(__VA_ARGS__); }, (smem))
 
 namespace qtx {
 inline char g_emu_error[512] = "";

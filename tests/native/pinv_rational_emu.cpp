@@ -3,6 +3,7 @@
 // qtx_sym_absmax_eig / qtx_pinv_rational_partial / qtx_dd_sum_scale run as they are; the emu_* wrappers below run
 // single kernels with a chosen launch geometry.  TEST INFRASTRUCTURE ONLY.
 #define QTX_HOST_EMULATION 1
+#include "zldlt.cu"  // the own-kernel route of pinv_rational.cu (qtx_pinv_ldlt_partial) links against it
 #include "pinv_rational.cu"
 
 // what the entry points of pinv_rational.cu link against inside the library

@@ -66,8 +66,13 @@ def test_config_e_forward_and_jacobian_vs_oracle(qtx):
     check("E forward log psi vs float64 evaluation of the same weights", np.abs(lg - l64).max() / scale, 1e-5)
     O = to_np(state.jacobian(st))
     Oo = net.jacobian(s)
+    O64 = _f64_twin(net).jacobian(s)
     assert O.shape == Oo.shape == (16, 1047552)
-    check("E jacobian vs float32 oracle", np.abs(O - Oo).max() / np.abs(Oo).max(), 1e-5)
+    scale = np.abs(O64).max()
+    noise = np.abs(Oo - O64).max() / scale  # what float32 rounding does to the oracle's own 16-layer backward pass
+    check("E jacobian vs float64 evaluation (bar: 1e-5 or the float32 oracle's own distance from it)",
+          np.abs(O - O64).max() / scale, max(1e-5, 2 * noise))
+    check("E jacobian vs float32 oracle", np.abs(O - Oo).max() / scale, max(1e-5, 3 * noise))
 
 
 def test_config_e_sweep_and_oloc_vs_oracle(qtx):
@@ -180,6 +185,14 @@ def test_config_d_projected_complex_state_vs_oracle(qtx):
     (24 images): amplitude, local energies and the stacked Jacobian on a few samples."""
     from tests.test_complex_gpu import make_model
 
+    qtx.set_default_dtype(torch.complex128)  # tutorials/triangular.ipynb cell 2
+    try:
+        _config_d(qtx, make_model)
+    finally:
+        qtx.set_default_dtype(torch.float64)
+
+
+def _config_d(qtx, make_model):
     lat, olat = lattice_pair(qtx, "triangular", 12, (72, 72))
     model, net = make_model(qtx, 12, 4, 8, torch.float32, "exp", seed=41)
     S = qtx.symmetry

@@ -171,6 +171,11 @@ class _FakeLib:
             def qtx_pinv_rational_workspace_size(n):
                 return 64
 
+            @staticmethod
+            def qtx_pinv_ldlt_workspace_size(n, nshifts):
+                assert 1 <= nshifts <= 3
+                return 64 * nshifts
+
         return L()
 
     @staticmethod
@@ -184,11 +189,11 @@ class _FakeLib:
     def call(self, name, *a):
         pr = self.pr
         self.calls.append(name)
-        if name == "qtx_sym_absmax_eig":
-            T, n, first, steps, lam, ws, wsz, stream = a
+        if name in ("qtx_sym_absmax_eig", "qtx_sym_absmax_eig_ws"):
+            T, n, first, steps, lam, ws, wsz = a[:7]
             assert T.shape == (n, n) and 0 <= first < steps
             lam[0] = pr.abs_max_eigenvalue(T.numpy(), steps=steps)
-        elif name == "qtx_pinv_rational_partial":
+        elif name in ("qtx_pinv_rational_partial", "qtx_pinv_ldlt_partial"):
             T, n, b, rtol, atol, lam, mask, refine, ydd, accumulate, info, ws, wsz, stream = a
             assert ydd.shape == (2, n) and accumulate == 0 and 0 < mask < 8
             which = [k for k in range(3) if (mask >> k) & 1]
@@ -231,7 +236,7 @@ def _rational_worker(rank, world, port, out):
         gathered = [torch.empty_like(y) for _ in range(world)]
         dist.all_gather(gathered, y)
         same = all(torch.equal(g, gathered[0]) for g in gathered)
-        nparts = fake.calls.count("qtx_pinv_rational_partial")
+        nparts = fake.calls.count("qtx_pinv_ldlt_partial")  # the default route: the library's own LDL^T kernels
         counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(counts, torch.tensor([nparts]))
         if rank == 0:

@@ -196,6 +196,10 @@ def _entry(emu):
     emu.qtx_sym_absmax_eig.argtypes = [vp, i64, i32, i32, vp, vp, sz, vp]
     emu.qtx_pinv_rational_partial.argtypes = [vp, i64, vp, d, d, vp, i32, i32, vp, i32, vp, vp, sz, vp]
     emu.qtx_dd_sum_scale.argtypes = [vp, i32, i64, d, vp, vp]
+    emu.qtx_pinv_ldlt_workspace_size.restype = sz
+    emu.qtx_pinv_ldlt_workspace_size.argtypes = [i64, i32]
+    emu.qtx_sym_absmax_eig_ws.argtypes = [vp, i64, i32, i32, vp, vp, sz, i32, vp]
+    emu.qtx_pinv_ldlt_partial.argtypes = emu.qtx_pinv_rational_partial.argtypes
     emu.emu_last_error.restype = C.c_char_p
     return emu
 
@@ -204,17 +208,25 @@ def _vp(a):
     return a.ctypes.data
 
 
-def _entry_solve(emu, T, b, rtol, atol=0.0, masks=(7,), refine=4, accumulate_split=False):
-    """quantax_b200.optimizer.pinv_rational_solve through the C entry points of the emulated library."""
+def _entry_solve(emu, T, b, rtol, atol=0.0, masks=(7,), refine=4, accumulate_split=False, route="rational"):
+    """quantax_b200.optimizer.pinv_rational_solve through the C entry points of the emulated library; route "ldlt" =
+    the library's own LDL^T kernels (csrc/zldlt.cu, the default of the product), "rational" = the cuSOLVER LU calls."""
     n = T.shape[0]
-    wsz = emu.qtx_pinv_rational_workspace_size(n)
+    ldlt = route == "ldlt"
+    nsh = max(1, max(bin(m).count("1") for m in masks))
+    wsz = emu.qtx_pinv_ldlt_workspace_size(n, nsh) if ldlt else emu.qtx_pinv_rational_workspace_size(n)
     assert wsz > 0
     ws = np.full(wsz + 8, 0x5A, dtype=np.uint8)  # guard bytes behind the promised size
     lam = np.zeros(1)
     done = 0
     for upto in pr.lanczos_stages(n):
-        assert emu.qtx_sym_absmax_eig(_vp(T), n, done, upto, _vp(lam), _vp(ws), wsz, None) == 0, emu.emu_last_error()
+        if ldlt:
+            rc = emu.qtx_sym_absmax_eig_ws(_vp(T), n, done, upto, _vp(lam), _vp(ws), wsz, nsh, None)
+        else:
+            rc = emu.qtx_sym_absmax_eig(_vp(T), n, done, upto, _vp(lam), _vp(ws), wsz, None)
+        assert rc == 0, emu.emu_last_error()
         done = upto
+    partial = emu.qtx_pinv_ldlt_partial if ldlt else emu.qtx_pinv_rational_partial
     parts = np.zeros((len(masks), 2, n))
     info = np.full(1, 77, dtype=np.int32)
     for q, mask in enumerate(masks):
@@ -224,14 +236,14 @@ def _entry_solve(emu, T, b, rtol, atol=0.0, masks=(7,), refine=4, accumulate_spl
             first = True
             for k in range(3):
                 if (mask >> k) & 1:
-                    rc = emu.qtx_pinv_rational_partial(_vp(T), n, _vp(b), rtol, atol, _vp(lam), 1 << k, refine,
-                                                       _vp(parts[q]), 0 if first else 1, _vp(info), _vp(ws), wsz, None)
+                    rc = partial(_vp(T), n, _vp(b), rtol, atol, _vp(lam), 1 << k, refine,
+                                 _vp(parts[q]), 0 if first else 1, _vp(info), _vp(ws), wsz, None)
                     assert rc == 0, emu.emu_last_error()
                     first = False
         else:
             parts[q] = 1e300  # accumulate = 0 must overwrite
-            rc = emu.qtx_pinv_rational_partial(_vp(T), n, _vp(b), rtol, atol, _vp(lam), mask, refine, _vp(parts[q]), 0,
-                                               _vp(info), _vp(ws), wsz, None)
+            rc = partial(_vp(T), n, _vp(b), rtol, atol, _vp(lam), mask, refine, _vp(parts[q]), 0,
+                         _vp(info), _vp(ws), wsz, None)
             assert rc == 0, emu.emu_last_error()
         assert info[0] == 0
     assert (ws[wsz:] == 0x5A).all(), "wrote behind the workspace"
@@ -240,16 +252,43 @@ def _entry_solve(emu, T, b, rtol, atol=0.0, masks=(7,), refine=4, accumulate_spl
     return y, float(lam[0])
 
 
+@pytest.mark.parametrize("route", ["rational", "ldlt"])
 @pytest.mark.parametrize("ns,npar,decay,rtol", [(40, 300, 3, -1.0), (33, 333, 1, 1e-10), (17, 100, 6, 1e-8)])
-def test_entry_points_equal_oracle_and_eigenvalue_route(emu, ns, npar, decay, rtol):
+def test_entry_points_equal_oracle_and_eigenvalue_route(emu, ns, npar, decay, rtol, route):
     emu = _entry(emu)
     A, b = _problem(ns, npar, decay, seed=ns + 1)
     T = np.ascontiguousarray(A @ A.T)
-    y, lam = _entry_solve(emu, T, b, rtol)
+    y, lam = _entry_solve(emu, T, b, rtol, route=route)
     r = None if rtol < 0 else rtol  # rtol < 0 selects the float64 default 1e-12
     assert abs(lam - np.abs(np.linalg.eigvalsh(T)).max()) <= 1e-12 * lam
     assert _rel(A.T @ y, A.T @ pr.pinv_rational_solve(T, b, rtol=r)) < 1e-11
     assert _rel(A.T @ y, A.T @ osolver.minsr_pinv_eig(T, b, rtol=r)) < (1e-10 if rtol > 0 else 1e-9)
+
+
+def test_ldlt_route_rank_split_accumulate_zero_matrix_and_errors(emu):
+    """qtx_pinv_ldlt_partial (own LDL^T kernels): rank split, accumulate, degenerate and refused inputs."""
+    emu = _entry(emu)
+    A, b = _problem(20, 100, 4, seed=3)
+    T = np.ascontiguousarray(A @ A.T)
+    y0, _ = _entry_solve(emu, T, b, 1e-12)  # the LU route
+    y1, _ = _entry_solve(emu, T, b, 1e-12, route="ldlt")
+    y2, _ = _entry_solve(emu, T, b, 1e-12, masks=(0b101, 0b010), route="ldlt")
+    y8, _ = _entry_solve(emu, T, b, 1e-12, masks=(1, 2, 4, 0, 0, 0, 0, 0), route="ldlt")
+    ya, _ = _entry_solve(emu, T, b, 1e-12, accumulate_split=True, route="ldlt")
+    assert _rel(A.T @ y1, A.T @ y0) < 1e-12
+    assert _rel(A.T @ y2, A.T @ y1) < 1e-13 and _rel(A.T @ y8, A.T @ y1) < 1e-13 and np.array_equal(ya, y1)
+    n = T.shape[0]
+    wsz = emu.qtx_pinv_ldlt_workspace_size(n, 3)
+    assert emu.qtx_pinv_ldlt_workspace_size(n, 4) == 0 and emu.qtx_pinv_ldlt_workspace_size(n, 1) < wsz
+    ws, lam, ydd, info = np.zeros(wsz, dtype=np.uint8), np.ones(1), np.zeros((2, n)), np.zeros(1, dtype=np.int32)
+    args = lambda rtol, atol, mask, size: (_vp(T), n, _vp(b), rtol, atol, _vp(lam), mask, 4, _vp(ydd), 0, _vp(info),
+                                           _vp(ws), size, None)
+    assert emu.qtx_pinv_ldlt_partial(*args(0.0, 0.0, 7, wsz)) == -3 and b"plain inverse" in emu.emu_last_error()
+    assert emu.qtx_pinv_ldlt_partial(*args(1e-12, 0.0, 7, emu.qtx_pinv_ldlt_workspace_size(n, 1))) == -1
+    assert emu.qtx_pinv_ldlt_partial(*args(1e-12, 0.0, 8, wsz)) == -1
+    Z = np.zeros((6, 6))
+    yz, lz = _entry_solve(emu, Z, np.arange(1.0, 7.0), 1e-12, route="ldlt")
+    assert lz == 0.0 and not yz.any()
 
 
 def test_entry_points_rank_split_accumulate_and_errors(emu):
@@ -283,8 +322,10 @@ def test_entry_points_against_the_references_own_solver_code(emu):
     emu = _entry(emu)
     gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_hotpath.npz"))
     A, b = gold["solver/minnorm/A"], gold["solver/minnorm/b"]
-    y, _ = _entry_solve(emu, np.ascontiguousarray(A @ A.T), np.ascontiguousarray(b), 1e-10)
-    assert _rel(A.T @ y, gold["solver/minnorm/auto_pinv_eig_snr0.0"]) < 1e-9
-    A, b = gold["solver/lstsq/A"], gold["solver/lstsq/b"]
-    x, _ = _entry_solve(emu, np.ascontiguousarray(A.T @ A), np.ascontiguousarray(A.T @ b), 1e-10)
-    assert _rel(x, gold["solver/lstsq/auto_pinv_eig_snr0.0"]) < 1e-9
+    for route in ("rational", "ldlt"):
+        A, b = gold["solver/minnorm/A"], gold["solver/minnorm/b"]
+        y, _ = _entry_solve(emu, np.ascontiguousarray(A @ A.T), np.ascontiguousarray(b), 1e-10, route=route)
+        assert _rel(A.T @ y, gold["solver/minnorm/auto_pinv_eig_snr0.0"]) < 1e-9
+        A, b = gold["solver/lstsq/A"], gold["solver/lstsq/b"]
+        x, _ = _entry_solve(emu, np.ascontiguousarray(A.T @ A), np.ascontiguousarray(A.T @ b), 1e-10, route=route)
+        assert _rel(x, gold["solver/lstsq/auto_pinv_eig_snr0.0"]) < 1e-9

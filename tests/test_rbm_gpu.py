@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import models as omodels, operator as oop, sampler as osmp, sites as osites, solver as osolver
-from tests.gpu_util import chains_equal, check, lattice_pair, make_rbm, to_np
+from tests.gpu_util import chains_equal, check, lattice_pair, make_rbm, sr_step_tolerance, to_np
 
 pytestmark = pytest.mark.gpu
 
@@ -336,7 +336,9 @@ def test_rbm_conv_matches_oracle(qtx, kind, L, shape, nup, tmp_path):
     assert np.abs(to_np(opt._Eloc) - Eo).max() <= 1e-10 * np.abs(Eo).max()
     xo, eo, vo = osolver.sr_step(net.jacobian(sc), Eo, np.ones(ns))
     assert abs(opt.energy - eo) <= 1e-10 * abs(eo)
-    check("RBM_Conv SR step vs oracle", np.linalg.norm(step - xo) / np.linalg.norm(xo), 1e-10)
+    # 1e-10 unless the kept eigenvalues of this 32-row system reach below 2e-6 lambda_max (then eps * condition)
+    check("RBM_Conv SR step vs oracle", np.linalg.norm(step - xo) / np.linalg.norm(xo),
+          sr_step_tolerance(osolver.obar(net.jacobian(sc), np.ones(ns))[0]))
     f = tmp_path / "rbmconv.eqx"
     state.save(f)
     state2 = qtx.state.Variational(qtx.model.RBM_Conv(3, dtype=torch.float64), param_file=f)
