@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import solver as osolver
-from tests.gpu_util import to_np
+from tests.gpu_util import check,  to_np
 
 pytestmark = pytest.mark.gpu
 
@@ -249,16 +249,18 @@ def _centred_problem(ns, npar, decay, kind, seed):
     return A / np.sqrt(ns), rng.standard_normal(ns) / np.sqrt(ns)
 
 
+@pytest.mark.parametrize("method", ["ldlt", "rational"])  # own LDL^T kernels (default) / cuSOLVER LU (cross-check)
 @pytest.mark.parametrize("ns,npar,decay,kind,rtol", [(96, 700, 3, "col", None), (130, 333, 1, "col", 1e-10),
-                                                     (64, 640, 6, "svd", 1e-8), (300, 1200, 2, "svd", 1e-3)])
-def test_rational_pseudo_inverse_equals_the_eigenvalue_route(qtx, ns, npar, decay, kind, rtol):
+                                                     (64, 640, 6, "svd", 1e-8), (300, 1200, 2, "svd", 1e-3),
+                                                     (1000, 3000, 4, "col", 1e-9)])
+def test_rational_pseudo_inverse_equals_the_eigenvalue_route(qtx, ns, npar, decay, kind, rtol, method):
     from oracle import pinv_rational as pr
     from quantax_b200.optimizer import pinv_eig_solve, pinv_rational_solve
 
     A, b = _centred_problem(ns, npar, decay, kind, ns)
     T = A @ A.T
     Tt, bt = torch.from_numpy(T).cuda(), torch.from_numpy(b).cuda()
-    y, info = pinv_rational_solve(Tt, bt, rtol, 0.0)
+    y, info = pinv_rational_solve(Tt, bt, rtol, 0.0, method=method)
     assert int(info.item()) == 0
     assert np.array_equal(to_np(Tt), T)  # T is not overwritten
     y = to_np(y)
@@ -277,9 +279,10 @@ def test_rational_pseudo_inverse_at_the_cutoff_beats_eigh(qtx):
     T = A @ A.T
     xt = A.T @ _exact(T, b, 1e-12)
     Tt, bt = torch.from_numpy(T).cuda(), torch.from_numpy(b).cuda()
-    e_rat = _rel(A.T @ to_np(pinv_rational_solve(Tt, bt, None, 0.0)[0]), xt)
     e_eig = _rel(A.T @ to_np(pinv_eig_solve(Tt.clone(), bt, None, 0.0)[0]), xt)
-    assert e_rat < 1e-8 and e_rat < e_eig
+    for method in ("ldlt", "rational"):
+        e_rat = _rel(A.T @ to_np(pinv_rational_solve(Tt, bt, None, 0.0, method=method)[0]), xt)
+        assert e_rat < 1e-8 and e_rat < e_eig, (method, e_rat, e_eig)
 
 
 def test_minsr_step_through_the_rational_route(qtx, monkeypatch):
@@ -287,11 +290,40 @@ def test_minsr_step_through_the_rational_route(qtx, monkeypatch):
 
     A, b = _problem(200, 3000, seed=5)
     At, bt = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
-    x_eig = to_np(qopt.auto_pinv_eig(rtol=1e-10)(At.clone(), bt))
-    monkeypatch.setattr(qopt, "PINV_METHOD", "rational")
-    x_rat = to_np(qopt.auto_pinv_eig(rtol=1e-10)(At.clone(), bt))
     ref = osolver.auto_pinv_eig(A, b, rtol=1e-10)
-    assert _rel(x_rat, ref) < 1e-9 and _rel(x_rat, x_eig) < 1e-9
+    monkeypatch.setattr(qopt, "PINV_METHOD", "eigh")
+    x_eig = to_np(qopt.auto_pinv_eig(rtol=1e-10)(At.clone(), bt))
+    for method in ("ldlt", "rational"):
+        monkeypatch.setattr(qopt, "PINV_METHOD", method)
+        x_rat = to_np(qopt.auto_pinv_eig(rtol=1e-10)(At.clone(), bt))
+        assert _rel(x_rat, ref) < 1e-9 and _rel(x_rat, x_eig) < 1e-9, method
     # SNR damping needs the eigen-directions: it stays on the eigenvalue route
     x_snr = to_np(qopt.auto_pinv_eig(rtol=1e-10, tol_snr=1.0)(At.clone(), bt))
     assert _rel(x_snr, osolver.auto_pinv_eig(A, b, rtol=1e-10, tol_snr=1.0)) < 1e-8
+
+
+def test_ldlt_factorisation_and_solves_at_ragged_and_large_sizes(qtx):
+    """csrc/zldlt.cu through qtx_pinv_ldlt_partial: sizes off the 64-row block, single shifts (the rank split), more
+    block rows than SMs' worth of resident CTAs is not needed -- the ticket order makes the wavefront deadlock-free."""
+    from quantax_b200 import _lib
+    from quantax_b200.optimizer import _pinv_workspace, pinv_rational_solve, sym_absmax_eig
+
+    for n, npar, seed in ((1, 4, 0), (63, 200, 1), (65, 300, 2), (129, 500, 3), (777, 2500, 4), (2048, 6000, 5)):
+        A, b = _centred_problem(n, npar, 3, "col", seed)
+        T = A @ A.T
+        Tt, bt = torch.from_numpy(T).cuda(), torch.from_numpy(b).cuda()
+        y, info = pinv_rational_solve(Tt, bt, 1e-9, 0.0, method="ldlt")
+        assert int(info.item()) == 0
+        ref = osolver.minsr_pinv_eig(T, b, rtol=1e-9)
+        check(f"ldlt route n={n}", _rel(A.T @ to_np(y), A.T @ ref), 1e-10)
+        # one shift per call, accumulated: what the ranks of a replicated solve do
+        lam = sym_absmax_eig(Tt, method="ldlt", nshifts=1)
+        ws, wsz = _pinv_workspace(n, "ldlt", 1)
+        ydd = torch.zeros((2, n), dtype=torch.float64, device="cuda")
+        inf = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for k in range(3):
+            _lib.call("qtx_pinv_ldlt_partial", _lib.ptr(Tt), n, _lib.ptr(bt), 1e-9, 0.0, _lib.ptr(lam), 1 << k, 3,
+                      _lib.ptr(ydd), int(k > 0), _lib.ptr(inf), _lib.ptr(ws), wsz, _lib.stream())
+            assert int(inf.item()) == 0
+        y1 = (ydd[0] + ydd[1]) / 3.0
+        check(f"ldlt route, one shift per call n={n}", _rel(A.T @ to_np(y1), A.T @ to_np(y)), 1e-13)
