@@ -169,14 +169,17 @@ def sgd_solver(A, b):
     return A.conj().T @ b / b.shape[0]
 
 
-def sr_step(Omat, Eloc, rw, rtol=None, atol=0.0, real_to_complex=False):
-    """optimizer/sr.py:90-123, imag_time=True.  ``real_to_complex`` (real parameters, complex output,
-    sr.py:99-104): the real and imaginary parts of Obar and Ebar are stacked as 2 Ns rows."""
+def sr_step(Omat, Eloc, rw, rtol=None, atol=0.0, real_to_complex=False, imag_time=True):
+    """optimizer/sr.py:90-123.  ``real_to_complex`` (real parameters, complex output, sr.py:99-104): the real and
+    imaginary parts of Obar and Ebar are stacked as 2 Ns rows; real-time evolution (``imag_time=False``) stacks
+    [-Im Ebar; Re Ebar] instead (sr.py:103-104)."""
     eb, energy, var = ebar(Eloc, rw)
     ob, _ = obar(Omat, rw)
     if real_to_complex:
         ob = np.concatenate([ob.real, ob.imag], axis=0)
-        eb = np.concatenate([eb.real, eb.imag])
+        eb = np.concatenate([eb.real, eb.imag]) if imag_time else np.concatenate([-eb.imag, eb.real])
+    elif not imag_time:
+        raise NotImplementedError("real output: Ebar *= 1j needs complex parameters (out of scope)")
     return auto_pinv_eig(ob, eb, rtol, atol), energy, var
 
 

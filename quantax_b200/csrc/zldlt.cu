@@ -1,22 +1,26 @@
 // Complex-symmetric LDL^T factorisation and triangular solves for the shifted systems (T - z I) x = b of the soft
 // pseudo-inverse (pinv_rational.cu; quantax/optimizer/solver.py:94-111,142-146 compute the same y = f(T) b from eigh).
-// Own kernels, FP64 FMA pipe, no library call.
+// Own kernels on the FP64 pipes (DMMA m8n8k4 for the trailing updates), no library call.
 //
 // M = T - z I is complex SYMMETRIC (not Hermitian) and its field of values is the segment [-z, lambda_max - z], which
 // stays at distance Im z > 0 from the origin: e^{i phi} M has a positive definite Hermitian part for a suitable phi, so
 // the factorisation M = L D L^T (L unit lower triangular, D diagonal, both complex) needs NO pivoting.  Only the lower
 // triangle of M is read and written: L below the diagonal, D on it.
 //
-// Right-looking, block size NB = 64, three launches per block column:
-//   zldlt_diag_kernel   : one CTA factorises the NB x NB diagonal block in shared memory;
-//   zldlt_panel_kernel  : CTA per 64-row tile below it: W = A21 L11^-T (column sweep in shared memory), L21 = W D^-1;
-//                         L21 goes back into M, W and L21 also into k-major scratch panels WT / LT [NB][n];
-//   zldlt_update_kernel : CTA per 64 x 64 tile of the lower triangle of the trailing matrix: C -= W L21^T, operands
-//                         staged k-major in shared memory (conflict-free 16-byte loads), 4 x 4 complex register tile
-//                         per thread (64 DFMA per k step and thread).
+// Right-looking with look-ahead, block size NB = 64, ONE launch per block column (zldlt_step_kernel):
+//   * every CTA owns a 64 x 64 tile of the lower triangle of the trailing matrix and applies C -= W L21^T of the
+//     previous block column: operands staged as real / imaginary planes in shared memory, FP64 tensor-core MMAs
+//     (mma.sync m8n8k4, four per complex 8 x 8 x 4 product), accumulators in registers;
+//   * the CTA of tile (0, 0) then factorises its tile -- the NEXT diagonal block -- in registers (one barrier per
+//     column) and publishes L11, D and 1 / D;
+//   * the CTAs of the tiles (I, 0) below it wait for that flag and turn their updated tiles into the next panel:
+//     W = A21 L11^-T by a column sweep in registers, L21 = W D^-1; L21 goes into M, W into a panel buffer.
+//   Tiles are handed out through an atomic ticket, column tiles first, so the diagonal CTA is always running when
+//   somebody waits for it; the rest of the trailing update hides the panel's latency.
 // Solves L D L^T x = r run as two persistent wavefront kernels (ztrsv_kernel<false/true>): CTA per 64-row block,
-// block rows are handed out in dependency order through an atomic ticket, a CTA consumes the solution blocks it
-// depends on as soon as their flag is published, solves its diagonal block and publishes its own.
+// block rows handed out in dependency order through an atomic ticket, a CTA consumes the solution blocks it depends
+// on as soon as their flag is published, multiplies by the inverse of its diagonal block (zldlt_diaginv_kernel,
+// all blocks in parallel after the factorisation) and publishes its own.
 #ifdef QTX_HOST_EMULATION
 #include "cuda_emu.h"
 #include "cuda_emu_host.h"
@@ -32,15 +36,18 @@
 namespace qtx {
 
 #ifdef QTX_HOST_EMULATION
-constexpr int kNB = 8, kR = 2;  // small blocks: a few std::threads per CTA, several block columns at n ~ 40
+constexpr int kNB = 16, kWR = 1, kWC = 2;  // small blocks, two emulated warps: several block columns at n ~ 40
 #else
-constexpr int kNB = 64, kR = 4;
+constexpr int kNB = 64, kWR = 2, kWC = 4;  // 8 warps, warp tile 32 x 16
 #endif
-constexpr int kTB = kNB / kR;          // threads per tile edge
-constexpr int kThreads = kTB * kTB;    // 256
-constexpr int kPad = kNB + 1;          // row pitch (complex numbers) of the row-major shared-memory tiles
-constexpr int kKH = kNB / 2;           // k extent staged per pass of the update kernel
-constexpr int kTPR = kThreads / kNB;   // threads cooperating on one row / column of a 64 x 64 block product
+constexpr int kThreads = 32 * kWR * kWC;
+constexpr int kWTR = kNB / kWR, kWTC = kNB / kWC;  // warp tile
+constexpr int kFI = kWTR / 8, kFJ = kWTC / 8;      // 8 x 8 accumulator fragments per warp tile
+constexpr int kPad = kNB + 1;                      // row pitch (complex numbers) of the row-major shared-memory tiles
+constexpr int kKC = kNB / 2;                       // k extent staged per pass of the trailing update
+constexpr int kKP = kKC + 4;                       // pitch (doubles) of an operand plane: conflict-free fragment loads
+constexpr int kTPR = kThreads / kNB;               // threads cooperating on one row / column of a block product
+static_assert(kKC % 4 == 0 && kWTR % 8 == 0 && kWTC % 8 == 0, "tile shapes");
 
 typedef cuDoubleComplex cplx;
 
@@ -65,148 +72,328 @@ __device__ __forceinline__ cplx crecip(cplx d) {  // 1 / d, scaled against overf
   const double q = 1.0 / ((a * a + b * b) * s);
   return cmake(a * q, -b * q);
 }
+__device__ __forceinline__ unsigned ld_flag(const unsigned* p) { return *(const volatile unsigned*)p; }
+__device__ __forceinline__ cplx ld_cg(const cplx* p) {  // a value another CTA of this launch has just published
+#ifdef QTX_HOST_EMULATION
+  return *p;
+#else
+  const double2 t = __ldcg(reinterpret_cast<const double2*>(p));
+  return cmake(t.x, t.y);
+#endif
+}
+__device__ __forceinline__ void spin_until_set(const unsigned* flag) {  // one thread; bounded: trap, never hang
+  unsigned long long spins = 0;
+  while (ld_flag(flag) == 0u) {
+    if (++spins > (1ull << 34)) {
+#ifndef QTX_HOST_EMULATION
+      __trap();
+#endif
+    }
+  }
+}
+__device__ __forceinline__ void publish(unsigned* flag) {
+#ifdef QTX_HOST_EMULATION
+  *flag = 1u;
+#else
+  atomicExch(flag, 1u);
+#endif
+}
+__device__ __forceinline__ void fence_all() {
+#ifndef QTX_HOST_EMULATION
+  __threadfence();
+#endif
+}
+
+// D (8 x 8) += A (8 x 4, row) B (4 x 8, col) in float64: lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and
+// C[l / 4][2 (l % 4) + {0, 1}]  (PTX mma.sync.m8n8k4.f64)
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+#ifdef QTX_HOST_EMULATION
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < 4; ++k) {
+    const double ak = __shfl_sync(FULL, a, g * 4 + k);
+    const double b0 = __shfl_sync(FULL, b, (2 * q) * 4 + k);
+    const double b1 = __shfl_sync(FULL, b, (2 * q + 1) * 4 + k);
+    s0 += ak * b0;
+    s1 += ak * b1;
+  }
+  c0 += s0;
+  c1 += s1;
+#else
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+#endif
+}
 
 // ---- factorisation ----------------------------------------------------------------------------------------------
-// diagonal block [k0, k0 + nb): in place L11 (strictly lower) and D1 (diagonal).  A zero pivot sets info = its 1-based
-// index (first one wins) and is replaced by 1 so that the factorisation continues with finite numbers.
-__global__ void __launch_bounds__(kThreads) zldlt_diag_kernel(cplx* __restrict__ M, int64_t n, int64_t k0, int nb,
-                                                             int32_t* __restrict__ info) {
-  QTX_DYN_SMEM(cplx, sm);
-  cplx* A = sm;                  // [kNB][kPad]
-  cplx* wv = sm + kNB * kPad;    // [kNB]
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < nb * nb; idx += kThreads) {
-    const int i = idx / nb, j = idx % nb;
-    if (j <= i) A[i * kPad + j] = M[(k0 + i) * n + k0 + j];
-  }
-  __syncthreads();
+// A 64 x 64 complex tile lives in the registers of the CTA in the accumulator layout of the MMAs: thread (warp w,
+// lane l) holds, for fragment (fi, fj) and e in {0, 1}, the element
+//   row = (w / kWC) kWTR + 8 fi + l / 4,   col = (w % kWC) kWTC + 8 fj + 2 (l % 4) + e.
+struct TilePos {
+  int row0, col0;  // row of fragment row 0, column of fragment column 0, e = 0
+  __device__ __forceinline__ int row(int fi) const { return row0 + 8 * fi; }
+  __device__ __forceinline__ int col(int fj, int e) const { return col0 + 8 * fj + e; }
+};
+__device__ __forceinline__ TilePos tile_pos() {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  return {(w / kWC) * kWTR + (l >> 2), (w % kWC) * kWTC + 2 * (l & 3)};
+}
+
+// in-register LDL^T of the leading nb x nb block of the tile (lower triangle; the upper triangle of the registers is
+// never read).  wv: shared [2][kNB] complex, dinv_s: shared [kNB].  One barrier per column.
+__device__ __forceinline__ void tile_ldlt(double (&tr)[kFI][kFJ][2], double (&ti)[kFI][kFJ][2], const TilePos tp, int nb,
+                                          cplx* wv, cplx* dinv_s, int32_t* info, int64_t global_col0) {
   for (int k = 0; k < nb; ++k) {
-    cplx d = A[k * kPad + k];
-    if (d.x == 0.0 && d.y == 0.0) {
-      if (tid == 0 && info[0] == 0) info[0] = (int32_t)(k0 + k + 1);
-      d = cmake(1.0, 0.0);
-    }
+    cplx* w = wv + (k & 1) * kNB;
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (tp.col(fj, e) == k) {
+#pragma unroll
+          for (int fi = 0; fi < kFI; ++fi) w[tp.row(fi)] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
+        }
+    __syncthreads();
+    cplx d = w[k];
+    const bool zero = (d.x == 0.0 && d.y == 0.0);
+    if (zero) d = cmake(1.0, 0.0);  // reported below; the factorisation continues with finite numbers
     const cplx inv = crecip(d);
-    const int m = nb - k - 1;
-    if (tid < m) {
-      const int i = k + 1 + tid;
-      const cplx w = A[i * kPad + k];
-      wv[i] = w;
-      A[i * kPad + k] = cmul_(w, inv);
+#pragma unroll
+    for (int fi = 0; fi < kFI; ++fi) {
+      const int i = tp.row(fi);
+      const cplx li = cmul_(w[i], inv);
+#pragma unroll
+      for (int fj = 0; fj < kFJ; ++fj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = tp.col(fj, e);
+          if (i == k && j == k) {
+            tr[fi][fj][e] = d.x;
+            ti[fi][fj][e] = d.y;
+            dinv_s[k] = inv;
+            if (zero && info[0] == 0) info[0] = (int32_t)(global_col0 + k + 1);
+          } else if (j == k && i > k && i < nb) {
+            tr[fi][fj][e] = li.x;
+            ti[fi][fj][e] = li.y;
+          } else if (j > k && j <= i && i < nb) {
+            const cplx wj = w[j];
+            tr[fi][fj][e] -= li.x * wj.x - li.y * wj.y;
+            ti[fi][fj][e] -= li.x * wj.y + li.y * wj.x;
+          }
+        }
     }
-    __syncthreads();  // also orders the read of A[k][k] above against the write-back of the patched pivot below
-    if (tid == 0) A[k * kPad + k] = d;
-    for (int idx = tid; idx < m * m; idx += kThreads) {
-      const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-      if (j <= i) cfms(A[i * kPad + j], A[i * kPad + k], wv[j]);
-    }
-    __syncthreads();
   }
-  for (int idx = tid; idx < nb * nb; idx += kThreads) {
-    const int i = idx / nb, j = idx % nb;
-    if (j <= i) M[(k0 + i) * n + k0 + j] = A[i * kPad + j];
-  }
+  __syncthreads();  // dinv_s complete
 }
 
-// rows [k0 + nb, n) of block column [k0, k0 + nb): W = A21 L11^-T, L21 = W D1^-1
-__global__ void __launch_bounds__(kThreads) zldlt_panel_kernel(cplx* __restrict__ M, int64_t n, int64_t k0, int nb,
-                                                              cplx* __restrict__ WT, cplx* __restrict__ LT) {
-  QTX_DYN_SMEM(cplx, sm);
-  cplx* L11 = sm;               // [kNB][kPad]: strictly lower = L, diagonal = D
-  cplx* X = sm + kNB * kPad;    // [kNB][kPad]: row tile of A21 -> W
-  const int tid = threadIdx.x;
-  const int64_t i0 = k0 + nb + (int64_t)blockIdx.x * kNB;
-  const int nr = (int)((n - i0) < kNB ? (n - i0) : kNB);
-  for (int idx = tid; idx < nb * nb; idx += kThreads) {
-    const int i = idx / nb, j = idx % nb;
-    if (j <= i) L11[i * kPad + j] = M[(k0 + i) * n + k0 + j];
-  }
-  for (int idx = tid; idx < nr * nb; idx += kThreads) {
-    const int r = idx / nb, c = idx % nb;
-    X[r * kPad + c] = M[(i0 + r) * n + k0 + c];
-  }
-  __syncthreads();
-  for (int c = 0; c + 1 < nb; ++c) {  // column c of X is final (= W[:, c]); eliminate it from the columns behind it
-    const int rest = nb - c - 1;
-    for (int idx = tid; idx < nr * rest; idx += kThreads) {
-      const int r = idx % nr, c2 = c + 1 + idx / nr;
-      cfms(X[r * kPad + c2], X[r * kPad + c], L11[c2 * kPad + c]);
-    }
+// in-register panel solve: the tile holds rows of A21 (nb columns); on exit it holds W = A21 L11^-T.
+// Ls: shared [kNB][kPad] with L11 strictly below the diagonal; xc: shared [2][kNB].
+__device__ __forceinline__ void tile_panel(double (&tr)[kFI][kFJ][2], double (&ti)[kFI][kFJ][2], const TilePos tp, int nb,
+                                           const cplx* Ls, cplx* xc) {
+  for (int c = 0; c + 1 < nb; ++c) {
+    cplx* x = xc + (c & 1) * kNB;
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (tp.col(fj, e) == c) {
+#pragma unroll
+          for (int fi = 0; fi < kFI; ++fi) x[tp.row(fi)] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
+        }
     __syncthreads();
-  }
-  for (int idx = tid; idx < nr * nb; idx += kThreads) {  // L21 into M: c fastest (row-major M)
-    const int r = idx / nb, c = idx % nb;
-    M[(i0 + r) * n + k0 + c] = cmul_(X[r * kPad + c], crecip(L11[c * kPad + c]));
-  }
-  for (int idx = tid; idx < nr * nb; idx += kThreads) {  // k-major panels: r fastest
-    const int r = idx % nr, c = idx / nr;
-    const cplx w = X[r * kPad + c];
-    WT[(int64_t)c * n + i0 + r] = w;
-    LT[(int64_t)c * n + i0 + r] = cmul_(w, crecip(L11[c * kPad + c]));
-  }
-}
-
-// trailing update: tile (I, J), J <= I, of the lower triangle behind block column [k0, k0 + nb):  C -= W L21^T
-__global__ void __launch_bounds__(kThreads, 2) zldlt_update_kernel(cplx* __restrict__ M, int64_t n, int64_t k0, int nb,
-                                                                  const cplx* __restrict__ WT,
-                                                                  const cplx* __restrict__ LT) {
-  QTX_DYN_SMEM(cplx, sm);
-  cplx* Ws = sm;                 // [kKH][kNB]  (k-major: one k = 64 consecutive rows)
-  cplx* Ls = sm + kKH * kNB;     // [kKH][kNB]
-  const int tid = threadIdx.x, tx = tid % kTB, ty = tid / kTB;
-  // linear block index -> (I, J) with J <= I
-  const unsigned b = blockIdx.x;
-  int I = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
-  while ((unsigned)I * (unsigned)(I + 1) / 2u > b) --I;
-  while ((unsigned)(I + 1) * (unsigned)(I + 2) / 2u <= b) ++I;
-  const int J = (int)(b - (unsigned)I * (unsigned)(I + 1) / 2u);
-  const int64_t t0 = k0 + nb;
-  const int64_t i0 = t0 + (int64_t)I * kNB, j0 = t0 + (int64_t)J * kNB;
-  const int nr = (int)((n - i0) < kNB ? (n - i0) : kNB), nc = (int)((n - j0) < kNB ? (n - j0) : kNB);
-  cplx acc[kR][kR];
 #pragma unroll
-  for (int a = 0; a < kR; ++a)
+    for (int fj = 0; fj < kFJ; ++fj)
 #pragma unroll
-    for (int c = 0; c < kR; ++c) acc[a][c] = cmake(0.0, 0.0);
-  for (int kh = 0; kh < nb; kh += kKH) {
-    const int kn = (nb - kh) < kKH ? (nb - kh) : kKH;
-    for (int idx = tid; idx < kKH * kNB; idx += kThreads) {
-      const int k = idx / kNB, r = idx % kNB;
-      const bool kin = k < kn;
-      Ws[idx] = (kin && r < nr) ? WT[(int64_t)(kh + k) * n + i0 + r] : cmake(0.0, 0.0);
-      Ls[idx] = (kin && r < nc) ? LT[(int64_t)(kh + k) * n + j0 + r] : cmake(0.0, 0.0);
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < kKH; ++k) {
-      cplx av[kR], bv[kR];
+      for (int e = 0; e < 2; ++e) {
+        const int j = tp.col(fj, e);
+        if (j > c && j < nb) {
+          const cplx l = Ls[j * kPad + c];
 #pragma unroll
-      for (int a = 0; a < kR; ++a) av[a] = Ws[k * kNB + ty + kTB * a];
-#pragma unroll
-      for (int c = 0; c < kR; ++c) bv[c] = Ls[k * kNB + tx + kTB * c];
-#pragma unroll
-      for (int a = 0; a < kR; ++a)
-#pragma unroll
-        for (int c = 0; c < kR; ++c) cfma_(acc[a][c], av[a], bv[c]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int a = 0; a < kR; ++a) {
-    const int r = ty + kTB * a;
-    if (r >= nr) continue;
-    const int64_t i = i0 + r;
-#pragma unroll
-    for (int c = 0; c < kR; ++c) {
-      const int cc = tx + kTB * c;
-      const int64_t j = j0 + cc;
-      if (cc < nc && j <= i) {
-        cplx v = M[i * n + j];
-        v.x -= acc[a][c].x;
-        v.y -= acc[a][c].y;
-        M[i * n + j] = v;
+          for (int fi = 0; fi < kFI; ++fi) {
+            const cplx xr = x[tp.row(fi)];
+            tr[fi][fj][e] -= xr.x * l.x - xr.y * l.y;
+            ti[fi][fj][e] -= xr.x * l.y + xr.y * l.x;
+          }
+        }
       }
+  }
+}
+
+struct StepArgs {
+  cplx* M;
+  int64_t n;
+  int64_t k0;        // block column whose panel is applied (ignored by the head launch)
+  int64_t t0;        // first row / column of the trailing matrix = block column that is factorised by this launch
+  const cplx* Wprev; // [n][kNB] row-major: W of block column k0
+  cplx* Wnext;       // [n][kNB]: W of block column t0
+  cplx* dinvg;       // [n]: 1 / D
+  unsigned* sync;    // [0] ticket, [1] flag "diagonal block t0 factorised"
+  int32_t* info;
+};
+
+// kHead: no trailing update (first block column); grid = number of row tiles.  Otherwise grid = tiles of the lower
+// triangle of the trailing matrix.
+template <bool kHead>
+__global__ void __launch_bounds__(kThreads, 2) zldlt_step_kernel(const StepArgs a) {
+  QTX_DYN_SMEM(double, smd);
+  __shared__ unsigned ticket_s;
+  const int tid = threadIdx.x;
+  if (tid == 0) ticket_s = atomicAdd(a.sync, 1u);
+  __syncthreads();
+  const int64_t n = a.n;
+  const int T = (int)((n - a.t0 + kNB - 1) / kNB);  // row tiles of the trailing matrix
+  int I, J;
+  {
+    const unsigned t = ticket_s;
+    if (kHead || t < (unsigned)T) {
+      I = (int)t;
+      J = 0;
+    } else {  // the remaining triangle (I, J >= 1), row by row
+      const unsigned b = t - (unsigned)T;
+      int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+      while ((unsigned)r * (unsigned)(r + 1) / 2u > b) --r;
+      while ((unsigned)(r + 1) * (unsigned)(r + 2) / 2u <= b) ++r;
+      I = r + 1;
+      J = (int)(b - (unsigned)r * (unsigned)(r + 1) / 2u) + 1;
     }
+  }
+  const int64_t i0 = a.t0 + (int64_t)I * kNB, j0 = a.t0 + (int64_t)J * kNB;
+  const int nr = (int)((n - i0) < kNB ? (n - i0) : kNB), nc = (int)((n - j0) < kNB ? (n - j0) : kNB);
+  const TilePos tp = tile_pos();
+  double tr[kFI][kFJ][2], ti[kFI][kFJ][2];
+#pragma unroll
+  for (int fi = 0; fi < kFI; ++fi)
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj) tr[fi][fj][0] = tr[fi][fj][1] = ti[fi][fj][0] = ti[fi][fj][1] = 0.0;
+
+  if (!kHead) {
+    // ---- acc = W L21^T over the kNB columns of block column k0, staged in two k passes --------------------------
+    double* sWr = smd;
+    double* sWi = sWr + kNB * kKP;
+    double* sLr = sWi + kNB * kKP;
+    double* sLi = sLr + kNB * kKP;
+    const int w = tid >> 5, l = tid & 31, g = l >> 2, q = l & 3;
+    const int arow = (w / kWC) * kWTR + g, brow = (w % kWC) * kWTC + g;
+    for (int kh = 0; kh < kNB; kh += kKC) {
+      for (int idx = tid; idx < kNB * kKC; idx += kThreads) {
+        const int r = idx / kKC, k = idx % kKC;
+        cplx wv = cmake(0.0, 0.0), lv = cmake(0.0, 0.0);
+        if (r < nr) wv = a.Wprev[(i0 + r) * kNB + kh + k];
+        if (r < nc) lv = a.M[(j0 + r) * n + a.k0 + kh + k];
+        sWr[r * kKP + k] = wv.x;
+        sWi[r * kKP + k] = wv.y;
+        sLr[r * kKP + k] = lv.x;
+        sLi[r * kKP + k] = lv.y;
+      }
+      __syncthreads();
+#pragma unroll 2
+      for (int kk = 0; kk < kKC; kk += 4) {
+        double ar[kFI], ai[kFI], br[kFJ], bi[kFJ];
+#pragma unroll
+        for (int fi = 0; fi < kFI; ++fi) {
+          ar[fi] = sWr[(arow + 8 * fi) * kKP + kk + q];
+          ai[fi] = sWi[(arow + 8 * fi) * kKP + kk + q];
+        }
+#pragma unroll
+        for (int fj = 0; fj < kFJ; ++fj) {
+          br[fj] = sLr[(brow + 8 * fj) * kKP + kk + q];
+          bi[fj] = sLi[(brow + 8 * fj) * kKP + kk + q];
+        }
+#pragma unroll
+        for (int fi = 0; fi < kFI; ++fi)
+#pragma unroll
+          for (int fj = 0; fj < kFJ; ++fj) {
+            dmma(tr[fi][fj][0], tr[fi][fj][1], ar[fi], br[fj]);
+            dmma(tr[fi][fj][0], tr[fi][fj][1], -ai[fi], bi[fj]);
+            dmma(ti[fi][fj][0], ti[fi][fj][1], ar[fi], bi[fj]);
+            dmma(ti[fi][fj][0], ti[fi][fj][1], ai[fi], br[fj]);
+          }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- tile = C - acc (only entries of the lower triangle of M exist) -------------------------------------------
+#pragma unroll
+  for (int fi = 0; fi < kFI; ++fi) {
+    const int r = tp.row(fi);
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = tp.col(fj, e);
+        cplx v = cmake(0.0, 0.0);
+        if (r < nr && c < nc && j0 + c <= i0 + r) v = a.M[(i0 + r) * n + j0 + c];
+        tr[fi][fj][e] = v.x - tr[fi][fj][e];
+        ti[fi][fj][e] = v.y - ti[fi][fj][e];
+      }
+  }
+  cplx* smc = reinterpret_cast<cplx*>(smd);
+  if (J != 0) {  // plain trailing tile: store and leave
+#pragma unroll
+    for (int fi = 0; fi < kFI; ++fi) {
+      const int r = tp.row(fi);
+#pragma unroll
+      for (int fj = 0; fj < kFJ; ++fj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = tp.col(fj, e);
+          if (r < nr && c < nc && j0 + c <= i0 + r) a.M[(i0 + r) * n + j0 + c] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
+        }
+    }
+    return;
+  }
+  const int nb = nc;  // width of block column t0
+  if (I == 0) {
+    // ---- the next diagonal block: factorise in registers, publish L11 / D / 1/D ---------------------------------
+    cplx* wv = smc;                 // [2][kNB]
+    cplx* dinv_s = smc + 2 * kNB;   // [kNB]
+    tile_ldlt(tr, ti, tp, nb, wv, dinv_s, a.info, a.t0);
+#pragma unroll
+    for (int fi = 0; fi < kFI; ++fi) {
+      const int r = tp.row(fi);
+#pragma unroll
+      for (int fj = 0; fj < kFJ; ++fj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = tp.col(fj, e);
+          if (r < nb && c <= r) a.M[(a.t0 + r) * n + a.t0 + c] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
+        }
+    }
+    if (tid < nb) a.dinvg[a.t0 + tid] = dinv_s[tid];
+    fence_all();
+    __syncthreads();
+    if (tid == 0) publish(a.sync + 1);
+    return;
+  }
+  // ---- a tile below it: wait for the diagonal block, then W = A21 L11^-T, L21 = W D^-1 ---------------------------
+  cplx* Ls = smc;                        // [kNB][kPad]
+  cplx* xc = smc + kNB * kPad;           // [2][kNB]
+  cplx* dinv_s = xc + 2 * kNB;           // [kNB]
+  if (tid == 0) spin_until_set(a.sync + 1);
+  __syncthreads();
+  fence_all();
+  for (int idx = tid; idx < nb * nb; idx += kThreads) {
+    const int i = idx / nb, j = idx % nb;
+    if (j < i) Ls[i * kPad + j] = ld_cg(a.M + (a.t0 + i) * n + a.t0 + j);
+  }
+  if (tid < nb) dinv_s[tid] = ld_cg(a.dinvg + a.t0 + tid);
+  __syncthreads();
+  tile_panel(tr, ti, tp, nb, Ls, xc);
+#pragma unroll
+  for (int fi = 0; fi < kFI; ++fi) {
+    const int r = tp.row(fi);
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = tp.col(fj, e);
+        if (r < nr && c < nb) {
+          const cplx wv = cmake(tr[fi][fj][e], ti[fi][fj][e]);
+          a.Wnext[(i0 + r) * kNB + c] = wv;
+          a.M[(i0 + r) * n + a.t0 + c] = cmul_(wv, dinv_s[c]);
+        }
+      }
   }
 }
 
@@ -240,7 +427,6 @@ __global__ void __launch_bounds__(kThreads) zldlt_diaginv_kernel(const cplx* __r
 }
 
 // ---- triangular solves ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ld_flag(const unsigned* p) { return *(const volatile unsigned*)p; }
 
 // kBackward = false:  x <- L^-1 x          (block rows in increasing order)
 // kBackward = true :  x <- L^-T D^-1 x     (block rows in decreasing order)
@@ -276,20 +462,9 @@ __global__ void __launch_bounds__(kThreads) ztrsv_kernel(const cplx* __restrict_
   cplx mine = cmake(0.0, 0.0);
   const int jbeg = kBackward ? nblk - 1 : 0, jend = b, jstep = kBackward ? -1 : 1;
   for (int j = jbeg; j != jend; j += jstep) {
-    if (tid == 0) {
-      unsigned long long spins = 0;
-      while (ld_flag(sync + 1 + j) == 0u) {
-        if (++spins > (1ull << 34)) {
-#ifndef QTX_HOST_EMULATION
-          __trap();  // a dependency that never arrives is a bug: fail instead of hanging the GPU
-#endif
-        }
-      }
-    }
+    if (tid == 0) spin_until_set(sync + 1 + j);  // bounded: a dependency that never arrives traps instead of hanging
     __syncthreads();
-#ifndef QTX_HOST_EMULATION
-    __threadfence();
-#endif
+    fence_all();
     const int64_t j0 = (int64_t)j * kNB;
     const int nj = (int)((n - j0) < kNB ? (n - j0) : kNB);
     if (tid < kNB) {
@@ -369,31 +544,44 @@ __global__ void zero_sync_kernel(unsigned* sync, int count) {
 // ---- host side --------------------------------------------------------------------------------------------------
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-constexpr size_t kSmemDiag = (size_t)(kNB * kPad + kNB) * sizeof(cplx);
-constexpr size_t kSmemPanel = (size_t)(2 * kNB * kPad) * sizeof(cplx);
-constexpr size_t kSmemUpdate = (size_t)(2 * kKH * kNB) * sizeof(cplx);
+constexpr size_t kSmemPlanes = (size_t)4 * kNB * kKP * sizeof(double);
+constexpr size_t kSmemPanelStage = (size_t)(kNB * kPad + 3 * kNB) * sizeof(cplx);
+constexpr size_t kSmemStep = kSmemPlanes > kSmemPanelStage ? kSmemPlanes : kSmemPanelStage;
+constexpr size_t kSmemInv = (size_t)(2 * kNB * kPad) * sizeof(cplx);
 constexpr size_t kSmemTrsv = (size_t)(kNB * kPad + 2 * kNB + kNB * kTPR) * sizeof(cplx);
 
 struct ZldltScratch {
-  cplx *WT, *LT, *invL;
-  unsigned* sync;  // [2][nblk + 1]: forward and backward sweep
+  cplx* Wp[2];     // [n][kNB] row-major W = L21 D of the current / next block column
+  cplx *dinvg, *invL;
+  unsigned* fsync; // [nblk][2]: ticket and flag of every factorisation launch
+  unsigned* tsync; // [2][nblk + 1]: forward and backward sweep of a solve
 };
 
+static size_t nblk_of(int64_t n) { return (size_t)((n + kNB - 1) / kNB); }
 static size_t panel_bytes(int64_t n) { return align256((size_t)kNB * (size_t)n * sizeof(cplx)); }
-static size_t invl_bytes(int64_t n) { return align256((size_t)((n + kNB - 1) / kNB) * kNB * kNB * sizeof(cplx)); }
+static size_t dinv_bytes(int64_t n) { return align256((size_t)n * sizeof(cplx)); }
+static size_t invl_bytes(int64_t n) { return align256(nblk_of(n) * kNB * kNB * sizeof(cplx)); }
+static size_t fsync_bytes(int64_t n) { return align256(2 * nblk_of(n) * sizeof(unsigned)); }
+static size_t tsync_bytes(int64_t n) { return align256(2 * (nblk_of(n) + 1) * sizeof(unsigned)); }
 
 size_t zldlt_scratch_bytes(int64_t n) {
-  const size_t nblk = (size_t)((n + kNB - 1) / kNB);
-  return 2 * panel_bytes(n) + invl_bytes(n) + align256(2 * (nblk + 1) * sizeof(unsigned)) + 256;
+  return 2 * panel_bytes(n) + dinv_bytes(n) + invl_bytes(n) + fsync_bytes(n) + tsync_bytes(n) + 256;
 }
 
 static ZldltScratch carve(void* scratch, int64_t n) {
-  char* base = (char*)align256((size_t)scratch);
+  char* p = (char*)align256((size_t)scratch);
   ZldltScratch s;
-  s.WT = (cplx*)base;
-  s.LT = (cplx*)(base + panel_bytes(n));
-  s.invL = (cplx*)(base + 2 * panel_bytes(n));
-  s.sync = (unsigned*)(base + 2 * panel_bytes(n) + invl_bytes(n));
+  s.Wp[0] = (cplx*)p;
+  p += panel_bytes(n);
+  s.Wp[1] = (cplx*)p;
+  p += panel_bytes(n);
+  s.dinvg = (cplx*)p;
+  p += dinv_bytes(n);
+  s.invL = (cplx*)p;
+  p += invl_bytes(n);
+  s.fsync = (unsigned*)p;
+  p += fsync_bytes(n);
+  s.tsync = (unsigned*)p;
   return s;
 }
 
@@ -403,10 +591,9 @@ static int zldlt_prepare() {
   int dev = 0;
   QTX_CUDA(cudaGetDevice(&dev));
   if (prepared_device != dev) {
-    QTX_CUDA(cudaFuncSetAttribute(zldlt_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDiag));
-    QTX_CUDA(cudaFuncSetAttribute(zldlt_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPanel));
-    QTX_CUDA(cudaFuncSetAttribute(zldlt_diaginv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPanel));
-    QTX_CUDA(cudaFuncSetAttribute(zldlt_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemUpdate));
+    QTX_CUDA(cudaFuncSetAttribute(zldlt_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemStep));
+    QTX_CUDA(cudaFuncSetAttribute(zldlt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemStep));
+    QTX_CUDA(cudaFuncSetAttribute(zldlt_diaginv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemInv));
     QTX_CUDA(cudaFuncSetAttribute(ztrsv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTrsv));
     QTX_CUDA(cudaFuncSetAttribute(ztrsv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTrsv));
     prepared_device = dev;
@@ -419,20 +606,33 @@ int zldlt_factor(cuDoubleComplex* M, int64_t n, void* scratch, int32_t* info, cu
   int rc = zldlt_prepare();
   if (rc) return rc;
   const ZldltScratch s = carve(scratch, n);
-  for (int64_t k0 = 0; k0 < n; k0 += kNB) {
-    const int nb = (int)((n - k0) < kNB ? (n - k0) : kNB);
-    QTX_LAUNCH_SMEM(zldlt_diag_kernel, 1, kThreads, kSmemDiag, st, M, n, k0, nb, info);
-    QTX_LAUNCH_CHECK();
-    const int64_t rest = n - k0 - nb;
-    if (rest <= 0) break;
-    const unsigned tiles = (unsigned)((rest + kNB - 1) / kNB);
-    QTX_LAUNCH_SMEM(zldlt_panel_kernel, tiles, kThreads, kSmemPanel, st, M, n, k0, nb, s.WT, s.LT);
-    QTX_LAUNCH_CHECK();
-    QTX_LAUNCH_SMEM(zldlt_update_kernel, tiles * (tiles + 1) / 2, kThreads, kSmemUpdate, st, M, n, k0, nb, s.WT, s.LT);
+  const unsigned nblk = (unsigned)nblk_of(n);
+  QTX_LAUNCH_SMEM(zero_sync_kernel, 1, 256, 0, st, s.fsync, (int)(2 * nblk));
+  QTX_LAUNCH_CHECK();
+  StepArgs a;
+  a.M = M;
+  a.n = n;
+  a.dinvg = s.dinvg;
+  a.info = info;
+  // block column 0: factorise the first diagonal block and its panel
+  a.k0 = 0;
+  a.t0 = 0;
+  a.Wprev = nullptr;
+  a.Wnext = s.Wp[0];
+  a.sync = s.fsync;
+  QTX_LAUNCH_SMEM(zldlt_step_kernel<true>, nblk, kThreads, kSmemStep, st, a);
+  QTX_LAUNCH_CHECK();
+  for (unsigned step = 1; step < nblk; ++step) {  // apply block column step - 1, factorise block column step
+    a.k0 = (int64_t)(step - 1) * kNB;
+    a.t0 = (int64_t)step * kNB;
+    a.Wprev = s.Wp[(step - 1) & 1];
+    a.Wnext = s.Wp[step & 1];
+    a.sync = s.fsync + 2 * step;
+    const unsigned T = nblk - step;
+    QTX_LAUNCH_SMEM(zldlt_step_kernel<false>, T * (T + 1) / 2, kThreads, kSmemStep, st, a);
     QTX_LAUNCH_CHECK();
   }
-  const unsigned nblk = (unsigned)((n + kNB - 1) / kNB);
-  QTX_LAUNCH_SMEM(zldlt_diaginv_kernel, nblk, kThreads, kSmemPanel, st, M, n, s.invL);
+  QTX_LAUNCH_SMEM(zldlt_diaginv_kernel, nblk, kThreads, kSmemInv, st, M, n, s.invL);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }
@@ -441,12 +641,12 @@ int zldlt_solve(const cuDoubleComplex* M, int64_t n, cuDoubleComplex* x, void* s
   int rc = zldlt_prepare();
   if (rc) return rc;
   const ZldltScratch s = carve(scratch, n);
-  const unsigned nblk = (unsigned)((n + kNB - 1) / kNB);
-  QTX_LAUNCH_SMEM(zero_sync_kernel, 1, 256, 0, st, s.sync, (int)(2 * (nblk + 1)));
+  const unsigned nblk = (unsigned)nblk_of(n);
+  QTX_LAUNCH_SMEM(zero_sync_kernel, 1, 256, 0, st, s.tsync, (int)(2 * (nblk + 1)));
   QTX_LAUNCH_CHECK();
-  QTX_LAUNCH_SMEM(ztrsv_kernel<false>, nblk, kThreads, kSmemTrsv, st, M, s.invL, n, x, s.sync);
+  QTX_LAUNCH_SMEM(ztrsv_kernel<false>, nblk, kThreads, kSmemTrsv, st, M, s.invL, n, x, s.tsync);
   QTX_LAUNCH_CHECK();
-  QTX_LAUNCH_SMEM(ztrsv_kernel<true>, nblk, kThreads, kSmemTrsv, st, M, s.invL, n, x, s.sync + nblk + 1);
+  QTX_LAUNCH_SMEM(ztrsv_kernel<true>, nblk, kThreads, kSmemTrsv, st, M, s.invL, n, x, s.tsync + nblk + 1);
   QTX_LAUNCH_CHECK();
   return QTX_OK;
 }

@@ -2,16 +2,43 @@
 markers: the arithmetic is fused into the CUDA forward / backward kernels."""
 
 
-def exp_by_scale(x):  # quantax/nn/activation.py:26-32
-    raise RuntimeError("exp_by_scale is evaluated inside the CUDA kernels; pass it as ResConv(final_activation=...)")
+def _as_tensor(x):
+    import torch
+
+    return x if torch.is_tensor(x) else torch.as_tensor(x)
 
 
-def sinhp1_by_scale(x):  # quantax/nn/activation.py:7-14
-    raise RuntimeError("sinhp1_by_scale is evaluated inside the CUDA kernels; pass it as ResConv(final_activation=...)")
+def exp_by_scale(x):
+    r"""f(x) = exp(x) as a ``ScaleArray`` with the scalar exponent max|x| (quantax/nn/activation.py:26-32).  Callable
+    on any tensor like the reference's; inside ``ResConv`` the same function is evaluated by the CUDA kernels, which
+    recognise it by identity (``ResConv(final_activation=exp_by_scale)``)."""
+    import torch
+
+    from .utils import ScaleArray
+
+    x = _as_tensor(x)
+    xmax = torch.nan_to_num(x.abs(), nan=0.0).max() if x.numel() else x.new_zeros(())
+    return ScaleArray(torch.exp(x - xmax), xmax)
 
 
-def pair_cpl(x):  # quantax/nn/activation.py:75-81
-    raise RuntimeError("pair_cpl is applied inside the CUDA kernels when ResConv(out_dtype=torch.complex128)")
+def sinhp1_by_scale(x):
+    r"""f(x) = sinh(x) + 1 as a ``ScaleArray`` (quantax/nn/activation.py:7-14); see ``exp_by_scale``."""
+    import torch
+
+    from .utils import ScaleArray
+
+    x = _as_tensor(x)
+    xmax = torch.nan_to_num(x.abs(), nan=0.0).max() if x.numel() else x.new_zeros(())
+    return ScaleArray((torch.exp(x - xmax) - torch.exp(-x - xmax)) / 2 + torch.exp(-xmax), xmax)
+
+
+def pair_cpl(x):
+    r"""f(x) = x_1 + i x_2 for x = (x_1, x_2) split along the first axis (quantax/nn/activation.py:75-81)."""
+    import torch
+
+    x = _as_tensor(x)
+    h = x.shape[0] // 2
+    return torch.complex(x[:h], x[h:])
 
 
 class RawInputLayer:

@@ -17,6 +17,7 @@ from __future__ import annotations
 import os
 from typing import Callable, Optional
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -110,6 +111,10 @@ def _eig_workspace(n: int):
 PINV_METHOD = os.environ.get("QTX_PINV", "ldlt")
 LANCZOS_STEPS = max(1, min(1024, int(os.environ.get("QTX_LANCZOS_STEPS", "512"))))  # upper bound of the adaptive run
 REFINE_STEPS = int(os.environ.get("QTX_PINV_REFINE", "3"))
+# two consecutive stages (k, 2k steps) of the Lanczos run must agree to this: the error of an extreme Ritz value after
+# 2k steps is about the square of its error after k steps, so the accepted value is good to ~1e-14; max|lambda| only
+# enters through the cut-off c = rtol max|lambda| + atol, to which f is insensitive away from the cut-off
+LANCZOS_AGREE = 1e-7
 
 
 def _shift_count(mask: int) -> int:
@@ -132,9 +137,9 @@ def _pinv_workspace(n: int, method: str, nshifts: int):
 def sym_absmax_eig(T: torch.Tensor, steps: Optional[int] = None, method: Optional[str] = None,
                    nshifts: int = 3) -> torch.Tensor:
     """max|lambda| of a symmetric float64 matrix as a device scalar [1] (Lanczos, qtx_sym_absmax_eig[_ws]).  With
-    ``steps=None`` the recurrence is continued to 64, 128, 256, ... steps (at most QTX_LANCZOS_STEPS) until two
-    consecutive values agree to 1e-14 -- the error after 2k steps is about the square of the error after k -- which
-    costs one scalar read-back per stage; an explicit ``steps`` runs exactly that many without synchronising."""
+    ``steps=None`` the recurrence is continued to 32, 64, 128, ... steps (at most QTX_LANCZOS_STEPS) until two
+    consecutive values agree to LANCZOS_AGREE -- the error after 2k steps is about the square of the error after k --
+    which costs one scalar read-back per stage; an explicit ``steps`` runs exactly that many without synchronising."""
     n = T.shape[0]
     method = "rational" if method is None and PINV_METHOD == "rational" else ("ldlt" if method is None else method)
     ws, wsz = _pinv_workspace(n, method, nshifts)
@@ -156,15 +161,15 @@ def sym_absmax_eig(T: torch.Tensor, steps: Optional[int] = None, method: Optiona
         run(done, upto)
         done = upto
         cur = float(lam.item())
-        if prev is not None and abs(cur - prev) <= 1e-14 * abs(cur):
+        if prev is not None and abs(cur - prev) <= LANCZOS_AGREE * abs(cur):
             break
         prev = cur
     return lam
 
 
 def lanczos_stages(n: int, max_steps: int):
-    """Step counts at which the adaptive Lanczos run is evaluated: 64, 128, 256, ... capped by n and max_steps."""
-    out, k = [], 64
+    """Step counts at which the adaptive Lanczos run is evaluated: 32, 64, 128, ... capped by n and max_steps."""
+    out, k = [], 32
     cap = max(1, min(n, max_steps))
     while k < cap:
         out.append(k)
@@ -401,6 +406,15 @@ def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops, tsolv
 
 
 # ---- solvers (callables (A, b) -> x; A is the rank-local row block of Obar) -----------------------
+def _dtype_rtol(rtol: Optional[float], dtype) -> float:
+    """The reference takes the default cut-off from the dtype of the eigenvalues, i.e. of A (solver.py:12-21):
+    1e-6 for float32, 1e-12 for float64.  The Gram is accumulated in float64 here whatever A is, so the default is
+    resolved from A's dtype before it crosses the C ABI (whose own default is the float64 one)."""
+    if rtol is not None:
+        return float(rtol)
+    return 1e-6 if dtype in (torch.float32, torch.complex64) else 1e-12
+
+
 def _snr_tsolve(rtol, atol, tol_snr):
     if tol_snr > 1e-6:
         return lambda T, bfull: pinv_eig_solve(T, bfull, rtol, atol, tol_snr=tol_snr)
@@ -412,12 +426,13 @@ def minnorm_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: f
 
     def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         rank, P = world()
+        rt = _dtype_rtol(rtol, A.dtype)
         if P == 1:
             T = gram(A, nslices=nslices)
-            y, info = pinv_eig_solve(T, b, rtol, atol, tol_snr=tol_snr, rational_ok=True)
+            y, info = pinv_eig_solve(T, b, rt, atol, tol_snr=tol_snr, rational_ok=True)
             solve.last_info = info
             return matvec_t(A, y)
-        x, info = distributed_minnorm(A, b, rtol, atol, _CudaOps(nslices), _snr_tsolve(rtol, atol, tol_snr))
+        x, info = distributed_minnorm(A, b, rt, atol, _CudaOps(nslices), _snr_tsolve(rt, atol, tol_snr))
         solve.last_info = info
         return x
 
@@ -440,6 +455,7 @@ def lstsq_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: flo
 
     def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         rank, P = world()
+        rt = _dtype_rtol(rtol, A.dtype)
         At = A.t().contiguous()  # [np, nl]: S = At At^T sums over the local samples
         S = gram(At, nslices=nslices)
         if P > 1:
@@ -454,13 +470,13 @@ def lstsq_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: flo
                 bl = torch.empty(P * b.shape[0], dtype=b.dtype, device=b.device)
                 _dist().all_gather_into_tensor(bl, b.contiguous())
             rho = rows_dot_snr(M, bl, tol_snr)
-            x = pinv_apply(S, evals, rho, rtol, atol)
+            x = pinv_apply(S, evals, rho, rt, atol)
         else:
             F = matvec_t(A, b)
             if P > 1:
                 _dist().all_reduce(F)
             # S, F are all-reduced (the same on all ranks) and F = A^T b lies in the range of S
-            x, info = pinv_eig_solve(S, F, rtol, atol, replicated=True, rational_ok=True)
+            x, info = pinv_eig_solve(S, F, rt, atol, replicated=True, rational_ok=True)
         solve.last_info = info
         return x
 
@@ -495,13 +511,14 @@ def minnorm_shift_eig(rshift: Optional[float] = None, ashift: float = 1e-4, nsli
 
     def solve(A: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         rank, P = world()
+        rs = _dtype_rtol(rshift, A.dtype)
         if P == 1:
             T = gram(A, nslices=nslices)
-            y, info = shift_chol_solve(T, b, rshift, ashift)
+            y, info = shift_chol_solve(T, b, rs, ashift)
             solve.last_info = info
             return matvec_t(A, y)
         x, info = distributed_minnorm(A, b, None, 0.0, _CudaOps(nslices),
-                                      lambda T, bfull: shift_chol_solve(T, bfull, rshift, ashift))
+                                      lambda T, bfull: shift_chol_solve(T, bfull, rs, ashift))
         solve.last_info = info
         return x
 
@@ -519,7 +536,7 @@ def lstsq_shift_eig(rshift: Optional[float] = None, ashift: float = 1e-4, nslice
         if P > 1:
             _dist().all_reduce(S)
             _dist().all_reduce(F)
-        x, info = shift_chol_solve(S, F, rshift, ashift)
+        x, info = shift_chol_solve(S, F, _dtype_rtol(rshift, A.dtype), ashift)
         solve.last_info = info
         return x
 
@@ -713,7 +730,12 @@ class QNGD:
         return Obar
 
     def solve(self, Obar: torch.Tensor, Ebar: torch.Tensor) -> torch.Tensor:
-        """Solve Obar x = Ebar (sr.py:90-113, real parameters / real output)."""
+        """Solve Obar x = Ebar (sr.py:90-113).  Real parameters: for a complex-output state Obar and Ebar arrive
+        stacked as [Re; Im]; real-time evolution (``imag_time=False``) solves against [-Im Ebar; Re Ebar]
+        (sr.py:99-104)."""
+        if self._state.vs_type == VS_TYPE.real_to_complex and not self._imag_time:
+            n = Ebar.shape[0] // 2
+            Ebar = torch.cat([-Ebar[n:], Ebar[:n]])
         ev = self._tic("solve")
         step = self._solver(Obar, Ebar)
         self._toc(ev)
@@ -976,6 +998,33 @@ def _vec(n: int) -> torch.Tensor:
     return torch.zeros(n, dtype=torch.float64, device=device())
 
 
+def _save_leaves(file, leaves) -> None:
+    """The optimizer's internal quantities in the leaf order of ``eqx.tree_serialise_leaves(file, (...))`` (one
+    ``np.save`` blob per leaf, scalars included), written by rank 0 only (sr.py:256-262, 343-349, 423-429)."""
+    from .utils import write_eqx_leaves
+
+    if world()[0] == 0:
+        write_eqx_leaves(file, [v.detach().cpu().numpy() if torch.is_tensor(v) else v for v in leaves])
+
+
+def _load_leaves(file, like):
+    """Leaves of a file written by ``_save_leaves`` / the reference, validated against ``like`` (scalars and vectors)."""
+    from .utils import read_eqx_leaves
+
+    got = read_eqx_leaves(file)
+    if len(got) != len(like):
+        raise ValueError(f"optimizer file holds {len(got)} leaves, expected {len(like)}")
+    out = []
+    for g, l in zip(got, like):
+        if torch.is_tensor(l):
+            if g.size != l.numel():
+                raise ValueError(f"optimizer file: vector of {g.size} entries, expected {l.numel()}")
+            out.append(torch.from_numpy(np.ascontiguousarray(np.real(g).astype(np.float64)).reshape(-1)).to(l.device))
+        else:
+            out.append(type(l)(np.asarray(g).reshape(())))
+    return out
+
+
 def _scale_columns(A: torch.Tensor, d: torch.Tensor) -> None:
     _lib.call("qtx_scale_columns", _lib.dtype_code(A.dtype), _lib.ptr2d(A), A.shape[0], A.shape[1], A.stride(0),
               _lib.ptr(d), _lib.stream())
@@ -999,17 +1048,11 @@ class SPRING(SR):
         return step
 
     def save(self, file) -> None:
-        import numpy as np
-
-        if world()[0] == 0:
-            np.savez(file, mu=self._mu, last_step=self._last_step.cpu().numpy())
+        """sr.py:256-262: leaves (mu, last_step)."""
+        _save_leaves(file, (float(self._mu), self._last_step))
 
     def load(self, file) -> None:
-        import numpy as np
-
-        d = np.load(file)
-        self._mu = float(d["mu"])
-        self._last_step = torch.from_numpy(d["last_step"]).to(device())
+        self._mu, self._last_step = _load_leaves(file, (float(self._mu), self._last_step))
 
 
 class MARCH(SR):
@@ -1023,6 +1066,17 @@ class MARCH(SR):
         self._V = _vec(state.nparams)
         self._t = 0
         self._V_is_zero = True
+        if file is not None:
+            self.load(file)
+
+    def save(self, file) -> None:
+        """sr.py:343-349: leaves (mu, beta, last_step, V, t)."""
+        _save_leaves(file, (float(self._mu), float(self._beta), self._last_step, self._V, int(self._t)))
+
+    def load(self, file) -> None:
+        self._mu, self._beta, self._last_step, self._V, self._t = _load_leaves(
+            file, (float(self._mu), float(self._beta), self._last_step, self._V, int(self._t)))
+        self._V_is_zero = not bool(torch.any(self._V.abs() > 1e-8))  # `jnp.allclose(self._V, 0)` (sr.py:298)
 
     def solve(self, Obar: torch.Tensor, Ebar: torch.Tensor) -> torch.Tensor:
         self._t += 1
@@ -1054,6 +1108,16 @@ class AdamSR(SR):
         self._m = _vec(state.nparams)
         self._v = _vec(state.nparams)
         self._t = 0
+        if file is not None:
+            self.load(file)
+
+    def save(self, file) -> None:
+        """sr.py:423-429: leaves (mu, beta, m, v, t)."""
+        _save_leaves(file, (float(self._mu), float(self._beta), self._m, self._v, int(self._t)))
+
+    def load(self, file) -> None:
+        self._mu, self._beta, self._m, self._v, self._t = _load_leaves(
+            file, (float(self._mu), float(self._beta), self._m, self._v, int(self._t)))
 
     def solve(self, Obar: torch.Tensor, Ebar: torch.Tensor) -> torch.Tensor:
         self._t += 1

@@ -386,6 +386,10 @@ class Variational(State):
         loads into the reference's ``Variational(model, param_file=...)`` and vice versa."""
         from .utils import write_eqx_leaves
 
+        from .global_defs import world
+
+        if world()[0] != 0:  # the reference writes on process 0 only (variational.py:581-587)
+            return
         m = self._model
         flat = m.params.detach().cpu().numpy()
         arrays = [flat[o:o + int(np.prod(shape))].reshape(shape) for _, o, shape in m.eqx_leaf_layout()]

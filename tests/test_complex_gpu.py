@@ -126,6 +126,11 @@ def test_complex_oloc_sweep_and_sr_step(qtx, phase, tol):
     assert abs(opt.energy - eo.real) <= tol * abs(eo) and abs(opt.VarE - vo) <= 10 * tol * abs(vo)
     assert np.isrealobj(step)
     check(f"complex stacked SR step phase={phase}", np.linalg.norm(step - xo.real) / np.linalg.norm(xo), 10 * tol)
+    # real-time evolution of the same state: the solver sees [-Im Ebar; Re Ebar] (sr.py:103-104)
+    step_rt = to_np(qtx.optimizer.SR(state, H, imag_time=False).get_step(samples))
+    xo_rt, _, _ = osolver.sr_step(net.jacobian(s), Eo, np.ones(ns), real_to_complex=True, imag_time=False)
+    check(f"complex stacked SR step, imag_time=False, phase={phase}", np.linalg.norm(step_rt - xo_rt.real) / np.linalg.norm(xo_rt), 10 * tol)
+    assert np.linalg.norm(step_rt - step) > 0.1 * np.linalg.norm(step)
     p0 = to_np(state.get_params_flatten()).copy()
     state.update(torch.from_numpy(step).cuda() * 0.01)
     assert np.allclose(to_np(state.get_params_flatten()), p0 - 0.01 * step, rtol=1e-12, atol=1e-14)

@@ -263,6 +263,17 @@ def test_final_activations_match_reference_code(tag):
     xc = GOLD[f"act/{tag}/pair_in"]
     C = xc.shape[0]
     assert np.array_equal(xc[: C // 2] + 1j * xc[C // 2:], GOLD[f"act/{tag}/pair_cpl"])  # pairing used by ResConv._final
+    # the product's callable activations (quantax_b200/nn.py; the CUDA kernels evaluate the same functions in place)
+    import torch
+
+    from quantax_b200 import nn as qnn
+
+    for name, fn in (("exp_by_scale", qnn.exp_by_scale), ("sinhp1_by_scale", qnn.sinhp1_by_scale)):
+        out = fn(torch.from_numpy(x))
+        ref = GOLD[f"act/{tag}/{name}/0"]
+        assert np.allclose(out.significand.numpy(), ref, rtol=1e-6 if tag == "float32" else 1e-14, atol=0), name
+        assert float(out.exponent) == float(GOLD[f"act/{tag}/{name}/1"]), name
+    assert np.array_equal(qnn.pair_cpl(torch.from_numpy(xc)).numpy(), GOLD[f"act/{tag}/pair_cpl"])
 
 
 # ---- Metropolis proposals and accept/reject on injected picks / uniforms ------------------------------------------------

@@ -119,8 +119,8 @@ def test_adaptive_lanczos_on_a_dense_spectral_edge():
     ref = np.linalg.eigvalsh(T).max()
     assert abs(pr.abs_max_eigenvalue(T, steps=32) - ref) > 1e-9 * ref  # too few steps: not converged
     assert abs(pr.abs_max_eigenvalue(T) - ref) <= 1e-12 * ref
-    assert pr.lanczos_stages(700) == [64, 128, 256, 512] and pr.lanczos_stages(50) == [50]
-    assert pr.lanczos_stages(64) == [64] and pr.lanczos_stages(5000, 100) == [64, 100]
+    assert pr.lanczos_stages(700) == [32, 64, 128, 256, 512] and pr.lanczos_stages(50) == [32, 50]
+    assert pr.lanczos_stages(32) == [32] and pr.lanczos_stages(5000, 100) == [32, 64, 100]
     from quantax_b200.optimizer import lanczos_stages
 
     for n, mx in ((700, 512), (50, 512), (64, 512), (5000, 100), (1, 512), (4096, 1024)):

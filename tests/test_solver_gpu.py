@@ -184,3 +184,31 @@ def test_momentum_optimizers_match_oracle(qtx, name):
         ob, _ = osolver.obar(net.jacobian(s), np.ones(ns))
         xo = orc.solve(ob, eb)
         assert np.linalg.norm(step - xo) <= 1e-5 * np.linalg.norm(xo), (name, it)
+
+
+def test_momentum_optimizers_save_and_resume(qtx, tmp_path):
+    """SPRING / MARCH / AdamSR write their internal quantities in the reference's leaf order (sr.py:256-262, 343-349,
+    423-429: one np.save blob per leaf of (mu, last_step) / (mu, beta, last_step, V, t) / (mu, beta, m, v, t)) and a
+    resumed optimizer continues exactly like the one that kept running."""
+    from quantax_b200.utils import read_eqx_leaves
+
+    lat, olat = lattice_pair(qtx, "square", 4, (8, 8))
+    model, net = make_rbm(qtx, 16, 6, torch.float64, seed=9)
+    state = qtx.state.Variational(model)
+    H = qtx.operator.Heisenberg(msr=True)
+    s = osmp.rand_states(96, 16, 8, seed=10)
+    st = torch.from_numpy(s).cuda()
+    samples = qtx.sampler.Samples(st, state(st), None, torch.ones(96, dtype=torch.float64, device="cuda"))
+    for cls, nleaves, kw in ((qtx.optimizer.SPRING, 2, {"mu": 0.8}), (qtx.optimizer.MARCH, 5, {"mu": 0.9, "beta": 0.99}),
+                             (qtx.optimizer.AdamSR, 5, {"mu": 0.9, "beta": 0.99})):
+        a = cls(state, H, **kw)
+        for _ in range(2):
+            a.get_step(samples)
+        f = str(tmp_path / f"{cls.__name__}.eqx")  # no suffix games: the path is used as given
+        a.save(f)
+        leaves = read_eqx_leaves(f)
+        assert len(leaves) == nleaves and leaves[0].shape == () and float(leaves[0]) == kw["mu"]
+        assert leaves[-1].shape == ((model.nparams,) if nleaves == 2 else ())
+        b = cls(state, H, file=f)  # mu / beta come from the file
+        xa, xb = a.get_step(samples), b.get_step(samples)
+        assert torch.equal(xa, xb)

@@ -52,10 +52,10 @@ def _ldlt_ref(M):
     return L, d
 
 
-@pytest.mark.parametrize("n", [1, 5, 8, 9, 16, 23, 40])
+@pytest.mark.parametrize("n", [1, 5, 15, 16, 17, 33, 50, 71])
 @pytest.mark.parametrize("theta", [np.pi / 6, np.pi / 2, 5 * np.pi / 6])
 def test_factor_and_solve(emu, n, theta):
-    assert emu.emu_zldlt_block_size() == 8
+    assert emu.emu_zldlt_block_size() == 16
     T, z, M = _shifted(n, n, theta=theta)
     work = np.ascontiguousarray(np.tril(M) + np.triu(np.full((n, n), 7.5 + 3j), 1))  # the upper triangle is never read
     scratch = np.zeros(emu.emu_zldlt_scratch_bytes(n) + 64, dtype=np.uint8)
