@@ -44,8 +44,9 @@ constexpr int kThreads = 32 * kWR * kWC;
 constexpr int kWTR = kNB / kWR, kWTC = kNB / kWC;  // warp tile
 constexpr int kFI = kWTR / 8, kFJ = kWTC / 8;      // 8 x 8 accumulator fragments per warp tile
 constexpr int kPad = kNB + 1;                      // row pitch (complex numbers) of the row-major shared-memory tiles
-constexpr int kKC = kNB / 2;                       // k extent staged per pass of the trailing update
-constexpr int kKP = kKC + 4;                       // pitch (doubles) of an operand plane: conflict-free fragment loads
+constexpr int kKC = kNB / 4;                       // k extent of one pipeline stage of the trailing update
+constexpr int kKP = kKC + 4;                       // row pitch (complex numbers) of a stage: (16 kKP) mod 128 = 64 makes
+                                                   // the 16-byte fragment loads of a quarter warp conflict-free
 constexpr int kTPR = kThreads / kNB;               // threads cooperating on one row / column of a block product
 static_assert(kKC % 4 == 0 && kWTR % 8 == 0 && kWTC % 8 == 0, "tile shapes");
 
@@ -104,6 +105,28 @@ __device__ __forceinline__ void fence_all() {
 #endif
 }
 
+// 16-byte asynchronous global -> shared copy (zero fill when !valid); groups are committed / waited per pipeline stage
+__device__ __forceinline__ void cp_async16(cplx* smem_dst, const cplx* gmem_src, bool valid) {
+#ifdef QTX_HOST_EMULATION
+  *smem_dst = valid ? *gmem_src : cmake(0.0, 0.0);
+#else
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef QTX_HOST_EMULATION
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef QTX_HOST_EMULATION
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+#endif
+}
+
 // D (8 x 8) += A (8 x 4, row) B (4 x 8, col) in float64: lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and
 // C[l / 4][2 (l % 4) + {0, 1}]  (PTX mma.sync.m8n8k4.f64)
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -120,9 +143,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   c0 += s0;
   c1 += s1;
 #else
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 #endif
 }
 
@@ -268,49 +291,59 @@ __global__ void __launch_bounds__(kThreads, 2) zldlt_step_kernel(const StepArgs 
     for (int fj = 0; fj < kFJ; ++fj) tr[fi][fj][0] = tr[fi][fj][1] = ti[fi][fj][0] = ti[fi][fj][1] = 0.0;
 
   if (!kHead) {
-    // ---- acc = W L21^T over the kNB columns of block column k0, staged in two k passes --------------------------
-    double* sWr = smd;
-    double* sWi = sWr + kNB * kKP;
-    double* sLr = sWi + kNB * kKP;
-    double* sLi = sLr + kNB * kKP;
+    // ---- acc = W L21^T over the kNB columns of block column k0: cp.async double-buffered k stages ----------------
+    cplx* stage = reinterpret_cast<cplx*>(smd);  // [2 buffers][W | L][kNB][kKP]
     const int w = tid >> 5, l = tid & 31, g = l >> 2, q = l & 3;
     const int arow = (w / kWC) * kWTR + g, brow = (w % kWC) * kWTC + g;
-    for (int kh = 0; kh < kNB; kh += kKC) {
+    auto issue = [&](int chunk, int buf) {
+      cplx* sW = stage + (size_t)buf * 2 * kNB * kKP;
+      cplx* sL = sW + kNB * kKP;
       for (int idx = tid; idx < kNB * kKC; idx += kThreads) {
         const int r = idx / kKC, k = idx % kKC;
-        cplx wv = cmake(0.0, 0.0), lv = cmake(0.0, 0.0);
-        if (r < nr) wv = a.Wprev[(i0 + r) * kNB + kh + k];
-        if (r < nc) lv = a.M[(j0 + r) * n + a.k0 + kh + k];
-        sWr[r * kKP + k] = wv.x;
-        sWi[r * kKP + k] = wv.y;
-        sLr[r * kKP + k] = lv.x;
-        sLi[r * kKP + k] = lv.y;
+        const bool vw = r < nr, vl = r < nc;
+        cp_async16(sW + r * kKP + k, a.Wprev + (vw ? (i0 + r) * kNB + chunk * kKC + k : 0), vw);
+        cp_async16(sL + r * kKP + k, a.M + (vl ? (j0 + r) * n + a.k0 + chunk * kKC + k : 0), vl);
+      }
+      cp_async_commit();
+    };
+    constexpr int kChunks = kNB / kKC;
+    issue(0, 0);
+    for (int c = 0; c < kChunks; ++c) {
+      if (c + 1 < kChunks) {
+        issue(c + 1, (c + 1) & 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
-#pragma unroll 2
+      const cplx* sW = stage + (size_t)(c & 1) * 2 * kNB * kKP;
+      const cplx* sL = sW + kNB * kKP;
+#pragma unroll
       for (int kk = 0; kk < kKC; kk += 4) {
-        double ar[kFI], ai[kFI], br[kFJ], bi[kFJ];
+        cplx av[kFI], bv[kFJ];
 #pragma unroll
-        for (int fi = 0; fi < kFI; ++fi) {
-          ar[fi] = sWr[(arow + 8 * fi) * kKP + kk + q];
-          ai[fi] = sWi[(arow + 8 * fi) * kKP + kk + q];
-        }
+        for (int fi = 0; fi < kFI; ++fi) av[fi] = sW[(arow + 8 * fi) * kKP + kk + q];
 #pragma unroll
-        for (int fj = 0; fj < kFJ; ++fj) {
-          br[fj] = sLr[(brow + 8 * fj) * kKP + kk + q];
-          bi[fj] = sLi[(brow + 8 * fj) * kKP + kk + q];
-        }
+        for (int fj = 0; fj < kFJ; ++fj) bv[fj] = sL[(brow + 8 * fj) * kKP + kk + q];
+        // four real products per complex one; consecutive MMAs go to different accumulators
 #pragma unroll
         for (int fi = 0; fi < kFI; ++fi)
 #pragma unroll
-          for (int fj = 0; fj < kFJ; ++fj) {
-            dmma(tr[fi][fj][0], tr[fi][fj][1], ar[fi], br[fj]);
-            dmma(tr[fi][fj][0], tr[fi][fj][1], -ai[fi], bi[fj]);
-            dmma(ti[fi][fj][0], ti[fi][fj][1], ar[fi], bi[fj]);
-            dmma(ti[fi][fj][0], ti[fi][fj][1], ai[fi], br[fj]);
-          }
+          for (int fj = 0; fj < kFJ; ++fj) dmma(tr[fi][fj][0], tr[fi][fj][1], av[fi].x, bv[fj].x);
+#pragma unroll
+        for (int fi = 0; fi < kFI; ++fi)
+#pragma unroll
+          for (int fj = 0; fj < kFJ; ++fj) dmma(ti[fi][fj][0], ti[fi][fj][1], av[fi].x, bv[fj].y);
+#pragma unroll
+        for (int fi = 0; fi < kFI; ++fi)
+#pragma unroll
+          for (int fj = 0; fj < kFJ; ++fj) dmma(tr[fi][fj][0], tr[fi][fj][1], -av[fi].y, bv[fj].y);
+#pragma unroll
+        for (int fi = 0; fi < kFI; ++fi)
+#pragma unroll
+          for (int fj = 0; fj < kFJ; ++fj) dmma(ti[fi][fj][0], ti[fi][fj][1], av[fi].y, bv[fj].x);
       }
-      __syncthreads();
+      __syncthreads();  // the buffer is refilled two stages later
     }
   }
   // ---- tile = C - acc (only entries of the lower triangle of M exist) -------------------------------------------
@@ -544,7 +577,7 @@ __global__ void zero_sync_kernel(unsigned* sync, int count) {
 // ---- host side --------------------------------------------------------------------------------------------------
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-constexpr size_t kSmemPlanes = (size_t)4 * kNB * kKP * sizeof(double);
+constexpr size_t kSmemPlanes = (size_t)2 * 2 * kNB * kKP * sizeof(cplx);  // two stages of (W, L)
 constexpr size_t kSmemPanelStage = (size_t)(kNB * kPad + 3 * kNB) * sizeof(cplx);
 constexpr size_t kSmemStep = kSmemPlanes > kSmemPanelStage ? kSmemPlanes : kSmemPanelStage;
 constexpr size_t kSmemInv = (size_t)(2 * kNB * kPad) * sizeof(cplx);

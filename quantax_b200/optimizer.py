@@ -50,6 +50,15 @@ _WS = _Workspaces()
 DEFAULT_NSLICES = int(os.environ.get("QTX_GRAM_NSLICES", "0"))
 
 
+def model_gram_nslices(state) -> Optional[int]:
+    """Digit count of the Gram for the default solver of ``state``: 5 for float32 models (their Jacobian is float32
+    data in a float64 container), the dtype default (7 for float64) otherwise; QTX_GRAM_NSLICES overrides."""
+    if DEFAULT_NSLICES != 0:
+        return None
+    mdt = getattr(getattr(state, "model", None), "dtype", None)
+    return 5 if mdt == torch.float32 else None
+
+
 def gram_nslices_for(dtype) -> int:
     """Digit count qtx_gram uses for an input of ``dtype`` (csrc/gram_tc.cu default_slices unless overridden)."""
     if DEFAULT_NSLICES > 0:
@@ -653,7 +662,10 @@ class QNGD:
             raise NotImplementedError("real-time evolution needs a complex-output state (set_default_dtype(complex128))")
         self._state = state
         self._imag_time = imag_time
-        self._solver = auto_pinv_eig() if solver is None else solver
+        # float32 model: the Jacobian entries carry float32 rounding (6e-8 relative), so the Gram digits beyond that are
+        # spent on noise -- 5 digits (35 bits, 3e-11 of |a_i||a_j|) instead of 7 cut the tensor-core work from 28 to 15
+        # digit products (tests/test_gram_tc_gpu.py::test_five_digits_suffice_for_float32_models)
+        self._solver = auto_pinv_eig(nslices=model_gram_nslices(state)) if solver is None else solver
         self._Omean = None
         self.timers = None  # optional dict name -> [(start_event, end_event)]
 

@@ -68,11 +68,18 @@ def test_config_e_forward_and_jacobian_vs_oracle(qtx):
     Oo = net.jacobian(s)
     O64 = _f64_twin(net).jacobian(s)
     assert O.shape == Oo.shape == (16, 1047552)
+    # relative error of every sample's log-derivative vector (1 047 552 entries) against the float64 evaluation
+    rows = np.linalg.norm(O - O64, axis=1) / np.linalg.norm(O64, axis=1)
+    rows_oracle = np.linalg.norm(Oo - O64, axis=1) / np.linalg.norm(O64, axis=1)
+    check("E jacobian rows vs float64 evaluation (relative 2-norm per sample)", rows.max(), 1e-5)
+    check("E jacobian rows vs float32 oracle (relative 2-norm per sample)",
+          (np.linalg.norm(O - Oo, axis=1) / np.linalg.norm(O64, axis=1)).max(), 1e-5)
+    # the single worst of the 16.8 M entries, on the scale of the largest entry: the float32 backward pass through
+    # 16 layers sits AT the bar here (measured 1.0e-5, the NumPy float32 oracle's own worst entry: see the report)
     scale = np.abs(O64).max()
-    noise = np.abs(Oo - O64).max() / scale  # what float32 rounding does to the oracle's own 16-layer backward pass
-    check("E jacobian vs float64 evaluation (bar: 1e-5 or the float32 oracle's own distance from it)",
-          np.abs(O - O64).max() / scale, max(1e-5, 2 * noise))
-    check("E jacobian vs float32 oracle", np.abs(O - Oo).max() / scale, max(1e-5, 3 * noise))
+    check("E jacobian, float32 oracle's own worst entry vs float64 (context)", np.abs(Oo - O64).max() / scale, 1e-5)
+    check("E jacobian worst entry vs float64 evaluation", np.abs(O - O64).max() / scale, 2e-5)
+    assert rows.max() <= 4 * rows_oracle.max() + 1e-6
 
 
 def test_config_e_sweep_and_oloc_vs_oracle(qtx):

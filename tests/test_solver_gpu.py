@@ -211,4 +211,5 @@ def test_momentum_optimizers_save_and_resume(qtx, tmp_path):
         assert leaves[-1].shape == ((model.nparams,) if nleaves == 2 else ())
         b = cls(state, H, file=f)  # mu / beta come from the file
         xa, xb = a.get_step(samples), b.get_step(samples)
-        assert torch.equal(xa, xb)
+        # same state, same inputs; A^T y sums with atomics, so equal to rounding rather than bit for bit
+        assert (xa - xb).norm().item() <= 1e-12 * xa.norm().item(), cls.__name__
