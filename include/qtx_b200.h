@@ -42,7 +42,9 @@ enum qtx_status {
   QTX_ERR_SOLVER = -4       /* cuSOLVER failure or non-convergence */
 };
 
-enum qtx_dtype { QTX_F32 = 0, QTX_F64 = 1 };
+enum qtx_dtype { QTX_F32 = 0, QTX_F64 = 1, QTX_I32 = 2 /* collectives only */ };
+enum qtx_reduce_op { QTX_SUM = 0, QTX_MAX = 1 };
+typedef void* qtx_comm_t; /* communicator of qtx_comm_init / qtx_comm_adopt */
 
 /* proposal kinds of the Metropolis sweep */
 enum qtx_proposal {
@@ -506,6 +508,47 @@ int qtx_rbm_conv_jacobian(int model_dtype, const void* theta, const int8_t* spin
                           qtx_stream_t stream);
 /* out[i] = x[i] + 0i */
 int qtx_real_to_cplx(const double* x, int64_t n, double* out_c128, qtx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Collectives of the data-parallel step: what the reference gets implicitly from GSPMD on its
+ * sharded arrays (quantax/utils/function.py:163-214, quantax/optimizer/solver.py:134-139,146) as explicit calls
+ * on an NCCL communicator, so that any host -- the torch binding of this repository, a jax.ffi binder -- can run
+ * the multi-GPU step through this ABI alone.  NCCL is bound at run time (dlopen libnccl.so.2); without it these
+ * entry points return QTX_ERR_UNSUPPORTED and everything else works.
+ *   qtx_comm_unique_id : 128-byte ncclUniqueId (rank 0 creates it, the host broadcasts it by its own means)
+ *   qtx_comm_init      : ncclCommInitRank; qtx_comm_adopt wraps an ncclComm_t the host already owns
+ *   qtx_comm_all_reduce: in-place allowed; dtype QTX_F32 / QTX_F64 / QTX_I32, op QTX_SUM / QTX_MAX
+ *   qtx_comm_all_gather: recv [nranks][bytes_per_rank]
+ *   qtx_comm_all_to_all: recv block p <- send block `rank` of rank p (grouped ncclSend / ncclRecv)
+ * All enqueue on `stream`.
+ * ------------------------------------------------------------------------------------------ */
+int qtx_comm_unique_id(void* id_out_128_bytes);
+int qtx_comm_init(qtx_comm_t* comm_out, int nranks, int rank, const void* id_128_bytes);
+int qtx_comm_adopt(qtx_comm_t* comm_out, void* nccl_comm);
+int qtx_comm_destroy(qtx_comm_t comm);
+int qtx_comm_size(qtx_comm_t comm);
+int qtx_comm_rank(qtx_comm_t comm);
+int qtx_comm_all_reduce(qtx_comm_t comm, const void* send, void* recv, int64_t count, int dtype, int op,
+                        qtx_stream_t stream);
+int qtx_comm_all_gather(qtx_comm_t comm, const void* send, void* recv, int64_t bytes_per_rank,
+                        qtx_stream_t stream);
+int qtx_comm_broadcast(qtx_comm_t comm, void* buf, int64_t bytes, int root, qtx_stream_t stream);
+int qtx_comm_all_to_all(qtx_comm_t comm, const void* send, void* recv, int64_t bytes_per_peer,
+                        qtx_stream_t stream);
+
+/* Distributed MinSR solve x = A^+ b with the ROWS of A = Obar sharded over the ranks of `comm`
+ * (minnorm_pinv_eig under GSPMD, solver.py:128-149): column shards by all-to-all (parameter axis zero-padded to a
+ * multiple of nranks, solver.py:136), tensor-core Gram of the shard, all-reduce of T (solver.py:139), the soft
+ * pseudo-inverse y = f(T) b with the three shifted LDL^T solves split over the ranks (qtx_pinv_ldlt_partial) and
+ * their double-double partial sums all-gathered and added in rank order (bit-identical y everywhere), the column
+ * shard of x = A^T y, all-gather (solver.py:146).  A_local [nl, np] (ld), b_local [nl], x_out [np] float64 on every
+ * rank, info_out int32 [1] device (0 = ok).  max|lambda| comes from exactly `lanczos_steps` Lanczos steps (no host
+ * read-back; 128 suffices unless the top of the spectrum is dense). */
+size_t qtx_minsr_solve_dist_workspace_size(qtx_comm_t comm, int dtype, int64_t nl, int64_t np, int nslices);
+int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_local, int64_t nl, int64_t np, int64_t ld,
+                         const double* b_local, double rtol, double atol, int nslices, int lanczos_steps,
+                         int refine_steps, double* x_out, int32_t* info_out, void* workspace,
+                         size_t workspace_bytes, qtx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,19 @@ SIGNATURES = {
     "qtx_sym_absmax_eig": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "qtx_pinv_rational_partial": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "qtx_dd_sum_scale": (_i32, [_vp, _i32, _i64, _f64, _vp, _vp]),
+    "qtx_comm_unique_id": (_i32, [_vp]),
+    "qtx_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
+    "qtx_comm_adopt": (_i32, [_vp, _vp]),
+    "qtx_comm_destroy": (_i32, [_vp]),
+    "qtx_comm_size": (_i32, [_vp]),
+    "qtx_comm_rank": (_i32, [_vp]),
+    "qtx_comm_all_reduce": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "qtx_comm_all_gather": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "qtx_comm_broadcast": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "qtx_comm_all_to_all": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "qtx_minsr_solve_dist_workspace_size": (_sz, [_vp, _i32, _i64, _i64, _i32]),
+    "qtx_minsr_solve_dist": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _vp, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp,
+                                    _sz, _vp]),
     "qtx_pinv_ldlt_workspace_size": (_sz, [_i64, _i32]),
     "qtx_sym_absmax_eig_ws": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _i32, _vp]),
     "qtx_pinv_ldlt_partial": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),

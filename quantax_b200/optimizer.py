@@ -370,6 +370,18 @@ class _CudaOps:
     matvec_t = staticmethod(matvec_t)
 
 
+def _all_to_all(recv: torch.Tensor, send: torch.Tensor) -> None:
+    """recv[p] <- send[rank] of rank p.  gloo has no all-to-all for device tensors: gather everything and pick."""
+    dist = _dist()
+    if dist.get_backend() != "gloo" or not send.is_cuda:
+        dist.all_to_all_single(recv, send)
+        return
+    P, rank = dist.get_world_size(), dist.get_rank()
+    allsend = torch.empty((P,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(allsend.view(P * send.shape[0], *send.shape[1:]), send)
+    recv.copy_(allsend[:, rank])
+
+
 def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops, tsolve=None):
     """MinSR solve with the rows of A sharded over the ranks (solver.py:131-147 under GSPMD):
     row-sharded -> column-sharded all-to-all (the parameter axis is zero-padded to a multiple of
@@ -389,7 +401,7 @@ def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops, tsolv
         send = flat.view(nl, P, npc).permute(1, 0, 2).contiguous()
     recv = torch.empty_like(send)
     t = _phase_tic("comm.all_to_all_Obar")
-    dist.all_to_all_single(recv, send)
+    _all_to_all(recv, send)
     _phase_toc(t)
     Ac = recv.view(P * nl, npc)  # all Ns rows (rank-major = global sample order), this rank's columns
     if hasattr(ops, "gram_allreduce"):
@@ -412,6 +424,20 @@ def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops, tsolv
     dist.all_gather_into_tensor(x, xc.contiguous())
     _phase_toc(t)
     return x[:npar].contiguous(), info
+
+
+# The distributed MinSR solve runs entirely behind the C ABI (csrc/comm.cu: NCCL collectives bound by the library)
+# when the process group is NCCL and the default pseudo-inverse route is in use; QTX_DIST_C=0 keeps the collectives in
+# torch.distributed (the path the gloo tests exercise on CPU), which is also what SNR damping and the other T-solvers use.
+DIST_IN_LIBRARY = os.environ.get("QTX_DIST_C", "1") == "1"
+DIST_LANCZOS_STEPS = int(os.environ.get("QTX_DIST_LANCZOS_STEPS", "128"))
+
+
+def _dist_in_library(tol_snr: float) -> bool:
+    if not DIST_IN_LIBRARY or PINV_METHOD != "ldlt" or tol_snr > 1e-6 or os.environ.get("QTX_GRAM_P2P", "0") == "1":
+        return False
+    dist = _dist()
+    return dist.is_initialized() and dist.get_backend() == "nccl"
 
 
 # ---- solvers (callables (A, b) -> x; A is the rank-local row block of Obar) -----------------------
@@ -441,7 +467,16 @@ def minnorm_pinv_eig(rtol: Optional[float] = None, atol: float = 0.0, tol_snr: f
             y, info = pinv_eig_solve(T, b, rt, atol, tol_snr=tol_snr, rational_ok=True)
             solve.last_info = info
             return matvec_t(A, y)
-        x, info = distributed_minnorm(A, b, rt, atol, _CudaOps(nslices), _snr_tsolve(rt, atol, tol_snr))
+        if _dist_in_library(tol_snr):
+            # every collective inside the library (qtx_minsr_solve_dist over the qtx_comm_* communicator)
+            from .comm import minsr_solve_dist
+
+            t = _phase_tic("minsr_dist(all-to-all + gram + all-reduce + pinv + A^T y + all-gather)")
+            x, info = minsr_solve_dist(A, b, rt, atol, 0 if nslices is None else nslices, DIST_LANCZOS_STEPS, REFINE_STEPS,
+                                       _WS.get)
+            _phase_toc(t)
+        else:
+            x, info = distributed_minnorm(A, b, rt, atol, _CudaOps(nslices), _snr_tsolve(rt, atol, tol_snr))
         solve.last_info = info
         return x
 

@@ -50,11 +50,18 @@ def vmc(model_kind, nsamples):
 def main():
     warnings.simplefilter("ignore")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    # QTX_DIST_CHECK_BACKEND=gloo: all ranks share GPU 0 (a 1-GPU box): the CUDA kernels, the sharded layout and the
+    # rank split of the shifted solves run for real, the collectives go through gloo instead of NCCL
+    backend = os.environ.get("QTX_DIST_CHECK_BACKEND", "nccl")
+    local = int(os.environ["LOCAL_RANK"]) if backend == "nccl" else 0
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     ok = True
     cases = (("rbm", 64 * world), ("resconv", 32 * world), ("cplx", 16 * world))
-    dist.init_process_group("nccl", device_id=dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
     results = []
     for kind, ns in cases:
         spins, e, v, step, spins2, params = vmc(kind, ns)
@@ -73,7 +80,7 @@ def main():
             ds = float((step - step_ref).norm() / step_ref.norm())
             dp = float((params - p_ref).abs().max())
             print(f"{kind}: chains equal {same1}/{same2}, dE {de:.2e}, dstep {ds:.2e}, dparams {dp:.2e}", flush=True)
-            ok &= same1 and same2 and de < 1e-12 and ds < 1e-6 and dp < 1e-8
+            ok &= same1 and same2 and de < 1e-12 and ds < 1e-9 and dp < 1e-10
     if rank == 0:
         print("DIST_CHECK_OK" if ok else "DIST_CHECK_FAILED", flush=True)
 
