@@ -228,6 +228,18 @@ int qtx_metropolis_accept_compact(int8_t* spins, const int8_t* new_spins, const 
                                   uint64_t chain0, int32_t* naccept, uint8_t* accept_log,
                                   qtx_stream_t stream);
 
+/* Whole sweep of a bare ResConv state in ONE call (Metropolis._partial_sweep, metropolis.py:246-275): `nsweeps` times
+ * propose -> forward of the (moved) proposals -> accept, enqueued back to back with no host synchronisation; spins
+ * [ns, N] in/out, significand / exponent [ns] = psi of the final chains, naccept int32 [ns] nullable.  Same Philox
+ * stream, same chains as the step-by-step entry points above.  Workspace from qtx_resconv_sweep_workspace_size. */
+size_t qtx_resconv_sweep_workspace_size(int model_dtype, int64_t ns, int nblocks, int channels, int lx, int ly,
+                                        int kh, int kw);
+int qtx_resconv_sweep(int model_dtype, const void* params, int nblocks, int channels, int lx, int ly, int kh,
+                      int kw, int final_act, int8_t* spins, int64_t ns, int nsweeps, int kind,
+                      const int32_t* nbr_table, int max_nb, int hop, double reweight, uint64_t seed,
+                      uint64_t step0, uint64_t chain0, double* significand_out, double* exponent_out,
+                      int32_t* naccept_out, void* workspace, size_t workspace_bytes, qtx_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * State-level symmetry projection psi(s) = sum_g w_g psi(T_g s), w_g = chi_g chi_0 / |G|
  * (quantax/state/variational.py:262-266, quantax/symmetry/symmetry.py:325-392).

@@ -81,6 +81,9 @@ SIGNATURES = {
     "qtx_sym_absmax_eig": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "qtx_pinv_rational_partial": (_i32, [_vp, _i64, _vp, _f64, _f64, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "qtx_dd_sum_scale": (_i32, [_vp, _i32, _i64, _f64, _vp, _vp]),
+    "qtx_resconv_sweep_workspace_size": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "qtx_resconv_sweep": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _i32,
+                                 _i32, _f64, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qtx_comm_unique_id": (_i32, [_vp]),
     "qtx_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
     "qtx_comm_adopt": (_i32, [_vp, _vp]),

@@ -129,6 +129,27 @@ def generic_sweep(state, spins, nsweeps, kind, nbr, max_nb, hop, reweight, seed,
     host synchronisation; psi of the current chains is carried along (Samples.psi)."""
     ns, N = spins.shape
     dev = spins.device
+    m = state.model
+    import os
+
+    if (injected is None and not record and state.symm.is_identity and getattr(m, "kind", None) == "resconv"
+            and os.environ.get("QTX_SWEEP_COMPACT", "1") != "0" and not getattr(m, "cplx", False) and not getattr(m, "raw_layers", ()) and ns > 0
+            and _chunk(state, ns, False) >= ns):
+        # bare real ResConv: the whole step loop runs behind one C-ABI call (qtx_resconv_sweep)
+        mdt = _lib.dtype_code(m.dtype)
+        wsz = _lib.lib().qtx_resconv_sweep_workspace_size(mdt, ns, *_shape_args(m))
+        if wsz == 0:
+            raise _lib.QtxError(f"qtx_resconv_sweep_workspace_size failed: {_lib.lib().qtx_last_error().decode()}")
+        ws = state._workspace("resconv_sweep", wsz)
+        sig = torch.empty(ns, dtype=torch.float64, device=dev)
+        ex = torch.empty(ns, dtype=torch.float64, device=dev)
+        nacc = torch.empty(ns, dtype=torch.int32, device=dev)
+        _lib.call("qtx_resconv_sweep", mdt, _lib.ptr(m.params), *_shape_args(m), m.final, _lib.ptr(spins), ns,
+                  int(nsweeps), int(kind), _lib.ptr(nbr), int(max_nb), int(hop), float(reweight),
+                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(step0), int(chain0), _lib.ptr(sig), _lib.ptr(ex), _lib.ptr(nacc),
+                  _lib.ptr(ws), wsz, _lib.stream())
+        out = ScaleArray(sig, ex)
+        return out, out, nacc, None
     psi = state(spins)  # bare model or symmetry-projected, LogArray or ScaleArray
     mult, expo = psi.mult.contiguous(), psi.expo.contiguous()
     accept = "qtx_metropolis_accept_cplx" if mult.is_complex() else "qtx_metropolis_accept"

@@ -272,3 +272,24 @@ def test_sweep_of_moved_proposals_only_equals_full_sweep(qtx, monkeypatch, cplx)
             assert ref["margin"][t, c] < 1e-3
     finally:
         qtx.set_default_dtype(torch.float64)
+
+
+@pytest.mark.parametrize("kind,dtype", [("exchange", torch.float32), ("localflip", torch.float32), ("exchange", torch.float64)])
+def test_one_call_sweep_equals_the_step_by_step_sweep(qtx, kind, dtype):
+    """qtx_resconv_sweep (the whole sweep behind one C-ABI call: what a jax.ffi binder would register) against the
+    step-by-step entry points driven from Python, on the production Philox stream: identical chains, accept counts
+    and amplitudes."""
+    nup = (32, 32) if kind == "exchange" else None
+    outs = []
+    for record in (False, True):  # record=True keeps the Python loop (it needs the per-step accept log)
+        qtx.set_random_seed(77)
+        lattice_pair(qtx, "square", 8, nup)
+        model, _ = make_resconv(qtx, (8, 8), 2, 16, 3, dtype, "sinhp1", seed=9)
+        state = qtx.state.Variational(model)
+        cls = qtx.sampler.SpinExchange if kind == "exchange" else qtx.sampler.LocalFlip
+        sampler = cls(state, 96, thermal_steps=0)
+        samples = sampler.sweep(40, record=record)
+        outs.append((to_np(samples.spins), to_np(samples.psi.significand), to_np(samples.psi.exponent),
+                     to_np(sampler.last_naccept)))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
