@@ -66,12 +66,35 @@ __device__ __forceinline__ void cfma_(cplx& acc, cplx a, cplx b) {  // acc += a 
   acc.y += a.x * b.y;
   acc.y += a.y * b.x;
 }
-__device__ __forceinline__ cplx crecip(cplx d) {  // 1 / d, scaled against overflow of |d|^2
-  const double s = fmax(fabs(d.x), fabs(d.y));
-  if (s == 0.0) return cmake(0.0, 0.0);
-  const double a = d.x / s, b = d.y / s;
-  const double q = 1.0 / ((a * a + b * b) * s);
-  return cmake(a * q, -b * q);
+// 1 / s for a positive finite double without the IEEE division sequence (it sits on the pivot-to-pivot critical path
+// of the factorisation): exponent removed by bit manipulation, float reciprocal of the mantissa, three Newton steps
+// (23 -> 46 -> 92 bits, the third one absorbs the rounding of the first two).
+__device__ __forceinline__ double fast_recip_pos(double s) {
+#ifdef QTX_HOST_EMULATION
+  return 1.0 / s;
+#else
+  const int hi = __double2hiint(s);
+  const int ex = ((hi >> 20) & 0x7ff) - 1023;               // unbiased exponent
+  if (ex < -1000 || ex > 1000) return 1.0 / s;               // subnormal / huge: the slow exact path
+  const double m = __hiloint2double(hi - (ex << 20), __double2loint(s));  // s 2^-ex in [1, 2)
+  double r = (double)__frcp_rn((float)m);
+  r = r * (2.0 - m * r);
+  r = r * (2.0 - m * r);
+  r = r * (2.0 - m * r);
+  return __hiloint2double(__double2hiint(r) - (ex << 20), __double2loint(r));  // r 2^-ex
+#endif
+}
+__device__ __forceinline__ cplx crecip(cplx d) {  // 1 / d = conj(d) / |d|^2
+  const double s = d.x * d.x + d.y * d.y;
+  if (!(s > 0.0)) return cmake(0.0, 0.0);
+  if (s > 1e300 || s < 1e-300) {  // |d|^2 out of range: scale first
+    const double m = fmax(fabs(d.x), fabs(d.y));
+    const double a = d.x / m, b = d.y / m;
+    const double q = 1.0 / ((a * a + b * b) * m);
+    return cmake(a * q, -b * q);
+  }
+  const double r = fast_recip_pos(s);
+  return cmake(d.x * r, -d.y * r);
 }
 __device__ __forceinline__ unsigned ld_flag(const unsigned* p) { return *(const volatile unsigned*)p; }
 __device__ __forceinline__ cplx ld_cg(const cplx* p) {  // a value another CTA of this launch has just published
@@ -494,35 +517,38 @@ __global__ void __launch_bounds__(kThreads) ztrsv_kernel(const cplx* __restrict_
   const int col = tid % kNB, q = tid / kNB;        // backward: (column, part) -- coalesced along the rows of M
   cplx mine = cmake(0.0, 0.0);
   const int jbeg = kBackward ? nblk - 1 : 0, jend = b, jstep = kBackward ? -1 : 1;
+  // the coefficients of block (b, j) do not depend on x_j: they are fetched into registers BEFORE waiting for its
+  // flag, so that only the flag, the 64 values of x_j and 16 complex FMAs per thread sit on the dependency chain
+  constexpr int kPer = kNB / kTPR;  // coefficients per thread and block
+  cplx coef[kPer];
+  auto fetch = [&](int j) {
+    const int64_t j0 = (int64_t)j * kNB;
+    const int nj = (int)((n - j0) < kNB ? (n - j0) : kNB);
+#pragma unroll
+    for (int t = 0; t < kPer; ++t) {
+      cplx v = cmake(0.0, 0.0);
+      if (!kBackward) {
+        const int c = p + kTPR * t;
+        if (line < nr && c < nj) v = M[(i0 + line) * n + j0 + c];
+      } else {
+        const int r = q + kTPR * t;
+        if (col < nr && r < nj) v = M[(j0 + r) * n + i0 + col];
+      }
+      coef[t] = v;
+    }
+  };
+  if (jbeg != jend) fetch(jbeg);
   for (int j = jbeg; j != jend; j += jstep) {
     if (tid == 0) spin_until_set(sync + 1 + j);  // bounded: a dependency that never arrives traps instead of hanging
     __syncthreads();
     fence_all();
     const int64_t j0 = (int64_t)j * kNB;
     const int nj = (int)((n - j0) < kNB ? (n - j0) : kNB);
-    if (tid < kNB) {
-#ifdef QTX_HOST_EMULATION
-      xj[tid] = tid < nj ? x[j0 + tid] : cmake(0.0, 0.0);
-#else
-      cplx v = cmake(0.0, 0.0);
-      if (tid < nj) {
-        const double2 t = __ldcg(reinterpret_cast<const double2*>(x + j0 + tid));
-        v = cmake(t.x, t.y);
-      }
-      xj[tid] = v;
-#endif
-    }
+    if (tid < kNB) xj[tid] = tid < nj ? ld_cg(x + j0 + tid) : cmake(0.0, 0.0);
     __syncthreads();
-    if (!kBackward) {
-      if (line < nr) {
-        const cplx* row = M + (i0 + line) * n + j0;
-        for (int c = p; c < nj; c += kTPR) cfms(mine, row[c], xj[c]);
-      }
-    } else {
-      if (col < nr) {
-        for (int r = q; r < nj; r += kTPR) cfms(mine, M[(j0 + r) * n + i0 + col], xj[r]);
-      }
-    }
+#pragma unroll
+    for (int t = 0; t < kPer; ++t) cfms(mine, coef[t], xj[(kBackward ? q : p) + kTPR * t]);
+    if (j + jstep != jend) fetch(j + jstep);
     __syncthreads();  // xj is rewritten by the next block
   }
   if (!kBackward) part[line * kTPR + p] = mine;

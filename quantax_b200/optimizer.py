@@ -119,7 +119,7 @@ def _eig_workspace(n: int):
 #              eigen-quantity callers -- SNR damping, minsr_pinv_eig / pinvh_solve, rtol = atol = 0 -- keep using)
 PINV_METHOD = os.environ.get("QTX_PINV", "ldlt")
 LANCZOS_STEPS = max(1, min(1024, int(os.environ.get("QTX_LANCZOS_STEPS", "512"))))  # upper bound of the adaptive run
-REFINE_STEPS = int(os.environ.get("QTX_PINV_REFINE", "3"))
+REFINE_STEPS = int(os.environ.get("QTX_PINV_REFINE", "2"))  # corrections 2e-5 -> 4e-10 -> 7e-15 (measured)
 # two consecutive stages (k, 2k steps) of the Lanczos run must agree to this: the error of an extreme Ritz value after
 # 2k steps is about the square of its error after k steps, so the accepted value is good to ~1e-14; max|lambda| only
 # enters through the cut-off c = rtol max|lambda| + atol, to which f is insensitive away from the cut-off
