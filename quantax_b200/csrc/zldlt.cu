@@ -201,16 +201,33 @@ __device__ __forceinline__ void tile_ldlt(double (&tr)[kFI][kFJ][2], double (&ti
           for (int fi = 0; fi < kFI; ++fi) w[tp.row(fi)] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
         }
     __syncthreads();
+    // everything this step reads from shared memory, loaded up front (independent 16-byte loads in flight together)
     cplx d = w[k];
+    cplx wi[kFI], wj[kFJ][2];
+#pragma unroll
+    for (int fi = 0; fi < kFI; ++fi) wi[fi] = w[tp.row(fi)];
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj) {
+      wj[fj][0] = w[tp.col(fj, 0)];
+      wj[fj][1] = w[tp.col(fj, 1)];
+    }
     const bool zero = (d.x == 0.0 && d.y == 0.0);
     if (zero) d = cmake(1.0, 0.0);  // reported below; the factorisation continues with finite numbers
     const cplx inv = crecip(d);
+    // fragment (fi, fj) spans rows [row(fi) - g, +8) and columns [col(fj, 0) - 2 q, +8): fragments that lie entirely
+    // above the diagonal, or entirely in finished rows / columns, are skipped by the whole warp
+    const int rbase = tp.row0 - ((threadIdx.x & 31) >> 2), cbase = tp.col0 - 2 * (threadIdx.x & 3);
 #pragma unroll
     for (int fi = 0; fi < kFI; ++fi) {
       const int i = tp.row(fi);
-      const cplx li = cmul_(w[i], inv);
+      const int rlo = rbase + 8 * fi;
+      if (rlo + 7 < k) continue;
+      const cplx li = cmul_(wi[fi], inv);
+      const bool below = i > k && i < nb;
 #pragma unroll
-      for (int fj = 0; fj < kFJ; ++fj)
+      for (int fj = 0; fj < kFJ; ++fj) {
+        const int clo = cbase + 8 * fj;
+        if (clo + 7 < k || clo > rlo + 7) continue;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = tp.col(fj, e);
@@ -219,15 +236,15 @@ __device__ __forceinline__ void tile_ldlt(double (&tr)[kFI][kFJ][2], double (&ti
             ti[fi][fj][e] = d.y;
             dinv_s[k] = inv;
             if (zero && info[0] == 0) info[0] = (int32_t)(global_col0 + k + 1);
-          } else if (j == k && i > k && i < nb) {
+          } else if (j == k && below) {
             tr[fi][fj][e] = li.x;
             ti[fi][fj][e] = li.y;
-          } else if (j > k && j <= i && i < nb) {
-            const cplx wj = w[j];
-            tr[fi][fj][e] -= li.x * wj.x - li.y * wj.y;
-            ti[fi][fj][e] -= li.x * wj.y + li.y * wj.x;
+          } else if (j > k && j <= i && below) {
+            tr[fi][fj][e] -= li.x * wj[fj][e].x - li.y * wj[fj][e].y;
+            ti[fi][fj][e] -= li.x * wj[fj][e].y + li.y * wj[fj][e].x;
           }
         }
+      }
     }
   }
   __syncthreads();  // dinv_s complete
@@ -248,21 +265,31 @@ __device__ __forceinline__ void tile_panel(double (&tr)[kFI][kFJ][2], double (&t
           for (int fi = 0; fi < kFI; ++fi) x[tp.row(fi)] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
         }
     __syncthreads();
+    cplx xr[kFI], lc[kFJ][2];  // loaded up front; Ls above the diagonal is never written and never used
 #pragma unroll
-    for (int fj = 0; fj < kFJ; ++fj)
+    for (int fi = 0; fi < kFI; ++fi) xr[fi] = x[tp.row(fi)];
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj) {
+      lc[fj][0] = Ls[tp.col(fj, 0) * kPad + c];
+      lc[fj][1] = Ls[tp.col(fj, 1) * kPad + c];
+    }
+    const int cbase = tp.col0 - 2 * (threadIdx.x & 3);
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj) {
+      if (cbase + 8 * fj + 7 <= c) continue;  // all eight columns of this fragment are final (warp-uniform)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = tp.col(fj, e);
         if (j > c && j < nb) {
-          const cplx l = Ls[j * kPad + c];
+          const cplx l = lc[fj][e];
 #pragma unroll
           for (int fi = 0; fi < kFI; ++fi) {
-            const cplx xr = x[tp.row(fi)];
-            tr[fi][fj][e] -= xr.x * l.x - xr.y * l.y;
-            ti[fi][fj][e] -= xr.x * l.y + xr.y * l.x;
+            tr[fi][fj][e] -= xr[fi].x * l.x - xr[fi].y * l.y;
+            ti[fi][fj][e] -= xr[fi].x * l.y + xr[fi].y * l.x;
           }
         }
       }
+    }
   }
 }
 
