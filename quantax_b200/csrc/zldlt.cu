@@ -214,8 +214,13 @@ __device__ __forceinline__ void tile_ldlt(double (&tr)[kFI][kFJ][2], double (&ti
     const bool zero = (d.x == 0.0 && d.y == 0.0);
     if (zero) d = cmake(1.0, 0.0);  // reported below; the factorisation continues with finite numbers
     const cplx inv = crecip(d);
+    if (threadIdx.x == 0) {
+      dinv_s[k] = inv;
+      if (zero && info[0] == 0) info[0] = (int32_t)(global_col0 + k + 1);
+    }
     // fragment (fi, fj) spans rows [row(fi) - g, +8) and columns [col(fj, 0) - 2 q, +8): fragments that lie entirely
-    // above the diagonal, or entirely in finished rows / columns, are skipped by the whole warp
+    // above the diagonal, or entirely in finished rows / columns, are skipped by the whole warp; inside a fragment
+    // the three cases (pivot, column of L, trailing update) are selects, not branches
     const int rbase = tp.row0 - ((threadIdx.x & 31) >> 2), cbase = tp.col0 - 2 * (threadIdx.x & 3);
 #pragma unroll
     for (int fi = 0; fi < kFI; ++fi) {
@@ -231,18 +236,11 @@ __device__ __forceinline__ void tile_ldlt(double (&tr)[kFI][kFJ][2], double (&ti
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = tp.col(fj, e);
-          if (i == k && j == k) {
-            tr[fi][fj][e] = d.x;
-            ti[fi][fj][e] = d.y;
-            dinv_s[k] = inv;
-            if (zero && info[0] == 0) info[0] = (int32_t)(global_col0 + k + 1);
-          } else if (j == k && below) {
-            tr[fi][fj][e] = li.x;
-            ti[fi][fj][e] = li.y;
-          } else if (j > k && j <= i && below) {
-            tr[fi][fj][e] -= li.x * wj[fj][e].x - li.y * wj[fj][e].y;
-            ti[fi][fj][e] -= li.x * wj[fj][e].y + li.y * wj[fj][e].x;
-          }
+          const double ur = tr[fi][fj][e] - (li.x * wj[fj][e].x - li.y * wj[fj][e].y);
+          const double ui = ti[fi][fj][e] - (li.x * wj[fj][e].y + li.y * wj[fj][e].x);
+          const bool pivot = (i == k) & (j == k), lcol = (j == k) & below, upd = (j > k) & (j <= i) & below;
+          tr[fi][fj][e] = pivot ? d.x : (lcol ? li.x : (upd ? ur : tr[fi][fj][e]));
+          ti[fi][fj][e] = pivot ? d.y : (lcol ? li.y : (upd ? ui : ti[fi][fj][e]));
         }
       }
     }
@@ -280,13 +278,14 @@ __device__ __forceinline__ void tile_panel(double (&tr)[kFI][kFJ][2], double (&t
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = tp.col(fj, e);
-        if (j > c && j < nb) {
-          const cplx l = lc[fj][e];
+        const bool upd = (j > c) & (j < nb);
+        const cplx l = lc[fj][e];
 #pragma unroll
-          for (int fi = 0; fi < kFI; ++fi) {
-            tr[fi][fj][e] -= xr[fi].x * l.x - xr[fi].y * l.y;
-            ti[fi][fj][e] -= xr[fi].x * l.y + xr[fi].y * l.x;
-          }
+        for (int fi = 0; fi < kFI; ++fi) {  // select, not branch: the lanes of a warp hold different columns
+          const double ur = tr[fi][fj][e] - (xr[fi].x * l.x - xr[fi].y * l.y);
+          const double ui = ti[fi][fj][e] - (xr[fi].x * l.y + xr[fi].y * l.x);
+          tr[fi][fj][e] = upd ? ur : tr[fi][fj][e];
+          ti[fi][fj][e] = upd ? ui : ti[fi][fj][e];
         }
       }
     }
