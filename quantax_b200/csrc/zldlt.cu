@@ -96,7 +96,18 @@ __device__ __forceinline__ cplx crecip(cplx d) {  // 1 / d = conj(d) / |d|^2
   const double r = fast_recip_pos(s);
   return cmake(d.x * r, -d.y * r);
 }
-__device__ __forceinline__ unsigned ld_flag(const unsigned* p) { return *(const volatile unsigned*)p; }
+// Hand-over between CTAs of one launch (CUTLASS semaphore pattern): the producer's threads write, __syncthreads(), then
+// ONE thread stores the flag with release semantics at gpu scope (cumulative over the barrier); the consumer's thread
+// 0 polls with acquire loads, __syncthreads(), and everybody reads the published data through L2 (ld.global.cg).
+__device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
+#ifdef QTX_HOST_EMULATION
+  return *(const volatile unsigned*)p;
+#else
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
 __device__ __forceinline__ cplx ld_cg(const cplx* p) {  // a value another CTA of this launch has just published
 #ifdef QTX_HOST_EMULATION
   return *p;
@@ -115,16 +126,11 @@ __device__ __forceinline__ void spin_until_set(const unsigned* flag) {  // one t
     }
   }
 }
-__device__ __forceinline__ void publish(unsigned* flag) {
+__device__ __forceinline__ void publish(unsigned* flag) {  // by one thread, after the __syncthreads() behind the writes
 #ifdef QTX_HOST_EMULATION
   *flag = 1u;
 #else
-  atomicExch(flag, 1u);
-#endif
-}
-__device__ __forceinline__ void fence_all() {
-#ifndef QTX_HOST_EMULATION
-  __threadfence();
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
 #endif
 }
 
@@ -186,109 +192,86 @@ __device__ __forceinline__ TilePos tile_pos() {
   return {(w / kWC) * kWTR + (l >> 2), (w % kWC) * kWTC + 2 * (l & 3)};
 }
 
-// in-register LDL^T of the leading nb x nb block of the tile (lower triangle; the upper triangle of the registers is
-// never read).  wv: shared [2][kNB] complex, dinv_s: shared [kNB].  One barrier per column.
-__device__ __forceinline__ void tile_ldlt(double (&tr)[kFI][kFJ][2], double (&ti)[kFI][kFJ][2], const TilePos tp, int nb,
-                                          cplx* wv, cplx* dinv_s, int32_t* info, int64_t global_col0) {
+// The pivot sweeps below run on a tile in SHARED memory with a compact loop body: one barrier-to-barrier step of the
+// factorisation is a dependent chain of a few hundred cycles (measured: barrier 30, STS-BAR-LDS 90, reciprocal 90,
+// DFMA 9), and an unrolled in-register version -- 850 instructions per step, executed once per step -- was bound by
+// instruction fetch instead (2 260 cycles per step).  Threads form a kTX x kTX grid, thread (ty, tx) handles the
+// elements (ty + kTX a, tx + kTX c).
+#ifdef QTX_HOST_EMULATION
+constexpr int kTX = 8;
+#else
+constexpr int kTX = 16;
+#endif
+static_assert(kTX * kTX == kThreads && kNB % kTX == 0, "thread grid of the shared-memory sweeps");
+constexpr int kEP = kNB / kTX;  // elements per thread and dimension
+
+// LDL^T of the leading nb x nb block of the shared tile A [kNB][kPad] (lower triangle; the upper triangle is never
+// read): on exit L below the diagonal, D on it, 1 / D in dinv_s.  wv, lv: shared [kNB].  Two barriers per column.
+__device__ __forceinline__ void tile_ldlt(cplx* A, int nb, cplx* wv, cplx* lv, cplx* dinv_s, int32_t* info,
+                                          int64_t global_col0) {
+  const int tid = threadIdx.x, tx = tid % kTX, ty = tid / kTX;
   for (int k = 0; k < nb; ++k) {
-    cplx* w = wv + (k & 1) * kNB;
-#pragma unroll
-    for (int fj = 0; fj < kFJ; ++fj)
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-        if (tp.col(fj, e) == k) {
-#pragma unroll
-          for (int fi = 0; fi < kFI; ++fi) w[tp.row(fi)] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
-        }
-    __syncthreads();
-    // everything this step reads from shared memory, loaded up front (independent 16-byte loads in flight together)
-    cplx d = w[k];
-    cplx wi[kFI], wj[kFJ][2];
-#pragma unroll
-    for (int fi = 0; fi < kFI; ++fi) wi[fi] = w[tp.row(fi)];
-#pragma unroll
-    for (int fj = 0; fj < kFJ; ++fj) {
-      wj[fj][0] = w[tp.col(fj, 0)];
-      wj[fj][1] = w[tp.col(fj, 1)];
-    }
-    const bool zero = (d.x == 0.0 && d.y == 0.0);
-    if (zero) d = cmake(1.0, 0.0);  // reported below; the factorisation continues with finite numbers
-    const cplx inv = crecip(d);
-    if (threadIdx.x == 0) {
-      dinv_s[k] = inv;
-      if (zero && info[0] == 0) info[0] = (int32_t)(global_col0 + k + 1);
-    }
-    // fragment (fi, fj) spans rows [row(fi) - g, +8) and columns [col(fj, 0) - 2 q, +8): fragments that lie entirely
-    // above the diagonal, or entirely in finished rows / columns, are skipped by the whole warp; inside a fragment
-    // the three cases (pivot, column of L, trailing update) are selects, not branches
-    const int rbase = tp.row0 - ((threadIdx.x & 31) >> 2), cbase = tp.col0 - 2 * (threadIdx.x & 3);
-#pragma unroll
-    for (int fi = 0; fi < kFI; ++fi) {
-      const int i = tp.row(fi);
-      const int rlo = rbase + 8 * fi;
-      if (rlo + 7 < k) continue;
-      const cplx li = cmul_(wi[fi], inv);
-      const bool below = i > k && i < nb;
-#pragma unroll
-      for (int fj = 0; fj < kFJ; ++fj) {
-        const int clo = cbase + 8 * fj;
-        if (clo + 7 < k || clo > rlo + 7) continue;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = tp.col(fj, e);
-          const double ur = tr[fi][fj][e] - (li.x * wj[fj][e].x - li.y * wj[fj][e].y);
-          const double ui = ti[fi][fj][e] - (li.x * wj[fj][e].y + li.y * wj[fj][e].x);
-          const bool pivot = (i == k) & (j == k), lcol = (j == k) & below, upd = (j > k) & (j <= i) & below;
-          tr[fi][fj][e] = pivot ? d.x : (lcol ? li.x : (upd ? ur : tr[fi][fj][e]));
-          ti[fi][fj][e] = pivot ? d.y : (lcol ? li.y : (upd ? ui : ti[fi][fj][e]));
-        }
+    if (tid < nb) {  // column k: w_i = A[i][k] (what the trailing update needs), l_i = w_i / d
+      cplx d = A[k * kPad + k];
+      const bool zero = (d.x == 0.0 && d.y == 0.0);
+      if (zero) d = cmake(1.0, 0.0);  // reported; the factorisation continues with finite numbers
+      const cplx inv = crecip(d);
+      const cplx w = A[tid * kPad + k];
+      const cplx l = cmul_(w, inv);
+      wv[tid] = w;
+      lv[tid] = l;
+      if (tid > k) A[tid * kPad + k] = l;
+      if (tid == k) {
+        A[k * kPad + k] = d;
+        dinv_s[k] = inv;
+        if (zero && info[0] == 0) info[0] = (int32_t)(global_col0 + k + 1);
       }
     }
+    __syncthreads();
+    // trailing update of rows / columns k+1 .. nb-1 (lower triangle): first element index of this thread beyond k
+    const int a0 = (k + 1 - ty + kTX - 1 > 0) ? (k + 1 - ty + kTX - 1) / kTX : 0;
+    const int c0 = (k + 1 - tx + kTX - 1 > 0) ? (k + 1 - tx + kTX - 1) / kTX : 0;
+    for (int a = a0; a < kEP; ++a) {
+      const int i = ty + kTX * a;
+      if (i >= nb) break;
+      const cplx li = lv[i];
+#pragma unroll
+      for (int c = 0; c < kEP; ++c) {
+        const int j = tx + kTX * c;
+        if (c >= c0 && j <= i) cfms(A[i * kPad + j], li, wv[j]);
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();  // dinv_s complete
 }
 
-// in-register panel solve: the tile holds rows of A21 (nb columns); on exit it holds W = A21 L11^-T.
-// Ls: shared [kNB][kPad] with L11 strictly below the diagonal; xc: shared [2][kNB].
-__device__ __forceinline__ void tile_panel(double (&tr)[kFI][kFJ][2], double (&ti)[kFI][kFJ][2], const TilePos tp, int nb,
-                                           const cplx* Ls, cplx* xc) {
-  for (int c = 0; c + 1 < nb; ++c) {
-    cplx* x = xc + (c & 1) * kNB;
-#pragma unroll
-    for (int fj = 0; fj < kFJ; ++fj)
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-        if (tp.col(fj, e) == c) {
-#pragma unroll
-          for (int fi = 0; fi < kFI; ++fi) x[tp.row(fi)] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
-        }
-    __syncthreads();
-    cplx xr[kFI], lc[kFJ][2];  // loaded up front; Ls above the diagonal is never written and never used
-#pragma unroll
-    for (int fi = 0; fi < kFI; ++fi) xr[fi] = x[tp.row(fi)];
-#pragma unroll
-    for (int fj = 0; fj < kFJ; ++fj) {
-      lc[fj][0] = Ls[tp.col(fj, 0) * kPad + c];
-      lc[fj][1] = Ls[tp.col(fj, 1) * kPad + c];
+// panel solve on the shared tile X [kNB][kPad] (nr rows of A21, nb columns): on exit W = A21 L11^-T.  L11 (published
+// by the diagonal CTA of this launch, read through L2) is staged kLC columns at a time in Lc [kNB][kLC + 1]; one
+// barrier per column plus two per chunk.
+constexpr int kLC = 16;
+__device__ __forceinline__ void tile_panel(cplx* X, int nr, int nb, const cplx* L11g, int64_t ldg, cplx* Lc) {
+  const int tid = threadIdx.x, tx = tid % kTX, ty = tid / kTX;
+  for (int c = 0; c + 1 < nb; ++c) {  // column c is final: remove it from the columns behind it
+    if (c % kLC == 0) {
+      __syncthreads();  // the previous chunk is no longer read
+      for (int idx = tid; idx < kNB * kLC; idx += kThreads) {
+        const int j = idx / kLC, cc = idx % kLC;
+        if (j < nb && c + cc < j) Lc[j * (kLC + 1) + cc] = ld_cg(L11g + (int64_t)j * ldg + c + cc);
+      }
+      __syncthreads();
     }
-    const int cbase = tp.col0 - 2 * (threadIdx.x & 3);
+    const int q0 = (c + 1 - tx + kTX - 1 > 0) ? (c + 1 - tx + kTX - 1) / kTX : 0;
+    for (int q = q0; q < kEP; ++q) {
+      const int j = tx + kTX * q;
+      if (j >= nb) break;
+      const cplx l = Lc[j * (kLC + 1) + c % kLC];
 #pragma unroll
-    for (int fj = 0; fj < kFJ; ++fj) {
-      if (cbase + 8 * fj + 7 <= c) continue;  // all eight columns of this fragment are final (warp-uniform)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = tp.col(fj, e);
-        const bool upd = (j > c) & (j < nb);
-        const cplx l = lc[fj][e];
-#pragma unroll
-        for (int fi = 0; fi < kFI; ++fi) {  // select, not branch: the lanes of a warp hold different columns
-          const double ur = tr[fi][fj][e] - (xr[fi].x * l.x - xr[fi].y * l.y);
-          const double ui = ti[fi][fj][e] - (xr[fi].x * l.y + xr[fi].y * l.x);
-          tr[fi][fj][e] = upd ? ur : tr[fi][fj][e];
-          ti[fi][fj][e] = upd ? ui : ti[fi][fj][e];
-        }
+      for (int a = 0; a < kEP; ++a) {
+        const int r = ty + kTX * a;
+        if (r < nr) cfms(X[r * kPad + j], X[r * kPad + c], l);
       }
     }
+    __syncthreads();
   }
 }
 
@@ -425,57 +408,46 @@ __global__ void __launch_bounds__(kThreads, 2) zldlt_step_kernel(const StepArgs 
     }
     return;
   }
+  // ---- column tile: move the updated tile from the accumulator registers into shared memory -----------------------
+  cplx* Xs = smc;  // [kNB][kPad]   (the operand stages are no longer needed: every thread is past its last barrier)
+#pragma unroll
+  for (int fi = 0; fi < kFI; ++fi)
+#pragma unroll
+    for (int fj = 0; fj < kFJ; ++fj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) Xs[tp.row(fi) * kPad + tp.col(fj, e)] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
+  __syncthreads();
   const int nb = nc;  // width of block column t0
   if (I == 0) {
-    // ---- the next diagonal block: factorise in registers, publish L11 / D / 1/D ---------------------------------
-    cplx* wv = smc;                 // [2][kNB]
-    cplx* dinv_s = smc + 2 * kNB;   // [kNB]
-    tile_ldlt(tr, ti, tp, nb, wv, dinv_s, a.info, a.t0);
-#pragma unroll
-    for (int fi = 0; fi < kFI; ++fi) {
-      const int r = tp.row(fi);
-#pragma unroll
-      for (int fj = 0; fj < kFJ; ++fj)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = tp.col(fj, e);
-          if (r < nb && c <= r) a.M[(a.t0 + r) * n + a.t0 + c] = cmake(tr[fi][fj][e], ti[fi][fj][e]);
-        }
+    // ---- the next diagonal block: factorise, publish L11 / D / 1/D ----------------------------------------------
+    cplx* wv = Xs + kNB * kPad;   // [kNB]
+    cplx* lv = wv + kNB;          // [kNB]
+    cplx* dinv_s = lv + kNB;      // [kNB]
+    tile_ldlt(Xs, nb, wv, lv, dinv_s, a.info, a.t0);
+    for (int idx = tid; idx < nb * kNB; idx += kThreads) {
+      const int r = idx / kNB, c = idx % kNB;
+      if (c <= r) a.M[(a.t0 + r) * n + a.t0 + c] = Xs[r * kPad + c];
     }
     if (tid < nb) a.dinvg[a.t0 + tid] = dinv_s[tid];
-    fence_all();
     __syncthreads();
     if (tid == 0) publish(a.sync + 1);
     return;
   }
   // ---- a tile below it: wait for the diagonal block, then W = A21 L11^-T, L21 = W D^-1 ---------------------------
-  cplx* Ls = smc;                        // [kNB][kPad]
-  cplx* xc = smc + kNB * kPad;           // [2][kNB]
-  cplx* dinv_s = xc + 2 * kNB;           // [kNB]
+  cplx* Lc = Xs + kNB * kPad;            // [kNB][kLC + 1]
+  cplx* dinv_s = Lc + kNB * (kLC + 1);   // [kNB]
   if (tid == 0) spin_until_set(a.sync + 1);
   __syncthreads();
-  fence_all();
-  for (int idx = tid; idx < nb * nb; idx += kThreads) {
-    const int i = idx / nb, j = idx % nb;
-    if (j < i) Ls[i * kPad + j] = ld_cg(a.M + (a.t0 + i) * n + a.t0 + j);
-  }
   if (tid < nb) dinv_s[tid] = ld_cg(a.dinvg + a.t0 + tid);
+  tile_panel(Xs, nr, nb, a.M + a.t0 * n + a.t0, n, Lc);
   __syncthreads();
-  tile_panel(tr, ti, tp, nb, Ls, xc);
-#pragma unroll
-  for (int fi = 0; fi < kFI; ++fi) {
-    const int r = tp.row(fi);
-#pragma unroll
-    for (int fj = 0; fj < kFJ; ++fj)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = tp.col(fj, e);
-        if (r < nr && c < nb) {
-          const cplx wv = cmake(tr[fi][fj][e], ti[fi][fj][e]);
-          a.Wnext[(i0 + r) * kNB + c] = wv;
-          a.M[(i0 + r) * n + a.t0 + c] = cmul_(wv, dinv_s[c]);
-        }
-      }
+  for (int idx = tid; idx < nr * kNB; idx += kThreads) {
+    const int r = idx / kNB, c = idx % kNB;
+    if (c < nb) {
+      const cplx wv = Xs[r * kPad + c];
+      a.Wnext[(i0 + r) * kNB + c] = wv;
+      a.M[(i0 + r) * n + a.t0 + c] = cmul_(wv, dinv_s[c]);
+    }
   }
 }
 
@@ -567,7 +539,6 @@ __global__ void __launch_bounds__(kThreads) ztrsv_kernel(const cplx* __restrict_
   for (int j = jbeg; j != jend; j += jstep) {
     if (tid == 0) spin_until_set(sync + 1 + j);  // bounded: a dependency that never arrives traps instead of hanging
     __syncthreads();
-    fence_all();
     const int64_t j0 = (int64_t)j * kNB;
     const int nj = (int)((n - j0) < kNB ? (n - j0) : kNB);
     if (tid < kNB) xj[tid] = tid < nj ? ld_cg(x + j0 + tid) : cmake(0.0, 0.0);
@@ -609,17 +580,8 @@ __global__ void __launch_bounds__(kThreads) ztrsv_kernel(const cplx* __restrict_
     }
     x[i0 + tid] = v;
   }
-#ifndef QTX_HOST_EMULATION
-  __threadfence();
-#endif
   __syncthreads();
-  if (tid == 0) {
-#ifdef QTX_HOST_EMULATION
-    sync[1 + b] = 1u;
-#else
-    atomicExch(sync + 1 + b, 1u);
-#endif
-  }
+  if (tid == 0) publish(sync + 1 + b);
 }
 
 __global__ void zero_sync_kernel(unsigned* sync, int count) {
@@ -630,7 +592,7 @@ __global__ void zero_sync_kernel(unsigned* sync, int count) {
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 constexpr size_t kSmemPlanes = (size_t)2 * 2 * kNB * kKP * sizeof(cplx);  // two stages of (W, L)
-constexpr size_t kSmemPanelStage = (size_t)(kNB * kPad + 3 * kNB) * sizeof(cplx);
+constexpr size_t kSmemPanelStage = (size_t)(kNB * kPad + kNB * (kLC + 1) + 3 * kNB) * sizeof(cplx);  // tile + L11 chunk
 constexpr size_t kSmemStep = kSmemPlanes > kSmemPanelStage ? kSmemPlanes : kSmemPanelStage;
 constexpr size_t kSmemInv = (size_t)(2 * kNB * kPad) * sizeof(cplx);
 constexpr size_t kSmemTrsv = (size_t)(kNB * kPad + 2 * kNB + kNB * kTPR) * sizeof(cplx);

@@ -23,6 +23,14 @@ from .global_defs import PARTICLE_TYPE, device, get_seed, get_sites, get_subkeys
 from .utils import LogArray, ScaleArray, log_abs, rand_states
 
 
+# QTX_DRIFT_CHECK=1: run the reference's post-sweep drift check (metropolis.py:201-213) after every sweep of a state
+# with local updates; off by default because it costs a device -> host read-back per sweep (check_local_updates()
+# does the same on demand)
+import os as _os
+
+DRIFT_CHECK = _os.environ.get("QTX_DRIFT_CHECK", "0") == "1"
+
+
 @dataclass(frozen=True)
 class Samples:
     """quantax/sampler/samples.py:11-74."""
@@ -184,7 +192,12 @@ class Metropolis(Sampler):
             self._rank * self._nlocal, injected, record)
         self._step += nsweeps
         self.last_accept_log, self.last_naccept, self.last_psi_chain = log, nacc, psi_chain
-        return Samples(self._spins.clone(), psi, None, self._get_reweight_factor(psi))
+        samples = Samples(self._spins.clone(), psi, None, self._get_reweight_factor(psi))
+        if DRIFT_CHECK and state.use_ref:
+            # the reference compares the local-update amplitudes with a direct forward pass after EVERY sweep and
+            # warns (metropolis.py:201-213); that read-back synchronises the host, so it is behind QTX_DRIFT_CHECK=1
+            self.check_local_updates(samples)
+        return samples
 
     def check_local_updates(self, samples: Samples) -> int:
         """The reference's post-sweep drift check (metropolis.py:201-212), on demand: it needs a
