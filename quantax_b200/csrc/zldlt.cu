@@ -228,19 +228,29 @@ __device__ __forceinline__ void tile_ldlt(cplx* A, int nb, cplx* wv, cplx* lv, c
       }
     }
     __syncthreads();
-    // trailing update of rows / columns k+1 .. nb-1 (lower triangle): first element index of this thread beyond k
-    const int a0 = (k + 1 - ty + kTX - 1 > 0) ? (k + 1 - ty + kTX - 1) / kTX : 0;
-    const int c0 = (k + 1 - tx + kTX - 1 > 0) ? (k + 1 - tx + kTX - 1) / kTX : 0;
-    for (int a = a0; a < kEP; ++a) {
-      const int i = ty + kTX * a;
-      if (i >= nb) break;
-      const cplx li = lv[i];
+    // trailing update of rows / columns k+1 .. nb-1 (lower triangle).  All loads first, then the arithmetic, then the
+    // stores: element by element the compiler has to order every store before the next load (same pointer type)
+    cplx wj[kEP], li[kEP], v[kEP][kEP];
+    bool m[kEP][kEP];
+#pragma unroll
+    for (int c = 0; c < kEP; ++c) wj[c] = wv[tx + kTX * c];
+#pragma unroll
+    for (int a = 0; a < kEP; ++a) li[a] = lv[ty + kTX * a];
+#pragma unroll
+    for (int a = 0; a < kEP; ++a)
 #pragma unroll
       for (int c = 0; c < kEP; ++c) {
-        const int j = tx + kTX * c;
-        if (c >= c0 && j <= i) cfms(A[i * kPad + j], li, wv[j]);
+        const int i = ty + kTX * a, j = tx + kTX * c;
+        m[a][c] = (j > k) & (j <= i) & (i < nb);
+        v[a][c] = m[a][c] ? A[i * kPad + j] : cmake(0.0, 0.0);
       }
-    }
+#pragma unroll
+    for (int a = 0; a < kEP; ++a)
+#pragma unroll
+      for (int c = 0; c < kEP; ++c) {
+        cfms(v[a][c], li[a], wj[c]);
+        if (m[a][c]) A[(ty + kTX * a) * kPad + tx + kTX * c] = v[a][c];
+      }
     __syncthreads();
   }
 }
@@ -260,17 +270,27 @@ __device__ __forceinline__ void tile_panel(cplx* X, int nr, int nb, const cplx* 
       }
       __syncthreads();
     }
-    const int q0 = (c + 1 - tx + kTX - 1 > 0) ? (c + 1 - tx + kTX - 1) / kTX : 0;
-    for (int q = q0; q < kEP; ++q) {
-      const int j = tx + kTX * q;
-      if (j >= nb) break;
-      const cplx l = Lc[j * (kLC + 1) + c % kLC];
+    cplx xr[kEP], l[kEP], v[kEP][kEP];
+    bool m[kEP][kEP];
 #pragma unroll
-      for (int a = 0; a < kEP; ++a) {
-        const int r = ty + kTX * a;
-        if (r < nr) cfms(X[r * kPad + j], X[r * kPad + c], l);
+    for (int a = 0; a < kEP; ++a) xr[a] = X[(ty + kTX * a) * kPad + c];
+#pragma unroll
+    for (int q = 0; q < kEP; ++q) l[q] = Lc[(tx + kTX * q) * (kLC + 1) + c % kLC];  // rows j <= c hold stale data: masked
+#pragma unroll
+    for (int a = 0; a < kEP; ++a)
+#pragma unroll
+      for (int q = 0; q < kEP; ++q) {
+        const int r = ty + kTX * a, j = tx + kTX * q;
+        m[a][q] = (j > c) & (j < nb) & (r < nr);
+        v[a][q] = m[a][q] ? X[r * kPad + j] : cmake(0.0, 0.0);
       }
-    }
+#pragma unroll
+    for (int a = 0; a < kEP; ++a)
+#pragma unroll
+      for (int q = 0; q < kEP; ++q) {
+        cfms(v[a][q], xr[a], l[q]);
+        if (m[a][q]) X[(ty + kTX * a) * kPad + tx + kTX * q] = v[a][q];
+      }
     __syncthreads();
   }
 }
