@@ -531,6 +531,16 @@ def measure_B(ctx, args):
         "minsr_phases_ms": {**phase, **{"in_step." + k: v for k, v in inner.items()}},
         "proposals_per_s": NSB * 2 * N / (sweep_ms * 1e-3),
     }
+    ss_ms = inner.get("pinv.shifted_solves")
+    if ss_ms and world == 1:
+        fl = 3 * (4.0 / 3.0) * float(NSB) ** 3  # three complex-symmetric LDL^T factorisations, real flops
+        out["pinv_roofline"] = {
+            "kernel": "zldlt_step_kernel x 3 shifts (complex-symmetric LDL^T, FP64 MMA) + wavefront solves + "
+                      "double-double refinement, in-step CUDA events",
+            "bound": "fp64", "achieved": fl / (ss_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+            "peak_note": "FP64 pipe: cuBLAS DGEMM measured in this run = pipe_peaks_measured_here.fp64_tflops (35 on this "
+                         "pool); at n = 4096 the factorisation is bound by the pivot chain of the look-ahead, not by the "
+                         "MMA pipe (DESIGN 4.0b)"}
     if gram_ms:
         ach = 2.0 * NSB * NSB * np_g / (gram_ms * 1e-3) / 1e12
         int8_ach = pairs * float(NSB) * (NSB + 1) * np_g / (gram_ms * 1e-3) / 1e12

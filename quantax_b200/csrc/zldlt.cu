@@ -211,9 +211,10 @@ __device__ __forceinline__ void tile_ldlt(cplx* A, int nb, cplx* wv, cplx* lv, c
                                           int64_t global_col0) {
   const int tid = threadIdx.x, tx = tid % kTX, ty = tid / kTX;
   for (int k = 0; k < nb; ++k) {
+    bool zero = false;
     if (tid < nb) {  // column k: w_i = A[i][k] (what the trailing update needs), l_i = w_i / d
       cplx d = A[k * kPad + k];
-      const bool zero = (d.x == 0.0 && d.y == 0.0);
+      zero = (d.x == 0.0 && d.y == 0.0);
       if (zero) d = cmake(1.0, 0.0);  // reported; the factorisation continues with finite numbers
       const cplx inv = crecip(d);
       const cplx w = A[tid * kPad + k];
@@ -221,13 +222,13 @@ __device__ __forceinline__ void tile_ldlt(cplx* A, int nb, cplx* wv, cplx* lv, c
       wv[tid] = w;
       lv[tid] = l;
       if (tid > k) A[tid * kPad + k] = l;
-      if (tid == k) {
-        A[k * kPad + k] = d;
-        dinv_s[k] = inv;
-        if (zero && info[0] == 0) info[0] = (int32_t)(global_col0 + k + 1);
-      }
+      if (tid == k) dinv_s[k] = inv;
     }
     __syncthreads();
+    if (tid == k && zero) {  // after the barrier: every thread of the column step has read the pivot
+      A[k * kPad + k] = cmake(1.0, 0.0);
+      if (info[0] == 0) info[0] = (int32_t)(global_col0 + k + 1);
+    }
     // trailing update of rows / columns k+1 .. nb-1 (lower triangle).  All loads first, then the arithmetic, then the
     // stores: element by element the compiler has to order every store before the next load (same pointer type)
     cplx wj[kEP], li[kEP], v[kEP][kEP];
