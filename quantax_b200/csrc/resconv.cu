@@ -20,7 +20,11 @@ namespace qtx {
 
 // tensor-core forward (resconv_tc.cu)
 bool resconv_tc_supported(int C, int lx, int ly, int kh, int kw);
-size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly);
+size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly, int grad);
+bool resconv_tc_backward_supported(int C, int lx, int ly, int kh, int kw);
+int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params, int64_t ns, const float* X,
+                        const float* Hs, const float* seed, void* out, int out_f64, int64_t ld, void* ws, size_t ws_bytes,
+                        const float** raw_grad, cudaStream_t st);
 int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
                        float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, const float** x_final,
                        int* x_final_planes, const long long* ns_dev, cudaStream_t st);
@@ -928,16 +932,20 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
     }
   }
   // ---- forward (conv_nets.py:78-92) ----
-  bool tc_done = false;
+  bool tc_done = false, tc_bwd = false;
   const T* tc_xfinal = nullptr;
   int tc_planes = 0;
+  unsigned char* tc_ws = nullptr;
+  size_t tc_ws_bytes = 0;
   if constexpr (std::is_same<T, float>::value) {
     if (resconv_tc_supported(C, sh.lx, sh.ly, sh.kh, sh.kw)) {
       // tensor-core tower (resconv_tc.cu); its workspace follows the regular one
       const size_t base_bytes = resconv_ws_base(QTX_F32, ns, sh, grad);
-      int rc = resconv_tc_forward(nb, C, sh.lx, sh.ly, params, spins, ns, X, Hs, grad ? 1 : 0,
-                                  (unsigned char*)ws + base_bytes, resconv_tc_workspace(ns, nb, C, sh.lx, sh.ly),
-                                  &tc_xfinal, &tc_planes, ns_dev, st);
+      tc_bwd = grad && resconv_tc_backward_supported(C, sh.lx, sh.ly, sh.kh, sh.kw);
+      tc_ws = (unsigned char*)ws + base_bytes;
+      tc_ws_bytes = resconv_tc_workspace(ns, nb, C, sh.lx, sh.ly, grad ? 1 : 0);
+      int rc = resconv_tc_forward(nb, C, sh.lx, sh.ly, params, spins, ns, X, Hs, grad ? (tc_bwd ? 2 : 1) : 0, tc_ws,
+                                  tc_ws_bytes, &tc_xfinal, &tc_planes, ns_dev, st);
       if (rc) return rc;
       tc_done = true;
     }
@@ -1012,6 +1020,32 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
   }
   T* dX = pass == 0 ? dA : dC;  // gradient w.r.t. X_{i+1}
   T* tmp = dB;
+  if constexpr (std::is_same<T, float>::value) {
+    if (tc_bwd) {
+      // tensor-core Jacobian (resconv_tc.cu): backward-data tower + per-sample weight gradients of the C x C
+      // convolutions; biases and the one-channel first convolution from the raw output gradients it leaves behind
+      const float* rg[2 * 64 + 1];
+      int rc = resconv_tc_backward(nb, C, sh.lx, sh.ly, params, ns, X, Hs, dX, out, out_dtype == QTX_F64 ? 1 : 0, ld,
+                                   tc_ws, tc_ws_bytes, rg, st);
+      if (rc) return rc;
+      for (int i = nb - 1; i >= 0; --i) {
+        const int k = 2 * (nb - 1 - i);
+        if (col_b2[i] >= 0 && (rc = bgrad(rg[k], col_b2[i]))) return rc;
+        if ((rc = bgrad(rg[k + 1], col_b1[i]))) return rc;
+      }
+      if ((rc = wgrad(rg[2 * nb - 1], x0, 1, (T)(1.0 / sqrt(2.0)), 0, col_w1[0]))) return rc;
+      const char* e = getenv("QTX_TC_WGRAD");
+      if (e && e[0] == '0') {  // dev knob: weight gradients on the CUDA cores from the tower's raw gradients
+        for (int i = nb - 1; i >= 0; --i) {
+          const int k = 2 * (nb - 1 - i);
+          if ((rc = wgrad(rg[k], Hs + (int64_t)i * act, C, (T)1, 1, col_w2[i]))) return rc;
+          if (i > 0 && (rc = wgrad(rg[k + 1], X + (int64_t)(i - 1) * act, C, (T)(1.0 / sqrt((double)(i + 1))), 1, col_w1[i])))
+            return rc;
+        }
+      }
+      continue;
+    }
+  }
   for (int i = nb - 1; i >= 0; --i) {
     const T* xin = (i == 0) ? x0 : X + (int64_t)(i - 1) * act;
     const T* h = Hs + (int64_t)i * act;
@@ -1056,7 +1090,7 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
 static size_t resconv_ws(int dtype, int64_t ns, const NetShape& sh, bool grad) {
   size_t b = resconv_ws_base(dtype, ns, sh, grad);
   if (dtype == QTX_F32 && resconv_tc_supported(sh.C, sh.lx, sh.ly, sh.kh, sh.kw))
-    b += resconv_tc_workspace(ns, sh.nblocks, sh.C, sh.lx, sh.ly);
+    b += resconv_tc_workspace(ns, sh.nblocks, sh.C, sh.lx, sh.ly, grad ? 1 : 0);
   return b;
 }
 

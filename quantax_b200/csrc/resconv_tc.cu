@@ -73,6 +73,21 @@ struct TcLayer {
   float out_alpha;         // operand out = split(kActScale * gelu(out_alpha * v))
   int write_act;
   int planar;              // raw layout: 0 = [ns, C, N], 1 = [ns, Np/8, N, 8] (forward-only residual stream)
+  // operand buffers (units of one raster set [KS][hi|lo][2][slots]): the forward-only tower works in place (0, 0),
+  // the towers of the Jacobian keep every layer's operand (CTA-pair kernel only)
+  int in_buf, out_buf;
+  // mode 1 = backward-data layer (variational.py:429-491 through conv_nets.py:78-92):
+  //   v = conv^T(g) * mul_alpha * gelu'(mul_alpha * mul) + res,  operand out = split(sig_out * v)
+  // with per-sample power-of-two scales so that the binary16 pair keeps float32 accuracy at any gradient magnitude
+  int mode;
+  const float* mul;        // raw pre-activation [ns, C, N]
+  float mul_alpha;
+  const float* sig_in;     // [ns] scale of the incoming gradient operand
+  const float* max_in;     // [ns] max |g| of the incoming gradient
+  const float* max_res;    // [ns] max |res| or null
+  const float* wnorm;      // [1] max_c sum_{o,tap} |w[o,c,tap]|: |conv^T(g)| <= wnorm * max|g|
+  float* sig_out;          // [ns]
+  float* max_out;          // [ns] float bits, atomicMax (zeroed by the host)
 };
 
 struct TcNetParams {
@@ -82,6 +97,9 @@ struct TcNetParams {
   int C, Np, KS;
   int layer0, layer1;  // layers [layer0, layer1) are run by this launch
   int act_stages, w_stages;
+  int64_t buf_u4;          // 16-byte units per operand buffer
+  int precise;             // accurate gelu / gelu' (towers of the Jacobian)
+  float out_scale;         // kOutScale times the expected-value correction of the truncating accumulator (tc_trunc_comp)
   unsigned long long* dbg;  // optional [grid][16] cycle counters (QTX_TC_DEBUG=1)
   const long long* ns_dev;  // optional device-side sample count (<= g.ns): batches whose size is decided on the device
   TcLayer layer[kTcMaxLayers];
@@ -139,6 +157,7 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
                : "r"(taddr));
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // K-major, no swizzle: core matrix = 8 rows x 16 B (rows 16 B apart); LBO = distance between the two
@@ -156,9 +175,13 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_addr, uint32_t 
 //   gelu(x) = x * sigmoid(2 sqrt(2/pi) (x + 0.044715 x^3)) = x / (1 + 2^(x (a + b x^2)))
 struct GeluConst {
   float a, b, c;  // exponent polynomial in v, output factor
+  float alpha;
+  int precise;    // accurate exp and division (the forward pass that feeds the Jacobian)
 };
-__host__ __device__ inline GeluConst gelu_const(float alpha) {
+__host__ __device__ inline GeluConst gelu_const(float alpha, int precise = 0) {
   GeluConst k;
+  k.alpha = alpha;
+  k.precise = precise;
   const float l2e = 1.4426950408889634f, s = -1.5957691216057308f;
   k.a = s * l2e * alpha;
   k.b = s * l2e * 0.044715f * alpha * alpha * alpha;
@@ -166,11 +189,40 @@ __host__ __device__ inline GeluConst gelu_const(float alpha) {
   return k;
 }
 __device__ __forceinline__ float gelu_scaled(float v, const GeluConst& k) {
+  if (k.precise) {
+    const float x = k.alpha * v;
+    const float u = 1.5957691216057308f * (x + 0.044715f * x * x * x);
+    return kActScale * (x / (1.0f + expf(-u)));
+  }
   const float t = v * fmaf(v * v, k.b, k.a);
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return (k.c * v) * r;
+}
+
+// d/dx gelu(x) (tanh form): s + x s (1 - s) 2 sqrt(2/pi) (1 + 3 * 0.044715 x^2),  s = sigmoid(2 sqrt(2/pi) (x + 0.044715 x^3))
+__device__ __forceinline__ float gelu_grad_fast(float x, int precise = 0) {
+  const float l2e = 1.4426950408889634f, c = 1.5957691216057308f;
+  const float x2 = x * x;
+  if (precise) {
+    const float sg = 1.0f / (1.0f + expf(-c * x * fmaf(0.044715f, x2, 1.0f)));
+    return fmaf(x * sg * (1.0f - sg), c * fmaf(3.0f * 0.044715f, x2, 1.0f), sg);
+  }
+  const float t = -c * l2e * x * fmaf(0.044715f, x2, 1.0f);
+  float e, sg;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + e));
+  return fmaf(x * sg * (1.0f - sg), c * fmaf(3.0f * 0.044715f, x2, 1.0f), sg);
+}
+// power of two that maps |v| <= bound below 2^15 (binary16 overflows at 65504)
+__device__ __forceinline__ float grad_scale(float bound) {
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.0f;
+  int e;
+  (void)frexpf(bound, &e);  // bound = m 2^e, m in [0.5, 1)
+  int k = 15 - e;
+  k = k < -100 ? -100 : (k > 100 ? 100 : k);
+  return __int_as_float((k + 127) << 23);
 }
 
 // x = hi + lo in binary16, two values at a time
@@ -241,6 +293,8 @@ struct TcPrepParams {
   int64_t b_off[kTcMaxLayers];   // offset of the conv bias in `params`, -1 = no bias
   int64_t blob_off[kTcMaxLayers];
   float* bias_pad;               // [nconv][Np]
+  int transpose;                 // backward-data blobs: W'[c][o][tap] = w[o][c][8 - tap], no bias
+  float* wnorm;                  // transpose: [nconv] max_c sum_{o,tap} |w[o][c][tap]|
 };
 
 __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
@@ -250,12 +304,13 @@ __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
   const int Kp = p.KS * 16;
   if (blockIdx.x == 0)
     for (int o = threadIdx.x; o < p.Np; o += blockDim.x)
-      p.bias_pad[L * p.Np + o] = (o < p.C && p.b_off[L] >= 0) ? p.params[p.b_off[L] + o] : 0.f;
+      p.bias_pad[L * p.Np + o] = (o < p.C && p.b_off[L] >= 0 && !p.transpose) ? p.params[p.b_off[L] + o] : 0.f;
   const int n = 9 * Kp * p.Np;  // one entry per (tap, c, o)
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const int o = e % p.Np, c = (e / p.Np) % Kp, tap = e / (p.Np * Kp);
     float v = 0.f;
-    if (o < p.C && c < p.C) v = kWScale * w[((int64_t)o * p.C + c) * 9 + tap];
+    if (o < p.C && c < p.C)
+      v = kWScale * (p.transpose ? w[((int64_t)c * p.C + o) * 9 + (8 - tap)] : w[((int64_t)o * p.C + c) * 9 + tap]);
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn(v - __half2float(h));
     const int ks = c >> 4, p2 = (c >> 3) & 1, j = c & 7;
@@ -272,6 +327,28 @@ __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
   }
 }
 
+// operator-norm bound of the transposed convolutions: block per layer
+__global__ void __launch_bounds__(256) tc_wnorm_kernel(TcPrepParams p) {
+  __shared__ float red[8];
+  const int L = blockIdx.x;
+  const float* w = p.params + p.w_off[L];
+  float m = 0.f;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    float a = 0.f;
+    for (int o = 0; o < p.C; ++o)
+      for (int tap = 0; tap < 9; ++tap) a += fabsf(w[((int64_t)o * p.C + c) * 9 + tap]);
+    m = fmaxf(m, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    p.wnorm[L] = m * 1.001f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // first layer (conv1 of block 0, cin = 1; conv_nets.py:84-86): CUDA cores, writes the operand raster of
 // conv2_0 = split(4 * gelu(conv1_0(s / sqrt 2) + b)) and optionally the raw pre-activation.
@@ -280,7 +357,7 @@ __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
 __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __restrict__ spins, const float* __restrict__ w,
                                                              const float* __restrict__ b, TcGeom g, int C, int Np,
                                                              __half* __restrict__ act, float* __restrict__ raw_out,
-                                                             const long long* __restrict__ ns_dev) {
+                                                             const long long* __restrict__ ns_dev, int precise) {
   // thread per (sample, pixel): the nine neighbour spins are read once and reused for all channels; the weights
   // [C][9] and biases sit in shared memory (broadcast reads)
   extern __shared__ float wb_s[];  // [Np * 9] weights (zero padded), [Np] biases
@@ -289,7 +366,7 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
   for (int e = threadIdx.x; e < Np; e += blockDim.x) wb_s[Np * 9 + e] = (e < C) ? b[e] : 0.f;
   __syncthreads();
   const float* bs = wb_s + Np * 9;
-  const GeluConst gk = gelu_const(1.0f);
+  const GeluConst gk = gelu_const(1.0f, precise);
   const int64_t total = (ns_dev ? (int64_t)*ns_dev : g.ns) * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int pix = (int)(e % N);
@@ -333,7 +410,7 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(const int8_t* __res
 // The layer flags (res / raw null, write_act) are warp-uniform.
 template <bool PLANAR>
 __device__ __forceinline__ void epi_load(float (&a)[8], float resv, int nvalid, const float* __restrict__ bias,
-                                         const float* res, int N) {
+                                         const float* res, int N, float out_scale) {
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias));
   const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
   float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -350,7 +427,7 @@ __device__ __forceinline__ void epi_load(float (&a)[8], float resv, int nvalid, 
   }
   const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], kOutScale, resv + bb[j]) + r[j];
+  for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], out_scale, resv + bb[j]) + r[j];
 }
 
 template <bool PLANAR>
@@ -600,7 +677,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
           if (lane == 0) mbar_arrive(tmem_empty);
           t_drain += (unsigned long long)(clock64() - t_d0);
           // ---- bias / residual / raw output / gelu / split / operand store ----
-          const GeluConst gk = gelu_const(L.out_alpha);
+          const GeluConst gk = gelu_const(L.out_alpha, p.precise);
           const float* Lbias = L.bias;
           const float* Lres = L.res;
           float* Lraw = L.raw_out;
@@ -625,7 +702,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_tc_kernel(const __grid_
                 uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
                 if (PLANAR && Lres && plane + kColGroups < planes)  // next plane's residual -> L1 while this one computes
                   prefetch_l1(Lres + roff + (int64_t)kColGroups * N * 8);
-                epi_load<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr, N);
+                epi_load<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr, N, p.out_scale);
                 epi_store<PLANAR>(acc[t][k], p.C - c0, Lraw ? Lraw + roff : nullptr, N, Lwrite, gk, act_hi, 2 * g.slots,
                                   rps[t]);
               }
@@ -814,6 +891,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             ++cnt[j];
             const int layer = p.layer0 + li;
+            const int row_in = p.layer[layer].in_buf * p.KS * 4;
             const int64_t slot0 = item * g.spi * g.Ps;
             for (int ks = 0; ks < p.KS; ++ks) {
               mbar_wait(act_empty + as, pa ^ 1);
@@ -827,8 +905,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
                 for (int run = 0; run < 4; ++run) {
                   unsigned char* d = dst + (size_t)t * tile_bytes + (size_t)run * run_bytes;
-                  tc2_tma_2d(d, &tmapA, lbar, e0, ks * 4 + run);
-                  tc2_tma_2d(d + (run_bytes >> 1), &tmapA, lbar, e0 + g.TSh, ks * 4 + run);
+                  tc2_tma_2d(d, &tmapA, lbar, e0, row_in + ks * 4 + run);
+                  tc2_tma_2d(d + (run_bytes >> 1), &tmapA, lbar, e0 + g.TSh, row_in + ks * 4 + run);
                 }
               }
               if (++as == (uint32_t)p.act_stages) { as = 0; pa ^= 1; }
@@ -938,6 +1016,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       rpix[t] = rvalid[t] ? y * g.W + x : 0;
       rps[t] = pixel_slots(g, rvalid[t] ? y : 0, rvalid[t] ? x : 0);
     }
+    // first and last valid pixel of this warp's rows (prefetch lines of the backward-data layers)
+    int wpix_lo[2], wpix_hi[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      int lo = rvalid[t] ? rpix[t] : 0x7fffffff, hi = rvalid[t] ? rpix[t] : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(FULL, lo, o));
+        hi = max(hi, __shfl_xor_sync(FULL, hi, o));
+      }
+      wpix_lo[t] = lo == 0x7fffffff ? 0 : lo;
+      wpix_hi[t] = hi;
+    }
     const uint32_t tmem_empty_leader = tc2_mapa(smem_u32(tmem_empty), 0);
     uint32_t ready_addr[2][2];
 #pragma unroll
@@ -959,6 +1050,27 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               const int64_t s = item * g.spi + tsl[t];
               if (rvalid[t] && s < ns_rt && cgp < planes)
                 prefetch_l1(L.res + s * planes * N * 8 + ((int64_t)cgp * N + rpix[t]) * 8);
+            }
+          }
+          if (L.mode == 1) {
+            // backward-data layer: the raw pre-activations and the residual gradient come from HBM (written by earlier
+            // launches / layers); pull this warp's lines into L2 while the MMAs of the item run.  Lane -> channel.
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int64_t s = item * g.spi + tsl[t];
+              if (s >= ns_rt) continue;
+              for (int idx = lane; idx < PL * 8; idx += 32) {
+                const int c = (cgp + kColGroups * (idx >> 3)) * 8 + (idx & 7);
+                if (c < p.C) {
+                  const int64_t o0 = (s * p.C + c) * N;
+                  prefetch_l2(L.mul + o0 + wpix_lo[t]);
+                  prefetch_l2(L.mul + o0 + wpix_hi[t]);
+                  if (L.res) {
+                    prefetch_l2(L.res + o0 + wpix_lo[t]);
+                    prefetch_l2(L.res + o0 + wpix_hi[t]);
+                  }
+                }
+              }
             }
           }
           if (lane == 0) QTX_TIMED_WAIT(t_tfull, tmem_full, q & 1);
@@ -986,7 +1098,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           __syncwarp();
           if (lane == 0) tc2_arrive_remote_relaxed(tmem_empty_leader);
           t_drain += (unsigned long long)(clock64() - t_d0);
-          const GeluConst gk = gelu_const(L.out_alpha);
+          const GeluConst gk = gelu_const(L.out_alpha, p.precise);
           const float* Lbias = L.bias;
           const float* Lres = L.res;
           float* Lraw = L.raw_out;
@@ -1000,7 +1112,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               if (!rvalid[t] || s >= ns_rt) continue;
               const int pix = rpix[t];
               const float resv = Lspin ? (float)Lspin[s * N + pix] : 0.f;
-              uint4* act_sample = reinterpret_cast<uint4*>(p.act) + s * g.Ps;
+              uint4* act_sample = reinterpret_cast<uint4*>(p.act) + (int64_t)L.out_buf * p.buf_u4 + s * g.Ps;
               const int64_t raw_sample = PLANAR ? s * planes * N * 8 + (int64_t)pix * 8 : s * p.C * N + pix;
 #pragma unroll
               for (int k = 0; k < PL; ++k) {
@@ -1011,13 +1123,72 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
                 if (PLANAR && Lres && plane + kColGroups < planes)  // next plane's residual -> L1 while this one computes
                   prefetch_l1(Lres + roff + (int64_t)kColGroups * N * 8);
-                epi_load<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr, N);
+                epi_load<PLANAR>(acc[t][k], resv, p.C - c0, Lbias + c0, Lres ? Lres + roff : nullptr, N, p.out_scale);
                 epi_store<PLANAR>(acc[t][k], p.C - c0, Lraw ? Lraw + roff : nullptr, N, Lwrite, gk, act_hi, 2 * g.slots,
                                   rps[t]);
               }
             }
           };
-          if (L.planar) run(std::true_type{});
+          // backward-data layer: v = conv^T(g) * alpha gelu'(alpha * mul) + res; per-sample scales (see TcLayer)
+          auto run_bwd = [&]() {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int64_t s = item * g.spi + tsl[t];
+              if (s >= ns_rt) continue;  // warp-uniform
+              const float s_in = __ldcg(L.sig_in + s);
+              const float m_in = __ldcg(L.max_in + s);
+              const float m_res = L.max_res ? __ldcg(L.max_res + s) : 0.f;
+              const float s_out = grad_scale(fmaf(m_in * __ldg(L.wnorm), 1.13f * L.mul_alpha, m_res));
+              const float oscale = p.out_scale * kActScale / s_in;  // out_scale = comp / (kActScale kWScale)
+              const float ma = L.mul_alpha;
+              float vmax = 0.f;
+              if (rvalid[t]) {
+                const int pix = rpix[t];
+                uint4* act_sample = reinterpret_cast<uint4*>(p.act) + (int64_t)L.out_buf * p.buf_u4 + s * g.Ps;
+                const int64_t raw_sample = s * p.C * N + pix;
+#pragma unroll
+                for (int k = 0; k < PL; ++k) {
+                  const int plane = cgp + kColGroups * k;
+                  if (plane >= planes) continue;
+                  const int c0 = plane * 8, nvalid = p.C - c0;
+                  const int64_t roff = raw_sample + (int64_t)c0 * N;
+                  float v[8];
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    v[jj] = 0.f;
+                    if (jj < nvalid) {
+                      const float mv = L.mul[roff + (int64_t)jj * N];
+                      const float r = Lres ? Lres[roff + (int64_t)jj * N] : 0.f;
+                      v[jj] = fmaf(acc[t][k][jj] * oscale, ma * gelu_grad_fast(ma * mv, p.precise), r);
+                      if (Lraw) Lraw[roff + (int64_t)jj * N] = v[jj];
+                      vmax = fmaxf(vmax, fabsf(v[jj]));
+                    }
+                  }
+                  if (Lwrite) {
+                    uint4 vh, vl;
+                    split2(v[0] * s_out, v[1] * s_out, vh.x, vl.x);
+                    split2(v[2] * s_out, v[3] * s_out, vh.y, vl.y);
+                    split2(v[4] * s_out, v[5] * s_out, vh.z, vl.z);
+                    split2(v[6] * s_out, v[7] * s_out, vh.w, vl.w);
+                    uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
+                    uint4* act_lo = act_hi + 2 * g.slots;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                      if (q4 < rps[t].n) {
+                        act_hi[rps[t].o[q4]] = vh;
+                        act_lo[rps[t].o[q4]] = vl;
+                      }
+                  }
+                }
+                if (pix == 0 && cgp == 0) L.sig_out[s] = s_out;
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
+              if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned*>(L.max_out + s), __float_as_uint(vmax));
+            }
+          };
+          if (L.mode == 1) run_bwd();
+          else if (L.planar) run(std::true_type{});
           else run(std::false_type{});
           // the next layer's TMA loads (either CTA) must see these stores: proxy fence by every writer, a named
           // barrier over the epilogue warps (orders all their stores before the signalling thread), then ONE thread
@@ -1038,6 +1209,256 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   __syncthreads();
   tc2_cluster_sync();  // the peer must not exit (or free TMEM) while the leader still reads its smem / TMEM
   if (warp == 1) tc2_tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobian on the tensor cores (variational.py:429-491): the backward-data layers are the SAME persistent CTA-pair
+// kernel (mode 1 layers, transposed / flipped weight blobs); below are the seed of that tower and the per-sample
+// weight gradients.
+// ---------------------------------------------------------------------------------------------
+// seed: raw d log psi / d x_last [ns, C, N] -> gradient operand buffer 0 (scaled per sample), max and scale arrays
+__global__ void __launch_bounds__(256) tc_grad_seed_kernel(const float* __restrict__ dz, TcGeom g, int C, int Np,
+                                                           __half* __restrict__ gbuf, float* __restrict__ gmax,
+                                                           float* __restrict__ gsig) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int64_t s = blockIdx.x;
+  const int N = g.H * g.W, planes = Np >> 3;
+  const float* d = dz + s * C * N;
+  float m = 0.f;
+  for (int e = threadIdx.x; e < C * N; e += blockDim.x) m = fmaxf(m, fabsf(d[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bc = m;
+    gmax[s] = m;
+    gsig[s] = grad_scale(m);
+  }
+  __syncthreads();
+  const float sig = grad_scale(bc);
+  for (int e = threadIdx.x; e < planes * N; e += blockDim.x) {
+    const int pix = e % N, plane = e / N;
+    const PixSlots ps = pixel_slots(g, pix / g.W, pix % g.W);
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = plane * 8 + j;
+      t[j] = (c < C) ? sig * d[c * N + pix] : 0.f;
+    }
+    store_plane(gbuf, g, plane, s * g.Ps, ps, t);
+  }
+}
+
+// Per-sample weight gradient of one convolution (SEG raster only):
+//   O[s, col0 + (o C + c) 9 + tap] = sum_pix dY[s, o, pix] * a[s, c, pix + tap]
+// as a GEMM with M = o (128 rows, C used), N = c, K = pixels.  Both operands are the rasters the towers left behind,
+// read MN-major: a 16-byte slot holds 8 channels of one pixel, 8 consecutive slots of a plane are a core matrix of
+// the no-swizzle MN-major layout (SBO = plane pitch, LBO = 10 slots = the next 8-pixel segment), and the operand of
+// tap (dy, dx) is the staged activation chunk addressed dy * row_pitch + dx slots further.  TMEM holds the nine tap
+// accumulators of NPh in-channels (9 NPh <= 512 columns), so the in-channel planes are covered in `npass` passes;
+// K runs over chunks of CR pixel rows staged by bulk copies (dY rows + activation rows with their halo).
+//   warp 0 producer, warp 1 MMA issuer, warps 2-13 epilogue (TMEM -> float64 / float32 Jacobian entries).
+struct WgLayer {
+  int g_buf, a_buf;   // gradient / activation operand buffers
+  int64_t col0;       // first Jacobian column of this weight
+};
+struct WgParams {
+  const __half* G;
+  const __half* A;
+  int64_t buf_halfs;
+  TcGeom g;
+  int C, Np, KS, nl;
+  int CR, nchunks, KK;   // pixel rows per chunk, chunks per sample, K steps (16 pixels) per chunk
+  int npass, PP;         // passes over the in-channel planes, planes per pass
+  int stages;
+  int pad_bytes;         // slack behind the last stage (the 128-row gradient operand reads 16 planes)
+  float comp;            // expected-value correction of the truncating accumulator (tc_trunc_comp)
+  const float* gsig;     // [buffers][ns]
+  int64_t ns;
+  void* out;
+  int64_t ld;
+  int out_f64;
+  int vec_ok;            // rows of 8 channels x 9 taps are 32-byte (f64) / 16-byte (f32) aligned
+  WgLayer layer[kTcMaxLayers];
+};
+
+// the epilogue transposes through shared memory: a TMEM lane (thread) holds one out-channel row, but consecutive
+// Jacobian entries run over (in-channel, tap) of one row -- a warp storing straight from registers touches 32
+// cache lines per instruction (measured: the store unit, not the tensor pipe, set the kernel time)
+constexpr int kWgRow = 37;   // 4 in-channels x 9 taps = 36 consecutive entries per step, padded (conflict-free column writes)
+
+template <typename OutT>
+__global__ void __launch_bounds__(kTcThreads, 1) resconv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const TcGeom& g = p.g;
+  const int planes = p.Np >> 3;
+  const uint32_t runA16 = (uint32_t)(p.CR * g.RP), runB16 = (uint32_t)((p.CR + 2) * g.RP);  // slots per staged plane run
+  const uint32_t offA_lo = (uint32_t)planes * runA16;
+  const uint32_t offB_hi = 2u * (uint32_t)planes * runA16, offB_lo = offB_hi + (uint32_t)p.PP * runB16;
+  const uint32_t stage16 = offB_hi + 2u * (uint32_t)p.PP * runB16;
+  const uint32_t stage_bytes = stage16 * 16u;
+  float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + p.pad_bytes);  // [kEpiWarps][32][kWgRow]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + kEpiWarps * 32 * kWgRow);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const int NPh = p.PP * 8;
+  const int64_t nunits = p.ns * p.nl;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int64_t s = u / p.nl;
+        const WgLayer& L = p.layer[(int)(u - s * p.nl)];
+        const __half* gsrc = p.G + (int64_t)L.g_buf * p.buf_halfs;
+        const __half* asrc = p.A + (int64_t)L.a_buf * p.buf_halfs;
+        for (int pass = 0; pass < p.npass; ++pass)
+          for (int ch = 0; ch < p.nchunks; ++ch) {
+            mbar_wait(empty + st, ph ^ 1);
+            const int np_pass = min(p.PP, planes - pass * p.PP);  // planes of this pass
+            const uint32_t bytes = (2u * (uint32_t)planes * runA16 + 2u * (uint32_t)np_pass * runB16) * 16u;
+            mbar_expect_tx(full + st, bytes);
+            unsigned char* dst = smem + (size_t)st * stage_bytes;
+            const int64_t slotA = s * g.Ps + (int64_t)(ch * p.CR + 1) * g.RP;  // first interior row of the chunk
+            const int64_t slotB = s * g.Ps + (int64_t)(ch * p.CR) * g.RP;      // one row above it
+            for (int hl = 0; hl < 2; ++hl)
+              for (int pl = 0; pl < planes; ++pl) {
+                const int64_t row = (pl >> 1) * 4 + hl * 2 + (pl & 1);
+                bulk_g2s(dst + ((size_t)(hl * planes + pl) * runA16) * 16, gsrc + (row * g.slots + slotA) * 8, runA16 * 16u,
+                         full + st);
+              }
+            for (int hl = 0; hl < 2; ++hl)
+              for (int pp = 0; pp < np_pass; ++pp) {
+                const int pl = pass * p.PP + pp;
+                const int64_t row = (pl >> 1) * 4 + hl * 2 + (pl & 1);
+                bulk_g2s(dst + ((size_t)offB_hi + (size_t)(hl * p.PP + pp) * runB16) * 16, asrc + (row * g.slots + slotB) * 8,
+                         runB16 * 16u, full + st);
+              }
+            if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // D = F32, A = B = F16, both MN-major, M = 128, N = NPh
+    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NPh >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t lbo = (uint32_t)g.SB << 16;  // next 8-pixel segment
+    const uint32_t a_hi_w = runA16 | (1u << 14), b_hi_w = runB16 | (1u << 14);
+    const uint32_t smem16 = smem_u32(smem) >> 4;
+    uint32_t st = 0, ph = 0, q = 0;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x)
+      for (int pass = 0; pass < p.npass; ++pass) {
+        mbar_wait(tmem_empty, (q & 1) ^ 1);
+        ++q;
+        tc_fence_after();
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+          mbar_wait(full + st, ph);
+          tc_fence_after();
+          const uint32_t base = smem16 + st * stage16;
+          for (int kk = 0; kk < p.KK; ++kk) {
+            const uint32_t a_h = (base + 1u + (uint32_t)kk * 2u * (uint32_t)g.SB) | lbo, a_l = a_h + offA_lo;
+            const uint32_t b0 = (base + offB_hi + (uint32_t)kk * 2u * (uint32_t)g.SB) | lbo;
+            const uint32_t acc0 = (ch == 0 && kk == 0) ? 0u : 1u;
+            if (elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t b_h = b0 + (uint32_t)((tap / 3) * g.RP + (tap % 3)), b_l = b_h + (offB_lo - offB_hi);
+                const uint32_t d = tmem_base + (uint32_t)(tap * NPh);
+                umma_f16_split(d, a_h, a_hi_w, b_h, b_hi_w, idesc, acc0);
+                umma_f16_split(d, a_l, a_hi_w, b_h, b_hi_w, idesc, 1u);
+                umma_f16_split(d, a_h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+              }
+              if (kk == p.KK - 1) {
+                umma_commit(empty + st);
+                if (ch == p.nchunks - 1) umma_commit(tmem_full);
+              }
+            }
+            __syncwarp();
+          }
+          if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
+        }
+      }
+  } else {
+    const int lq = warp & 3, cgp = (warp - 2) >> 2;
+    float* sb = stg + (warp - 2) * 32 * kWgRow;
+    const int rows_valid = min(32, p.C - lq * 32);  // out-channel rows of this warp that exist (warp-uniform)
+    uint32_t q = 0;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const int64_t s = u / p.nl;
+      const WgLayer& L = p.layer[(int)(u - s * p.nl)];
+      const float scale = p.comp / (__ldg(p.gsig + (int64_t)L.g_buf * p.ns + s) * kActScale);
+      OutT* obase = reinterpret_cast<OutT*>(p.out) + s * p.ld + L.col0 + (int64_t)(lq * 32) * p.C * 9;
+      for (int pass = 0; pass < p.npass; ++pass) {
+        if (lane == 0) mbar_wait(tmem_full, q & 1);
+        __syncwarp();
+        ++q;
+        tc_fence_after();
+        int last = -1;  // the last in-channel group this warp drains in this pass
+        if (rows_valid > 0)
+          for (int cg = cgp; cg < p.PP; cg += kColGroups)
+            if ((pass * p.PP + cg) * 8 < p.C) last = cg;
+        for (int cg = cgp; cg <= last; cg += kColGroups) {
+          uint32_t r[9][8];
+          __syncwarp();
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(tap * NPh + cg * 8), r[tap]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (cg == last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+          }
+          const int c0 = (pass * p.PP + cg) * 8;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int nv = min(4, p.C - c0 - 4 * half);  // in-channels of this half that exist (warp-uniform)
+            if (nv <= 0) break;
+            __syncwarp();  // the previous half has been read
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) sb[lane * kWgRow + jj * 9 + tap] = __uint_as_float(r[tap][4 * half + jj]) * scale;
+            __syncwarp();
+            const int len = nv * 9, total = rows_valid * len;
+            OutT* dst0 = obase + (int64_t)(c0 + 4 * half) * 9;
+            int row = 0, e = lane;
+            while (e >= len) { e -= len; ++row; }
+            for (int idx = lane; idx < total; idx += 32) {
+              dst0[(int64_t)row * p.C * 9 + e] = (OutT)sb[row * kWgRow + e];
+              e += 32;
+              while (e >= len) { e -= len; ++row; }
+            }
+          }
+        }
+        if (last < 0) {  // nothing to drain (idle rows / padded channels): the warp still takes part in the hand-over
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1092,6 +1513,21 @@ static bool tc_geometry(int H, int W, int64_t ns, TcGeom& g, bool pair = false) 
   return true;
 }
 
+// The float32 accumulator of tcgen05.mma rounds TOWARD ZERO at every accumulate, i.e. a sum of n
+// instructions loses part of an ulp of the running sum n times, always in the direction of zero: a systematic shrink
+// per accumulate relative to the result.  A NumPy model of a truncating accumulator (tools/trunc_bias_sim.py) gives
+// 2.15 .. 2.33e-8 per accumulate for random-walk, coherent, biased and heavy-tailed sums alike (n = 18 .. 72); on the
+// B200 the constant that minimises the error against a float64 evaluation is 1.75 .. 1.9e-8 for three network shapes
+// (C = 32 / 88 / 128; profiles/r2_tc_trunc_comp_scan.md).  Left alone it is THE error of the towers -- 1e-6 per
+// convolution at C = 88, in phase over all layers and samples: log psi 2.7e-6, Jacobian rows 1.2e-5 at config E;
+// with the epilogues multiplying by the expected value 1 + 1.8e-8 n: 1e-7 and 1.1e-6.
+// QTX_TC_TRUNC_COMP sets the constant in units of 1e-8 (0 = off).
+static float tc_trunc_comp(int naccum) {
+  double per = 1.8e-8;
+  if (const char* e = getenv("QTX_TC_TRUNC_COMP")) per = atof(e) * 1e-8;
+  return (float)(1.0 + per * naccum);
+}
+
 static bool tc_disabled() {
   const char* e = getenv("QTX_RESCONV_TC");
   return e && e[0] == '0';
@@ -1122,7 +1558,49 @@ static void tc_sizes(int nblocks, int C, int lx, int ly, int64_t ns, TcGeom& g, 
   resid_bytes = align256((size_t)ns * Np * lx * ly * 4);  // planar residual stream of the forward-only mode
 }
 
-size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly) {
+static bool tc_bwd_disabled() {
+  const char* e = getenv("QTX_RESCONV_TC_BWD");
+  return e && e[0] == '0';
+}
+
+// the Jacobian runs on the tensor cores for the SEG raster of the CTA-pair kernel (resconv_tc_backward)
+bool resconv_tc_backward_supported(int C, int lx, int ly, int kh, int kw) {
+  if (!resconv_tc_supported(C, lx, ly, kh, kw) || !tc_use_pair() || tc_bwd_disabled()) return false;
+  TcGeom g;
+  if (!tc_geometry(lx, ly, 1, g, true) || g.mode != 1) return false;
+  return ((C + 15) & ~15) <= 128;
+}
+
+// workspace of the tensor-core Jacobian: every layer's operand rasters of both towers, both weight blob sets, the
+// raw gradients [ns, C, N] of every convolution output, per-sample scales
+struct TcBwdLayout {
+  size_t buf_bytes;  // one operand buffer
+  size_t op_off, wf_off, wb_off, g_off, rg_off, gmax_off, gsig_off, wnorm_off, total;
+  int nl;
+};
+static TcBwdLayout tc_bwd_layout(int nblocks, int C, int lx, int ly, int64_t ns) {
+  TcGeom g;
+  int Np, KS;
+  size_t bh, ab, wb, rb;
+  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, bh, ab, wb, rb);
+  TcBwdLayout L{};
+  L.nl = 2 * nblocks - 1;
+  L.buf_bytes = (size_t)KS * 4 * g.slots * 16;  // exact: buffer b starts at tensor-map row b * KS * 4
+  size_t off = 0;
+  L.op_off = off; off += align256((size_t)L.nl * L.buf_bytes);
+  L.wf_off = off; off += wb;
+  L.wb_off = off; off += wb;
+  L.g_off = off; off += align256((size_t)L.nl * L.buf_bytes);
+  L.rg_off = off; off += (size_t)L.nl * align256((size_t)ns * C * lx * ly * 4);
+  L.gmax_off = off; off += align256((size_t)(L.nl + 1) * ns * 4);
+  L.gsig_off = off; off += align256((size_t)(L.nl + 1) * ns * 4);
+  L.wnorm_off = off; off += align256((size_t)L.nl * 4);
+  L.total = off + 512;
+  return L;
+}
+
+size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly, int grad) {
+  if (grad && resconv_tc_backward_supported(C, lx, ly, 3, 3)) return tc_bwd_layout(nblocks, C, lx, ly, ns).total;
   TcGeom g;
   int Np, KS;
   size_t bh, ab, wb, rb;
@@ -1130,93 +1608,12 @@ size_t resconv_tc_workspace(int64_t ns, int nblocks, int C, int lx, int ly) {
   return ab + wb + rb + 512;
 }
 
-// Forward through the tower.
-//   save_all == 0: *x_final receives the residual stream x_nblocks in the PLANAR layout [ns, Np/8, N, 8]
-//                  (it lives in the tensor-core workspace), X / Hs are not touched
-//   save_all == 1: X[i] = X + i*act holds x_{i+1}, Hs[i] = Hs + i*act the conv1 pre-activation of block i,
-//                  both [ns, C, N] (what the backward kernels of resconv.cu read); *x_final = X[nblocks-1]
-int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
-                       float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, const float** x_final,
-                       int* x_final_planes, const long long* ns_dev, cudaStream_t st) {
-  TcGeom g;
-  int Np, KS;
-  size_t blob_halfs, act_bytes, wblob_bytes, resid_bytes;
-  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, blob_halfs, act_bytes, wblob_bytes, resid_bytes);
-  QTX_REQUIRE(ws_bytes >= act_bytes + wblob_bytes + resid_bytes + 256, QTX_ERR_INVALID, "resconv_tc: workspace too small");
-  QTX_REQUIRE(2 * nblocks - 1 <= kTcMaxLayers, QTX_ERR_UNSUPPORTED, "resconv_tc: too many blocks");
-  unsigned char* base = (unsigned char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-  __half* act = reinterpret_cast<__half*>(base);
-  __half* wblob = reinterpret_cast<__half*>(base + act_bytes);
-  float* resid = reinterpret_cast<float*>(base + act_bytes + wblob_bytes);
-  float* bias_pad = reinterpret_cast<float*>(wblob + (size_t)(2 * nblocks - 1) * blob_halfs);
-  const int N = lx * ly;
-  const int64_t actsz = ns * C * N;
-
-  // parameter offsets (ravel_pytree order, see resconv.cu)
-  int64_t off = 0;
-  int64_t w1[64], b1[64], w2[64], b2[64];
-  for (int i = 0; i < nblocks; ++i) {
-    w1[i] = off; off += (int64_t)C * (i == 0 ? 1 : C) * 9;
-    b1[i] = off; off += C;
-    w2[i] = off; off += (int64_t)C * C * 9;
-    if (i == nblocks - 1) b2[i] = -1;
-    else { b2[i] = off; off += C; }
-  }
-
-  // tensor-core layers: conv2_0, then (conv1_i, conv2_i) for i >= 1
-  TcPrepParams pp{};
-  pp.params = params; pp.wblob = wblob; pp.C = C; pp.Np = Np; pp.KS = KS; pp.pair = g.pair;
-  TcNetParams np{};
-  np.act = act; np.wblob = wblob; np.g = g; np.C = C; np.Np = Np; np.KS = KS;
-  int nl = 0;
-  for (int i = 0; i < nblocks; ++i) {
-    if (i > 0) {
-      TcLayer& L = np.layer[nl];
-      pp.w_off[nl] = w1[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
-      L.wblob_off = pp.blob_off[nl];
-      pp.b_off[nl] = b1[i];
-      L.bias = bias_pad + (size_t)nl * Np; L.res = nullptr; L.res_spin = nullptr;
-      L.raw_out = save_all ? Hs + (int64_t)i * actsz : nullptr;
-      L.out_alpha = 1.0f; L.write_act = 1; L.planar = 0;
-      ++nl;
-    }
-    TcLayer& L = np.layer[nl];
-    pp.w_off[nl] = w2[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
-    L.wblob_off = pp.blob_off[nl];
-    pp.b_off[nl] = b2[i];
-    L.bias = bias_pad + (size_t)nl * Np;
-    L.res_spin = (i == 0) ? spins : nullptr;
-    if (save_all) {
-      L.res = (i == 0) ? nullptr : X + (int64_t)(i - 1) * actsz;
-      L.raw_out = X + (int64_t)i * actsz;
-      L.planar = 0;
-    } else {
-      L.res = (i == 0) ? nullptr : resid;
-      L.raw_out = resid;
-      L.planar = 1;
-    }
-    L.out_alpha = (float)(1.0 / sqrt((double)(i + 2)));
-    L.write_act = (i < nblocks - 1) ? 1 : 0;
-    ++nl;
-  }
-  pp.nconv = nl;
-  pp.bias_pad = bias_pad;
-  if (x_final) *x_final = save_all ? X + (int64_t)(nblocks - 1) * actsz : resid;
-  if (x_final_planes) *x_final_planes = save_all ? 0 : (Np >> 3);
-  {
-    const int n = 9 * KS * 16 * Np;
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nl);
-    tc_weight_prep_kernel<<<grid, 256, 0, st>>>(pp);
-    QTX_LAUNCH_CHECK();
-  }
-  {
-    const int64_t total = ns * N;
-    unsigned gsz = (unsigned)((total + 255) / 256);
-    if (gsz > 16u * num_sms()) gsz = 16u * num_sms();
-    tc_first_layer_kernel<<<gsz, 256, (size_t)Np * 10 * sizeof(float), st>>>(spins, params + w1[0], params + b1[0], g, C,
-                                                                             Np, act, save_all ? Hs : nullptr, ns_dev);
-    QTX_LAUNCH_CHECK();
-  }
+// launch the persistent tower kernel over the layers of `np` (operand buffers: `nbuf` raster sets behind np.act)
+static int tc_launch_tower(TcNetParams& np, int nbuf, int nl, cudaStream_t st) {
+  const TcGeom& g = np.g;
+  const int Np = np.Np, KS = np.KS;
+  __half* act = np.act;
+  const __half* wblob = np.wblob;
   // shared memory: activation ring + weight ring + barriers
   const size_t act_stage = g.pair ? (size_t)2 * 4 * g.TSh * 16 : (size_t)4 * g.TS * 16;
   const size_t w_stage = g.pair ? (size_t)3 * 4 * (Np / 2) * 16 : (size_t)3 * 4 * Np * 16;
@@ -1235,8 +1632,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   const bool dbg = getenv("QTX_TC_DEBUG") != nullptr;
   if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 256 * 16 * sizeof(unsigned long long));
   np.dbg = dbg ? dbg_buf : nullptr;
-  np.ns_dev = ns_dev;
-  auto report = [&](int units) {
+    auto report = [&](int units) {
     static unsigned long long h[256 * 16];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1255,7 +1651,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
     CUtensorMap tmA, tmW;
     {
       // operand rasters as 8-byte elements: (2 * slot, plane = kstep * 4 + hi|lo * 2 + p2); box = half a plane run
-      cuuint64_t gdim[2] = {(cuuint64_t)g.slots * 2, (cuuint64_t)KS * 4};
+      cuuint64_t gdim[2] = {(cuuint64_t)g.slots * 2, (cuuint64_t)KS * 4 * (cuuint64_t)nbuf};
       cuuint64_t gstride[1] = {(cuuint64_t)g.slots * 16};
       cuuint32_t box[2] = {(cuuint32_t)g.TSh, 1};
       cuuint32_t estr[2] = {1, 1};
@@ -1271,7 +1667,7 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
       cuuint64_t gstride[1] = {rowel * 8};
       cuuint32_t box[2] = {(cuuint32_t)rowel, 6};
       cuuint32_t estr[2] = {1, 1};
-      CUresult cr = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, wblob, gdim, gstride, box, estr,
+      CUresult cr = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<__half*>(wblob), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       QTX_REQUIRE(cr == CUDA_SUCCESS, QTX_ERR_CUDA, "resconv_tc: cuTensorMapEncodeTiled (weights) failed (%d)", (int)cr);
@@ -1328,6 +1724,266 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
     QTX_LAUNCH_CHECK();
     if (dbg) report(grid);
   }
+  return QTX_OK;
+}
+
+// Forward through the tower.
+//   save_all == 0: *x_final receives the residual stream x_nblocks in the PLANAR layout [ns, Np/8, N, 8]
+//                  (it lives in the tensor-core workspace), X / Hs are not touched
+//   save_all == 1: X[i] = X + i*act holds x_{i+1}, Hs[i] = Hs + i*act the conv1 pre-activation of block i,
+//                  both [ns, C, N] (what the backward kernels of resconv.cu read); *x_final = X[nblocks-1]
+int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, const int8_t* spins, int64_t ns,
+                       float* X, float* Hs, int save_all, void* ws, size_t ws_bytes, const float** x_final,
+                       int* x_final_planes, const long long* ns_dev, cudaStream_t st) {
+  TcGeom g;
+  int Np, KS;
+  size_t blob_halfs, act_bytes, wblob_bytes, resid_bytes;
+  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, blob_halfs, act_bytes, wblob_bytes, resid_bytes);
+  QTX_REQUIRE(2 * nblocks - 1 <= kTcMaxLayers, QTX_ERR_UNSUPPORTED, "resconv_tc: too many blocks");
+  unsigned char* base = (unsigned char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  // save_all == 2: layout of the tensor-core Jacobian (every layer keeps its operand buffer)
+  const bool keep_ops = save_all == 2;
+  const TcBwdLayout bl = keep_ops ? tc_bwd_layout(nblocks, C, lx, ly, ns) : TcBwdLayout{};
+  if (keep_ops) {
+    QTX_REQUIRE(g.pair, QTX_ERR_UNSUPPORTED, "resconv_tc: the tensor-core Jacobian needs the CTA-pair kernel");
+    QTX_REQUIRE(ws_bytes >= bl.total - 256, QTX_ERR_INVALID, "resconv_tc: workspace too small");
+  } else {
+    QTX_REQUIRE(ws_bytes >= act_bytes + wblob_bytes + resid_bytes + 256, QTX_ERR_INVALID, "resconv_tc: workspace too small");
+  }
+  __half* act = reinterpret_cast<__half*>(base + (keep_ops ? bl.op_off : 0));
+  __half* wblob = reinterpret_cast<__half*>(base + (keep_ops ? bl.wf_off : act_bytes));
+  float* resid = keep_ops ? nullptr : reinterpret_cast<float*>(base + act_bytes + wblob_bytes);
+  float* bias_pad = reinterpret_cast<float*>(wblob + (size_t)(2 * nblocks - 1) * blob_halfs);
+  const int N = lx * ly;
+  const int64_t actsz = ns * C * N;
+
+  // parameter offsets (ravel_pytree order, see resconv.cu)
+  int64_t off = 0;
+  int64_t w1[64], b1[64], w2[64], b2[64];
+  for (int i = 0; i < nblocks; ++i) {
+    w1[i] = off; off += (int64_t)C * (i == 0 ? 1 : C) * 9;
+    b1[i] = off; off += C;
+    w2[i] = off; off += (int64_t)C * C * 9;
+    if (i == nblocks - 1) b2[i] = -1;
+    else { b2[i] = off; off += C; }
+  }
+
+  // tensor-core layers: conv2_0, then (conv1_i, conv2_i) for i >= 1
+  TcPrepParams pp{};
+  pp.params = params; pp.wblob = wblob; pp.C = C; pp.Np = Np; pp.KS = KS; pp.pair = g.pair;
+  TcNetParams np{};
+  np.act = act; np.wblob = wblob; np.g = g; np.C = C; np.Np = Np; np.KS = KS;
+  np.buf_u4 = (int64_t)KS * 4 * g.slots;
+  {
+    const char* e = getenv("QTX_TC_PRECISE_GELU");  // dev knob: accurate exp / division in gelu (no measurable effect)
+    np.precise = e ? atoi(e) : 0;
+  }
+  np.out_scale = kOutScale * tc_trunc_comp(9 * ((C + 15) / 16));  // hi * hi accumulator: 9 taps x channel groups
+  int nl = 0;
+  for (int i = 0; i < nblocks; ++i) {
+    if (i > 0) {
+      TcLayer& L = np.layer[nl];
+      pp.w_off[nl] = w1[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
+      L.wblob_off = pp.blob_off[nl];
+      pp.b_off[nl] = b1[i];
+      L.bias = bias_pad + (size_t)nl * Np; L.res = nullptr; L.res_spin = nullptr;
+      L.raw_out = save_all ? Hs + (int64_t)i * actsz : nullptr;
+      L.out_alpha = 1.0f; L.write_act = 1; L.planar = 0;
+      L.in_buf = keep_ops ? nl : 0; L.out_buf = keep_ops ? nl + 1 : 0;
+      ++nl;
+    }
+    TcLayer& L = np.layer[nl];
+    L.in_buf = keep_ops ? nl : 0; L.out_buf = keep_ops ? nl + 1 : 0;
+    pp.w_off[nl] = w2[i]; pp.blob_off[nl] = (int64_t)nl * blob_halfs;
+    L.wblob_off = pp.blob_off[nl];
+    pp.b_off[nl] = b2[i];
+    L.bias = bias_pad + (size_t)nl * Np;
+    L.res_spin = (i == 0) ? spins : nullptr;
+    if (save_all) {
+      L.res = (i == 0) ? nullptr : X + (int64_t)(i - 1) * actsz;
+      L.raw_out = X + (int64_t)i * actsz;
+      L.planar = 0;
+    } else {
+      L.res = (i == 0) ? nullptr : resid;
+      L.raw_out = resid;
+      L.planar = 1;
+    }
+    L.out_alpha = (float)(1.0 / sqrt((double)(i + 2)));
+    L.write_act = (i < nblocks - 1) ? 1 : 0;
+    ++nl;
+  }
+  pp.nconv = nl;
+  pp.bias_pad = bias_pad;
+  if (x_final) *x_final = save_all ? X + (int64_t)(nblocks - 1) * actsz : resid;
+  if (x_final_planes) *x_final_planes = save_all ? 0 : (Np >> 3);
+  {
+    const int n = 9 * KS * 16 * Np;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nl);
+    tc_weight_prep_kernel<<<grid, 256, 0, st>>>(pp);
+    QTX_LAUNCH_CHECK();
+  }
+  {
+    const int64_t total = ns * N;
+    unsigned gsz = (unsigned)((total + 255) / 256);
+    if (gsz > 16u * num_sms()) gsz = 16u * num_sms();
+    tc_first_layer_kernel<<<gsz, 256, (size_t)Np * 10 * sizeof(float), st>>>(spins, params + w1[0], params + b1[0], g, C,
+                                                                             Np, act, save_all ? Hs : nullptr, ns_dev, np.precise);
+    QTX_LAUNCH_CHECK();
+  }
+  np.ns_dev = ns_dev;
+  return tc_launch_tower(np, keep_ops ? nl : 1, nl, st);
+}
+
+// Jacobian rows of the tensor-core layers (variational.py:429-491).  Requires resconv_tc_forward(save_all = 2) on the
+// same workspace (operand buffers of every layer, raw X / Hs) and the seed d log psi / d x_last in `seed` [ns, C, N].
+//   raw_grad[k], k = 0 .. 2 nblocks - 1: raw gradient w.r.t. the output of  conv2_{nb-1}, conv1_{nb-1}, conv2_{nb-2}, ...
+//   (raw_grad[0] = seed); the caller turns them into bias gradients and the first layer's weight gradient.
+// The weight gradients of all convolutions with C input channels are written here.
+int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params, int64_t ns, const float* X,
+                        const float* Hs, const float* seed, void* out, int out_f64, int64_t ld, void* ws, size_t ws_bytes,
+                        const float** raw_grad, cudaStream_t st) {
+  TcGeom g;
+  int Np, KS;
+  size_t blob_halfs, act_bytes, wblob_bytes, resid_bytes;
+  tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, blob_halfs, act_bytes, wblob_bytes, resid_bytes);
+  QTX_REQUIRE(g.pair && g.mode == 1, QTX_ERR_UNSUPPORTED, "resconv_tc_backward: needs the SEG raster of the CTA-pair kernel");
+  const TcBwdLayout bl = tc_bwd_layout(nblocks, C, lx, ly, ns);
+  QTX_REQUIRE(ws_bytes >= bl.total - 256, QTX_ERR_INVALID, "resconv_tc_backward: workspace too small");
+  unsigned char* base = (unsigned char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+  const int nl = bl.nl, N = lx * ly, planes = Np >> 3;
+  const int64_t actsz = ns * C * N;
+  __half* OP = reinterpret_cast<__half*>(base + bl.op_off);
+  __half* G = reinterpret_cast<__half*>(base + bl.g_off);
+  __half* wblob = reinterpret_cast<__half*>(base + bl.wb_off);
+  float* bias_pad = reinterpret_cast<float*>(wblob + (size_t)nl * blob_halfs);
+  float* gmax = reinterpret_cast<float*>(base + bl.gmax_off);
+  float* gsig = reinterpret_cast<float*>(base + bl.gsig_off);
+  float* wnorm = reinterpret_cast<float*>(base + bl.wnorm_off);
+  const size_t rg_stride = align256((size_t)actsz * 4);
+  auto RG = [&](int k) -> float* { return k == 0 ? const_cast<float*>(seed) : reinterpret_cast<float*>(base + bl.rg_off + (size_t)(k - 1) * rg_stride); };
+  for (int k = 0; k <= nl; ++k) raw_grad[k] = RG(k);
+
+  int64_t off = 0;
+  int64_t w1[64], w2[64];
+  for (int i = 0; i < nblocks; ++i) {
+    w1[i] = off; off += (int64_t)C * (i == 0 ? 1 : C) * 9 + C;
+    w2[i] = off; off += (int64_t)C * C * 9 + (i == nblocks - 1 ? 0 : C);
+  }
+
+  // ---- backward-data tower: layer d reads gradient buffer d, writes d + 1 ----
+  TcPrepParams pp{};
+  pp.params = params; pp.wblob = wblob; pp.C = C; pp.Np = Np; pp.KS = KS; pp.pair = g.pair;
+  pp.transpose = 1; pp.wnorm = wnorm; pp.bias_pad = bias_pad;
+  TcNetParams np{};
+  np.act = G; np.wblob = wblob; np.g = g; np.C = C; np.Np = Np; np.KS = KS;
+  np.buf_u4 = (int64_t)KS * 4 * g.slots;
+  {
+    const char* e = getenv("QTX_TC_PRECISE_GELU");
+    np.precise = e ? atoi(e) : 0;
+  }
+  np.out_scale = kOutScale * tc_trunc_comp(9 * ((C + 15) / 16));
+  WgParams wp{};
+  int d = 0, nw = 0;
+  for (int i = nblocks - 1; i >= 0; --i) {
+    for (int which = 0; which < 2; ++which) {  // 0: through conv2_i, 1: through conv1_i
+      if (which == 1 && i == 0) break;
+      TcLayer& L = np.layer[d];
+      pp.w_off[d] = which == 0 ? w2[i] : w1[i];
+      pp.b_off[d] = -1;
+      pp.blob_off[d] = (int64_t)d * blob_halfs;
+      L.wblob_off = pp.blob_off[d];
+      L.bias = bias_pad + (size_t)d * Np;  // zeros
+      L.res_spin = nullptr; L.out_alpha = 1.0f; L.planar = 0;
+      L.mode = 1;
+      L.in_buf = d; L.out_buf = d + 1;
+      L.sig_in = gsig + (int64_t)d * ns; L.max_in = gmax + (int64_t)d * ns;
+      L.sig_out = gsig + (int64_t)(d + 1) * ns; L.max_out = gmax + (int64_t)(d + 1) * ns;
+      L.wnorm = wnorm + d;
+      L.raw_out = RG(d + 1);
+      if (which == 0) {
+        L.mul = Hs + (int64_t)i * actsz; L.mul_alpha = 1.0f; L.res = nullptr; L.max_res = nullptr;
+        L.write_act = i > 0 ? 1 : 0;
+      } else {
+        L.mul = X + (int64_t)(i - 1) * actsz; L.mul_alpha = (float)(1.0 / sqrt((double)(i + 1)));
+        L.res = RG(d - 1); L.max_res = gmax + (int64_t)(d - 1) * ns;
+        L.write_act = 1;
+      }
+      // weight gradient of the convolution whose OUTPUT gradient is buffer d: conv2_i reads operand 2 i, conv1_i 2 i - 1
+      WgLayer& W = wp.layer[nw++];
+      W.g_buf = d;
+      W.a_buf = which == 0 ? 2 * i : 2 * i - 1;
+      W.col0 = which == 0 ? w2[i] : w1[i];
+      ++d;
+    }
+  }
+  // conv1_0 (one input channel) is left to the caller; its output gradient is raw_grad[nl]
+  QTX_REQUIRE(d == nl, QTX_ERR_INVALID, "resconv_tc_backward: layer count");
+  pp.nconv = nl;
+  QTX_CUDA(cudaMemsetAsync(gmax, 0, (size_t)(nl + 1) * ns * 4, st));
+  {
+    const int n = 9 * KS * 16 * Np;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nl);
+    tc_weight_prep_kernel<<<grid, 256, 0, st>>>(pp);
+    QTX_LAUNCH_CHECK();
+    tc_wnorm_kernel<<<nl, 256, 0, st>>>(pp);
+    QTX_LAUNCH_CHECK();
+  }
+  tc_grad_seed_kernel<<<(unsigned)ns, 256, 0, st>>>(seed, g, C, Np, G, gmax, gsig);
+  QTX_LAUNCH_CHECK();
+  {
+    int rc = tc_launch_tower(np, nl, nl, st);
+    if (rc) return rc;
+  }
+
+  // ---- weight gradients ----
+  if (const char* e = getenv("QTX_TC_WGRAD")) {  // dev knob: 0 = the caller computes them from raw_grad (CUDA cores)
+    if (e[0] == '0') return QTX_OK;
+  }
+  wp.G = G; wp.A = OP; wp.buf_halfs = (int64_t)KS * 4 * g.slots * 8; wp.g = g; wp.C = C; wp.Np = Np; wp.KS = KS;
+  wp.nl = nw; wp.gsig = gsig; wp.ns = ns; wp.out = out; wp.ld = ld; wp.out_f64 = out_f64;
+  wp.PP = planes >= 6 ? 6 : ((planes + 1) & ~1);
+  wp.npass = (planes + wp.PP - 1) / wp.PP;
+  const size_t cap = 227 * 1024 - 1024 - (size_t)kEpiWarps * 32 * kWgRow * 4;  // minus the epilogue's transpose buffers
+  int CR = 0;
+  size_t stage = 0;
+  for (int cr = g.H; cr >= 1; --cr) {
+    if (g.H % cr || (cr * g.nseg) % 2) continue;
+    const size_t sb = ((size_t)2 * planes * cr * g.RP + (size_t)2 * wp.PP * (cr + 2) * g.RP) * 16;
+    const size_t rch = (size_t)(planes + 16) * cr * g.RP * 16;
+    const size_t pd = rch > sb ? rch - sb + 128 : 0;
+    if (3 * sb + pd + 256 <= cap || (CR == 0 && cr == 1)) { CR = cr; stage = sb; break; }
+  }
+  // M = 128 reads 16 planes from each gradient half: the rows beyond Np alias whatever follows in shared memory
+  // (results of those rows are never read); behind the last stage that needs slack
+  const size_t reach = (size_t)(planes + 16) * CR * g.RP * 16;
+  const size_t pad = reach > stage ? ((reach - stage + 127) & ~(size_t)127) : 0;
+  QTX_REQUIRE(CR > 0 && 2 * stage + pad + 256 <= cap, QTX_ERR_UNSUPPORTED, "resconv_tc_backward: no pixel-row chunk fits");
+  wp.CR = CR; wp.nchunks = g.H / CR; wp.KK = CR * g.nseg / 2;
+  wp.comp = tc_trunc_comp(3 * (g.H * g.nseg / 2));  // one accumulator: three products per 16-pixel step
+  int stages = (int)((cap - 256 - pad) / stage);
+  if (stages > 6) stages = 6;
+  wp.stages = stages;
+  wp.pad_bytes = (int)pad;
+  {
+    bool ok = true;
+    const int64_t al = out_f64 ? 2 : 4;
+    if (C % al || ld % al || ((uintptr_t)out & 15)) ok = false;
+    for (int i = 0; i < nw; ++i)
+      if (wp.layer[i].col0 % al) ok = false;
+    wp.vec_ok = ok ? 1 : 0;
+  }
+  const size_t smem = (size_t)stages * stage + pad + (size_t)kEpiWarps * 32 * kWgRow * 4 + (size_t)(2 * stages + 2) * 8 + 16 + 128;
+  int64_t nunits = ns * nw;
+  int grid = num_sms();
+  if ((int64_t)grid > nunits) grid = (int)nunits;
+  if (out_f64) {
+    QTX_CUDA(cudaFuncSetAttribute(resconv_wgrad_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    resconv_wgrad_tc_kernel<double><<<grid, kTcThreads, smem, st>>>(wp);
+  } else {
+    QTX_CUDA(cudaFuncSetAttribute(resconv_wgrad_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    resconv_wgrad_tc_kernel<float><<<grid, kTcThreads, smem, st>>>(wp);
+  }
+  QTX_LAUNCH_CHECK();
   return QTX_OK;
 }
 

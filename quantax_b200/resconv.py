@@ -12,7 +12,7 @@ from .utils import ScaleArray
 
 # default per-launch sample caps when the state has no max_parallel (bytes of activation workspace)
 _FWD_BUDGET = 4 << 30
-_BWD_BUDGET = 12 << 30
+_BWD_BUDGET = 24 << 30
 
 
 def _shape_args(m):
