@@ -35,6 +35,7 @@ SIGNATURES = {
     "qtx_rbm_colmean_workspace_size": (_sz, [_i32, _i32, _i32, _i64]),
     "qtx_rbm_jacobian_colmean": (_i32, [_i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "qtx_resconv_tc_available": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "qtx_resconv_tc_backward_available": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "qtx_resconv_nparams": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "qtx_resconv_workspace_size": (_sz, [_i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "qtx_resconv_forward": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz,

@@ -32,13 +32,18 @@ template <typename T>
 __global__ void __launch_bounds__(256) gram_split_kernel(const T* __restrict__ A, int64_t ns, int64_t np, int64_t ld,
                                                          int64_t k0, int64_t kc, int64_t kc_pad, int64_t ns_pad,
                                                          int nslices, int8_t* __restrict__ Q,
-                                                         double* __restrict__ rowscale, int first_chunk) {
+                                                         double* __restrict__ rowscale, int first_chunk, int have_scale) {
   __shared__ double red[8];
   __shared__ double s_inv;
   const int64_t r = blockIdx.x;
   const int tid = threadIdx.x;
   double inv = 0.0;
-  if (r < ns) {
+  if (have_scale) {
+    // several K chunks: the scales were computed once by this kernel's scale-only launch (kc_pad == 0); re-reading the
+    // full row for every chunk cost 10 x 17 GB at config E
+    const double sc = r < ns ? rowscale[r] : 0.0;
+    inv = (sc > 0.0 && isfinite(sc)) ? 1.0 / sc : 0.0;  // power of two: exact
+  } else if (r < ns) {
     // row scale from the FULL row (all K chunks share it)
     double mx = 0.0;
     const T* row = A + r * ld;
@@ -387,16 +392,26 @@ static int gram_tc_impl(int dtype, const void* A, int64_t ns, int64_t np, int64_
     grid = ntiles < num_sms() ? ntiles : num_sms();
   }
   int chunk = 0;
+  const int multi = np > kc ? 1 : 0;
   for (int64_t k0 = 0; k0 < np; k0 += kc, ++chunk) {
     const int64_t kcur = (np - k0) < kc ? (np - k0) : kc;
     const int64_t kcur_pad = (kcur + 63) / 64 * 64;
     QTX_REQUIRE(kcur_pad == kc_pad || chunk > 0, QTX_ERR_INVALID, "qtx_gram: internal chunk error");
+    if (chunk == 0 && multi) {  // scale-only launch: no columns to cut (kc_pad = 0), writes rowscale
+      if (dtype == QTX_F64)
+        gram_split_kernel<double><<<(unsigned)ns_pad, 256, 0, st>>>((const double*)A, ns, np, ld, 0, 0, 0, ns_pad, s, Q,
+                                                                    rowscale, 1, 0);
+      else
+        gram_split_kernel<float><<<(unsigned)ns_pad, 256, 0, st>>>((const float*)A, ns, np, ld, 0, 0, 0, ns_pad, s, Q,
+                                                                   rowscale, 1, 0);
+      QTX_LAUNCH_CHECK();
+    }
     if (dtype == QTX_F64)
       gram_split_kernel<double><<<(unsigned)ns_pad, 256, 0, st>>>((const double*)A, ns, np, ld, k0, kcur, kc_pad,
-                                                                  ns_pad, s, Q, rowscale, chunk == 0);
+                                                                  ns_pad, s, Q, rowscale, chunk == 0 && !multi, multi);
     else
       gram_split_kernel<float><<<(unsigned)ns_pad, 256, 0, st>>>((const float*)A, ns, np, ld, k0, kcur, kc_pad, ns_pad,
-                                                                 s, Q, rowscale, chunk == 0);
+                                                                 s, Q, rowscale, chunk == 0 && !multi, multi);
     QTX_LAUNCH_CHECK();
     p.nkb = (int)(kc_pad / kBK);
     p.accum = (accum != 0 || chunk > 0) ? 1 : 0;

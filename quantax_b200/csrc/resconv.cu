@@ -1107,6 +1107,10 @@ extern "C" int qtx_resconv_tc_available(int model_dtype, int channels, int lx, i
   return (model_dtype == QTX_F32 && resconv_tc_supported(channels, lx, ly, kh, kw)) ? 1 : 0;
 }
 
+extern "C" int qtx_resconv_tc_backward_available(int model_dtype, int channels, int lx, int ly, int kh, int kw) {
+  return (model_dtype == QTX_F32 && resconv_tc_backward_supported(channels, lx, ly, kh, kw)) ? 1 : 0;
+}
+
 extern "C" int64_t qtx_resconv_nparams(int nblocks, int channels, int lx, int ly, int kh, int kw) {
   NetShape sh{nblocks, channels, lx, ly, kh, kw, 0};
   return sh.nparams();

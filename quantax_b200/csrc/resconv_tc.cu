@@ -817,7 +817,9 @@ __device__ __forceinline__ void tc2_commit(uint64_t* bar) {  // arrives on `bar`
       : "memory");
 }
 
-template <int PL>
+// BWD: the tower of backward-data layers (mode 1) -- a separate instantiation so that its epilogue does not cost the
+// forward kernel registers
+template <int PL, bool BWD>
 __global__ void __launch_bounds__(kTcThreads, 1)
     resconv_tc2_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapW,
                        const __grid_constant__ TcNetParams p) {
@@ -1052,7 +1054,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 prefetch_l1(L.res + s * planes * N * 8 + ((int64_t)cgp * N + rpix[t]) * 8);
             }
           }
-          if (L.mode == 1) {
+          if constexpr (BWD) {
             // backward-data layer: the raw pre-activations and the residual gradient come from HBM (written by earlier
             // launches / layers); pull this warp's lines into L2 while the MMAs of the item run.  Lane -> channel.
 #pragma unroll
@@ -1187,9 +1189,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               if (lane == 0 && vmax > 0.f) atomicMax(reinterpret_cast<unsigned*>(L.max_out + s), __float_as_uint(vmax));
             }
           };
-          if (L.mode == 1) run_bwd();
-          else if (L.planar) run(std::true_type{});
-          else run(std::false_type{});
+          if constexpr (BWD) {
+            run_bwd();
+          } else {
+            if (L.planar) run(std::true_type{});
+            else run(std::false_type{});
+          }
           // the next layer's TMA loads (either CTA) must see these stores: proxy fence by every writer, a named
           // barrier over the epilogue warps (orders all their stores before the signalling thread), then ONE thread
           // pays the cluster-scope release (it waits for the stores to be performed) while the other warps move on
@@ -1285,13 +1290,37 @@ struct WgParams {
   WgLayer layer[kTcMaxLayers];
 };
 
-// the epilogue transposes through shared memory: a TMEM lane (thread) holds one out-channel row, but consecutive
-// Jacobian entries run over (in-channel, tap) of one row -- a warp storing straight from registers touches 32
-// cache lines per instruction (measured: the store unit, not the tensor pipe, set the kernel time)
-constexpr int kWgRow = 37;   // 4 in-channels x 9 taps = 36 consecutive entries per step, padded (conflict-free column writes)
+// Epilogue: a TMEM lane (thread) holds one out-channel row, and consecutive Jacobian entries run over (in-channel,
+// tap) of that row, so a warp storing straight from registers touches 32 cache lines per instruction; a transpose
+// through shared memory with per-element global stores made the epilogue the longest phase (3.2 G instructions per
+// 2048 samples), and one bulk copy per thread and row overran the copy engine with 288-byte requests
+// (profiles/r2_wgrad_tc_epilogue_history.md).  So every thread converts 4 in-channels x 9 taps = 36 consecutive
+// entries of ITS row into its line of the warp's [32 rows][36] box, and ONE tensor store per warp writes the box
+// (cp.async.bulk.tensor, map = (in-channel * 9 + tap, out-channel, sample) of this layer's weight block; rows and
+// columns beyond C are clipped by the map).  Two boxes per warp alternate.
+constexpr int kWgThreads = 192;  // producer, MMA issuer, 4 epilogue warps (one per TMEM lane quarter)
+constexpr int kWgEpiWarps = 4;
+template <typename OutT>
+struct WgLine {
+  static constexpr int kPitch = 36 * (int)sizeof(OutT);  // dense box rows (the tensor store's shared-memory layout)
+};
+struct WgMaps {
+  CUtensorMap m[kTcMaxLayers];  // per weight block: (in-channel * 9 + tap, out-channel, sample), box 36 x 32 x 1
+};
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
 
 template <typename OutT>
-__global__ void __launch_bounds__(kTcThreads, 1) resconv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+__global__ void __launch_bounds__(kWgThreads, 1) resconv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps,
+                                                                        const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   const TcGeom& g = p.g;
@@ -1301,8 +1330,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_wgrad_tc_kernel(const _
   const uint32_t offB_hi = 2u * (uint32_t)planes * runA16, offB_lo = offB_hi + (uint32_t)p.PP * runB16;
   const uint32_t stage16 = offB_hi + 2u * (uint32_t)p.PP * runB16;
   const uint32_t stage_bytes = stage16 * 16u;
-  float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + p.pad_bytes);  // [kEpiWarps][32][kWgRow]
-  uint64_t* full = reinterpret_cast<uint64_t*>(stg + kEpiWarps * 32 * kWgRow);
+  // [active quarter][2 boxes][32 lines], 128-byte aligned (tensor store source)
+  unsigned char* stg = (unsigned char*)(((uintptr_t)(smem + (size_t)p.stages * stage_bytes + p.pad_bytes) + 127) & ~(uintptr_t)127);
+  const int nact = (p.C + 31) >> 5;  // TMEM lane quarters that hold out-channel rows
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + (size_t)nact * 2 * 32 * WgLine<OutT>::kPitch);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
   uint64_t* tmem_empty = tmem_full + 1;
@@ -1311,7 +1342,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_wgrad_tc_kernel(const _
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, kEpiWarps);
+    mbar_init(tmem_empty, kWgEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
@@ -1396,25 +1427,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_wgrad_tc_kernel(const _
         }
       }
   } else {
-    const int lq = warp & 3, cgp = (warp - 2) >> 2;
-    float* sb = stg + (warp - 2) * 32 * kWgRow;
-    const int rows_valid = min(32, p.C - lq * 32);  // out-channel rows of this warp that exist (warp-uniform)
+    const int lq = warp & 3;
+    const int o = lq * 32 + lane;
+    const bool row_ok = o < p.C;
+    unsigned char* box0 = stg + (size_t)(lq < nact ? lq : 0) * 2 * 32 * WgLine<OutT>::kPitch;
+    unsigned char* box1 = box0 + (size_t)32 * WgLine<OutT>::kPitch;
     uint32_t q = 0;
     for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
       const int64_t s = u / p.nl;
-      const WgLayer& L = p.layer[(int)(u - s * p.nl)];
+      const int li = (int)(u - s * p.nl);
+      const WgLayer& L = p.layer[li];
       const float scale = p.comp / (__ldg(p.gsig + (int64_t)L.g_buf * p.ns + s) * kActScale);
-      OutT* obase = reinterpret_cast<OutT*>(p.out) + s * p.ld + L.col0 + (int64_t)(lq * 32) * p.C * 9;
+      OutT* orow = reinterpret_cast<OutT*>(p.out) + s * p.ld + L.col0 + (int64_t)o * p.C * 9;
       for (int pass = 0; pass < p.npass; ++pass) {
         if (lane == 0) mbar_wait(tmem_full, q & 1);
         __syncwarp();
         ++q;
         tc_fence_after();
-        int last = -1;  // the last in-channel group this warp drains in this pass
-        if (rows_valid > 0)
-          for (int cg = cgp; cg < p.PP; cg += kColGroups)
+        int last = -1;  // the last in-channel group of this pass that exists (warp-uniform)
+        if (lq < nact)
+          for (int cg = 0; cg < p.PP; ++cg)
             if ((pass * p.PP + cg) * 8 < p.C) last = cg;
-        for (int cg = cgp; cg <= last; cg += kColGroups) {
+        for (int cg = 0; cg <= last; ++cg) {
           uint32_t r[9][8];
           __syncwarp();
 #pragma unroll
@@ -1431,30 +1465,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) resconv_wgrad_tc_kernel(const _
           for (int half = 0; half < 2; ++half) {
             const int nv = min(4, p.C - c0 - 4 * half);  // in-channels of this half that exist (warp-uniform)
             if (nv <= 0) break;
-            __syncwarp();  // the previous half has been read
+            if (p.vec_ok) {
+              unsigned char* box = half ? box1 : box0;
+              if (lane == 0) bulk_wait_read<1>();  // the store that last read this box (two groups ago) has drained it
+              __syncwarp();
+              unsigned char* line = box + (size_t)lane * WgLine<OutT>::kPitch;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
+              for (int e4 = 0; e4 < 9; ++e4) {  // entries e = jj * 9 + tap, four at a time
+                float v[4];
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) sb[lane * kWgRow + jj * 9 + tap] = __uint_as_float(r[tap][4 * half + jj]) * scale;
-            __syncwarp();
-            const int len = nv * 9, total = rows_valid * len;
-            OutT* dst0 = obase + (int64_t)(c0 + 4 * half) * 9;
-            int row = 0, e = lane;
-            while (e >= len) { e -= len; ++row; }
-            for (int idx = lane; idx < total; idx += 32) {
-              dst0[(int64_t)row * p.C * 9 + e] = (OutT)sb[row * kWgRow + e];
-              e += 32;
-              while (e >= len) { e -= len; ++row; }
+                for (int i = 0; i < 4; ++i) {
+                  const int e = e4 * 4 + i;
+                  v[i] = __uint_as_float(r[e % 9][4 * half + e / 9]) * scale;
+                }
+                if constexpr (sizeof(OutT) == 8) {
+                  *reinterpret_cast<double2*>(line + e4 * 32) = make_double2((double)v[0], (double)v[1]);
+                  *reinterpret_cast<double2*>(line + e4 * 32 + 16) = make_double2((double)v[2], (double)v[3]);
+                } else {
+                  *reinterpret_cast<float4*>(line + e4 * 16) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&maps.m[li], box, (c0 + 4 * half) * 9, lq * 32, (int)s);
+                bulk_commit();
+              }
+            } else if (row_ok) {
+              OutT* dst = orow + (int64_t)(c0 + 4 * half) * 9;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (jj < nv) {
+#pragma unroll
+                  for (int tap = 0; tap < 9; ++tap) dst[jj * 9 + tap] = (OutT)(__uint_as_float(r[tap][4 * half + jj]) * scale);
+                }
             }
           }
         }
-        if (last < 0) {  // nothing to drain (idle rows / padded channels): the warp still takes part in the hand-over
+        if (last < 0) {  // nothing to drain (idle quarter / padded channels): the warp still takes part in the hand-over
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty);
         }
       }
     }
+    if (lane == 0) bulk_wait_read<0>();  // the copy engine no longer reads this CTA's shared memory
   }
   tc_fence_before();
   __syncthreads();
@@ -1673,13 +1728,14 @@ static int tc_launch_tower(TcNetParams& np, int nbuf, int nl, cudaStream_t st) {
       QTX_REQUIRE(cr == CUDA_SUCCESS, QTX_ERR_CUDA, "resconv_tc: cuTensorMapEncodeTiled (weights) failed (%d)", (int)cr);
     }
     void (*kern)(CUtensorMap, CUtensorMap, TcNetParams) = nullptr;
+    const bool bwd = np.layer[0].mode == 1;
     switch (PL) {
-      case 1: kern = resconv_tc2_kernel<1>; break;
-      case 2: kern = resconv_tc2_kernel<2>; break;
-      case 3: kern = resconv_tc2_kernel<3>; break;
-      case 4: kern = resconv_tc2_kernel<4>; break;
-      case 5: kern = resconv_tc2_kernel<5>; break;
-      default: kern = resconv_tc2_kernel<6>; break;
+      case 1: kern = bwd ? resconv_tc2_kernel<1, true> : resconv_tc2_kernel<1, false>; break;
+      case 2: kern = bwd ? resconv_tc2_kernel<2, true> : resconv_tc2_kernel<2, false>; break;
+      case 3: kern = bwd ? resconv_tc2_kernel<3, true> : resconv_tc2_kernel<3, false>; break;
+      case 4: kern = bwd ? resconv_tc2_kernel<4, true> : resconv_tc2_kernel<4, false>; break;
+      case 5: kern = bwd ? resconv_tc2_kernel<5, true> : resconv_tc2_kernel<5, false>; break;
+      default: kern = bwd ? resconv_tc2_kernel<6, true> : resconv_tc2_kernel<6, false>; break;
     }
     QTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int npairs = num_sms() / 2;
@@ -1943,7 +1999,8 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
   wp.nl = nw; wp.gsig = gsig; wp.ns = ns; wp.out = out; wp.ld = ld; wp.out_f64 = out_f64;
   wp.PP = planes >= 6 ? 6 : ((planes + 1) & ~1);
   wp.npass = (planes + wp.PP - 1) / wp.PP;
-  const size_t cap = 227 * 1024 - 1024 - (size_t)kEpiWarps * 32 * kWgRow * 4;  // minus the epilogue's transpose buffers
+  const size_t line_bytes = (size_t)((C + 31) / 32) * 2 * 32 * (out_f64 ? WgLine<double>::kPitch : WgLine<float>::kPitch);
+  const size_t cap = 227 * 1024 - 1024 - line_bytes - 128;  // minus the epilogue's output boxes
   int CR = 0;
   size_t stage = 0;
   for (int cr = g.H; cr >= 1; --cr) {
@@ -1972,16 +2029,34 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
       if (wp.layer[i].col0 % al) ok = false;
     wp.vec_ok = ok ? 1 : 0;
   }
-  const size_t smem = (size_t)stages * stage + pad + (size_t)kEpiWarps * 32 * kWgRow * 4 + (size_t)(2 * stages + 2) * 8 + 16 + 128;
+  WgMaps wmaps;
+  memset(&wmaps, 0, sizeof(wmaps));
+  if (wp.vec_ok) {
+    EncodeTiledFn encode = tc_encode_fn();
+    QTX_REQUIRE(encode != nullptr, QTX_ERR_CUDA, "resconv_tc_backward: cuTensorMapEncodeTiled is unavailable");
+    const size_t esz = out_f64 ? 8 : 4;
+    for (int i = 0; i < nw; ++i) {
+      cuuint64_t gdim[3] = {(cuuint64_t)C * 9, (cuuint64_t)C, (cuuint64_t)ns};
+      cuuint64_t gstride[2] = {(cuuint64_t)C * 9 * esz, (cuuint64_t)ld * esz};
+      cuuint32_t box[3] = {36, 32, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult cr = encode(&wmaps.m[i], out_f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                           (unsigned char*)out + (size_t)wp.layer[i].col0 * esz, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      QTX_REQUIRE(cr == CUDA_SUCCESS, QTX_ERR_CUDA, "resconv_tc_backward: cuTensorMapEncodeTiled (Jacobian) failed (%d)", (int)cr);
+    }
+  }
+  const size_t smem = (size_t)stages * stage + pad + line_bytes + 128 + (size_t)(2 * stages + 2) * 8 + 16 + 128;
   int64_t nunits = ns * nw;
   int grid = num_sms();
   if ((int64_t)grid > nunits) grid = (int)nunits;
   if (out_f64) {
     QTX_CUDA(cudaFuncSetAttribute(resconv_wgrad_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    resconv_wgrad_tc_kernel<double><<<grid, kTcThreads, smem, st>>>(wp);
+    resconv_wgrad_tc_kernel<double><<<grid, kWgThreads, smem, st>>>(wmaps, wp);
   } else {
     QTX_CUDA(cudaFuncSetAttribute(resconv_wgrad_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    resconv_wgrad_tc_kernel<float><<<grid, kTcThreads, smem, st>>>(wp);
+    resconv_wgrad_tc_kernel<float><<<grid, kWgThreads, smem, st>>>(wmaps, wp);
   }
   QTX_LAUNCH_CHECK();
   return QTX_OK;

@@ -94,6 +94,22 @@ def test_complex_forward_and_jacobian(qtx, final, dtype, tol, phase):
     assert np.abs(O - Oo).max() <= 10 * tol * np.abs(Oo).max()
 
 
+def test_complex_jacobian_on_the_tensor_cores(qtx):
+    """Complex-output float32 ResConv on a 16x16 lattice: both backward passes (seeds d Re log psi, d Im log psi,
+    variational.py:461-487) run through the tensor-core towers (csrc/resconv_tc.cu); rows against the oracle."""
+    from quantax_b200 import _lib
+
+    lattice_pair(qtx, "square", 16)
+    model, net = make_model(qtx, 16, 2, 24, torch.float32, "sinhp1", seed=4, phase=False)
+    state = qtx.state.Variational(model)
+    assert _lib.lib().qtx_resconv_tc_backward_available(_lib.dtype_code(torch.float32), 24, 16, 16, 3, 3)
+    s = osmp.rand_states(9, 256, seed=5)
+    O = to_np(state.jacobian(torch.from_numpy(s)))
+    Oo = net.jacobian(s)
+    assert O.shape == Oo.shape and np.iscomplexobj(O)
+    check("complex tc jacobian rows vs oracle", (np.linalg.norm(O - Oo, axis=1) / np.linalg.norm(Oo, axis=1)).max(), 1e-5)
+
+
 @pytest.mark.parametrize("phase,tol", [(True, 1e-6), (False, 1e-10)])
 def test_complex_oloc_sweep_and_sr_step(qtx, phase, tol):
     """Heisenberg on the 6x6 triangular lattice: exchange sweep with injected randoms (bit-exact accept pattern),

@@ -105,6 +105,69 @@ def test_jacobian_matches_oracle(qtx, kind, L, shape, nb, C, k, final, dtype, to
     check(f"jacobian {shape} C={C} {dtype}", np.abs(O - Oo).max() / np.abs(Oo).max(), tol)
 
 
+# shapes served by the tensor-core Jacobian (csrc/resconv_tc.cu: backward-data tower + per-sample weight gradients on
+# the SEG raster): two tiles per sample (16x16), one (16x8), four samples per CTA pair (32x8 has two), channel counts
+# that are odd (scalar store path), not a multiple of 8 and above one 32-row quarter
+TC_BWD_CASES = [
+    ((16, 16), 2, 24, "exp"),
+    ((16, 16), 3, 40, "sinhp1"),
+    ((16, 16), 2, 5, "exp"),
+    ((16, 8), 2, 20, "sinhp1"),
+    ((32, 8), 2, 12, "exp"),
+    ((16, 16), 1, 16, "exp"),
+]
+
+
+@pytest.mark.parametrize("shape,nb,C,final", TC_BWD_CASES)
+def test_tensor_core_jacobian_matches_oracle(qtx, monkeypatch, shape, nb, C, final):
+    """variational.py:429-491 on the tensor cores: rows of the log-derivative matrix against the float32 oracle AND the
+    float64 evaluation of the same weights (relative 2-norm per sample, bar 1e-5), and the launch list shows that the
+    CUDA-core backward pass did not run."""
+    from quantax_b200 import _lib
+
+    qtx.sites.Sites._SITES = None
+    qtx.sites.Grid(list(shape))
+    model, net = make_resconv(qtx, shape, nb, C, 3, torch.float32, final, seed=5)
+    state = qtx.state.Variational(model)
+    N = shape[0] * shape[1]
+    s = osmp.rand_states(11, N, seed=6)
+    st = torch.from_numpy(s).cuda()
+    assert _lib.lib().qtx_resconv_tc_backward_available(_lib.dtype_code(torch.float32), C, shape[0], shape[1], 3, 3)
+    n0 = _lib.lib().qtx_launch_count()
+    O = to_np(state.jacobian(st))
+    n_tc = _lib.lib().qtx_launch_count() - n0
+    monkeypatch.setenv("QTX_RESCONV_TC_BWD", "0")
+    n0 = _lib.lib().qtx_launch_count()
+    Oc = to_np(state.jacobian(st))
+    n_fp = _lib.lib().qtx_launch_count() - n0
+    monkeypatch.delenv("QTX_RESCONV_TC_BWD")
+    if nb >= 2:  # two persistent towers + one weight-gradient launch instead of four launches per block
+        assert n_tc < n_fp
+    assert n_tc != n_fp
+    Oo = net.jacobian(s)
+    blocks = [{k: (None if v is None else v.astype(np.float64)) for k, v in blk.items()} for blk in net.blocks]
+    O64 = omodels.ResConv(blocks, net.shape, net.final).jacobian(s)
+    nrm = np.linalg.norm(O64, axis=1)
+    check(f"tc jacobian {shape} C={C} rows vs float64 evaluation", (np.linalg.norm(O - O64, axis=1) / nrm).max(), 1e-5)
+    check(f"tc jacobian {shape} C={C} rows vs float32 oracle", (np.linalg.norm(O - Oo, axis=1) / nrm).max(), 1e-5)
+    check(f"tc jacobian {shape} C={C} rows vs CUDA-core backward", (np.linalg.norm(O - Oc, axis=1) / nrm).max(), 1e-5)
+    check(f"tc jacobian {shape} C={C} worst entry vs float64 evaluation", np.abs(O - O64).max() / np.abs(O64).max(), 1e-5)
+
+
+def test_tensor_core_jacobian_float32_rows_and_chunks(qtx):
+    """float32 output rows (the C ABI's out_dtype) and several backward chunks give the same matrix."""
+    qtx.sites.Sites._SITES = None
+    qtx.sites.Grid([16, 16])
+    model, net = make_resconv(qtx, (16, 16), 2, 24, 3, torch.float32, "exp", seed=7)
+    s = torch.from_numpy(osmp.rand_states(13, 256, seed=8)).cuda()
+    O = qtx.state.Variational(model).jacobian(s)
+    O32 = torch.empty((13, model.nparams), dtype=torch.float32, device="cuda")
+    qtx.state.Variational(model).jacobian(s, out=O32)
+    assert torch.equal(O32, O.to(torch.float32))  # the same float32 values, rounded once
+    Oc = qtx.state.Variational(model, max_parallel=(64, 5)).jacobian(s)  # chunks of 5, 5, 3 samples
+    assert torch.equal(O, Oc)
+
+
 @pytest.mark.parametrize("kind", ["localflip", "exchange"])
 def test_generic_sweep_bit_exact_f64(qtx, kind):
     """ResConv has no local-update path: full forward per proposal; accept/reject pattern and chains

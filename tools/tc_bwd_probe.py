@@ -58,6 +58,10 @@ def main():
         compare("seg16 C=16 nb=1", (16, 16), 16, 1, 3)
         compare("seg 16x8 (one tile per sample)", (16, 8), 24, 2, 6)
         compare("seg 32x8", (32, 8), 20, 2, 5)
+    if what == "sanitize":  # small enough for compute-sanitizer
+        compare("seg16 C=24 nb=2", (16, 16), 24, 2, 3)
+        compare("seg 16x8 C=20 nb=2", (16, 8), 20, 2, 5, final="sinhp1")
+        print("SANITIZE_PROBE_DONE", flush=True)
     if what in ("E", "all"):
         compare("config E", (16, 16), 88, 8, 64, final="sinhp1")
     if what in ("time", "all"):
