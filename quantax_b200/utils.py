@@ -450,3 +450,61 @@ def read_eqx_leaves(file):
         return load(file)
     with open(file, "rb") as f:
         return load(f)
+
+
+# ---- chunk_map (quantax/utils/function.py:12-146) -----------------------------------------------------------------
+def _chunk_split(x: torch.Tensor, axis: int, chunk_size: int):
+    """The reference's chunk composition on ONE device (this process owns one GPU, so the `devices` axis of
+    utils/function.py:28-39 has length 1): a batch longer than ``chunk_size`` is zero-padded to a multiple of it,
+    viewed as [chunk_size, nchunks] and chunk i takes column i -- samples i, i + nchunks, i + 2 nchunks, ... --
+    otherwise the whole batch is the only chunk.  Returns [nchunks, ..., chunk, ...]."""
+    n = x.shape[axis]
+    if n > chunk_size:
+        pad = (-n) % chunk_size
+        if pad:
+            shape = list(x.shape)
+            shape[axis] = pad
+            x = torch.cat([x, torch.zeros(shape, dtype=x.dtype, device=x.device)], dim=axis)
+        before, after = x.shape[:axis], x.shape[axis + 1:]
+        x = x.reshape(*before, chunk_size, -1, *after)
+    else:
+        before, after = x.shape[:axis], x.shape[axis + 1:]
+        x = x.reshape(*before, n, 1, *after)
+    return torch.movedim(x, axis + 1, 0)
+
+
+def _chunk_combine(x: torch.Tensor, axis: int, batch: int) -> torch.Tensor:
+    """Inverse of _chunk_split on stacked chunk outputs [nchunks, ..., chunk, ...] (utils/function.py:69-76): the
+    chunk axis goes back behind the in-chunk axis, padding rows are cut."""
+    x = torch.movedim(x, axis + 1, 0)  # [chunk, nchunks, ...]
+    rest = x.shape[2:]
+    x = x.reshape(-1, *rest)[:batch]
+    return torch.movedim(x, 0, axis)
+
+
+def chunk_map(f, in_axes=0, out_axes=0, chunk_size: Optional[int] = None, use_scan: bool = False):
+    """``chunk_map`` of the reference (utils/function.py:88-146) for torch tensors: a per-sample (vmapped) function is
+    evaluated chunk by chunk with the reference's interleaved chunk composition and zero padding, and the outputs are
+    re-assembled in sample order.  ``use_scan`` is accepted for signature parity (there is no tracing here)."""
+    all_none = isinstance(in_axes, (tuple, list)) and all(a is None for a in in_axes)
+    if in_axes is None or all_none or chunk_size is None:
+        return f
+    if out_axes is None or (isinstance(out_axes, (tuple, list)) and any(a is None for a in out_axes)):
+        raise NotImplementedError("`chunk_map` with `out_axes=None` not implemented")
+
+    def chunked_f(*args):
+        axes = tuple(in_axes) if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        batch = next(a.shape[ax] for a, ax in zip(args, axes) if ax is not None)
+        split = [None if ax is None else _chunk_split(a, ax, chunk_size) for a, ax in zip(args, axes)]
+        nchunks = next(s.shape[0] for s in split if s is not None)
+        outs = []
+        for i in range(nchunks):
+            outs.append(f(*[a if s is None else s[i] for a, s in zip(args, split)]))
+        is_tuple = isinstance(outs[0], tuple)
+        if not is_tuple:
+            outs = [(o,) for o in outs]
+        oaxes = tuple(out_axes) if isinstance(out_axes, (tuple, list)) else (out_axes,) * len(outs[0])
+        res = tuple(_chunk_combine(torch.stack([o[k] for o in outs], dim=0), oaxes[k], batch) for k in range(len(outs[0])))
+        return res if is_tuple else res[0]
+
+    return chunked_f

@@ -860,6 +860,30 @@ def gen_resconv(ref, out):
         gd.set_default_dtype(np.float64)
 
 
+def gen_chunk_map(ref, out):
+    """utils/function.py:12-146: the reference's own chunk_map (interleaved chunk composition [devices, chunk, nchunks],
+    zero padding, re-assembly) on one device: which samples every chunk sees and what comes back."""
+    fn = importlib.import_module("quantax.utils.function")
+    W = minijax.wrap
+    cases = [(10, 4), (8, 4), (5, 8), (7, 7), (13, 5), (1, 3)]
+    out["chunk/cases"] = np.asarray(cases)
+    for ci, (B, cs) in enumerate(cases):
+        x = (np.arange(B * 3, dtype=np.float64).reshape(B, 3) + 1.0)
+        w = np.linspace(0.5, 1.5, 3)
+        seen = []
+
+        def f(xc, ww):  # per-sample function of the chunk; records the chunk it was given
+            seen.append(np.asarray(xc).copy())
+            return W(np.asarray(xc) @ np.asarray(ww)), W(np.asarray(xc).T * 2.0)  # batch axis 0 and batch axis 1
+
+        y, z = fn.chunk_map(f, in_axes=(0, None), out_axes=(0, 1), chunk_size=cs)(W(x.copy()), W(w.copy()))
+        out[f"chunk/{ci}/x"], out[f"chunk/{ci}/w"] = x, w
+        out[f"chunk/{ci}/nchunks"] = np.asarray(len(seen))
+        for k, c in enumerate(seen):
+            out[f"chunk/{ci}/seen{k}"] = c
+        out[f"chunk/{ci}/y"], out[f"chunk/{ci}/z"] = np.asarray(y), np.asarray(z)
+
+
 def main():
     import warnings
 
@@ -882,6 +906,7 @@ def main():
     gen_time_evol(ref, out)
     gen_full_sweep(ref, out)
     gen_chunk_and_mix_sweeps(ref, out)
+    gen_chunk_map(ref, out)
     path = os.path.join(HERE, "ref_hotpath.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -410,6 +410,22 @@ class Lambda(Module):
         return self.fn(x)
 
 
+def _eqx_combine(*trees):
+    """equinox.combine: leaf-wise first non-None of trees of equal structure (None = missing leaf)."""
+    def rec(xs):
+        xs = [x for x in xs if x is not None]
+        if not xs:
+            return None
+        x0 = xs[0]
+        if isinstance(x0, dict):
+            return {k: rec([x.get(k) for x in xs]) for k in x0}
+        if isinstance(x0, (list, tuple)) and not _is_registered(x0):
+            return type(x0)(rec([x[i] for x in xs]) for i in range(len(x0)))
+        return x0
+
+    return rec(list(trees))
+
+
 def install():
     """Put the stand-ins into sys.modules under the names the reference imports."""
     jnp = make_jnp()
@@ -460,6 +476,10 @@ def install():
     eqx.is_array_like = lambda x: isinstance(x, (int, float, complex, np.number))
     eqx.is_array = lambda x: isinstance(x, np.ndarray)
     eqx.filter_jit = jit
+    # eqx.filter / partition / combine on the pytrees above (documented behaviour: leaves failing the predicate -> None)
+    eqx.filter = lambda tree, pred, inverse=False: tree_map(lambda x: x if bool(pred(x)) != inverse else None, tree)
+    eqx.partition = lambda tree, pred: (eqx.filter(tree, pred), eqx.filter(tree, pred, inverse=True))
+    eqx.combine = _eqx_combine
     eqx.Module = Module
     eqx.field = lambda **k: None
     eqx.nn = mods["equinox.nn"]

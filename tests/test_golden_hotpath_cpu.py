@@ -562,3 +562,32 @@ def test_mix_sampler_sweep_matches_reference_code():
                          pos=g("pos"), slot=g("slot"), u=g("u"))
     assert np.array_equal(res["spins"], g("spins"))
     assert np.array_equal(res["psi"][0], g("sign")) and np.allclose(res["psi"][1], g("logabs"), rtol=1e-12, atol=1e-12)
+
+
+def test_chunk_map_has_the_reference_chunk_composition():
+    """utils/function.py:12-146, executed by tests/golden/make_golden_hotpath.py::gen_chunk_map: the chunks a
+    per-sample function is given (interleaved samples, zero padding) and the re-assembled outputs (batch axis 0 and
+    batch axis 1) of the product's chunk_map equal the reference's."""
+    import torch
+
+    from quantax_b200.utils import chunk_map
+
+    g = GOLD
+    for ci, (B, cs) in enumerate(g["chunk/cases"]):
+        x, w = torch.from_numpy(g[f"chunk/{ci}/x"]), torch.from_numpy(g[f"chunk/{ci}/w"])
+        seen = []
+
+        def f(xc, ww):
+            seen.append(xc.clone())
+            return xc @ ww, xc.T * 2.0
+
+        y, z = chunk_map(f, in_axes=(0, None), out_axes=(0, 1), chunk_size=int(cs))(x, w)
+        assert len(seen) == int(g[f"chunk/{ci}/nchunks"])
+        for k, c in enumerate(seen):
+            assert np.array_equal(c.numpy(), g[f"chunk/{ci}/seen{k}"]), (ci, k)
+        assert np.array_equal(y.numpy(), g[f"chunk/{ci}/y"]) and np.array_equal(z.numpy(), g[f"chunk/{ci}/z"])
+    # fast returns and the unsupported case (utils/function.py:116-122)
+    f0 = lambda a: a
+    assert chunk_map(f0, chunk_size=None) is f0 and chunk_map(f0, in_axes=None, chunk_size=4) is f0
+    with pytest.raises(NotImplementedError):
+        chunk_map(f0, out_axes=None, chunk_size=4)
