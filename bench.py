@@ -318,6 +318,24 @@ class Ctx:
         return float(t.item())
 
 
+_DIST_PHASES = ("comm.pack+all_to_all_Obar", "gram", "comm.all_reduce_T+all_gather_b", "pinv.lanczos",
+                "pinv.shifted_solves(this rank's shifts)", "comm.all_gather_y+dd_sum", "matvec_t", "comm.all_gather_x")
+
+
+def _dist_phases(world):
+    """Phase times (ms) of the LAST qtx_minsr_solve_dist call, from the library's own CUDA events (csrc/comm.cu)."""
+    import ctypes
+
+    from quantax_b200 import _lib
+
+    if world <= 1:
+        return {}
+    buf = (ctypes.c_double * 8)()
+    if _lib.lib().qtx_minsr_solve_dist_phases(ctypes.cast(buf, ctypes.c_void_p)) != 0:
+        return {}
+    return {"dist_last_step." + n: float(buf[i]) for i, n in enumerate(_DIST_PHASES)}
+
+
 def _phase_avg(events, steps):
     return {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in (events or {}).items()}
 
@@ -361,6 +379,8 @@ def measure_E(ctx, args):
     ctx.sync()
     optimizer.timers = {}
     optmod.PHASE_EVENTS = {}
+    if world > 1:
+        _lib.lib().qtx_minsr_solve_dist_timing(1)
     clocks = ClockSampler(ctx.local_rank)
     clocks.start()
     _lib.lib().qtx_launch_count_reset()
@@ -382,7 +402,10 @@ def measure_E(ctx, args):
     nconn = sum(n for _, n in timed) / K
     phase = _phase_avg(optimizer.timers, K)
     inner = _phase_avg(optmod.PHASE_EVENTS, K)
+    inner.update(_dist_phases(world))
     optimizer.timers, optmod.PHASE_EVENTS = None, None
+    if world > 1:
+        _lib.lib().qtx_minsr_solve_dist_timing(0)
 
     # e2e: host buffers, copies inside the timed region
     spins_host = torch.empty((NSG, N), dtype=torch.int8).pin_memory()
@@ -500,6 +523,8 @@ def measure_B(ctx, args):
     ctx.sync()
     optimizer.timers = {}
     optmod.PHASE_EVENTS = {}
+    if world > 1:
+        _lib.lib().qtx_minsr_solve_dist_timing(1)
     timed = []
     for _ in range(steps):
         vmc_step(timed)
@@ -509,7 +534,10 @@ def measure_B(ctx, args):
     minsr_ms = sum(e[2].elapsed_time(e[3]) for e in timed) / steps
     phase = _phase_avg(optimizer.timers, steps)
     inner = _phase_avg(optmod.PHASE_EVENTS, steps)
+    inner.update(_dist_phases(world))
     optimizer.timers, optmod.PHASE_EVENTS = None, None
+    if world > 1:
+        _lib.lib().qtx_minsr_solve_dist_timing(0)
     sweep_oloc_ms, sweep_ms, minsr_ms = (ctx.allmax(v) for v in (sweep_oloc_ms, sweep_ms, minsr_ms))
     inner = {k: ctx.allmax(v) for k, v in sorted(inner.items())}
     phase = {k: ctx.allmax(v) for k, v in sorted(phase.items())}

@@ -564,6 +564,13 @@ int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_local, int64_
                          const double* b_local, double rtol, double atol, int nslices, int lanczos_steps,
                          int refine_steps, double* x_out, int32_t* info_out, void* workspace,
                          size_t workspace_bytes, qtx_stream_t stream);
+/* Phase timing of qtx_minsr_solve_dist (measurement aid, off by default): after qtx_minsr_solve_dist_timing(1) every
+ * solve records CUDA events on its stream; qtx_minsr_solve_dist_phases waits for the last solve and returns the
+ * milliseconds of  [0] pack + all-to-all of Obar  [1] Gram of the column shard  [2] all-reduce of T + all-gather of b
+ * [3] Lanczos max|lambda|  [4] shifted LDL^T solves of this rank  [5] all-gather + rank-ordered sum of y
+ * [6] column shard of A^T y  [7] all-gather of x. */
+int qtx_minsr_solve_dist_timing(int enable);
+int qtx_minsr_solve_dist_phases(double* ms_out_8);
 
 #ifdef __cplusplus
 }

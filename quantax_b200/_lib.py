@@ -96,6 +96,8 @@ SIGNATURES = {
     "qtx_comm_broadcast": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "qtx_comm_all_to_all": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "qtx_minsr_solve_dist_workspace_size": (_sz, [_vp, _i32, _i64, _i64, _i32]),
+    "qtx_minsr_solve_dist_timing": (_i32, [_i32]),
+    "qtx_minsr_solve_dist_phases": (_i32, [_vp]),
     "qtx_minsr_solve_dist": (_i32, [_vp, _i32, _vp, _i64, _i64, _i64, _vp, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp,
                                     _sz, _vp]),
     "qtx_pinv_ldlt_workspace_size": (_sz, [_i64, _i32]),

@@ -91,6 +91,23 @@ __global__ void __launch_bounds__(256) pack_column_shards_kernel(const T* __rest
 
 __global__ void abs_info_kernel(int32_t* info) { info[0] = info[0] < 0 ? -info[0] : info[0]; }
 
+// optional phase timing of qtx_minsr_solve_dist (qtx_minsr_solve_dist_timing): CUDA events on the solve's stream at the
+// phase boundaries; nothing is recorded unless enabled
+constexpr int kDistPhases = 8;
+static bool g_dist_timing = false;
+static bool g_dist_timed = false;
+static cudaEvent_t g_dist_ev[kDistPhases + 1];
+static bool g_dist_ev_ready = false;
+static void dist_mark(int i, cudaStream_t st) {
+  if (!g_dist_timing) return;
+  if (!g_dist_ev_ready) {
+    for (int k = 0; k <= kDistPhases; ++k) cudaEventCreate(&g_dist_ev[k]);
+    g_dist_ev_ready = true;
+  }
+  cudaEventRecord(g_dist_ev[i], st);
+  if (i == kDistPhases) g_dist_timed = true;
+}
+
 }  // namespace qtx
 
 using namespace qtx;
@@ -283,6 +300,7 @@ extern "C" int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_lo
   char* base = (char*)al((size_t)workspace);
   const size_t esz = dtype == QTX_F32 ? 4 : 8;
   const int64_t npc = L.npc;
+  dist_mark(0, st);
   // 1. row-sharded -> column-sharded (solver.py:134-137; the parameter axis is zero-padded to a multiple of P)
   const unsigned grid = 8u * (unsigned)num_sms();
   if (dtype == QTX_F32)
@@ -292,13 +310,16 @@ extern "C" int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_lo
   QTX_LAUNCH_CHECK();
   rc = qtx_comm_all_to_all(comm, base + L.send, base + L.recv, (int64_t)((size_t)nl * npc * esz), stream);
   if (rc) return rc;
+  dist_mark(1, st);
   // 2. Gram of the column shard (all Ns rows, rank-major = global sample order), summed over the ranks (solver.py:139)
   double* T = (double*)(base + L.T);
   rc = qtx_gram(dtype, base + L.recv, ns, npc, npc, nslices, T, 0, base + L.gram, L.gram_bytes, stream);
   if (rc) return rc;
+  dist_mark(2, st);
   QTX_NCCL(api, api->AllReduce(T, T, (size_t)ns * ns, ncclFloat64, ncclSum, c->nccl, st));
   double* bfull = (double*)(base + L.bfull);
   QTX_NCCL(api, api->AllGather(b_local, bfull, (size_t)nl, ncclFloat64, c->nccl, st));
+  dist_mark(3, st);
   // 3. soft pseudo-inverse y = f(T) b: the ranks take different shifts (T, b are identical everywhere)
   const int mask = shift_mask_of(P, rank);
   int nsh = 0;
@@ -306,6 +327,7 @@ extern "C" int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_lo
   double* lam = (double*)(base + L.lam);
   rc = qtx_sym_absmax_eig_ws(T, ns, 0, lanczos_steps, lam, base + L.pinv, L.pinv_bytes, nsh > 0 ? nsh : 1, stream);
   if (rc) return rc;
+  dist_mark(4, st);
   double* ydd = (double*)(base + L.ydd);
   int32_t* info = (int32_t*)(base + L.info);
   rc = qtx_pinv_ldlt_partial(T, ns, bfull, rtol, atol, lam, mask, refine_steps, ydd, 0, info, base + L.pinv, L.pinv_bytes,
@@ -313,16 +335,19 @@ extern "C" int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_lo
   if (rc) return rc;
   abs_info_kernel<<<1, 1, 0, st>>>(info);
   QTX_LAUNCH_CHECK();
+  dist_mark(5, st);
   double* yall = (double*)(base + L.yall);
   QTX_NCCL(api, api->AllGather(ydd, yall, (size_t)2 * ns, ncclFloat64, c->nccl, st));
   QTX_NCCL(api, api->AllReduce(info, info_out, 1, ncclInt32, ncclMax, c->nccl, st));
   double* y = (double*)(base + L.y);
   rc = qtx_dd_sum_scale(yall, P, ns, 1.0 / 3.0, y, stream);
   if (rc) return rc;
+  dist_mark(6, st);
   // 4. column shard of x = A^T y, gathered (solver.py:146)
   double* xc = (double*)(base + L.xc);
   rc = qtx_matvec_t(dtype, base + L.recv, ns, npc, npc, y, xc, 0, stream);
   if (rc) return rc;
+  dist_mark(7, st);
   if ((int64_t)P * npc == np) {
     QTX_NCCL(api, api->AllGather(xc, x_out, (size_t)npc, ncclFloat64, c->nccl, st));
   } else {  // gather the padded vector into the send area (free again), copy the first np entries
@@ -330,6 +355,25 @@ extern "C" int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_lo
     QTX_NCCL(api, api->AllGather(xc, xpad, (size_t)npc, ncclFloat64, c->nccl, st));
     QTX_CUDA(cudaMemcpyAsync(x_out, xpad, (size_t)np * 8, cudaMemcpyDeviceToDevice, st));
   }
+  dist_mark(8, st);
   count_launch(5);
+  return QTX_OK;
+}
+
+extern "C" int qtx_minsr_solve_dist_timing(int enable) {
+  g_dist_timing = enable != 0;
+  g_dist_timed = false;
+  return QTX_OK;
+}
+
+extern "C" int qtx_minsr_solve_dist_phases(double* ms_out_8) {
+  QTX_REQUIRE(ms_out_8, QTX_ERR_INVALID, "qtx_minsr_solve_dist_phases: null output");
+  QTX_REQUIRE(g_dist_timing && g_dist_timed, QTX_ERR_INVALID, "qtx_minsr_solve_dist_phases: no timed solve (enable with qtx_minsr_solve_dist_timing)");
+  QTX_CUDA(cudaEventSynchronize(g_dist_ev[kDistPhases]));
+  for (int k = 0; k < kDistPhases; ++k) {
+    float ms = 0.f;
+    QTX_CUDA(cudaEventElapsedTime(&ms, g_dist_ev[k], g_dist_ev[k + 1]));
+    ms_out_8[k] = (double)ms;
+  }
   return QTX_OK;
 }
