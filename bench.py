@@ -483,7 +483,7 @@ def measure_B(ctx, args):
     """Config B in the same run (extra keys): sweep + Oloc on 4096 chains per GPU, the MinSR step of the 4096-row
     system sharded over the N GPUs (strong scaling of the communicating part), its phases and collectives."""
     import quantax_b200 as qtx
-    from quantax_b200 import optimizer as optmod
+    from quantax_b200 import _lib, optimizer as optmod
 
     torch, world, rank, dev = ctx.torch, ctx.world, ctx.rank, ctx.dev
     N, M = LB * LB, ALPHA * LB * LB
