@@ -318,6 +318,20 @@ class Ctx:
         return float(t.item())
 
 
+def _jacobian_roofline(inner, rows, nparams, peaks):
+    """HBM view of the log-derivative rows (state.jacobian: forward tower with saved operands, backward-data tower,
+    per-sample weight gradients on tcgen05): algorithmic bytes = the float64 rows written once."""
+    ms = inner.get("jacobian.rows")
+    if not ms:
+        return None
+    peak = peaks.get("hbm_gbs", 6458.0)
+    ach = rows * nparams * 8.0 / (ms * 1e-3) / 1e9
+    return {"kernel": "qtx_resconv_jacobian (resconv_tc2_kernel forward + backward-data, resconv_wgrad_tc_kernel), in-step CUDA events",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "note": "achieved = rows x parameters x 8 B (the float64 Jacobian, written once) / time of state.jacobian; the "
+                    "towers additionally move 2 x 4.5 GB of operand rasters and 5.8 GB of raw activations / gradients per 2048 rows"}
+
+
 _DIST_PHASES = ("comm.pack+all_to_all_Obar", "gram", "comm.all_reduce_T+all_gather_b", "pinv.lanczos",
                 "pinv.shifted_solves(this rank's shifts)", "comm.all_gather_y+dd_sum", "matvec_t", "comm.all_gather_x")
 
@@ -458,6 +472,7 @@ def measure_E(ctx, args):
                        "oloc_forwards_per_s": nconn / (oloc_ms * 1e-3)},
         "minsr_phases_ms": {**phase, **{"in_step." + k: v for k, v in inner.items()}},
         "pinv_method": optmod.PINV_METHOD,
+        "jacobian_roofline": _jacobian_roofline(inner, NSG, Np, peaks),
         "e2e": {"value": NSG * world * e2e_steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clk,

@@ -28,7 +28,9 @@ def chunk_columns(npar: int, s: int) -> int:
     """K chunk keeping the int32 level sums exact (gram_tc.cu gram_tc_sizes): K * s * 4096 < 2^31."""
     kmax = (1 << 31) // (4096 * s) - 1
     kmax = kmax // 64 * 64
-    return min(npar, kmax)
+    nchunks = (npar + kmax - 1) // kmax  # equal chunks, rounded up to the 64-column padding unit
+    kc = ((npar + nchunks - 1) // nchunks + 63) // 64 * 64
+    return min(kc, kmax)
 
 
 def split_digits(A: np.ndarray, s: int):

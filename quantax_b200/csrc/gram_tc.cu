@@ -21,6 +21,8 @@
 // 32-element K block of all needed digit slices of both row panels (2 * s * 4 KB).
 #include <stdlib.h>
 
+#include <vector>
+
 #include "gram_tc_common.cuh"
 
 namespace qtx {
@@ -100,6 +102,31 @@ __global__ void __launch_bounds__(256) gram_split_kernel(const T* __restrict__ A
         const int64_t nkb = kc_pad / kBK;
         *reinterpret_cast<uint32_t*>(Q + (((int64_t)a * nkb + kb / kBK) * ns_pad + r) * kBK + (kb % kBK)) = w[a];
       }
+  }
+}
+
+// upper triangle <- lower triangle (the CTA-pair kernel writes j <= i only): 32 x 32 blocks through shared memory,
+// both sides coalesced
+__global__ void __launch_bounds__(256) gram_mirror_kernel(double* __restrict__ T, int64_t ns) {
+  __shared__ double tile[32][33];
+  const int nbk = (int)((ns + 31) / 32);
+  const int64_t nblocks = (int64_t)nbk * (nbk + 1) / 2;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    int bi = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(bi + 1) * (bi + 2) / 2 <= b) ++bi;
+    while ((int64_t)bi * (bi + 1) / 2 > b) --bi;
+    const int bj = (int)(b - (int64_t)bi * (bi + 1) / 2);
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t i = (int64_t)bi * 32 + r, j = (int64_t)bj * 32 + tx;
+      tile[r][tx] = (i < ns && j < ns) ? T[i * ns + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t j = (int64_t)bj * 32 + r, i = (int64_t)bi * 32 + tx;  // T[j][i] = T[i][j] for j < i
+      if (i < ns && j < ns && j < i) T[j * ns + i] = tile[tx][r];
+    }
   }
 }
 
@@ -318,7 +345,11 @@ static void gram_tc_sizes(int dtype, int64_t ns, int64_t np, int nslices, int& s
   // exact int32 accumulation: up to s pairs per level, |q| <= 64  ->  K * s * 4096 < 2^31
   int64_t kmax = ((int64_t)1 << 31) / (4096 * (int64_t)s) - 1;
   kmax = kmax / 64 * 64;
-  kc = np < kmax ? np : kmax;
+  // equal K chunks: the kernels always run over kc_pad columns (zero padded), so a short last chunk cost as much as a
+  // full one (config E shard on 8 GPUs: 130 944 columns = 104 832 + 26 112, both 265 ms)
+  const int64_t nchunks = (np + kmax - 1) / kmax;
+  kc = ((np + nchunks - 1) / nchunks + 63) / 64 * 64;
+  if (kc > kmax) kc = kmax;
   kc_pad = (kc + 63) / 64 * 64;
 }
 
@@ -326,7 +357,8 @@ size_t gram_tc_workspace(int dtype, int64_t ns, int64_t np, int nslices) {
   int s;
   int64_t ns_pad, kc, kc_pad;
   gram_tc_sizes(dtype, ns, np, nslices, s, ns_pad, kc, kc_pad);
-  return (size_t)s * ns_pad * kc_pad + (size_t)ns_pad * sizeof(double) + 1024;
+  const size_t nb2 = (size_t)(ns_pad / (2 * kTile));
+  return (size_t)s * ns_pad * kc_pad + (size_t)ns_pad * sizeof(double) + nb2 * (nb2 + 1) * sizeof(int) + 256 + 1024;
 }
 
 // push_slots != nullptr: fused Gram + exchange (qtx_gram_push) -- the last K chunk runs the PUSH kernel, which also
@@ -344,7 +376,9 @@ static int gram_tc_impl(int dtype, const void* A, int64_t ns, int64_t np, int64_
   EncodeTiledFn encode = get_encode_fn();
   QTX_REQUIRE(encode != nullptr, QTX_ERR_CUDA, "qtx_gram: cuTensorMapEncodeTiled is unavailable");
   double* rowscale = reinterpret_cast<double*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-  int8_t* Q = reinterpret_cast<int8_t*>(((uintptr_t)(rowscale + ns_pad) + 255) & ~(uintptr_t)255);
+  const int nb2_map = (int)(ns_pad / (2 * kTile));
+  int* tile_map = reinterpret_cast<int*>(((uintptr_t)(rowscale + ns_pad) + 255) & ~(uintptr_t)255);
+  int8_t* Q = reinterpret_cast<int8_t*>(((uintptr_t)(tile_map + (size_t)nb2_map * (nb2_map + 1)) + 255) & ~(uintptr_t)255);
 
   CUtensorMap tmap;
   // dims: (byte in K block, row, slice * nkb + kblock)
@@ -367,16 +401,41 @@ static int gram_tc_impl(int dtype, const void* A, int64_t ns, int64_t np, int64_
     QTX_REQUIRE(cr == CUDA_SUCCESS, QTX_ERR_CUDA, "qtx_gram: cuTensorMapEncodeTiled (B) failed (%d)", (int)cr);
   }
   const uint32_t stage_bytes = pair ? (uint32_t)s * (kSliceBytes + kSliceBytes / 2) : 2u * s * kSliceBytes;
-  int stages = (int)((220 * 1024) / stage_bytes);
+  const size_t epi_bytes = pair ? (size_t)4 * 32 * 17 * sizeof(double) + 64 : 0;  // transpose blocks of the pair kernel's epilogue
+  int stages = (int)((220 * 1024 - epi_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (const char* e = getenv("QTX_GRAM_STAGES")) {
     int v = atoi(e);
     if (v >= 2 && v <= stages) stages = v;
   }
   QTX_REQUIRE(stages >= 2, QTX_ERR_UNSUPPORTED, "qtx_gram: pipeline does not fit in shared memory");
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 2) * 8 + 16;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 2) * 8 + 16 + epi_bytes;
 
   GramTcParams p;
+  p.tile_map = nullptr;
+  if (pair) {
+    // supertile order of the lower-triangular (256-row block, 128-column block) tiles: bands of 6 row blocks, walked in
+    // chunks of 12 column blocks (see tile2_from_index)
+    static thread_local std::vector<int> order;
+    order.clear();
+    const int GI = 6, GJ = 12;
+    for (int b = 0; b < nb2_map; b += GI) {
+      const int i1 = b + GI < nb2_map ? b + GI : nb2_map;
+      const int jmax = 2 * (i1 - 1) + 1;
+      for (int jc = 0; jc <= jmax; jc += GJ)
+        for (int i = b; i < i1; ++i)
+          for (int j = jc; j < jc + GJ && j <= 2 * i + 1; ++j) order.push_back((i << 16) | j);
+    }
+    QTX_REQUIRE((int)order.size() == nb2_map * (nb2_map + 1), QTX_ERR_INVALID, "qtx_gram: tile order");
+    // measured (tools/gram_order_probe.py): no gain at config B (7.6 vs 7.6 ms) or the config E slice (47.1 vs 47.7 ms) and a
+    // loss on the 16384-row shard of config E on 8 GPUs (362 vs 333 ms): with 5 or 7 digits the kernel is bound by the
+    // L2 -> shared-memory stream of its own CTA pair, which the order does not change.  Opt-in: QTX_GRAM_SUPERTILE=1
+    const char* e = getenv("QTX_GRAM_SUPERTILE");
+    if (e && e[0] == '1') {
+      QTX_CUDA(cudaMemcpyAsync(tile_map, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      p.tile_map = tile_map;
+    }
+  }
   p.nb = (int)(ns_pad / kTile);
   p.nslices = s;
   p.stages = stages;
@@ -435,6 +494,10 @@ static int gram_tc_impl(int dtype, const void* A, int64_t ns, int64_t np, int64_
       default: rc = launch_gram_tc<8>(tmap, p, grid, smem, st); break;
     }
     if (rc) return rc;
+  }
+  if (pair && !push_slots) {  // the fused path's reduce kernel writes both triangles itself
+    gram_mirror_kernel<<<8 * num_sms(), 256, 0, st>>>(Tout, ns);
+    QTX_LAUNCH_CHECK();
   }
   return QTX_OK;
 }

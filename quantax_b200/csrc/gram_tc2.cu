@@ -91,8 +91,16 @@ __device__ __forceinline__ void issue_kblock2(uint32_t tmem_base, uint32_t desc_
   }
 }
 
-// tile t of the pair -> (I2: 256-row block, J: 128-column block), J <= 2*I2 + 1
-__device__ __forceinline__ void tile2_from_index(int t, int& I2, int& J) {
+// tile t of the pair -> (I2: 256-row block, J: 128-column block), J <= 2*I2 + 1.  With a tile map (opt-in, see
+// gram_tc.cu) the order is the host's supertile order: the tiles that run at the same time (one per CTA pair, round
+// robin) form a 6 x 12 block of the lower triangle, i.e. share 6 row panels and 12 column panels instead of 1 and 74
+__device__ __forceinline__ void tile2_from_index(const int* __restrict__ map, int t, int& I2, int& J) {
+  if (map) {
+    const int m = __ldg(map + t);
+    I2 = m >> 16;
+    J = m & 0xffff;
+    return;
+  }
   int i = (int)((sqrtf(4.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
   while ((i + 1) * (i + 2) <= t) ++i;
   while (i * (i + 1) > t) --i;
@@ -120,6 +128,7 @@ __device__ __forceinline__ void gram_tc2_body(const CUtensorMap& tmapA, const CU
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  double* stg = reinterpret_cast<double*>(((uintptr_t)(tmem_holder + 1) + 15) & ~(uintptr_t)15);  // [4 epilogue warps][32][17]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -150,7 +159,7 @@ __device__ __forceinline__ void gram_tc2_body(const CUtensorMap& tmapA, const CU
       uint32_t stage = 0, phase = 0;
       for (int t = cluster_id; t < ntiles; t += nclusters) {
         int I2, J;
-        tile2_from_index(t, I2, J);
+        tile2_from_index(p.tile_map, t, I2, J);
         const int rowA = I2 * 256 + (int)rank * kTile;
         const int rowB = J * kTile + (int)rank * (kTile / 2);
 #pragma unroll
@@ -208,10 +217,11 @@ __device__ __forceinline__ void gram_tc2_body(const CUtensorMap& tmapA, const CU
   } else {
     // ===== epilogue warps 2..5 of both CTAs: own TMEM lanes 32*(warp%4) .. +31 =====
     const int lg = warp & 3;
+    double* sb = stg + lg * 32 * 17;
     uint32_t tphase = 0;
     for (int t = cluster_id; t < ntiles; t += nclusters) {
       int I2, J;
-      tile2_from_index(t, I2, J);
+      tile2_from_index(p.tile_map, t, I2, J);
       const int64_t row = (int64_t)I2 * 256 + (int64_t)rank * kTile + lg * 32 + lane;
       const double rs_i = (row < p.ns) ? p.rowscale[row] : 0.0;
       for (int pass = 0; pass < npasses; ++pass) {
@@ -235,19 +245,32 @@ __device__ __forceinline__ void gram_tc2_body(const CUtensorMap& tmapA, const CU
 #pragma unroll
               for (int e = 0; e < 16; ++e) sum[e] += w * (double)v[e];
             }
-            if (row < p.ns) {
+            // A TMEM lane is a row of T, so storing from registers puts the 32 lanes of an instruction 8 ns bytes apart:
+            // with T beyond the L2 (ns = 16384: 2.1 GB) the read-modify-write of the later passes / K chunks ran at
+            // DRAM-page-miss speed and was 90 % of the kernel (265 ms per launch whatever K).  The 32 x 16 block goes
+            // through shared memory instead and is written (and, when accumulating, read) 16 consecutive columns per
+            // half warp; only the lower triangle is touched here, gram_mirror_kernel fills the upper one at the end.
+            __syncwarp();
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int64_t col = (int64_t)J * kTile + c0 + e;
-                if (col <= row) {
-                  const double val = sum[e] * (rs_i * p.rowscale[col]);
-                  double* p1 = p.T + row * p.ns + col;
-                  *p1 = add ? *p1 + val : val;
-                  if (col != row) {
-                    double* p2 = p.T + col * p.ns + row;
-                    *p2 = add ? *p2 + val : val;
-                  }
-                }
+            for (int e = 0; e < 16; ++e) {
+              const int64_t col = (int64_t)J * kTile + c0 + e;
+              sb[lane * 17 + e] = (row < p.ns && col < p.ns) ? sum[e] * (rs_i * __ldg(p.rowscale + col)) : 0.0;
+            }
+            __syncwarp();
+            {
+              const int hw = lane >> 4, ce = lane & 15;
+              const int64_t row0 = (int64_t)I2 * 256 + (int64_t)rank * kTile + lg * 32;
+              const int64_t gcol = (int64_t)J * kTile + c0 + ce;
+              double old[16];
+#pragma unroll
+              for (int rr = 0; rr < 16; ++rr) {
+                const int64_t grow = row0 + 2 * rr + hw;
+                old[rr] = (add && grow < p.ns && gcol <= grow) ? p.T[grow * p.ns + gcol] : 0.0;
+              }
+#pragma unroll
+              for (int rr = 0; rr < 16; ++rr) {
+                const int64_t grow = row0 + 2 * rr + hw;
+                if (grow < p.ns && gcol <= grow) p.T[grow * p.ns + gcol] = old[rr] + sb[(2 * rr + hw) * 17 + ce];
               }
             }
           }

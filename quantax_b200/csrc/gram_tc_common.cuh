@@ -119,6 +119,7 @@ struct GramTcParams {
   const double* rowscale;
   double* T;
   int accum;
+  const int* tile_map;  // CTA-pair kernel: tile t -> (I2 << 16) | J in supertile order (gram_tc.cu), or null
 };
 
 }  // namespace qtx

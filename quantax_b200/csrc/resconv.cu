@@ -532,6 +532,68 @@ __global__ void __launch_bounds__(256) resconv_final_kernel(const T* __restrict_
   }
 }
 
+// The same final layer for the forward-only tensor-core tower (planar float32 stream, no seed output) in ONE pass over
+// the sample: every thread keeps a running max m of |z| and the sums of exp(z - m), exp(-z - m) relative to it
+// (rescaled when the max moves), the block merges the (m, A, B) triples.  The two-pass kernel above read the 98 KB of
+// a config E sample twice; this kernel runs once per forward of the sweep and of Oloc.
+__global__ void __launch_bounds__(256) resconv_final_planar_kernel(const float* __restrict__ x, int64_t ns, int C, int N,
+                                                                   float inv_norm, int final_act,
+                                                                   double* __restrict__ sig_out, double* __restrict__ exp_out,
+                                                                   int planes, const long long* __restrict__ ns_dev) {
+  __shared__ float red[3][8];
+  const int64_t s = blockIdx.x;
+  if (ns_dev && s >= *ns_dev) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* x4 = reinterpret_cast<const float4*>(x + s * (int64_t)planes * N * 8);
+  float m = 0.f, A = 0.f, B = 0.f;
+  for (int e4 = tid; e4 < planes * N * 2; e4 += blockDim.x) {
+    const int c0 = (e4 / (N * 2)) * 8 + (e4 & 1) * 4;
+    if (c0 >= C) continue;
+    const float4 q = x4[e4];
+    float z[4] = {q.x * inv_norm, q.y * inv_norm, q.z * inv_norm, q.w * inv_norm};
+    const int nv = min(4, C - c0);
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) mx = fmaxf(mx, fabsf(z[i]));
+    if (mx > m) {
+      const float r = expf(m - mx);
+      A *= r; B *= r; m = mx;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) {
+        A += expf(z[i] - m);
+        if (final_act == 1) B += expf(-z[i] - m);
+      }
+  }
+  auto merge = [](float& m1, float& a1, float& b1, float m2, float a2, float b2) {
+    const float mm = fmaxf(m1, m2);
+    const float r1 = expf(m1 - mm), r2 = expf(m2 - mm);
+    a1 = a1 * r1 + a2 * r2;
+    b1 = b1 * r1 + b2 * r2;
+    m1 = mm;
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(FULL, m, o), a2 = __shfl_xor_sync(FULL, A, o), b2 = __shfl_xor_sync(FULL, B, o);
+    merge(m, A, B, m2, a2, b2);
+  }
+  if (lane == 0) { red[0][warp] = m; red[1][warp] = A; red[2][warp] = B; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) merge(m, A, B, red[0][w], red[1][w], red[2][w]);
+    float tot = A;
+    if (final_act == 1) tot = (A - B) * 0.5f + (float)(C * N) * expf(-m);
+    const float a = tot / (float)C;
+    const float ch = 1.0f / (float)N;  // character of sector 0 (symmetry.py:391)
+    const float ech = logf(ch);        // ScaleArray.from_value(character).normalize() (big_array.py:442-451)
+    const float c1 = ch * expf(0.f - ech);
+    if (sig_out) sig_out[s] = (double)(a * c1);
+    if (exp_out) exp_out[s] = (double)(m + ech);
+  }
+}
+
 // Complex-output final layer (conv_nets.py:165-173 with out_dtype complex: pair_cpl, nn/activation.py:75-81):
 //   z_c = (x_c + i x_{c + C/2}) / sqrt(nblocks+1), cast to complex128; m = max|z|; sig = exp(z - m) | sinh-plus-one
 //   a_r = mean_c sig; psi = ScaleArray(sum_r a_r * c1, m + log(1/N)), all in complex128 / float64.
@@ -982,6 +1044,9 @@ static int resconv_run(const NetShape& sh, const T* params, const int8_t* spins,
   if (cpl)
     resconv_final_cplx_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
                                                                sh.final_act, (double2*)sig_out, exp_out, dA, dC, tc_planes, ns_dev);
+  else if (std::is_same<T, float>::value && tc_planes > 0 && !dA && !getenv("QTX_FINAL_TWO_PASS"))
+    resconv_final_planar_kernel<<<(unsigned)ns, 256, 0, st>>>((const float*)xlast, ns, C, N, (float)(1.0 / sqrt((double)(nb + 1))),
+                                                              sh.final_act, sig_out, exp_out, tc_planes, ns_dev);
   else
     resconv_final_kernel<T><<<(unsigned)ns, 256, 0, st>>>(xlast, ns, C, N, (T)(1.0 / sqrt((double)(nb + 1))),
                                                           sh.final_act, sig_out, exp_out, dA, tc_planes, ns_dev);

@@ -106,3 +106,26 @@ def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+# ---- NVTX ranges per phase of the VMC step (QTX_NVTX=1; SURVEY section 5: tracing) --------------------------------
+import contextlib as _contextlib
+import os as _os
+
+NVTX = _os.environ.get("QTX_NVTX", "0") == "1"
+
+
+@_contextlib.contextmanager
+def nvtx_range(name: str):
+    """``with nvtx_range("sweep"):`` -- an NVTX range around a phase when QTX_NVTX=1 (ncu / nsys can filter on it),
+    nothing otherwise."""
+    if not NVTX:
+        yield
+        return
+    import torch
+
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()

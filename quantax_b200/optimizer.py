@@ -761,17 +761,23 @@ class QNGD:
             self._Omean = mean  # == mean(O * rw) for reweight 2 (rw = 1)
             Obar = state.jacobian(samples.spins, col_mean=mean, row_scale=scale, tanh_table=table)
         else:
+            t = _phase_tic("jacobian.rows")
             Omat = state.jacobian(samples.spins)
+            _phase_toc(t)
             mean = torch.empty(Omat.shape[1], dtype=torch.float64, device=Omat.device)
             dt = _lib.dtype_code(Omat.dtype)
+            t = _phase_tic("jacobian.colmean")
             _lib.call("qtx_colmean", dt, _lib.ptr(Omat), Omat.shape[0], Omat.shape[1], Omat.stride(0), None,
                       _lib.ptr(mean), _lib.stream())
             if P > 1:
                 _dist().all_reduce(mean)
                 mean /= P
+            _phase_toc(t)
             self._Omean = mean
+            t = _phase_tic("jacobian.center_scale")
             _lib.call("qtx_center_scale", dt, _lib.ptr(Omat), Omat.shape[0], Omat.shape[1], Omat.stride(0),
                       _lib.ptr(mean), _lib.ptr(scale), _lib.stream())
+            _phase_toc(t)
             Obar = Omat
         self._toc(ev)
         return Obar
@@ -794,9 +800,14 @@ class QNGD:
         """Save the optimizer internal quantities (sr.py:125-128): plain SR has none."""
 
     def get_step(self, samples, **kw) -> torch.Tensor:
-        Ebar = self.get_Ebar(samples, **kw)
-        Obar = self.get_Obar(samples)
-        return self.solve(Obar, Ebar)
+        from .global_defs import nvtx_range
+
+        with nvtx_range("qtx.Ebar(Oloc)"):
+            Ebar = self.get_Ebar(samples, **kw)
+        with nvtx_range("qtx.Obar(jacobian)"):
+            Obar = self.get_Obar(samples)
+        with nvtx_range("qtx.solve"):
+            return self.solve(Obar, Ebar)
 
 
 class SR(QNGD):

@@ -182,6 +182,12 @@ class Metropolis(Sampler):
 
     def sweep(self, nsweeps: Optional[int] = None, record: bool = False) -> Samples:
         """Generate new samples (metropolis.py:171-215)."""
+        from .global_defs import nvtx_range
+
+        with nvtx_range("qtx.sweep"):
+            return self._sweep(nsweeps, record)
+
+    def _sweep(self, nsweeps: Optional[int] = None, record: bool = False) -> Samples:
         if nsweeps is None:
             nsweeps = self._sweep_steps
         state = self._state

@@ -122,25 +122,32 @@ class Symmetry:
         return self._device_tables
 
 
-_IDENTITY = {}
-_Z2 = {}
+# Per-lattice singletons.  The cache holds the lattice object itself: keyed by id() alone, a new lattice that happened to
+# get the address of a collected one was handed the old lattice's tables (wrong Nmodes).
+_SINGLETONS = {"sites": None, "identity": None, "z2": {}}
+
+
+def _singletons():
+    sites = get_sites()
+    if _SINGLETONS["sites"] is not sites:
+        _SINGLETONS.update(sites=sites, identity=None, z2={})
+    return _SINGLETONS
 
 
 def Identity() -> Symmetry:
-    key = id(get_sites())
-    if key not in _IDENTITY:
-        _IDENTITY.clear()
-        _IDENTITY[key] = Symmetry()
-    return _IDENTITY[key]
+    c = _singletons()
+    if c["identity"] is None:
+        c["identity"] = Symmetry()
+    return c["identity"]
 
 
 def Z2Inversion(eigval: int = 1) -> Symmetry:
     if eigval not in (1, -1):
         raise ValueError("'eigval' of Z2Inversion should be 1 or -1.")
-    key = (id(get_sites()), eigval)
-    if key not in _Z2:
-        _Z2[key] = Symmetry(Z2_inversion=eigval)
-    return _Z2[key]
+    c = _singletons()
+    if eigval not in c["z2"]:
+        c["z2"][eigval] = Symmetry(Z2_inversion=eigval)
+    return c["z2"][eigval]
 
 
 def SpinInverse(eigval: int = 1) -> Symmetry:

@@ -65,9 +65,11 @@ def test_float32_input_is_exact_with_four_digits_up_to_the_dropped_levels():
 
 def test_k_chunks_accumulate_and_accumulate_flag():
     s = 8
-    kc = gd.chunk_columns(10 ** 6, s)
-    assert kc % 64 == 0 and kc * s * 4096 < 2 ** 31 <= (kc + 64) * s * 4096 + s * 4096 * 64
-    A = _matrix(6, kc + 777, 4)  # two K chunks
+    kmax = gd.chunk_columns(1 << 40, s)  # the largest chunk the exact int32 accumulation allows
+    assert kmax % 64 == 0 and kmax * s * 4096 < 2 ** 31 <= (kmax + 64) * s * 4096 + s * 4096 * 64
+    kc = gd.chunk_columns(10 ** 6, s)  # equal chunks: 16 of 62 528 columns, not 15 of 65 472 and a short one
+    assert kc % 64 == 0 and kc <= kmax and -(-10 ** 6 // kc) == -(-10 ** 6 // kmax) and 10 ** 6 - 15 * kc > kc // 2
+    A = _matrix(6, kmax + 777, 4)  # two K chunks
     T = gd.gram(A, s)
     assert _rel_err(T, A) <= 2e-15
     # T_accum: second call adds to the first (qtx_gram T_accum = 1)

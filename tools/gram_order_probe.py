@@ -40,7 +40,7 @@ def main():
         print(f"{name}: identical {torch.equal(out['0'], out['1'])}", flush=True)
         del A, out
         torch.cuda.empty_cache()
-    os.environ["QTX_GRAM_SUPERTILE"] = "1"
+    os.environ.pop("QTX_GRAM_SUPERTILE", None)
 
 
 if __name__ == "__main__":
