@@ -338,7 +338,9 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(qtx_ffi_matvec_t, MatvecTImpl,
                                   .Ret<ffi::Buffer<ffi::F64>>());
 
 // ---- distributed MinSR solve over the library's own communicator (optimizer/solver.py:128-149 under GSPMD) -----------------------
-// `comm` is the qtx_comm_t the host created once (qtx_comm_init / qtx_comm_adopt), passed as an integer attribute
+// `comm` is the qtx_comm_t the host created once (qtx_comm_init / qtx_comm_adopt), passed as an integer attribute;
+// lanczos_steps < 0 runs exactly that many Lanczos steps without a host read-back inside the custom call, > 0 is the
+// adaptive run of the single-GPU solve (include/qtx_b200.h)
 ffi::Error MinsrSolveDistImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> obar_local, ffi::Buffer<ffi::F64> ebar_local,
                               ffi::ResultBuffer<ffi::F64> x, ffi::ResultBuffer<ffi::S32> info,
                               ffi::ResultBuffer<ffi::U8> workspace, int64_t comm, double rtol, double atol,

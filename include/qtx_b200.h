@@ -557,8 +557,10 @@ int qtx_comm_all_to_all(qtx_comm_t comm, const void* send, void* recv, int64_t b
  * pseudo-inverse y = f(T) b with the three shifted LDL^T solves split over the ranks (qtx_pinv_ldlt_partial) and
  * their double-double partial sums all-gathered and added in rank order (bit-identical y everywhere), the column
  * shard of x = A^T y, all-gather (solver.py:146).  A_local [nl, np] (ld), b_local [nl], x_out [np] float64 on every
- * rank, info_out int32 [1] device (0 = ok).  max|lambda| comes from exactly `lanczos_steps` Lanczos steps (no host
- * read-back; 128 suffices unless the top of the spectrum is dense). */
+ * rank, info_out int32 [1] device (0 = ok).  max|lambda|: `lanczos_steps` > 0 = adaptive Lanczos run of at most that
+ * many steps (stages 32, 64, 128, ... until two stages agree to 1e-7, one scalar read-back per stage, the rule of the
+ * single-GPU solve; all ranks stop at the same stage because T is bit-identical); < 0 = exactly |lanczos_steps| steps
+ * without any host synchronisation (128 suffices unless the top of the spectrum is dense). */
 size_t qtx_minsr_solve_dist_workspace_size(qtx_comm_t comm, int dtype, int64_t nl, int64_t np, int nslices);
 int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_local, int64_t nl, int64_t np, int64_t ld,
                          const double* b_local, double rtol, double atol, int nslices, int lanczos_steps,

@@ -285,7 +285,7 @@ extern "C" int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_lo
                                     int refine_steps, double* x_out, int32_t* info_out, void* workspace,
                                     size_t workspace_bytes, qtx_stream_t stream) {
   QTX_REQUIRE(comm && A_local && b_local && x_out && info_out && workspace && nl > 0 && np > 0 && ld >= np &&
-                  (dtype == QTX_F32 || dtype == QTX_F64) && lanczos_steps > 0,
+                  (dtype == QTX_F32 || dtype == QTX_F64) && lanczos_steps != 0,
               QTX_ERR_INVALID, "qtx_minsr_solve_dist: bad argument");
   Comm* c = (Comm*)comm;
   NcclApi* api;
@@ -325,8 +325,31 @@ extern "C" int qtx_minsr_solve_dist(qtx_comm_t comm, int dtype, const void* A_lo
   int nsh = 0;
   for (int k = 0; k < 3; ++k) nsh += (mask >> k) & 1;
   double* lam = (double*)(base + L.lam);
-  rc = qtx_sym_absmax_eig_ws(T, ns, 0, lanczos_steps, lam, base + L.pinv, L.pinv_bytes, nsh > 0 ? nsh : 1, stream);
-  if (rc) return rc;
+  if (lanczos_steps < 0) {  // exactly |lanczos_steps| steps, no host read-back
+    rc = qtx_sym_absmax_eig_ws(T, ns, 0, -lanczos_steps, lam, base + L.pinv, L.pinv_bytes, nsh > 0 ? nsh : 1, stream);
+    if (rc) return rc;
+  } else {
+    // adaptive like the single-GPU solve (optimizer.py sym_absmax_eig): continue the recurrence to 32, 64, 128, ...
+    // steps until two consecutive values agree to 1e-7 (the error roughly squares when the step count doubles); one
+    // scalar read-back per stage.  T is bit-identical on all ranks, so all ranks stop at the same stage.
+    const int cap = (int)(lanczos_steps < ns ? lanczos_steps : ns);
+    double prev = 0.0;
+    bool have_prev = false;
+    int done = 0;
+    for (int upto = 32;; upto *= 2) {
+      if (upto > cap) upto = cap;
+      rc = qtx_sym_absmax_eig_ws(T, ns, done, upto, lam, base + L.pinv, L.pinv_bytes, nsh > 0 ? nsh : 1, stream);
+      if (rc) return rc;
+      done = upto;
+      if (upto >= cap) break;
+      double cur = 0.0;
+      QTX_CUDA(cudaMemcpyAsync(&cur, lam, sizeof(double), cudaMemcpyDeviceToHost, st));
+      QTX_CUDA(cudaStreamSynchronize(st));
+      if (have_prev && fabs(cur - prev) <= 1e-7 * fabs(cur)) break;
+      prev = cur;
+      have_prev = true;
+    }
+  }
   dist_mark(4, st);
   double* ydd = (double*)(base + L.ydd);
   int32_t* info = (int32_t*)(base + L.info);

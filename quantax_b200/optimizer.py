@@ -430,7 +430,7 @@ def distributed_minnorm(A: torch.Tensor, b: torch.Tensor, rtol, atol, ops, tsolv
 # when the process group is NCCL and the default pseudo-inverse route is in use; QTX_DIST_C=0 keeps the collectives in
 # torch.distributed (the path the gloo tests exercise on CPU), which is also what SNR damping and the other T-solvers use.
 DIST_IN_LIBRARY = os.environ.get("QTX_DIST_C", "1") == "1"
-DIST_LANCZOS_STEPS = int(os.environ.get("QTX_DIST_LANCZOS_STEPS", "128"))
+DIST_LANCZOS_STEPS = int(os.environ.get("QTX_DIST_LANCZOS_STEPS", str(LANCZOS_STEPS)))  # > 0 adaptive cap, < 0 exactly
 
 
 def _dist_in_library(tol_snr: float) -> bool:
