@@ -170,7 +170,7 @@ int64_t qtx_resconv_nparams(int nblocks, int channels, int lx, int ly, int kh, i
 /* 1 if the float32 tensor-core tower (csrc/resconv_tc.cu) serves this shape, else 0 (CUDA-core path). */
 int qtx_resconv_tc_available(int model_dtype, int channels, int lx, int ly, int kh, int kw);
 /* 1 if qtx_resconv_jacobian / _cplx also run their backward pass (variational.py:429-491) on the tensor cores for
- * this shape (SEG raster of the CTA-pair tower: ly % 8 == 0, lx * ly / 128 in {1, 2}), else 0 (CUDA-core backward). */
+ * this shape (wherever the CTA-pair tower serves the forward), else 0 (CUDA-core backward). */
 int qtx_resconv_tc_backward_available(int model_dtype, int channels, int lx, int ly, int kh, int kw);
 size_t qtx_resconv_workspace_size(int model_dtype, int64_t ns, int nblocks, int channels, int lx,
                                   int ly, int kh, int kw, int need_grad);

@@ -99,6 +99,8 @@ struct TcNetParams {
   int act_stages, w_stages;
   int64_t buf_u4;          // 16-byte units per operand buffer
   int precise;             // accurate gelu / gelu' (towers of the Jacobian)
+  __half* act_z;           // backward-data tower on the RASTER layout: second operand set written WITHOUT halo copies
+                           // (the K axis of the weight-gradient GEMM crosses the halo columns), or null
   float out_scale;         // kOutScale times the expected-value correction of the truncating accumulator (tc_trunc_comp)
   unsigned long long* dbg;  // optional [grid][16] cycle counters (QTX_TC_DEBUG=1)
   const long long* ns_dev;  // optional device-side sample count (<= g.ns): batches whose size is decided on the device
@@ -1172,7 +1174,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     split2(v[2] * s_out, v[3] * s_out, vh.y, vl.y);
                     split2(v[4] * s_out, v[5] * s_out, vh.z, vl.z);
                     split2(v[6] * s_out, v[7] * s_out, vh.w, vl.w);
-                    uint4* act_hi = act_sample + (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
+                    const int64_t poff = (int64_t)((plane >> 1) * 4 + (plane & 1)) * g.slots;
+                    uint4* act_hi = act_sample + poff;
                     uint4* act_lo = act_hi + 2 * g.slots;
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4)
@@ -1180,6 +1183,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         act_hi[rps[t].o[q4]] = vh;
                         act_lo[rps[t].o[q4]] = vl;
                       }
+                    if (p.act_z) {  // interior slot only
+                      uint4* z_hi = reinterpret_cast<uint4*>(p.act_z) + (int64_t)L.out_buf * p.buf_u4 + s * g.Ps + poff;
+                      z_hi[rps[t].o[0]] = vh;
+                      z_hi[2 * g.slots + rps[t].o[0]] = vl;
+                    }
                   }
                 }
                 if (pix == 0 && cgp == 0) L.sig_out[s] = s_out;
@@ -1223,8 +1231,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // ---------------------------------------------------------------------------------------------
 // seed: raw d log psi / d x_last [ns, C, N] -> gradient operand buffer 0 (scaled per sample), max and scale arrays
 __global__ void __launch_bounds__(256) tc_grad_seed_kernel(const float* __restrict__ dz, TcGeom g, int C, int Np,
-                                                           __half* __restrict__ gbuf, float* __restrict__ gmax,
-                                                           float* __restrict__ gsig) {
+                                                           __half* __restrict__ gbuf, __half* __restrict__ gzbuf,
+                                                           float* __restrict__ gmax, float* __restrict__ gsig) {
   __shared__ float red[8];
   __shared__ float bc;
   const int64_t s = blockIdx.x;
@@ -1254,17 +1262,25 @@ __global__ void __launch_bounds__(256) tc_grad_seed_kernel(const float* __restri
       t[j] = (c < C) ? sig * d[c * N + pix] : 0.f;
     }
     store_plane(gbuf, g, plane, s * g.Ps, ps, t);
+    if (gzbuf) {  // RASTER: the copy without halo slots (weight-gradient kernel)
+      PixSlots p1 = ps;
+      p1.n = 1;
+      store_plane(gzbuf, g, plane, s * g.Ps, p1, t);
+    }
   }
 }
 
-// Per-sample weight gradient of one convolution (SEG raster only):
+// Per-sample weight gradient of one convolution:
 //   O[s, col0 + (o C + c) 9 + tap] = sum_pix dY[s, o, pix] * a[s, c, pix + tap]
 // as a GEMM with M = o (128 rows, C used), N = c, K = pixels.  Both operands are the rasters the towers left behind,
 // read MN-major: a 16-byte slot holds 8 channels of one pixel, 8 consecutive slots of a plane are a core matrix of
 // the no-swizzle MN-major layout (SBO = plane pitch, LBO = 10 slots = the next 8-pixel segment), and the operand of
 // tap (dy, dx) is the staged activation chunk addressed dy * row_pitch + dx slots further.  TMEM holds the nine tap
 // accumulators of NPh in-channels (9 NPh <= 512 columns), so the in-channel planes are covered in `npass` passes;
-// K runs over chunks of CR pixel rows staged by bulk copies (dY rows + activation rows with their halo).
+// K runs over chunks of pixel rows (SEG) / of 16-slot steps (RASTER) staged by bulk copies (gradient slots +
+// activation slots with one raster row of halo on either side).  On the RASTER layout K runs over ALL slots from the
+// first to the last interior pixel, halo columns included, so the gradient operand must be ZERO there: the towers
+// keep a second copy of every gradient operand without halo copies for this kernel (TcNetParams::act_z).
 //   warp 0 producer, warp 1 MMA issuer, warps 2-13 epilogue (TMEM -> float64 / float32 Jacobian entries).
 struct WgLayer {
   int g_buf, a_buf;   // gradient / activation operand buffers
@@ -1276,7 +1292,9 @@ struct WgParams {
   int64_t buf_halfs;
   TcGeom g;
   int C, Np, KS, nl;
-  int CR, nchunks, KK;   // pixel rows per chunk, chunks per sample, K steps (16 pixels) per chunk
+  int nchunks, KK;       // chunks per sample, K steps (16 pixels) per chunk
+  int runA, runB;        // slots per staged plane run of the gradient / activation chunk
+  int chunk_stride;      // slots between consecutive chunks (KK K steps)
   int npass, PP;         // passes over the in-channel planes, planes per pass
   int stages;
   int pad_bytes;         // slack behind the last stage (the 128-row gradient operand reads 16 planes)
@@ -1325,7 +1343,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) resconv_wgrad_tc_kernel(const _
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   const TcGeom& g = p.g;
   const int planes = p.Np >> 3;
-  const uint32_t runA16 = (uint32_t)(p.CR * g.RP), runB16 = (uint32_t)((p.CR + 2) * g.RP);  // slots per staged plane run
+  const uint32_t runA16 = (uint32_t)p.runA, runB16 = (uint32_t)p.runB;  // slots per staged plane run
   const uint32_t offA_lo = (uint32_t)planes * runA16;
   const uint32_t offB_hi = 2u * (uint32_t)planes * runA16, offB_lo = offB_hi + (uint32_t)p.PP * runB16;
   const uint32_t stage16 = offB_hi + 2u * (uint32_t)p.PP * runB16;
@@ -1368,8 +1386,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) resconv_wgrad_tc_kernel(const _
             const uint32_t bytes = (2u * (uint32_t)planes * runA16 + 2u * (uint32_t)np_pass * runB16) * 16u;
             mbar_expect_tx(full + st, bytes);
             unsigned char* dst = smem + (size_t)st * stage_bytes;
-            const int64_t slotA = s * g.Ps + (int64_t)(ch * p.CR + 1) * g.RP;  // first interior row of the chunk
-            const int64_t slotB = s * g.Ps + (int64_t)(ch * p.CR) * g.RP;      // one row above it
+            const int64_t slotA = s * g.Ps + g.RP + (int64_t)ch * p.chunk_stride;  // raster row of the chunk's first pixel
+            const int64_t slotB = slotA - g.RP;                                     // one row above it
             for (int hl = 0; hl < 2; ++hl)
               for (int pl = 0; pl < planes; ++pl) {
                 const int64_t row = (pl >> 1) * 4 + hl * 2 + (pl & 1);
@@ -1618,11 +1636,15 @@ static bool tc_bwd_disabled() {
   return e && e[0] == '0';
 }
 
-// the Jacobian runs on the tensor cores for the SEG raster of the CTA-pair kernel (resconv_tc_backward)
+// the Jacobian runs on the tensor cores wherever the CTA-pair tower does (resconv_tc_backward)
 bool resconv_tc_backward_supported(int C, int lx, int ly, int kh, int kw) {
   if (!resconv_tc_supported(C, lx, ly, kh, kw) || !tc_use_pair() || tc_bwd_disabled()) return false;
   TcGeom g;
-  if (!tc_geometry(lx, ly, 1, g, true) || g.mode != 1) return false;
+  if (!tc_geometry(lx, ly, 1, g, true)) return false;
+  if (g.mode != 1) {  // RASTER (dev knob: QTX_RESCONV_TC_BWD_RASTER=0 keeps these lattices on the CUDA cores)
+    const char* e = getenv("QTX_RESCONV_TC_BWD_RASTER");
+    if (e && e[0] == '0') return false;
+  }
   return ((C + 15) & ~15) <= 128;
 }
 
@@ -1630,8 +1652,8 @@ bool resconv_tc_backward_supported(int C, int lx, int ly, int kh, int kw) {
 // raw gradients [ns, C, N] of every convolution output, per-sample scales
 struct TcBwdLayout {
   size_t buf_bytes;  // one operand buffer
-  size_t op_off, wf_off, wb_off, g_off, rg_off, gmax_off, gsig_off, wnorm_off, total;
-  int nl;
+  size_t op_off, wf_off, wb_off, g_off, gz_off, rg_off, gmax_off, gsig_off, wnorm_off, total;
+  int nl, raster;
 };
 static TcBwdLayout tc_bwd_layout(int nblocks, int C, int lx, int ly, int64_t ns) {
   TcGeom g;
@@ -1646,6 +1668,9 @@ static TcBwdLayout tc_bwd_layout(int nblocks, int C, int lx, int ly, int64_t ns)
   L.wf_off = off; off += wb;
   L.wb_off = off; off += wb;
   L.g_off = off; off += align256((size_t)L.nl * L.buf_bytes);
+  L.raster = g.mode == 0 ? 1 : 0;
+  L.gz_off = off;  // RASTER: gradient operands without halo copies
+  if (L.raster) off += align256((size_t)L.nl * L.buf_bytes);
   L.rg_off = off; off += (size_t)L.nl * align256((size_t)ns * C * lx * ly * 4);
   L.gmax_off = off; off += align256((size_t)(L.nl + 1) * ns * 4);
   L.gsig_off = off; off += align256((size_t)(L.nl + 1) * ns * 4);
@@ -1870,6 +1895,11 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   }
   pp.nconv = nl;
   pp.bias_pad = bias_pad;
+  if (keep_ops && g.mode == 0)
+    // RASTER: the K axis of the weight-gradient GEMM runs a few slots past the last interior pixel of a sample; the
+    // gradient is zero there, so the activation slots it meets only have to be finite -- also in the guard behind the
+    // last sample, which no kernel writes
+    QTX_CUDA(cudaMemsetAsync(act, 0, (size_t)nl * bl.buf_bytes, st));
   if (x_final) *x_final = save_all ? X + (int64_t)(nblocks - 1) * actsz : resid;
   if (x_final_planes) *x_final_planes = save_all ? 0 : (Np >> 3);
   {
@@ -1902,7 +1932,7 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
   int Np, KS;
   size_t blob_halfs, act_bytes, wblob_bytes, resid_bytes;
   tc_sizes(nblocks, C, lx, ly, ns, g, Np, KS, blob_halfs, act_bytes, wblob_bytes, resid_bytes);
-  QTX_REQUIRE(g.pair && g.mode == 1, QTX_ERR_UNSUPPORTED, "resconv_tc_backward: needs the SEG raster of the CTA-pair kernel");
+  QTX_REQUIRE(g.pair, QTX_ERR_UNSUPPORTED, "resconv_tc_backward: needs the CTA-pair kernel");
   const TcBwdLayout bl = tc_bwd_layout(nblocks, C, lx, ly, ns);
   QTX_REQUIRE(ws_bytes >= bl.total - 256, QTX_ERR_INVALID, "resconv_tc_backward: workspace too small");
   unsigned char* base = (unsigned char*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
@@ -1910,6 +1940,7 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
   const int64_t actsz = ns * C * N;
   __half* OP = reinterpret_cast<__half*>(base + bl.op_off);
   __half* G = reinterpret_cast<__half*>(base + bl.g_off);
+  __half* Gz = bl.raster ? reinterpret_cast<__half*>(base + bl.gz_off) : nullptr;
   __half* wblob = reinterpret_cast<__half*>(base + bl.wb_off);
   float* bias_pad = reinterpret_cast<float*>(wblob + (size_t)nl * blob_halfs);
   float* gmax = reinterpret_cast<float*>(base + bl.gmax_off);
@@ -1938,6 +1969,7 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
     np.precise = e ? atoi(e) : 0;
   }
   np.out_scale = kOutScale * tc_trunc_comp(9 * ((C + 15) / 16));
+  np.act_z = Gz;
   WgParams wp{};
   int d = 0, nw = 0;
   for (int i = nblocks - 1; i >= 0; --i) {
@@ -1976,6 +2008,8 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
   QTX_REQUIRE(d == nl, QTX_ERR_INVALID, "resconv_tc_backward: layer count");
   pp.nconv = nl;
   QTX_CUDA(cudaMemsetAsync(gmax, 0, (size_t)(nl + 1) * ns * 4, st));
+  if (Gz)  // halo slots and the guard behind the last sample stay zero (K of the weight-gradient GEMM crosses them)
+    QTX_CUDA(cudaMemsetAsync(Gz, 0, (size_t)nl * bl.buf_bytes, st));
   {
     const int n = 9 * KS * 16 * Np;
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)nl);
@@ -1984,7 +2018,7 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
     tc_wnorm_kernel<<<nl, 256, 0, st>>>(pp);
     QTX_LAUNCH_CHECK();
   }
-  tc_grad_seed_kernel<<<(unsigned)ns, 256, 0, st>>>(seed, g, C, Np, G, gmax, gsig);
+  tc_grad_seed_kernel<<<(unsigned)ns, 256, 0, st>>>(seed, g, C, Np, G, Gz, gmax, gsig);
   QTX_LAUNCH_CHECK();
   {
     int rc = tc_launch_tower(np, nl, nl, st);
@@ -1995,28 +2029,31 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
   if (const char* e = getenv("QTX_TC_WGRAD")) {  // dev knob: 0 = the caller computes them from raw_grad (CUDA cores)
     if (e[0] == '0') return QTX_OK;
   }
-  wp.G = G; wp.A = OP; wp.buf_halfs = (int64_t)KS * 4 * g.slots * 8; wp.g = g; wp.C = C; wp.Np = Np; wp.KS = KS;
+  wp.G = Gz ? Gz : G; wp.A = OP; wp.buf_halfs = (int64_t)KS * 4 * g.slots * 8; wp.g = g; wp.C = C; wp.Np = Np; wp.KS = KS;
   wp.nl = nw; wp.gsig = gsig; wp.ns = ns; wp.out = out; wp.ld = ld; wp.out_f64 = out_f64;
   wp.PP = planes >= 6 ? 6 : ((planes + 1) & ~1);
   wp.npass = (planes + wp.PP - 1) / wp.PP;
   const size_t line_bytes = (size_t)((C + 31) / 32) * 2 * 32 * (out_f64 ? WgLine<double>::kPitch : WgLine<float>::kPitch);
   const size_t cap = 227 * 1024 - 1024 - line_bytes - 128;  // minus the epilogue's output boxes
-  int CR = 0;
-  size_t stage = 0;
-  for (int cr = g.H; cr >= 1; --cr) {
-    if (g.H % cr || (cr * g.nseg) % 2) continue;
-    const size_t sb = ((size_t)2 * planes * cr * g.RP + (size_t)2 * wp.PP * (cr + 2) * g.RP) * 16;
-    const size_t rch = (size_t)(planes + 16) * cr * g.RP * 16;
-    const size_t pd = rch > sb ? rch - sb + 128 : 0;
-    if (3 * sb + pd + 256 <= cap || (CR == 0 && cr == 1)) { CR = cr; stage = sb; break; }
+  // K axis: SEG = interior 8-pixel segments (two per step), RASTER = all slots from the first to the last interior
+  // pixel, padded to whole steps of 16 (the padding lies in the zeroed halo of the gradient copy)
+  const int kstride = 2 * g.SB;  // slots per K step
+  const int Ktot = g.mode ? g.H * g.nseg / 2 : ((g.H - 1) * g.RP + g.W + 15) / 16;
+  int KK = 0;
+  size_t stage = 0, pad = 0;
+  for (int kk = Ktot; kk >= 1; --kk) {
+    if (Ktot % kk) continue;
+    const int runA = kk * kstride + (g.mode ? 0 : 2), runB = kk * kstride + 2 * g.RP + 2;
+    const size_t sb = ((size_t)2 * planes * runA + (size_t)2 * wp.PP * runB) * 16;
+    // M = 128 reads 16 planes from each gradient half: the rows beyond Np alias whatever follows in shared memory
+    // (results of those rows are never read); behind the last stage that needs slack
+    const size_t reach = (size_t)(planes + 16) * runA * 16;
+    const size_t pd = reach > sb ? ((reach - sb + 127) & ~(size_t)127) : 0;
+    if (3 * sb + pd + 256 <= cap || kk == 1) { KK = kk; stage = sb; pad = pd; wp.runA = runA; wp.runB = runB; break; }
   }
-  // M = 128 reads 16 planes from each gradient half: the rows beyond Np alias whatever follows in shared memory
-  // (results of those rows are never read); behind the last stage that needs slack
-  const size_t reach = (size_t)(planes + 16) * CR * g.RP * 16;
-  const size_t pad = reach > stage ? ((reach - stage + 127) & ~(size_t)127) : 0;
-  QTX_REQUIRE(CR > 0 && 2 * stage + pad + 256 <= cap, QTX_ERR_UNSUPPORTED, "resconv_tc_backward: no pixel-row chunk fits");
-  wp.CR = CR; wp.nchunks = g.H / CR; wp.KK = CR * g.nseg / 2;
-  wp.comp = tc_trunc_comp(3 * (g.H * g.nseg / 2));  // one accumulator: three products per 16-pixel step
+  QTX_REQUIRE(KK > 0 && 2 * stage + pad + 256 <= cap, QTX_ERR_UNSUPPORTED, "resconv_tc_backward: no K chunk fits");
+  wp.KK = KK; wp.nchunks = Ktot / KK; wp.chunk_stride = KK * kstride;
+  wp.comp = tc_trunc_comp(3 * Ktot);  // one accumulator: three products per 16-pixel step
   int stages = (int)((cap - 256 - pad) / stage);
   if (stages > 6) stages = 6;
   wp.stages = stages;

@@ -105,10 +105,14 @@ def test_jacobian_matches_oracle(qtx, kind, L, shape, nb, C, k, final, dtype, to
     check(f"jacobian {shape} C={C} {dtype}", np.abs(O - Oo).max() / np.abs(Oo).max(), tol)
 
 
-# shapes served by the tensor-core Jacobian (csrc/resconv_tc.cu: backward-data tower + per-sample weight gradients on
-# the SEG raster): two tiles per sample (16x16), one (16x8), four samples per CTA pair (32x8 has two), channel counts
-# that are odd (scalar store path), not a multiple of 8 and above one 32-row quarter
+# shapes served by the tensor-core Jacobian (csrc/resconv_tc.cu: backward-data tower + per-sample weight gradients):
+# both rasters, one and two tiles per sample, two and four samples per CTA pair, channel counts that are odd (scalar
+# store path), not a multiple of 8 and above one 32-row quarter
 TC_BWD_CASES = [
+    ((10, 10), 3, 32, "sinhp1"),   # RASTER layout, one tile per sample (config C lattice and width)
+    ((12, 12), 2, 20, "exp"),      # RASTER, two tiles per sample (config D lattice)
+    ((6, 10), 2, 5, "exp"),        # RASTER, rectangular, odd channel count
+    ((4, 4), 2, 8, "sinhp1"),      # RASTER, four samples per CTA pair, K padded from 22 to 32 slots
     ((16, 16), 2, 24, "exp"),
     ((16, 16), 3, 40, "sinhp1"),
     ((16, 16), 2, 5, "exp"),

@@ -58,9 +58,18 @@ def main():
         compare("seg16 C=16 nb=1", (16, 16), 16, 1, 3)
         compare("seg 16x8 (one tile per sample)", (16, 8), 24, 2, 6)
         compare("seg 32x8", (32, 8), 20, 2, 5)
+    if what in ("raster", "all"):  # RASTER layout (any width): one and two tiles per sample
+        compare("raster 10x10 C=32 nb=3", (10, 10), 32, 3, 9, final="sinhp1")
+        compare("raster 10x10 C=36 nb=2", (10, 10), 36, 2, 5)
+        compare("raster 12x12 C=20 nb=2", (12, 12), 20, 2, 7)
+        compare("raster 8x8 C=12 nb=2", (8, 8), 12, 2, 6)
+        compare("raster 6x6 C=5 nb=3", (6, 6), 5, 3, 4)
+        compare("raster 4x4 C=8 nb=2", (4, 4), 8, 2, 11)
+        compare("raster 6x10 C=16 nb=2", (6, 10), 16, 2, 5)
     if what == "sanitize":  # small enough for compute-sanitizer
         compare("seg16 C=24 nb=2", (16, 16), 24, 2, 3)
         compare("seg 16x8 C=20 nb=2", (16, 8), 20, 2, 5, final="sinhp1")
+        compare("raster 10x10 C=16 nb=2", (10, 10), 16, 2, 3)
         print("SANITIZE_PROBE_DONE", flush=True)
     if what in ("E", "all"):
         compare("config E", (16, 16), 88, 8, 64, final="sinhp1")
@@ -79,6 +88,19 @@ def main():
         os.environ["QTX_RESCONV_TC_BWD"] = "1"
         tf = timeit(lambda: state(s))
         print(f"config E forward ns={ns}: {tf:8.2f} ms", flush=True)
+    if what in ("timeC", "all"):  # config C lattice (10x10, RASTER layout), 8 blocks of 32 channels
+        qtx.sites.Sites._SITES = None
+        qtx.sites.Square(10)
+        model = qtx.model.ResConv(8, 32, 3)
+        state = qtx.state.Variational(model)
+        ns = 8192
+        s = qtx.utils.rand_states(ns)
+        out = torch.empty((ns, model.nparams), dtype=torch.float64, device="cuda")
+        for flag in ("1", "0"):
+            os.environ["QTX_RESCONV_TC_BWD"] = flag
+            t = timeit(lambda: state.jacobian(s, out=out), 2)
+            print(f"config C shape jacobian ns={ns} Np={model.nparams} QTX_RESCONV_TC_BWD={flag}: {t:8.2f} ms", flush=True)
+        os.environ["QTX_RESCONV_TC_BWD"] = "1"
 
 
 if __name__ == "__main__":
