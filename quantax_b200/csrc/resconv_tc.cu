@@ -102,6 +102,7 @@ struct TcNetParams {
   __half* act_z;           // backward-data tower on the RASTER layout: second operand set written WITHOUT halo copies
                            // (the K axis of the weight-gradient GEMM crosses the halo columns), or null
   float out_scale;         // kOutScale times the expected-value correction of the truncating accumulator (tc_trunc_comp)
+  int epi_generic;         // dev knob QTX_TC_EPI_GENERIC=1: the generic epilogue for every layer
   unsigned long long* dbg;  // optional [grid][16] cycle counters (QTX_TC_DEBUG=1)
   const long long* ns_dev;  // optional device-side sample count (<= g.ns): batches whose size is decided on the device
   TcLayer layer[kTcMaxLayers];
@@ -1133,6 +1134,84 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               }
             }
           };
+          // The two layer kinds of the forward-only tower (sweep, Oloc) with the pointers formed once per tile: IO =
+          // planar residual stream in / out (conv2 layers), !IO = operand store only (conv1 layers).  Same arithmetic
+          // as `run`; the generic version recomputed the 64-bit element offsets of the residual, the raw output and
+          // every operand store from indices (14 integer instructions per element, at half the FP32 rate).
+          auto run_fast = [&](auto io_tag) {
+            constexpr bool IO = decltype(io_tag)::value;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int64_t s = item * g.spi + tsl[t];
+              if (!rvalid[t] || s >= ns_rt) continue;
+              const int pix = rpix[t];
+              float resv = 0.f;
+              const float* res_p = nullptr;
+              float* raw_p = nullptr;
+              if constexpr (IO) {
+                resv = Lspin ? (float)Lspin[s * N + pix] : 0.f;
+                const int64_t e0 = ((s * planes + cgp) * (int64_t)N + pix) * 8;  // plane cgp of this pixel
+                res_p = Lres ? Lres + e0 : nullptr;
+                raw_p = Lraw ? Lraw + e0 : nullptr;
+              }
+              const int64_t rstep = (int64_t)kColGroups * N * 8;  // floats between this thread's planes
+              char* act_t = reinterpret_cast<char*>(p.act) + ((int64_t)L.out_buf * p.buf_u4 + s * g.Ps) * 16;
+              const int64_t plane_bytes = (int64_t)g.slots * 16, lo_bytes = 2 * plane_bytes;
+              int64_t ob[4];
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) ob[q4] = (int64_t)rps[t].o[q4] * 16;
+              const int nslot = rps[t].n;
+#pragma unroll
+              for (int k = 0; k < PL; ++k) {
+                const int plane = cgp + kColGroups * k;
+                if (plane >= planes) continue;
+                float(&a)[8] = acc[t][k];
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(Lbias + plane * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(Lbias + plane * 8) + 1);
+                float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if constexpr (IO) {
+                  if (res_p) {
+                    const float4 r0 = *reinterpret_cast<const float4*>(res_p + k * rstep);
+                    const float4 r1 = *reinterpret_cast<const float4*>(res_p + k * rstep + 4);
+                    r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+                    if (plane + kColGroups < planes) prefetch_l1(res_p + (k + 1) * rstep);
+                  }
+                }
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) a[jj] = fmaf(a[jj], p.out_scale, resv + bb[jj]) + r[jj];
+                if constexpr (IO) {
+                  if (raw_p) {
+                    *reinterpret_cast<float4*>(raw_p + k * rstep) = make_float4(a[0], a[1], a[2], a[3]);
+                    *reinterpret_cast<float4*>(raw_p + k * rstep + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                  }
+                }
+                if (Lwrite) {
+                  float tt[8];
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) tt[jj] = gelu_scaled(a[jj], gk);
+                  uint4 vh, vl;
+                  split2(tt[0], tt[1], vh.x, vl.x);
+                  split2(tt[2], tt[3], vh.y, vl.y);
+                  split2(tt[4], tt[5], vh.z, vl.z);
+                  split2(tt[6], tt[7], vh.w, vl.w);
+                  char* ph = act_t + (int64_t)((plane >> 1) * 4 + (plane & 1)) * plane_bytes;
+                  *reinterpret_cast<uint4*>(ph + ob[0]) = vh;
+                  *reinterpret_cast<uint4*>(ph + lo_bytes + ob[0]) = vl;
+                  if (nslot >= 2) {  // halo copies: a pixel has 1, 2 (edge) or 4 (corner) slots
+                    *reinterpret_cast<uint4*>(ph + ob[1]) = vh;
+                    *reinterpret_cast<uint4*>(ph + lo_bytes + ob[1]) = vl;
+                    if (nslot == 4) {
+                      *reinterpret_cast<uint4*>(ph + ob[2]) = vh;
+                      *reinterpret_cast<uint4*>(ph + lo_bytes + ob[2]) = vl;
+                      *reinterpret_cast<uint4*>(ph + ob[3]) = vh;
+                      *reinterpret_cast<uint4*>(ph + lo_bytes + ob[3]) = vl;
+                    }
+                  }
+                }
+              }
+            }
+          };
           // backward-data layer: v = conv^T(g) * alpha gelu'(alpha * mul) + res; per-sample scales (see TcLayer)
           auto run_bwd = [&]() {
 #pragma unroll
@@ -1200,7 +1279,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           if constexpr (BWD) {
             run_bwd();
           } else {
-            if (L.planar) run(std::true_type{});
+            const bool fast_ok = p.epi_generic == 0;
+            if (L.planar && fast_ok) run_fast(std::true_type{});
+            else if (!Lres && !Lraw && !Lspin && fast_ok) run_fast(std::false_type{});
+            else if (L.planar) run(std::true_type{});
             else run(std::false_type{});
           }
           // the next layer's TMA loads (either CTA) must see these stores: proxy fence by every writer, a named
@@ -1860,6 +1942,10 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
     np.precise = e ? atoi(e) : 0;
   }
   np.out_scale = kOutScale * tc_trunc_comp(9 * ((C + 15) / 16));  // hi * hi accumulator: 9 taps x channel groups
+  {
+    const char* e = getenv("QTX_TC_EPI_GENERIC");
+    np.epi_generic = (e && e[0] == '1') ? 1 : 0;
+  }
   int nl = 0;
   for (int i = 0; i < nblocks; ++i) {
     if (i > 0) {
