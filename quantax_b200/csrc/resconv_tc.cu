@@ -103,6 +103,7 @@ struct TcNetParams {
                            // (the K axis of the weight-gradient GEMM crosses the halo columns), or null
   float out_scale;         // kOutScale times the expected-value correction of the truncating accumulator (tc_trunc_comp)
   int epi_generic;         // dev knob QTX_TC_EPI_GENERIC=1: the generic epilogue for every layer
+  int pair_k;              // CTA-pair kernel, C % 16 in 1..8: the half-filled last K step pairs two taps per MMA
   unsigned long long* dbg;  // optional [grid][16] cycle counters (QTX_TC_DEBUG=1)
   const long long* ns_dev;  // optional device-side sample count (<= g.ns): batches whose size is decided on the device
   TcLayer layer[kTcMaxLayers];
@@ -297,6 +298,7 @@ struct TcPrepParams {
   int64_t blob_off[kTcMaxLayers];
   float* bias_pad;               // [nconv][Np]
   int transpose;                 // backward-data blobs: W'[c][o][tap] = w[o][c][8 - tap], no bias
+  int pair_k;                    // last K step: tap-pair slots (see the MMA issuer of resconv_tc2_kernel)
   float* wnorm;                  // transpose: [nconv] max_c sum_{o,tap} |w[o][c][tap]|
 };
 
@@ -311,9 +313,20 @@ __global__ void __launch_bounds__(256) tc_weight_prep_kernel(TcPrepParams p) {
   const int n = 9 * Kp * p.Np;  // one entry per (tap, c, o)
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const int o = e % p.Np, c = (e / p.Np) % Kp, tap = e / (p.Np * Kp);
+    // source (channel, tap) of blob entry (slot `tap`, K position c).  Last K step of a tap-pair layout: slot
+    // (dy', dx') of the stage holds the channel group of taps 2 pi and 2 pi + 1, pi = 2 dy' + dx' (dx' < 2, pi <= 4),
+    // in its two K halves
+    int cs = c, ts = tap;
+    bool live = true;
+    if (p.pair_k && (c >> 4) == p.KS - 1) {
+      const int dyp = tap / 3, dxp = tap - dyp * 3, pi = dyp * 2 + dxp;
+      ts = 2 * pi + ((c >> 3) & 1);
+      cs = (p.KS - 1) * 16 + (c & 7);
+      live = dxp < 2 && pi <= 4 && ts <= 8;
+    }
     float v = 0.f;
-    if (o < p.C && c < p.C)
-      v = kWScale * (p.transpose ? w[((int64_t)c * p.C + o) * 9 + (8 - tap)] : w[((int64_t)o * p.C + c) * 9 + tap]);
+    if (live && o < p.C && cs < p.C)
+      v = kWScale * (p.transpose ? w[((int64_t)cs * p.C + o) * 9 + (8 - ts)] : w[((int64_t)o * p.C + cs) * 9 + ts]);
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn(v - __half2float(h));
     const int ks = c >> 4, p2 = (c >> 3) & 1, j = c & 7;
@@ -965,19 +978,49 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t a_row0 = a_stage + (uint32_t)(dy * g.RP);
                 const uint32_t a_row1 = a_row0 + tile16;
                 const uint32_t acc0 = (ks == 0 && dy == 0) ? 0u : 1u;
+                const bool pair_step = p.pair_k != 0 && ks == p.KS - 1;  // warp-uniform
                 if (elect_one()) {
+                  if (pair_step) {
+                    // The last K step holds at most 8 channels: instead of nine MMAs with a half-empty K, one MMA
+                    // takes that channel group of TWO taps -- its second K core matrix is the partner tap's, reached
+                    // through the leading-dimension offset of the descriptor.  Stage dy holds the tap pairs
+                    // (0,1),(2,3) | (4,5),(6,7) | (8,-) (tc_weight_prep_kernel); 5 MMA groups instead of 9.
+                    const uint32_t a_addr = (smem_u32(act_s) >> 4) + as * act_stage16;
 #pragma unroll
-                  for (int dx = 0; dx < 3; ++dx) {
-                    const uint32_t b_h = w_stage + (uint32_t)dx * w_tap16, b_l = b_h + 2u * nh16;
-                    const uint32_t acc = (dx == 0) ? acc0 : 1u;
-                    const uint32_t a0h = a_row0 + dx, a0l = a0h + 2u * run16;
-                    const uint32_t a1h = a_row1 + dx, a1l = a1h + 2u * run16;
-                    tc2_umma(d_main0, a0h, a_hi_w, b_h, b_hi_w, idesc, acc);
-                    tc2_umma(d_main1, a1h, a_hi_w, b_h, b_hi_w, idesc, acc);
-                    tc2_umma(d_cross0, a0l, a_hi_w, b_h, b_hi_w, idesc, acc);
-                    tc2_umma(d_cross1, a1l, a_hi_w, b_h, b_hi_w, idesc, acc);
-                    tc2_umma(d_cross0, a0h, a_hi_w, b_l, b_hi_w, idesc, 1u);
-                    tc2_umma(d_cross1, a1h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                    for (int sl = 0; sl < 2; ++sl) {
+                      const int pi = dy * 2 + sl;
+                      if (pi <= 4) {
+                        const int t0 = 2 * pi, t1 = t0 + 1;
+                        const uint32_t off0 = (uint32_t)((t0 / 3) * g.RP + t0 % 3);
+                        // tap 8 has no partner: its second K half (zero weights) re-reads the first, which is finite --
+                        // one slot further may lie behind the last sample's raster, where nothing is ever written
+                        const uint32_t off1 = t1 <= 8 ? (uint32_t)((t1 / 3) * g.RP + t1 % 3) : off0;
+                        const uint32_t b_h = w_stage + (uint32_t)sl * w_tap16, b_l = b_h + 2u * nh16;
+                        const uint32_t acc = (sl == 0) ? acc0 : 1u;
+                        const uint32_t a0h = (a_addr + off0) | ((off1 - off0) << 16), a0l = a0h + 2u * run16;
+                        const uint32_t a1h = a0h + tile16, a1l = a1h + 2u * run16;
+                        tc2_umma(d_main0, a0h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                        tc2_umma(d_main1, a1h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                        tc2_umma(d_cross0, a0l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                        tc2_umma(d_cross1, a1l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                        tc2_umma(d_cross0, a0h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                        tc2_umma(d_cross1, a1h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                      const uint32_t b_h = w_stage + (uint32_t)dx * w_tap16, b_l = b_h + 2u * nh16;
+                      const uint32_t acc = (dx == 0) ? acc0 : 1u;
+                      const uint32_t a0h = a_row0 + dx, a0l = a0h + 2u * run16;
+                      const uint32_t a1h = a_row1 + dx, a1l = a1h + 2u * run16;
+                      tc2_umma(d_main0, a0h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                      tc2_umma(d_main1, a1h, a_hi_w, b_h, b_hi_w, idesc, acc);
+                      tc2_umma(d_cross0, a0l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                      tc2_umma(d_cross1, a1l, a_hi_w, b_h, b_hi_w, idesc, acc);
+                      tc2_umma(d_cross0, a0h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                      tc2_umma(d_cross1, a1h, a_hi_w, b_l, b_hi_w, idesc, 1u);
+                    }
                   }
                   tc2_commit(w_empty + ws);
                   if (dy == 2) tc2_commit(act_empty + as);
@@ -1683,6 +1726,19 @@ static float tc_trunc_comp(int naccum) {
   return (float)(1.0 + per * naccum);
 }
 
+// tap-pair layout of a half-filled last K step (CTA-pair kernel): C % 16 in 1..8; QTX_TC_PAIRK=0 switches it off
+static int tc_pair_k(int C, bool pair) {
+  const char* e = getenv("QTX_TC_PAIRK");
+  if (e && e[0] == '0') return 0;
+  const int r = C & 15;
+  return (pair && r >= 1 && r <= 8) ? 1 : 0;
+}
+// MMA instructions that feed the hi * hi accumulator of one tile and layer
+static int tc_main_accumulates(int C, int pair_k) {
+  const int KS = (C + 15) / 16;
+  return pair_k ? 9 * (KS - 1) + 5 : 9 * KS;
+}
+
 static bool tc_disabled() {
   const char* e = getenv("QTX_RESCONV_TC");
   return e && e[0] == '0';
@@ -1934,14 +1990,16 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   // tensor-core layers: conv2_0, then (conv1_i, conv2_i) for i >= 1
   TcPrepParams pp{};
   pp.params = params; pp.wblob = wblob; pp.C = C; pp.Np = Np; pp.KS = KS; pp.pair = g.pair;
+  pp.pair_k = tc_pair_k(C, g.pair != 0);
   TcNetParams np{};
   np.act = act; np.wblob = wblob; np.g = g; np.C = C; np.Np = Np; np.KS = KS;
   np.buf_u4 = (int64_t)KS * 4 * g.slots;
+  np.pair_k = pp.pair_k;
   {
     const char* e = getenv("QTX_TC_PRECISE_GELU");  // dev knob: accurate exp / division in gelu (no measurable effect)
     np.precise = e ? atoi(e) : 0;
   }
-  np.out_scale = kOutScale * tc_trunc_comp(9 * ((C + 15) / 16));  // hi * hi accumulator: 9 taps x channel groups
+  np.out_scale = kOutScale * tc_trunc_comp(tc_main_accumulates(C, np.pair_k));  // hi * hi accumulator
   {
     const char* e = getenv("QTX_TC_EPI_GENERIC");
     np.epi_generic = (e && e[0] == '1') ? 1 : 0;
@@ -2047,6 +2105,7 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
   TcPrepParams pp{};
   pp.params = params; pp.wblob = wblob; pp.C = C; pp.Np = Np; pp.KS = KS; pp.pair = g.pair;
   pp.transpose = 1; pp.wnorm = wnorm; pp.bias_pad = bias_pad;
+  pp.pair_k = tc_pair_k(C, g.pair != 0);
   TcNetParams np{};
   np.act = G; np.wblob = wblob; np.g = g; np.C = C; np.Np = Np; np.KS = KS;
   np.buf_u4 = (int64_t)KS * 4 * g.slots;
@@ -2054,7 +2113,8 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
     const char* e = getenv("QTX_TC_PRECISE_GELU");
     np.precise = e ? atoi(e) : 0;
   }
-  np.out_scale = kOutScale * tc_trunc_comp(9 * ((C + 15) / 16));
+  np.pair_k = pp.pair_k;
+  np.out_scale = kOutScale * tc_trunc_comp(tc_main_accumulates(C, np.pair_k));
   np.act_z = Gz;
   WgParams wp{};
   int d = 0, nw = 0;
