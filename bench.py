@@ -457,7 +457,11 @@ def measure_E(ctx, args):
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
     flops = forward_flops_E()
     cp = (CH + 15) // 16 * 16
-    f16_flops = 3 * 2.0 * N * (2 * NB - 1) * 9 * cp * cp  # executed per forward: 3 binary16 products, padded channels
+    # executed per forward: 3 binary16 products on padded out-channels; K = 16 channels per MMA, and the half-filled
+    # last K step of C = 88 takes two taps per MMA (50 instead of 54 K steps per tap set)
+    pair_k = os.environ.get("QTX_TC_PAIRK", "1") != "0" and 1 <= CH % 16 <= 8
+    k_exec = 16 * (9 * (cp // 16 - 1) + 5) if pair_k else 9 * cp
+    f16_flops = 3 * 2.0 * N * (2 * NB - 1) * k_exec * cp
     ach = flops * nconn / (oloc_ms * 1e-3) / 1e12  # this rank's Oloc phase
     prof = _load_json("profiles/r2_ncu_resconv_tc_E.json")
     line = {
