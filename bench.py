@@ -490,7 +490,8 @@ def measure_E(ctx, args):
                     "configurations evaluated in the Oloc phase / CUDA-event duration of that phase inside the timed "
                     "steps (enumeration and reduction kernels included); peak = cuBLAS bf16 of MEASURED_PEAKS.json "
                     "(sustained figure: the kernel runs inside a seconds-long step).  float32 accuracy costs 3 binary16 "
-                    "products on channels padded 88 -> 96, so this fraction is bounded by (88/96)^2 / 3 = 0.28",
+                    "products on out-channels padded 88 -> 96 and K = 800 instead of 792 per tap set (tap-pair last K step), so this "
+                    "fraction is bounded by (88 / 96) (792 / 800) / 3 = 0.30",
             "tensor_pipe": {"f16_tflops": f16_flops * nconn / (oloc_ms * 1e-3) / 1e12, "peak": peak_tf,
                             "frac": f16_flops * nconn / (oloc_ms * 1e-3) / 1e12 / peak_tf,
                             "note": "executed binary16 tensor work (3 products, 96 channels) vs the same peak"}},
