@@ -104,6 +104,7 @@ struct TcNetParams {
   float out_scale;         // kOutScale times the expected-value correction of the truncating accumulator (tc_trunc_comp)
   int epi_generic;         // dev knob QTX_TC_EPI_GENERIC=1: the generic epilogue for every layer
   int pair_k;              // CTA-pair kernel, C % 16 in 1..8: the half-filled last K step pairs two taps per MMA
+  int keep_pad;            // dev knob QTX_TC_KEEP_PAD=1: the forward-only epilogues also process the padded channel group
   unsigned long long* dbg;  // optional [grid][16] cycle counters (QTX_TC_DEBUG=1)
   const long long* ns_dev;  // optional device-side sample count (<= g.ns): batches whose size is decided on the device
   TcLayer layer[kTcMaxLayers];
@@ -914,7 +915,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int ks = 0; ks < p.KS; ++ks) {
               mbar_wait(act_empty + as, pa ^ 1);
               const uint32_t lbar = smem_u32(act_full + as) & 0xFEFFFFFFu;
-              if (leader) mbar_expect_tx(act_full + as, 2u * act_stage_bytes);
+              // tap-pair K step: only the plane with the real channels (p2 = 0) is read by the MMAs
+              const bool half_step = p.pair_k != 0 && p.keep_pad == 0 && ks == p.KS - 1;
+              if (leader) mbar_expect_tx(act_full + as, half_step ? act_stage_bytes : 2u * act_stage_bytes);
               unsigned char* dst = act_s + (size_t)as * act_stage_bytes;
               // the map counts 8-byte elements (2 per slot); one box = half of one plane run (<= 256 elements)
 #pragma unroll
@@ -922,6 +925,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int e0 = 2 * (int)(slot0 + (int64_t)tsl[t] * g.Ps + ttis[t] * 16 * g.SB);
 #pragma unroll
                 for (int run = 0; run < 4; ++run) {
+                  if (half_step && (run & 1)) continue;
                   unsigned char* d = dst + (size_t)t * tile_bytes + (size_t)run * run_bytes;
                   tc2_tma_2d(d, &tmapA, lbar, e0, row_in + ks * 4 + run);
                   tc2_tma_2d(d + (run_bytes >> 1), &tmapA, lbar, e0 + g.TSh, row_in + ks * 4 + run);
@@ -1181,6 +1185,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           // planar residual stream in / out (conv2 layers), !IO = operand store only (conv1 layers).  Same arithmetic
           // as `run`; the generic version recomputed the 64-bit element offsets of the residual, the raw output and
           // every operand store from indices (14 integer instructions per element, at half the FP32 rate).
+          // with the tap-pair K step nothing reads the padded channel group behind C (operand plane and residual-stream
+          // plane ceil(C/8) .. Np/8 - 1): the forward-only bodies skip it
+          const int planes_live = (p.pair_k && !p.keep_pad) ? ((p.C + 7) >> 3) : planes;
           auto run_fast = [&](auto io_tag) {
             constexpr bool IO = decltype(io_tag)::value;
 #pragma unroll
@@ -1207,7 +1214,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
               for (int k = 0; k < PL; ++k) {
                 const int plane = cgp + kColGroups * k;
-                if (plane >= planes) continue;
+                if (plane >= planes_live) continue;
                 float(&a)[8] = acc[t][k];
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(Lbias + plane * 8));
                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(Lbias + plane * 8) + 1);
@@ -1256,6 +1263,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           };
           // backward-data layer: v = conv^T(g) * alpha gelu'(alpha * mul) + res; per-sample scales (see TcLayer)
+          const int planes_live_b = (p.pair_k && !p.keep_pad && !p.act_z) ? ((p.C + 7) >> 3) : planes;
           auto run_bwd = [&]() {
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
@@ -1275,7 +1283,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
                 for (int k = 0; k < PL; ++k) {
                   const int plane = cgp + kColGroups * k;
-                  if (plane >= planes) continue;
+                  if (plane >= planes_live_b) continue;  // nothing reads the padded channel group (tap-pair K step)
                   const int c0 = plane * 8, nvalid = p.C - c0;
                   const int64_t roff = raw_sample + (int64_t)c0 * N;
                   float v[8];
@@ -2003,6 +2011,8 @@ int resconv_tc_forward(int nblocks, int C, int lx, int ly, const float* params, 
   {
     const char* e = getenv("QTX_TC_EPI_GENERIC");
     np.epi_generic = (e && e[0] == '1') ? 1 : 0;
+    e = getenv("QTX_TC_KEEP_PAD");
+    np.keep_pad = (e && e[0] == '1') ? 1 : 0;
   }
   int nl = 0;
   for (int i = 0; i < nblocks; ++i) {
@@ -2114,6 +2124,10 @@ int resconv_tc_backward(int nblocks, int C, int lx, int ly, const float* params,
     np.precise = e ? atoi(e) : 0;
   }
   np.pair_k = pp.pair_k;
+  {
+    const char* e = getenv("QTX_TC_KEEP_PAD");
+    np.keep_pad = (e && e[0] == '1') ? 1 : 0;
+  }
   np.out_scale = kOutScale * tc_trunc_comp(tc_main_accumulates(C, np.pair_k));
   np.act_z = Gz;
   WgParams wp{};
