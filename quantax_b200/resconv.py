@@ -11,7 +11,7 @@ from . import _lib
 from .utils import ScaleArray
 
 # default per-launch sample caps when the state has no max_parallel (bytes of activation workspace)
-_FWD_BUDGET = 4 << 30
+_FWD_BUDGET = 12 << 30  # ~30 K configurations per tower launch at config E (the last round of a launch is partly idle)
 _BWD_BUDGET = 24 << 30
 
 
